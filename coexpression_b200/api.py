@@ -1,0 +1,246 @@
+"""Host-side handle over the batched C ABI: the table is made resident once and K permutations
+are reduced to network densities per call (the reference re-reads, re-ranks and re-marshals the
+whole table in each of its per-permutation processes, 1-make-network.py:70,100-122)."""
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import CoexParams, check
+
+STAGES = ["rank_pack", "rowstats", "gather", "corr_gemm", "count_score", "network"]
+
+
+@dataclass
+class Options:
+    """The options of 0-prepare-coex.py that change hot-path arithmetic."""
+    correlationmeasure: str = "Spearman"      # -cm
+    anticorrelation: bool = False             # -a
+    noiter: bool = False                      # -i
+    useaverage: bool = False                  # -u
+    nsp: float = 1.0                          # -s
+    pval_to_join: float = 0.1                 # -j
+    selectionthreshold: float = 0.0           # -st
+    selectionthreshold_is_j: bool = False     # -m
+    soft_separation: int = 100000             # -ss
+
+    def to_params(self, N):
+        if self.nsp < 1 and not (self.nsp <= 1.0 / N):
+            # reference 1-make-network.py:200-201 uses `random` without importing it (quirk Q8)
+            raise NameError("name 'random' is not defined")
+        thr = self.selectionthreshold
+        if self.selectionthreshold_is_j:                       # 1-make-network.py:95-96
+            thr = -math.log(self.pval_to_join, 10)
+        return CoexParams(
+            measure=0 if self.correlationmeasure == "Spearman" else 1,
+            anticorrelation=int(bool(self.anticorrelation)), noiter=int(bool(self.noiter)),
+            useaverage=int(bool(self.useaverage)),
+            use_specific_p=0 if self.nsp <= 1.0 / N else 1,    # 1-make-network.py:189-193
+            reserved=0, pval_to_join=float(self.pval_to_join), selectionthreshold=float(thr),
+            soft_separation=int(self.soft_separation))
+
+
+@dataclass
+class BatchResult:
+    perm_off: np.ndarray        # [K+1]
+    hit_rows: np.ndarray        # [H]
+    n_groups: np.ndarray        # [K]
+    group_of_hit: np.ndarray    # [H]
+    group_label: np.ndarray     # [H] hit position of each group's label (first n_groups[k] slots)
+    group_winner: np.ndarray    # [H]
+    group_density: np.ndarray   # [H]
+    hit_score: np.ndarray       # [H]
+    scores: np.ndarray | None   # [sum P^2]
+    counts: np.ndarray | None
+
+    def perm(self, k):
+        a, b = int(self.perm_off[k]), int(self.perm_off[k + 1])
+        g = int(self.n_groups[k])
+        return dict(hit_rows=self.hit_rows[a:b], group_of_hit=self.group_of_hit[a:b],
+                    label=self.group_label[a:a + g], winner=self.group_winner[a:a + g],
+                    density=self.group_density[a:a + g], hit_score=self.hit_score[a:b])
+
+    def score_matrix(self, k):
+        P = np.diff(self.perm_off)
+        off = np.concatenate([[0], np.cumsum(P * P)])
+        p = int(P[k])
+        return self.scores[off[k]:off[k + 1]].reshape(p, p)
+
+    def count_matrix(self, k):
+        P = np.diff(self.perm_off)
+        off = np.concatenate([[0], np.cumsum(P * P)])
+        p = int(P[k])
+        return self.counts[off[k]:off[k + 1]].reshape(p, p)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class CoexContext:
+    """One GPU, one resident expression table."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        if self.lib.coex_device_count() <= 0:
+            raise _lib.CoexError("no CUDA device: the coexpression hot path has no CPU fallback")
+        h = ctypes.c_void_p()
+        check(self.lib.coex_create(ctypes.byref(h), int(device)), "coex_create")
+        self.h = h
+        self.N = self.n = 0
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            self.lib.coex_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- table -------------------------------------------------------------------------------
+    def set_expression(self, X):
+        """X: float64 [N, n] numpy array (host) -- one bulk H2D copy (A3)."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        self.N, self.n = X.shape
+        check(self.lib.coex_set_expression(self.h, X.ctypes.data, self.N, self.n, 0), "coex_set_expression")
+
+    def set_expression_device(self, dev_ptr, N, n, keepalive=None):
+        """dev_ptr: device pointer to float64 [N, n] (e.g. torch tensor .data_ptr())."""
+        self.N, self.n = int(N), int(n)
+        self._keep.append(keepalive)
+        check(self.lib.coex_set_expression(self.h, ctypes.c_void_p(dev_ptr), self.N, self.n, 1),
+              "coex_set_expression")
+
+    def prepare(self):
+        check(self.lib.coex_prepare(self.h), "coex_prepare")
+
+    def ranks(self):
+        out = np.empty((self.N, self.n), dtype=np.float64)
+        check(self.lib.coex_get_ranks(self.h, out.ctypes.data), "coex_get_ranks")
+        return out
+
+    def set_features(self, chrom, start, end, names):
+        """chrom: per-row chromosome strings; names: row labels.  Strings are replaced by their
+        ranks in sorted order, which preserves every comparison the reference makes on them
+        (pandas sort on 'chromosome', coexfunctions.py:288; sorted(names), :314)."""
+        chrom = np.asarray(chrom)
+        uniq, chrom_id = np.unique(chrom, return_inverse=True)          # np.unique sorts
+        order = np.argsort(np.asarray(names), kind="stable")
+        name_rank = np.empty(len(names), dtype=np.int32)
+        name_rank[order] = np.arange(len(names), dtype=np.int32)
+        self.set_features_raw(chrom_id.astype(np.int32), np.asarray(start, dtype=np.int64),
+                              np.asarray(end, dtype=np.int64), name_rank)
+
+    def set_features_raw(self, chrom_id, start, end, name_rank):
+        chrom_id = np.ascontiguousarray(chrom_id, dtype=np.int32)
+        start = np.ascontiguousarray(start, dtype=np.int64)
+        end = np.ascontiguousarray(end, dtype=np.int64)
+        name_rank = np.ascontiguousarray(name_rank, dtype=np.int32)
+        check(self.lib.coex_set_features(self.h, chrom_id.ctypes.data, start.ctypes.data, end.ctypes.data,
+                                         name_rank.ctypes.data, len(chrom_id)), "coex_set_features")
+
+    def set_global_list(self, values):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        check(self.lib.coex_set_global_list(self.h, v.ctypes.data, v.size), "coex_set_global_list")
+
+    # ---- A1 on the resident table ----------------------------------------------------------------
+    def pairs(self, idxa, idxb, ranked):
+        idxa = np.ascontiguousarray(idxa, dtype=np.int32)
+        idxb = np.ascontiguousarray(idxb, dtype=np.int32)
+        out = np.empty(idxa.size, dtype=np.float64)
+        check(self.lib.coex_pairs(self.h, 1 if ranked else 0, idxa.ctypes.data, idxb.ctypes.data, idxa.size,
+                                  out.ctypes.data, 0), "coex_pairs")
+        return out
+
+    def allpairs_histogram(self, ranked, row0=0, row1=None, nbins=1 << 20):
+        row1 = self.N if row1 is None else row1
+        hist = np.zeros(nbins, dtype=np.uint64)
+        nan = np.zeros(1, dtype=np.uint64)
+        check(self.lib.coex_allpairs_histogram(self.h, 1 if ranked else 0, row0, row1, nbins, hist.ctypes.data,
+                                               nan.ctypes.data), "coex_allpairs_histogram")
+        return hist, int(nan[0])
+
+    # ---- A4-A12 batched -----------------------------------------------------------------------------
+    def network_batch(self, hit_sets, options: Options, want_scores=False, want_counts=False):
+        """hit_sets: list of int arrays (table rows, map-file order), one per permutation."""
+        K = len(hit_sets)
+        perm_off = np.zeros(K + 1, dtype=np.int64)
+        perm_off[1:] = np.cumsum([len(h) for h in hit_sets])
+        H = int(perm_off[-1])
+        hit_rows = (np.concatenate([np.asarray(h, dtype=np.int32) for h in hit_sets])
+                    if H else np.zeros(0, dtype=np.int32))
+        hit_rows = np.ascontiguousarray(hit_rows, dtype=np.int32)
+        Hn = max(H, 1)
+        n_groups = np.zeros(max(K, 1), dtype=np.int32)
+        group_of_hit = np.full(Hn, -1, dtype=np.int32)
+        group_label = np.full(Hn, -1, dtype=np.int32)
+        group_winner = np.full(Hn, -1, dtype=np.int32)
+        group_density = np.zeros(Hn, dtype=np.float64)
+        hit_score = np.zeros(Hn, dtype=np.float64)
+        SC = int(np.sum(np.diff(perm_off) ** 2))
+        scores = np.zeros(max(SC, 1), dtype=np.float64) if want_scores else None
+        counts = np.full(max(SC, 1), -1, dtype=np.int64) if want_counts else None
+        prm = options.to_params(self.N)
+        check(self.lib.coex_network_batch(self.h, ctypes.byref(prm), K, perm_off.ctypes.data, _ptr(hit_rows),
+                                          n_groups.ctypes.data, group_of_hit.ctypes.data, group_label.ctypes.data,
+                                          group_winner.ctypes.data, group_density.ctypes.data,
+                                          hit_score.ctypes.data, _ptr(scores), _ptr(counts), 0),
+              "coex_network_batch")
+        return BatchResult(perm_off, hit_rows, n_groups[:K], group_of_hit[:H], group_label[:H], group_winner[:H],
+                           group_density[:H], hit_score[:H], scores, counts)
+
+    def network_batch_device(self, options: Options, K, perm_off_host, ptrs):
+        """All buffers already on the device (ptrs: dict of device pointers); asynchronous on
+        the context stream apart from the final stream sync the C entry point performs."""
+        prm = options.to_params(self.N)
+        perm_off_host = np.ascontiguousarray(perm_off_host, dtype=np.int64)
+        g = lambda k: ctypes.c_void_p(ptrs[k]) if ptrs.get(k) else None
+        check(self.lib.coex_network_batch(self.h, ctypes.byref(prm), int(K), perm_off_host.ctypes.data,
+                                          g("hit_rows"), g("n_groups"), g("group_of_hit"), g("group_label"),
+                                          g("group_winner"), g("group_density"), g("hit_score"), g("scores"),
+                                          g("counts"), 1), "coex_network_batch")
+
+    # ---- introspection ------------------------------------------------------------------------------
+    def stage_ms(self):
+        out = {}
+        for i, name in enumerate(STAGES):
+            ms = ctypes.c_double()
+            ln = ctypes.c_longlong()
+            check(self.lib.coex_stage_ms(self.h, i, ctypes.byref(ms), ctypes.byref(ln)), "coex_stage_ms")
+            out[name] = (ms.value, ln.value)
+        return out
+
+    def launch_count(self):
+        return int(self.lib.coex_launch_count(self.h))
+
+    def stream_ptr(self):
+        return self.lib.coex_stream(self.h)
+
+    def sync(self):
+        check(self.lib.coex_sync(self.h), "coex_sync")
+
+    def set_gemm_mode(self, mode):
+        check(self.lib.coex_set_gemm_mode(self.h, {"tcgen05": 0, "simt": 1}.get(mode, mode)), "coex_set_gemm_mode")
+
+    def set_workspace_mb(self, mb):
+        check(self.lib.coex_set_workspace_mb(self.h, int(mb)), "coex_set_workspace_mb")
+
+    def selftest_gemm(self, m_rows):
+        bad = ctypes.c_longlong()
+        first = (ctypes.c_longlong * 4)()
+        check(self.lib.coex_selftest_gemm(self.h, int(m_rows), ctypes.byref(bad), first), "coex_selftest_gemm")
+        return int(bad.value), [int(x) for x in first]

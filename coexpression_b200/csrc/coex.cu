@@ -1,0 +1,545 @@
+// coex.cu -- the C ABI of include/coexpression_b200.h on top of the sm_100a kernels.
+// Built into coexpression_v2.so (the file name the reference loads through ctypes,
+// reference 1-make-network.py:66-67).  No CPU fallback anywhere in this file.
+#include "common.cuh"
+#include "prepare.cuh"
+#include "pairs.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+#include "count.cuh"
+#include "network.cuh"
+#include "allpairs.cuh"
+
+#include <algorithm>
+#include <mutex>
+
+namespace coex {
+thread_local std::string g_last_error;
+
+static int check_ctx(coex_ctx *c) {
+    if (!c) COEX_FAIL("null context");
+    COEX_CUDA(cudaSetDevice(c->device));
+    return 0;
+}
+
+static int prepare_impl(coex_ctx *c) {
+    if (!c->raw) COEX_FAIL("coex_prepare: call coex_set_expression first");
+    const long long N = c->N;
+    const int n = c->n;
+    if (n > 8192) COEX_FAIL("coex_prepare: more than 8192 samples per row is not supported");
+    c->n_pad = (int)round_up(n, 128);
+    c->N_pad = round_up(N, 256);
+    stage_reset(c);
+    COEX_TRY(c->raw_sum.reserve(N)); COEX_TRY(c->raw_mean.reserve(N)); COEX_TRY(c->raw_xx.reserve(N));
+    COEX_TRY(c->rawsum_pos.reserve(N));
+    COEX_TRY(c->rank2.reserve((size_t)N * n));
+    COEX_TRY(c->u_hi.reserve((size_t)c->N_pad * c->n_pad));
+    COEX_TRY(c->u_lo.reserve((size_t)c->N_pad * c->n_pad));
+    COEX_TRY(c->suu.reserve(c->N_pad)); COEX_TRY(c->sx.reserve(c->N_pad));
+    // padding rows must be exact zeros (they enter the GEMM as B rows)
+    const size_t tail = (size_t)(c->N_pad - N) * c->n_pad;
+    if (tail) {
+        COEX_CUDA(cudaMemsetAsync(c->u_hi.p + (size_t)N * c->n_pad, 0, tail, c->stream));
+        COEX_CUDA(cudaMemsetAsync(c->u_lo.p + (size_t)N * c->n_pad, 0, tail, c->stream));
+    }
+    COEX_CUDA(cudaMemsetAsync(c->suu.p, 0, c->N_pad * sizeof(long long), c->stream));
+    COEX_CUDA(cudaMemsetAsync(c->sx.p, 0, c->N_pad * sizeof(double), c->stream));
+
+    COEX_TRY(stage_begin(c, ST_RANK));
+    const int P2 = next_pow2(n);
+    const size_t smem = (size_t)P2 * 10 + (size_t)c->n_pad * 2;
+    COEX_CUDA(cudaFuncSetAttribute(rank_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rank_pack_kernel<<<(unsigned)N, kRankThreads, smem, c->stream>>>(
+        c->raw, N, n, c->n_pad, P2, c->rank2.p, c->u_hi.p, c->u_lo.p, c->suu.p, c->sx.p);
+    COEX_CUDA(cudaGetLastError());
+    COEX_TRY(stage_end(c, 1));
+
+    COEX_TRY(stage_begin(c, ST_ROWSTATS));
+    rowstats_kernel<<<(unsigned)((N + kStatRows - 1) / kStatRows), 256, 0, c->stream>>>(
+        c->raw, N, n, c->raw_sum.p, c->raw_mean.p, c->raw_xx.p, c->rawsum_pos.p);
+    COEX_CUDA(cudaGetLastError());
+    COEX_TRY(stage_end(c, 1));
+    COEX_TRY(tc_invalidate(c));
+    c->prepared = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// correlation strip: S[q, c] for queries q0..q0+nq of d_hits against the whole table
+// ------------------------------------------------------------------------------------------
+static int run_strip_gemm(coex_ctx *c, const int *d_rows, long long nq, long long nq_pad) {
+    COEX_TRY(stage_begin(c, ST_GATHER));
+    {
+        const long long total = nq_pad * (c->n_pad >> 4);
+        const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)c->sm_count * 16);
+        gather_rows_kernel<<<blocks, 256, 0, c->stream>>>(c->u_hi.p, c->u_lo.p, c->n_pad, d_rows, nq, nq_pad,
+                                                         c->a_hi.p, c->a_lo.p);
+        COEX_CUDA(cudaGetLastError());
+    }
+    COEX_TRY(stage_end(c, 1));
+    COEX_TRY(stage_begin(c, ST_GEMM));
+    if (c->gemm_mode == 0) {
+        COEX_TRY(tc_gemm_i8(c, nq_pad));
+    } else {
+        dim3 grid((unsigned)(c->N_pad / kSimtTile), (unsigned)(nq_pad / kSimtTile));
+        gemm_i8_simt_kernel<<<grid, 256, 0, c->stream>>>(c->a_hi.p, c->a_lo.p, c->u_hi.p, c->u_lo.p, c->n_pad,
+                                                         c->strip.p, c->N_pad);
+        COEX_CUDA(cudaGetLastError());
+    }
+    COEX_TRY(stage_end(c, 1));
+    return 0;
+}
+
+static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const long long *perm_off,
+                              const int *hit_rows, int *n_groups, int *group_of_hit, int *group_label,
+                              int *group_winner, double *group_density, double *hit_score, double *scores,
+                              long long *counts, int on_device) {
+    if (!c->prepared) COEX_FAIL("coex_network_batch: call coex_prepare first");
+    if (!c->have_features) COEX_FAIL("coex_network_batch: call coex_set_features first");
+    if (c->glist_len <= 0) COEX_FAIL("coex_network_batch: call coex_set_global_list first");
+    if (K <= 0) return 0;
+    if (perm_off[0] != 0) COEX_FAIL("perm_off[0] must be 0");
+    const long long H = perm_off[K];
+    std::vector<long long> sc_off(K + 1, 0);
+    int Pmax = 0;
+    for (int k = 0; k < K; ++k) {
+        const long long P = perm_off[k + 1] - perm_off[k];
+        if (P < 0 || P > c->N) COEX_FAIL("permutation with an invalid number of hits");
+        if (P > 8192) COEX_FAIL("more than 8192 hit regions in one permutation is not supported");
+        Pmax = std::max<int>(Pmax, (int)P);
+        sc_off[k + 1] = sc_off[k] + P * P;
+    }
+    const long long SC = sc_off[K];
+    if (prm->measure == 0 && prm->use_specific_p && c->n > 1860)
+        COEX_FAIL("Spearman tensor path supports up to 1860 samples (int32 dot products)");
+    stage_reset(c);
+    cudaStream_t st = c->stream;
+
+    // ---- buffers ----------------------------------------------------------------------------
+    COEX_TRY(c->d_perm_off.reserve(K + 1)); COEX_TRY(c->d_sc_off.reserve(K + 1));
+    COEX_CUDA(cudaMemcpyAsync(c->d_perm_off.p, perm_off, (K + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    COEX_CUDA(cudaMemcpyAsync(c->d_sc_off.p, sc_off.data(), (K + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    // sc_off is a stack-lifetime vector: the copy above must finish before we return
+    const size_t Hs_alloc = (size_t)std::max<long long>(H, 1);
+    const int *d_hits = hit_rows;
+    int *d_ng = n_groups, *d_grp = group_of_hit, *d_lab = group_label, *d_win = group_winner;
+    double *d_dens = group_density, *d_aps = hit_score, *d_sc = scores;
+    long long *d_cn = counts;
+    if (!on_device) {
+        COEX_TRY(c->d_hits.reserve(Hs_alloc));
+        COEX_CUDA(cudaMemcpyAsync(c->d_hits.p, hit_rows, H * sizeof(int), cudaMemcpyHostToDevice, st));
+        d_hits = c->d_hits.p;
+        COEX_TRY(c->d_ngroups.reserve(K)); COEX_TRY(c->d_grp.reserve(Hs_alloc)); COEX_TRY(c->d_label.reserve(Hs_alloc));
+        COEX_TRY(c->d_win.reserve(Hs_alloc)); COEX_TRY(c->d_dens.reserve(Hs_alloc)); COEX_TRY(c->d_aps.reserve(Hs_alloc));
+        d_ng = c->d_ngroups.p; d_grp = c->d_grp.p; d_lab = c->d_label.p; d_win = c->d_win.p;
+        d_dens = c->d_dens.p; d_aps = c->d_aps.p;
+        if (counts) { COEX_TRY(c->d_counts.reserve(std::max<long long>(SC, 1))); d_cn = c->d_counts.p; }
+        d_sc = nullptr;
+    }
+    if (!d_sc) { COEX_TRY(c->d_scores.reserve(std::max<long long>(SC, 1))); d_sc = c->d_scores.p; }
+    COEX_TRY(c->w_root.reserve(Hs_alloc)); COEX_TRY(c->w_pos.reserve(Hs_alloc)); COEX_TRY(c->w_s1.reserve(Hs_alloc));
+    COEX_TRY(c->w_d0.reserve(Hs_alloc)); COEX_TRY(c->w_w.reserve(Hs_alloc)); COEX_TRY(c->w_best.reserve(Hs_alloc));
+    COEX_TRY(c->w_cand.reserve(Hs_alloc));
+    // outputs of unused slots are defined
+    COEX_CUDA(cudaMemsetAsync(d_grp, 0xff, H * sizeof(int), st));
+    COEX_CUDA(cudaMemsetAsync(d_lab, 0xff, H * sizeof(int), st));
+    COEX_CUDA(cudaMemsetAsync(d_win, 0xff, H * sizeof(int), st));
+    COEX_CUDA(cudaMemsetAsync(d_dens, 0, H * sizeof(double), st));
+    COEX_CUDA(cudaMemsetAsync(d_aps, 0, H * sizeof(double), st));
+
+    const int T2max = next_pow2(std::max(Pmax, 2));
+    if (H > 0 && Pmax >= 2) {
+        if (prm->use_specific_p) {
+            // ---- node-specific null: strips of query rows x all table columns ---------------
+            const long long ld = (prm->measure == 0) ? c->N_pad : c->N;
+            const long long elt = (prm->measure == 0) ? 4 : 8;
+            long long Hs = (c->strip_mb << 20) / (ld * elt);
+            Hs = std::max<long long>(256, Hs / 256 * 256);
+            Hs = std::min<long long>(Hs, round_up(H, 256));
+            if (prm->measure == 0) {
+                COEX_TRY(c->strip.reserve((size_t)Hs * ld));
+                COEX_TRY(c->a_hi.reserve((size_t)Hs * c->n_pad)); COEX_TRY(c->a_lo.reserve((size_t)Hs * c->n_pad));
+            } else {
+                COEX_TRY(c->strip_f64.reserve((size_t)Hs * ld));
+                StatArgs sa{c->d_perm_off.p, c->d_sc_off.p, d_hits, c->rank2.p, c->n, c->sx.p, c->rawsum_pos.p, d_sc};
+                COEX_TRY(stage_begin(c, ST_COUNT));
+                dim3 g((unsigned)std::min<long long>(((long long)Pmax * Pmax * 32 + 255) / 256, 4096), (unsigned)K);
+                stat_rank_kernel<<<g, 256, 0, st>>>(sa);
+                COEX_CUDA(cudaGetLastError());
+                COEX_TRY(stage_end(c, 1));
+            }
+            const size_t smem = (size_t)T2max * 16;
+            COEX_CUDA(cudaFuncSetAttribute(count_score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            COEX_CUDA(cudaFuncSetAttribute(count_score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            for (long long q0 = 0; q0 < H; q0 += Hs) {
+                const long long nq = std::min(Hs, H - q0);
+                CountArgs ca{};
+                ca.ld = ld; ca.q0 = q0; ca.nq = nq; ca.perm_off = c->d_perm_off.p; ca.sc_off = c->d_sc_off.p;
+                ca.K = K; ca.hit_rows = d_hits; ca.sx = c->sx.p; ca.rawsum_pos = c->rawsum_pos.p; ca.N = c->N;
+                ca.anticor = prm->anticorrelation; ca.scores = d_sc; ca.counts = d_cn; ca.T2max = T2max;
+                if (prm->measure == 0) {
+                    COEX_TRY(run_strip_gemm(c, d_hits + q0, nq, round_up(nq, 256)));
+                    ca.strip = c->strip.p;
+                    COEX_TRY(stage_begin(c, ST_COUNT));
+                    count_score_kernel<false><<<(unsigned)nq, kCountThreads, smem, st>>>(ca);
+                } else {
+                    COEX_TRY(stage_begin(c, ST_GEMM));
+                    dim3 g((unsigned)((c->N + 63) / 64), (unsigned)((nq + 15) / 16));
+                    pearson_strip_kernel<<<g, 256, 0, st>>>(c->raw, c->n, c->N, d_hits + q0, nq, c->raw_sum.p,
+                                                            c->raw_mean.p, c->raw_xx.p, c->strip_f64.p, ld);
+                    COEX_CUDA(cudaGetLastError());
+                    COEX_TRY(stage_end(c, 1));
+                    ca.strip_f64 = c->strip_f64.p;
+                    COEX_TRY(stage_begin(c, ST_COUNT));
+                    count_score_kernel<true><<<(unsigned)nq, kCountThreads, smem, st>>>(ca);
+                }
+                COEX_CUDA(cudaGetLastError());
+                COEX_TRY(stage_end(c, 1));
+            }
+        } else {
+            // ---- nsp == 0: whole-distribution p from the global list -------------------------
+            StatArgs sa{c->d_perm_off.p, c->d_sc_off.p, d_hits, c->rank2.p, c->n, c->sx.p, c->rawsum_pos.p, d_sc};
+            COEX_TRY(stage_begin(c, ST_COUNT));
+            dim3 g((unsigned)std::min<long long>(((long long)Pmax * Pmax * 32 + 255) / 256, 4096), (unsigned)K);
+            stat_rank_kernel<<<g, 256, 0, st>>>(sa);
+            COEX_CUDA(cudaGetLastError());
+            dim3 g2((unsigned)std::min<long long>(((long long)Pmax * Pmax + 255) / 256, 4096), (unsigned)K);
+            global_from_stat_kernel<<<g2, 256, 0, st>>>(c->d_perm_off.p, c->d_sc_off.p, c->glist.p, c->glist_len,
+                                                       prm->anticorrelation, d_sc, d_cn);
+            COEX_CUDA(cudaGetLastError());
+            COEX_TRY(stage_end(c, 2));
+        }
+    }
+    // ---- K4: groups, winners, densities -----------------------------------------------------
+    {
+        NetArgs na{};
+        na.K = K; na.perm_off = c->d_perm_off.p; na.sc_off = c->d_sc_off.p; na.hit_rows = d_hits; na.scores = d_sc;
+        na.N = c->N; na.n = c->n; na.raw = c->raw; na.raw_sum = c->raw_sum.p; na.raw_mean = c->raw_mean.p;
+        na.raw_xx = c->raw_xx.p; na.rank2 = c->rank2.p; na.sx = c->sx.p; na.rawsum_pos = c->rawsum_pos.p;
+        na.chrom_id = c->chrom_id.p; na.name_rank = c->name_rank.p; na.feat_start = c->feat_start.p;
+        na.feat_end = c->feat_end.p; na.glist = c->glist.p; na.glist_len = c->glist_len;
+        na.measure = prm->measure; na.anticor = prm->anticorrelation; na.noiter = prm->noiter;
+        na.useaverage = prm->useaverage; na.pvtj = prm->pval_to_join; na.thr = prm->selectionthreshold;
+        na.softsep = prm->soft_separation;
+        na.n_groups = d_ng; na.group_of_hit = d_grp; na.group_label = d_lab; na.group_winner = d_win;
+        na.group_density = d_dens; na.hit_score = d_aps;
+        na.w_root = c->w_root.p; na.w_pos = c->w_pos.p; na.w_s1 = c->w_s1.p; na.w_d0 = c->w_d0.p; na.w_w = c->w_w.p;
+        na.w_best = c->w_best.p; na.w_cand = c->w_cand.p;
+        na.P2max = T2max;
+        const size_t smem = (size_t)T2max * 24;
+        COEX_CUDA(cudaFuncSetAttribute(network_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        COEX_TRY(stage_begin(c, ST_NETWORK));
+        network_kernel<<<K, kNetThreads, smem, st>>>(na);
+        COEX_CUDA(cudaGetLastError());
+        COEX_TRY(stage_end(c, 1));
+    }
+    if (!on_device) {
+        COEX_CUDA(cudaMemcpyAsync(n_groups, d_ng, K * sizeof(int), cudaMemcpyDeviceToHost, st));
+        COEX_CUDA(cudaMemcpyAsync(group_of_hit, d_grp, H * sizeof(int), cudaMemcpyDeviceToHost, st));
+        COEX_CUDA(cudaMemcpyAsync(group_label, d_lab, H * sizeof(int), cudaMemcpyDeviceToHost, st));
+        COEX_CUDA(cudaMemcpyAsync(group_winner, d_win, H * sizeof(int), cudaMemcpyDeviceToHost, st));
+        COEX_CUDA(cudaMemcpyAsync(group_density, d_dens, H * sizeof(double), cudaMemcpyDeviceToHost, st));
+        COEX_CUDA(cudaMemcpyAsync(hit_score, d_aps, H * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (scores) COEX_CUDA(cudaMemcpyAsync(scores, d_sc, SC * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (counts) COEX_CUDA(cudaMemcpyAsync(counts, d_cn, SC * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    }
+    // perm_off / sc_off staging copies read host memory that dies with this frame
+    COEX_CUDA(cudaStreamSynchronize(st));
+    if (prm->measure == 0 && prm->use_specific_p && c->gemm_mode == 0) COEX_TRY(tc_check_error(c));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// on-device cross-check of the tcgen05 GEMM against the dp4a GEMM on the resident table
+// ------------------------------------------------------------------------------------------
+__global__ void compare_strips_kernel(const int *a, const int *b, long long rows, long long cols, long long ld,
+                                      unsigned long long *nbad, long long *first) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < rows * cols;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long r = t / cols, col = t - r * cols;
+        if (a[r * ld + col] != b[r * ld + col]) {
+            if (atomicAdd(nbad, 1ULL) == 0) { first[0] = r; first[1] = col; first[2] = a[r * ld + col]; first[3] = b[r * ld + col]; }
+        }
+    }
+}
+
+static int selftest_gemm_impl(coex_ctx *c, long long m_rows, long long *mismatches, long long *first4) {
+    if (!c->prepared) COEX_FAIL("coex_selftest_gemm: call coex_prepare first");
+    m_rows = std::min(round_up(std::max<long long>(m_rows, 1), 256), c->N_pad);
+    const long long nq = std::min(m_rows, c->N);
+    cudaStream_t st = c->stream;
+    COEX_TRY(c->d_hits.reserve(m_rows));
+    COEX_TRY(c->strip.reserve((size_t)m_rows * c->N_pad));
+    COEX_TRY(c->a_hi.reserve((size_t)m_rows * c->n_pad)); COEX_TRY(c->a_lo.reserve((size_t)m_rows * c->n_pad));
+    DevBuf<int> ref;
+    DevBuf<unsigned long long> bad;
+    DevBuf<long long> first;
+    COEX_TRY(ref.reserve((size_t)m_rows * c->N_pad)); COEX_TRY(bad.reserve(1)); COEX_TRY(first.reserve(4));
+    COEX_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(unsigned long long), st));
+    COEX_CUDA(cudaMemsetAsync(first.p, 0xff, 4 * sizeof(long long), st));
+    COEX_CUDA(cudaMemsetAsync(c->strip.p, 0x5a, (size_t)m_rows * c->N_pad * sizeof(int), st));
+    iota_rows_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(c->d_hits.p, 0, nq);
+    const long long total = m_rows * (c->n_pad >> 4);
+    gather_rows_kernel<<<(int)std::min<long long>((total + 255) / 256, 4096), 256, 0, st>>>(
+        c->u_hi.p, c->u_lo.p, c->n_pad, c->d_hits.p, nq, m_rows, c->a_hi.p, c->a_lo.p);
+    COEX_CUDA(cudaGetLastError());
+    COEX_TRY(tc_gemm_i8(c, m_rows));
+    dim3 grid((unsigned)(c->N_pad / kSimtTile), (unsigned)(m_rows / kSimtTile));
+    gemm_i8_simt_kernel<<<grid, 256, 0, st>>>(c->a_hi.p, c->a_lo.p, c->u_hi.p, c->u_lo.p, c->n_pad, ref.p, c->N_pad);
+    COEX_CUDA(cudaGetLastError());
+    compare_strips_kernel<<<1024, 256, 0, st>>>(c->strip.p, ref.p, m_rows, c->N_pad, c->N_pad, bad.p, first.p);
+    COEX_CUDA(cudaGetLastError());
+    unsigned long long hb = 0;
+    COEX_CUDA(cudaMemcpyAsync(&hb, bad.p, sizeof hb, cudaMemcpyDeviceToHost, st));
+    COEX_CUDA(cudaMemcpyAsync(first4, first.p, 4 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    COEX_CUDA(cudaStreamSynchronize(st));
+    *mismatches = (long long)hb;
+    ref.release(); bad.release(); first.release();
+    c->launches += 5;
+    return tc_check_error(c);
+}
+
+}  // namespace coex
+
+using namespace coex;
+
+// ============================================================================================
+// C ABI
+// ============================================================================================
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char *coex_last_error(void) { return g_last_error.c_str(); }
+int coex_abi_version(void) { return 1; }
+
+int coex_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int coex_create(coex_ctx **out, int device) {
+    if (!out) COEX_FAIL("coex_create: null output pointer");
+    *out = nullptr;
+    int ndev = 0;
+    COEX_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) COEX_FAIL("coex_create: no such CUDA device (there is no CPU fallback)");
+    COEX_CUDA(cudaSetDevice(device));
+    coex_ctx *c = new coex_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    COEX_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    COEX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    *out = c;
+    return 0;
+}
+
+int coex_destroy(coex_ctx *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    stage_reset(c);
+    tc_destroy(c);
+    c->raw_own.release(); c->raw_sum.release(); c->raw_mean.release(); c->raw_xx.release(); c->rawsum_pos.release();
+    c->rank2.release(); c->u_hi.release(); c->u_lo.release(); c->suu.release(); c->sx.release();
+    c->z_hi.release(); c->z_lo.release();
+    c->chrom_id.release(); c->name_rank.release(); c->feat_start.release(); c->feat_end.release(); c->glist.release();
+    c->a_hi.release(); c->a_lo.release(); c->strip.release(); c->strip_f64.release();
+    c->d_perm_off.release(); c->d_sc_off.release(); c->d_hits.release(); c->d_ngroups.release(); c->d_grp.release();
+    c->d_label.release(); c->d_win.release(); c->w_root.release(); c->w_pos.release(); c->d_dens.release();
+    c->d_aps.release(); c->d_scores.release(); c->w_s1.release(); c->w_d0.release(); c->w_w.release();
+    c->d_counts.release(); c->w_best.release(); c->w_cand.release(); c->p_idxa.release(); c->p_idxb.release();
+    c->p_out.release();
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int coex_sync(coex_ctx *c) {
+    COEX_TRY(check_ctx(c));
+    COEX_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+void *coex_stream(coex_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int coex_set_expression(coex_ctx *c, const double *data, long long N, int n, int on_device) {
+    COEX_TRY(check_ctx(c));
+    if (!data || N <= 0 || n <= 0) COEX_FAIL("coex_set_expression: empty table");
+    if (N > 2000000000LL) COEX_FAIL("coex_set_expression: too many rows");
+    c->prepared = false;
+    c->N = N; c->n = n;
+    if (on_device) {
+        c->raw = data;
+    } else {
+        COEX_TRY(c->raw_own.reserve((size_t)N * n));
+        COEX_CUDA(cudaMemcpyAsync(c->raw_own.p, data, (size_t)N * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        COEX_CUDA(cudaStreamSynchronize(c->stream));
+        c->raw = c->raw_own.p;
+    }
+    return 0;
+}
+
+int coex_prepare(coex_ctx *c) {
+    COEX_TRY(check_ctx(c));
+    return prepare_impl(c);
+}
+
+int coex_get_ranks(coex_ctx *c, double *out) {
+    COEX_TRY(check_ctx(c));
+    if (!c->prepared) COEX_FAIL("coex_get_ranks: call coex_prepare first");
+    std::vector<uint16_t> h((size_t)c->N * c->n);
+    COEX_CUDA(cudaMemcpyAsync(h.data(), c->rank2.p, h.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
+    COEX_CUDA(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < h.size(); ++i) out[i] = 0.5 * (double)h[i];
+    return 0;
+}
+
+int coex_set_features(coex_ctx *c, const int *chrom_id, const long long *start, const long long *end,
+                      const int *name_rank, long long N) {
+    COEX_TRY(check_ctx(c));
+    if (N != c->N) COEX_FAIL("coex_set_features: N differs from the expression table");
+    for (long long i = 0; i < N; ++i)
+        if (start[i] < 0 || start[i] >= (1LL << 39) || end[i] < 0 || end[i] >= (1LL << 39) || chrom_id[i] < 0 ||
+            chrom_id[i] >= (1 << 20))
+            COEX_FAIL("coex_set_features: coordinate out of range");
+    COEX_TRY(c->chrom_id.reserve(N)); COEX_TRY(c->name_rank.reserve(N));
+    COEX_TRY(c->feat_start.reserve(N)); COEX_TRY(c->feat_end.reserve(N));
+    COEX_CUDA(cudaMemcpyAsync(c->chrom_id.p, chrom_id, N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    COEX_CUDA(cudaMemcpyAsync(c->name_rank.p, name_rank, N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    COEX_CUDA(cudaMemcpyAsync(c->feat_start.p, start, N * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    COEX_CUDA(cudaMemcpyAsync(c->feat_end.p, end, N * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    COEX_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_features = true;
+    return 0;
+}
+
+int coex_set_global_list(coex_ctx *c, const double *v, long long len) {
+    COEX_TRY(check_ctx(c));
+    if (len <= 0) COEX_FAIL("coex_set_global_list: empty list");
+    for (long long i = 1; i < len; ++i)
+        if (v[i] < v[i - 1]) COEX_FAIL("coex_set_global_list: list is not ascending");
+    COEX_TRY(c->glist.reserve(len));
+    COEX_CUDA(cudaMemcpyAsync(c->glist.p, v, len * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    COEX_CUDA(cudaStreamSynchronize(c->stream));
+    c->glist_len = len;
+    return 0;
+}
+
+int coex_pairs(coex_ctx *c, int which, const int *idxa, const int *idxb, long long npairs, double *out,
+               int on_device) {
+    COEX_TRY(check_ctx(c));
+    if (!c->prepared) COEX_FAIL("coex_pairs: call coex_prepare first");
+    if (npairs <= 0) return 0;
+    const int *da = idxa, *db = idxb;
+    double *dout = out;
+    if (!on_device) {
+        COEX_TRY(c->p_idxa.reserve(npairs)); COEX_TRY(c->p_idxb.reserve(npairs)); COEX_TRY(c->p_out.reserve(npairs));
+        COEX_CUDA(cudaMemcpyAsync(c->p_idxa.p, idxa, npairs * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        COEX_CUDA(cudaMemcpyAsync(c->p_idxb.p, idxb, npairs * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        da = c->p_idxa.p; db = c->p_idxb.p; dout = c->p_out.p;
+    }
+    if (which == 1) {
+        const long long blocks = (npairs * 32 + 255) / 256;
+        pairs_rank_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(c->rank2.p, c->n, da, db, npairs, c->sx.p, dout);
+    } else {
+        const long long blocks = (npairs + kPairsPerBlock - 1) / kPairsPerBlock;
+        pairs_exact_kernel<<<(unsigned)blocks, kPairsPerBlock, 0, c->stream>>>(c->raw, c->n, da, db, npairs, c->raw_sum.p,
+                                                                              c->raw_mean.p, c->raw_xx.p, dout);
+    }
+    COEX_CUDA(cudaGetLastError());
+    c->launches += 1;
+    if (!on_device) {
+        COEX_CUDA(cudaMemcpyAsync(out, dout, npairs * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        COEX_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+int coex_allpairs_histogram(coex_ctx *c, int which, long long row0, long long row1, int nbins,
+                            unsigned long long *hist, unsigned long long *nan_count) {
+    COEX_TRY(check_ctx(c));
+    if (!c->prepared) COEX_FAIL("coex_allpairs_histogram: call coex_prepare first");
+    return allpairs_histogram_impl(c, which, row0, row1, nbins, hist, nan_count);
+}
+
+int coex_network_batch(coex_ctx *c, const coex_params *prm, int K, const long long *perm_off, const int *hit_rows,
+                       int *n_groups, int *group_of_hit, int *group_label, int *group_winner, double *group_density,
+                       double *hit_score, double *scores, long long *counts, int on_device) {
+    COEX_TRY(check_ctx(c));
+    if (!prm || !perm_off || (!hit_rows && perm_off[K] > 0)) COEX_FAIL("coex_network_batch: null argument");
+    return network_batch_impl(c, prm, K, perm_off, hit_rows, n_groups, group_of_hit, group_label, group_winner,
+                              group_density, hit_score, scores, counts, on_device);
+}
+
+long long coex_launch_count(coex_ctx *c) { return c ? c->launches : 0; }
+
+int coex_stage_ms(coex_ctx *c, int stage, double *ms, long long *launches) {
+    COEX_TRY(check_ctx(c));
+    if (stage < 0 || stage >= kNumStages) COEX_FAIL("coex_stage_ms: bad stage");
+    COEX_TRY(stage_collect(c));
+    if (ms) *ms = c->stage_ms[stage];
+    if (launches) *launches = c->stage_launches[stage];
+    return 0;
+}
+
+int coex_selftest_gemm(coex_ctx *c, long long m_rows, long long *mismatches, long long *first4) {
+    COEX_TRY(check_ctx(c));
+    if (!mismatches || !first4) COEX_FAIL("coex_selftest_gemm: null output");
+    return selftest_gemm_impl(c, m_rows, mismatches, first4);
+}
+
+int coex_set_gemm_mode(coex_ctx *c, int mode) {
+    if (!c) COEX_FAIL("null context");
+    if (mode != 0 && mode != 1) COEX_FAIL("coex_set_gemm_mode: 0 = tcgen05, 1 = SIMT dp4a");
+    c->gemm_mode = mode;
+    return 0;
+}
+
+int coex_set_workspace_mb(coex_ctx *c, long long strip_mb) {
+    if (!c) COEX_FAIL("null context");
+    if (strip_mb < 16) COEX_FAIL("coex_set_workspace_mb: at least 16 MB");
+    c->strip_mb = strip_mb;
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// Legacy drop-in (reference coexpression_v2.c:22-23).  Host pointers in, results written on
+// return.  The symbol has no error channel, so any CUDA failure aborts loudly.
+// --------------------------------------------------------------------------------------------
+static void legacy_die(const char *what) {
+    fprintf(stderr, "coexpression_v2.so (B200): getPearson failed: %s: %s\n", what, coex_last_error());
+    abort();
+}
+
+void getPearson(double *dataAll, double *resultAll, int *idxa_all, int *idxb_all, int nPromPairs, int n) {
+    if (nPromPairs <= 0) return;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    long long rows = 0;
+    for (int x = 0; x < nPromPairs; ++x) {
+        if (idxa_all[x] < 0 || idxb_all[x] < 0) { g_last_error = "negative row index"; legacy_die("arguments"); }
+        rows = std::max<long long>(rows, std::max(idxa_all[x], idxb_all[x]) + 1LL);
+    }
+    coex_ctx *c = nullptr;
+    if (coex_create(&c, 0)) legacy_die("no CUDA device (this library has no CPU path)");
+    auto run = [&]() -> int {
+        COEX_TRY(c->raw_own.reserve((size_t)rows * n));
+        COEX_CUDA(cudaMemcpyAsync(c->raw_own.p, dataAll, (size_t)rows * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        c->raw = c->raw_own.p; c->N = rows; c->n = n;
+        COEX_TRY(c->raw_sum.reserve(rows)); COEX_TRY(c->raw_mean.reserve(rows)); COEX_TRY(c->raw_xx.reserve(rows));
+        rowstats_kernel<<<(unsigned)((rows + kStatRows - 1) / kStatRows), 256, 0, c->stream>>>(
+            c->raw, rows, n, c->raw_sum.p, c->raw_mean.p, c->raw_xx.p, nullptr);
+        COEX_CUDA(cudaGetLastError());
+        c->prepared = true;               // only the raw statistics are needed by which == 0
+        COEX_TRY(coex_pairs(c, 0, idxa_all, idxb_all, nPromPairs, resultAll, 0));
+        return 0;
+    };
+    const int status = run();
+    if (status) { coex_destroy(c); legacy_die("device computation"); }
+    coex_destroy(c);
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,188 @@
+// common.cuh -- context, error handling and small device helpers shared by every kernel file.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/coexpression_b200.h"
+
+namespace coex {
+
+// ------------------------------------------------------------------------------------------
+// errors: thread-local message, int status codes on the batched API
+// ------------------------------------------------------------------------------------------
+extern thread_local std::string g_last_error;
+
+inline int fail(const char *file, int line, const std::string &msg) {
+    char buf[64];
+    snprintf(buf, sizeof buf, " (%s:%d)", file, line);
+    g_last_error = msg + buf;
+    return 1;
+}
+
+#define COEX_FAIL(msg) return ::coex::fail(__FILE__, __LINE__, (msg))
+#define COEX_CUDA(expr)                                                                         \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return ::coex::fail(__FILE__, __LINE__,                                             \
+                                std::string(#expr " -> ") + cudaGetErrorString(_e));            \
+    } while (0)
+#define COEX_TRY(expr)                                                                          \
+    do {                                                                                        \
+        int _s = (expr);                                                                        \
+        if (_s) return _s;                                                                      \
+    } while (0)
+
+constexpr int kNumStages = 6;
+enum Stage { ST_RANK = 0, ST_ROWSTATS = 1, ST_GATHER = 2, ST_GEMM = 3, ST_COUNT = 4, ST_NETWORK = 5 };
+
+struct StageSpan {
+    int stage;
+    cudaEvent_t a, b;
+};
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;   // elements
+    int reserve(size_t n) {
+        if (n <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e != cudaSuccess)
+            return fail(__FILE__, __LINE__, std::string("cudaMalloc of ") + std::to_string(n * sizeof(T)) +
+                                                " bytes -> " + cudaGetErrorString(e));
+        cap = n;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace coex
+
+// The opaque handle of include/coexpression_b200.h
+struct coex_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+
+    // ---- resident table -----------------------------------------------------------------
+    long long N = 0;       // rows
+    int n = 0;             // samples
+    int n_pad = 0;         // samples padded to a multiple of 128 (one SW128 TMA chunk of int8)
+    long long N_pad = 0;   // rows padded to a multiple of 256 (GEMM tile)
+    const double *raw = nullptr;  // [N, n] device
+    coex::DevBuf<double> raw_own;
+    bool prepared = false;
+
+    // in-order row statistics of the raw table (reference coexpression_v2.c:74-110 per row)
+    coex::DevBuf<double> raw_sum, raw_mean, raw_xx;
+    coex::DevBuf<unsigned char> rawsum_pos;   // sum(row) > 0 (coexfunctions.py:389)
+
+    // rank transform: 2*rank (u16), u = 2*rank-(n+1) as two int8 digits, sum u^2, sqrt(sum/4)
+    coex::DevBuf<uint16_t> rank2;             // [N, n]
+    coex::DevBuf<int8_t> u_hi, u_lo;          // [N_pad, n_pad] each, K-major
+    coex::DevBuf<long long> suu;              // [N_pad]
+    coex::DevBuf<double> sx;                  // [N_pad]  sqrt(0.25*suu); 0 for padding
+
+    // Pearson packing (split-precision limbs of the centred, normalised rows)
+    coex::DevBuf<uint16_t> z_hi, z_lo;        // [N_pad, n_pad2] fp16 limbs, K-major
+    int n_pad2 = 0;
+
+    // ---- join_nearby inputs -------------------------------------------------------------
+    coex::DevBuf<int> chrom_id, name_rank;
+    coex::DevBuf<long long> feat_start, feat_end;
+    bool have_features = false;
+    coex::DevBuf<double> glist;
+    long long glist_len = 0;
+
+    // ---- workspaces -----------------------------------------------------------------------
+    coex::DevBuf<int8_t> a_hi, a_lo;          // gathered query rows [Hs, n_pad]
+    coex::DevBuf<int> strip;                  // S strip [Hs, N_pad] int32
+    coex::DevBuf<double> strip_f64;           // Pearson null strip [Hs, N]
+    coex::DevBuf<long long> d_perm_off, d_sc_off;
+    coex::DevBuf<int> d_hits, d_ngroups, d_grp, d_label, d_win, w_root, w_pos;
+    coex::DevBuf<double> d_dens, d_aps, d_scores, w_s1, w_d0, w_w;
+    coex::DevBuf<long long> d_counts;
+    coex::DevBuf<unsigned long long> w_best, w_cand;
+    coex::DevBuf<int> p_idxa, p_idxb;         // coex_pairs staging
+    coex::DevBuf<double> p_out;
+    long long strip_mb = 1024;
+    int gemm_mode = 0;
+
+    // ---- bookkeeping ------------------------------------------------------------------------
+    long long launches = 0;
+    std::vector<coex::StageSpan> spans;
+    double stage_ms[coex::kNumStages] = {0};
+    long long stage_launches[coex::kNumStages] = {0};
+    void *tc = nullptr;                       // tensor-core GEMM state (tensor maps), gemm_tc.cuh
+};
+
+namespace coex {
+
+// RAII-free helpers to bracket a stage with events on the context's stream
+inline int stage_begin(coex_ctx *c, int stage) {
+    StageSpan s;
+    s.stage = stage;
+    COEX_CUDA(cudaEventCreate(&s.a));
+    COEX_CUDA(cudaEventCreate(&s.b));
+    COEX_CUDA(cudaEventRecord(s.a, c->stream));
+    c->spans.push_back(s);
+    return 0;
+}
+inline int stage_end(coex_ctx *c, long long launches) {
+    StageSpan &s = c->spans.back();
+    COEX_CUDA(cudaEventRecord(s.b, c->stream));
+    c->launches += launches;
+    c->stage_launches[s.stage] += launches;
+    return 0;
+}
+inline void stage_reset(coex_ctx *c) {
+    for (auto &s : c->spans) {
+        cudaEventDestroy(s.a);
+        cudaEventDestroy(s.b);
+    }
+    c->spans.clear();
+    for (int i = 0; i < kNumStages; ++i) {
+        c->stage_ms[i] = 0;
+        c->stage_launches[i] = 0;
+    }
+}
+inline int stage_collect(coex_ctx *c) {
+    COEX_CUDA(cudaStreamSynchronize(c->stream));
+    for (auto &s : c->spans) {
+        float ms = 0.f;
+        COEX_CUDA(cudaEventElapsedTime(&ms, s.a, s.b));
+        c->stage_ms[s.stage] += ms;
+        cudaEventDestroy(s.a);
+        cudaEventDestroy(s.b);
+    }
+    c->spans.clear();
+    return 0;
+}
+
+__host__ __device__ inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+
+__device__ __forceinline__ int next_pow2_dev(int x) {
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+inline int next_pow2(int x) {
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+}  // namespace coex

@@ -1,0 +1,306 @@
+// gemm_tc.cuh -- K3: the correlation step as a dense contraction on the sm_100a tensor cores.
+//
+// Exact-integer Spearman:  u = 2*rank-(n+1) (|u| <= n-1) is split into two int8 digits,
+// u = 128*hi + lo, and
+//      S[q, c] = sum_k u_q[k]*u_c[k] = 16384*(hi.hi) + 128*(hi.lo + lo.hi) + (lo.lo)
+// is formed from four int8 x int8 -> int32 products on tcgen05 (`kind::i8`, UTCIMMA), so the
+// correlation is exact (no split-precision error at all): r = (S/4)/(sqrt(Saa/4)*sqrt(Sbb/4))
+// reproduces the reference's double result bit for bit (coexpression_v2.c:105-113 on ranks).
+//
+// Kernel shape (one CTA per 128 x 128 output tile, 192 threads, warp-specialised):
+//   warp 0      TMA producer: per 128-byte K block four SWIZZLE_128B boxes (A_hi, A_lo: 128 rows;
+//               B_hi, B_lo: 128 rows each, stacked into ONE 256-row B operand) -> 64 KB / stage,
+//               3 stages, mbarrier full/empty ring.
+//   warp 1      TMEM allocator (512 columns) + single-thread MMA issuer: per 32-byte K step
+//                 D1[128 x 256] += A_hi * [B_hi ; B_lo]^T      (columns 0..127 hi.hi, 128..255 hi.lo)
+//                 D2[128 x 256] += A_lo * [B_hi ; B_lo]^T      (columns 0..127 lo.hi, 128..255 lo.lo)
+//               i.e. two M128 N256 K32 UTCIMMA per step instead of four N128 ones: the stacked B
+//               halves the shared-memory operand traffic per useful MAC.
+//   warps 2..5  epilogue: tcgen05.ld the four partial sums, recombine in int64, store int32.
+// Grid is rasterised with the query-row tile fastest so that one B column tile is reused from
+// L2 by every row tile of the strip and the table streams from HBM once per strip.
+#pragma once
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+
+namespace coex {
+
+constexpr int kTcBM = 128, kTcBN = 128, kTcBK = 128;      // BK in bytes (= int8 elements)
+constexpr int kTcStages = 3;
+constexpr int kTcStageBytes = 65536;                      // A_hi 16K | A_lo 16K | B_hi 16K | B_lo 16K
+constexpr int kTcThreads = 192;
+constexpr int kTcSmemBytes = kTcStages * kTcStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr unsigned kTcSpinLimit = 1u << 22;   // bounded mbarrier polls (~seconds) -> error, not a hang
+
+struct TcState {
+    PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+    CUtensorMap map_bh, map_bl, map_ah, map_al;
+    const void *bh = nullptr, *bl = nullptr, *ah = nullptr, *al = nullptr;
+    long long b_rows = 0, a_rows = 0;
+    int n_pad = 0;
+    int *d_err = nullptr;
+    bool attr_set = false;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug must surface as an error code, never as a hung GPU
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int *err, int code) {
+    for (unsigned spin = 0; spin < kTcSpinLimit; ++spin)
+        if (mbar_try_wait(bar, parity)) return true;
+    atomicExch(err, code);
+    return false;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start address >> 4 in
+// bits [0,14), LBO (unused for swizzled K-major) = 1 in [16,30), SBO = 1024 B (8 rows x 128 B)
+// >> 4 in [32,46), descriptor version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ULL << 16) | (64ULL << 32) | (1ULL << 46) | (2ULL << 61);
+}
+// kind::i8 instruction descriptor: D = S32 (2 @ bit 4), A = B = signed int8 (1 @ bits 7, 10),
+// both K-major (bits 15, 16 = 0), N >> 3 @ bit 17, M >> 4 @ bit 24.
+__host__ __device__ constexpr uint32_t umma_idesc_i8(int M, int N) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                  const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+                  int *__restrict__ out, long long ldo, int nkb, int *err) {
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;          // SWIZZLE_128B: 1024-B aligned
+    const uint32_t bars = base + kTcStages * kTcStageBytes;               // full[3], empty[3], tmem_full, slot
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * kTcStages, bar_tmem = bars + 16 * kTcStages;
+    const uint32_t tmem_slot = bar_tmem + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * kTcBM;           // query-row tile (fastest)
+    const int c0 = blockIdx.y * kTcBN;           // table-column tile
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kTcStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_tmem, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % kTcStages;
+                if (kb >= kTcStages && !mbar_wait(bar_empty + 8 * s, ((kb / kTcStages) - 1) & 1, err, 1)) break;
+                const uint32_t st = base + s * kTcStageBytes;
+                mbar_expect_tx(bar_full + 8 * s, kTcStageBytes);
+                tma_load_2d(st, &map_ah, bar_full + 8 * s, kb * kTcBK, m0);
+                tma_load_2d(st + 16384, &map_al, bar_full + 8 * s, kb * kTcBK, m0);
+                tma_load_2d(st + 32768, &map_bh, bar_full + 8 * s, kb * kTcBK, c0);
+                tma_load_2d(st + 49152, &map_bl, bar_full + 8 * s, kb * kTcBK, c0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_i8(128, 256);
+            bool ok = true;
+            for (int kb = 0; kb < nkb && ok; ++kb) {
+                const int s = kb % kTcStages;
+                ok = mbar_wait(bar_full + 8 * s, (kb / kTcStages) & 1, err, 2);
+                if (!ok) break;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = base + s * kTcStageBytes;
+#pragma unroll
+                for (int ks = 0; ks < kTcBK / 32; ++ks) {
+                    const uint64_t a_hi = umma_desc_sw128(st + ks * 32);
+                    const uint64_t a_lo = umma_desc_sw128(st + 16384 + ks * 32);
+                    const uint64_t b_cat = umma_desc_sw128(st + 32768 + ks * 32);
+                    const uint32_t acc = (kb | ks) ? 1u : 0u;
+                    umma_i8(tmem_base, a_hi, b_cat, idesc, acc);            // [hi.hi | hi.lo]
+                    umma_i8(tmem_base + 256, a_lo, b_cat, idesc, acc);      // [lo.hi | lo.lo]
+                }
+                umma_commit(bar_empty + 8 * s);        // frees the stage once these MMAs retire
+            }
+            umma_commit(bar_tmem);                     // accumulators complete
+        }
+    } else {
+        // ===== epilogue: 4 warps, TMEM lane quarter = warp % 4 =====
+        const int quarter = warp & 3;
+        if (mbar_wait(bar_tmem, 0, err, 3)) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16);
+            int *orow = out + (long long)(m0 + quarter * 32 + lane) * ldo + c0;
+#pragma unroll 1
+            for (int cc = 0; cc < kTcBN; cc += 16) {
+                uint32_t hh[16], hl[16], lh[16], ll[16];
+                tmem_ld16(tl + cc, hh);
+                tmem_ld16(tl + 128 + cc, hl);
+                tmem_ld16(tl + 256 + cc, lh);
+                tmem_ld16(tl + 384 + cc, ll);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    int4 v;
+                    v.x = (int)(16384LL * (int)hh[j] + 128LL * ((long long)(int)hl[j] + (int)lh[j]) + (int)ll[j]);
+                    v.y = (int)(16384LL * (int)hh[j + 1] + 128LL * ((long long)(int)hl[j + 1] + (int)lh[j + 1]) + (int)ll[j + 1]);
+                    v.z = (int)(16384LL * (int)hh[j + 2] + 128LL * ((long long)(int)hl[j + 2] + (int)lh[j + 2]) + (int)ll[j + 2]);
+                    v.w = (int)(16384LL * (int)hh[j + 3] + 128LL * ((long long)(int)hl[j + 3] + (int)lh[j + 3]) + (int)ll[j + 3]);
+                    *reinterpret_cast<int4 *>(orow + cc + j) = v;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+static int tc_state(coex_ctx *c, TcState **out) {
+    if (!c->tc) {
+        TcState *t = new TcState();
+        cudaDriverEntryPointQueryResult qres;
+        void *fn = nullptr;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+            delete t;
+            COEX_FAIL("cuTensorMapEncodeTiled is not available from the CUDA driver");
+        }
+        t->encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+        if (cudaMalloc(&t->d_err, sizeof(int)) != cudaSuccess) { delete t; COEX_FAIL("cudaMalloc(error flag)"); }
+        cudaMemset(t->d_err, 0, sizeof(int));
+        c->tc = t;
+    }
+    *out = static_cast<TcState *>(c->tc);
+    return 0;
+}
+
+static int tc_encode(TcState *t, CUtensorMap *map, const void *ptr, long long rows, int n_pad) {
+    cuuint64_t dims[2] = {(cuuint64_t)n_pad, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)n_pad};
+    cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = t->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) COEX_FAIL("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return 0;
+}
+
+inline int tc_invalidate(coex_ctx *c) {
+    if (c->tc) {
+        TcState *t = static_cast<TcState *>(c->tc);
+        t->bh = t->bl = t->ah = t->al = nullptr;
+    }
+    return 0;
+}
+
+inline void tc_destroy(coex_ctx *c) {
+    if (c->tc) {
+        TcState *t = static_cast<TcState *>(c->tc);
+        if (t->d_err) cudaFree(t->d_err);
+        delete t;
+        c->tc = nullptr;
+    }
+}
+
+// S strip [m_rows, N_pad] = A (gathered query digits, c->a_hi / c->a_lo) x table digits^T
+inline int tc_gemm_i8_ptrs(coex_ctx *c, const int8_t *a_hi, const int8_t *a_lo, long long a_rows_alloc,
+                           long long m_rows, int *out, long long ldo) {
+    TcState *t = nullptr;
+    COEX_TRY(tc_state(c, &t));
+    if (m_rows % kTcBM) COEX_FAIL("tc_gemm: query rows must be padded to 128");
+    if (t->bh != c->u_hi.p || t->bl != c->u_lo.p || t->b_rows != c->N_pad || t->n_pad != c->n_pad) {
+        COEX_TRY(tc_encode(t, &t->map_bh, c->u_hi.p, c->N_pad, c->n_pad));
+        COEX_TRY(tc_encode(t, &t->map_bl, c->u_lo.p, c->N_pad, c->n_pad));
+        t->bh = c->u_hi.p; t->bl = c->u_lo.p; t->b_rows = c->N_pad; t->n_pad = c->n_pad;
+        t->ah = t->al = nullptr;
+    }
+    if (t->ah != a_hi || t->al != a_lo || t->a_rows != a_rows_alloc) {
+        COEX_TRY(tc_encode(t, &t->map_ah, a_hi, a_rows_alloc, c->n_pad));
+        COEX_TRY(tc_encode(t, &t->map_al, a_lo, a_rows_alloc, c->n_pad));
+        t->ah = a_hi; t->al = a_lo; t->a_rows = a_rows_alloc;
+    }
+    if (!t->attr_set) {
+        COEX_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+        t->attr_set = true;
+    }
+    dim3 grid((unsigned)(m_rows / kTcBM), (unsigned)(c->N_pad / kTcBN));
+    gemm_i8_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, c->stream>>>(t->map_ah, t->map_al, t->map_bh, t->map_bl, out, ldo,
+                                                                    c->n_pad / kTcBK, t->d_err);
+    COEX_CUDA(cudaGetLastError());
+    return 0;
+}
+
+inline int tc_gemm_i8(coex_ctx *c, long long m_rows) {
+    return tc_gemm_i8_ptrs(c, c->a_hi.p, c->a_lo.p, (long long)(c->a_hi.cap / c->n_pad), m_rows, c->strip.p, c->N_pad);
+}
+
+// non-zero if any tensor-core kernel of this context hit its bounded-wait limit
+inline int tc_check_error(coex_ctx *c) {
+    if (!c->tc) return 0;
+    TcState *t = static_cast<TcState *>(c->tc);
+    int h = 0;
+    COEX_CUDA(cudaMemcpyAsync(&h, t->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    COEX_CUDA(cudaStreamSynchronize(c->stream));
+    if (h) {
+        cudaMemsetAsync(t->d_err, 0, sizeof(int), c->stream);
+        COEX_FAIL("tcgen05 GEMM pipeline timed out waiting on mbarrier (role code " + std::to_string(h) + ")");
+    }
+    return 0;
+}
+
+}  // namespace coex

@@ -1,0 +1,165 @@
+// prepare.cuh -- per-row work done once per table:
+//   K1  rank_pack_kernel    average-tie ranks (scipy.stats.rankdata 'average' as called at
+//                           reference 1-make-network.py:110-111), fused with the packing of
+//                           u = 2*rank-(n+1) into two int8 digit planes for the exact integer
+//                           correlation GEMM, sum(u^2) and sqrt(sum/4).
+//   K1b rowstats_kernel     the per-row quantities reference coexpression_v2.c:74-110
+//                           recomputes for every pair: left-to-right sum, mean = sum/n and
+//                           sum((x-mean)^2), bit-identical to the reference's doubles.
+#pragma once
+#include "common.cuh"
+
+namespace coex {
+
+// -------------------------------------------------------------------------------------------
+// K1: one CTA per row.  Shared-memory bitonic sort of (value, column) pairs, tie runs located
+// by binary search in the sorted keys, 2*rank = first+last+2 scattered back to column order,
+// then the packed outputs are written with 16-byte stores.
+//
+// HBM traffic per element: 8 B read (f64) + 2 B (u16 2*rank) + 2 B (two int8 digits) written.
+// -------------------------------------------------------------------------------------------
+constexpr int kRankThreads = 256;
+
+__global__ void __launch_bounds__(kRankThreads)
+rank_pack_kernel(const double *__restrict__ raw, long long N, int n, int n_pad, int P2,
+                 uint16_t *__restrict__ rank2_out, int8_t *__restrict__ hi_out,
+                 int8_t *__restrict__ lo_out, long long *__restrict__ suu_out,
+                 double *__restrict__ sx_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *keys = reinterpret_cast<double *>(smem_raw);                    // [P2]
+    uint16_t *idx = reinterpret_cast<uint16_t *>(keys + P2);                // [P2]
+    uint16_t *r2 = idx + P2;                                                // [n_pad]
+    __shared__ long long red[kRankThreads / 32];
+
+    const long long row = blockIdx.x;
+    const int tid = threadIdx.x;
+    const double *x = raw + row * (long long)n;
+
+    for (int p = tid; p < P2; p += kRankThreads) {
+        // +0.0 canonicalises -0.0 so that it ties with 0.0 exactly as a double compare does
+        keys[p] = (p < n) ? (x[p] + 0.0) : __longlong_as_double(0x7ff0000000000000LL);
+        idx[p] = (p < n) ? (uint16_t)p : (uint16_t)0xFFFF;
+    }
+    __syncthreads();
+
+    for (int k = 2; k <= P2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (P2 >> 1); t += kRankThreads) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const double ka = keys[i], kb = keys[l];
+                const uint16_t ia = idx[i], ib = idx[l];
+                const bool gt = (ka > kb) || (ka == kb && ia > ib);
+                const bool up = ((i & k) == 0);
+                if (gt == up) {
+                    keys[i] = kb; keys[l] = ka;
+                    idx[i] = ib;  idx[l] = ia;
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // tie run of sorted position p = [lower_bound(key), upper_bound(key)) within the n real keys
+    for (int p = tid; p < n; p += kRankThreads) {
+        const double key = keys[p];
+        int lo = 0, hi = p;                       // first position with keys[pos] >= key
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (keys[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        const int first = lo;
+        lo = p + 1; hi = n;                       // first position with keys[pos] > key
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (keys[mid] <= key) lo = mid + 1; else hi = mid;
+        }
+        const int last = lo - 1;
+        r2[idx[p]] = (uint16_t)(first + last + 2);   // 2 * average rank (1-based)
+    }
+    __syncthreads();
+
+    // outputs: u16 2*rank, digits of u = 2*rank-(n+1) = 128*hi + lo, lo in [-64, 63]
+    long long acc = 0;
+    uint16_t *r2row = rank2_out + row * (long long)n;
+    for (int c = tid; c < n; c += kRankThreads) {
+        r2row[c] = r2[c];
+        const long long u = (long long)r2[c] - (n + 1);
+        acc += u * u;
+    }
+    const long long prow = row * (long long)n_pad;
+    for (int v = tid; v < (n_pad >> 4); v += kRankThreads) {
+        alignas(16) int8_t h[16], l[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const int c = (v << 4) + e;
+            const int u = (c < n) ? ((int)r2[c] - (n + 1)) : 0;
+            const int hh = (u + 64) >> 7;            // floor((u+64)/128): arithmetic shift
+            h[e] = (int8_t)hh;
+            l[e] = (int8_t)(u - (hh << 7));
+        }
+        *reinterpret_cast<int4 *>(hi_out + prow + (v << 4)) = *reinterpret_cast<const int4 *>(h);
+        *reinterpret_cast<int4 *>(lo_out + prow + (v << 4)) = *reinterpret_cast<const int4 *>(l);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((tid & 31) == 0) red[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        long long s = 0;
+        for (int w = 0; w < kRankThreads / 32; ++w) s += red[w];
+        suu_out[row] = s;
+        // reference: xx = sum((rank-mean)^2) = s/4 exactly; sqrt as coexpression_v2.c:113
+        sx_out[row] = sqrt(0.25 * (double)s);
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// K1b: in-order row statistics.  One thread owns one row and accumulates strictly left to
+// right (the reference's order); a 32x32 tile is staged through shared memory so that global
+// loads stay coalesced.  32 rows per CTA, 256 threads load, one warp accumulates.
+// -------------------------------------------------------------------------------------------
+constexpr int kStatRows = 32;
+
+__global__ void __launch_bounds__(256)
+rowstats_kernel(const double *__restrict__ data, long long N, int n, double *__restrict__ sum_out,
+                double *__restrict__ mean_out, double *__restrict__ xx_out,
+                unsigned char *__restrict__ pos_out) {
+    __shared__ double tile[kStatRows][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long long row0 = (long long)blockIdx.x * kStatRows;
+    double s = 0.0, mean = 0.0, xx = 0.0;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int c0 = 0; c0 < n; c0 += 32) {
+#pragma unroll
+            for (int r = ty; r < kStatRows; r += 8) {
+                const long long row = row0 + r;
+                const int c = c0 + tx;
+                tile[r][tx] = (row < N && c < n) ? data[row * (long long)n + c] : 0.0;
+            }
+            __syncthreads();
+            if (ty == 0) {
+                const int lim = min(32, n - c0);
+                if (pass == 0) {
+                    for (int j = 0; j < lim; ++j) s = __dadd_rn(s, tile[tx][j]);
+                } else {
+                    for (int j = 0; j < lim; ++j) {
+                        const double d = __dsub_rn(tile[tx][j], mean);
+                        xx = __dadd_rn(xx, __dmul_rn(d, d));
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (pass == 0) mean = s / (double)n;
+    }
+    const long long row = row0 + tx;
+    if (ty == 0 && row < N) {
+        sum_out[row] = s;
+        mean_out[row] = mean;
+        xx_out[row] = xx;
+        if (pos_out) pos_out[row] = (s > 0.0) ? 1 : 0;
+    }
+}
+
+}  // namespace coex

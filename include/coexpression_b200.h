@@ -1,0 +1,131 @@
+/*
+ * coexpression_b200.h -- C ABI of the B200-native drop-in for the network-density hot path
+ * of baillielab/coexpression.  The shared library is built as `coexpression_v2.so` (the file
+ * name the reference loads with ctypes.cdll.LoadLibrary, reference 1-make-network.py:66-67,
+ * 0-prepare-coex.py:162,223).  Plain C types only: pointers, sizes, ints, doubles.
+ *
+ * Two groups of entry points:
+ *   1. the LEGACY symbol `getPearson`, bit-for-bit the reference's signature, for unmodified
+ *      reference scripts (call sites 1-make-network.py:229-234 and 0-prepare-coex.py:692-697);
+ *   2. a handle-based BATCHED API (new; the reference has no counterpart because it re-uploads
+ *      and re-ranks the whole table in every one of its per-permutation processes,
+ *      1-make-network.py:100-122) in which the table is made resident once and K permutations
+ *      are reduced to network densities per call.
+ *
+ * Every function of group 2 returns 0 on success and a non-zero code on failure; the message
+ * is available from coex_last_error().  There is NO CPU fallback: without a CUDA device every
+ * compute entry point fails (group 2) or aborts loudly (getPearson, which has no error channel,
+ * reference coexpression_v2.c:22 returns void).
+ */
+#ifndef COEXPRESSION_B200_H
+#define COEXPRESSION_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * 1. Legacy drop-in.  Replaces reference coexpression_v2.c:22-129.
+ *    dataAll  : host, double [rows * n] row-major (rows is implied: max index + 1)
+ *    resultAll: host, double [nPromPairs], written on return (synchronous)
+ *    idxa_all, idxb_all: host, int [nPromPairs], 0-based row numbers
+ *    Result per pair is bit-identical to the reference's: left-to-right double sums,
+ *    NaN when either row sums to exactly 0.0 (coexpression_v2.c:89-92) or has zero variance.
+ * ---------------------------------------------------------------------------------------- */
+void getPearson(double *dataAll, double *resultAll, int *idxa_all, int *idxb_all,
+                int nPromPairs, int n);
+
+/* ------------------------------------------------------------------------------------------
+ * 2. Batched API.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct coex_ctx coex_ctx;
+
+const char *coex_last_error(void);
+int coex_abi_version(void);
+int coex_device_count(void);            /* 0 when no CUDA device / driver is present */
+
+int coex_create(coex_ctx **out, int device);
+int coex_destroy(coex_ctx *ctx);
+int coex_sync(coex_ctx *ctx);
+void *coex_stream(coex_ctx *ctx);       /* the cudaStream_t every kernel of ctx is launched on */
+
+/* A3 "matrix marshal" (1-make-network.py:100-122): one bulk copy instead of N*n Python stores.
+ * data: double [N * n] row-major in table order.  `on_device` != 0: data is a device pointer. */
+int coex_set_expression(coex_ctx *ctx, const double *data, long long N, int n, int on_device);
+
+/* A2 rank transform (scipy.stats.rankdata 'average', 1-make-network.py:108-111) + per-row
+ * statistics + packing for the correlation kernels.  Must follow coex_set_expression. */
+int coex_prepare(coex_ctx *ctx);
+/* ranks as doubles [N * n] (host), for parity checks against scipy.stats.rankdata */
+int coex_get_ranks(coex_ctx *ctx, double *ranks_out);
+
+/* Genomic coordinates of every table row, for join_nearby (coexfunctions.py:277-316):
+ * chrom_id orders like the chromosome string, name_rank orders like the row label. */
+int coex_set_features(coex_ctx *ctx, const int *chrom_id, const long long *start,
+                      const long long *end, const int *name_rank, long long N);
+/* ascending global correlation list (<expr>.spearmanlist, 1-make-network.py:76-79) */
+int coex_set_global_list(coex_ctx *ctx, const double *sorted_values, long long len);
+
+/* A1 on the resident table.  which: 0 = raw values (Pearson), 1 = ranks (Spearman).
+ * idxa/idxb/out are host pointers (on_device == 0) or device pointers. */
+int coex_pairs(coex_ctx *ctx, int which, const int *idxa, const int *idxb, long long npairs,
+               double *out, int on_device);
+
+/* All-pairs correlation of the resident table reduced on the device (config C3): histogram of
+ * r over `nbins` equal bins on [-1, 1] for row pairs (a, b), a in [row0, row1), b > a; NaN pairs
+ * counted in nan_count.  which as in coex_pairs.  hist: host, unsigned long long [nbins]. */
+int coex_allpairs_histogram(coex_ctx *ctx, int which, long long row0, long long row1, int nbins,
+                            unsigned long long *hist, unsigned long long *nan_count);
+
+typedef struct coex_params {
+    int measure;                /* -cm: 0 Spearman, 1 Pearson (null list + join_nearby; the   */
+                                /*      hit-vs-hit statistic is always Spearman, quirk Q2)     */
+    int anticorrelation;        /* -a  (1-make-network.py:289-292, coexfunctions.py:305-307)   */
+    int noiter;                 /* -i  (1-make-network.py:465)                                 */
+    int useaverage;             /* -u  (1-make-network.py:457)                                 */
+    int use_specific_p;         /* nsp > 1/N (1-make-network.py:189-193); 0 = global list      */
+    int reserved;
+    double pval_to_join;        /* -j                                                          */
+    double selectionthreshold;  /* -st, or -log10(pval_to_join) under -m                       */
+    long long soft_separation;  /* -ss                                                         */
+} coex_params;
+
+/* A4-A12 for K permutations in one call (1-make-network.py:198-482 once per permutation).
+ *   perm_off : long long [K+1], hits of permutation k are hit_rows[perm_off[k] .. perm_off[k+1])
+ *   hit_rows : int [H], table rows in map-file first-appearance order (Q1: the null list of
+ *              hit position i omits table column i)
+ * Outputs (H = perm_off[K]; per-group arrays use the first n_groups[k] slots of permutation k's
+ * segment; groups are numbered in ascending label order):
+ *   n_groups        int    [K]
+ *   group_of_hit    int    [H]   group number of each hit
+ *   group_label     int    [H]   per group: hit position (within the permutation) of its label
+ *   group_winner    int    [H]   per group: hit position of its winner (1-make-network.py:431-434)
+ *   group_density   double [H]   per group: indmeasure (after iterative removal unless noiter)
+ *   hit_score       double [H]   allpromoterscores (1-make-network.py:424)
+ *   scores          double [sum P_k^2] or NULL: individualscores, row-major per permutation
+ *   counts          long long [sum P_k^2] or NULL: bisect_left indices (-1 where not computed)
+ * on_device != 0: every pointer (inputs and outputs) is a device pointer and the call is
+ * asynchronous on coex_stream(ctx). */
+int coex_network_batch(coex_ctx *ctx, const coex_params *params, int K,
+                       const long long *perm_off, const int *hit_rows,
+                       int *n_groups, int *group_of_hit, int *group_label, int *group_winner,
+                       double *group_density, double *hit_score,
+                       double *scores, long long *counts, int on_device);
+
+/* Introspection for bench.py: kernels launched by ctx so far, and per-stage device time (ms,
+ * CUDA events on coex_stream) of the last coex_network_batch / coex_prepare call.
+ * stage ids: 0 rank+pack, 1 row stats, 2 gather, 3 correlation GEMM, 4 count+score, 5 network */
+long long coex_launch_count(coex_ctx *ctx);
+int coex_stage_ms(coex_ctx *ctx, int stage, double *ms, long long *launches);
+/* 0 = tcgen05/TMA tensor-core GEMM, 1 = SIMT dp4a GEMM (validation path) */
+int coex_set_gemm_mode(coex_ctx *ctx, int mode);
+int coex_set_workspace_mb(coex_ctx *ctx, long long strip_mb);
+/* On-device cross-check: the first m_rows table rows against the whole table through the tcgen05
+ * kernel and through the dp4a kernel; *mismatches = differing int32 dot products,
+ * first4 = {row, column, tensor value, dp4a value} of one of them (or -1s). */
+int coex_selftest_gemm(coex_ctx *ctx, long long m_rows, long long *mismatches, long long *first4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COEXPRESSION_B200_H */

@@ -1,0 +1,216 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle.  Needs a B200: -m gpu."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import has_cuda
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")]
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.int64)
+
+
+def _same_doubles(a, b):
+    """bit-exact where defined, NaN exactly where the reference has NaN"""
+    a = np.asarray(a); b = np.asarray(b)
+    return np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(_bits(a[~np.isnan(a)]), _bits(b[~np.isnan(b)]))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from coexpression_b200 import _lib
+    return _lib.load()
+
+
+# ---------------------------------------------------------------------------------------------
+# A1: the legacy drop-in symbol, called exactly as 1-make-network.py:229-234 does
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["getpearson_raw", "getpearson_ranked", "getpearson_onepair"])
+def test_legacy_getpearson_golden(lib, name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    X = np.ascontiguousarray(g["X"]); ia = np.ascontiguousarray(g["ia"]); ib = np.ascontiguousarray(g["ib"])
+    n_pairs = ia.size
+    data_c = (ctypes.c_double * X.size)(*X.ravel())
+    idxa_c = (ctypes.c_int * n_pairs)(*ia.tolist())
+    idxb_c = (ctypes.c_int * n_pairs)(*ib.tolist())
+    result_c = (ctypes.c_double * n_pairs)()
+    raw = ctypes.cdll.LoadLibrary(lib._name)          # untyped, as the reference calls it
+    raw.getPearson(ctypes.byref(data_c), ctypes.byref(result_c), ctypes.byref(idxa_c), ctypes.byref(idxb_c),
+                   ctypes.c_int(n_pairs), ctypes.c_int(X.shape[1]))
+    assert _same_doubles(np.array(result_c[:]), g["r"])
+
+
+def test_legacy_getpearson_zero_pairs_and_random(lib):
+    from oracle import network_oracle as no
+    rng = np.random.default_rng(5)
+    X = rng.lognormal(0, 2, size=(700, 1829)) * (rng.random((700, 1829)) < 0.5)
+    X[11] = 0.0
+    ia = rng.integers(0, 700, 30000).astype(np.int32); ib = rng.integers(0, 700, 30000).astype(np.int32)
+    out = np.full(ia.size, 7.0)
+    lib.getPearson(X.ctypes.data, out.ctypes.data, ia.ctypes.data, ib.ctypes.data, 0, 1829)
+    assert np.all(out == 7.0)                           # nPromPairs == 0 touches nothing
+    lib.getPearson(X.ctypes.data, out.ctypes.data, ia.ctypes.data, ib.ctypes.data, ia.size, 1829)
+    assert _same_doubles(out, no.get_pearson(X, ia, ib))
+    Y = X - 0.3                                         # mixed signs
+    lib.getPearson(Y.ctypes.data, out.ctypes.data, ia.ctypes.data, ib.ctypes.data, ia.size, 1829)
+    assert _same_doubles(out, no.get_pearson(Y, ia, ib))
+
+
+# ---------------------------------------------------------------------------------------------
+# A2: ranks bit-exact with scipy.stats.rankdata
+# ---------------------------------------------------------------------------------------------
+def test_ranks_golden_and_random():
+    from coexpression_b200.api import CoexContext
+    from oracle import network_oracle as no
+    g = np.load(os.path.join(GOLDEN, "ranks_small.npz"))
+    with CoexContext() as ctx:
+        ctx.set_expression(g["X"]); ctx.prepare()
+        assert np.array_equal(ctx.ranks(), g["ranks"])
+        rng = np.random.default_rng(3)
+        for n in (1, 2, 31, 256, 1000, 1829):
+            X = np.round(rng.gamma(0.4, 3.0, size=(97, n)), 1)      # heavy ties
+            X[0] = 0.0
+            X[1] = np.arange(n)
+            ctx.set_expression(X); ctx.prepare()
+            assert np.array_equal(ctx.ranks(), no.rank_rows(X)), n
+
+
+def test_pairs_on_resident_table():
+    from coexpression_b200 import synth
+    from coexpression_b200.api import CoexContext
+    from oracle import network_oracle as no
+    t = synth.make_table(900, 333, seed=9)
+    R = no.rank_rows(t.X)
+    rng = np.random.default_rng(1)
+    ia = rng.integers(0, 900, 20000).astype(np.int32); ib = rng.integers(0, 900, 20000).astype(np.int32)
+    with CoexContext() as ctx:
+        ctx.set_expression(t.X); ctx.prepare()
+        assert _same_doubles(ctx.pairs(ia, ib, ranked=True), no.get_pearson(R, ia, ib))
+        assert _same_doubles(ctx.pairs(ia, ib, ranked=False), no.get_pearson(t.X, ia, ib))
+
+
+# ---------------------------------------------------------------------------------------------
+# K3: tcgen05 GEMM == dp4a GEMM (exact integers), several K extents incl. the FANTOM5 one
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,n", [(600, 48), (1000, 300), (2500, 1829), (700, 1860)])
+def test_tcgen05_gemm_matches_dp4a(N, n):
+    from coexpression_b200 import synth
+    from coexpression_b200.api import CoexContext
+    t = synth.make_table(N, n, seed=N + n)
+    with CoexContext() as ctx:
+        ctx.set_expression(t.X); ctx.prepare()
+        bad, first = ctx.selftest_gemm(min(N, 512))
+        assert bad == 0, first
+
+
+# ---------------------------------------------------------------------------------------------
+# A4-A12: golden network cases (oracle consistent mode driving the reference C build)
+# ---------------------------------------------------------------------------------------------
+NETWORK_CASES = ["spearman_default", "spearman_anticor", "spearman_noiter_j001", "spearman_useavg_m",
+                 "spearman_global_nsp0", "pearson_default", "pearson_anticor_j05"]
+
+
+def _run_case(name, gemm_mode):
+    from coexpression_b200.api import CoexContext, Options
+    from coexpression_b200.results import perm_objects
+    with open(os.path.join(GOLDEN, f"network_{name}.json")) as f:
+        case = json.load(f)
+    kw = case["kwargs"]
+    cm = kw.get("correlationmeasure", "Spearman")
+    inp = np.load(os.path.join(GOLDEN, f"network_inputs_{case['shape']}_{cm}.npz"))
+    names = [str(s) for s in inp["names"]]
+    opts = Options(**kw)
+    with CoexContext() as ctx:
+        ctx.set_gemm_mode(gemm_mode)
+        ctx.set_expression(inp["X"]); ctx.prepare()
+        ctx.set_features(inp["chrom"], inp["start"], inp["end"], names)
+        ctx.set_global_list(inp["glist"])
+        res = ctx.network_batch([np.array(p["hit_rows"], dtype=np.int32) for p in case["perms"]], opts,
+                                want_scores=True, want_counts=True)
+    for k, perm in enumerate(case["perms"]):
+        got = perm_objects(res, k, names)
+        P = len(perm["hit_rows"])
+        assert np.array_equal(res.count_matrix(k), np.array(perm["counts"]).reshape(P, P)), (name, k)
+        assert got["prom_to_join"] == perm["prom_to_join"], (name, k)            # bit-exact groups
+        assert got["winners"] == perm["winners"], (name, k)
+        assert set(got["indmeasure"]) == set(perm["indmeasure"])
+        for g, v in perm["indmeasure"].items():
+            assert abs(got["indmeasure"][g] - v) <= 1e-6, (name, k, g)           # north_star tolerance
+        for p_, v in perm["allpromoterscores"].items():
+            assert abs(got["allpromoterscores"][p_] - v) <= 1e-6
+
+
+@pytest.mark.parametrize("name", NETWORK_CASES)
+def test_network_golden_tcgen05(name):
+    _run_case(name, "tcgen05")
+
+
+@pytest.mark.parametrize("name", ["spearman_default", "spearman_anticor"])
+def test_network_golden_dp4a(name):
+    _run_case(name, "simt")
+
+
+def test_network_against_live_oracle_small_shape():
+    """Bigger than the golden cases: 3000 x 96 table, 4 hit sets incl. an empty and a single-hit one."""
+    from coexpression_b200 import synth
+    from coexpression_b200.api import CoexContext, Options
+    from coexpression_b200.results import perm_objects
+    from oracle import network_oracle as no
+    N, n = synth.SHAPES["small"]
+    t = synth.make_table(N, n, seed=31)
+    hits, loci, m = synth.make_permutation_hits(t, 150, 3, window=6000, seed=8)
+    hits = hits + [np.zeros(0, dtype=np.int32), hits[0][:1]]
+    R = no.rank_rows(t.X)
+    ga, gb = synth.global_pair_indices(t.names, 50000, seed=2)
+    g = no.get_pearson(R, ga, gb)
+    glist = np.sort(np.where(np.isnan(g), -99.0, g))
+    for opts in (Options(), Options(anticorrelation=True, pval_to_join=0.01)):
+        with CoexContext() as ctx:
+            ctx.set_expression(t.X); ctx.prepare()
+            ctx.set_features(t.chrom, t.start, t.end, t.names)
+            ctx.set_global_list(glist)
+            # the global list itself through the resident-table pair kernel (call site #2)
+            g_gpu = ctx.pairs(ga, gb, ranked=True)
+            assert _same_doubles(g_gpu, g)
+            res = ctx.network_batch(hits, opts, want_scores=True, want_counts=True)
+        for k, h in enumerate(hits):
+            want = no.make_network(t.names, t.X, [t.names[r] for r in h], t.addresses(), glist.tolist(),
+                                   anticorrelation=opts.anticorrelation, pval_to_join=opts.pval_to_join,
+                                   Xrank=R, return_counts=True)
+            got = perm_objects(res, k, t.names)
+            assert got["prom_to_join"] == want["prom_to_join"]
+            assert got["winners"] == want["winners"]
+            if len(h) > 1:
+                assert np.array_equal(res.count_matrix(k), want["_counts"])
+            assert set(got["indmeasure"]) == set(want["indmeasure"])
+            for grp, v in want["indmeasure"].items():
+                assert abs(got["indmeasure"][grp] - v) <= 1e-6
+            for a in want["individualscores"]:
+                for b, v in want["individualscores"][a].items():
+                    assert abs(got["individualscores"][a][b] - v) <= 1e-6
+
+
+def test_allpairs_histogram_small():
+    from coexpression_b200 import synth
+    from coexpression_b200.api import CoexContext
+    from oracle import network_oracle as no
+    t = synth.make_table(500, 64, seed=12)
+    R = no.rank_rows(t.X)
+    iu = np.triu_indices(500, 1)
+    nb = 4096
+    for ranked, data in ((True, R), (False, t.X)):
+        r = no.get_pearson(data, iu[0].astype(np.int32), iu[1].astype(np.int32))
+        ok = ~np.isnan(r)
+        want = np.bincount(np.clip(((r[ok] + 1.0) * 0.5 * nb).astype(np.int64), 0, nb - 1), minlength=nb)
+        with CoexContext() as ctx:
+            ctx.set_expression(t.X); ctx.prepare()
+            hist, nan = ctx.allpairs_histogram(ranked, nbins=nb)
+        assert nan == int((~ok).sum())
+        assert np.array_equal(hist.astype(np.int64), want)
