@@ -13,6 +13,12 @@ def perm_objects(res, k, names, with_scores=True):
     G = len(p["label"])
     labels = [hit_names[i] for i in p["label"]]
     members = [[] for _ in range(G)]
+    if G == 0:      # fewer than two hits: individualscores is empty, nothing is grouped (1-make-network.py:333-338)
+        out = dict(indmeasure={}, prom_to_join={}, joining_instructions={}, winners={}, allpromoterscores={})
+        if with_scores and res.scores is not None:
+            out["individualscores"] = {}
+            out["indjoined"] = {}
+        return out
     for i, g in enumerate(p["group_of_hit"]):
         members[g].append(hit_names[i])
     prom_to_join = {labels[g]: sorted(members[g]) for g in range(G)}
