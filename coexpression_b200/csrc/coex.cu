@@ -226,7 +226,8 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
         na.w_root = c->w_root.p; na.w_pos = c->w_pos.p; na.w_s1 = c->w_s1.p; na.w_d0 = c->w_d0.p; na.w_w = c->w_w.p;
         na.w_best = c->w_best.p; na.w_cand = c->w_cand.p;
         na.P2max = T2max;
-        const size_t smem = (size_t)T2max * 24;
+        // sort/cluster arrays (24 B per padded hit) or the pass-1 staging tiles (8 warps x 32x17 doubles)
+        const size_t smem = std::max<size_t>((size_t)T2max * 24, 36 * 1024);
         COEX_CUDA(cudaFuncSetAttribute(network_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         COEX_TRY(stage_begin(c, ST_NETWORK));
         network_kernel<<<K, kNetThreads, smem, st>>>(na);

@@ -220,17 +220,38 @@ network_kernel(NetArgs a) {
     for (int g = tid; g < G; g += kNetThreads) { best[g] = 0ULL; cand[g] = ~0ULL; }
     __syncthreads();
     // ---- (5) pass 1: member score = sum over other-group hits, hit order -------------------
-    for (int i = tid; i < P; i += kNetThreads) {
-        const double *row = Sc + (long long)i * P;
-        const int gi = grp[i];
-        double s = 0.0;
-        for (int j = 0; j < P; ++j) {
-            if (j == i) continue;
-            const double v = row[j];
-            if (v >= a.thr && grp[j] != gi) s = __dadd_rn(s, v);
+    // One warp owns 32 rows; a 32 x 16 tile of the score matrix is staged through shared memory
+    // (coalesced 128-byte row segments in, one lane per row walking left to right out).
+    {
+        double *tile = reinterpret_cast<double *>(smem_raw) + warp * (32 * 17);   // [32][17] per warp
+        int *gcol = reinterpret_cast<int *>(reinterpret_cast<double *>(smem_raw) + (kNetThreads / 32) * (32 * 17)) + warp * 16;
+        const int half = lane >> 4, col = lane & 15;
+        for (int i0 = warp * 32; i0 < P; i0 += kNetThreads) {
+            const int i = i0 + lane;
+            const int gi = (i < P) ? grp[i] : -1;
+            double s = 0.0;
+            for (int j0 = 0; j0 < P; j0 += 16) {
+                __syncwarp();
+#pragma unroll 4
+                for (int r = half; r < 32; r += 2) {
+                    const int row = i0 + r, j = j0 + col;
+                    tile[r * 17 + col] = (row < P && j < P) ? Sc[(long long)row * P + j] : -1.0;
+                }
+                if (lane < 16) gcol[lane] = (j0 + lane < P) ? grp[j0 + lane] : gi;
+                __syncwarp();
+                if (i < P) {
+                    const int lim = min(16, P - j0);
+                    for (int c = 0; c < lim; ++c) {
+                        const double v = tile[lane * 17 + c];
+                        if ((j0 + c) != i && v >= a.thr && gcol[c] != gi) s = __dadd_rn(s, v);
+                    }
+                }
+            }
+            if (i < P) {
+                s1[i] = s;
+                atomicMax(&best[gi], (unsigned long long)__double_as_longlong(s));
+            }
         }
-        s1[i] = s;
-        atomicMax(&best[gi], (unsigned long long)__double_as_longlong(s));
     }
     __syncthreads();
     for (int i = tid; i < P; i += kNetThreads) {
@@ -239,53 +260,59 @@ network_kernel(NetArgs a) {
             atomicMin(&cand[gi], ((unsigned long long)(unsigned)a.name_rank[hits[i]] << 32) | (unsigned)i);
     }
     __syncthreads();
-    for (int g = tid; g < G; g += kNetThreads) win[g] = (int)(cand[g] & 0xffffffffULL);
+    // pass-1 winners w1 (kept in pos[]) and the working copy win[]
+    for (int g = tid; g < G; g += kNetThreads) { const int w = (int)(cand[g] & 0xffffffffULL); pos[g] = w; win[g] = w; }
     __syncthreads();
     // ---- (6) pass 2: Gauss-Seidel over groups in group order -------------------------------
-    // All member sums are evaluated against the current winners; the first group (in order)
-    // whose winner changes is committed, sums of the LATER groups are re-evaluated, and so on.
-    int cur = 0;                                   // groups < cur are final
-    while (true) {
-        for (int g = cur + tid; g < G; g += kNetThreads) { best[g] = 0ULL; cand[g] = ~0ULL; }
-        if (tid == 0) s_changed = G;
+    // The sequential rule "group g is scored against the FINAL winners of groups < g and the
+    // pass-1 winners of groups > g" is lower-triangular, so iterating
+    //     win_new[g] = argmax_m sum_h Sc[m][ h < g ? win_old[h] : w1[h] ]
+    // from win = w1 reaches the sequential result as its unique fixed point; after r rounds
+    // the first r groups are final, in practice a handful of rounds suffice.  The sums of the
+    // last round are exactly the sequential ones (allpromoterscores).
+    const int *w1 = pos;
+    for (int round = 0; round <= G; ++round) {
+        for (int g = tid; g < G; g += kNetThreads) { best[g] = 0ULL; cand[g] = ~0ULL; }
+        if (tid == 0) s_changed = 0;
         __syncthreads();
         for (int i = tid; i < P; i += kNetThreads) {
             const int gi = grp[i];
-            if (gi < cur) continue;
             const double *row = Sc + (long long)i * P;
             double s = 0.0;
-            for (int h = 0; h < G; ++h) {
-                if (h == gi) continue;
-                s = __dadd_rn(s, row[win[h]]);      // prom != otherprom holds: other group
+            int h = 0;
+            for (; h + 4 <= gi; h += 4) {                  // groups before gi: current winners
+                const double v0 = row[win[h]], v1 = row[win[h + 1]], v2 = row[win[h + 2]], v3 = row[win[h + 3]];
+                s = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(s, v0), v1), v2), v3);
             }
+            for (; h < gi; ++h) s = __dadd_rn(s, row[win[h]]);
+            h = gi + 1;
+            for (; h + 4 <= G; h += 4) {                   // groups after gi: pass-1 winners
+                const double v0 = row[w1[h]], v1 = row[w1[h + 1]], v2 = row[w1[h + 2]], v3 = row[w1[h + 3]];
+                s = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(s, v0), v1), v2), v3);
+            }
+            for (; h < G; ++h) s = __dadd_rn(s, row[w1[h]]);
             s1[i] = s;
             atomicMax(&best[gi], (unsigned long long)__double_as_longlong(s));
         }
         __syncthreads();
         for (int i = tid; i < P; i += kNetThreads) {
             const int gi = grp[i];
-            if (gi < cur) continue;
             if ((unsigned long long)__double_as_longlong(s1[i]) == best[gi])
                 atomicMin(&cand[gi], ((unsigned long long)(unsigned)a.name_rank[hits[i]] << 32) | (unsigned)i);
         }
         __syncthreads();
-        for (int g = cur + tid; g < G; g += kNetThreads)
-            if ((int)(cand[g] & 0xffffffffULL) != win[g]) atomicMin(&s_changed, g);
-        __syncthreads();
-        const int ch = s_changed;
-        // groups cur..min(ch, G-1) are final with the sums just computed
-        const int upto = (ch < G) ? ch : (G - 1);
-        for (int i = tid; i < P; i += kNetThreads) {
-            const int gi = grp[i];
-            if (gi >= cur && gi <= upto) aps[i] = s1[i];
+        int changed = 0;
+        for (int g = tid; g < G; g += kNetThreads) {
+            const int w = (int)(cand[g] & 0xffffffffULL);
+            if (w != win[g]) { win[g] = w; changed = 1; }
         }
+        if (changed) s_changed = 1;
         __syncthreads();
-        if (ch >= G) break;
-        if (tid == 0) win[ch] = (int)(cand[ch] & 0xffffffffULL);
-        cur = ch + 1;
+        if (!s_changed) break;
         __syncthreads();
-        if (cur >= G) break;
     }
+    for (int i = tid; i < P; i += kNetThreads) aps[i] = s1[i];
+    __syncthreads();
     // ---- (7) indjoined row sums = density ---------------------------------------------------
     const double gdiv = (double)G;
     for (int g = tid; g < G; g += kNetThreads) {
@@ -310,15 +337,15 @@ network_kernel(NetArgs a) {
                 const double dh = d0[h];
                 before += (dh > dg) || (dh == dg && h > g);   // larger label == larger group number
             }
-            pos[g] = before;
+            root[g] = before;
         }
         __syncthreads();
         for (int g = tid; g < G; g += kNetThreads) {
             const double *row = Sc + (long long)win[g] * P;
-            const int pg = pos[g];
+            const int pg = root[g];
             double s = 0.0;
             for (int h = 0; h < G; ++h) {
-                if (h == g || pos[h] < pg) continue;          // h already cut
+                if (h == g || root[h] < pg) continue;          // h already cut
                 const double v = row[win[h]];
                 if (v >= a.thr) s = __dadd_rn(s, v);
             }

@@ -1,0 +1,139 @@
+"""B200 drop-in for the reference's per-permutation driver (reference 1-make-network.py).
+
+Same command line (`-mf <mapfile> -wd <working_files_dir> [-t N] [-r]`), same inputs
+(settings.txt, expression table, feature BED, global correlation list, windowBed map file) and
+the same eight JSON objects in `perm_results_store/` (1-make-network.py:523-540), so that
+2-collate-results.py and runlocal.py's completion polling keep working.
+
+`run_batch` is the B200-first entry: every map file of `permutation_store/` is reduced in ONE
+process with the table resident on the GPU (the reference starts one process per permutation
+and re-reads / re-ranks / re-marshals the table in each, runlocal.py:50-55).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+from .api import CoexContext, Options
+from .coexfunctions import (read_correlation_list, read_expression_file, read_snp_map, readfeaturecoordinates,
+                            readsettings)
+from .results import perm_objects
+
+
+def options_from_settings(st):
+    """settings.txt keys read at 1-make-network.py:35-49 (values arrive as floats / bools, Q9)."""
+    return Options(
+        correlationmeasure=st.get("correlationmeasure", "Spearman"),
+        anticorrelation=bool(st.get("anticorrelation", False)),
+        noiter=bool(st.get("noiter", False)),
+        useaverage=bool(st.get("useaverage", False)),
+        nsp=float(st.get("nsp", 1.0)),
+        pval_to_join=float(st.get("pval_to_join", 0.1)),
+        selectionthreshold=float(st.get("selectionthreshold", 0)),
+        selectionthreshold_is_j=bool(st.get("selectionthreshold_is_j", False)),
+        soft_separation=int(float(st.get("soft_separation", 100000))))
+
+
+def result_path(store, mapfile, label):
+    parts = os.path.split(mapfile)[-1].replace(".bed", "").split(".")
+    return os.path.join(store, ".".join(parts[:-1] + [label] + parts[-1:]))
+
+
+class Session:
+    """Expression table resident on one GPU + everything a permutation needs besides its hits."""
+
+    def __init__(self, settings, device=0, verbose=False):
+        self.settings = settings
+        self.verbose = verbose
+        self.options = options_from_settings(settings)
+        self.table, self.header = read_expression_file(settings["expression_file"])
+        addresses, _, _ = readfeaturecoordinates(settings["feature_coordinates"])
+        self.addresses = addresses
+        glist = read_correlation_list(settings["correlationfile"])
+        names = self.table.names
+        chrom = np.array([addresses[nm][0] if nm in addresses else "" for nm in names])
+        start = np.array([addresses[nm][1] if nm in addresses else 0 for nm in names], dtype=np.int64)
+        end = np.array([addresses[nm][2] if nm in addresses else 0 for nm in names], dtype=np.int64)
+        self.has_address = np.array([nm in addresses for nm in names])
+        self.ctx = CoexContext(device)
+        self.ctx.set_expression(self.table.values)
+        self.ctx.prepare()
+        self.ctx.set_features(chrom, start, end, names)
+        self.ctx.set_global_list(glist)
+
+    def close(self):
+        self.ctx.close()
+
+    def hits_of(self, mapfile):
+        snp_map = read_snp_map(mapfile, self.table, self.verbose)
+        rows = np.array([self.table.index[p] for p in snp_map], dtype=np.int32)
+        if len(rows) > 1 and not self.has_address[rows].all():
+            missing = [self.table.names[r] for r in rows if not self.has_address[r]]
+            raise KeyError(missing[0])          # the reference fails in join_nearby (coexfunctions.py:285)
+        return snp_map, rows
+
+    def run(self, mapfiles, store, full_dump=True, max_scores_bytes=8 << 30):
+        """Reduce the map files in chunks whose score matrices fit `max_scores_bytes`."""
+        os.makedirs(store, exist_ok=True)
+        parsed = [self.hits_of(mf) for mf in mapfiles]
+        written = []
+        i = 0
+        while i < len(mapfiles):
+            j, used = i, 0
+            while j < len(mapfiles):
+                need = 8 * len(parsed[j][1]) ** 2
+                if j > i and used + need > max_scores_bytes:
+                    break
+                used += need
+                j += 1
+            res = self.ctx.network_batch([parsed[k][1] for k in range(i, j)], self.options, want_scores=full_dump)
+            for k in range(i, j):
+                objs = perm_objects(res, k - i, self.table.names, with_scores=full_dump)
+                objs["snp_map"] = parsed[k][0]
+                for label, var in objs.items():
+                    path = result_path(store, mapfiles[k], label)
+                    with open(path, "w") as o:
+                        json.dump(var, o)
+                    written.append(path)
+            i = j
+        return written
+
+
+def run_batch(working_files_dir, mapfiles=None, device=0, verbose=False, full_dump=True):
+    settings = readsettings(working_files_dir)
+    perm_dir = os.path.join(working_files_dir, "permutation_store")
+    if mapfiles is None:
+        mapfiles = sorted((os.path.join(perm_dir, f) for f in os.listdir(perm_dir) if f.endswith(".bed")),
+                          key=lambda p: int(p.split(".")[-2]))
+    sess = Session(settings, device, verbose)
+    try:
+        return sess.run(mapfiles, os.path.join(working_files_dir, "perm_results_store"), full_dump)
+    finally:
+        sess.close()
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("-mf", "--mapfile", type=str, default="null", help="filepath")
+    ap.add_argument("-wd", "--working_files_dir", type=str, default="null", help="filepath")
+    ap.add_argument("-t", "--numthreads", type=int, default=1, help="accepted and ignored, as in the reference (Q10)")
+    ap.add_argument("-r", "--recordedges", action="store_true", default=False,
+                    help="accepted; the reference crashes on it (Q11) so nothing is recorded")
+    ap.add_argument("--all", action="store_true", help="B200 extension: reduce every map file of permutation_store/")
+    ap.add_argument("--device", type=int, default=0)
+    args = ap.parse_args(argv)
+    settings = readsettings(args.working_files_dir)
+    verbose = bool(settings.get("verbose", False))
+    if args.all:
+        run_batch(args.working_files_dir, None, args.device, verbose)
+    else:
+        run_batch(args.working_files_dir, [args.mapfile], args.device, verbose)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
