@@ -139,7 +139,8 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
     if (!d_sc) { COEX_TRY(c->d_scores.reserve(std::max<long long>(SC, 1))); d_sc = c->d_scores.p; }
     COEX_TRY(c->w_root.reserve(Hs_alloc)); COEX_TRY(c->w_pos.reserve(Hs_alloc)); COEX_TRY(c->w_s1.reserve(Hs_alloc));
     COEX_TRY(c->w_d0.reserve(Hs_alloc)); COEX_TRY(c->w_w.reserve(Hs_alloc)); COEX_TRY(c->w_best.reserve(Hs_alloc));
-    COEX_TRY(c->w_cand.reserve(Hs_alloc));
+    COEX_TRY(c->w_cand.reserve(Hs_alloc)); COEX_TRY(c->w_state.reserve(K + 1));
+    COEX_CUDA(cudaMemsetAsync(c->w_state.p, 0, (K + 1) * sizeof(int), st));
     // outputs of unused slots are defined
     COEX_CUDA(cudaMemsetAsync(d_grp, 0xff, H * sizeof(int), st));
     COEX_CUDA(cudaMemsetAsync(d_lab, 0xff, H * sizeof(int), st));
@@ -211,8 +212,8 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
         }
     }
     // ---- K4: groups, winners, densities -----------------------------------------------------
+    NetArgs na{};
     {
-        NetArgs na{};
         na.K = K; na.perm_off = c->d_perm_off.p; na.sc_off = c->d_sc_off.p; na.hit_rows = d_hits; na.scores = d_sc;
         na.N = c->N; na.n = c->n; na.raw = c->raw; na.raw_sum = c->raw_sum.p; na.raw_mean = c->raw_mean.p;
         na.raw_xx = c->raw_xx.p; na.rank2 = c->rank2.p; na.sx = c->sx.p; na.rawsum_pos = c->rawsum_pos.p;
@@ -224,15 +225,45 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
         na.n_groups = d_ng; na.group_of_hit = d_grp; na.group_label = d_lab; na.group_winner = d_win;
         na.group_density = d_dens; na.hit_score = d_aps;
         na.w_root = c->w_root.p; na.w_pos = c->w_pos.p; na.w_s1 = c->w_s1.p; na.w_d0 = c->w_d0.p; na.w_w = c->w_w.p;
-        na.w_best = c->w_best.p; na.w_cand = c->w_cand.p;
+        na.w_best = c->w_best.p; na.w_cand = c->w_cand.p; na.w_state = c->w_state.p; na.w_flags = c->w_state.p + K;
         na.P2max = T2max;
-        // sort/cluster arrays (24 B per padded hit) or the pass-1 staging tiles (8 warps x 32x17 doubles)
-        const size_t smem = std::max<size_t>((size_t)T2max * 24, 36 * 1024);
-        COEX_CUDA(cudaFuncSetAttribute(network_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        COEX_TRY(stage_begin(c, ST_NETWORK));
-        network_kernel<<<K, kNetThreads, smem, st>>>(na);
+    }
+    const unsigned warp_blocks = (unsigned)((H * 32 + 255) / 256), thread_blocks = (unsigned)((H + 255) / 256);
+    auto pass2_round = [&](bool last) -> int {
+        net_pass2_kernel<<<warp_blocks, 256, 0, st>>>(na, H);
+        net_pick_kernel<<<thread_blocks, 256, 0, st>>>(na, H);
+        if (last) COEX_CUDA(cudaMemsetAsync(na.w_flags, 0, sizeof(int), st));
+        net_commit_kernel<<<K, 256, 0, st>>>(na, 0);
         COEX_CUDA(cudaGetLastError());
-        COEX_TRY(stage_end(c, 1));
+        return 0;
+    };
+    auto density_tail = [&]() -> int {
+        const size_t rsmem = (size_t)T2max * 8;
+        net_density_kernel<<<warp_blocks, 256, 0, st>>>(na, H, 0);
+        net_removal_kernel<<<K, 256, rsmem, st>>>(na, 0);
+        if (!prm->noiter) net_density_kernel<<<warp_blocks, 256, 0, st>>>(na, H, 1);
+        net_removal_kernel<<<K, 256, rsmem, st>>>(na, 1);
+        COEX_CUDA(cudaGetLastError());
+        return 0;
+    };
+    const int kRounds = 8;
+    long long net_launches = 0;
+    if (H > 0) {
+        const size_t gsmem = (size_t)T2max * 24;
+        COEX_CUDA(cudaFuncSetAttribute(net_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+        COEX_CUDA(cudaFuncSetAttribute(net_removal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(T2max * 8)));
+        COEX_TRY(stage_begin(c, ST_NETWORK));
+        net_group_kernel<<<K, kNetThreads, gsmem, st>>>(na);
+        net_pass1_kernel<<<warp_blocks, 256, 0, st>>>(na, H);
+        net_pick_kernel<<<thread_blocks, 256, 0, st>>>(na, H);
+        net_commit_kernel<<<K, 256, 0, st>>>(na, 1);
+        COEX_CUDA(cudaGetLastError());
+        for (int r = 0; r < kRounds; ++r) COEX_TRY(pass2_round(r == kRounds - 1));
+        COEX_TRY(density_tail());
+        net_launches = 4 + 3 * kRounds + (prm->noiter ? 3 : 4);
+        COEX_TRY(stage_end(c, net_launches));
+    } else {
+        COEX_CUDA(cudaMemsetAsync(d_ng, 0, K * sizeof(int), st));
     }
     if (!on_device) {
         COEX_CUDA(cudaMemcpyAsync(n_groups, d_ng, K * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -246,6 +277,28 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
     }
     // perm_off / sc_off staging copies read host memory that dies with this frame
     COEX_CUDA(cudaStreamSynchronize(st));
+    if (H > 0) {
+        // pass 2 is a fixed-point iteration: kRounds rounds were queued without looking; in the rare
+        // case that some permutation was still moving, iterate to convergence and redo the tail.
+        int flag = 0;
+        COEX_CUDA(cudaMemcpy(&flag, na.w_flags, sizeof(int), cudaMemcpyDeviceToHost));
+        if (flag) {
+            for (int guard = 0; flag && guard < 8192 + 2; ++guard) {
+                COEX_TRY(pass2_round(true));
+                c->launches += 3;
+                COEX_CUDA(cudaStreamSynchronize(st));
+                COEX_CUDA(cudaMemcpy(&flag, na.w_flags, sizeof(int), cudaMemcpyDeviceToHost));
+            }
+            COEX_TRY(density_tail());
+            c->launches += 4;
+            if (!on_device) {
+                COEX_CUDA(cudaMemcpyAsync(group_winner, d_win, H * sizeof(int), cudaMemcpyDeviceToHost, st));
+                COEX_CUDA(cudaMemcpyAsync(group_density, d_dens, H * sizeof(double), cudaMemcpyDeviceToHost, st));
+                COEX_CUDA(cudaMemcpyAsync(hit_score, d_aps, H * sizeof(double), cudaMemcpyDeviceToHost, st));
+            }
+            COEX_CUDA(cudaStreamSynchronize(st));
+        }
+    }
     if (prm->measure == 0 && prm->use_specific_p && c->gemm_mode == 0) COEX_TRY(tc_check_error(c));
     return 0;
 }
@@ -350,7 +403,7 @@ int coex_destroy(coex_ctx *c) {
     c->d_perm_off.release(); c->d_sc_off.release(); c->d_hits.release(); c->d_ngroups.release(); c->d_grp.release();
     c->d_label.release(); c->d_win.release(); c->w_root.release(); c->w_pos.release(); c->d_dens.release();
     c->d_aps.release(); c->d_scores.release(); c->w_s1.release(); c->w_d0.release(); c->w_w.release();
-    c->d_counts.release(); c->w_best.release(); c->w_cand.release(); c->p_idxa.release(); c->p_idxb.release();
+    c->d_counts.release(); c->w_best.release(); c->w_cand.release(); c->w_state.release(); c->p_idxa.release(); c->p_idxb.release();
     c->p_out.release();
     cudaStreamDestroy(c->stream);
     delete c;

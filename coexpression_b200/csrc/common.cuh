@@ -112,7 +112,7 @@ struct coex_ctx {
     coex::DevBuf<int> strip;                  // S strip [Hs, N_pad] int32
     coex::DevBuf<double> strip_f64;           // Pearson null strip [Hs, N]
     coex::DevBuf<long long> d_perm_off, d_sc_off;
-    coex::DevBuf<int> d_hits, d_ngroups, d_grp, d_label, d_win, w_root, w_pos;
+    coex::DevBuf<int> d_hits, d_ngroups, d_grp, d_label, d_win, w_root, w_pos, w_state;
     coex::DevBuf<double> d_dens, d_aps, d_scores, w_s1, w_d0, w_w;
     coex::DevBuf<long long> d_counts;
     coex::DevBuf<unsigned long long> w_best, w_cand;

@@ -44,6 +44,8 @@ struct NetArgs {
     int *w_root, *w_pos;
     double *w_s1, *w_d0, *w_w;
     unsigned long long *w_best, *w_cand;
+    int *w_state;                // [K] 1 while the permutation's pass-2 iteration has not converged
+    int *w_flags;                // [1] bit 0: some permutation changed in the last committed round
     int P2max;
 };
 
@@ -103,15 +105,18 @@ __device__ double warp_correlation(const NetArgs &a, int ra, int rb, int lane) {
     return r;
 }
 
+// ===========================================================================================
+// K4a  net_group_kernel: one CTA per permutation -- join_nearby (coexfunctions.py:277-316)
+// ===========================================================================================
 __global__ void __launch_bounds__(kNetThreads)
-network_kernel(NetArgs a) {
+net_group_kernel(NetArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int k = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long off = a.perm_off[k];
     const int P = (int)(a.perm_off[k + 1] - off);
     if (P < 2) {                     // individualscores empty -> no groups (1-make-network.py:333-338)
-        if (tid == 0) a.n_groups[k] = 0;
+        if (tid == 0) { a.n_groups[k] = 0; a.w_state[k] = 0; }
         return;
     }
     int P2 = 1;
@@ -121,16 +126,12 @@ network_kernel(NetArgs a) {
     int *order = reinterpret_cast<int *>(ekey + a.P2max);                               // [P2]
     int *clend = order + a.P2max;                                                       // [P2]
     int *parent = reinterpret_cast<int *>(ekey);                                        // reuse after clustering
-    __shared__ int s_G, s_changed;
+    __shared__ int s_G;
 
     const int *hits = a.hit_rows + off;
-    const double *Sc = a.scores + a.sc_off[k];
     int *grp = a.group_of_hit + off;
-    int *label = a.group_label + off, *win = a.group_winner + off;
-    double *dens = a.group_density + off, *aps = a.hit_score + off;
-    int *root = a.w_root + off, *pos = a.w_pos + off;
-    double *s1 = a.w_s1 + off, *d0 = a.w_d0 + off, *wown = a.w_w + off;
-    unsigned long long *best = a.w_best + off, *cand = a.w_cand + off;
+    int *label = a.group_label + off;
+    int *root = a.w_root + off;
 
     // ---- (1) sort hits by (chromosome, start) ----------------------------------------------
     for (int p = tid; p < P2; p += kNetThreads) {
@@ -169,15 +170,23 @@ network_kernel(NetArgs a) {
     for (int p = tid; p < P; p += kNetThreads) parent[p] = p;     // indexed by hit position
     __syncthreads();
     // ---- (3) in-cluster pairs -> edges -> union-find (smaller name wins the root) ----------
+    // A warp owns sorted position s and walks its partners t in batches of 32: the correlations
+    // of the batch are formed cooperatively, then every lane bisects its own pair into the
+    // global list (32 independent chains) and links the two trees.
     for (int s = warp; s < P; s += kNetThreads / 32) {
         const int ha = order[s];
         const int ra = hits[ha];
-        for (int t = s + 1; t < clend[s]; ++t) {
-            const int hb = order[t];
-            const int rb = hits[hb];
-            const double r = warp_correlation(a, ra, rb, lane);
-            if (lane == 0) {
-                const long long idx = lower_bound_dev(a.glist, a.glist_len, r);
+        const int cend = clend[s];
+        for (int t0 = s + 1; t0 < cend; t0 += 32) {
+            const int nb = min(32, cend - t0);
+            double rmine = 0.0;
+            for (int b = 0; b < nb; ++b) {
+                const double r = warp_correlation(a, ra, hits[order[t0 + b]], lane);
+                if (lane == b) rmine = r;
+            }
+            if (lane < nb) {
+                const int hb = order[t0 + lane];
+                const long long idx = lower_bound_dev(a.glist, a.glist_len, rmine);
                 const double p1 = 1.0 - (double)idx / (double)a.glist_len;
                 double p = p1;
                 if (a.anticor) p = fmin(p1, (double)idx / (double)a.glist_len);
@@ -193,6 +202,7 @@ network_kernel(NetArgs a) {
                     }
                 }
             }
+            __syncwarp();
         }
     }
     __syncthreads();
@@ -217,152 +227,205 @@ network_kernel(NetArgs a) {
     __syncthreads();
     const int G = s_G;
     for (int p = tid; p < P; p += kNetThreads) grp[p] = clend[root[p]];
-    for (int g = tid; g < G; g += kNetThreads) { best[g] = 0ULL; cand[g] = ~0ULL; }
-    __syncthreads();
-    // ---- (5) pass 1: member score = sum over other-group hits, hit order -------------------
-    // One warp owns 32 rows; a 32 x 16 tile of the score matrix is staged through shared memory
-    // (coalesced 128-byte row segments in, one lane per row walking left to right out).
-    {
-        double *tile = reinterpret_cast<double *>(smem_raw) + warp * (32 * 17);   // [32][17] per warp
-        int *gcol = reinterpret_cast<int *>(reinterpret_cast<double *>(smem_raw) + (kNetThreads / 32) * (32 * 17)) + warp * 16;
-        const int half = lane >> 4, col = lane & 15;
-        for (int i0 = warp * 32; i0 < P; i0 += kNetThreads) {
-            const int i = i0 + lane;
-            const int gi = (i < P) ? grp[i] : -1;
-            double s = 0.0;
-            for (int j0 = 0; j0 < P; j0 += 16) {
-                __syncwarp();
-#pragma unroll 4
-                for (int r = half; r < 32; r += 2) {
-                    const int row = i0 + r, j = j0 + col;
-                    tile[r * 17 + col] = (row < P && j < P) ? Sc[(long long)row * P + j] : -1.0;
-                }
-                if (lane < 16) gcol[lane] = (j0 + lane < P) ? grp[j0 + lane] : gi;
-                __syncwarp();
-                if (i < P) {
-                    const int lim = min(16, P - j0);
-                    for (int c = 0; c < lim; ++c) {
-                        const double v = tile[lane * 17 + c];
-                        if ((j0 + c) != i && v >= a.thr && gcol[c] != gi) s = __dadd_rn(s, v);
-                    }
-                }
-            }
-            if (i < P) {
-                s1[i] = s;
-                atomicMax(&best[gi], (unsigned long long)__double_as_longlong(s));
-            }
+    for (int g = tid; g < P; g += kNetThreads) { a.w_best[off + g] = 0ULL; a.w_cand[off + g] = ~0ULL; }
+    if (tid == 0) { a.n_groups[k] = G; a.w_state[k] = 1; }
+}
+
+// ===========================================================================================
+// K4b..  grid-wide kernels: one warp per hit (or per group slot) of ANY permutation, so that a
+// large hit set is spread over the whole GPU instead of one SM.  All sums are left-to-right:
+// the 32 lanes fetch 32 consecutive addends, lane order is then folded in with shuffles.
+// Skipped addends are replaced by +0.0, which leaves a non-negative running sum bit-identical.
+// ===========================================================================================
+__device__ __forceinline__ int perm_of(const long long *perm_off, int K, long long q) {
+    int lo = 0, hi = K;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (perm_off[mid] <= q) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ double warp_ordered_add(double s, double v) {
+#pragma unroll
+    for (int l = 0; l < 32; ++l) s = __dadd_rn(s, __shfl_sync(0xffffffffu, v, l));
+    return s;
+}
+
+// pass 1 (1-make-network.py:365-375): member score over other-group hits, hit order
+__global__ void __launch_bounds__(256)
+net_pass1_kernel(NetArgs a, long long H) {
+    const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= H) return;
+    const int k = perm_of(a.perm_off, a.K, q);
+    const long long off = a.perm_off[k];
+    const int P = (int)(a.perm_off[k + 1] - off);
+    if (P < 2) return;
+    const int i = (int)(q - off);
+    const int *grp = a.group_of_hit + off;
+    const int gi = grp[i];
+    const double *row = a.scores + a.sc_off[k] + (long long)i * P;
+    double s = 0.0;
+    for (int j0 = 0; j0 < P; j0 += 32) {
+        const int j = j0 + lane;
+        double v = 0.0;
+        if (j < P && j != i) {
+            const double x = row[j];
+            if (x >= a.thr && grp[j] != gi) v = x;
+        }
+        s = warp_ordered_add(s, v);
+    }
+    if (lane == 0) {
+        a.w_s1[q] = s;
+        atomicMax(&a.w_best[off + gi], (unsigned long long)__double_as_longlong(s));
+    }
+}
+
+// argmax tie-break: among the members reaching the group's best sum, the smallest name
+__global__ void __launch_bounds__(256)
+net_pick_kernel(NetArgs a, long long H) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= H) return;
+    const int k = perm_of(a.perm_off, a.K, q);
+    if (!a.w_state[k]) return;
+    const long long off = a.perm_off[k];
+    if (a.perm_off[k + 1] - off < 2) return;
+    const int gi = a.group_of_hit[q];
+    if ((unsigned long long)__double_as_longlong(a.w_s1[q]) == a.w_best[off + gi])
+        atomicMin(&a.w_cand[off + gi],
+                  ((unsigned long long)(unsigned)a.name_rank[a.hit_rows[q]] << 32) | (unsigned)(q - off));
+}
+
+// one CTA per permutation: commit the picked winners.  first != 0: pass-1 winners (w1 + working
+// copy).  Otherwise one Gauss-Seidel fixed-point round (see net_pass2_kernel): state[k] stays 1
+// while any winner moved; when nothing moved the sums of this round are final (allpromoterscores).
+__global__ void __launch_bounds__(256)
+net_commit_kernel(NetArgs a, int first) {
+    const int k = blockIdx.x;
+    if (!a.w_state[k]) return;
+    const long long off = a.perm_off[k];
+    const int P = (int)(a.perm_off[k + 1] - off);
+    if (P < 2) { if (threadIdx.x == 0) a.w_state[k] = 0; return; }
+    const int G = a.n_groups[k];
+    int *win = a.group_winner + off, *w1 = a.w_pos + off;
+    int changed = 0;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        const int w = (int)(a.w_cand[off + g] & 0xffffffffULL);
+        if (first) { w1[g] = w; win[g] = w; }
+        else if (w != win[g]) { win[g] = w; changed = 1; }
+        a.w_best[off + g] = 0ULL;
+        a.w_cand[off + g] = ~0ULL;
+    }
+    changed = __syncthreads_or(changed);
+    if (!first) {
+        if (!changed)
+            for (int i = threadIdx.x; i < P; i += blockDim.x) a.hit_score[off + i] = a.w_s1[off + i];
+        if (threadIdx.x == 0) {
+            a.w_state[k] = changed;
+            if (changed) atomicOr(a.w_flags, 1);
         }
     }
-    __syncthreads();
-    for (int i = tid; i < P; i += kNetThreads) {
-        const int gi = grp[i];
-        if ((unsigned long long)__double_as_longlong(s1[i]) == best[gi])
-            atomicMin(&cand[gi], ((unsigned long long)(unsigned)a.name_rank[hits[i]] << 32) | (unsigned)i);
+}
+
+// pass 2 (1-make-network.py:378-434), one round of the lower-triangular fixed-point iteration:
+// member m of group g is scored against the CURRENT winners of groups < g and the pass-1
+// winners of groups > g.  Starting from the pass-1 winners, round r fixes at least the first r
+// groups, and the unique fixed point is the reference's sequential (Gauss-Seidel) result.
+__global__ void __launch_bounds__(256)
+net_pass2_kernel(NetArgs a, long long H) {
+    const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= H) return;
+    const int k = perm_of(a.perm_off, a.K, q);
+    if (!a.w_state[k]) return;
+    const long long off = a.perm_off[k];
+    const int P = (int)(a.perm_off[k + 1] - off);
+    if (P < 2) return;
+    const int i = (int)(q - off);
+    const int G = a.n_groups[k];
+    const int gi = a.group_of_hit[q];
+    const int *win = a.group_winner + off, *w1 = a.w_pos + off;
+    const double *row = a.scores + a.sc_off[k] + (long long)i * P;
+    double s = 0.0;
+    for (int h0 = 0; h0 < G; h0 += 32) {
+        const int h = h0 + lane;
+        double v = 0.0;
+        if (h < G && h != gi) v = row[h < gi ? win[h] : w1[h]];
+        s = warp_ordered_add(s, v);
     }
-    __syncthreads();
-    // pass-1 winners w1 (kept in pos[]) and the working copy win[]
-    for (int g = tid; g < G; g += kNetThreads) { const int w = (int)(cand[g] & 0xffffffffULL); pos[g] = w; win[g] = w; }
-    __syncthreads();
-    // ---- (6) pass 2: Gauss-Seidel over groups in group order -------------------------------
-    // The sequential rule "group g is scored against the FINAL winners of groups < g and the
-    // pass-1 winners of groups > g" is lower-triangular, so iterating
-    //     win_new[g] = argmax_m sum_h Sc[m][ h < g ? win_old[h] : w1[h] ]
-    // from win = w1 reaches the sequential result as its unique fixed point; after r rounds
-    // the first r groups are final, in practice a handful of rounds suffice.  The sums of the
-    // last round are exactly the sequential ones (allpromoterscores).
-    const int *w1 = pos;
-    for (int round = 0; round <= G; ++round) {
-        for (int g = tid; g < G; g += kNetThreads) { best[g] = 0ULL; cand[g] = ~0ULL; }
-        if (tid == 0) s_changed = 0;
-        __syncthreads();
-        for (int i = tid; i < P; i += kNetThreads) {
-            const int gi = grp[i];
-            const double *row = Sc + (long long)i * P;
-            double s = 0.0;
-            int h = 0;
-            for (; h + 4 <= gi; h += 4) {                  // groups before gi: current winners
-                const double v0 = row[win[h]], v1 = row[win[h + 1]], v2 = row[win[h + 2]], v3 = row[win[h + 3]];
-                s = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(s, v0), v1), v2), v3);
-            }
-            for (; h < gi; ++h) s = __dadd_rn(s, row[win[h]]);
-            h = gi + 1;
-            for (; h + 4 <= G; h += 4) {                   // groups after gi: pass-1 winners
-                const double v0 = row[w1[h]], v1 = row[w1[h + 1]], v2 = row[w1[h + 2]], v3 = row[w1[h + 3]];
-                s = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(s, v0), v1), v2), v3);
-            }
-            for (; h < G; ++h) s = __dadd_rn(s, row[w1[h]]);
-            s1[i] = s;
-            atomicMax(&best[gi], (unsigned long long)__double_as_longlong(s));
-        }
-        __syncthreads();
-        for (int i = tid; i < P; i += kNetThreads) {
-            const int gi = grp[i];
-            if ((unsigned long long)__double_as_longlong(s1[i]) == best[gi])
-                atomicMin(&cand[gi], ((unsigned long long)(unsigned)a.name_rank[hits[i]] << 32) | (unsigned)i);
-        }
-        __syncthreads();
-        int changed = 0;
-        for (int g = tid; g < G; g += kNetThreads) {
-            const int w = (int)(cand[g] & 0xffffffffULL);
-            if (w != win[g]) { win[g] = w; changed = 1; }
-        }
-        if (changed) s_changed = 1;
-        __syncthreads();
-        if (!s_changed) break;
-        __syncthreads();
+    if (lane == 0) {
+        a.w_s1[q] = s;
+        atomicMax(&a.w_best[off + gi], (unsigned long long)__double_as_longlong(s));
     }
-    for (int i = tid; i < P; i += kNetThreads) aps[i] = s1[i];
-    __syncthreads();
-    // ---- (7) indjoined row sums = density ---------------------------------------------------
-    const double gdiv = (double)G;
-    for (int g = tid; g < G; g += kNetThreads) {
-        const double *row = Sc + (long long)win[g] * P;
-        double s = 0.0;
-        for (int h = 0; h < G; ++h) {
-            if (h == g) continue;
-            const double v = row[win[h]];
-            if (v >= a.thr) s = __dadd_rn(s, v);
+}
+
+// density (1-make-network.py:437-462) and, with `removal`, the whittled sum of
+// 1-make-network.py:471-478: one warp per group slot
+__global__ void __launch_bounds__(256)
+net_density_kernel(NetArgs a, long long H, int removal) {
+    const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= H) return;
+    const int k = perm_of(a.perm_off, a.K, q);
+    const long long off = a.perm_off[k];
+    const int P = (int)(a.perm_off[k + 1] - off);
+    if (P < 2) return;
+    const int g = (int)(q - off);
+    const int G = a.n_groups[k];
+    if (g >= G) return;
+    const int *win = a.group_winner + off;
+    const int *vis = a.w_root + off;                 // visiting position (removal only)
+    const int pg = removal ? vis[g] : 0;
+    const double *row = a.scores + a.sc_off[k] + (long long)win[g] * P;
+    double s = 0.0;
+    for (int h0 = 0; h0 < G; h0 += 32) {
+        const int h = h0 + lane;
+        double v = 0.0;
+        if (h < G && h != g && !(removal && vis[h] < pg)) {
+            const double x = row[win[h]];
+            if (x >= a.thr) v = x;
         }
-        d0[g] = a.useaverage ? s / gdiv : s;
+        s = warp_ordered_add(s, v);
     }
+    if (lane == 0) {
+        const double d = a.useaverage ? s / (double)G : s;
+        if (removal) a.w_w[q] = d; else a.w_d0[q] = d;
+    }
+}
+
+// iterative removal bookkeeping, one CTA per permutation.
+// stage 0: visiting order by (density, label) descending (1-make-network.py:467)
+// stage 1: tie reuse, quirk Q7 (1-make-network.py:468-469) -> final densities
+__global__ void __launch_bounds__(256)
+net_removal_kernel(NetArgs a, int stage) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *d = reinterpret_cast<double *>(smem_raw);
+    const int k = blockIdx.x;
+    const long long off = a.perm_off[k];
+    if (a.perm_off[k + 1] - off < 2) return;
+    const int G = a.n_groups[k];
+    for (int g = threadIdx.x; g < G; g += blockDim.x) d[g] = a.w_d0[off + g];
     __syncthreads();
     if (a.noiter) {
-        for (int g = tid; g < G; g += kNetThreads) dens[g] = d0[g];
-    } else {
-        // ---- (8) iterative removal: order by (density, label) descending -------------------
-        for (int g = tid; g < G; g += kNetThreads) {
-            const double dg = d0[g];
-            int before = 0;                         // groups visited before g
+        if (stage == 1) for (int g = threadIdx.x; g < G; g += blockDim.x) a.group_density[off + g] = d[g];
+        return;
+    }
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        const double dg = d[g];
+        if (stage == 0) {
+            int before = 0;                            // groups visited before g
             for (int h = 0; h < G; ++h) {
-                const double dh = d0[h];
-                before += (dh > dg) || (dh == dg && h > g);   // larger label == larger group number
+                const double dh = d[h];
+                before += (dh > dg) || (dh == dg && h > g);     // larger label == larger group number
             }
-            root[g] = before;
-        }
-        __syncthreads();
-        for (int g = tid; g < G; g += kNetThreads) {
-            const double *row = Sc + (long long)win[g] * P;
-            const int pg = root[g];
-            double s = 0.0;
-            for (int h = 0; h < G; ++h) {
-                if (h == g || root[h] < pg) continue;          // h already cut
-                const double v = row[win[h]];
-                if (v >= a.thr) s = __dadd_rn(s, v);
-            }
-            wown[g] = a.useaverage ? s / gdiv : s;
-        }
-        __syncthreads();
-        // tie reuse (quirk Q7): a group whose un-whittled density equals its predecessor's
-        // inherits the predecessor's whittled value -> value of the head of its run.
-        for (int g = tid; g < G; g += kNetThreads) {
-            const double dg = d0[g];
-            int head = g;
-            for (int h = g + 1; h < G; ++h) if (d0[h] == dg) head = h;   // largest label in the run
-            // the first visited group compares against lastscore = -1, never equal
-            dens[g] = wown[head];
+            a.w_root[off + g] = before;
+        } else {
+            int head = g;                              // first visited group of the run of equal densities
+            for (int h = g + 1; h < G; ++h) if (d[h] == dg) head = h;
+            a.group_density[off + g] = a.w_w[off + head];
         }
     }
-    if (tid == 0) a.n_groups[k] = G;
 }
 
 }  // namespace coex
