@@ -57,6 +57,7 @@ SIGNATURES = {
     "coex_stage_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
                                      ctypes.POINTER(c_ll)]),
     "coex_set_gemm_mode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "coex_set_count_mode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "coex_set_workspace_mb": (ctypes.c_int, [ctypes.c_void_p, c_ll]),
     "coex_selftest_gemm": (ctypes.c_int, [ctypes.c_void_p, c_ll, ctypes.POINTER(c_ll), ctypes.POINTER(c_ll)]),
 }

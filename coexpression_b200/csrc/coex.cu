@@ -7,6 +7,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "count.cuh"
+#include "count_dedup.cuh"
 #include "network.cuh"
 #include "allpairs.cuh"
 
@@ -59,8 +60,111 @@ static int prepare_impl(coex_ctx *c) {
         c->raw, N, n, c->raw_sum.p, c->raw_mean.p, c->raw_xx.p, c->rawsum_pos.p);
     COEX_CUDA(cudaGetLastError());
     COEX_TRY(stage_end(c, 1));
+    COEX_TRY(c->icol.reserve(c->N_pad)); COEX_TRY(c->d_ndeg.reserve(1));
+    COEX_CUDA(cudaMemsetAsync(c->d_ndeg.p, 0, sizeof(int), c->stream));
+    icol_kernel<<<(unsigned)((c->N_pad + 255) / 256), 256, 0, c->stream>>>(c->sx.p, N, c->N_pad, c->icol.p, c->d_ndeg.p);
+    COEX_CUDA(cudaGetLastError());
+    c->launches += 1;
+    COEX_CUDA(cudaMemcpyAsync(&c->n_degenerate, c->d_ndeg.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    COEX_CUDA(cudaStreamSynchronize(c->stream));
     COEX_TRY(tc_invalidate(c));
     c->prepared = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// de-duplicated Spearman null: unique hit rows -> GEMM strips -> count_dedup_kernel
+// ------------------------------------------------------------------------------------------
+static int run_strip_gemm(coex_ctx *c, const int *d_rows, long long nq, long long nq_pad);
+
+static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const long long *perm_off,
+                               const int *h_hits, const int *d_hits, int Pmax, double *d_sc, long long *d_cn) {
+    const long long H = perm_off[K];
+    const long long N = c->N;
+    cudaStream_t st = c->stream;
+    // ---- counting sort of the queries by table row (host, O(N + H)) -------------------------------
+    std::vector<int> cnt((size_t)N + 1, 0);
+    for (long long q = 0; q < H; ++q) {
+        const int r = h_hits[q];
+        if (r < 0 || r >= N) COEX_FAIL("hit row out of range");
+        cnt[(size_t)r + 1]++;
+    }
+    std::vector<int> uniq; uniq.reserve((size_t)std::min<long long>(H, N));
+    std::vector<int> ustart;                         // start of each unique row's queries in qlist
+    std::vector<int> cursor((size_t)N, -1);
+    int acc = 0;
+    for (long long r = 0; r < N; ++r)
+        if (cnt[(size_t)r + 1]) { cursor[(size_t)r] = acc; ustart.push_back(acc); uniq.push_back((int)r); acc += cnt[(size_t)r + 1]; }
+    ustart.push_back(acc);
+    std::vector<int> qlist((size_t)H);
+    std::vector<int> Pq((size_t)H);
+    for (int k = 0; k < K; ++k)
+        for (long long q = perm_off[k]; q < perm_off[k + 1]; ++q) {
+            qlist[(size_t)cursor[(size_t)h_hits[q]]++] = (int)q;
+            Pq[(size_t)q] = (int)(perm_off[k + 1] - perm_off[k]);
+        }
+    const long long U = (long long)uniq.size();
+    const int Tcap = std::max(4096, (int)round_up(Pmax, 256));
+    // ---- strips of unique rows ------------------------------------------------------------------------
+    const long long ld = c->N_pad;
+    long long Us = (c->strip_mb << 20) / (ld * 4);
+    Us = std::max<long long>(256, Us / 256 * 256);
+    Us = std::min<long long>(Us, round_up(U, 256));
+    COEX_TRY(c->strip.reserve((size_t)Us * ld));
+    COEX_TRY(c->a_hi.reserve((size_t)Us * c->n_pad)); COEX_TRY(c->a_lo.reserve((size_t)Us * c->n_pad));
+    COEX_TRY(c->dd_uniq.reserve((size_t)std::max<long long>(U, 1))); COEX_TRY(c->dd_qlist.reserve((size_t)std::max<long long>(H, 1)));
+    COEX_CUDA(cudaMemcpyAsync(c->dd_uniq.p, uniq.data(), U * sizeof(int), cudaMemcpyHostToDevice, st));
+    COEX_CUDA(cudaMemcpyAsync(c->dd_qlist.p, qlist.data(), H * sizeof(int), cudaMemcpyHostToDevice, st));
+    // ---- work items: (unique row, run of its queries whose statistics fit Tcap) -------------------------
+    std::vector<DedupItem> items;
+    std::vector<long long> strip_item_begin;
+    int Qcap = 2;
+    for (long long u0 = 0; u0 < U; u0 += Us) {
+        strip_item_begin.push_back((long long)items.size());
+        const long long u1 = std::min(U, u0 + Us);
+        for (long long u = u0; u < u1; ++u) {
+            int qb = ustart[(size_t)u];
+            const int qend = ustart[(size_t)u + 1];
+            while (qb < qend) {
+                int qe = qb, T = 0;
+                while (qe < qend && (qe == qb || T + Pq[(size_t)qlist[(size_t)qe]] <= Tcap)) { T += Pq[(size_t)qlist[(size_t)qe]]; ++qe; }
+                items.push_back(DedupItem{(int)(u - u0), qb, qe, T});
+                Qcap = std::max(Qcap, qe - qb);
+                qb = qe;
+            }
+        }
+    }
+    strip_item_begin.push_back((long long)items.size());
+    Qcap = (Qcap + 1) & ~1;
+    COEX_TRY(c->dd_items.reserve(std::max<size_t>(items.size(), 1) * sizeof(DedupItem)));
+    COEX_CUDA(cudaMemcpyAsync(c->dd_items.p, items.data(), items.size() * sizeof(DedupItem), cudaMemcpyHostToDevice, st));
+    const size_t smem = dedup_smem_bytes(Tcap, Qcap);
+    if (smem > 227 * 1024) COEX_FAIL("count_dedup: too many queries of one table row for shared memory");
+    COEX_CUDA(cudaFuncSetAttribute(count_dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_dedup_kernel, kDdThreads, smem));
+    const int grid_max = std::max(1, per_sm) * c->sm_count;
+    COEX_TRY(c->dd_gthr.reserve((size_t)grid_max * Tcap)); COEX_TRY(c->dd_gorg.reserve((size_t)grid_max * Tcap));
+    size_t s_idx = 0;
+    for (long long u0 = 0; u0 < U; u0 += Us, ++s_idx) {
+        const long long nu = std::min(Us, U - u0);
+        COEX_TRY(run_strip_gemm(c, c->dd_uniq.p + u0, nu, round_up(nu, 256)));
+        DedupArgs da{};
+        da.strip = c->strip.p; da.ld = ld;
+        da.items = reinterpret_cast<const DedupItem *>(c->dd_items.p) + strip_item_begin[s_idx];
+        da.n_items = (int)(strip_item_begin[s_idx + 1] - strip_item_begin[s_idx]);
+        da.uniq_rows = c->dd_uniq.p + u0; da.qlist = c->dd_qlist.p;
+        da.perm_off = c->d_perm_off.p; da.sc_off = c->d_sc_off.p; da.K = K; da.hit_rows = d_hits;
+        da.sx = c->sx.p; da.icol = c->icol.p; da.rawsum_pos = c->rawsum_pos.p; da.N = N;
+        da.n_degenerate = c->n_degenerate; da.anticor = prm->anticorrelation; da.scores = d_sc; da.counts = d_cn;
+        da.Tcap = Tcap; da.Qcap = Qcap; da.g_thr = c->dd_gthr.p; da.g_org = c->dd_gorg.p;
+        COEX_TRY(stage_begin(c, ST_COUNT));
+        count_dedup_kernel<<<std::min(grid_max, std::max(da.n_items, 1)), kDdThreads, smem, st>>>(da);
+        COEX_CUDA(cudaGetLastError());
+        COEX_TRY(stage_end(c, 1));
+    }
+    // the host vectors above feed async copies: they must be consumed before this frame dies
+    COEX_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
 
@@ -169,6 +273,17 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
                 COEX_CUDA(cudaGetLastError());
                 COEX_TRY(stage_end(c, 1));
             }
+            if (prm->measure == 0 && c->count_mode == 0) {
+                std::vector<int> hh;
+                const int *h_hits = hit_rows;
+                if (on_device) {
+                    hh.resize((size_t)H);
+                    COEX_CUDA(cudaMemcpyAsync(hh.data(), d_hits, H * sizeof(int), cudaMemcpyDeviceToHost, st));
+                    COEX_CUDA(cudaStreamSynchronize(st));
+                    h_hits = hh.data();
+                }
+                COEX_TRY(spearman_dedup_path(c, prm, K, perm_off, h_hits, d_hits, Pmax, d_sc, d_cn));
+            } else {
             const size_t smem = (size_t)T2max * 16;
             COEX_CUDA(cudaFuncSetAttribute(count_score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             COEX_CUDA(cudaFuncSetAttribute(count_score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -196,6 +311,7 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
                 }
                 COEX_CUDA(cudaGetLastError());
                 COEX_TRY(stage_end(c, 1));
+            }
             }
         } else {
             // ---- nsp == 0: whole-distribution p from the global list -------------------------
@@ -404,7 +520,8 @@ int coex_destroy(coex_ctx *c) {
     c->d_label.release(); c->d_win.release(); c->w_root.release(); c->w_pos.release(); c->d_dens.release();
     c->d_aps.release(); c->d_scores.release(); c->w_s1.release(); c->w_d0.release(); c->w_w.release();
     c->d_counts.release(); c->w_best.release(); c->w_cand.release(); c->w_state.release(); c->p_idxa.release(); c->p_idxb.release();
-    c->p_out.release();
+    c->p_out.release(); c->icol.release(); c->d_ndeg.release(); c->dd_uniq.release(); c->dd_qlist.release();
+    c->dd_items.release(); c->dd_gthr.release(); c->dd_gorg.release();
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -548,6 +665,13 @@ int coex_set_gemm_mode(coex_ctx *c, int mode) {
     if (!c) COEX_FAIL("null context");
     if (mode != 0 && mode != 1) COEX_FAIL("coex_set_gemm_mode: 0 = tcgen05, 1 = SIMT dp4a");
     c->gemm_mode = mode;
+    return 0;
+}
+
+int coex_set_count_mode(coex_ctx *c, int mode) {
+    if (!c) COEX_FAIL("null context");
+    if (mode != 0 && mode != 1) COEX_FAIL("coex_set_count_mode: 0 = de-duplicated bucket kernel, 1 = per-query kernel");
+    c->count_mode = mode;
     return 0;
 }
 

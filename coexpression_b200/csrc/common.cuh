@@ -116,6 +116,14 @@ struct coex_ctx {
     coex::DevBuf<double> d_dens, d_aps, d_scores, w_s1, w_d0, w_w;
     coex::DevBuf<long long> d_counts;
     coex::DevBuf<unsigned long long> w_best, w_cand;
+    coex::DevBuf<float> icol;                 // [N_pad] (float)(0.5/sx), 0 for zero-variance rows
+    coex::DevBuf<int> d_ndeg;                 // [1]
+    int n_degenerate = 0;
+    coex::DevBuf<int> dd_uniq, dd_qlist;      // de-duplicated query rows
+    coex::DevBuf<unsigned char> dd_items;     // DedupItem[]
+    coex::DevBuf<double> dd_gthr;
+    coex::DevBuf<unsigned int> dd_gorg;
+    int count_mode = 0;                       // 0 = de-duplicated bucket kernel, 1 = per-query binary-search kernel
     coex::DevBuf<int> p_idxa, p_idxb;         // coex_pairs staging
     coex::DevBuf<double> p_out;
     long long strip_mb = 1024;

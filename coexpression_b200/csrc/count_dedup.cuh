@@ -1,0 +1,311 @@
+// count_dedup.cuh -- K3 epilogue stage, production version for the Spearman null.
+//
+// Same contract as count.cuh (reference 1-make-network.py:239-258, 273-327) with three changes
+// that remove the work the ncu capture of round 1 showed to dominate (profiles/r01_summary.md):
+//
+//  1. De-duplication.  The null values of a table row do not depend on the permutation, only
+//     the statistics (thresholds) do, and the same row is hit by several permutations.  Work
+//     items are therefore (unique row, a set of its (permutation, hit position) queries): the
+//     row is correlated and streamed ONCE and searched against the merged statistics of all
+//     its queries.  Quirk Q1 (the null list of hit position i omits table column i) becomes a
+//     per-query correction: idx = #{all columns below t} - [value at column i below t].
+//  2. Bucket table instead of a 10..13-step binary search: statistics are counting-sorted into
+//     4096 uniform buckets of [-1, 1] (ranked inside their bucket), a streamed value finds its
+//     bucket with one multiply and searches only the few statistics sharing it.
+//  3. fp32 pre-filter with exact fp64 refinement: the value and the bucket search are done in
+//     float; whenever the float result could differ from the double one (value within 5e-7 of a
+//     statistic or of a bucket edge, ~1-2 % of values) the column is queued and redone in double
+//     with the reference's exact arithmetic.  Counts are therefore still EXACT.
+#pragma once
+#include "common.cuh"
+#include "count.cuh"
+
+namespace coex {
+
+constexpr int kDdThreads = 256;
+constexpr int kDdBuckets = 4096;
+constexpr int kDdQueue = 2048;
+constexpr float kDdDelta = 5e-7f;        // |v32 - v64| <= 3e-7, |t32 - t64| <= 6e-8  
+constexpr float kDdEdge = 2e-3f;         // same bound in bucket units (x 2048) with margin
+
+struct DedupItem {
+    int urow;        // index into the strip (unique-row slot)
+    int qb, qe;      // range in qlist
+    int T;           // number of statistics of this item (upper bound: sum (P-1))
+};
+
+struct DedupArgs {
+    const int *strip;               // [rows_in_strip, ld]
+    long long ld;
+    const DedupItem *items;         // items of this launch
+    int n_items;
+    const int *uniq_rows;           // table row of each unique-row slot of the strip
+    const int *qlist;               // flat hit indices grouped by unique row
+    const long long *perm_off, *sc_off;
+    int K;
+    const int *hit_rows;
+    const double *sx;               // [N_pad]
+    const float *icol;              // [N_pad] (float)(0.5 / sx), 0 for zero-variance / padding rows
+    const unsigned char *rawsum_pos;
+    long long N;
+    int n_degenerate;               // zero-variance table rows: their null value is -99 for every query
+    int anticor;
+    double *scores;
+    long long *counts;
+    int Tcap, Qcap;                 // shared-memory capacities (statistics, queries per item)
+    double *g_thr;                  // scratch [gridDim.x, Tcap]
+    unsigned int *g_org;            // scratch [gridDim.x, Tcap]
+};
+
+__device__ __forceinline__ int dd_bucket64(double t) {
+    int b = (int)((t + 1.0) * (double)(kDdBuckets / 2));
+    return b < 0 ? 0 : (b >= kDdBuckets ? kDdBuckets - 1 : b);
+}
+
+__global__ void __launch_bounds__(kDdThreads)
+count_dedup_kernel(DedupArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: thr64[Tcap] | thr32[Tcap] | org[Tcap] | hist[Tcap+4] (= cursor[B]) | lut[B+4] | queue[kDdQueue] | qmeta
+    double *thr64 = reinterpret_cast<double *>(smem_raw);
+    float *thr32 = reinterpret_cast<float *>(thr64 + a.Tcap);
+    unsigned int *org = reinterpret_cast<unsigned int *>(thr32 + a.Tcap);
+    unsigned int *hist = org + a.Tcap;
+    unsigned int *lut = hist + a.Tcap + 4;
+    unsigned int *cursor = hist;                 // bucket cursors alias hist (dead until step C; Tcap >= 4096)
+    int *queue = reinterpret_cast<int *>(lut + kDdBuckets + 4);
+    int *q_k = queue + kDdQueue;                 // [Qcap] permutation
+    int *q_i = q_k + a.Qcap;                     // [Qcap] hit position
+    int *q_toff = q_i + a.Qcap;                  // [Qcap+1] offset of the query's statistics in the item
+    double *q_vi = reinterpret_cast<double *>(q_toff + a.Qcap + 2);   // [Qcap] exact null value at the skipped column
+    __shared__ int s_T, s_qn;
+    __shared__ unsigned int s_warp[kDdThreads / 32];
+
+    const int tid = threadIdx.x;
+    double *g_thr = a.g_thr + (long long)blockIdx.x * a.Tcap;
+    unsigned int *g_org = a.g_org + (long long)blockIdx.x * a.Tcap;
+
+    for (int it = blockIdx.x; it < a.n_items; it += gridDim.x) {
+        const DedupItem item = a.items[it];
+        const int nq = item.qe - item.qb;
+        const int u = a.uniq_rows[item.urow];
+        const int *srow = a.strip + (long long)item.urow * a.ld;
+        const double sxu = a.sx[u];
+        const bool posu = a.rawsum_pos[u] != 0;
+        __syncthreads();                                   // previous item fully retired
+        // ---- A. query metadata ----------------------------------------------------------------
+        for (int ql = tid; ql < nq; ql += kDdThreads) {
+            const long long q = a.qlist[item.qb + ql];
+            int lo = 0, hi = a.K;
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (a.perm_off[mid] <= q) lo = mid; else hi = mid; }
+            q_k[ql] = lo;
+            const int i = (int)(q - a.perm_off[lo]);
+            q_i[ql] = i;
+            double vi = -99.0;                             // null value at table column i (quirk Q1)
+            const double sxc = a.sx[i];
+            if (sxu != 0.0 && sxc != 0.0) vi = __ddiv_rn(0.25 * (double)srow[i], __dmul_rn(sxu, sxc));
+            q_vi[ql] = vi;
+        }
+        if (tid == 0) { s_T = 0; s_qn = 0; }
+        for (int b = tid; b <= kDdBuckets; b += kDdThreads) lut[b] = 0;
+        __syncthreads();
+        if (tid == 0) {
+            int acc = 0;
+            for (int ql = 0; ql < nq; ++ql) {
+                q_toff[ql] = acc;
+                acc += (int)(a.perm_off[q_k[ql] + 1] - a.perm_off[q_k[ql]]);       // P (diagonal included)
+            }
+            q_toff[nq] = acc;
+        }
+        __syncthreads();
+        const int TP = q_toff[nq];
+        // ---- B. statistics: pass 1 counts per bucket, pass 2 groups them ----------------------------
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int t = tid; t < TP; t += kDdThreads) {
+                int lo = 0, hi = nq;
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (q_toff[mid] <= t) lo = mid; else hi = mid; }
+                const int ql = lo, j = t - q_toff[ql];
+                const int k = q_k[ql], i = q_i[ql];
+                const long long off = a.perm_off[k];
+                const int P = (int)(a.perm_off[k + 1] - off);
+                double *sc = a.scores + a.sc_off[k] + (long long)i * P;
+                long long *cn = a.counts ? a.counts + a.sc_off[k] + (long long)i * P : nullptr;
+                if (j == i) { if (pass == 0) { sc[j] = 0.0; if (cn) cn[j] = -1; } continue; }
+                const int c = a.hit_rows[off + j];
+                double r = -99.0;
+                if (posu && a.rawsum_pos[c]) {                              // coexfunctions.py:389
+                    r = __ddiv_rn(0.25 * (double)srow[c], __dmul_rn(sxu, a.sx[c]));
+                    if (r != r) r = -99.0;                                  // coexfunctions.py:406-408
+                }
+                if (r == -99.0) {                                           // 1-make-network.py:284-285
+                    if (pass == 0) { sc[j] = -log10(1.0); if (cn) cn[j] = -1; }
+                    continue;
+                }
+                const int b = dd_bucket64(r);
+                if (pass == 0) {
+                    atomicAdd(&lut[b], 1u);
+                } else {
+                    const unsigned int pos = lut[b] + atomicAdd(&cursor[b], 1u);
+                    g_thr[pos] = r;
+                    g_org[pos] = ((unsigned int)ql << 13) | (unsigned int)j;
+                }
+            }
+            __syncthreads();
+            if (pass == 0) {
+                // exclusive scan of the 4096 bucket counts (16 per thread + block scan)
+                constexpr int per = kDdBuckets / kDdThreads;
+                unsigned int loc[per], sum = 0;
+#pragma unroll
+                for (int e = 0; e < per; ++e) { loc[e] = lut[tid * per + e]; sum += loc[e]; }
+                unsigned int incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const unsigned int x = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += x; }
+                if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+                __syncthreads();
+                unsigned int base = incl - sum;
+                for (int w = 0; w < (tid >> 5); ++w) base += s_warp[w];
+#pragma unroll
+                for (int e = 0; e < per; ++e) { lut[tid * per + e] = base; cursor[tid * per + e] = 0; base += loc[e]; }
+                if (tid == kDdThreads - 1) { lut[kDdBuckets] = base; s_T = (int)base; }
+                __syncthreads();
+            }
+        }
+        const int T = s_T;
+        if (T == 0) continue;                               // every statistic undefined: scores already written
+        __threadfence_block();
+        // ---- C. rank inside the bucket -> fully sorted statistics in shared memory ----------------
+        for (int e = tid; e < T; e += kDdThreads) {
+            const double t = g_thr[e];
+            const int b = dd_bucket64(t);
+            const int lo = (int)lut[b], hi = (int)lut[b + 1];
+            int rank = 0;
+            for (int m = lo; m < hi; ++m) {
+                const double x = g_thr[m];
+                rank += (x < t) || (x == t && m < e);
+            }
+            thr64[lo + rank] = t;
+            thr32[lo + rank] = (float)t;
+            org[lo + rank] = g_org[e];
+        }
+        for (int p = tid; p <= T; p += kDdThreads) hist[p] = 0;
+        __syncthreads();
+        // ---- D. stream the null values of table row u (fp32 fast path) -----------------------------
+        const float iu = (float)(0.5 / sxu);
+        const long long N = a.N;
+        for (long long c0 = (long long)tid * 4; c0 < N; c0 += kDdThreads * 4) {
+            const int4 s4 = *reinterpret_cast<const int4 *>(srow + c0);
+            const float4 w4 = *reinterpret_cast<const float4 *>(a.icol + c0);
+            const int sv[4] = {s4.x, s4.y, s4.z, s4.w};
+            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (wv[e] == 0.0f || c0 + e >= N) continue;            // zero-variance column: -99, counted in bulk
+                const float v = __int2float_rn(sv[e]) * (iu * wv[e]);
+                const float f = (v + 1.0f) * (float)(kDdBuckets / 2);
+                int b = (int)f;
+                const float fr = f - floorf(f);
+                bool amb = (fr < kDdEdge) || (fr > 1.0f - kDdEdge);
+                b = b < 0 ? 0 : (b >= kDdBuckets ? kDdBuckets - 1 : b);
+                int lo = (int)lut[b];
+                const int hi = (int)lut[b + 1];
+                int p = lo;
+                if (!amb) {
+                    // statistics of this bucket: count those <= v, flag any within delta
+                    int len = hi - lo;
+                    while (len > 0) {
+                        const int half = len >> 1;
+                        if (thr32[p + half] <= v) { p += half + 1; len -= half + 1; } else len = half;
+                    }
+                    if (p > lo && v - thr32[p - 1] < kDdDelta) amb = true;
+                    if (p < hi && thr32[p] - v < kDdDelta) amb = true;
+                }
+                if (!amb) {
+                    atomicAdd(&hist[p], 1u);
+                } else {
+                    const int slot = atomicAdd(&s_qn, 1);
+                    if (slot < kDdQueue) {
+                        queue[slot] = (int)(c0 + e);
+                    } else {                                                  // queue full: refine in place
+                        const double vv = __ddiv_rn(0.25 * (double)sv[e], __dmul_rn(sxu, a.sx[c0 + e]));
+                        const int bb = dd_bucket64(vv);
+                        int pp = (int)lut[bb];
+                        int len = (int)lut[bb + 1] - pp;
+                        while (len > 0) {
+                            const int half = len >> 1;
+                            if (thr64[pp + half] <= vv) { pp += half + 1; len -= half + 1; } else len = half;
+                        }
+                        atomicAdd(&hist[pp], 1u);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- E. exact refinement of the queued columns ------------------------------------------
+        const int qn = min(s_qn, kDdQueue);
+        for (int x = tid; x < qn; x += kDdThreads) {
+            const int c = queue[x];
+            const double vv = __ddiv_rn(0.25 * (double)srow[c], __dmul_rn(sxu, a.sx[c]));
+            const int bb = dd_bucket64(vv);
+            int pp = (int)lut[bb];
+            int len = (int)lut[bb + 1] - pp;
+            while (len > 0) {
+                const int half = len >> 1;
+                if (thr64[pp + half] <= vv) { pp += half + 1; len -= half + 1; } else len = half;
+            }
+            atomicAdd(&hist[pp], 1u);
+        }
+        __syncthreads();
+        // ---- F. inclusive prefix sum of hist[0..T), scores ----------------------------------------
+        {
+            const int per = (T + 1 + kDdThreads - 1) / kDdThreads;
+            const int b0 = tid * per, b1 = min(b0 + per, T + 1);
+            unsigned int local = 0;
+            for (int p = b0; p < b1; ++p) local += hist[p];
+            unsigned int incl = local;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned int x = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += x; }
+            if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+            __syncthreads();
+            unsigned int base = incl - local;
+            for (int w = 0; w < (tid >> 5); ++w) base += s_warp[w];
+            for (int p = b0; p < b1; ++p) { base += hist[p]; hist[p] = base; }
+        }
+        __syncthreads();
+        for (int s = tid; s < T; s += kDdThreads) {
+            const unsigned int o = org[s];
+            const int ql = (int)(o >> 13), j = (int)(o & 8191u);
+            const int k = q_k[ql], i = q_i[ql];
+            const int P = (int)(a.perm_off[k + 1] - a.perm_off[k]);
+            const double t = thr64[s];
+            // all columns strictly below t: streamed values + zero-variance columns (-99 < t always),
+            // minus the skipped column i of this query if it is below t (quirk Q1)
+            long long idx = (long long)hist[s] + a.n_degenerate;
+            long long len = N;
+            if (i < N) { len = N - 1; if (q_vi[ql] < t) idx -= 1; }
+            const long long w = a.sc_off[k] + (long long)i * P + j;
+            a.scores[w] = edge_score_dev(idx, len, a.anticor);
+            if (a.counts) a.counts[w] = idx;
+        }
+    }
+}
+
+// float reciprocal half-norms for the fp32 fast path + number of zero-variance rows
+__global__ void icol_kernel(const double *__restrict__ sx, long long N, long long N_pad, float *__restrict__ icol,
+                            int *__restrict__ n_degenerate) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int deg = 0;
+    if (t < N_pad) {
+        const double s = sx[t];
+        const bool ok = (t < N) && (s != 0.0);
+        icol[t] = ok ? (float)(0.5 / s) : 0.0f;
+        deg = (t < N && s == 0.0) ? 1 : 0;
+    }
+    deg = __syncthreads_count(deg);
+    if (threadIdx.x == 0 && deg) atomicAdd(n_degenerate, deg);
+}
+
+inline size_t dedup_smem_bytes(int Tcap, int Qcap) {
+    return (size_t)Tcap * 8 + (size_t)Tcap * 4 * 2 + (size_t)(Tcap + 4) * 4 + (size_t)(kDdBuckets + 4) * 4 +
+           (size_t)kDdQueue * 4 + (size_t)Qcap * 4 * 2 + (size_t)(Qcap + 2) * 4 + (size_t)Qcap * 8 + 16;
+}
+
+}  // namespace coex

@@ -119,6 +119,8 @@ long long coex_launch_count(coex_ctx *ctx);
 int coex_stage_ms(coex_ctx *ctx, int stage, double *ms, long long *launches);
 /* 0 = tcgen05/TMA tensor-core GEMM, 1 = SIMT dp4a GEMM (validation path) */
 int coex_set_gemm_mode(coex_ctx *ctx, int mode);
+/* 0 = de-duplicated bucket-table count kernel (default), 1 = per-query binary-search kernel */
+int coex_set_count_mode(coex_ctx *ctx, int mode);
 int coex_set_workspace_mb(coex_ctx *ctx, long long strip_mb);
 /* On-device cross-check: the first m_rows table rows against the whole table through the tcgen05
  * kernel and through the dp4a kernel; *mismatches = differing int32 dot products,

@@ -117,7 +117,7 @@ NETWORK_CASES = ["spearman_default", "spearman_anticor", "spearman_noiter_j001",
                  "spearman_global_nsp0", "pearson_default", "pearson_anticor_j05"]
 
 
-def _run_case(name, gemm_mode):
+def _run_case(name, gemm_mode, count_mode="dedup"):
     from coexpression_b200.api import CoexContext, Options
     from coexpression_b200.results import perm_objects
     with open(os.path.join(GOLDEN, f"network_{name}.json")) as f:
@@ -129,6 +129,7 @@ def _run_case(name, gemm_mode):
     opts = Options(**kw)
     with CoexContext() as ctx:
         ctx.set_gemm_mode(gemm_mode)
+        ctx.set_count_mode(count_mode)
         ctx.set_expression(inp["X"]); ctx.prepare()
         ctx.set_features(inp["chrom"], inp["start"], inp["end"], names)
         ctx.set_global_list(inp["glist"])
@@ -155,6 +156,11 @@ def test_network_golden_tcgen05(name):
 @pytest.mark.parametrize("name", ["spearman_default", "spearman_anticor"])
 def test_network_golden_dp4a(name):
     _run_case(name, "simt")
+
+
+@pytest.mark.parametrize("name", ["spearman_default", "spearman_anticor", "spearman_useavg_m"])
+def test_network_golden_per_query_count_kernel(name):
+    _run_case(name, "tcgen05", "per_query")
 
 
 def test_network_against_live_oracle_small_shape():
