@@ -144,7 +144,11 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     int per_sm = 1;
     COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_dedup_kernel, kDdThreads, smem));
     const int grid_max = std::max(1, per_sm) * c->sm_count;
-    COEX_TRY(c->dd_gthr.reserve((size_t)grid_max * Tcap)); COEX_TRY(c->dd_gorg.reserve((size_t)grid_max * Tcap));
+    COEX_TRY(c->dd_gthr.reserve((size_t)grid_max * Tcap * 3)); COEX_TRY(c->dd_gorg.reserve((size_t)grid_max * Tcap * 2));
+    COEX_TRY(c->dd_tab.reserve((size_t)N + 1));
+    score_table_kernel<<<(unsigned)((N + 256) / 256), 256, 0, st>>>(c->dd_tab.p, N, prm->anticorrelation);
+    COEX_CUDA(cudaGetLastError());
+    c->launches += 1;
     size_t s_idx = 0;
     for (long long u0 = 0; u0 < U; u0 += Us, ++s_idx) {
         const long long nu = std::min(Us, U - u0);
@@ -157,7 +161,7 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
         da.perm_off = c->d_perm_off.p; da.sc_off = c->d_sc_off.p; da.K = K; da.hit_rows = d_hits;
         da.sx = c->sx.p; da.icol = c->icol.p; da.rawsum_pos = c->rawsum_pos.p; da.N = N;
         da.n_degenerate = c->n_degenerate; da.anticor = prm->anticorrelation; da.scores = d_sc; da.counts = d_cn;
-        da.Tcap = Tcap; da.Qcap = Qcap; da.g_thr = c->dd_gthr.p; da.g_org = c->dd_gorg.p;
+        da.Tcap = Tcap; da.Qcap = Qcap; da.g_thr = c->dd_gthr.p; da.g_org = c->dd_gorg.p; da.score_tab = c->dd_tab.p;
         COEX_TRY(stage_begin(c, ST_COUNT));
         count_dedup_kernel<<<std::min(grid_max, std::max(da.n_items, 1)), kDdThreads, smem, st>>>(da);
         COEX_CUDA(cudaGetLastError());
@@ -521,7 +525,7 @@ int coex_destroy(coex_ctx *c) {
     c->d_aps.release(); c->d_scores.release(); c->w_s1.release(); c->w_d0.release(); c->w_w.release();
     c->d_counts.release(); c->w_best.release(); c->w_cand.release(); c->w_state.release(); c->p_idxa.release(); c->p_idxb.release();
     c->p_out.release(); c->icol.release(); c->d_ndeg.release(); c->dd_uniq.release(); c->dd_qlist.release();
-    c->dd_items.release(); c->dd_gthr.release(); c->dd_gorg.release();
+    c->dd_items.release(); c->dd_gthr.release(); c->dd_gorg.release(); c->dd_tab.release();
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;

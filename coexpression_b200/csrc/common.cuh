@@ -121,7 +121,7 @@ struct coex_ctx {
     int n_degenerate = 0;
     coex::DevBuf<int> dd_uniq, dd_qlist;      // de-duplicated query rows
     coex::DevBuf<unsigned char> dd_items;     // DedupItem[]
-    coex::DevBuf<double> dd_gthr;
+    coex::DevBuf<double> dd_gthr, dd_tab;
     coex::DevBuf<unsigned int> dd_gorg;
     int count_mode = 0;                       // 0 = de-duplicated bucket kernel, 1 = per-query binary-search kernel
     coex::DevBuf<int> p_idxa, p_idxb;         // coex_pairs staging

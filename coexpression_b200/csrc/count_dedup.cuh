@@ -53,8 +53,9 @@ struct DedupArgs {
     double *scores;
     long long *counts;
     int Tcap, Qcap;                 // shared-memory capacities (statistics, queries per item)
-    double *g_thr;                  // scratch [gridDim.x, Tcap]
-    unsigned int *g_org;            // scratch [gridDim.x, Tcap]
+    double *g_thr;                  // scratch [gridDim.x, 3, Tcap]: unsorted | grouped | sorted statistics
+    unsigned int *g_org;            // scratch [gridDim.x, 2, Tcap]: grouped | sorted origins
+    const double *score_tab;        // [N+1] edge score of every possible bisect index (len = N-1)
 };
 
 __device__ __forceinline__ int dd_bucket64(double t) {
@@ -65,24 +66,27 @@ __device__ __forceinline__ int dd_bucket64(double t) {
 __global__ void __launch_bounds__(kDdThreads)
 count_dedup_kernel(DedupArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: thr64[Tcap] | thr32[Tcap] | org[Tcap] | hist[Tcap+4] (= cursor[B]) | lut[B+4] | queue[kDdQueue] | qmeta
-    double *thr64 = reinterpret_cast<double *>(smem_raw);
-    float *thr32 = reinterpret_cast<float *>(thr64 + a.Tcap);
-    unsigned int *org = reinterpret_cast<unsigned int *>(thr32 + a.Tcap);
-    unsigned int *hist = org + a.Tcap;
+    // layout: q_vi[Qcap] | thr32[Tcap] | hist[Tcap+4] (= cursor[B]) | lut[B+4] | queue[kDdQueue] | q_k q_i q_toff
+    // (the double statistics and their origins live in an L2-resident per-CTA scratch: they are only
+    //  touched by the rare exact refinements and by the final scoring)
+    double *q_vi = reinterpret_cast<double *>(smem_raw);                      // [Qcap] exact null value at the skipped column
+    float *thr32 = reinterpret_cast<float *>(q_vi + a.Qcap);
+    unsigned int *hist = reinterpret_cast<unsigned int *>(thr32 + a.Tcap);
     unsigned int *lut = hist + a.Tcap + 4;
     unsigned int *cursor = hist;                 // bucket cursors alias hist (dead until step C; Tcap >= 4096)
     int *queue = reinterpret_cast<int *>(lut + kDdBuckets + 4);
     int *q_k = queue + kDdQueue;                 // [Qcap] permutation
     int *q_i = q_k + a.Qcap;                     // [Qcap] hit position
     int *q_toff = q_i + a.Qcap;                  // [Qcap+1] offset of the query's statistics in the item
-    double *q_vi = reinterpret_cast<double *>(q_toff + a.Qcap + 2);   // [Qcap] exact null value at the skipped column
     __shared__ int s_T, s_qn;
     __shared__ unsigned int s_warp[kDdThreads / 32];
 
     const int tid = threadIdx.x;
-    double *g_thr = a.g_thr + (long long)blockIdx.x * a.Tcap;
-    unsigned int *g_org = a.g_org + (long long)blockIdx.x * a.Tcap;
+    double *tmp_r = a.g_thr + (long long)blockIdx.x * 3 * a.Tcap;      // statistic of flat index t (-99 = undefined)
+    double *g_thr = tmp_r + a.Tcap;                                    // grouped by bucket
+    double *thr64 = g_thr + a.Tcap;                                    // sorted
+    unsigned int *g_org = a.g_org + (long long)blockIdx.x * 2 * a.Tcap;
+    unsigned int *org = g_org + a.Tcap;
 
     for (int it = blockIdx.x; it < a.n_items; it += gridDim.x) {
         const DedupItem item = a.items[it];
@@ -118,40 +122,45 @@ count_dedup_kernel(DedupArgs a) {
         }
         __syncthreads();
         const int TP = q_toff[nq];
-        // ---- B. statistics: pass 1 counts per bucket, pass 2 groups them ----------------------------
+        // ---- B. statistics: pass 0 evaluates them once and counts per bucket, pass 1 groups them -----
         for (int pass = 0; pass < 2; ++pass) {
             for (int t = tid; t < TP; t += kDdThreads) {
                 int lo = 0, hi = nq;
                 while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (q_toff[mid] <= t) lo = mid; else hi = mid; }
                 const int ql = lo, j = t - q_toff[ql];
-                const int k = q_k[ql], i = q_i[ql];
-                const long long off = a.perm_off[k];
-                const int P = (int)(a.perm_off[k + 1] - off);
-                double *sc = a.scores + a.sc_off[k] + (long long)i * P;
-                long long *cn = a.counts ? a.counts + a.sc_off[k] + (long long)i * P : nullptr;
-                if (j == i) { if (pass == 0) { sc[j] = 0.0; if (cn) cn[j] = -1; } continue; }
-                const int c = a.hit_rows[off + j];
-                double r = -99.0;
-                if (posu && a.rawsum_pos[c]) {                              // coexfunctions.py:389
-                    r = __ddiv_rn(0.25 * (double)srow[c], __dmul_rn(sxu, a.sx[c]));
-                    if (r != r) r = -99.0;                                  // coexfunctions.py:406-408
-                }
-                if (r == -99.0) {                                           // 1-make-network.py:284-285
-                    if (pass == 0) { sc[j] = -log10(1.0); if (cn) cn[j] = -1; }
-                    continue;
-                }
-                const int b = dd_bucket64(r);
                 if (pass == 0) {
-                    atomicAdd(&lut[b], 1u);
+                    const int k = q_k[ql], i = q_i[ql];
+                    const long long off = a.perm_off[k];
+                    const int P = (int)(a.perm_off[k + 1] - off);
+                    const long long w = a.sc_off[k] + (long long)i * P + j;
+                    double r = -99.0;
+                    if (j != i) {
+                        const int c = a.hit_rows[off + j];
+                        if (posu && a.rawsum_pos[c]) {                          // coexfunctions.py:389
+                            r = __ddiv_rn(0.25 * (double)srow[c], __dmul_rn(sxu, a.sx[c]));
+                            if (r != r) r = -99.0;                              // coexfunctions.py:406-408
+                        }
+                    }
+                    tmp_r[t] = r;
+                    if (r == -99.0) {                                           // diagonal, or 1-make-network.py:284-285
+                        a.scores[w] = (j == i) ? 0.0 : -log10(1.0);
+                        if (a.counts) a.counts[w] = -1;
+                    } else {
+                        atomicAdd(&lut[dd_bucket64(r)], 1u);
+                    }
                 } else {
-                    const unsigned int pos = lut[b] + atomicAdd(&cursor[b], 1u);
-                    g_thr[pos] = r;
-                    g_org[pos] = ((unsigned int)ql << 13) | (unsigned int)j;
+                    const double r = tmp_r[t];
+                    if (r != -99.0) {
+                        const int b = dd_bucket64(r);
+                        const unsigned int pos = lut[b] + atomicAdd(&cursor[b], 1u);
+                        g_thr[pos] = r;
+                        g_org[pos] = ((unsigned int)ql << 13) | (unsigned int)j;
+                    }
                 }
             }
             __syncthreads();
             if (pass == 0) {
-                // exclusive scan of the 4096 bucket counts (16 per thread + block scan)
+                // exclusive scan of the bucket counts
                 constexpr int per = kDdBuckets / kDdThreads;
                 unsigned int loc[per], sum = 0;
 #pragma unroll
@@ -282,10 +291,16 @@ count_dedup_kernel(DedupArgs a) {
             long long len = N;
             if (i < N) { len = N - 1; if (q_vi[ql] < t) idx -= 1; }
             const long long w = a.sc_off[k] + (long long)i * P + j;
-            a.scores[w] = edge_score_dev(idx, len, a.anticor);
+            a.scores[w] = (len == N - 1) ? a.score_tab[idx] : edge_score_dev(idx, len, a.anticor);
             if (a.counts) a.counts[w] = idx;
         }
     }
+}
+
+// edge score of every possible bisect index, evaluated once per call by the same device function
+__global__ void score_table_kernel(double *tab, long long N, int anticor) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx <= N) tab[idx] = edge_score_dev(idx, N - 1, anticor);
 }
 
 // float reciprocal half-norms for the fp32 fast path + number of zero-variance rows
@@ -304,8 +319,8 @@ __global__ void icol_kernel(const double *__restrict__ sx, long long N, long lon
 }
 
 inline size_t dedup_smem_bytes(int Tcap, int Qcap) {
-    return (size_t)Tcap * 8 + (size_t)Tcap * 4 * 2 + (size_t)(Tcap + 4) * 4 + (size_t)(kDdBuckets + 4) * 4 +
-           (size_t)kDdQueue * 4 + (size_t)Qcap * 4 * 2 + (size_t)(Qcap + 2) * 4 + (size_t)Qcap * 8 + 16;
+    return (size_t)Qcap * 8 + (size_t)Tcap * 4 + (size_t)(Tcap + 4) * 4 + (size_t)(kDdBuckets + 4) * 4 +
+           (size_t)kDdQueue * 4 + (size_t)Qcap * 4 * 2 + (size_t)(Qcap + 2) * 4 + 16;
 }
 
 }  // namespace coex
