@@ -164,7 +164,7 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
         da.Tcap = Tcap; da.Qcap = Qcap; da.g_thr = c->dd_gthr.p; da.g_org = c->dd_gorg.p; da.score_tab = c->dd_tab.p;
         COEX_TRY(stage_begin(c, ST_COUNT));
         count_dedup_kernel<<<std::min(grid_max, std::max(da.n_items, 1)), kDdThreads, smem, st>>>(da);
-        COEX_CUDA(cudaGetLastError());
+        COEX_KCHECK(st);
         COEX_TRY(stage_end(c, 1));
     }
     // the host vectors above feed async copies: they must be consumed before this frame dies
@@ -348,25 +348,35 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
         na.w_best = c->w_best.p; na.w_cand = c->w_cand.p; na.w_state = c->w_state.p; na.w_flags = c->w_state.p + K;
         na.P2max = T2max;
     }
-    const unsigned warp_blocks = (unsigned)((H * 32 + 255) / 256), thread_blocks = (unsigned)((H + 255) / 256);
+    std::vector<long long> warp_off(K + 1, 0);
+    for (int k = 0; k < K; ++k) warp_off[k + 1] = warp_off[k] + std::max<long long>(1, (perm_off[k + 1] - perm_off[k] + 31) / 32);
+    COEX_TRY(c->d_warp_off.reserve(K + 1));
+    COEX_CUDA(cudaMemcpyAsync(c->d_warp_off.p, warp_off.data(), (K + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    na.warp_off = c->d_warp_off.p;
+    const unsigned rs_blocks = (unsigned)((warp_off[K] + kRsWarps - 1) / kRsWarps), rs_threads = kRsWarps * 32;
+    const unsigned thread_blocks = (unsigned)((H + 255) / 256);
     auto pass2_round = [&](bool last) -> int {
-        net_pass2_kernel<<<warp_blocks, 256, 0, st>>>(na, H);
+        net_rowsum_kernel<1><<<rs_blocks, rs_threads, 0, st>>>(na);
+        COEX_KCHECK(st);
         net_pick_kernel<<<thread_blocks, 256, 0, st>>>(na, H);
+        COEX_KCHECK(st);
         if (last) COEX_CUDA(cudaMemsetAsync(na.w_flags, 0, sizeof(int), st));
         net_commit_kernel<<<K, 256, 0, st>>>(na, 0);
-        COEX_CUDA(cudaGetLastError());
+        COEX_KCHECK(st);
         return 0;
     };
     auto density_tail = [&]() -> int {
         const size_t rsmem = (size_t)T2max * 8;
-        net_density_kernel<<<warp_blocks, 256, 0, st>>>(na, H, 0);
+        net_rowsum_kernel<2><<<rs_blocks, rs_threads, 0, st>>>(na);
+        COEX_KCHECK(st);
         net_removal_kernel<<<K, 256, rsmem, st>>>(na, 0);
-        if (!prm->noiter) net_density_kernel<<<warp_blocks, 256, 0, st>>>(na, H, 1);
+        COEX_KCHECK(st);
+        if (!prm->noiter) { net_rowsum_kernel<3><<<rs_blocks, rs_threads, 0, st>>>(na); COEX_KCHECK(st); }
         net_removal_kernel<<<K, 256, rsmem, st>>>(na, 1);
-        COEX_CUDA(cudaGetLastError());
+        COEX_KCHECK(st);
         return 0;
     };
-    const int kRounds = 8;
+    const int kRounds = 12;
     long long net_launches = 0;
     if (H > 0) {
         const size_t gsmem = (size_t)T2max * 24;
@@ -374,10 +384,13 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
         COEX_CUDA(cudaFuncSetAttribute(net_removal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(T2max * 8)));
         COEX_TRY(stage_begin(c, ST_NETWORK));
         net_group_kernel<<<K, kNetThreads, gsmem, st>>>(na);
-        net_pass1_kernel<<<warp_blocks, 256, 0, st>>>(na, H);
+        COEX_KCHECK(st);
+        net_rowsum_kernel<0><<<rs_blocks, rs_threads, 0, st>>>(na);
+        COEX_KCHECK(st);
         net_pick_kernel<<<thread_blocks, 256, 0, st>>>(na, H);
+        COEX_KCHECK(st);
         net_commit_kernel<<<K, 256, 0, st>>>(na, 1);
-        COEX_CUDA(cudaGetLastError());
+        COEX_KCHECK(st);
         for (int r = 0; r < kRounds; ++r) COEX_TRY(pass2_round(r == kRounds - 1));
         COEX_TRY(density_tail());
         net_launches = 4 + 3 * kRounds + (prm->noiter ? 3 : 4);
@@ -520,7 +533,7 @@ int coex_destroy(coex_ctx *c) {
     c->z_hi.release(); c->z_lo.release();
     c->chrom_id.release(); c->name_rank.release(); c->feat_start.release(); c->feat_end.release(); c->glist.release();
     c->a_hi.release(); c->a_lo.release(); c->strip.release(); c->strip_f64.release();
-    c->d_perm_off.release(); c->d_sc_off.release(); c->d_hits.release(); c->d_ngroups.release(); c->d_grp.release();
+    c->d_perm_off.release(); c->d_sc_off.release(); c->d_warp_off.release(); c->d_hits.release(); c->d_ngroups.release(); c->d_grp.release();
     c->d_label.release(); c->d_win.release(); c->w_root.release(); c->w_pos.release(); c->d_dens.release();
     c->d_aps.release(); c->d_scores.release(); c->w_s1.release(); c->w_d0.release(); c->w_w.release();
     c->d_counts.release(); c->w_best.release(); c->w_cand.release(); c->w_state.release(); c->p_idxa.release(); c->p_idxb.release();

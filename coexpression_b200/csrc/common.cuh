@@ -32,11 +32,23 @@ inline int fail(const char *file, int line, const std::string &msg) {
             return ::coex::fail(__FILE__, __LINE__,                                             \
                                 std::string(#expr " -> ") + cudaGetErrorString(_e));            \
     } while (0)
+// after a kernel launch: always check the launch; with COEX_DEBUG_SYNC=1 also wait for it, so an
+// asynchronous fault is reported at the launch that caused it
+#define COEX_KCHECK(stream)                                                                     \
+    do {                                                                                        \
+        COEX_CUDA(cudaGetLastError());                                                          \
+        if (::coex::debug_sync()) COEX_CUDA(cudaStreamSynchronize(stream));                     \
+    } while (0)
 #define COEX_TRY(expr)                                                                          \
     do {                                                                                        \
         int _s = (expr);                                                                        \
         if (_s) return _s;                                                                      \
     } while (0)
+
+inline bool debug_sync() {
+    static const bool on = getenv("COEX_DEBUG_SYNC") != nullptr;
+    return on;
+}
 
 constexpr int kNumStages = 6;
 enum Stage { ST_RANK = 0, ST_ROWSTATS = 1, ST_GATHER = 2, ST_GEMM = 3, ST_COUNT = 4, ST_NETWORK = 5 };
@@ -111,7 +123,7 @@ struct coex_ctx {
     coex::DevBuf<int8_t> a_hi, a_lo;          // gathered query rows [Hs, n_pad]
     coex::DevBuf<int> strip;                  // S strip [Hs, N_pad] int32
     coex::DevBuf<double> strip_f64;           // Pearson null strip [Hs, N]
-    coex::DevBuf<long long> d_perm_off, d_sc_off;
+    coex::DevBuf<long long> d_perm_off, d_sc_off, d_warp_off;
     coex::DevBuf<int> d_hits, d_ngroups, d_grp, d_label, d_win, w_root, w_pos, w_state;
     coex::DevBuf<double> d_dens, d_aps, d_scores, w_s1, w_d0, w_w;
     coex::DevBuf<long long> d_counts;

@@ -14,7 +14,7 @@
 
 namespace coex {
 
-constexpr int kNetThreads = 256;
+constexpr int kNetThreads = 1024;   // net_group_kernel: one CTA per permutation, 32 warps share the in-cluster pairs
 
 struct NetArgs {
     int K;
@@ -46,6 +46,7 @@ struct NetArgs {
     unsigned long long *w_best, *w_cand;
     int *w_state;                // [K] 1 while the permutation's pass-2 iteration has not converged
     int *w_flags;                // [1] bit 0: some permutation changed in the last committed round
+    const long long *warp_off;   // [K+1] prefix of ceil(max(P_k, 1) / 32): warp -> permutation map of the row-sum kernels
     int P2max;
 };
 
@@ -246,39 +247,87 @@ __device__ __forceinline__ int perm_of(const long long *perm_off, int K, long lo
     return lo;
 }
 
-__device__ __forceinline__ double warp_ordered_add(double s, double v) {
-#pragma unroll
-    for (int l = 0; l < 32; ++l) s = __dadd_rn(s, __shfl_sync(0xffffffffu, v, l));
-    return s;
-}
+// Ordered row sums, shared by pass 1, pass 2 and the density / removal sums.  A warp owns 32
+// consecutive rows of ONE permutation.  For every chunk of 32 columns the warp fetches, row by
+// row, the 32 addends (lane = column: coalesced for pass 1, a near-contiguous gather of winner
+// columns otherwise) into a 32 x 33 shared-memory tile; then lane l adds row l left to right.
+// Skipped addends are stored as +0.0, which leaves a non-negative running sum bit-identical.
+//   MODE 0  pass 1  (1-make-network.py:365-375)  columns = all hits, hit order
+//   MODE 1  pass 2  (1-make-network.py:378-434)  columns = winners, group order (fixed-point round)
+//   MODE 2  density (1-make-network.py:437-462)  rows = groups (their winner's row)
+//   MODE 3  whittled density (1-make-network.py:471-478)
+constexpr int kRsWarps = 4;
 
-// pass 1 (1-make-network.py:365-375): member score over other-group hits, hit order
-__global__ void __launch_bounds__(256)
-net_pass1_kernel(NetArgs a, long long H) {
-    const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (q >= H) return;
-    const int k = perm_of(a.perm_off, a.K, q);
+template <int MODE>
+__global__ void __launch_bounds__(kRsWarps * 32)
+net_rowsum_kernel(NetArgs a) {
+    __shared__ double tiles[kRsWarps][32 * 33];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long w = (long long)blockIdx.x * kRsWarps + wib;
+    if (w >= a.warp_off[a.K]) return;
+    const int k = perm_of(a.warp_off, a.K, w);
+    if (MODE == 1 && !a.w_state[k]) return;
     const long long off = a.perm_off[k];
     const int P = (int)(a.perm_off[k + 1] - off);
     if (P < 2) return;
-    const int i = (int)(q - off);
+    const int G = a.n_groups[k];
+    const int nrows = (MODE <= 1) ? P : G;
+    const int ncols = (MODE == 0) ? P : G;
+    const int i0 = (int)(w - a.warp_off[k]) * 32;
+    if (i0 >= nrows) return;
+    double *tile = tiles[wib];
     const int *grp = a.group_of_hit + off;
-    const int gi = grp[i];
-    const double *row = a.scores + a.sc_off[k] + (long long)i * P;
+    const int *win = a.group_winner + off, *w1 = a.w_pos + off, *vis = a.w_root + off;
+    const double *Sc = a.scores + a.sc_off[k];
+    const int mine = i0 + lane;                                   // this lane's row
+    const bool mine_ok = mine < nrows;
+    // row attributes held by lane r for row i0 + r
+    const int my_g = mine_ok ? ((MODE <= 1) ? grp[mine] : mine) : -1;        // group of the row
+    const long long my_base = mine_ok ? (long long)((MODE <= 1) ? mine : win[mine]) * P : 0;
+    const int my_vis = (MODE == 3 && mine_ok) ? vis[mine] : 0;
     double s = 0.0;
-    for (int j0 = 0; j0 < P; j0 += 32) {
-        const int j = j0 + lane;
-        double v = 0.0;
-        if (j < P && j != i) {
-            const double x = row[j];
-            if (x >= a.thr && grp[j] != gi) v = x;
+    for (int c0 = 0; c0 < ncols; c0 += 32) {
+        const int c = c0 + lane;                                   // this lane's column
+        const bool c_ok = c < ncols;
+        int col_a = 0, col_b = 0, gcol = -2, vcol = 0;
+        if (c_ok) {
+            if (MODE == 0) { col_a = c; gcol = grp[c]; }
+            else { col_a = win[c]; col_b = (MODE == 1) ? w1[c] : col_a; gcol = c; if (MODE == 3) vcol = vis[c]; }
         }
-        s = warp_ordered_add(s, v);
+        // issue all 32 loads of the chunk before the first use: one memory latency per chunk
+        double x[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const int rg = __shfl_sync(0xffffffffu, my_g, r);
+            const long long rb = __shfl_sync(0xffffffffu, my_base, r);
+            const int rvis = (MODE == 3) ? __shfl_sync(0xffffffffu, my_vis, r) : 0;
+            bool use = c_ok && rg >= 0 && gcol != rg;
+            if (MODE == 0) use = use && (c != i0 + r);
+            if (MODE == 3) use = use && !(vcol < rvis);
+            const int col = (MODE == 1 && !(gcol < rg)) ? col_b : col_a;
+            x[r] = use ? Sc[rb + col] : 0.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            double v = x[r];
+            if (MODE != 1 && !(v >= a.thr)) v = 0.0;           // selection threshold (not applied in pass 2)
+            tile[r * 33 + lane] = v;
+        }
+        __syncwarp();
+        if (mine_ok) {
+            const int lim = min(32, ncols - c0);
+            for (int cc = 0; cc < lim; ++cc) s = __dadd_rn(s, tile[lane * 33 + cc]);
+        }
     }
-    if (lane == 0) {
-        a.w_s1[q] = s;
-        atomicMax(&a.w_best[off + gi], (unsigned long long)__double_as_longlong(s));
+    if (mine_ok) {
+        if (MODE <= 1) {
+            a.w_s1[off + mine] = s;
+            atomicMax(&a.w_best[off + my_g], (unsigned long long)__double_as_longlong(s));
+        } else {
+            const double d = a.useaverage ? s / (double)G : s;
+            if (MODE == 3) a.w_w[off + mine] = d; else a.w_d0[off + mine] = d;
+        }
     }
 }
 
@@ -325,72 +374,6 @@ net_commit_kernel(NetArgs a, int first) {
             a.w_state[k] = changed;
             if (changed) atomicOr(a.w_flags, 1);
         }
-    }
-}
-
-// pass 2 (1-make-network.py:378-434), one round of the lower-triangular fixed-point iteration:
-// member m of group g is scored against the CURRENT winners of groups < g and the pass-1
-// winners of groups > g.  Starting from the pass-1 winners, round r fixes at least the first r
-// groups, and the unique fixed point is the reference's sequential (Gauss-Seidel) result.
-__global__ void __launch_bounds__(256)
-net_pass2_kernel(NetArgs a, long long H) {
-    const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (q >= H) return;
-    const int k = perm_of(a.perm_off, a.K, q);
-    if (!a.w_state[k]) return;
-    const long long off = a.perm_off[k];
-    const int P = (int)(a.perm_off[k + 1] - off);
-    if (P < 2) return;
-    const int i = (int)(q - off);
-    const int G = a.n_groups[k];
-    const int gi = a.group_of_hit[q];
-    const int *win = a.group_winner + off, *w1 = a.w_pos + off;
-    const double *row = a.scores + a.sc_off[k] + (long long)i * P;
-    double s = 0.0;
-    for (int h0 = 0; h0 < G; h0 += 32) {
-        const int h = h0 + lane;
-        double v = 0.0;
-        if (h < G && h != gi) v = row[h < gi ? win[h] : w1[h]];
-        s = warp_ordered_add(s, v);
-    }
-    if (lane == 0) {
-        a.w_s1[q] = s;
-        atomicMax(&a.w_best[off + gi], (unsigned long long)__double_as_longlong(s));
-    }
-}
-
-// density (1-make-network.py:437-462) and, with `removal`, the whittled sum of
-// 1-make-network.py:471-478: one warp per group slot
-__global__ void __launch_bounds__(256)
-net_density_kernel(NetArgs a, long long H, int removal) {
-    const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (q >= H) return;
-    const int k = perm_of(a.perm_off, a.K, q);
-    const long long off = a.perm_off[k];
-    const int P = (int)(a.perm_off[k + 1] - off);
-    if (P < 2) return;
-    const int g = (int)(q - off);
-    const int G = a.n_groups[k];
-    if (g >= G) return;
-    const int *win = a.group_winner + off;
-    const int *vis = a.w_root + off;                 // visiting position (removal only)
-    const int pg = removal ? vis[g] : 0;
-    const double *row = a.scores + a.sc_off[k] + (long long)win[g] * P;
-    double s = 0.0;
-    for (int h0 = 0; h0 < G; h0 += 32) {
-        const int h = h0 + lane;
-        double v = 0.0;
-        if (h < G && h != g && !(removal && vis[h] < pg)) {
-            const double x = row[win[h]];
-            if (x >= a.thr) v = x;
-        }
-        s = warp_ordered_add(s, v);
-    }
-    if (lane == 0) {
-        const double d = a.useaverage ? s / (double)G : s;
-        if (removal) a.w_w[q] = d; else a.w_d0[q] = d;
     }
 }
 
