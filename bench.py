@@ -245,14 +245,19 @@ def run_ours(args):
     o_grp = torch.zeros(H, dtype=torch.int32, device=dev)
     o_lab = torch.zeros(H, dtype=torch.int32, device=dev)
     o_win = torch.zeros(H, dtype=torch.int32, device=dev)
-    o_den = torch.zeros(H, dtype=torch.float64, device=dev)
+    # the gathered density block must have one size on every rank: pad to the largest hit count
+    hpad = torch.tensor([H], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(hpad, op=dist.ReduceOp.MAX)
+    Hpad = int(hpad.item())
+    o_den = torch.zeros(Hpad, dtype=torch.float64, device=dev)
     o_aps = torch.zeros(H, dtype=torch.float64, device=dev)
     ptrs = dict(hit_rows=hits_dev.data_ptr(), n_groups=o_ng.data_ptr(), group_of_hit=o_grp.data_ptr(),
                 group_label=o_lab.data_ptr(), group_winner=o_win.data_ptr(), group_density=o_den.data_ptr(),
                 hit_score=o_aps.data_ptr())
     stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    gather_buf = [torch.zeros(H, dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
+    gather_buf = [torch.zeros(Hpad, dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
 
     def step_device():
         ctx.set_expression_device(X_dev.data_ptr(), t.N, t.n, keepalive=X_dev)
