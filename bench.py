@@ -218,7 +218,20 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on fd 1 when the communicator is created; stdout must
+        # carry ONE JSON line, so fd 1 points at stderr while NCCL initialises
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     t, hits, ga, gb = workload(args, rank)
     K = len(hits)
@@ -257,16 +270,17 @@ def run_ours(args):
                 hit_score=o_aps.data_ptr())
     stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    gather_buf = [torch.zeros(Hpad, dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
+    gather_buf = torch.zeros(world * Hpad, dtype=torch.float64, device=dev) if world > 1 else None
 
     def step_device():
         ctx.set_expression_device(X_dev.data_ptr(), t.N, t.n, keepalive=X_dev)
         ctx.prepare()
         ctx.network_batch_device(opts, K, perm_off, ptrs)
         if world > 1:
-            # the one collective of the path: density vectors of every rank (2-collate pools them)
-            with torch.cuda.stream(stream):
-                dist.all_gather(gather_buf, o_den)
+            # the one collective of the path: density vectors of every rank (2-collate pools them).
+            # coex_network_batch has drained the library stream when it returns, so the gather can
+            # be queued on torch's current stream.
+            dist.all_gather_into_tensor(gather_buf, o_den)
 
     def barrier():
         torch.cuda.synchronize()
@@ -283,6 +297,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
+    barrier()                                                # every rank enters the timed steps together
     launches0 = ctx.launch_count()
     t_wall0 = time.time()
     ms = []
@@ -291,14 +306,22 @@ def run_ours(args):
         torch.cuda.synchronize()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        h0 = time.perf_counter()
         ctx.set_expression_device(X_dev.data_ptr(), t.N, t.n, keepalive=X_dev)
         ctx.prepare()
+        h1 = time.perf_counter()
         prep = ctx.stage_ms()
+        h2 = time.perf_counter()
         ctx.network_batch_device(opts, K, perm_off, ptrs)
+        h3 = time.perf_counter()
+        if os.environ.get("COEX_BENCH_DEBUG"):
+            print(f"[rank {rank}] host ms: prepare {1e3*(h1-h0):.2f} stage_ms {1e3*(h2-h1):.2f} network_batch {1e3*(h3-h2):.2f}",
+                  file=sys.stderr)
         if world > 1:
-            with torch.cuda.stream(stream):
-                dist.all_gather(gather_buf, o_den)
-        e1.record(stream)
+            dist.all_gather_into_tensor(gather_buf, o_den)
+            e1.record()                                      # torch's current stream (after the gather)
+        else:
+            e1.record(stream)
         torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
         st = ctx.stage_ms()
@@ -328,6 +351,10 @@ def run_ours(args):
         ctx.prepare()
         res = ctx.network_batch(hits, opts)
         dens = res.group_density
+        if world > 1:
+            o_den[:H].copy_(torch.from_numpy(dens))
+            dist.all_gather_into_tensor(gather_buf, o_den)
+            all_dens = gather_buf.cpu()
         w1 = time.perf_counter()
         if i >= 2:
             e2e_ms.append(1e3 * (w1 - w0))
