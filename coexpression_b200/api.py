@@ -174,6 +174,16 @@ class CoexContext:
                                                nan.ctypes.data), "coex_allpairs_histogram")
         return hist, int(nan[0])
 
+    def corr_block(self, which, row0, nrows):
+        """which: 'spearman' | 'pearson' (tensor cores) | 'pearson_exact' -> float64 [nrows, N]."""
+        out = np.empty((nrows, self.N), dtype=np.float64)
+        code = {"spearman": 1, "pearson": 0, "pearson_exact": 2}[which]
+        check(self.lib.coex_corr_block(self.h, code, int(row0), int(nrows), out.ctypes.data), "coex_corr_block")
+        return out
+
+    def set_pearson(self, digits=4, mode="tensor"):
+        check(self.lib.coex_set_pearson(self.h, int(digits), {"tensor": 0, "exact": 1}[mode]), "coex_set_pearson")
+
     # ---- A4-A12 batched -----------------------------------------------------------------------------
     def network_batch(self, hit_sets, options: Options, want_scores=False, want_counts=False):
         """hit_sets: list of int arrays (table rows, map-file order), one per permutation."""

@@ -8,6 +8,7 @@
 #include "count.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "prepare.cuh"
 
 namespace coex {
 
@@ -20,8 +21,8 @@ __device__ __forceinline__ int r_to_bin(double r, int nbins) {
 template <bool F64>
 __global__ void __launch_bounds__(256)
 hist_strip_kernel(const int *__restrict__ strip, const double *__restrict__ strip_f64, long long ld, long long row0,
-                  long long nq, long long N, const double *__restrict__ sx, int nbins,
-                  unsigned long long *__restrict__ hist, unsigned long long *__restrict__ nan_count) {
+                  long long nq, long long N, const double *__restrict__ sx, const unsigned char *__restrict__ ok,
+                  int nbins, unsigned long long *__restrict__ hist, unsigned long long *__restrict__ nan_count) {
     const long long q = blockIdx.y;
     if (q >= nq) return;
     const long long row = row0 + q;
@@ -30,8 +31,12 @@ hist_strip_kernel(const int *__restrict__ strip, const double *__restrict__ stri
     for (long long c = row + 1 + (long long)blockIdx.x * blockDim.x + threadIdx.x; c < N;
          c += (long long)gridDim.x * blockDim.x) {
         double r;
-        if (F64) r = strip_f64[q * ld + c];
-        else r = __ddiv_rn(0.25 * (double)strip[q * ld + c], __dmul_rn(sxu, sx[c]));
+        if (F64) {
+            r = strip_f64[q * ld + c];
+            if (ok && !(ok[row] && ok[c])) r = __longlong_as_double(0x7ff8000000000000LL);
+        } else {
+            r = __ddiv_rn(0.25 * (double)strip[q * ld + c], __dmul_rn(sxu, sx[c]));
+        }
         if (r != r) { ++nans; continue; }
         atomicAdd(&hist[r_to_bin(r, nbins)], 1ULL);
     }
@@ -43,6 +48,39 @@ __global__ void iota_rows_kernel(int *rows, long long row0, long long nq) {
     if (t < nq) rows[t] = (int)(row0 + t);
 }
 
+// lazily pack the Pearson digit planes (after coex_prepare)
+static int pearson_pack(coex_ctx *c) {
+    const int D = c->pearson_digits;
+    if (c->z_digits == D) return 0;
+    const size_t plane = (size_t)c->N_pad * c->n_pad;
+    COEX_TRY(c->z_planes.reserve(plane * D)); COEX_TRY(c->z_ok.reserve(c->N_pad)); COEX_TRY(c->z_l1.reserve(c->N_pad));
+    COEX_TRY(c->z_inv_s.reserve(c->N_pad));
+    COEX_CUDA(cudaMemsetAsync(c->z_inv_s.p, 0, c->N_pad * sizeof(double), c->stream));
+    COEX_CUDA(cudaMemsetAsync(c->z_planes.p, 0, plane * D, c->stream));
+    COEX_CUDA(cudaMemsetAsync(c->z_ok.p, 0, c->N_pad, c->stream));
+    COEX_CUDA(cudaMemsetAsync(c->z_l1.p, 0, c->N_pad * sizeof(float), c->stream));
+    const unsigned blocks = (unsigned)((c->N * 32 + 255) / 256);
+    if (D == 3)
+        pearson_pack_kernel<3><<<blocks, 256, 0, c->stream>>>(c->raw, c->N, c->n, c->n_pad, c->raw_sum.p, c->raw_mean.p, c->raw_xx.p,
+                                                            c->z_planes.p, (long long)plane, c->z_ok.p, c->z_l1.p, c->z_inv_s.p);
+    else
+        pearson_pack_kernel<4><<<blocks, 256, 0, c->stream>>>(c->raw, c->N, c->n, c->n_pad, c->raw_sum.p, c->raw_mean.p, c->raw_xx.p,
+                                                            c->z_planes.p, (long long)plane, c->z_ok.p, c->z_l1.p, c->z_inv_s.p);
+    COEX_KCHECK(c->stream);
+    c->launches += 1;
+    c->z_digits = D;
+    return 0;
+}
+
+// Pearson r strip [m_rows, N_pad] (double) for table rows [row0, row0 + m_rows) on the tensor cores
+static int pearson_tensor_strip(coex_ctx *c, long long row0, long long m_rows, int upper_only) {
+    COEX_TRY(pearson_pack(c));
+    const size_t plane = (size_t)c->N_pad * c->n_pad;
+    if (c->z_digits == 3)
+        return tc_gemm_digits<3>(c, c->z_planes.p, (long long)plane, row0, m_rows, c->strip_f64.p, c->N_pad, c->z_inv_s.p, upper_only);
+    return tc_gemm_digits<4>(c, c->z_planes.p, (long long)plane, row0, m_rows, c->strip_f64.p, c->N_pad, c->z_inv_s.p, upper_only);
+}
+
 static int allpairs_histogram_impl(coex_ctx *c, int which, long long row0, long long row1, int nbins,
                                    unsigned long long *hist, unsigned long long *nan_count) {
     if (row0 < 0 || row1 > c->N || row0 > row1 || nbins <= 0) COEX_FAIL("coex_allpairs_histogram: bad arguments");
@@ -52,10 +90,12 @@ static int allpairs_histogram_impl(coex_ctx *c, int which, long long row0, long 
     DevBuf<unsigned long long> dh;
     COEX_TRY(dh.reserve((size_t)nbins + 1));
     COEX_CUDA(cudaMemsetAsync(dh.p, 0, ((size_t)nbins + 1) * sizeof(unsigned long long), st));
-    const long long ld = which == 1 ? c->N_pad : c->N;
+    const bool ptensor = (which == 0 && c->pearson_mode == 0);
+    const long long ld = (which == 1 || ptensor) ? c->N_pad : c->N;
     long long Hs = (c->strip_mb << 20) / (ld * (which == 1 ? 4 : 8));
     Hs = std::max<long long>(256, Hs / 256 * 256);
     Hs = std::min<long long>(Hs, round_up(std::max<long long>(row1 - row0, 1), 256));
+    if (ptensor && row0 % 128) COEX_FAIL("coex_allpairs_histogram: row0 must be a multiple of 128 on the tensor path");
     COEX_TRY(c->d_hits.reserve(Hs));
     if (which == 1) {
         COEX_TRY(c->strip.reserve((size_t)Hs * ld));
@@ -86,6 +126,10 @@ static int allpairs_histogram_impl(coex_ctx *c, int which, long long row0, long 
                 COEX_CUDA(cudaGetLastError());
             }
             COEX_TRY(stage_end(c, 1));
+        } else if (ptensor) {
+            COEX_TRY(stage_begin(c, ST_GEMM));
+            COEX_TRY(pearson_tensor_strip(c, r0, std::min(round_up(nq, 128), c->N_pad - r0), 1));
+            COEX_TRY(stage_end(c, 1));
         } else {
             COEX_TRY(stage_begin(c, ST_GEMM));
             dim3 g((unsigned)((c->N + 63) / 64), (unsigned)((nq + 15) / 16));
@@ -97,9 +141,9 @@ static int allpairs_histogram_impl(coex_ctx *c, int which, long long row0, long 
         COEX_TRY(stage_begin(c, ST_COUNT));
         dim3 hg((unsigned)std::min<long long>((c->N + 255) / 256, 64), (unsigned)nq);
         if (which == 1)
-            hist_strip_kernel<false><<<hg, 256, 0, st>>>(c->strip.p, nullptr, ld, r0, nq, c->N, c->sx.p, nbins, dh.p, dh.p + nbins);
+            hist_strip_kernel<false><<<hg, 256, 0, st>>>(c->strip.p, nullptr, ld, r0, nq, c->N, c->sx.p, nullptr, nbins, dh.p, dh.p + nbins);
         else
-            hist_strip_kernel<true><<<hg, 256, 0, st>>>(nullptr, c->strip_f64.p, ld, r0, nq, c->N, c->sx.p, nbins, dh.p, dh.p + nbins);
+            hist_strip_kernel<true><<<hg, 256, 0, st>>>(nullptr, c->strip_f64.p, ld, r0, nq, c->N, c->sx.p, ptensor ? c->z_ok.p : nullptr, nbins, dh.p, dh.p + nbins);
         COEX_CUDA(cudaGetLastError());
         COEX_TRY(stage_end(c, 1));
     }
@@ -107,7 +151,68 @@ static int allpairs_histogram_impl(coex_ctx *c, int which, long long row0, long 
     COEX_CUDA(cudaMemcpyAsync(nan_count, dh.p + nbins, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     COEX_CUDA(cudaStreamSynchronize(st));
     dh.release();
-    if (which == 1 && c->gemm_mode == 0) COEX_TRY(tc_check_error(c));
+    if ((which == 1 && c->gemm_mode == 0) || ptensor) COEX_TRY(tc_check_error(c));
+    return 0;
+}
+
+// expand a strip into r values (NaN where the reference yields NaN)
+__global__ void strip_to_r_kernel(const int *__restrict__ strip, const double *__restrict__ strip_f64, long long ld,
+                                  long long row0, long long nq, long long N, const double *__restrict__ sx,
+                                  const unsigned char *__restrict__ ok, double *__restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nq * N) return;
+    const long long q = t / N, col = t - q * N;
+    double r;
+    if (strip) r = __ddiv_rn(0.25 * (double)strip[q * ld + col], __dmul_rn(sx[row0 + q], sx[col]));
+    else {
+        r = strip_f64[q * ld + col];
+        if (ok && !(ok[row0 + q] && ok[col])) r = __longlong_as_double(0x7ff8000000000000LL);
+    }
+    out[t] = r;
+}
+
+// rows [row0, row0 + nrows) x all table rows: which 1 = Spearman (exact), 0 = Pearson on the tensor
+// cores (quantised digits), 2 = Pearson in-order double (bit-exact).  out: host double [nrows, N].
+static int corr_block_impl(coex_ctx *c, int which, long long row0, long long nrows, double *out) {
+    if (row0 < 0 || nrows <= 0 || row0 + nrows > c->N) COEX_FAIL("coex_corr_block: bad row range");
+    if (which != 2 && row0 % 128) COEX_FAIL("coex_corr_block: row0 must be a multiple of 128");
+    if (which == 1 && c->n > 1860) COEX_FAIL("Spearman tensor path supports up to 1860 samples");
+    cudaStream_t st = c->stream;
+    const long long m_rows = std::min(round_up(nrows, 256), c->N_pad - row0);
+    DevBuf<double> dout;
+    COEX_TRY(dout.reserve((size_t)nrows * c->N));
+    COEX_TRY(c->d_hits.reserve(m_rows));
+    iota_rows_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(c->d_hits.p, row0, nrows);
+    const unsigned eb = (unsigned)((nrows * c->N + 255) / 256);
+    if (which == 1) {
+        COEX_TRY(c->strip.reserve((size_t)m_rows * c->N_pad));
+        COEX_TRY(c->a_hi.reserve((size_t)m_rows * c->n_pad)); COEX_TRY(c->a_lo.reserve((size_t)m_rows * c->n_pad));
+        const long long total = m_rows * (c->n_pad >> 4);
+        gather_rows_kernel<<<(int)std::min<long long>((total + 255) / 256, 4096), 256, 0, st>>>(
+            c->u_hi.p, c->u_lo.p, c->n_pad, c->d_hits.p, nrows, m_rows, c->a_hi.p, c->a_lo.p);
+        if (c->gemm_mode == 0) COEX_TRY(tc_gemm_i8(c, m_rows));
+        else {
+            dim3 grid((unsigned)(c->N_pad / kSimtTile), (unsigned)(m_rows / kSimtTile));
+            gemm_i8_simt_kernel<<<grid, 256, 0, st>>>(c->a_hi.p, c->a_lo.p, c->u_hi.p, c->u_lo.p, c->n_pad, c->strip.p, c->N_pad);
+        }
+        strip_to_r_kernel<<<eb, 256, 0, st>>>(c->strip.p, nullptr, c->N_pad, row0, nrows, c->N, c->sx.p, nullptr, dout.p);
+    } else if (which == 0) {
+        COEX_TRY(c->strip_f64.reserve((size_t)m_rows * c->N_pad));
+        COEX_TRY(pearson_tensor_strip(c, row0, m_rows, 0));
+        strip_to_r_kernel<<<eb, 256, 0, st>>>(nullptr, c->strip_f64.p, c->N_pad, row0, nrows, c->N, c->sx.p, c->z_ok.p, dout.p);
+    } else {
+        COEX_TRY(c->strip_f64.reserve((size_t)m_rows * c->N));
+        dim3 g((unsigned)((c->N + 63) / 64), (unsigned)((nrows + 15) / 16));
+        pearson_strip_kernel<<<g, 256, 0, st>>>(c->raw, c->n, c->N, c->d_hits.p, nrows, c->raw_sum.p, c->raw_mean.p,
+                                                c->raw_xx.p, c->strip_f64.p, c->N);
+        strip_to_r_kernel<<<eb, 256, 0, st>>>(nullptr, c->strip_f64.p, c->N, row0, nrows, c->N, c->sx.p, nullptr, dout.p);
+    }
+    COEX_KCHECK(st);
+    c->launches += 4;
+    COEX_CUDA(cudaMemcpyAsync(out, dout.p, (size_t)nrows * c->N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    COEX_CUDA(cudaStreamSynchronize(st));
+    dout.release();
+    if (which != 2) COEX_TRY(tc_check_error(c));
     return 0;
 }
 

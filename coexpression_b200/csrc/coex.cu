@@ -31,6 +31,7 @@ static int prepare_impl(coex_ctx *c) {
     c->n_pad = (int)round_up(n, 128);
     c->N_pad = round_up(N, 256);
     stage_reset(c);
+    c->z_digits = 0;
     COEX_TRY(c->raw_sum.reserve(N)); COEX_TRY(c->raw_mean.reserve(N)); COEX_TRY(c->raw_xx.reserve(N));
     COEX_TRY(c->rawsum_pos.reserve(N));
     COEX_TRY(c->rank2.reserve((size_t)N * n));
@@ -530,7 +531,7 @@ int coex_destroy(coex_ctx *c) {
     tc_destroy(c);
     c->raw_own.release(); c->raw_sum.release(); c->raw_mean.release(); c->raw_xx.release(); c->rawsum_pos.release();
     c->rank2.release(); c->u_hi.release(); c->u_lo.release(); c->suu.release(); c->sx.release();
-    c->z_hi.release(); c->z_lo.release();
+    c->z_planes.release(); c->z_ok.release(); c->z_l1.release(); c->z_inv_s.release();
     c->chrom_id.release(); c->name_rank.release(); c->feat_start.release(); c->feat_end.release(); c->glist.release();
     c->a_hi.release(); c->a_lo.release(); c->strip.release(); c->strip_f64.release();
     c->d_perm_off.release(); c->d_sc_off.release(); c->d_warp_off.release(); c->d_hits.release(); c->d_ngroups.release(); c->d_grp.release();
@@ -557,6 +558,7 @@ int coex_set_expression(coex_ctx *c, const double *data, long long N, int n, int
     if (!data || N <= 0 || n <= 0) COEX_FAIL("coex_set_expression: empty table");
     if (N > 2000000000LL) COEX_FAIL("coex_set_expression: too many rows");
     c->prepared = false;
+    c->z_digits = 0;
     c->N = N; c->n = n;
     if (on_device) {
         c->raw = data;
@@ -650,6 +652,22 @@ int coex_allpairs_histogram(coex_ctx *c, int which, long long row0, long long ro
     COEX_TRY(check_ctx(c));
     if (!c->prepared) COEX_FAIL("coex_allpairs_histogram: call coex_prepare first");
     return allpairs_histogram_impl(c, which, row0, row1, nbins, hist, nan_count);
+}
+
+int coex_corr_block(coex_ctx *c, int which, long long row0, long long nrows, double *out) {
+    COEX_TRY(check_ctx(c));
+    if (!c->prepared) COEX_FAIL("coex_corr_block: call coex_prepare first");
+    if (!out) COEX_FAIL("coex_corr_block: null output");
+    return corr_block_impl(c, which, row0, nrows, out);
+}
+
+int coex_set_pearson(coex_ctx *c, int digits, int mode) {
+    if (!c) COEX_FAIL("null context");
+    if (digits != 3 && digits != 4) COEX_FAIL("coex_set_pearson: digits must be 3 or 4");
+    if (mode != 0 && mode != 1) COEX_FAIL("coex_set_pearson: mode 0 = tensor-core digits, 1 = in-order double");
+    c->pearson_digits = digits;
+    c->pearson_mode = mode;
+    return 0;
 }
 
 int coex_network_batch(coex_ctx *c, const coex_params *prm, int K, const long long *perm_off, const int *hit_rows,

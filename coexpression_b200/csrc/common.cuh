@@ -108,9 +108,14 @@ struct coex_ctx {
     coex::DevBuf<long long> suu;              // [N_pad]
     coex::DevBuf<double> sx;                  // [N_pad]  sqrt(0.25*suu); 0 for padding
 
-    // Pearson packing (split-precision limbs of the centred, normalised rows)
-    coex::DevBuf<uint16_t> z_hi, z_lo;        // [N_pad, n_pad2] fp16 limbs, K-major
-    int n_pad2 = 0;
+    // Pearson packing: z-scores quantised to D base-128 int8 digits, D K-major planes
+    coex::DevBuf<int8_t> z_planes;            // [D, N_pad, n_pad]
+    coex::DevBuf<unsigned char> z_ok;         // [N_pad] 0 where the reference yields NaN
+    coex::DevBuf<float> z_l1;                 // [N_pad] |z|_1 (error bound of the quantisation)
+    coex::DevBuf<double> z_inv_s;             // [N_pad] 1 / per-row quantisation scale
+    int z_digits = 0;                         // digits currently packed (0 = none)
+    int pearson_digits = 4;                   // requested: 4 (default, |r - ref| ~ 1e-8) or 3 (faster, ~ 1e-6)
+    int pearson_mode = 0;                     // 0 = tensor-core digits, 1 = in-order double strip (bit-exact)
 
     // ---- join_nearby inputs -------------------------------------------------------------
     coex::DevBuf<int> chrom_id, name_rank;

@@ -208,6 +208,129 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
     }
 }
 
+// =============================================================================================
+// Generic D-digit variant (Pearson): z-scores quantised to D base-128 int8 digits
+// (prepare.cuh: pearson_pack_kernel).  One CTA per 128 x 32 output tile; per 32-byte K step
+//      D_i[128 x (D*32)] += A_i * [B_{D-1} ; ... ; B_0]^T            i = 0 .. D-1
+// so TMEM holds the D*D partial products (D*D*32 <= 512 columns) and the epilogue recombines
+//      S = sum_{i,l} 128^(i+l) * P_il          (int64, exact),     r = S / s^2      (double).
+// Column tiles entirely at or below the diagonal are skipped when `upper_only` is set
+// (all-pairs: r(a,b) = r(b,a)).
+// =============================================================================================
+template <int D> struct TcDigits {
+    static constexpr int BN = 32;
+    static constexpr int N = D * BN;                           // UMMA N (96 or 128)
+    static constexpr int kStage = D * 16384 + D * BN * 128;    // A digits + stacked B digits
+    static constexpr int kStages = (D == 3) ? 3 : 2;
+    static constexpr int kSmem = kStages * kStage + 1024 + 256;
+};
+
+struct TcMaps8 { CUtensorMap a[4]; CUtensorMap b[4]; };
+
+template <int D>
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_digits_tc_kernel(const __grid_constant__ TcMaps8 maps, double *__restrict__ out, long long ldo, int nkb,
+                      long long a_row0, const double *__restrict__ inv_s, int upper_only, int *err) {
+    using T = TcDigits<D>;
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    const uint32_t bars = base + T::kStages * T::kStage;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * T::kStages, bar_tmem = bars + 16 * T::kStages;
+    const uint32_t tmem_slot = bar_tmem + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * kTcBM;                 // row tile inside the strip (fastest)
+    const int c0 = blockIdx.y * T::BN;                 // table-column tile
+    if (upper_only && (long long)c0 + T::BN <= a_row0 + m0) return;      // whole tile is below the diagonal
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < T::kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_tmem, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % T::kStages;
+                if (kb >= T::kStages && !mbar_wait(bar_empty + 8 * s, ((kb / T::kStages) - 1) & 1, err, 1)) break;
+                const uint32_t st = base + s * T::kStage;
+                mbar_expect_tx(bar_full + 8 * s, T::kStage);
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    tma_load_2d(st + d * 16384, &maps.a[d], bar_full + 8 * s, kb * kTcBK, (int)(a_row0 + m0));
+                    // stacked B operand: highest digit first is irrelevant, only the order must match the epilogue
+                    tma_load_2d(st + D * 16384 + d * T::BN * 128, &maps.b[d], bar_full + 8 * s, kb * kTcBK, c0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_i8(128, T::N);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % T::kStages;
+                if (!mbar_wait(bar_full + 8 * s, (kb / T::kStages) & 1, err, 2)) break;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = base + s * T::kStage;
+#pragma unroll
+                for (int ks = 0; ks < kTcBK / 32; ++ks) {
+                    const uint64_t b_cat = umma_desc_sw128(st + D * 16384 + ks * 32);
+                    const uint32_t acc = (kb | ks) ? 1u : 0u;
+#pragma unroll
+                    for (int d = 0; d < D; ++d)
+                        umma_i8(tmem_base + d * T::N, umma_desc_sw128(st + d * 16384 + ks * 32), b_cat, idesc, acc);
+                }
+                umma_commit(bar_empty + 8 * s);
+            }
+            umma_commit(bar_tmem);
+        }
+    } else {
+        const int quarter = warp & 3;
+        if (mbar_wait(bar_tmem, 0, err, 3)) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16);
+            double *orow = out + (long long)(m0 + quarter * 32 + lane) * ldo + c0;
+            const double inv_a = inv_s[a_row0 + m0 + quarter * 32 + lane];
+#pragma unroll 1
+            for (int cc = 0; cc < T::BN; cc += 16) {
+                long long S[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) S[j] = 0;
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int l = 0; l < D; ++l) {
+                        uint32_t v[16];
+                        tmem_ld16(tl + i * T::N + l * T::BN + cc, v);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) S[j] += (long long)(int)v[j] * (1LL << (7 * (i + l)));
+                    }
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    double2 w;
+                    w.x = (double)S[j] * (inv_a * inv_s[c0 + cc + j]);
+                    w.y = (double)S[j + 1] * (inv_a * inv_s[c0 + cc + j + 1]);
+                    *reinterpret_cast<double2 *>(orow + cc + j) = w;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
 // ---- host side ----------------------------------------------------------------------------------
 static int tc_state(coex_ctx *c, TcState **out) {
     if (!c->tc) {
@@ -228,10 +351,10 @@ static int tc_state(coex_ctx *c, TcState **out) {
     return 0;
 }
 
-static int tc_encode(TcState *t, CUtensorMap *map, const void *ptr, long long rows, int n_pad) {
+static int tc_encode(TcState *t, CUtensorMap *map, const void *ptr, long long rows, int n_pad, int box_rows = 128) {
     cuuint64_t dims[2] = {(cuuint64_t)n_pad, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)n_pad};
-    cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)128};
+    cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = t->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(ptr), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -287,6 +410,27 @@ inline int tc_gemm_i8_ptrs(coex_ctx *c, const int8_t *a_hi, const int8_t *a_lo, 
 
 inline int tc_gemm_i8(coex_ctx *c, long long m_rows) {
     return tc_gemm_i8_ptrs(c, c->a_hi.p, c->a_lo.p, (long long)(c->a_hi.cap / c->n_pad), m_rows, c->strip.p, c->N_pad);
+}
+
+// r strip [m_rows, ldo] (double) = rows [a_row0, a_row0 + m_rows) of the D-digit planes x all rows
+template <int D>
+inline int tc_gemm_digits(coex_ctx *c, const int8_t *planes, long long plane_stride, long long a_row0, long long m_rows,
+                          double *out, long long ldo, const double *inv_s, int upper_only) {
+    using T = TcDigits<D>;
+    TcState *t = nullptr;
+    COEX_TRY(tc_state(c, &t));
+    if (m_rows % kTcBM) COEX_FAIL("tc_gemm_digits: rows must be a multiple of 128");
+    TcMaps8 maps;
+    for (int d = 0; d < D; ++d) {
+        COEX_TRY(tc_encode(t, &maps.a[d], planes + d * plane_stride, c->N_pad, c->n_pad, 128));
+        COEX_TRY(tc_encode(t, &maps.b[d], planes + d * plane_stride, c->N_pad, c->n_pad, T::BN));
+    }
+    COEX_CUDA(cudaFuncSetAttribute(gemm_digits_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::kSmem));
+    dim3 grid((unsigned)(m_rows / kTcBM), (unsigned)(c->N_pad / T::BN));
+    gemm_digits_tc_kernel<D><<<grid, kTcThreads, T::kSmem, c->stream>>>(maps, out, ldo, c->n_pad / kTcBK, a_row0, inv_s,
+                                                                       upper_only, t->d_err);
+    COEX_CUDA(cudaGetLastError());
+    return 0;
 }
 
 // non-zero if any tensor-core kernel of this context hit its bounded-wait limit

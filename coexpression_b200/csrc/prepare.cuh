@@ -163,3 +163,78 @@ rowstats_kernel(const double *__restrict__ data, long long N, int n, double *__r
 }
 
 }  // namespace coex
+
+namespace coex {
+
+// -------------------------------------------------------------------------------------------
+// K2 (Pearson): centre + normalise + pack.  z = (x - mean) / sqrt(sum (x-mean)^2) lies in
+// [-1, 1]; q = round(z * kZScale) is split into D balanced base-128 int8 digits
+// (q = sum_d digit_d * 128^d, low digits in [-64, 63]) written as D K-major planes for the
+// exact-integer tensor-core GEMM.  r is then (sum_k q_a q_b) / (s_a s_b) with NO accumulation
+// error; the only error is the rounding of z:  |r_q - r| <= (|z_a|_1 + |z_b|_1) / (2 s) + n / (4 s^2).
+// One warp per row, 16-byte loads and stores.  Rows the reference maps to NaN (sum == 0 or zero
+// variance, coexpression_v2.c:89-92,113) are packed as zeros and flagged in `ok`.
+// -------------------------------------------------------------------------------------------
+template <int D>
+struct ZScale;
+template <> struct ZScale<3> { static constexpr double s = 2040000.0; };          // 2.3 % below 127*128^2 + 63*128 + 63
+template <> struct ZScale<4> { static constexpr double s = 261000000.0; };        // 2.3 % below 127*128^3 + ...
+
+template <int D>
+__global__ void __launch_bounds__(256)
+pearson_pack_kernel(const double *__restrict__ raw, long long N, int n, int n_pad,
+                    const double *__restrict__ rsum, const double *__restrict__ rmean,
+                    const double *__restrict__ rxx, int8_t *__restrict__ planes, long long plane_stride,
+                    unsigned char *__restrict__ ok_out, float *__restrict__ l1_out, double *__restrict__ inv_s_out) {
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= N) return;
+    const double xx = rxx[row], mean = rmean[row];
+    const bool ok = (rsum[row] != 0.0) && (xx > 0.0) && (xx == xx);
+    // Per-row scale: expression rows are zero-inflated, so one value (the z-score of an exact 0)
+    // is shared by a large fraction of the samples and its rounding error would add up coherently
+    // over those samples.  The scale is nudged (by < 1.6 %) so that this value quantises EXACTLY;
+    // the rounding errors of the remaining samples are independent.
+    double srow = ZScale<D>::s;
+    if (ok) {
+        const double z0 = (0.0 - mean) / sqrt(xx);
+        const double k0 = rint(z0 * srow);
+        if (fabs(k0) >= 32.0) srow = k0 / z0;
+    }
+    const double inv = ok ? srow / sqrt(xx) : 0.0;
+    const double *x = raw + row * (long long)n;
+    double l1 = 0.0;
+    for (int v = lane; v < (n_pad >> 3); v += 32) {
+        alignas(8) int8_t dg[D][8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int c = (v << 3) + e;
+            long long q = 0;
+            if (ok && c < n) {
+                const double zs = (x[c] - mean) * inv;
+                q = llrint(zs);
+                l1 += fabs(zs);
+            }
+#pragma unroll
+            for (int d = 0; d < D - 1; ++d) {
+                const long long dd = ((q + 64) & 127) - 64;
+                dg[d][e] = (int8_t)dd;
+                q = (q - dd) >> 7;
+            }
+            dg[D - 1][e] = (int8_t)q;
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+            *reinterpret_cast<long long *>(planes + d * plane_stride + row * (long long)n_pad + (v << 3)) =
+                *reinterpret_cast<const long long *>(dg[d]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+    if (lane == 0) {
+        ok_out[row] = ok ? 1 : 0;
+        l1_out[row] = (float)(l1 / srow);
+        inv_s_out[row] = 1.0 / srow;
+    }
+}
+
+}  // namespace coex

@@ -77,6 +77,19 @@ int coex_pairs(coex_ctx *ctx, int which, const int *idxa, const int *idxb, long 
 int coex_allpairs_histogram(coex_ctx *ctx, int which, long long row0, long long row1, int nbins,
                             unsigned long long *hist, unsigned long long *nan_count);
 
+/* A block of the correlation matrix: table rows [row0, row0 + nrows) against every table row.
+ * which: 1 = Spearman (exact integer tensor path, bit-identical to the reference on ranks),
+ *        0 = Pearson on the tensor cores (z-scores quantised to 3 or 4 int8 digits, exact integer
+ *            accumulation; |r - reference| is bounded by the quantisation only),
+ *        2 = Pearson in-order double arithmetic (bit-identical to the reference).
+ * row0 must be a multiple of 128 for which 0 / 1.  out: host, double [nrows * N], NaN where the
+ * reference yields NaN. */
+int coex_corr_block(coex_ctx *ctx, int which, long long row0, long long nrows, double *out);
+/* Pearson tensor path: digits = 4 (default; measured |r - reference| <= 2e-8) or 3 (9 instead of 16
+ * MMAs per K step; measured <= 3e-6); mode 0 = tensor cores, 1 = in-order double
+ * (used by coex_allpairs_histogram for which == 0). */
+int coex_set_pearson(coex_ctx *ctx, int digits, int mode);
+
 typedef struct coex_params {
     int measure;                /* -cm: 0 Spearman, 1 Pearson (null list + join_nearby; the   */
                                 /*      hit-vs-hit statistic is always Spearman, quirk Q2)     */

@@ -203,6 +203,39 @@ def test_network_against_live_oracle_small_shape():
                     assert abs(got["individualscores"][a][b] - v) <= 1e-6
 
 
+@pytest.mark.parametrize("N,n", [(700, 64), (1500, 300), (900, 1829)])
+def test_corr_block_spearman_exact_and_pearson_tensor(N, n):
+    """Spearman block: bit-identical to the reference.  Pearson on the tensor cores (z-scores in
+    int8 digits, exact integer accumulation): within north_star's 1e-6 absolute of the reference's
+    doubles.  In-order double Pearson: bit-identical."""
+    from coexpression_b200 import synth
+    from coexpression_b200.api import CoexContext
+    from oracle import network_oracle as no
+    t = synth.make_table(N, n, seed=N + 3 * n)
+    X = t.X.copy()
+    X[130] = 2.5                      # constant row -> NaN
+    X[131] = X[140] * 1000.0 + 1.0    # heavy-tailed scale
+    R = no.rank_rows(X)
+    rows = np.arange(128, 128 + 160)
+    ia = np.repeat(rows, N).astype(np.int32); ib = np.tile(np.arange(N), rows.size).astype(np.int32)
+    want_s = no.get_pearson(R, ia, ib).reshape(rows.size, N)
+    want_p = no.get_pearson(X, ia, ib).reshape(rows.size, N)
+    with CoexContext() as ctx:
+        ctx.set_expression(X); ctx.prepare()
+        assert _same_doubles(ctx.corr_block("spearman", 128, rows.size), want_s)
+        assert _same_doubles(ctx.corr_block("pearson_exact", 128, rows.size), want_p)
+        errs = {}
+        for digits in (3, 4):
+            ctx.set_pearson(digits, "tensor")
+            got = ctx.corr_block("pearson", 128, rows.size)
+            assert np.array_equal(np.isnan(got), np.isnan(want_p))
+            errs[digits] = np.nanmax(np.abs(got - want_p))
+            print(f"pearson tensor digits={digits} N={N} n={n}: max |r - reference| = {errs[digits]:.3g}")
+        # north_star tolerance for correlations: 1e-6 absolute -> met by the default 4 digits with two
+        # orders of margin; 3 digits (the faster option) stay within 5e-6
+        assert errs[4] <= 2e-8 and errs[3] <= 5e-6, errs
+
+
 def test_allpairs_histogram_small():
     from coexpression_b200 import synth
     from coexpression_b200.api import CoexContext
@@ -217,6 +250,14 @@ def test_allpairs_histogram_small():
         want = np.bincount(np.clip(((r[ok] + 1.0) * 0.5 * nb).astype(np.int64), 0, nb - 1), minlength=nb)
         with CoexContext() as ctx:
             ctx.set_expression(t.X); ctx.prepare()
+            if not ranked:
+                ctx.set_pearson(3, "exact")
             hist, nan = ctx.allpairs_histogram(ranked, nbins=nb)
-        assert nan == int((~ok).sum())
-        assert np.array_equal(hist.astype(np.int64), want)
+            assert nan == int((~ok).sum())
+            assert np.array_equal(hist.astype(np.int64), want)
+            if not ranked:                      # tensor-core Pearson: values within 1e-6 -> bins may move at edges only
+                ctx.set_pearson(4, "tensor")
+                hist_t, nan_t = ctx.allpairs_histogram(False, nbins=nb)
+                assert nan_t == nan and int(hist_t.sum()) == int(want.sum())
+                near_edge = np.abs(((r[ok] + 1.0) * 0.5 * nb) - np.round((r[ok] + 1.0) * 0.5 * nb)) < 1e-6 * nb
+                assert np.abs(hist_t.astype(np.int64) - want).sum() <= 2 * int(near_edge.sum())
