@@ -105,7 +105,7 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
             Pq[(size_t)q] = (int)(perm_off[k + 1] - perm_off[k]);
         }
     const long long U = (long long)uniq.size();
-    const int Tcap = std::max(4096, (int)round_up(Pmax, 256));
+    const int Tcap = std::max(kDdBuckets / 2, (int)round_up(Pmax, 256));   // 2*Tcap >= buckets: the bucket cursors alias thr32|hist
     // ---- strips of unique rows ------------------------------------------------------------------------
     const long long ld = c->N_pad;
     long long Us = (c->strip_mb << 20) / (ld * 4);
@@ -139,7 +139,8 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     Qcap = (Qcap + 1) & ~1;
     COEX_TRY(c->dd_items.reserve(std::max<size_t>(items.size(), 1) * sizeof(DedupItem)));
     COEX_CUDA(cudaMemcpyAsync(c->dd_items.p, items.data(), items.size() * sizeof(DedupItem), cudaMemcpyHostToDevice, st));
-    const size_t smem = dedup_smem_bytes(Tcap, Qcap);
+    const int bm_words = (N <= 262144) ? (int)((N + 31) / 32) : 0;     // hit-column bitmap (<= 32 KB)
+    const size_t smem = dedup_smem_bytes(Tcap, Qcap, bm_words);
     if (smem > 227 * 1024) COEX_FAIL("count_dedup: too many queries of one table row for shared memory");
     COEX_CUDA(cudaFuncSetAttribute(count_dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
@@ -150,6 +151,9 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     score_table_kernel<<<(unsigned)((N + 256) / 256), 256, 0, st>>>(c->dd_tab.p, N, prm->anticorrelation);
     COEX_CUDA(cudaGetLastError());
     c->launches += 1;
+    DevBuf<unsigned long long> phase;
+    const bool dbg = getenv("COEX_COUNT_DEBUG") != nullptr;
+    if (dbg) { COEX_TRY(phase.reserve(8)); COEX_CUDA(cudaMemsetAsync(phase.p, 0, 8 * sizeof(unsigned long long), st)); }
     size_t s_idx = 0;
     for (long long u0 = 0; u0 < U; u0 += Us, ++s_idx) {
         const long long nu = std::min(Us, U - u0);
@@ -162,7 +166,9 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
         da.perm_off = c->d_perm_off.p; da.sc_off = c->d_sc_off.p; da.K = K; da.hit_rows = d_hits;
         da.sx = c->sx.p; da.icol = c->icol.p; da.rawsum_pos = c->rawsum_pos.p; da.N = N;
         da.n_degenerate = c->n_degenerate; da.anticor = prm->anticorrelation; da.scores = d_sc; da.counts = d_cn;
-        da.Tcap = Tcap; da.Qcap = Qcap; da.g_thr = c->dd_gthr.p; da.g_org = c->dd_gorg.p; da.score_tab = c->dd_tab.p;
+        da.Tcap = Tcap; da.Qcap = Qcap;
+        da.bm_words = bm_words;
+        da.R = std::min(1.0, std::max(0.05, 8.0 / std::sqrt((double)std::max(c->n, 2)))); da.g_thr = c->dd_gthr.p; da.g_org = c->dd_gorg.p; da.score_tab = c->dd_tab.p; da.phase_clk = dbg ? phase.p : nullptr;
         COEX_TRY(stage_begin(c, ST_COUNT));
         count_dedup_kernel<<<std::min(grid_max, std::max(da.n_items, 1)), kDdThreads, smem, st>>>(da);
         COEX_KCHECK(st);
@@ -170,6 +176,14 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     }
     // the host vectors above feed async copies: they must be consumed before this frame dies
     COEX_CUDA(cudaStreamSynchronize(st));
+    if (dbg) {
+        unsigned long long h[8];
+        COEX_CUDA(cudaMemcpy(h, phase.p, sizeof h, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[coex count] items=%llu queued=%llu cycles/item: meta=%llu stats=%llu rank=%llu stream=%llu refine=%llu score=%llu (Tcap=%d Qcap=%d grid<=%d)\n",
+                h[6], h[7], h[0] / std::max(1ULL, h[6]), h[1] / std::max(1ULL, h[6]), h[2] / std::max(1ULL, h[6]), h[3] / std::max(1ULL, h[6]),
+                h[4] / std::max(1ULL, h[6]), h[5] / std::max(1ULL, h[6]), Tcap, Qcap, grid_max);
+        phase.release();
+    }
     return 0;
 }
 
@@ -350,7 +364,7 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
         na.P2max = T2max;
     }
     std::vector<long long> warp_off(K + 1, 0);
-    for (int k = 0; k < K; ++k) warp_off[k + 1] = warp_off[k] + std::max<long long>(1, (perm_off[k + 1] - perm_off[k] + 31) / 32);
+    for (int k = 0; k < K; ++k) warp_off[k + 1] = warp_off[k] + std::max<long long>(1, (perm_off[k + 1] - perm_off[k] + kRsRows - 1) / kRsRows);
     COEX_TRY(c->d_warp_off.reserve(K + 1));
     COEX_CUDA(cudaMemcpyAsync(c->d_warp_off.p, warp_off.data(), (K + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
     na.warp_off = c->d_warp_off.p;

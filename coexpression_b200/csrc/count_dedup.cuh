@@ -10,23 +10,24 @@
 //     its queries.  Quirk Q1 (the null list of hit position i omits table column i) becomes a
 //     per-query correction: idx = #{all columns below t} - [value at column i below t].
 //  2. Bucket table instead of a 10..13-step binary search: statistics are counting-sorted into
-//     4096 uniform buckets of [-1, 1] (ranked inside their bucket), a streamed value finds its
-//     bucket with one multiply and searches only the few statistics sharing it.
-//  3. fp32 pre-filter with exact fp64 refinement: the value and the bucket search are done in
-//     float; whenever the float result could differ from the double one (value within 5e-7 of a
-//     statistic or of a bucket edge, ~1-2 % of values) the column is queued and redone in double
-//     with the reference's exact arithmetic.  Counts are therefore still EXACT.
+//     8192 uniform buckets of [-R, R] (R ~ 8 standard deviations of a null correlation; values
+//     outside land in the edge buckets) and ranked inside their bucket; a streamed value finds its
+//     bucket with one multiply-add and searches only the statistics of that bucket and its two
+//     neighbours (so a float bucket index that is off by one is harmless).
+//  3. fp32 pre-filter with exact fp64 refinement: the value and the search are done in float;
+//     whenever the float result could differ from the double one (a statistic within 5e-7 of the
+//     value, < 1 % of values) the column is queued and redone in double with the reference's
+//     exact arithmetic.  Counts are therefore still EXACT.
 #pragma once
 #include "common.cuh"
 #include "count.cuh"
 
 namespace coex {
 
-constexpr int kDdThreads = 256;
-constexpr int kDdBuckets = 4096;
+constexpr int kDdThreads = 512;
+constexpr int kDdBuckets = 8192;
 constexpr int kDdQueue = 2048;
 constexpr float kDdDelta = 5e-7f;        // |v32 - v64| <= 3e-7, |t32 - t64| <= 6e-8  
-constexpr float kDdEdge = 2e-3f;         // same bound in bucket units (x 2048) with margin
 
 struct DedupItem {
     int urow;        // index into the strip (unique-row slot)
@@ -53,35 +54,42 @@ struct DedupArgs {
     double *scores;
     long long *counts;
     int Tcap, Qcap;                 // shared-memory capacities (statistics, queries per item)
+    double R;                       // bucket range [-R, R]
+    int bm_words;                   // 32-bit words of the hit-column bitmap (0 = table too long, bitmap disabled)
     double *g_thr;                  // scratch [gridDim.x, 3, Tcap]: unsorted | grouped | sorted statistics
     unsigned int *g_org;            // scratch [gridDim.x, 2, Tcap]: grouped | sorted origins
     const double *score_tab;        // [N+1] edge score of every possible bisect index (len = N-1)
+    unsigned long long *phase_clk;  // optional [8]: summed clock64 per phase over all CTAs (profiling aid)
 };
 
-__device__ __forceinline__ int dd_bucket64(double t) {
-    int b = (int)((t + 1.0) * (double)(kDdBuckets / 2));
-    return b < 0 ? 0 : (b >= kDdBuckets ? kDdBuckets - 1 : b);
+__device__ __forceinline__ int dd_bucket64(double t, double R, double scale) {
+    const double f = (t + R) * scale;
+    if (!(f > 0.0)) return 0;
+    return f >= (double)kDdBuckets ? kDdBuckets - 1 : (int)f;
 }
 
 __global__ void __launch_bounds__(kDdThreads)
 count_dedup_kernel(DedupArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: q_vi[Qcap] | thr32[Tcap] | hist[Tcap+4] (= cursor[B]) | lut[B+4] | queue[kDdQueue] | q_k q_i q_toff
+    // layout: q_vi[Qcap] | thr32[Tcap] | hist[Tcap+4] (thr32|hist = cursor[B] during step B) | lut[B+4] | queue[kDdQueue] | q_k q_i q_toff
     // (the double statistics and their origins live in an L2-resident per-CTA scratch: they are only
     //  touched by the rare exact refinements and by the final scoring)
     double *q_vi = reinterpret_cast<double *>(smem_raw);                      // [Qcap] exact null value at the skipped column
     float *thr32 = reinterpret_cast<float *>(q_vi + a.Qcap);
     unsigned int *hist = reinterpret_cast<unsigned int *>(thr32 + a.Tcap);
     unsigned int *lut = hist + a.Tcap + 4;
-    unsigned int *cursor = hist;                 // bucket cursors alias hist (dead until step C; Tcap >= 4096)
+    unsigned int *cursor = reinterpret_cast<unsigned int *>(thr32);   // bucket cursors alias thr32|hist (both dead until step C; 2*Tcap >= buckets)
     int *queue = reinterpret_cast<int *>(lut + kDdBuckets + 4);
     int *q_k = queue + kDdQueue;                 // [Qcap] permutation
     int *q_i = q_k + a.Qcap;                     // [Qcap] hit position
     int *q_toff = q_i + a.Qcap;                  // [Qcap+1] offset of the query's statistics in the item
+    unsigned int *bitmap = reinterpret_cast<unsigned int *>(q_toff + a.Qcap + 2);   // [bm_words] columns that are hit columns of this item
     __shared__ int s_T, s_qn;
     __shared__ unsigned int s_warp[kDdThreads / 32];
 
     const int tid = threadIdx.x;
+    const double bscale = (double)kDdBuckets / (2.0 * a.R);
+    const float bscale_f = (float)bscale, R_f = (float)a.R;
     double *tmp_r = a.g_thr + (long long)blockIdx.x * 3 * a.Tcap;      // statistic of flat index t (-99 = undefined)
     double *g_thr = tmp_r + a.Tcap;                                    // grouped by bucket
     double *thr64 = g_thr + a.Tcap;                                    // sorted
@@ -96,6 +104,8 @@ count_dedup_kernel(DedupArgs a) {
         const double sxu = a.sx[u];
         const bool posu = a.rawsum_pos[u] != 0;
         __syncthreads();                                   // previous item fully retired
+        long long tclk = clock64();
+#define DD_PHASE(id) do { if (a.phase_clk && tid == 0) { const long long now = clock64(); atomicAdd(&a.phase_clk[id], (unsigned long long)(now - tclk)); tclk = now; } } while (0)
         // ---- A. query metadata ----------------------------------------------------------------
         for (int ql = tid; ql < nq; ql += kDdThreads) {
             const long long q = a.qlist[item.qb + ql];
@@ -111,6 +121,7 @@ count_dedup_kernel(DedupArgs a) {
         }
         if (tid == 0) { s_T = 0; s_qn = 0; }
         for (int b = tid; b <= kDdBuckets; b += kDdThreads) lut[b] = 0;
+        for (int wd = tid; wd < a.bm_words; wd += kDdThreads) bitmap[wd] = 0;
         __syncthreads();
         if (tid == 0) {
             int acc = 0;
@@ -122,6 +133,7 @@ count_dedup_kernel(DedupArgs a) {
         }
         __syncthreads();
         const int TP = q_toff[nq];
+        DD_PHASE(0);
         // ---- B. statistics: pass 0 evaluates them once and counts per bucket, pass 1 groups them -----
         for (int pass = 0; pass < 2; ++pass) {
             for (int t = tid; t < TP; t += kDdThreads) {
@@ -134,8 +146,10 @@ count_dedup_kernel(DedupArgs a) {
                     const int P = (int)(a.perm_off[k + 1] - off);
                     const long long w = a.sc_off[k] + (long long)i * P + j;
                     double r = -99.0;
+                    int c_hit = 0;
                     if (j != i) {
                         const int c = a.hit_rows[off + j];
+                        c_hit = c;
                         if (posu && a.rawsum_pos[c]) {                          // coexfunctions.py:389
                             r = __ddiv_rn(0.25 * (double)srow[c], __dmul_rn(sxu, a.sx[c]));
                             if (r != r) r = -99.0;                              // coexfunctions.py:406-408
@@ -146,12 +160,15 @@ count_dedup_kernel(DedupArgs a) {
                         a.scores[w] = (j == i) ? 0.0 : -log10(1.0);
                         if (a.counts) a.counts[w] = -1;
                     } else {
-                        atomicAdd(&lut[dd_bucket64(r)], 1u);
+                        atomicAdd(&lut[dd_bucket64(r, a.R, bscale)], 1u);
+                        // the null value of a hit column IS this statistic (same arithmetic): it is
+                        // accounted exactly in step C' and skipped by the float streaming pass
+                        if (a.bm_words) atomicOr(&bitmap[c_hit >> 5], 1u << (c_hit & 31));
                     }
                 } else {
                     const double r = tmp_r[t];
                     if (r != -99.0) {
-                        const int b = dd_bucket64(r);
+                        const int b = dd_bucket64(r, a.R, bscale);
                         const unsigned int pos = lut[b] + atomicAdd(&cursor[b], 1u);
                         g_thr[pos] = r;
                         g_org[pos] = ((unsigned int)ql << 13) | (unsigned int)j;
@@ -179,12 +196,13 @@ count_dedup_kernel(DedupArgs a) {
             }
         }
         const int T = s_T;
+        DD_PHASE(1);
         if (T == 0) continue;                               // every statistic undefined: scores already written
         __threadfence_block();
         // ---- C. rank inside the bucket -> fully sorted statistics in shared memory ----------------
         for (int e = tid; e < T; e += kDdThreads) {
             const double t = g_thr[e];
-            const int b = dd_bucket64(t);
+            const int b = dd_bucket64(t, a.R, bscale);
             const int lo = (int)lut[b], hi = (int)lut[b + 1];
             int rank = 0;
             for (int m = lo; m < hi; ++m) {
@@ -197,63 +215,111 @@ count_dedup_kernel(DedupArgs a) {
         }
         for (int p = tid; p <= T; p += kDdThreads) hist[p] = 0;
         __syncthreads();
+        // ---- C'. hit columns: value == statistic exactly; the first statistic to claim a column adds it
+        if (a.bm_words) {
+            for (int sidx = tid; sidx < T; sidx += kDdThreads) {
+                const unsigned int o = org[sidx];
+                const int ql = (int)(o >> 13), j = (int)(o & 8191u);
+                const int c = a.hit_rows[a.perm_off[q_k[ql]] + j];
+                const unsigned int bit = 1u << (c & 31);
+                if (atomicAnd(&bitmap[c >> 5], ~bit) & bit) {
+                    const double t = thr64[sidx];
+                    int e2 = sidx + 1;
+                    while (e2 < T && thr64[e2] == t) ++e2;            // statistics <= value: through the run of equals
+                    atomicAdd(&hist[e2], 1u);
+                }
+            }
+            // re-arm the bitmap for the streaming pass: every column that has a statistic is skipped there
+            __syncthreads();
+            for (int sidx = tid; sidx < T; sidx += kDdThreads) {
+                const unsigned int o = org[sidx];
+                const int c = a.hit_rows[a.perm_off[q_k[(int)(o >> 13)]] + (int)(o & 8191u)];
+                atomicOr(&bitmap[c >> 5], 1u << (c & 31));
+            }
+            __syncthreads();
+        }
+        DD_PHASE(2);
         // ---- D. stream the null values of table row u (fp32 fast path) -----------------------------
         const float iu = (float)(0.5 / sxu);
         const long long N = a.N;
-        for (long long c0 = (long long)tid * 4; c0 < N; c0 += kDdThreads * 4) {
-            const int4 s4 = *reinterpret_cast<const int4 *>(srow + c0);
-            const float4 w4 = *reinterpret_cast<const float4 *>(a.icol + c0);
-            const int sv[4] = {s4.x, s4.y, s4.z, s4.w};
-            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+        // Four columns per thread are handled in lockstep (independent shared-memory chains overlap)
+        // and the next 16-byte strip / norm loads are issued before the current ones are consumed.
+        {
+            long long c0 = (long long)tid * 4;
+            bool have = c0 < N;
+            int4 s4n = make_int4(0, 0, 0, 0);
+            float4 w4n = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (have) { s4n = *reinterpret_cast<const int4 *>(srow + c0); w4n = *reinterpret_cast<const float4 *>(a.icol + c0); }
+            while (have) {
+                const int sv[4] = {s4n.x, s4n.y, s4n.z, s4n.w};
+                const float wv[4] = {w4n.x, w4n.y, w4n.z, w4n.w};
+                const long long cc = c0;
+                const unsigned int skip4 = a.bm_words ? (bitmap[cc >> 5] >> (cc & 31)) & 15u : 0u;   // cc % 4 == 0
+                c0 += kDdThreads * 4;
+                have = c0 < N;
+                if (have) { s4n = *reinterpret_cast<const int4 *>(srow + c0); w4n = *reinterpret_cast<const float4 *>(a.icol + c0); }
+                float v[4];
+                int p[4], lo[4], hi[4], len[4];
+                bool act[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (wv[e] == 0.0f || c0 + e >= N) continue;            // zero-variance column: -99, counted in bulk
-                const float v = __int2float_rn(sv[e]) * (iu * wv[e]);
-                const float f = (v + 1.0f) * (float)(kDdBuckets / 2);
-                int b = (int)f;
-                const float fr = f - floorf(f);
-                bool amb = (fr < kDdEdge) || (fr > 1.0f - kDdEdge);
-                b = b < 0 ? 0 : (b >= kDdBuckets ? kDdBuckets - 1 : b);
-                int lo = (int)lut[b];
-                const int hi = (int)lut[b + 1];
-                int p = lo;
-                if (!amb) {
-                    // statistics of this bucket: count those <= v, flag any within delta
-                    int len = hi - lo;
-                    while (len > 0) {
-                        const int half = len >> 1;
-                        if (thr32[p + half] <= v) { p += half + 1; len -= half + 1; } else len = half;
-                    }
-                    if (p > lo && v - thr32[p - 1] < kDdDelta) amb = true;
-                    if (p < hi && thr32[p] - v < kDdDelta) amb = true;
+                for (int e = 0; e < 4; ++e) {
+                    // zero-variance column: -99, counted in bulk; hit column: accounted exactly in step C'
+                    act[e] = (wv[e] != 0.0f) && (cc + e < N) && !((skip4 >> e) & 1u);
+                    v[e] = __int2float_rn(sv[e]) * (iu * wv[e]);
+                    // bucket of v, possibly off by one in float: search the bucket and both neighbours
+                    const float f = (v[e] + R_f) * bscale_f;
+                    int bkt = (f > 0.0f) ? (int)f : 0;
+                    bkt = bkt >= kDdBuckets ? kDdBuckets - 1 : bkt;
+                    lo[e] = (int)lut[bkt > 0 ? bkt - 1 : 0];
+                    hi[e] = (int)lut[bkt + 2 <= kDdBuckets ? bkt + 2 : kDdBuckets];
+                    p[e] = lo[e];
+                    len[e] = act[e] ? hi[e] - lo[e] : 0;
                 }
-                if (!amb) {
-                    atomicAdd(&hist[p], 1u);
-                } else {
-                    const int slot = atomicAdd(&s_qn, 1);
-                    if (slot < kDdQueue) {
-                        queue[slot] = (int)(c0 + e);
-                    } else {                                                  // queue full: refine in place
-                        const double vv = __ddiv_rn(0.25 * (double)sv[e], __dmul_rn(sxu, a.sx[c0 + e]));
-                        const int bb = dd_bucket64(vv);
-                        int pp = (int)lut[bb];
-                        int len = (int)lut[bb + 1] - pp;
-                        while (len > 0) {
-                            const int half = len >> 1;
-                            if (thr64[pp + half] <= vv) { pp += half + 1; len -= half + 1; } else len = half;
+                while ((len[0] | len[1] | len[2] | len[3]) > 0) {         // statistics <= v in [lo, hi)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (len[e] > 0) {
+                            const int half = len[e] >> 1;
+                            if (thr32[p[e] + half] <= v[e]) { p[e] += half + 1; len[e] -= half + 1; } else len[e] = half;
                         }
-                        atomicAdd(&hist[pp], 1u);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (!act[e]) continue;
+                    // a statistic closer than delta cannot be ordered in float (those outside [lo, hi)
+                    // are at least a whole bucket away)
+                    const float below = (p[e] > lo[e]) ? v[e] - thr32[p[e] - 1] : 1.0f;
+                    const float above = (p[e] < hi[e]) ? thr32[p[e]] - v[e] : 1.0f;
+                    if (fminf(below, above) >= kDdDelta) {
+                        atomicAdd(&hist[p[e]], 1u);
+                    } else {
+                        const int slot = atomicAdd(&s_qn, 1);
+                        if (slot < kDdQueue) {
+                            queue[slot] = (int)(cc + e);
+                        } else {                                          // queue full: refine in place
+                            const double vv = __ddiv_rn(0.25 * (double)sv[e], __dmul_rn(sxu, a.sx[cc + e]));
+                            const int bb = dd_bucket64(vv, a.R, bscale);
+                            int pp = (int)lut[bb];
+                            int ln = (int)lut[bb + 1] - pp;
+                            while (ln > 0) {
+                                const int half = ln >> 1;
+                                if (thr64[pp + half] <= vv) { pp += half + 1; ln -= half + 1; } else ln = half;
+                            }
+                            atomicAdd(&hist[pp], 1u);
+                        }
                     }
                 }
             }
         }
         __syncthreads();
+        DD_PHASE(3);
         // ---- E. exact refinement of the queued columns ------------------------------------------
         const int qn = min(s_qn, kDdQueue);
         for (int x = tid; x < qn; x += kDdThreads) {
             const int c = queue[x];
             const double vv = __ddiv_rn(0.25 * (double)srow[c], __dmul_rn(sxu, a.sx[c]));
-            const int bb = dd_bucket64(vv);
+            const int bb = dd_bucket64(vv, a.R, bscale);
             int pp = (int)lut[bb];
             int len = (int)lut[bb + 1] - pp;
             while (len > 0) {
@@ -263,6 +329,7 @@ count_dedup_kernel(DedupArgs a) {
             atomicAdd(&hist[pp], 1u);
         }
         __syncthreads();
+        DD_PHASE(4);
         // ---- F. inclusive prefix sum of hist[0..T), scores ----------------------------------------
         {
             const int per = (T + 1 + kDdThreads - 1) / kDdThreads;
@@ -294,6 +361,8 @@ count_dedup_kernel(DedupArgs a) {
             a.scores[w] = (len == N - 1) ? a.score_tab[idx] : edge_score_dev(idx, len, a.anticor);
             if (a.counts) a.counts[w] = idx;
         }
+        DD_PHASE(5);
+        if (a.phase_clk && tid == 0) { atomicAdd(&a.phase_clk[6], 1ULL); atomicAdd(&a.phase_clk[7], (unsigned long long)s_qn); }
     }
 }
 
@@ -318,9 +387,9 @@ __global__ void icol_kernel(const double *__restrict__ sx, long long N, long lon
     if (threadIdx.x == 0 && deg) atomicAdd(n_degenerate, deg);
 }
 
-inline size_t dedup_smem_bytes(int Tcap, int Qcap) {
+inline size_t dedup_smem_bytes(int Tcap, int Qcap, int bm_words) {
     return (size_t)Qcap * 8 + (size_t)Tcap * 4 + (size_t)(Tcap + 4) * 4 + (size_t)(kDdBuckets + 4) * 4 +
-           (size_t)kDdQueue * 4 + (size_t)Qcap * 4 * 2 + (size_t)(Qcap + 2) * 4 + 16;
+           (size_t)kDdQueue * 4 + (size_t)Qcap * 4 * 2 + (size_t)(Qcap + 2) * 4 + (size_t)bm_words * 4 + 16;
 }
 
 }  // namespace coex

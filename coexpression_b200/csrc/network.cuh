@@ -247,7 +247,7 @@ __device__ __forceinline__ int perm_of(const long long *perm_off, int K, long lo
     return lo;
 }
 
-// Ordered row sums, shared by pass 1, pass 2 and the density / removal sums.  A warp owns 32
+// Ordered row sums, shared by pass 1, pass 2 and the density / removal sums.  A warp owns kRsRows
 // consecutive rows of ONE permutation.  For every chunk of 32 columns the warp fetches, row by
 // row, the 32 addends (lane = column: coalesced for pass 1, a near-contiguous gather of winner
 // columns otherwise) into a 32 x 33 shared-memory tile; then lane l adds row l left to right.
@@ -256,12 +256,13 @@ __device__ __forceinline__ int perm_of(const long long *perm_off, int K, long lo
 //   MODE 1  pass 2  (1-make-network.py:378-434)  columns = winners, group order (fixed-point round)
 //   MODE 2  density (1-make-network.py:437-462)  rows = groups (their winner's row)
 //   MODE 3  whittled density (1-make-network.py:471-478)
-constexpr int kRsWarps = 4;
+constexpr int kRsWarps = 8;
+constexpr int kRsRows = 8;          // rows per warp: more warps in flight than 32-row blocks, one memory latency per chunk
 
 template <int MODE>
 __global__ void __launch_bounds__(kRsWarps * 32)
 net_rowsum_kernel(NetArgs a) {
-    __shared__ double tiles[kRsWarps][32 * 33];
+    __shared__ double tiles[kRsWarps][kRsRows * 33];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long w = (long long)blockIdx.x * kRsWarps + wib;
     if (w >= a.warp_off[a.K]) return;
@@ -273,14 +274,14 @@ net_rowsum_kernel(NetArgs a) {
     const int G = a.n_groups[k];
     const int nrows = (MODE <= 1) ? P : G;
     const int ncols = (MODE == 0) ? P : G;
-    const int i0 = (int)(w - a.warp_off[k]) * 32;
+    const int i0 = (int)(w - a.warp_off[k]) * kRsRows;
     if (i0 >= nrows) return;
     double *tile = tiles[wib];
     const int *grp = a.group_of_hit + off;
     const int *win = a.group_winner + off, *w1 = a.w_pos + off, *vis = a.w_root + off;
     const double *Sc = a.scores + a.sc_off[k];
     const int mine = i0 + lane;                                   // this lane's row
-    const bool mine_ok = mine < nrows;
+    const bool mine_ok = (lane < kRsRows) && (mine < nrows);
     // row attributes held by lane r for row i0 + r
     const int my_g = mine_ok ? ((MODE <= 1) ? grp[mine] : mine) : -1;        // group of the row
     const long long my_base = mine_ok ? (long long)((MODE <= 1) ? mine : win[mine]) * P : 0;
@@ -295,9 +296,9 @@ net_rowsum_kernel(NetArgs a) {
             else { col_a = win[c]; col_b = (MODE == 1) ? w1[c] : col_a; gcol = c; if (MODE == 3) vcol = vis[c]; }
         }
         // issue all 32 loads of the chunk before the first use: one memory latency per chunk
-        double x[32];
+        double x[kRsRows];
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
+        for (int r = 0; r < kRsRows; ++r) {
             const int rg = __shfl_sync(0xffffffffu, my_g, r);
             const long long rb = __shfl_sync(0xffffffffu, my_base, r);
             const int rvis = (MODE == 3) ? __shfl_sync(0xffffffffu, my_vis, r) : 0;
@@ -309,7 +310,7 @@ net_rowsum_kernel(NetArgs a) {
         }
         __syncwarp();
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
+        for (int r = 0; r < kRsRows; ++r) {
             double v = x[r];
             if (MODE != 1 && !(v >= a.thr)) v = 0.0;           // selection threshold (not applied in pass 2)
             tile[r * 33 + lane] = v;
