@@ -244,7 +244,8 @@ class CoexContext:
         check(self.lib.coex_sync(self.h), "coex_sync")
 
     def set_gemm_mode(self, mode):
-        check(self.lib.coex_set_gemm_mode(self.h, {"tcgen05": 0, "simt": 1}.get(mode, mode)), "coex_set_gemm_mode")
+        check(self.lib.coex_set_gemm_mode(self.h, {"tcgen05": 0, "simt": 1, "tcgen05_bn64": 64, "tcgen05_bn128": 128}.get(mode, mode)),
+              "coex_set_gemm_mode")
 
     def set_count_mode(self, mode):
         check(self.lib.coex_set_count_mode(self.h, {"dedup": 0, "per_query": 1}.get(mode, mode)), "coex_set_count_mode")

@@ -145,6 +145,7 @@ struct coex_ctx {
     coex::DevBuf<double> p_out;
     long long strip_mb = 1024;
     int gemm_mode = 0;
+    int gemm_bn = 128;                        // tcgen05 column tile: 128 (1 CTA/SM) or 64 (2 CTAs/SM)
 
     // ---- bookkeeping ------------------------------------------------------------------------
     long long launches = 0;

@@ -28,10 +28,7 @@
 namespace coex {
 
 constexpr int kTcBM = 128, kTcBN = 128, kTcBK = 128;      // BK in bytes (= int8 elements)
-constexpr int kTcStages = 3;
-constexpr int kTcStageBytes = 65536;                      // A_hi 16K | A_lo 16K | B_hi 16K | B_lo 16K
 constexpr int kTcThreads = 192;
-constexpr int kTcSmemBytes = kTcStages * kTcStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 constexpr unsigned kTcSpinLimit = 1u << 22;   // bounded mbarrier polls (~seconds) -> error, not a hang
 
 struct TcState {
@@ -40,6 +37,7 @@ struct TcState {
     const void *bh = nullptr, *bl = nullptr, *ah = nullptr, *al = nullptr;
     long long b_rows = 0, a_rows = 0;
     int n_pad = 0;
+    int bn = 0;
     int *d_err = nullptr;
     bool attr_set = false;
 };
@@ -108,26 +106,40 @@ __host__ __device__ constexpr uint32_t umma_idesc_i8(int M, int N) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+// BN = 128: one CTA per SM, 3 stages of 64 KB, all 512 TMEM columns.
+// BN = 64 : two CTAs per SM (2 stages of 48 KB, 256 TMEM columns each): while one CTA drains its
+//           accumulators the other one's MMAs keep the tensor pipe busy, which hides the epilogue
+//           without a persistent scheduler.
+template <int BN> struct TcCfg {
+    static constexpr int kStage = 32768 + 2 * BN * 128;            // A_hi 16K | A_lo 16K | B_hi | B_lo
+    static constexpr int kStages = (BN == 128) ? 3 : 2;
+    static constexpr int kCols = 4 * BN;                            // TMEM columns: [hh|hl] [lh|ll]
+    static constexpr int kSmem = kStages * kStage + 1024 + 256;
+    static constexpr int kMinBlocks = (BN == 128) ? 1 : 2;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kTcThreads, TcCfg<BN>::kMinBlocks)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                   const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
                   int *__restrict__ out, long long ldo, int nkb, int *err) {
+    using C = TcCfg<BN>;
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;          // SWIZZLE_128B: 1024-B aligned
-    const uint32_t bars = base + kTcStages * kTcStageBytes;               // full[3], empty[3], tmem_full, slot
-    const uint32_t bar_full = bars, bar_empty = bars + 8 * kTcStages, bar_tmem = bars + 16 * kTcStages;
+    const uint32_t bars = base + C::kStages * C::kStage;                  // full[], empty[], tmem_full, slot
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * C::kStages, bar_tmem = bars + 16 * C::kStages;
     const uint32_t tmem_slot = bar_tmem + 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * kTcBM;           // query-row tile (fastest)
-    const int c0 = blockIdx.y * kTcBN;           // table-column tile
+    const int c0 = blockIdx.y * BN;              // table-column tile
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kTcStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < C::kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_tmem, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::kCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -140,35 +152,35 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
         // ===== TMA producer =====
         if (lane == 0) {
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % kTcStages;
-                if (kb >= kTcStages && !mbar_wait(bar_empty + 8 * s, ((kb / kTcStages) - 1) & 1, err, 1)) break;
-                const uint32_t st = base + s * kTcStageBytes;
-                mbar_expect_tx(bar_full + 8 * s, kTcStageBytes);
+                const int s = kb % C::kStages;
+                if (kb >= C::kStages && !mbar_wait(bar_empty + 8 * s, ((kb / C::kStages) - 1) & 1, err, 1)) break;
+                const uint32_t st = base + s * C::kStage;
+                mbar_expect_tx(bar_full + 8 * s, C::kStage);
                 tma_load_2d(st, &map_ah, bar_full + 8 * s, kb * kTcBK, m0);
                 tma_load_2d(st + 16384, &map_al, bar_full + 8 * s, kb * kTcBK, m0);
                 tma_load_2d(st + 32768, &map_bh, bar_full + 8 * s, kb * kTcBK, c0);
-                tma_load_2d(st + 49152, &map_bl, bar_full + 8 * s, kb * kTcBK, c0);
+                tma_load_2d(st + 32768 + BN * 128, &map_bl, bar_full + 8 * s, kb * kTcBK, c0);
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_i8(128, 256);
+            constexpr uint32_t idesc = umma_idesc_i8(128, 2 * BN);
             bool ok = true;
             for (int kb = 0; kb < nkb && ok; ++kb) {
-                const int s = kb % kTcStages;
-                ok = mbar_wait(bar_full + 8 * s, (kb / kTcStages) & 1, err, 2);
+                const int s = kb % C::kStages;
+                ok = mbar_wait(bar_full + 8 * s, (kb / C::kStages) & 1, err, 2);
                 if (!ok) break;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t st = base + s * kTcStageBytes;
+                const uint32_t st = base + s * C::kStage;
 #pragma unroll
                 for (int ks = 0; ks < kTcBK / 32; ++ks) {
                     const uint64_t a_hi = umma_desc_sw128(st + ks * 32);
                     const uint64_t a_lo = umma_desc_sw128(st + 16384 + ks * 32);
                     const uint64_t b_cat = umma_desc_sw128(st + 32768 + ks * 32);
                     const uint32_t acc = (kb | ks) ? 1u : 0u;
-                    umma_i8(tmem_base, a_hi, b_cat, idesc, acc);            // [hi.hi | hi.lo]
-                    umma_i8(tmem_base + 256, a_lo, b_cat, idesc, acc);      // [lo.hi | lo.lo]
+                    umma_i8(tmem_base, a_hi, b_cat, idesc, acc);               // [hi.hi | hi.lo]
+                    umma_i8(tmem_base + 2 * BN, a_lo, b_cat, idesc, acc);      // [lo.hi | lo.lo]
                 }
                 umma_commit(bar_empty + 8 * s);        // frees the stage once these MMAs retire
             }
@@ -182,12 +194,12 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
             const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16);
             int *orow = out + (long long)(m0 + quarter * 32 + lane) * ldo + c0;
 #pragma unroll 1
-            for (int cc = 0; cc < kTcBN; cc += 16) {
+            for (int cc = 0; cc < BN; cc += 16) {
                 uint32_t hh[16], hl[16], lh[16], ll[16];
                 tmem_ld16(tl + cc, hh);
-                tmem_ld16(tl + 128 + cc, hl);
-                tmem_ld16(tl + 256 + cc, lh);
-                tmem_ld16(tl + 384 + cc, ll);
+                tmem_ld16(tl + BN + cc, hl);
+                tmem_ld16(tl + 2 * BN + cc, lh);
+                tmem_ld16(tl + 3 * BN + cc, ll);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
@@ -204,7 +216,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kCols));
     }
 }
 
@@ -386,10 +398,11 @@ inline int tc_gemm_i8_ptrs(coex_ctx *c, const int8_t *a_hi, const int8_t *a_lo, 
     TcState *t = nullptr;
     COEX_TRY(tc_state(c, &t));
     if (m_rows % kTcBM) COEX_FAIL("tc_gemm: query rows must be padded to 128");
-    if (t->bh != c->u_hi.p || t->bl != c->u_lo.p || t->b_rows != c->N_pad || t->n_pad != c->n_pad) {
-        COEX_TRY(tc_encode(t, &t->map_bh, c->u_hi.p, c->N_pad, c->n_pad));
-        COEX_TRY(tc_encode(t, &t->map_bl, c->u_lo.p, c->N_pad, c->n_pad));
-        t->bh = c->u_hi.p; t->bl = c->u_lo.p; t->b_rows = c->N_pad; t->n_pad = c->n_pad;
+    const int BN = c->gemm_bn;
+    if (t->bh != c->u_hi.p || t->bl != c->u_lo.p || t->b_rows != c->N_pad || t->n_pad != c->n_pad || t->bn != BN) {
+        COEX_TRY(tc_encode(t, &t->map_bh, c->u_hi.p, c->N_pad, c->n_pad, BN));
+        COEX_TRY(tc_encode(t, &t->map_bl, c->u_lo.p, c->N_pad, c->n_pad, BN));
+        t->bh = c->u_hi.p; t->bl = c->u_lo.p; t->b_rows = c->N_pad; t->n_pad = c->n_pad; t->bn = BN;
         t->ah = t->al = nullptr;
     }
     if (t->ah != a_hi || t->al != a_lo || t->a_rows != a_rows_alloc) {
@@ -398,12 +411,17 @@ inline int tc_gemm_i8_ptrs(coex_ctx *c, const int8_t *a_hi, const int8_t *a_lo, 
         t->ah = a_hi; t->al = a_lo; t->a_rows = a_rows_alloc;
     }
     if (!t->attr_set) {
-        COEX_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+        COEX_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmem));
+        COEX_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::kSmem));
         t->attr_set = true;
     }
-    dim3 grid((unsigned)(m_rows / kTcBM), (unsigned)(c->N_pad / kTcBN));
-    gemm_i8_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, c->stream>>>(t->map_ah, t->map_al, t->map_bh, t->map_bl, out, ldo,
-                                                                    c->n_pad / kTcBK, t->d_err);
+    dim3 grid((unsigned)(m_rows / kTcBM), (unsigned)(c->N_pad / BN));
+    if (BN == 128)
+        gemm_i8_tc_kernel<128><<<grid, kTcThreads, TcCfg<128>::kSmem, c->stream>>>(t->map_ah, t->map_al, t->map_bh, t->map_bl, out,
+                                                                                  ldo, c->n_pad / kTcBK, t->d_err);
+    else
+        gemm_i8_tc_kernel<64><<<grid, kTcThreads, TcCfg<64>::kSmem, c->stream>>>(t->map_ah, t->map_al, t->map_bh, t->map_bl, out,
+                                                                                ldo, c->n_pad / kTcBK, t->d_err);
     COEX_CUDA(cudaGetLastError());
     return 0;
 }
