@@ -375,27 +375,41 @@ def run_ours(args):
         peak_src = "measured (MEASURED_PEAKS.json, burst)" if peaks else "fallback (B200_PROFILING.md)"
         per = {s: (stage_tot[s] / args.steps, stage_launch[s] / args.steps) for s in STAGES}
         # algorithmic work per step
-        gemm_flops = 2.0 * t.n * H * t.N
-        count_bytes = 4.0 * H * t.N + 8.0 * float(np.sum(np.diff(perm_off) ** 2))
+        # the correlation strips are formed once per UNIQUE hit row (queries of several permutations share it)
+        U = int(np.unique(hit_rows).size)
+        gemm_flops = 2.0 * t.n * U * t.N
+        count_bytes = 4.0 * U * t.N + 8.0 * float(np.sum(np.diff(perm_off) ** 2))
+        traffic = {}
+        is_default = (args.shape == "minimal" and not args.rows and args.loci == 500 and args.perms == 100 and
+                      args.window == 10000 and args.seed == 1234 and world == 1)
+        try:
+            if is_default:
+                with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                    traffic = json.load(f)
+        except Exception:
+            traffic = {}
         rank_bytes = float(t.N) * t.n * (8 + 2 + 2)
         roof = {}
         if per["corr_gemm"][0] > 0:
             a = gemm_flops / (per["corr_gemm"][0] * 1e-3) / 1e12
             roof["corr_gemm"] = {"bound": "tensor", "achieved": a, "peak": tc_peak, "unit": "TFLOP/s", "frac": a / tc_peak,
-                                 "traffic": None, "ms_per_step": per["corr_gemm"][0], "launches_per_step": per["corr_gemm"][1]}
+                                 "traffic": traffic.get("corr_gemm"), "ms_per_step": per["corr_gemm"][0], "launches_per_step": per["corr_gemm"][1]}
         if per["count_score"][0] > 0:
             a = count_bytes / (per["count_score"][0] * 1e-3) / 1e9
             roof["count_score"] = {"bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak,
-                                   "traffic": None, "ms_per_step": per["count_score"][0],
+                                   "traffic": traffic.get("count_score"),
+                                   "algorithmic_bytes_per_launch": count_bytes / max(per["count_score"][1], 1), "ms_per_step": per["count_score"][0],
                                    "launches_per_step": per["count_score"][1]}
         if per["rank_pack"][0] > 0:
             a = rank_bytes / (per["rank_pack"][0] * 1e-3) / 1e9
             roof["rank_pack"] = {"bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak,
-                                 "traffic": None, "ms_per_step": per["rank_pack"][0], "launches_per_step": per["rank_pack"][1]}
+                                 "traffic": traffic.get("rank_pack"), "ms_per_step": per["rank_pack"][0], "launches_per_step": per["rank_pack"][1]}
         dominant = max(("corr_gemm", "count_score", "rank_pack", "network"), key=lambda s: per[s][0])
         main = dict(roof.get(dominant) or roof.get("corr_gemm") or {})
         main["kernel"] = dominant if dominant in roof else "corr_gemm"
         main["peak_source"] = peak_src
+        main["note"] = ("roofline of the kernel with the largest share of the step (CUDA events per launch on the library "
+                        "stream); traffic = ncu dram read+write per launch (profiles/r01_final_summary.md), null off the default config")
         total_perms = K * world
         line = {
             "metric": "permutations_per_sec", "value": total_perms / (step_ms_max * 1e-3), "unit": "permutations/s",

@@ -263,3 +263,54 @@ def test_allpairs_histogram_small():
                 assert nan_t == nan and int(hist_t.sum()) == int(want.sum())
                 near_edge = np.abs(((r[ok] + 1.0) * 0.5 * nb) - np.round((r[ok] + 1.0) * 0.5 * nb)) < 1e-6 * nb
                 assert np.abs(hist_t.astype(np.int64) - want).sum() <= 2 * int(near_edge.sum())
+
+
+def test_file_level_entry_point_matches_oracle(tmp_path):
+    """The drop-in for `1-make-network.py -wd ... --all`: same inputs on disk (settings.txt, expression table,
+    feature BED, correlation list, windowBed map files), same eight JSON objects per permutation."""
+    from coexpression_b200 import synth
+    from coexpression_b200.make_network import run_batch
+    from oracle import network_oracle as no
+    t = synth.make_table(1200, 60, seed=44)
+    wd = tmp_path / "work"
+    (wd / "permutation_store").mkdir(parents=True)
+    expr = tmp_path / "t.expression"; bed = tmp_path / "f5ep.bed"; clist = tmp_path / "t.expression.spearmanlist"
+    synth.write_expression_file(expr, t); synth.write_feature_bed(bed, t)
+    R = no.rank_rows(t.X)
+    ga, gb = synth.global_pair_indices(t.names, 30000, seed=3)
+    g = no.get_pearson(R, ga, gb)
+    glist = np.sort(np.where(np.isnan(g), -99.0, g))
+    with open(clist, "w") as o:
+        for v in glist:
+            o.write("%s\n" % (int(v) if v == -99 else repr(float(v))))
+    m = synth.Mapper(t)
+    loci = synth.make_loci(t, 70, seed=9)
+    sets = synth.circular_shifts(loci, m.genome_len, 2, seed=10)
+    for k, gw in enumerate(sets):
+        synth.write_map_file(wd / "permutation_store" / f"f5ep.{k}.bed", t, m, gw, 7000, prefix="rs" if k == 0 else "rand_rs")
+    settings = {"verbose": "False", "feature_coordinates": str(bed), "correlationfile": str(clist), "expression_file": str(expr),
+                "supplementary_label": "x", "correlationmeasure": "Spearman", "soft_separation": 100000, "nsp": 1.0,
+                "seedfile": "none", "pval_to_join": 0.1, "useaverage": "False", "anticorrelation": "True", "noiter": "False",
+                "selectionthreshold": 0, "selectionthreshold_is_j": "False", "config_file": "app.cfg"}
+    json.dump(settings, open(wd / "settings.txt", "w"))
+    written = run_batch(str(wd))
+    assert len(written) == 3 * 8
+    store = wd / "perm_results_store"
+    for k in range(3):
+        snp_map = json.load(open(store / f"f5ep.snp_map.{k}"))
+        promoters = list(snp_map)
+        want = no.make_network(t.names, t.X, promoters, t.addresses(), glist.tolist(), anticorrelation=True, Xrank=R)
+        got = {name: json.load(open(store / f"f5ep.{name}.{k}")) for name in
+               ("indmeasure", "individualscores", "prom_to_join", "indjoined", "joining_instructions", "winners",
+                "allpromoterscores")}
+        assert got["prom_to_join"] == want["prom_to_join"] and got["winners"] == want["winners"]
+        assert got["joining_instructions"] == want["joining_instructions"]
+        assert set(got["indmeasure"]) == set(want["indmeasure"]) and len(promoters) > 5
+        for grp, v in want["indmeasure"].items():
+            assert abs(got["indmeasure"][grp] - v) <= 1e-6
+        for a_ in want["indjoined"]:
+            for b_, v in want["indjoined"][a_].items():
+                assert abs(got["indjoined"][a_][b_] - v) <= 1e-6
+        for a_ in want["individualscores"]:
+            for b_, v in want["individualscores"][a_].items():
+                assert abs(got["individualscores"][a_][b_] - v) <= 1e-6
