@@ -35,10 +35,46 @@ rank_pack_kernel(const double *__restrict__ raw, long long N, int n, int n_pad, 
     const int tid = threadIdx.x;
     const double *x = raw + row * (long long)n;
 
-    for (int p = tid; p < P2; p += kRankThreads) {
-        // +0.0 canonicalises -0.0 so that it ties with 0.0 exactly as a double compare does
-        keys[p] = (p < n) ? (x[p] + 0.0) : __longlong_as_double(0x7ff0000000000000LL);
-        idx[p] = (p < n) ? (uint16_t)p : (uint16_t)0xFFFF;
+    // Expression rows are zero-inflated: every sample equal to the row minimum shares the average
+    // rank (m0+1)/2, so only the m = n - m0 remaining samples need sorting (a 2.4x smaller bitonic
+    // network for a half-zero FANTOM5 row).  Pass 1: row minimum.  Pass 2: compact the rest.
+    __shared__ double s_min[kRankThreads / 32];
+    __shared__ int s_cnt[kRankThreads / 32 + 1];
+    double vmin = __longlong_as_double(0x7ff0000000000000LL);
+    for (int p = tid; p < n; p += kRankThreads) vmin = fmin(vmin, x[p] + 0.0);   // +0.0: -0.0 ties 0.0 as a double compare does
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+    if ((tid & 31) == 0) s_min[tid >> 5] = vmin;
+    __syncthreads();
+    vmin = s_min[0];
+    for (int w = 1; w < kRankThreads / 32; ++w) vmin = fmin(vmin, s_min[w]);
+    // order-preserving compaction (ballot + prefix over warps), chunk by chunk
+    int m = 0;                                            // compacted so far (uniform)
+    for (int p0 = 0; p0 < n; p0 += kRankThreads) {
+        const int p = p0 + tid;
+        const double v = (p < n) ? (x[p] + 0.0) : vmin;
+        const bool keep = (p < n) && (v != vmin);
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if ((tid & 31) == 0) s_cnt[tid >> 5] = __popc(bal);
+        __syncthreads();
+        int base = m, total = 0;
+        for (int w = 0; w < kRankThreads / 32; ++w) { const int c = s_cnt[w]; if (w < (tid >> 5)) base += c; total += c; }
+        if (keep) {
+            const int slot = base + __popc(bal & ((1u << (tid & 31)) - 1u));
+            keys[slot] = v;
+            idx[slot] = (uint16_t)p;
+        } else if (p < n) {
+            r2[p] = 0;                                    // marked: rank of the minimum, filled in below
+        }
+        m += total;
+        __syncthreads();
+    }
+    const int m0 = n - m;                                 // samples equal to the row minimum
+    P2 = 1;
+    while (P2 < m) P2 <<= 1;
+    for (int p = m + tid; p < P2; p += kRankThreads) {
+        keys[p] = __longlong_as_double(0x7ff0000000000000LL);
+        idx[p] = (uint16_t)0xFFFF;
     }
     __syncthreads();
 
@@ -60,8 +96,9 @@ rank_pack_kernel(const double *__restrict__ raw, long long N, int n, int n_pad, 
         }
     }
 
-    // tie run of sorted position p = [lower_bound(key), upper_bound(key)) within the n real keys
-    for (int p = tid; p < n; p += kRankThreads) {
+    // tie run of sorted position p = [lower_bound(key), upper_bound(key)) within the m sorted keys;
+    // the m0 minimum samples occupy ranks 1..m0
+    for (int p = tid; p < m; p += kRankThreads) {
         const double key = keys[p];
         int lo = 0, hi = p;                       // first position with keys[pos] >= key
         while (lo < hi) {
@@ -69,14 +106,17 @@ rank_pack_kernel(const double *__restrict__ raw, long long N, int n, int n_pad, 
             if (keys[mid] < key) lo = mid + 1; else hi = mid;
         }
         const int first = lo;
-        lo = p + 1; hi = n;                       // first position with keys[pos] > key
+        lo = p + 1; hi = m;                       // first position with keys[pos] > key
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
             if (keys[mid] <= key) lo = mid + 1; else hi = mid;
         }
         const int last = lo - 1;
-        r2[idx[p]] = (uint16_t)(first + last + 2);   // 2 * average rank (1-based)
+        r2[idx[p]] = (uint16_t)(2 * m0 + first + last + 2);   // 2 * average rank (1-based)
     }
+    __syncthreads();
+    for (int c = tid; c < n; c += kRankThreads)
+        if (r2[c] == 0) r2[c] = (uint16_t)(m0 + 1);           // 2 * (1 + m0) / 2
     __syncthreads();
 
     // outputs: u16 2*rank, digits of u = 2*rank-(n+1) = 128*hi + lo, lo in [-64, 63]
