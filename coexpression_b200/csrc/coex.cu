@@ -146,7 +146,7 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     int per_sm = 1;
     COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_dedup_kernel, kDdThreads, smem));
     const int grid_max = std::max(1, per_sm) * c->sm_count;
-    COEX_TRY(c->dd_gthr.reserve((size_t)grid_max * Tcap * 3)); COEX_TRY(c->dd_gorg.reserve((size_t)grid_max * Tcap * 2));
+    COEX_TRY(c->dd_gthr.reserve((size_t)grid_max * Tcap * 3)); COEX_TRY(c->dd_gorg.reserve((size_t)grid_max * Tcap * 5));
     COEX_TRY(c->dd_tab.reserve((size_t)N + 1));
     score_table_kernel<<<(unsigned)((N + 256) / 256), 256, 0, st>>>(c->dd_tab.p, N, prm->anticorrelation);
     COEX_CUDA(cudaGetLastError());

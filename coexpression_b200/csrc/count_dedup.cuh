@@ -57,7 +57,7 @@ struct DedupArgs {
     double R;                       // bucket range [-R, R]
     int bm_words;                   // 32-bit words of the hit-column bitmap (0 = table too long, bitmap disabled)
     double *g_thr;                  // scratch [gridDim.x, 3, Tcap]: unsorted | grouped | sorted statistics
-    unsigned int *g_org;            // scratch [gridDim.x, 2, Tcap]: grouped | sorted origins
+    unsigned int *g_org;            // scratch [gridDim.x, 5, Tcap]: grouped | sorted origins, unsorted | grouped | sorted columns
     const double *score_tab;        // [N+1] edge score of every possible bisect index (len = N-1)
     unsigned long long *phase_clk;  // optional [8]: summed clock64 per phase over all CTAs (profiling aid)
 };
@@ -80,10 +80,12 @@ count_dedup_kernel(DedupArgs a) {
     unsigned int *lut = hist + a.Tcap + 4;
     unsigned int *cursor = reinterpret_cast<unsigned int *>(thr32);   // bucket cursors alias thr32|hist (both dead until step C; 2*Tcap >= buckets)
     int *queue = reinterpret_cast<int *>(lut + kDdBuckets + 4);
-    int *q_k = queue + kDdQueue;                 // [Qcap] permutation
-    int *q_i = q_k + a.Qcap;                     // [Qcap] hit position
-    int *q_toff = q_i + a.Qcap;                  // [Qcap+1] offset of the query's statistics in the item
-    unsigned int *bitmap = reinterpret_cast<unsigned int *>(q_toff + a.Qcap + 2);   // [bm_words] columns that are hit columns of this item
+    long long *q_sc = reinterpret_cast<long long *>(queue + kDdQueue);   // [Qcap] offset of the query's score row
+    int *q_i = reinterpret_cast<int *>(q_sc + a.Qcap);                     // [Qcap] hit position
+    int *q_off = q_i + a.Qcap;                   // [Qcap] offset of the query's permutation in hit_rows
+    int *q_P = q_off + a.Qcap;                   // [Qcap] hits of that permutation
+    int *q_toff = q_P + a.Qcap;                  // [Qcap+2] offset of the query's statistics in the item
+    unsigned int *bitmap = reinterpret_cast<unsigned int *>(q_toff + a.Qcap + 2);   // [2*bm_words] hit columns of this item: skip mask | claim mask
     __shared__ int s_T, s_qn;
     __shared__ unsigned int s_warp[kDdThreads / 32];
 
@@ -93,8 +95,10 @@ count_dedup_kernel(DedupArgs a) {
     double *tmp_r = a.g_thr + (long long)blockIdx.x * 3 * a.Tcap;      // statistic of flat index t (-99 = undefined)
     double *g_thr = tmp_r + a.Tcap;                                    // grouped by bucket
     double *thr64 = g_thr + a.Tcap;                                    // sorted
-    unsigned int *g_org = a.g_org + (long long)blockIdx.x * 2 * a.Tcap;
+    unsigned int *g_org = a.g_org + (long long)blockIdx.x * 5 * a.Tcap;
     unsigned int *org = g_org + a.Tcap;
+    int *tmp_c = reinterpret_cast<int *>(org + a.Tcap);              // column of flat index t
+    int *g_col = tmp_c + a.Tcap, *col = g_col + a.Tcap;              // grouped / sorted columns
 
     for (int it = blockIdx.x; it < a.n_items; it += gridDim.x) {
         const DedupItem item = a.items[it];
@@ -111,9 +115,13 @@ count_dedup_kernel(DedupArgs a) {
             const long long q = a.qlist[item.qb + ql];
             int lo = 0, hi = a.K;
             while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (a.perm_off[mid] <= q) lo = mid; else hi = mid; }
-            q_k[ql] = lo;
-            const int i = (int)(q - a.perm_off[lo]);
+            const long long off = a.perm_off[lo];
+            const int P = (int)(a.perm_off[lo + 1] - off);
+            const int i = (int)(q - off);
             q_i[ql] = i;
+            q_off[ql] = (int)off;
+            q_P[ql] = P;
+            q_sc[ql] = a.sc_off[lo] + (long long)i * P;
             double vi = -99.0;                             // null value at table column i (quirk Q1)
             const double sxc = a.sx[i];
             if (sxu != 0.0 && sxc != 0.0) vi = __ddiv_rn(0.25 * (double)srow[i], __dmul_rn(sxu, sxc));
@@ -121,85 +129,100 @@ count_dedup_kernel(DedupArgs a) {
         }
         if (tid == 0) { s_T = 0; s_qn = 0; }
         for (int b = tid; b <= kDdBuckets; b += kDdThreads) lut[b] = 0;
-        for (int wd = tid; wd < a.bm_words; wd += kDdThreads) bitmap[wd] = 0;
+        for (int wd = tid; wd < 2 * a.bm_words; wd += kDdThreads) bitmap[wd] = 0;       // skip mask | claim mask
         __syncthreads();
         if (tid == 0) {
             int acc = 0;
-            for (int ql = 0; ql < nq; ++ql) {
-                q_toff[ql] = acc;
-                acc += (int)(a.perm_off[q_k[ql] + 1] - a.perm_off[q_k[ql]]);       // P (diagonal included)
-            }
+            for (int ql = 0; ql < nq; ++ql) { q_toff[ql] = acc; acc += q_P[ql]; }       // P (diagonal included)
             q_toff[nq] = acc;
         }
         __syncthreads();
         const int TP = q_toff[nq];
         DD_PHASE(0);
-        // ---- B. statistics: pass 0 evaluates them once and counts per bucket, pass 1 groups them -----
-        for (int pass = 0; pass < 2; ++pass) {
-            for (int t = tid; t < TP; t += kDdThreads) {
-                int lo = 0, hi = nq;
-                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (q_toff[mid] <= t) lo = mid; else hi = mid; }
-                const int ql = lo, j = t - q_toff[ql];
-                if (pass == 0) {
-                    const int k = q_k[ql], i = q_i[ql];
-                    const long long off = a.perm_off[k];
-                    const int P = (int)(a.perm_off[k + 1] - off);
-                    const long long w = a.sc_off[k] + (long long)i * P + j;
-                    double r = -99.0;
-                    int c_hit = 0;
-                    if (j != i) {
-                        const int c = a.hit_rows[off + j];
-                        c_hit = c;
-                        if (posu && a.rawsum_pos[c]) {                          // coexfunctions.py:389
-                            r = __ddiv_rn(0.25 * (double)srow[c], __dmul_rn(sxu, a.sx[c]));
-                            if (r != r) r = -99.0;                              // coexfunctions.py:406-408
-                        }
-                    }
-                    tmp_r[t] = r;
-                    if (r == -99.0) {                                           // diagonal, or 1-make-network.py:284-285
-                        a.scores[w] = (j == i) ? 0.0 : -log10(1.0);
-                        if (a.counts) a.counts[w] = -1;
-                    } else {
-                        atomicAdd(&lut[dd_bucket64(r, a.R, bscale)], 1u);
-                        // the null value of a hit column IS this statistic (same arithmetic): it is
-                        // accounted exactly in step C' and skipped by the float streaming pass
-                        if (a.bm_words) atomicOr(&bitmap[c_hit >> 5], 1u << (c_hit & 31));
-                    }
+        // ---- B. statistics: evaluated once (four per thread in flight), counted per bucket ------
+        for (int t0 = tid; t0 < TP; t0 += 4 * kDdThreads) {
+            int tt[4], qq[4], jj[4], cc4[4], sraw[4];
+            double sxc4[4];
+            bool live[4], guard[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                tt[e] = t0 + e * kDdThreads;
+                live[e] = tt[e] < TP;
+                qq[e] = 0; jj[e] = 0; cc4[e] = -1;
+                if (live[e]) {
+                    int lo = 0, hi = nq;
+                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (q_toff[mid] <= tt[e]) lo = mid; else hi = mid; }
+                    qq[e] = lo; jj[e] = tt[e] - q_toff[lo];
+                    if (jj[e] != q_i[lo]) cc4[e] = a.hit_rows[q_off[lo] + jj[e]];
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                guard[e] = false; sraw[e] = 0; sxc4[e] = 0.0;
+                if (cc4[e] >= 0) { guard[e] = a.rawsum_pos[cc4[e]] != 0; sraw[e] = srow[cc4[e]]; sxc4[e] = a.sx[cc4[e]]; }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (!live[e]) continue;
+                double r = -99.0;
+                if (cc4[e] >= 0 && posu && guard[e]) {                      // coexfunctions.py:389
+                    r = __ddiv_rn(0.25 * (double)sraw[e], __dmul_rn(sxu, sxc4[e]));
+                    if (r != r) r = -99.0;                                  // coexfunctions.py:406-408
+                }
+                tmp_r[tt[e]] = r;
+                tmp_c[tt[e]] = cc4[e];
+                if (r == -99.0) {                                           // diagonal, or 1-make-network.py:284-285
+                    const long long w = q_sc[qq[e]] + jj[e];
+                    a.scores[w] = (cc4[e] < 0) ? 0.0 : -log10(1.0);
+                    if (a.counts) a.counts[w] = -1;
                 } else {
-                    const double r = tmp_r[t];
-                    if (r != -99.0) {
-                        const int b = dd_bucket64(r, a.R, bscale);
-                        const unsigned int pos = lut[b] + atomicAdd(&cursor[b], 1u);
-                        g_thr[pos] = r;
-                        g_org[pos] = ((unsigned int)ql << 13) | (unsigned int)j;
+                    atomicAdd(&lut[dd_bucket64(r, a.R, bscale)], 1u);
+                    // the null value of a hit column IS this statistic (same arithmetic): it is accounted
+                    // exactly in step C' and skipped by the float streaming pass
+                    if (a.bm_words) {
+                        const unsigned int bit = 1u << (cc4[e] & 31);
+                        atomicOr(&bitmap[cc4[e] >> 5], bit);
+                        atomicOr(&bitmap[a.bm_words + (cc4[e] >> 5)], bit);
                     }
                 }
             }
+        }
+        __syncthreads();
+        {   // exclusive scan of the bucket counts
+            constexpr int per = kDdBuckets / kDdThreads;
+            unsigned int loc[per], sum = 0;
+#pragma unroll
+            for (int e = 0; e < per; ++e) { loc[e] = lut[tid * per + e]; sum += loc[e]; }
+            unsigned int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned int x = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += x; }
+            if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
             __syncthreads();
-            if (pass == 0) {
-                // exclusive scan of the bucket counts
-                constexpr int per = kDdBuckets / kDdThreads;
-                unsigned int loc[per], sum = 0;
+            unsigned int base = incl - sum;
+            for (int w = 0; w < (tid >> 5); ++w) base += s_warp[w];
 #pragma unroll
-                for (int e = 0; e < per; ++e) { loc[e] = lut[tid * per + e]; sum += loc[e]; }
-                unsigned int incl = sum;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const unsigned int x = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += x; }
-                if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
-                __syncthreads();
-                unsigned int base = incl - sum;
-                for (int w = 0; w < (tid >> 5); ++w) base += s_warp[w];
-#pragma unroll
-                for (int e = 0; e < per; ++e) { lut[tid * per + e] = base; cursor[tid * per + e] = 0; base += loc[e]; }
-                if (tid == kDdThreads - 1) { lut[kDdBuckets] = base; s_T = (int)base; }
-                __syncthreads();
+            for (int e = 0; e < per; ++e) { lut[tid * per + e] = base; cursor[tid * per + e] = 0; base += loc[e]; }
+            if (tid == kDdThreads - 1) { lut[kDdBuckets] = base; s_T = (int)base; }
+            __syncthreads();
+        }
+        // group by bucket
+        for (int t = tid; t < TP; t += kDdThreads) {
+            const double r = tmp_r[t];
+            if (r != -99.0) {
+                int lo = 0, hi = nq;
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (q_toff[mid] <= t) lo = mid; else hi = mid; }
+                const int b = dd_bucket64(r, a.R, bscale);
+                const unsigned int pos = lut[b] + atomicAdd(&cursor[b], 1u);
+                g_thr[pos] = r;
+                g_org[pos] = ((unsigned int)lo << 13) | (unsigned int)(t - q_toff[lo]);
+                g_col[pos] = tmp_c[t];
             }
         }
+        __syncthreads();
         const int T = s_T;
         DD_PHASE(1);
         if (T == 0) continue;                               // every statistic undefined: scores already written
-        __threadfence_block();
-        // ---- C. rank inside the bucket -> fully sorted statistics in shared memory ----------------
+        // ---- C. rank inside the bucket -> fully sorted statistics -------------------------------------
         for (int e = tid; e < T; e += kDdThreads) {
             const double t = g_thr[e];
             const int b = dd_bucket64(t, a.R, bscale);
@@ -212,29 +235,21 @@ count_dedup_kernel(DedupArgs a) {
             thr64[lo + rank] = t;
             thr32[lo + rank] = (float)t;
             org[lo + rank] = g_org[e];
+            col[lo + rank] = g_col[e];
         }
         for (int p = tid; p <= T; p += kDdThreads) hist[p] = 0;
         __syncthreads();
         // ---- C'. hit columns: value == statistic exactly; the first statistic to claim a column adds it
         if (a.bm_words) {
             for (int sidx = tid; sidx < T; sidx += kDdThreads) {
-                const unsigned int o = org[sidx];
-                const int ql = (int)(o >> 13), j = (int)(o & 8191u);
-                const int c = a.hit_rows[a.perm_off[q_k[ql]] + j];
+                const int c = col[sidx];
                 const unsigned int bit = 1u << (c & 31);
-                if (atomicAnd(&bitmap[c >> 5], ~bit) & bit) {
+                if (atomicAnd(&bitmap[a.bm_words + (c >> 5)], ~bit) & bit) {
                     const double t = thr64[sidx];
                     int e2 = sidx + 1;
                     while (e2 < T && thr64[e2] == t) ++e2;            // statistics <= value: through the run of equals
                     atomicAdd(&hist[e2], 1u);
                 }
-            }
-            // re-arm the bitmap for the streaming pass: every column that has a statistic is skipped there
-            __syncthreads();
-            for (int sidx = tid; sidx < T; sidx += kDdThreads) {
-                const unsigned int o = org[sidx];
-                const int c = a.hit_rows[a.perm_off[q_k[(int)(o >> 13)]] + (int)(o & 8191u)];
-                atomicOr(&bitmap[c >> 5], 1u << (c & 31));
             }
             __syncthreads();
         }
@@ -349,15 +364,14 @@ count_dedup_kernel(DedupArgs a) {
         for (int s = tid; s < T; s += kDdThreads) {
             const unsigned int o = org[s];
             const int ql = (int)(o >> 13), j = (int)(o & 8191u);
-            const int k = q_k[ql], i = q_i[ql];
-            const int P = (int)(a.perm_off[k + 1] - a.perm_off[k]);
+            const int i = q_i[ql];
             const double t = thr64[s];
             // all columns strictly below t: streamed values + zero-variance columns (-99 < t always),
             // minus the skipped column i of this query if it is below t (quirk Q1)
             long long idx = (long long)hist[s] + a.n_degenerate;
             long long len = N;
             if (i < N) { len = N - 1; if (q_vi[ql] < t) idx -= 1; }
-            const long long w = a.sc_off[k] + (long long)i * P + j;
+            const long long w = q_sc[ql] + j;
             a.scores[w] = (len == N - 1) ? a.score_tab[idx] : edge_score_dev(idx, len, a.anticor);
             if (a.counts) a.counts[w] = idx;
         }
@@ -389,7 +403,7 @@ __global__ void icol_kernel(const double *__restrict__ sx, long long N, long lon
 
 inline size_t dedup_smem_bytes(int Tcap, int Qcap, int bm_words) {
     return (size_t)Qcap * 8 + (size_t)Tcap * 4 + (size_t)(Tcap + 4) * 4 + (size_t)(kDdBuckets + 4) * 4 +
-           (size_t)kDdQueue * 4 + (size_t)Qcap * 4 * 2 + (size_t)(Qcap + 2) * 4 + (size_t)bm_words * 4 + 16;
+           (size_t)kDdQueue * 4 + (size_t)Qcap * 8 + (size_t)Qcap * 4 * 3 + (size_t)(Qcap + 2) * 4 + (size_t)bm_words * 8 + 16;
 }
 
 }  // namespace coex
