@@ -188,21 +188,29 @@ count_dedup_kernel(DedupArgs a) {
             }
         }
         __syncthreads();
-        {   // exclusive scan of the bucket counts
-            constexpr int per = kDdBuckets / kDdThreads;
-            unsigned int loc[per], sum = 0;
+        {   // exclusive scan of the bucket counts (each warp scans a contiguous slice, bank-conflict free)
+            constexpr int kWarps = kDdThreads / 32, kPerWarp = kDdBuckets / kWarps;
+            const int wid = tid >> 5, ln = tid & 31;
+            unsigned int carry = 0;
+            for (int c = 0; c < kPerWarp; c += 32) {
+                const int b = wid * kPerWarp + c + ln;
+                const unsigned int v = lut[b];
+                unsigned int incl = v;
 #pragma unroll
-            for (int e = 0; e < per; ++e) { loc[e] = lut[tid * per + e]; sum += loc[e]; }
-            unsigned int incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const unsigned int x = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += x; }
-            if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+                for (int o = 1; o < 32; o <<= 1) { const unsigned int x = __shfl_up_sync(0xffffffffu, incl, o); if (ln >= o) incl += x; }
+                lut[b] = carry + incl - v;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (ln == 0) s_warp[wid] = carry;
             __syncthreads();
-            unsigned int base = incl - sum;
-            for (int w = 0; w < (tid >> 5); ++w) base += s_warp[w];
-#pragma unroll
-            for (int e = 0; e < per; ++e) { lut[tid * per + e] = base; cursor[tid * per + e] = 0; base += loc[e]; }
-            if (tid == kDdThreads - 1) { lut[kDdBuckets] = base; s_T = (int)base; }
+            unsigned int base = 0;
+            for (int w = 0; w < wid; ++w) base += s_warp[w];
+            for (int c = 0; c < kPerWarp; c += 32) {
+                const int b = wid * kPerWarp + c + ln;
+                lut[b] += base;
+                cursor[b] = 0;
+            }
+            if (tid == kDdThreads - 1) { lut[kDdBuckets] = base + carry; s_T = (int)(base + carry); }
             __syncthreads();
         }
         // group by bucket
