@@ -314,3 +314,62 @@ def test_file_level_entry_point_matches_oracle(tmp_path):
         for a_ in want["individualscores"]:
             for b_, v in want["individualscores"][a_].items():
                 assert abs(got["individualscores"][a_][b_] - v) <= 1e-6
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_randomised_stress_against_oracle(seed):
+    """Many small random configurations in one batch: duplicated rows inside and across groups, all-zero and
+    constant rows among the hits, two-hit and one-hit sets, dense clusters (every hit within the soft
+    separation), options drawn at random.  Everything the reference defines must match the oracle."""
+    from coexpression_b200 import synth
+    from coexpression_b200.api import CoexContext, Options
+    from coexpression_b200.results import perm_objects
+    from oracle import network_oracle as no
+    rng = np.random.default_rng(100 + seed)
+    N, n = int(rng.integers(150, 500)), int(rng.integers(5, 70))
+    t = synth.make_table(N, n, seed=200 + seed, zero_row_frac=0.03, dup_rows=12)
+    X = t.X.copy()
+    X[7] = 4.0                                        # constant, non-zero: zero variance -> NaN -> -99
+    X[8] = np.round(X[8], 0)                          # heavy ties
+    start, end, chrom = t.start.copy(), t.end.copy(), t.chrom.copy()
+    dense = rng.choice(N, size=40, replace=False)     # one dense cluster: 40 regions within 60 kb on one chromosome
+    chrom[dense] = "chr3"; start[dense] = 5_000_000 + np.sort(rng.integers(0, 60_000, size=40)); end[dense] = start[dense] + 20
+    names = [f"{c}:{s}..{e},+" for c, s, e in zip(chrom, start, end)]
+    addresses = {nm: (c, int(s), int(e)) for nm, c, s, e in zip(names, chrom, start, end)}
+    R = no.rank_rows(X)
+    ga = rng.integers(0, N, 8000).astype(np.int32); gb = rng.integers(0, N, 8000).astype(np.int32)
+    g = no.get_pearson(R, ga, gb)
+    glist = np.sort(np.where(np.isnan(g), -99.0, g))
+    hit_sets = []
+    for k in range(7):
+        p = int(rng.integers(2, 60))
+        h = rng.choice(N, size=p, replace=False)
+        if k == 0:
+            h = np.concatenate([dense[:25], [7, 8], h[:10]])
+        if k == 1:
+            h = h[:2]
+        if k == 2:
+            h = h[:1]
+        hit_sets.append(np.unique(h)[rng.permutation(len(np.unique(h)))].astype(np.int32))
+    opts = Options(anticorrelation=bool(rng.integers(0, 2)), noiter=bool(rng.integers(0, 2)),
+                   useaverage=bool(rng.integers(0, 2)), pval_to_join=float(rng.choice([0.01, 0.1, 0.5, 1.5])),
+                   selectionthreshold_is_j=bool(rng.integers(0, 2)))
+    with CoexContext() as ctx:
+        ctx.set_expression(X); ctx.prepare()
+        ctx.set_features(chrom, start, end, names)
+        ctx.set_global_list(glist)
+        res = ctx.network_batch(hit_sets, opts, want_scores=True, want_counts=True)
+    for k, h in enumerate(hit_sets):
+        want = no.make_network(names, X, [names[r] for r in h], addresses, glist.tolist(), Xrank=R, return_counts=True,
+                               anticorrelation=opts.anticorrelation, noiter=opts.noiter, useaverage=opts.useaverage,
+                               pval_to_join=opts.pval_to_join, selectionthreshold_is_j=opts.selectionthreshold_is_j)
+        got = perm_objects(res, k, names)
+        assert got["prom_to_join"] == want["prom_to_join"], (seed, k)
+        assert got["winners"] == want["winners"], (seed, k)
+        if len(h) > 1:
+            assert np.array_equal(res.count_matrix(k), want["_counts"]), (seed, k)
+        assert set(got["indmeasure"]) == set(want["indmeasure"])
+        for grp, v in want["indmeasure"].items():
+            assert abs(got["indmeasure"][grp] - v) <= 1e-6, (seed, k, grp)
+        for p_, v in want["allpromoterscores"].items():
+            assert abs(got["allpromoterscores"][p_] - v) <= 1e-6
