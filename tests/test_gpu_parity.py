@@ -373,3 +373,112 @@ def test_randomised_stress_against_oracle(seed):
             assert abs(got["indmeasure"][grp] - v) <= 1e-6, (seed, k, grp)
         for p_, v in want["allpromoterscores"].items():
             assert abs(got["allpromoterscores"][p_] - v) <= 1e-6
+
+
+def test_c1_anchor_minimal_shape_three_permutations():
+    """BASELINE config C1 (`-n 3`, Spearman, circular, minimal shape 20000 x 256): the parity anchor.
+    Four map files (real data + 3 permutations) against the oracle driving the reference C build."""
+    from coexpression_b200 import synth
+    from coexpression_b200.api import CoexContext, Options
+    from coexpression_b200.results import perm_objects
+    from oracle import network_oracle as no
+    N, n = synth.SHAPES["minimal"]
+    t = synth.make_table(N, n, seed=7)
+    hits, _, _ = synth.make_permutation_hits(t, 60, 3, window=6000, seed=70)
+    R = no.rank_rows(t.X)
+    ga, gb = synth.global_pair_indices(t.names, 100000, seed=71)
+    with CoexContext() as ctx:
+        ctx.set_expression(t.X); ctx.prepare()
+        assert np.array_equal(ctx.ranks(), R)
+        g = ctx.pairs(ga, gb, ranked=True)
+        assert _same_doubles(g, no.get_pearson(R, ga, gb))
+        glist = np.sort(np.where(np.isnan(g), -99.0, g))
+        ctx.set_features(t.chrom, t.start, t.end, t.names)
+        ctx.set_global_list(glist)
+        res = ctx.network_batch(hits, Options(), want_scores=True, want_counts=True)
+    addresses = t.addresses()
+    for k, h in enumerate(hits):
+        want = no.make_network(t.names, t.X, [t.names[r] for r in h], addresses, glist.tolist(), Xrank=R, return_counts=True)
+        got = perm_objects(res, k, t.names)
+        assert got["prom_to_join"] == want["prom_to_join"] and got["winners"] == want["winners"]
+        if len(h) > 1:
+            assert np.array_equal(res.count_matrix(k), want["_counts"])
+        for grp, v in want["indmeasure"].items():
+            assert abs(got["indmeasure"][grp] - v) <= 1e-6
+
+
+def test_c5_like_many_hits_j001_iterative_removal():
+    """BASELINE config C5 flavour: one hit set of ~2500 regions (wide window -> large clusters, statistics of a row
+    split over several work items), -j 0.01, iterative removal on, plus the same set under -a."""
+    from coexpression_b200 import synth
+    from coexpression_b200.api import CoexContext, Options
+    from coexpression_b200.results import perm_objects
+    from oracle import network_oracle as no
+    t = synth.make_table(6000, 80, seed=55)
+    hits, _, _ = synth.make_permutation_hits(t, 900, 1, window=40000, seed=56)
+    hits = [hits[0][:2500], hits[1][:800]]
+    assert len(hits[0]) > 2000
+    R = no.rank_rows(t.X)
+    ga, gb = synth.global_pair_indices(t.names, 60000, seed=57)
+    g = no.get_pearson(R, ga, gb)
+    glist = np.sort(np.where(np.isnan(g), -99.0, g))
+    addresses = t.addresses()
+    for anticor in (False, True):
+        opts = Options(pval_to_join=0.01, anticorrelation=anticor)
+        with CoexContext() as ctx:
+            ctx.set_expression(t.X); ctx.prepare()
+            ctx.set_features(t.chrom, t.start, t.end, t.names)
+            ctx.set_global_list(glist)
+            res = ctx.network_batch(hits, opts, want_scores=False, want_counts=True)
+        for k, h in enumerate(hits):
+            want = no.make_network(t.names, t.X, [t.names[r] for r in h], addresses, glist.tolist(), Xrank=R,
+                                   return_counts=True, pval_to_join=0.01, anticorrelation=anticor)
+            got = perm_objects(res, k, t.names, with_scores=False)
+            assert got["prom_to_join"] == want["prom_to_join"] and got["winners"] == want["winners"]
+            assert np.array_equal(res.count_matrix(k), want["_counts"])
+            assert max(len(v) for v in got["prom_to_join"].values()) >= 3
+            for grp, v in want["indmeasure"].items():
+                assert abs(got["indmeasure"][grp] - v) <= 1e-6
+
+
+def test_properties_at_scale_and_cross_implementation():
+    """Size-independent properties on a 40000 x 512 table (too large for the Python oracle): rank sums, symmetry and
+    unit diagonal of the correlation block, tcgen05 == dp4a, and the two independent count kernels
+    (de-duplicated bucket kernel vs per-query binary search) agreeing on every bisect index and density."""
+    from coexpression_b200 import synth
+    from coexpression_b200.api import CoexContext, Options
+    N, n = 40000, 512
+    t = synth.make_table(N, n, seed=91)
+    hits, _, _ = synth.make_permutation_hits(t, 300, 11, window=9000, seed=92)
+    ga, gb = synth.global_pair_indices(t.names, 100000, seed=93)
+    with CoexContext() as ctx:
+        ctx.set_expression(t.X); ctx.prepare()
+        R = ctx.ranks()
+        assert np.all(R.sum(axis=1) == n * (n + 1) / 2.0)                      # exact half-integer sums
+        assert R.min() >= 1.0 and R.max() <= n
+        bad, first = ctx.selftest_gemm(1024)
+        assert bad == 0, first
+        blk = ctx.corr_block("spearman", 1024, 256)
+        sub = blk[:, 1024:1280]
+        assert np.array_equal(np.isnan(sub), np.isnan(sub.T))
+        ok = ~np.isnan(sub)
+        assert np.array_equal(sub[ok], sub.T[ok])                              # bitwise symmetric
+        d = np.diag(sub)
+        assert np.all(np.isnan(d) | (np.abs(d - 1.0) < 1e-15))
+        assert np.nanmax(np.abs(blk)) <= 1.0 + 1e-15
+        g = ctx.pairs(ga, gb, ranked=True)
+        ctx.set_global_list(np.sort(np.where(np.isnan(g), -99.0, g)))
+        ctx.set_features(t.chrom, t.start, t.end, t.names)
+        out = {}
+        for mode in ("dedup", "per_query"):
+            ctx.set_count_mode(mode)
+            out[mode] = ctx.network_batch(hits, Options(anticorrelation=True), want_scores=True, want_counts=True)
+        a, b = out["dedup"], out["per_query"]
+        assert np.array_equal(a.counts, b.counts)
+        assert np.array_equal(a.scores, b.scores)
+        assert np.array_equal(a.n_groups, b.n_groups) and np.array_equal(a.group_winner, b.group_winner)
+        assert np.array_equal(a.group_density, b.group_density)
+        cnt = a.counts[a.counts >= 0]
+        assert cnt.min() >= 0 and cnt.max() <= N - 1
+        # idx is monotone in the statistic within a query row: higher score <=> larger idx (without -a it is strict)
+        assert np.all(a.scores >= 0)
