@@ -145,7 +145,7 @@ struct coex_ctx {
     coex::DevBuf<double> p_out;
     long long strip_mb = 1024;
     int gemm_mode = 0;
-    int gemm_bn = 128;                        // tcgen05 column tile: 128 (1 CTA/SM) or 64 (2 CTAs/SM)
+    int gemm_bn = 0;                          // tcgen05 kernel: 0 = persistent 128x64 tiles (default), 128 / 64 = one tile per CTA
 
     // ---- bookkeeping ------------------------------------------------------------------------
     long long launches = 0;

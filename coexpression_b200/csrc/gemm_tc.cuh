@@ -7,7 +7,10 @@
 // correlation is exact (no split-precision error at all): r = (S/4)/(sqrt(Saa/4)*sqrt(Sbb/4))
 // reproduces the reference's double result bit for bit (coexpression_v2.c:105-113 on ranks).
 //
-// Kernel shape (one CTA per 128 x 128 output tile, 192 threads, warp-specialised):
+// Three kernels share the pipeline below: gemm_i8_tc_persistent_kernel (default: one CTA per SM walks
+// 128 x 64 tiles, accumulators double-buffered in TMEM so the epilogue overlaps the next tile's MMAs),
+// gemm_i8_tc_kernel<128 / 64> (one tile per CTA) and gemm_digits_tc_kernel<D> (Pearson, D digits).
+// Kernel shape of gemm_i8_tc_kernel<128> (one CTA per 128 x 128 output tile, 192 threads, warp-specialised):
 //   warp 0      TMA producer: per 128-byte K block four SWIZZLE_128B boxes (A_hi, A_lo: 128 rows;
 //               B_hi, B_lo: 128 rows each, stacked into ONE 256-row B operand) -> 64 KB / stage,
 //               3 stages, mbarrier full/empty ring.
@@ -220,6 +223,141 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_const
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM walks a static list of 128 x 64 tiles.  The accumulators of a
+// tile take 256 TMEM columns ([hh|hl] [lh|ll], 64 columns each), so TWO tiles fit in TMEM and the
+// epilogue of tile t (warps 2..5) overlaps the MMAs of tile t+1 (warp 1) while warp 0 keeps the
+// 4-stage TMA ring (48 KB / stage) running across tile boundaries.
+//   barriers: full[4] / empty[4] (TMA <-> MMA), tmem_full[2] / tmem_empty[2] (MMA <-> epilogue)
+// ---------------------------------------------------------------------------------------------
+constexpr int kPsBN = 64, kPsStages = 4, kPsStage = 32768 + 2 * kPsBN * 128;
+constexpr int kPsSmem = kPsStages * kPsStage + 1024 + 256;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_i8_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                             const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+                             int *__restrict__ out, long long ldo, int nkb, int m_tiles, long long n_tiles, int *err) {
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    const uint32_t bars = base + kPsStages * kPsStage;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * kPsStages;
+    const uint32_t bar_tfull = bars + 16 * kPsStages, bar_tempty = bar_tfull + 16;
+    const uint32_t tmem_slot = bar_tempty + 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kPsStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ===== TMA producer: the stage ring runs continuously over all tiles of this CTA =====
+        if (lane == 0) {
+            long long g = 0;                                            // global K-block counter
+            bool ok = true;
+            for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+                const int m0 = (int)(tile % m_tiles) * kTcBM;           // query-row tile fastest
+                const int c0 = (int)(tile / m_tiles) * kPsBN;
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = (int)(g % kPsStages);
+                    if (g >= kPsStages && !mbar_wait(bar_empty + 8 * s, (uint32_t)((g / kPsStages) - 1) & 1u, err, 1)) { ok = false; break; }
+                    const uint32_t st = base + s * kPsStage;
+                    mbar_expect_tx(bar_full + 8 * s, kPsStage);
+                    tma_load_2d(st, &map_ah, bar_full + 8 * s, kb * kTcBK, m0);
+                    tma_load_2d(st + 16384, &map_al, bar_full + 8 * s, kb * kTcBK, m0);
+                    tma_load_2d(st + 32768, &map_bh, bar_full + 8 * s, kb * kTcBK, c0);
+                    tma_load_2d(st + 32768 + kPsBN * 128, &map_bl, bar_full + 8 * s, kb * kTcBK, c0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: alternates between the two accumulator buffers =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_i8(128, 2 * kPsBN);
+            long long g = 0;
+            int it = 0;
+            bool ok = true;
+            for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                if (it >= 2 && !mbar_wait(bar_tempty + 8 * buf, (uint32_t)((it >> 1) - 1) & 1u, err, 4)) { ok = false; break; }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc0 = tmem_base + buf * 256;
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = (int)(g % kPsStages);
+                    if (!mbar_wait(bar_full + 8 * s, (uint32_t)(g / kPsStages) & 1u, err, 2)) { ok = false; break; }
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = base + s * kPsStage;
+#pragma unroll
+                    for (int ks = 0; ks < kTcBK / 32; ++ks) {
+                        const uint64_t a_hi = umma_desc_sw128(st + ks * 32);
+                        const uint64_t a_lo = umma_desc_sw128(st + 16384 + ks * 32);
+                        const uint64_t b_cat = umma_desc_sw128(st + 32768 + ks * 32);
+                        const uint32_t acc = (kb | ks) ? 1u : 0u;
+                        umma_i8(acc0, a_hi, b_cat, idesc, acc);                    // [hi.hi | hi.lo]
+                        umma_i8(acc0 + 2 * kPsBN, a_lo, b_cat, idesc, acc);        // [lo.hi | lo.lo]
+                    }
+                    umma_commit(bar_empty + 8 * s);
+                }
+                if (ok) umma_commit(bar_tfull + 8 * buf);
+            }
+        }
+    } else {
+        // ===== epilogue: drains buffer `buf` while the MMA warp fills the other one =====
+        const int quarter = warp & 3;
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const int m0 = (int)(tile % m_tiles) * kTcBM;
+            const int c0 = (int)(tile / m_tiles) * kPsBN;
+            if (!mbar_wait(bar_tfull + 8 * buf, (uint32_t)(it >> 1) & 1u, err, 3)) break;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tl = tmem_base + buf * 256 + ((uint32_t)(quarter * 32) << 16);
+            int *orow = out + (long long)(m0 + quarter * 32 + lane) * ldo + c0;
+#pragma unroll 1
+            for (int cc = 0; cc < kPsBN; cc += 16) {
+                uint32_t hh[16], hl[16], lh[16], ll[16];
+                tmem_ld16(tl + cc, hh);
+                tmem_ld16(tl + kPsBN + cc, hl);
+                tmem_ld16(tl + 2 * kPsBN + cc, lh);
+                tmem_ld16(tl + 3 * kPsBN + cc, ll);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    int4 v;
+                    v.x = (int)(16384LL * (int)hh[j] + 128LL * ((long long)(int)hl[j] + (int)lh[j]) + (int)ll[j]);
+                    v.y = (int)(16384LL * (int)hh[j + 1] + 128LL * ((long long)(int)hl[j + 1] + (int)lh[j + 1]) + (int)ll[j + 1]);
+                    v.z = (int)(16384LL * (int)hh[j + 2] + 128LL * ((long long)(int)hl[j + 2] + (int)lh[j + 2]) + (int)ll[j + 2]);
+                    v.w = (int)(16384LL * (int)hh[j + 3] + 128LL * ((long long)(int)hl[j + 3] + (int)lh[j + 3]) + (int)ll[j + 3]);
+                    *reinterpret_cast<int4 *>(orow + cc + j) = v;
+                }
+            }
+            // this warp's TMEM reads have completed (wait::ld): hand the buffer back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
 // =============================================================================================
 // Generic D-digit variant (Pearson): z-scores quantised to D base-128 int8 digits
 // (prepare.cuh: pearson_pack_kernel).  One CTA per 128 x 32 output tile; per 32-byte K step
@@ -398,7 +536,8 @@ inline int tc_gemm_i8_ptrs(coex_ctx *c, const int8_t *a_hi, const int8_t *a_lo, 
     TcState *t = nullptr;
     COEX_TRY(tc_state(c, &t));
     if (m_rows % kTcBM) COEX_FAIL("tc_gemm: query rows must be padded to 128");
-    const int BN = c->gemm_bn;
+    const bool persistent = (c->gemm_bn == 0);
+    const int BN = persistent ? kPsBN : c->gemm_bn;
     if (t->bh != c->u_hi.p || t->bl != c->u_lo.p || t->b_rows != c->N_pad || t->n_pad != c->n_pad || t->bn != BN) {
         COEX_TRY(tc_encode(t, &t->map_bh, c->u_hi.p, c->N_pad, c->n_pad, BN));
         COEX_TRY(tc_encode(t, &t->map_bl, c->u_lo.p, c->N_pad, c->n_pad, BN));
@@ -413,7 +552,17 @@ inline int tc_gemm_i8_ptrs(coex_ctx *c, const int8_t *a_hi, const int8_t *a_lo, 
     if (!t->attr_set) {
         COEX_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmem));
         COEX_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::kSmem));
+        COEX_CUDA(cudaFuncSetAttribute(gemm_i8_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPsSmem));
         t->attr_set = true;
+    }
+    if (persistent) {
+        const int m_tiles = (int)(m_rows / kTcBM);
+        const long long n_tiles = (long long)m_tiles * (c->N_pad / kPsBN);
+        const unsigned ctas = (unsigned)std::min<long long>(n_tiles, c->sm_count);
+        gemm_i8_tc_persistent_kernel<<<ctas, kTcThreads, kPsSmem, c->stream>>>(t->map_ah, t->map_al, t->map_bh, t->map_bl, out, ldo,
+                                                                               c->n_pad / kTcBK, m_tiles, n_tiles, t->d_err);
+        COEX_CUDA(cudaGetLastError());
+        return 0;
     }
     dim3 grid((unsigned)(m_rows / kTcBM), (unsigned)(c->N_pad / BN));
     if (BN == 128)

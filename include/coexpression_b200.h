@@ -130,8 +130,9 @@ int coex_network_batch(coex_ctx *ctx, const coex_params *params, int K,
  * stage ids: 0 rank+pack, 1 row stats, 2 gather, 3 correlation GEMM, 4 count+score, 5 network */
 long long coex_launch_count(coex_ctx *ctx);
 int coex_stage_ms(coex_ctx *ctx, int stage, double *ms, long long *launches);
-/* 0 = tcgen05/TMA tensor-core GEMM, 1 = SIMT dp4a GEMM (validation path);
- * 64 / 128 = tcgen05 with that table-column tile (64: two CTAs per SM, 128: one) */
+/* 0 = tcgen05/TMA tensor-core GEMM (default: persistent kernel, 128 x 64 tiles, double-buffered TMEM),
+ * 1 = SIMT dp4a GEMM (validation path), 2 = persistent tcgen05 kernel explicitly,
+ * 64 / 128 = one-tile-per-CTA tcgen05 kernel with that table-column tile */
 int coex_set_gemm_mode(coex_ctx *ctx, int mode);
 /* 0 = de-duplicated bucket-table count kernel (default), 1 = per-query binary-search kernel */
 int coex_set_count_mode(coex_ctx *ctx, int mode);
