@@ -138,6 +138,42 @@ def read_snp_map(mapfile, table, verbose=False):
     return snp_map
 
 
+def make_correlation_list(ctx, names, correlationfile, correlationmeasure="Spearman", gpl_len=1000000, seed=None):
+    """Row N2: the global correlation list (reference 0-prepare-coex.py:621-716), the second caller of the
+    pair-list ABI.  Existing entries are kept (sub-sampled to gpl_len), int(1.1 * missing) random row pairs are
+    drawn, only pairs whose labels differ in their first five characters ("different chromosome", :682) are
+    correlated -- on the GPU, through the resident table (ctx.pairs == getPearson) -- NaN -> -99, and the
+    ascending list is written one value per line.  Returns the list as a numpy array."""
+    import random
+    rnd = random.Random(seed)
+    existing = []
+    if os.path.exists(correlationfile):
+        with open(correlationfile) as f:
+            lines = f.readlines()
+        if len(lines) > gpl_len:
+            lines = rnd.sample(lines, gpl_len)
+        try:
+            existing = [float(x) for x in lines if x.strip() != ""]
+        except ValueError:
+            existing = []
+    new_to_add = int(min(gpl_len, gpl_len - len(existing)) * 1.1)
+    if new_to_add > 0:
+        n = len(names)
+        ia, ib = [], []
+        for _ in range(new_to_add):
+            a, b = rnd.randint(0, n - 1), rnd.randint(0, n - 1)
+            if names[a][:5] != names[b][:5]:
+                ia.append(a)
+                ib.append(b)
+        r = ctx.pairs(np.array(ia, dtype=np.int32), np.array(ib, dtype=np.int32), ranked=(correlationmeasure == "Spearman"))
+        existing += [(-99 if v != v else float(v)) for v in r]
+        existing.sort()
+        with open(correlationfile, "w") as o:
+            for v in existing:
+                o.write("%s\n" % v)
+    return np.array(existing, dtype=np.float64)
+
+
 def empiricalp(thisvalue, empiricalcollection):
     if len(empiricalcollection) == 0:
         return 1

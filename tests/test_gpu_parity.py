@@ -482,3 +482,30 @@ def test_properties_at_scale_and_cross_implementation():
         assert cnt.min() >= 0 and cnt.max() <= N - 1
         # idx is monotone in the statistic within a query row: higher score <=> larger idx (without -a it is strict)
         assert np.all(a.scores >= 0)
+
+
+def test_global_correlation_list_row_n2(tmp_path):
+    """Row N2 (0-prepare-coex.py:621-716): the list file produced through the resident-table pair kernel holds
+    exactly the values the reference C library gives for the same random pairs, ascending, -99 for NaN."""
+    import random
+    from coexpression_b200 import synth
+    from coexpression_b200.api import CoexContext
+    from coexpression_b200.coexfunctions import make_correlation_list, read_correlation_list
+    from oracle import network_oracle as no
+    t = synth.make_table(2000, 50, seed=17)
+    R = no.rank_rows(t.X)
+    path = str(tmp_path / "t.expression.spearmanlist")
+    with CoexContext() as ctx:
+        ctx.set_expression(t.X); ctx.prepare()
+        got = make_correlation_list(ctx, t.names, path, "Spearman", gpl_len=5000, seed=123)
+        again = make_correlation_list(ctx, t.names, path, "Spearman", gpl_len=5000, seed=5)     # long enough: kept as is
+    rnd = random.Random(123)
+    ia, ib = [], []
+    for _ in range(int(5000 * 1.1)):
+        a, b = rnd.randint(0, 1999), rnd.randint(0, 1999)
+        if t.names[a][:5] != t.names[b][:5]:
+            ia.append(a); ib.append(b)
+    want = no.get_pearson(R, np.array(ia, dtype=np.int32), np.array(ib, dtype=np.int32))
+    want = np.sort(np.where(np.isnan(want), -99.0, want))
+    assert np.array_equal(got, want) and np.array_equal(read_correlation_list(path), want)
+    assert np.array_equal(again, want)

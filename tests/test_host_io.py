@@ -80,3 +80,35 @@ def test_correlation_list_and_collation_maths(tmp_path):
         assert np.array_equal(a[0], b[0]) and np.allclose(a[1], b[1], rtol=0, atol=1e-15)
     pool = [3.0, 1.0, 2.0, 2.0]
     assert empiricalp(2.0, pool) == 0.75 and empiricalp(9.0, pool) == 0.0 and empiricalp(1.0, []) == 1
+
+
+def test_collate_numbers_against_oracle(tmp_path):
+    """Row N3: pooled null, empirical p, BY / BH and the positional pairing of the main table."""
+    from coexpression_b200.collate import collate
+    from oracle import network_oracle as no
+    rng = np.random.default_rng(3)
+    wd = tmp_path / "w"; store = wd / "perm_results_store"; store.mkdir(parents=True)
+    groups = [f"chr1:{100 * i}..{100 * i + 10},+" for i in range(9)]
+    real = {g: float(v) for g, v in zip(groups, np.round(rng.gamma(2.0, 3.0, 9), 3))}
+    real[groups[4]] = real[groups[3]]                       # tied densities
+    objs = {"indmeasure": real, "individualscores": {}, "prom_to_join": {g: [g] for g in groups},
+            "indjoined": {g: {h: 1.0 for h in groups if h != g} for g in groups},
+            "joining_instructions": {g: g for g in groups}, "winners": {g: g for g in groups},
+            "allpromoterscores": {g: 0.0 for g in groups}, "snp_map": {g: {"p": -9999, "snps": f"rs{i}|rs{i}b"} for i, g in enumerate(groups)}}
+    for name, obj in objs.items():
+        json.dump(obj, open(store / f"f5ep.{name}.0", "w"))
+    perms = []
+    for k in range(1, 6):
+        d = {f"g{j}": float(v) for j, v in enumerate(np.round(rng.gamma(2.0, 2.5, 7), 3))}
+        perms.append(d)
+        json.dump(d, open(store / f"f5ep.indmeasure.{k}", "w"))
+    json.dump({"supplementary_label": "lab", "verbose": "False"}, open(wd / "settings.txt", "w"))
+    got = collate(str(wd))
+    ps, by, bh = no.collate(real, perms)
+    assert got["p"] == ps and np.allclose(got["fdr_by"], by, atol=1e-15) and np.allclose(got["fdr_bh"], bh, atol=1e-15)
+    assert got["num_completed_perms"] == 5
+    rows = open(got["individual_scores_file"]).read().splitlines()
+    assert len(rows) == 10 and rows[0].startswith("Top_promoter[SNPs_in_top_promoter]")
+    order = sorted(real.items(), key=lambda kv: (kv[1], kv[0]), reverse=True)
+    first = rows[1].split("\t")
+    assert first[2] == order[0][0] and float(first[5]) == order[0][1] / 9 and float(first[6]) == ps[0]
