@@ -12,6 +12,7 @@
 #include "allpairs.cuh"
 
 #include <algorithm>
+#include <ctime>
 #include <mutex>
 
 namespace coex {
@@ -83,6 +84,9 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     const long long H = perm_off[K];
     const long long N = c->N;
     cudaStream_t st = c->stream;
+    const bool tdbg = getenv("COEX_HOST_DEBUG") != nullptr;
+    auto now_us = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
+    const double t_start = now_us();
     // ---- counting sort of the queries by table row (host, O(N + H)) -------------------------------
     std::vector<int> cnt((size_t)N + 1, 0);
     for (long long q = 0; q < H; ++q) {
@@ -140,6 +144,7 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     COEX_TRY(c->dd_items.reserve(std::max<size_t>(items.size(), 1) * sizeof(DedupItem)));
     COEX_CUDA(cudaMemcpyAsync(c->dd_items.p, items.data(), items.size() * sizeof(DedupItem), cudaMemcpyHostToDevice, st));
     const int bm_words = (N <= 262144) ? (int)((N + 31) / 32) : 0;     // hit-column bitmap (<= 32 KB)
+    if (tdbg) fprintf(stderr, "[coex host] dedupe plan: %.0f us (H=%lld U=%lld items=%zu)\n", now_us() - t_start, H, U, items.size());
     const size_t smem = dedup_smem_bytes(Tcap, Qcap, bm_words);
     if (smem > 227 * 1024) COEX_FAIL("count_dedup: too many queries of one table row for shared memory");
     COEX_CUDA(cudaFuncSetAttribute(count_dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
