@@ -8,6 +8,7 @@
 #include "gemm_tc.cuh"
 #include "count.cuh"
 #include "count_dedup.cuh"
+#include "count_rows.cuh"
 #include "network.cuh"
 #include "allpairs.cuh"
 
@@ -109,7 +110,10 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
             Pq[(size_t)q] = (int)(perm_off[k + 1] - perm_off[k]);
         }
     const long long U = (long long)uniq.size();
-    const int Tcap = std::max(kDdBuckets / 2, (int)round_up(Pmax, 256));   // 2*Tcap >= buckets: the bucket cursors alias thr32|hist
+    const bool rows_kernel = (c->count_mode == 2);
+    const int KT = (Pmax <= 8 * kCrThreads) ? 8 : 16;
+    const int Tcap = rows_kernel ? KT * kCrThreads                           // running counts live in KT registers per thread
+                                 : std::max(kDdBuckets / 2, (int)round_up(Pmax, 256));   // 2*Tcap >= buckets: the bucket cursors alias thr32|hist
     // ---- strips of unique rows ------------------------------------------------------------------------
     const long long ld = c->N_pad;
     long long Us = (c->strip_mb << 20) / (ld * 4);
@@ -145,13 +149,28 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     COEX_CUDA(cudaMemcpyAsync(c->dd_items.p, items.data(), items.size() * sizeof(DedupItem), cudaMemcpyHostToDevice, st));
     const int bm_words = (N <= 262144) ? (int)((N + 31) / 32) : 0;     // hit-column bitmap (<= 32 KB)
     if (tdbg) fprintf(stderr, "[coex host] dedupe plan: %.0f us (H=%lld U=%lld items=%zu)\n", now_us() - t_start, H, U, items.size());
-    const size_t smem = dedup_smem_bytes(Tcap, Qcap, bm_words);
-    if (smem > 227 * 1024) COEX_FAIL("count_dedup: too many queries of one table row for shared memory");
-    COEX_CUDA(cudaFuncSetAttribute(count_dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = rows_kernel ? rows_smem_bytes(Tcap, Qcap) : dedup_smem_bytes(Tcap, Qcap, bm_words);
+    if (smem > 227 * 1024) COEX_FAIL("count kernel: too many queries of one table row for shared memory");
     int per_sm = 1;
-    COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_dedup_kernel, kDdThreads, smem));
+    if (rows_kernel) {
+        COEX_CUDA(cudaFuncSetAttribute(count_rows_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        COEX_CUDA(cudaFuncSetAttribute(count_rows_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (KT == 8) COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_rows_kernel<8>, kCrThreads, smem));
+        else COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_rows_kernel<16>, kCrThreads, smem));
+    } else {
+        COEX_CUDA(cudaFuncSetAttribute(count_dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_dedup_kernel, kDdThreads, smem));
+    }
     const int grid_max = std::max(1, per_sm) * c->sm_count;
-    COEX_TRY(c->dd_gthr.reserve((size_t)grid_max * Tcap * 3)); COEX_TRY(c->dd_gorg.reserve((size_t)grid_max * Tcap * 5));
+    if (rows_kernel) {
+        COEX_TRY(c->dd_gthr.reserve((size_t)grid_max * Tcap));
+        COEX_TRY(c->dd_qperm.reserve((size_t)std::max<long long>(H, 1)));
+        query_perm_kernel<<<(unsigned)((H + 255) / 256), 256, 0, st>>>(c->d_perm_off.p, K, H, c->dd_qperm.p);
+        COEX_CUDA(cudaGetLastError());
+        c->launches += 1;
+    } else {
+        COEX_TRY(c->dd_gthr.reserve((size_t)grid_max * Tcap * 3)); COEX_TRY(c->dd_gorg.reserve((size_t)grid_max * Tcap * 5));
+    }
     COEX_TRY(c->dd_tab.reserve((size_t)N + 1));
     score_table_kernel<<<(unsigned)((N + 256) / 256), 256, 0, st>>>(c->dd_tab.p, N, prm->anticorrelation);
     COEX_CUDA(cudaGetLastError());
@@ -175,7 +194,19 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
         da.bm_words = bm_words;
         da.R = std::min(1.0, std::max(0.05, 8.0 / std::sqrt((double)std::max(c->n, 2)))); da.g_thr = c->dd_gthr.p; da.g_org = c->dd_gorg.p; da.score_tab = c->dd_tab.p; da.phase_clk = dbg ? phase.p : nullptr;
         COEX_TRY(stage_begin(c, ST_COUNT));
-        count_dedup_kernel<<<std::min(grid_max, std::max(da.n_items, 1)), kDdThreads, smem, st>>>(da);
+        if (rows_kernel) {
+            RowCountArgs ra{};
+            ra.strip = da.strip; ra.ld = ld; ra.items = da.items; ra.n_items = da.n_items; ra.uniq_rows = da.uniq_rows;
+            ra.qlist = da.qlist; ra.q_perm = c->dd_qperm.p; ra.perm_off = da.perm_off; ra.sc_off = da.sc_off;
+            ra.hit_rows = d_hits; ra.sx = da.sx; ra.icol = da.icol; ra.rawsum_pos = da.rawsum_pos; ra.N = N;
+            ra.n_degenerate = da.n_degenerate; ra.anticor = da.anticor; ra.scores = d_sc; ra.counts = d_cn; ra.Qcap = Qcap;
+            ra.g_t64 = c->dd_gthr.p; ra.score_tab = da.score_tab; ra.phase_clk = da.phase_clk;
+            const int grid = std::min(grid_max, std::max(ra.n_items, 1));
+            if (KT == 8) count_rows_kernel<8><<<grid, kCrThreads, smem, st>>>(ra);
+            else count_rows_kernel<16><<<grid, kCrThreads, smem, st>>>(ra);
+        } else {
+            count_dedup_kernel<<<std::min(grid_max, std::max(da.n_items, 1)), kDdThreads, smem, st>>>(da);
+        }
         COEX_KCHECK(st);
         COEX_TRY(stage_end(c, 1));
     }
@@ -184,6 +215,10 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     if (dbg) {
         unsigned long long h[8];
         COEX_CUDA(cudaMemcpy(h, phase.p, sizeof h, cudaMemcpyDeviceToHost));
+        if (rows_kernel)
+            fprintf(stderr, "[coex count rows] items=%llu cycles/item: meta=%llu stats=%llu chunks=%llu score=%llu (Tcap=%d Qcap=%d grid<=%d smem=%zu)\n",
+                    h[6], h[0] / std::max(1ULL, h[6]), h[1] / std::max(1ULL, h[6]), h[2] / std::max(1ULL, h[6]), h[3] / std::max(1ULL, h[6]), Tcap, Qcap, grid_max, smem);
+        else
         fprintf(stderr, "[coex count] items=%llu queued=%llu cycles/item: meta=%llu stats=%llu rank=%llu stream=%llu refine=%llu score=%llu (Tcap=%d Qcap=%d grid<=%d)\n",
                 h[6], h[7], h[0] / std::max(1ULL, h[6]), h[1] / std::max(1ULL, h[6]), h[2] / std::max(1ULL, h[6]), h[3] / std::max(1ULL, h[6]),
                 h[4] / std::max(1ULL, h[6]), h[5] / std::max(1ULL, h[6]), Tcap, Qcap, grid_max);
@@ -297,7 +332,7 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
                 COEX_CUDA(cudaGetLastError());
                 COEX_TRY(stage_end(c, 1));
             }
-            if (prm->measure == 0 && c->count_mode == 0) {
+            if (prm->measure == 0 && c->count_mode != 1) {
                 std::vector<int> hh;
                 const int *h_hits = hit_rows;
                 if (on_device) {
@@ -558,7 +593,7 @@ int coex_destroy(coex_ctx *c) {
     c->d_aps.release(); c->d_scores.release(); c->w_s1.release(); c->w_d0.release(); c->w_w.release();
     c->d_counts.release(); c->w_best.release(); c->w_cand.release(); c->w_state.release(); c->p_idxa.release(); c->p_idxb.release();
     c->p_out.release(); c->icol.release(); c->d_ndeg.release(); c->dd_uniq.release(); c->dd_qlist.release();
-    c->dd_items.release(); c->dd_gthr.release(); c->dd_gorg.release(); c->dd_tab.release();
+    c->dd_items.release(); c->dd_qperm.release(); c->dd_gthr.release(); c->dd_gorg.release(); c->dd_tab.release();
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -727,7 +762,8 @@ int coex_set_gemm_mode(coex_ctx *c, int mode) {
 
 int coex_set_count_mode(coex_ctx *c, int mode) {
     if (!c) COEX_FAIL("null context");
-    if (mode != 0 && mode != 1) COEX_FAIL("coex_set_count_mode: 0 = de-duplicated bucket kernel, 1 = per-query kernel");
+    if (mode != 0 && mode != 1 && mode != 2)
+        COEX_FAIL("coex_set_count_mode: 0 = de-duplicated sorted-statistics kernel, 1 = per-query kernel, 2 = de-duplicated bucket-window kernel");
     c->count_mode = mode;
     return 0;
 }

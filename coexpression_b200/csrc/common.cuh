@@ -136,11 +136,11 @@ struct coex_ctx {
     coex::DevBuf<float> icol;                 // [N_pad] (float)(0.5/sx), 0 for zero-variance rows
     coex::DevBuf<int> d_ndeg;                 // [1]
     int n_degenerate = 0;
-    coex::DevBuf<int> dd_uniq, dd_qlist;      // de-duplicated query rows
+    coex::DevBuf<int> dd_uniq, dd_qlist, dd_qperm;   // de-duplicated query rows; permutation of every flat hit index
     coex::DevBuf<unsigned char> dd_items;     // DedupItem[]
     coex::DevBuf<double> dd_gthr, dd_tab;
     coex::DevBuf<unsigned int> dd_gorg;
-    int count_mode = 0;                       // 0 = de-duplicated bucket kernel, 1 = per-query binary-search kernel
+    int count_mode = 0;                       // 0 = de-duplicated sorted-statistics kernel (count_dedup), 1 = per-query binary-search kernel, 2 = de-duplicated bucket-window kernel (count_rows)
     coex::DevBuf<int> p_idxa, p_idxb;         // coex_pairs staging
     coex::DevBuf<double> p_out;
     long long strip_mb = 1024;

@@ -134,7 +134,8 @@ int coex_stage_ms(coex_ctx *ctx, int stage, double *ms, long long *launches);
  * 1 = SIMT dp4a GEMM (validation path), 2 = persistent tcgen05 kernel explicitly,
  * 64 / 128 = one-tile-per-CTA tcgen05 kernel with that table-column tile */
 int coex_set_gemm_mode(coex_ctx *ctx, int mode);
-/* 0 = de-duplicated bucket-table count kernel (default), 1 = per-query binary-search kernel */
+/* 0 = de-duplicated sorted-statistics count kernel (default, count_dedup.cuh), 1 = per-query binary-search kernel,
+ * 2 = de-duplicated bucket-window kernel (count_rows.cuh): three independent implementations of the same counts */
 int coex_set_count_mode(coex_ctx *ctx, int mode);
 int coex_set_workspace_mb(coex_ctx *ctx, long long strip_mb);
 /* On-device cross-check: the first m_rows table rows against the whole table through the tcgen05

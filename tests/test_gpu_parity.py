@@ -161,8 +161,9 @@ def test_network_golden_dp4a(name):
 
 
 @pytest.mark.parametrize("name", ["spearman_default", "spearman_anticor", "spearman_useavg_m"])
-def test_network_golden_per_query_count_kernel(name):
-    _run_case(name, "tcgen05", "per_query")
+@pytest.mark.parametrize("count_mode", ["per_query", "dedup_window"])
+def test_network_golden_other_count_kernels(name, count_mode):
+    _run_case(name, "tcgen05", count_mode)
 
 
 def test_network_against_live_oracle_small_shape():
@@ -470,14 +471,16 @@ def test_properties_at_scale_and_cross_implementation():
         ctx.set_global_list(np.sort(np.where(np.isnan(g), -99.0, g)))
         ctx.set_features(t.chrom, t.start, t.end, t.names)
         out = {}
-        for mode in ("dedup", "per_query"):
+        for mode in ("dedup", "per_query", "dedup_window"):
             ctx.set_count_mode(mode)
             out[mode] = ctx.network_batch(hits, Options(anticorrelation=True), want_scores=True, want_counts=True)
-        a, b = out["dedup"], out["per_query"]
-        assert np.array_equal(a.counts, b.counts)
-        assert np.array_equal(a.scores, b.scores)
-        assert np.array_equal(a.n_groups, b.n_groups) and np.array_equal(a.group_winner, b.group_winner)
-        assert np.array_equal(a.group_density, b.group_density)
+        a = out["dedup"]
+        for other in ("per_query", "dedup_window"):
+            b = out[other]
+            assert np.array_equal(a.counts, b.counts), other
+            assert np.array_equal(a.scores, b.scores), other
+            assert np.array_equal(a.n_groups, b.n_groups) and np.array_equal(a.group_winner, b.group_winner)
+            assert np.array_equal(a.group_density, b.group_density), other
         cnt = a.counts[a.counts >= 0]
         assert cnt.min() >= 0 and cnt.max() <= N - 1
         # idx is monotone in the statistic within a query row: higher score <=> larger idx (without -a it is strict)
@@ -498,7 +501,10 @@ def test_global_correlation_list_row_n2(tmp_path):
     with CoexContext() as ctx:
         ctx.set_expression(t.X); ctx.prepare()
         got = make_correlation_list(ctx, t.names, path, "Spearman", gpl_len=5000, seed=123)
-        again = make_correlation_list(ctx, t.names, path, "Spearman", gpl_len=5000, seed=5)     # long enough: kept as is
+        # a file that already holds gpl_len entries is kept as is (0-prepare-coex.py:629-637: no sub-sampling, new_to_add == 0)
+        again = make_correlation_list(ctx, t.names, path, "Spearman", gpl_len=len(got), seed=5)
+        # a longer file is sub-sampled to gpl_len (random.sample, :630) and nothing is added
+        fewer = make_correlation_list(ctx, t.names, path, "Spearman", gpl_len=1000, seed=5)
     rnd = random.Random(123)
     ia, ib = [], []
     for _ in range(int(5000 * 1.1)):
@@ -509,3 +515,4 @@ def test_global_correlation_list_row_n2(tmp_path):
     want = np.sort(np.where(np.isnan(want), -99.0, want))
     assert np.array_equal(got, want) and np.array_equal(read_correlation_list(path), want)
     assert np.array_equal(again, want)
+    assert len(fewer) == 1000 and np.all(np.isin(fewer, want))
