@@ -303,6 +303,8 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
     COEX_TRY(c->w_root.reserve(Hs_alloc)); COEX_TRY(c->w_pos.reserve(Hs_alloc)); COEX_TRY(c->w_s1.reserve(Hs_alloc));
     COEX_TRY(c->w_d0.reserve(Hs_alloc)); COEX_TRY(c->w_w.reserve(Hs_alloc)); COEX_TRY(c->w_best.reserve(Hs_alloc));
     COEX_TRY(c->w_cand.reserve(Hs_alloc)); COEX_TRY(c->w_state.reserve(K + 1));
+    COEX_TRY(c->w_gsize.reserve(Hs_alloc)); COEX_TRY(c->w_cursor.reserve(Hs_alloc)); COEX_TRY(c->w_act.reserve(Hs_alloc));
+    COEX_TRY(c->w_actn.reserve(K)); COEX_TRY(c->w_front.reserve(K));
     COEX_CUDA(cudaMemsetAsync(c->w_state.p, 0, (K + 1) * sizeof(int), st));
     // outputs of unused slots are defined
     COEX_CUDA(cudaMemsetAsync(d_grp, 0xff, H * sizeof(int), st));
@@ -401,6 +403,7 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
         na.group_density = d_dens; na.hit_score = d_aps;
         na.w_root = c->w_root.p; na.w_pos = c->w_pos.p; na.w_s1 = c->w_s1.p; na.w_d0 = c->w_d0.p; na.w_w = c->w_w.p;
         na.w_best = c->w_best.p; na.w_cand = c->w_cand.p; na.w_state = c->w_state.p; na.w_flags = c->w_state.p + K;
+        na.w_gsize = c->w_gsize.p; na.w_cursor = c->w_cursor.p; na.w_act = c->w_act.p; na.w_actn = c->w_actn.p; na.w_front = c->w_front.p;
         na.P2max = T2max;
     }
     std::vector<long long> warp_off(K + 1, 0);
@@ -413,7 +416,7 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
     auto pass2_round = [&](bool last) -> int {
         net_rowsum_kernel<1><<<rs_blocks, rs_threads, 0, st>>>(na);
         COEX_KCHECK(st);
-        net_pick_kernel<<<thread_blocks, 256, 0, st>>>(na, H);
+        net_pick_kernel<<<thread_blocks, 256, 0, st>>>(na, H, 0);
         COEX_KCHECK(st);
         if (last) COEX_CUDA(cudaMemsetAsync(na.w_flags, 0, sizeof(int), st));
         net_commit_kernel<<<K, 256, 0, st>>>(na, 0);
@@ -422,6 +425,8 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
     };
     auto density_tail = [&]() -> int {
         const size_t rsmem = (size_t)T2max * 8;
+        net_rowsum_kernel<4><<<rs_blocks, rs_threads, 0, st>>>(na);      // allpromoterscores against the final winners
+        COEX_KCHECK(st);
         net_rowsum_kernel<2><<<rs_blocks, rs_threads, 0, st>>>(na);
         COEX_KCHECK(st);
         net_removal_kernel<<<K, 256, rsmem, st>>>(na, 0);
@@ -442,13 +447,13 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
         COEX_KCHECK(st);
         net_rowsum_kernel<0><<<rs_blocks, rs_threads, 0, st>>>(na);
         COEX_KCHECK(st);
-        net_pick_kernel<<<thread_blocks, 256, 0, st>>>(na, H);
+        net_pick_kernel<<<thread_blocks, 256, 0, st>>>(na, H, 1);
         COEX_KCHECK(st);
         net_commit_kernel<<<K, 256, 0, st>>>(na, 1);
         COEX_KCHECK(st);
         for (int r = 0; r < kRounds; ++r) COEX_TRY(pass2_round(r == kRounds - 1));
         COEX_TRY(density_tail());
-        net_launches = 4 + 3 * kRounds + (prm->noiter ? 3 : 4);
+        net_launches = 4 + 3 * kRounds + (prm->noiter ? 4 : 5);
         COEX_TRY(stage_end(c, net_launches));
     } else {
         COEX_CUDA(cudaMemsetAsync(d_ng, 0, K * sizeof(int), st));
@@ -478,7 +483,7 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
                 COEX_CUDA(cudaMemcpy(&flag, na.w_flags, sizeof(int), cudaMemcpyDeviceToHost));
             }
             COEX_TRY(density_tail());
-            c->launches += 4;
+            c->launches += 5;
             if (!on_device) {
                 COEX_CUDA(cudaMemcpyAsync(group_winner, d_win, H * sizeof(int), cudaMemcpyDeviceToHost, st));
                 COEX_CUDA(cudaMemcpyAsync(group_density, d_dens, H * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -591,7 +596,7 @@ int coex_destroy(coex_ctx *c) {
     c->d_perm_off.release(); c->d_sc_off.release(); c->d_warp_off.release(); c->d_hits.release(); c->d_ngroups.release(); c->d_grp.release();
     c->d_label.release(); c->d_win.release(); c->w_root.release(); c->w_pos.release(); c->d_dens.release();
     c->d_aps.release(); c->d_scores.release(); c->w_s1.release(); c->w_d0.release(); c->w_w.release();
-    c->d_counts.release(); c->w_best.release(); c->w_cand.release(); c->w_state.release(); c->p_idxa.release(); c->p_idxb.release();
+    c->d_counts.release(); c->w_gsize.release(); c->w_cursor.release(); c->w_act.release(); c->w_actn.release(); c->w_front.release(); c->w_best.release(); c->w_cand.release(); c->w_state.release(); c->p_idxa.release(); c->p_idxb.release();
     c->p_out.release(); c->icol.release(); c->d_ndeg.release(); c->dd_uniq.release(); c->dd_qlist.release();
     c->dd_items.release(); c->dd_qperm.release(); c->dd_gthr.release(); c->dd_gorg.release(); c->dd_tab.release();
     cudaStreamDestroy(c->stream);

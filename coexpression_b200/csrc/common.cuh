@@ -130,6 +130,7 @@ struct coex_ctx {
     coex::DevBuf<double> strip_f64;           // Pearson null strip [Hs, N]
     coex::DevBuf<long long> d_perm_off, d_sc_off, d_warp_off;
     coex::DevBuf<int> d_hits, d_ngroups, d_grp, d_label, d_win, w_root, w_pos, w_state;
+    coex::DevBuf<int> w_gsize, w_cursor, w_act, w_actn, w_front;   // pass-2 active rows (network.cuh)
     coex::DevBuf<double> d_dens, d_aps, d_scores, w_s1, w_d0, w_w;
     coex::DevBuf<long long> d_counts;
     coex::DevBuf<unsigned long long> w_best, w_cand;

@@ -44,6 +44,11 @@ struct NetArgs {
     int *w_root, *w_pos;
     double *w_s1, *w_d0, *w_w;
     unsigned long long *w_best, *w_cand;
+    int *w_gsize;                // [H] members of group g (slot off + g)
+    int *w_cursor;               // [H] scratch of the active-row list builder
+    int *w_act;                  // [H] hit positions of the members of multi-member groups, grouped by ascending group
+    int *w_actn;                 // [K] length of that list
+    int *w_front;                // [K] pass-2 frontier: groups <= front are final (see net_commit_kernel)
     int *w_state;                // [K] 1 while the permutation's pass-2 iteration has not converged
     int *w_flags;                // [1] bit 0: some permutation changed in the last committed round
     const long long *warp_off;   // [K+1] prefix of ceil(max(P_k, 1) / 32): warp -> permutation map of the row-sum kernels
@@ -253,11 +258,15 @@ __device__ __forceinline__ int perm_of(const long long *perm_off, int K, long lo
 // columns otherwise) into a 32 x 33 shared-memory tile; then lane l adds row l left to right.
 // Skipped addends are stored as +0.0, which leaves a non-negative running sum bit-identical.
 //   MODE 0  pass 1  (1-make-network.py:365-375)  columns = all hits, hit order
-//   MODE 1  pass 2  (1-make-network.py:378-434)  columns = winners, group order (fixed-point round)
+//   MODE 1  pass 2  (1-make-network.py:378-434)  columns = winners, group order (fixed-point round); rows = the
+//           members of multi-member groups behind the permutation's frontier only (a one-member group cannot change
+//           its winner, a group at or before the frontier is final)
 //   MODE 2  density (1-make-network.py:437-462)  rows = groups (their winner's row)
 //   MODE 3  whittled density (1-make-network.py:471-478)
+//   MODE 4  pass 2 sums of EVERY hit against the final winners = allpromoterscores (1-make-network.py:424)
 constexpr int kRsWarps = 8;
-constexpr int kRsRows = 8;          // rows per warp: more warps in flight than 32-row blocks, one memory latency per chunk
+constexpr int kRsRows = 4;          // rows per warp: more warps in flight than 32-row blocks
+constexpr int kRsStages = 4;        // register pipeline depth: 32-column chunks of addends in flight per warp
 
 template <int MODE>
 __global__ void __launch_bounds__(kRsWarps * 32)
@@ -266,13 +275,15 @@ net_rowsum_kernel(NetArgs a) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long w = (long long)blockIdx.x * kRsWarps + wib;
     if (w >= a.warp_off[a.K]) return;
+    constexpr bool kHitRows = (MODE == 0 || MODE == 1 || MODE == 4);        // rows are hits (else groups)
+    constexpr bool kPass2 = (MODE == 1 || MODE == 4);
     const int k = perm_of(a.warp_off, a.K, w);
     if (MODE == 1 && !a.w_state[k]) return;
     const long long off = a.perm_off[k];
     const int P = (int)(a.perm_off[k + 1] - off);
     if (P < 2) return;
     const int G = a.n_groups[k];
-    const int nrows = (MODE <= 1) ? P : G;
+    const int nrows = (MODE == 1) ? a.w_actn[k] : (kHitRows ? P : G);
     const int ncols = (MODE == 0) ? P : G;
     const int i0 = (int)(w - a.warp_off[k]) * kRsRows;
     if (i0 >= nrows) return;
@@ -280,51 +291,94 @@ net_rowsum_kernel(NetArgs a) {
     const int *grp = a.group_of_hit + off;
     const int *win = a.group_winner + off, *w1 = a.w_pos + off, *vis = a.w_root + off;
     const double *Sc = a.scores + a.sc_off[k];
-    const int mine = i0 + lane;                                   // this lane's row
-    const bool mine_ok = (lane < kRsRows) && (mine < nrows);
-    // row attributes held by lane r for row i0 + r
-    const int my_g = mine_ok ? ((MODE <= 1) ? grp[mine] : mine) : -1;        // group of the row
-    const long long my_base = mine_ok ? (long long)((MODE <= 1) ? mine : win[mine]) * P : 0;
+    const int slot = i0 + lane;                                   // this lane's row slot
+    bool mine_ok = (lane < kRsRows) && (slot < nrows);
+    const int mine = (MODE == 1) ? (mine_ok ? a.w_act[off + slot] : 0) : slot;   // hit position (or group) of the row
+    // row attributes held by lane r for row slot i0 + r
+    int my_g = mine_ok ? (kHitRows ? grp[mine] : mine) : -1;                 // group of the row
+    if (MODE == 1) {
+        if (my_g <= a.w_front[k]) { my_g = -1; mine_ok = false; }            // final already
+        if (!__any_sync(0xffffffffu, mine_ok)) return;
+    }
+    const long long my_base = mine_ok ? (long long)(kHitRows ? mine : win[mine]) * P : 0;
     const int my_vis = (MODE == 3 && mine_ok) ? vis[mine] : 0;
     double s = 0.0;
-    for (int c0 = 0; c0 < ncols; c0 += 32) {
-        const int c = c0 + lane;                                   // this lane's column
-        const bool c_ok = c < ncols;
-        int col_a = 0, col_b = 0, gcol = -2, vcol = 0;
-        if (c_ok) {
-            if (MODE == 0) { col_a = c; gcol = grp[c]; }
-            else { col_a = win[c]; col_b = (MODE == 1) ? w1[c] : col_a; gcol = c; if (MODE == 3) vcol = vis[c]; }
+    // Register pipeline over the 32-column chunks: the kRsRows x 32 addends of kRsStages - 1 chunks are in flight and the
+    // column attributes (winner indices) one chunk further ahead, so the critical path per chunk is the 32 dependent
+    // additions and not two memory latencies plus them.  (An 8-byte cp.async gather into shared-memory stages was
+    // measured 1.9x SLOWER than this, profiles/r01_network.md.)
+    struct ColIdx { int col_a, col_b, gcol, vcol; bool ok; };
+    auto load_idx = [&](int chunk) -> ColIdx {
+        ColIdx ix{0, 0, -2, 0, false};
+        const int c = chunk * 32 + lane;                           // this lane's column
+        ix.ok = c < ncols;
+        if (ix.ok) {
+            if (MODE == 0) { ix.col_a = c; ix.gcol = grp[c]; }
+            else { ix.col_a = win[c]; ix.col_b = kPass2 ? w1[c] : ix.col_a; ix.gcol = c; if (MODE == 3) ix.vcol = vis[c]; }
         }
-        // issue all 32 loads of the chunk before the first use: one memory latency per chunk
-        double x[kRsRows];
+        return ix;
+    };
+    auto load_x = [&](const ColIdx &ix, int chunk, double (&x)[kRsRows]) {
+        const int c = chunk * 32 + lane;
 #pragma unroll
         for (int r = 0; r < kRsRows; ++r) {
             const int rg = __shfl_sync(0xffffffffu, my_g, r);
             const long long rb = __shfl_sync(0xffffffffu, my_base, r);
             const int rvis = (MODE == 3) ? __shfl_sync(0xffffffffu, my_vis, r) : 0;
-            bool use = c_ok && rg >= 0 && gcol != rg;
+            bool use = ix.ok && rg >= 0 && ix.gcol != rg;
             if (MODE == 0) use = use && (c != i0 + r);
-            if (MODE == 3) use = use && !(vcol < rvis);
-            const int col = (MODE == 1 && !(gcol < rg)) ? col_b : col_a;
+            if (MODE == 3) use = use && !(ix.vcol < rvis);
+            const int col = (kPass2 && !(ix.gcol < rg)) ? ix.col_b : ix.col_a;
             x[r] = use ? Sc[rb + col] : 0.0;
         }
-        __syncwarp();
+    };
+    auto consume = [&](const double (&x)[kRsRows]) {
+        __syncwarp();                                              // the previous chunk's additions have read the tile
 #pragma unroll
         for (int r = 0; r < kRsRows; ++r) {
             double v = x[r];
-            if (MODE != 1 && !(v >= a.thr)) v = 0.0;           // selection threshold (not applied in pass 2)
+            if (!kPass2 && !(v >= a.thr)) v = 0.0;             // selection threshold (not applied in pass 2)
             tile[r * 33 + lane] = v;
         }
         __syncwarp();
         if (mine_ok) {
-            const int lim = min(32, ncols - c0);
-            for (int cc = 0; cc < lim; ++cc) s = __dadd_rn(s, tile[lane * 33 + cc]);
+            // masked and out-of-range addends are +0.0: a non-negative running sum stays bit-identical
+            double v[32];
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc) v[cc] = tile[lane * 33 + cc];
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc) s = __dadd_rn(s, v[cc]);
+        }
+    };
+    {
+        const int nch = (ncols + 31) >> 5;
+        double x[kRsStages][kRsRows];
+        ColIdx ix_next;
+        {
+            ColIdx pre[kRsStages];
+#pragma unroll
+            for (int j = 0; j < kRsStages; ++j) pre[j] = load_idx(j);
+#pragma unroll
+            for (int j = 0; j < kRsStages - 1; ++j) load_x(pre[j], j, x[j]);
+            ix_next = pre[kRsStages - 1];
+        }
+        for (int base = 0; base < nch; base += kRsStages) {
+#pragma unroll
+            for (int j = 0; j < kRsStages; ++j) {
+                const int i = base + j;
+                if (i >= nch) break;                               // warp-uniform
+                load_x(ix_next, i + kRsStages - 1, x[(j + kRsStages - 1) % kRsStages]);
+                ix_next = load_idx(i + kRsStages);
+                consume(x[j]);
+            }
         }
     }
     if (mine_ok) {
         if (MODE <= 1) {
             a.w_s1[off + mine] = s;
             atomicMax(&a.w_best[off + my_g], (unsigned long long)__double_as_longlong(s));
+        } else if (MODE == 4) {
+            a.hit_score[off + mine] = s;
         } else {
             const double d = a.useaverage ? s / (double)G : s;
             if (MODE == 3) a.w_w[off + mine] = d; else a.w_d0[off + mine] = d;
@@ -334,7 +388,7 @@ net_rowsum_kernel(NetArgs a) {
 
 // argmax tie-break: among the members reaching the group's best sum, the smallest name
 __global__ void __launch_bounds__(256)
-net_pick_kernel(NetArgs a, long long H) {
+net_pick_kernel(NetArgs a, long long H, int first) {
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= H) return;
     const int k = perm_of(a.perm_off, a.K, q);
@@ -342,14 +396,21 @@ net_pick_kernel(NetArgs a, long long H) {
     const long long off = a.perm_off[k];
     if (a.perm_off[k + 1] - off < 2) return;
     const int gi = a.group_of_hit[q];
+    // pass-2 rounds recompute the members of multi-member groups behind the frontier only
+    if (!first && (a.w_gsize[off + gi] < 2 || gi <= a.w_front[k])) return;
     if ((unsigned long long)__double_as_longlong(a.w_s1[q]) == a.w_best[off + gi])
         atomicMin(&a.w_cand[off + gi],
                   ((unsigned long long)(unsigned)a.name_rank[a.hit_rows[q]] << 32) | (unsigned)(q - off));
 }
 
-// one CTA per permutation: commit the picked winners.  first != 0: pass-1 winners (w1 + working
-// copy).  Otherwise one Gauss-Seidel fixed-point round (see net_pass2_kernel): state[k] stays 1
-// while any winner moved; when nothing moved the sums of this round are final (allpromoterscores).
+// one CTA per permutation: commit the picked winners.
+// first != 0: pass-1 winners (w1 + working copy); it also counts the members of every group and lists the hits of
+// the multi-member groups by ascending group (the only rows pass 2 has to iterate on).
+// Otherwise one fixed-point round of pass 2.  Pass 2 is sequential in the reference (Gauss-Seidel over groups, quirk
+// Q6): W*[g] = f_g(W*[< g], W1[> g]) with W1 the pass-1 winners, a lower-triangular rule.  Iterating
+// W^r[g] = f_g(W^(r-1)[< g], W1[> g]) from W^0 = W1 reaches W* as its unique fixed point; if c is the FIRST group whose
+// winner moved in round r, every group <= c has unchanged inputs in round r + 1 and is final: front[k] = c, the next
+// round only recomputes the groups behind it, and state[k] drops to 0 when nothing moved.
 __global__ void __launch_bounds__(256)
 net_commit_kernel(NetArgs a, int first) {
     const int k = blockIdx.x;
@@ -359,21 +420,62 @@ net_commit_kernel(NetArgs a, int first) {
     if (P < 2) { if (threadIdx.x == 0) a.w_state[k] = 0; return; }
     const int G = a.n_groups[k];
     int *win = a.group_winner + off, *w1 = a.w_pos + off;
-    int changed = 0;
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    int *gsize = a.w_gsize + off, *cursor = a.w_cursor + off;
+    const int *grp = a.group_of_hit + off;
+    __shared__ int s_part[256];
+    __shared__ int s_first;
+    if (first) {
+        for (int g = threadIdx.x; g < G; g += blockDim.x) {
+            const int w = (int)(a.w_cand[off + g] & 0xffffffffULL);
+            w1[g] = w; win[g] = w;
+            a.w_best[off + g] = 0ULL;
+            a.w_cand[off + g] = ~0ULL;
+            gsize[g] = 0;
+        }
+        __syncthreads();
+        for (int p = threadIdx.x; p < P; p += blockDim.x) atomicAdd(&gsize[grp[p]], 1);
+        __syncthreads();
+        // exclusive scan over the groups of (members of multi-member groups): contiguous slice per thread
+        const int per = (G + blockDim.x - 1) / blockDim.x;
+        const int g0 = min(G, (int)threadIdx.x * per), g1 = min(G, g0 + per);
+        int local = 0;
+        for (int g = g0; g < g1; ++g) local += (gsize[g] >= 2) ? gsize[g] : 0;
+        s_part[threadIdx.x] = local;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int acc = 0;
+            for (int t = 0; t < (int)blockDim.x; ++t) { const int v = s_part[t]; s_part[t] = acc; acc += v; }
+            a.w_actn[k] = acc;
+            a.w_front[k] = -1;
+        }
+        __syncthreads();
+        int base = s_part[threadIdx.x];
+        for (int g = g0; g < g1; ++g) { cursor[g] = base; base += (gsize[g] >= 2) ? gsize[g] : 0; }
+        __syncthreads();
+        for (int p = threadIdx.x; p < P; p += blockDim.x) {
+            const int g = grp[p];
+            if (gsize[g] >= 2) a.w_act[off + atomicAdd(&cursor[g], 1)] = p;
+        }
+        return;
+    }
+    const int front = a.w_front[k];
+    if (threadIdx.x == 0) s_first = 0x7fffffff;
+    __syncthreads();
+    for (int g = front + 1 + (int)threadIdx.x; g < G; g += blockDim.x) {
+        if (gsize[g] < 2) continue;
         const int w = (int)(a.w_cand[off + g] & 0xffffffffULL);
-        if (first) { w1[g] = w; win[g] = w; }
-        else if (w != win[g]) { win[g] = w; changed = 1; }
+        if (w != win[g]) { win[g] = w; atomicMin(&s_first, g); }
         a.w_best[off + g] = 0ULL;
         a.w_cand[off + g] = ~0ULL;
     }
-    changed = __syncthreads_or(changed);
-    if (!first) {
-        if (!changed)
-            for (int i = threadIdx.x; i < P; i += blockDim.x) a.hit_score[off + i] = a.w_s1[off + i];
-        if (threadIdx.x == 0) {
-            a.w_state[k] = changed;
-            if (changed) atomicOr(a.w_flags, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int c = s_first;
+        if (c == 0x7fffffff) {
+            a.w_state[k] = 0;
+        } else {
+            a.w_front[k] = c;
+            atomicOr(a.w_flags, 1);
         }
     }
 }
