@@ -111,8 +111,7 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
         }
     const long long U = (long long)uniq.size();
     const bool rows_kernel = (c->count_mode == 2);
-    const int KT = (Pmax <= 8 * kCrThreads) ? 8 : 16;
-    const int Tcap = rows_kernel ? KT * kCrThreads                           // running counts live in KT registers per thread
+    const int Tcap = rows_kernel ? std::max(4096, (int)round_up(Pmax, 512))
                                  : std::max(kDdBuckets / 2, (int)round_up(Pmax, 256));   // 2*Tcap >= buckets: the bucket cursors alias thr32|hist
     // ---- strips of unique rows ------------------------------------------------------------------------
     const long long ld = c->N_pad;
@@ -153,10 +152,8 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     if (smem > 227 * 1024) COEX_FAIL("count kernel: too many queries of one table row for shared memory");
     int per_sm = 1;
     if (rows_kernel) {
-        COEX_CUDA(cudaFuncSetAttribute(count_rows_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        COEX_CUDA(cudaFuncSetAttribute(count_rows_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (KT == 8) COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_rows_kernel<8>, kCrThreads, smem));
-        else COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_rows_kernel<16>, kCrThreads, smem));
+        COEX_CUDA(cudaFuncSetAttribute(count_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_rows_kernel, kCrThreads, smem));
     } else {
         COEX_CUDA(cudaFuncSetAttribute(count_dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_dedup_kernel, kDdThreads, smem));
@@ -199,11 +196,10 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
             ra.strip = da.strip; ra.ld = ld; ra.items = da.items; ra.n_items = da.n_items; ra.uniq_rows = da.uniq_rows;
             ra.qlist = da.qlist; ra.q_perm = c->dd_qperm.p; ra.perm_off = da.perm_off; ra.sc_off = da.sc_off;
             ra.hit_rows = d_hits; ra.sx = da.sx; ra.icol = da.icol; ra.rawsum_pos = da.rawsum_pos; ra.N = N;
-            ra.n_degenerate = da.n_degenerate; ra.anticor = da.anticor; ra.scores = d_sc; ra.counts = d_cn; ra.Qcap = Qcap;
+            ra.n_degenerate = da.n_degenerate; ra.anticor = da.anticor; ra.scores = d_sc; ra.counts = d_cn; ra.Tcap = Tcap; ra.Qcap = Qcap;
             ra.g_t64 = c->dd_gthr.p; ra.score_tab = da.score_tab; ra.phase_clk = da.phase_clk;
             const int grid = std::min(grid_max, std::max(ra.n_items, 1));
-            if (KT == 8) count_rows_kernel<8><<<grid, kCrThreads, smem, st>>>(ra);
-            else count_rows_kernel<16><<<grid, kCrThreads, smem, st>>>(ra);
+            count_rows_kernel<<<grid, kCrThreads, smem, st>>>(ra);
         } else {
             count_dedup_kernel<<<std::min(grid_max, std::max(da.n_items, 1)), kDdThreads, smem, st>>>(da);
         }
@@ -578,6 +574,7 @@ int coex_create(coex_ctx **out, int device) {
     COEX_CUDA(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     COEX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    if (const char *e = getenv("COEX_COUNT_MODE")) c->count_mode = atoi(e);      // profiling aid (scripts/): same as coex_set_count_mode
     *out = c;
     return 0;
 }

@@ -1,6 +1,6 @@
-// count_rows.cuh -- K3 epilogue stage, sort-free variant for the Spearman null (count mode 2; a third independent
-// implementation of the counts.  Measured on B200 it is SLOWER than count_dedup.cuh: it needs two shared-memory
-// atomics per streamed value and ATOMS costs ~2 cycles per lane, profiles/r01_count_rows.md).
+// count_rows.cuh -- K3 epilogue stage, sort-free variant for the Spearman null (count mode 2): a third independent
+// implementation of the counts, used by the cross-implementation parity tests.  On B200 it is slower than the default
+// count_dedup.cuh (7.9 vs 4.6 ms per C2 step, profiles/r01_count_rows.md).
 //
 // Same contract as count.cuh (reference 1-make-network.py:239-258 null lists, :273-327 edge loop):
 // for every query (permutation k, hit position i, table row u) and every other hit j of that
@@ -9,20 +9,19 @@
 // count_dedup.cuh: one work item = (unique table row u, a run of its queries), the row of the
 // integer correlation strip is streamed ONCE for all of them.
 //
-// What changed against count_dedup.cuh (its ncu capture: ~150 instructions per streamed value and
-// more than half of the item time in latency-bound set-up phases that sorted the statistics):
-// NOTHING IS SORTED and no value is searched.  Per chunk of 8192 null values
+// Difference to count_dedup.cuh: NOTHING IS SORTED and no value is searched.  Per chunk of 8192 null values
 //   1. value -> float -> uniform bucket over [min statistic, max statistic] of the item (one subtract,
-//      one multiply, one clamp); shared-memory histogram                         (~12 instructions / value)
-//   2. exclusive scan of the 8192 bucket counts
-//   3. counting-sort scatter of the chunk's column numbers by bucket             (~8 instructions / value)
+//      one multiply, one clamp); shared-memory histogram
+//   2. exclusive scan of the 4096 bucket counts
+//   3. counting-sort scatter of the chunk's column numbers by bucket
 //   4. every statistic t, independently: (values in lower buckets) + (values of its own bucket window
 //      that are below t).  The window is [bucket(t - delta), bucket(t + delta)]; the bucket function is
 //      monotone, so a value outside the window differs from t by more than delta in float and its order
-//      against t is certain; inside the window a value closer than delta is re-evaluated in double with
-//      the reference's exact arithmetic (its own hit column always is: value == statistic).  Counts are
+//      against t is certain; inside the window a value closer than delta is queued and re-evaluated in double
+//      with the reference's exact arithmetic (its own hit column always is: value == statistic).  Windows made
+//      long by tied values (sparse rows share identical correlations) are scanned by whole warps.  Counts are
 //      therefore EXACT (tests/test_gpu_parity.py compares every index with the oracle).
-// Float error budget: |v32 - v64| <= 3e-7, |t32 - t64| <= 6e-8, delta = 5e-7.
+// Float error budget: see cr_delta below (relative: 5e-7 |t|).
 // Values below the item's lowest statistic are only counted (bucket 0), values above its highest one are
 // ignored (last bucket): neither is histogrammed, so a narrow statistic range costs no atomic contention.
 #pragma once
@@ -33,9 +32,12 @@
 namespace coex {
 
 constexpr int kCrThreads = 512;
-constexpr int kCrBuckets = 8192;
+constexpr int kCrBuckets = 4096;
 constexpr int kCrChunk = 8192;          // null values staged in shared memory per pass
 constexpr float kCrDelta = 5e-7f;
+constexpr int kCrInline = 12;           // longer bucket windows are scanned by a whole warp
+constexpr int kCrLong = 1024;
+constexpr int kCrQueue = 3072;          // (statistic, column) pairs per chunk that need the reference's double arithmetic
 
 struct RowCountArgs {
     const int *strip;               // [rows_in_strip, ld]
@@ -55,8 +57,8 @@ struct RowCountArgs {
     int anticor;
     double *scores;
     long long *counts;
-    int Qcap;                       // queries per item (shared-memory capacity); statistics per item <= KT * 512
-    double *g_t64;                  // scratch [gridDim.x, KT * 512]: statistics in double (exact refinements, scoring)
+    int Tcap, Qcap;                 // shared-memory capacities: statistics and queries per item
+    double *g_t64;                  // scratch [gridDim.x, Tcap]: statistics in double (exact refinements, scoring)
     const double *score_tab;        // [N+1] edge score of every possible bisect index (len = N-1)
     unsigned long long *phase_clk;  // optional [8]
 };
@@ -67,22 +69,28 @@ __device__ __forceinline__ int cr_bucket(float v, float lo, float scale) {
     return (int)f;
 }
 
+// |v32 - v64| <= 5 * 2^-24 |v| (int -> float, two rounded reciprocal half-norms, two products: all relative) and
+// |t32 - t64| <= 2^-24 |t|.  If |v| < 1.13 |t| the two errors add up to < 3.97e-7 |t|, otherwise |t - v| > 0.1 |v| dwarfs
+// them; a float difference of at least 5e-7 |t| (4.4e-7 |t| after the rounding of t -+ delta in the window bounds)
+// therefore decides the order.  The floor keeps exact ties at zero (d == 0) out of the "certain" branch.
+__device__ __forceinline__ float cr_delta(float t) { return fmaxf(5e-7f * fabsf(t), 1e-30f); }
+
 inline size_t rows_smem_bytes(int Tcap, int Qcap) {
-    return (size_t)kCrChunk * 4 + (size_t)kCrBuckets * 4 + (size_t)kCrChunk * 2 + (size_t)Tcap * 4 +
+    return (size_t)kCrChunk * 4 + (size_t)kCrBuckets * 4 + (size_t)kCrChunk * 2 + (size_t)Tcap * 8 + (size_t)kCrQueue * 4 +
            (size_t)Qcap * 16 + (size_t)Qcap * 8 + (size_t)(Qcap + 2) * 4 + 16;
 }
 
-// KT = statistics per thread: an item holds at most KT * 512 statistics, their running counts live in registers.
-template <int KT>
-__global__ void __launch_bounds__(kCrThreads, (KT <= 8) ? 2 : 1)
+__global__ void __launch_bounds__(kCrThreads, 2)
 count_rows_kernel(RowCountArgs a) {
-    constexpr int Tcap = KT * kCrThreads;
+    const int Tcap = a.Tcap;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *chunkv = reinterpret_cast<float *>(smem_raw);                                  // [chunk] null values (NaN = not a list entry)
     unsigned int *cum = reinterpret_cast<unsigned int *>(chunkv + kCrChunk);               // [buckets]
     unsigned short *list = reinterpret_cast<unsigned short *>(cum + kCrBuckets);           // [chunk] columns grouped by bucket
     float *t32 = reinterpret_cast<float *>(list + kCrChunk);                               // [Tcap] statistics (NaN = undefined / diagonal)
-    double *q_vi = reinterpret_cast<double *>(t32 + Tcap);                                 // [Qcap] exact null value at the skipped column (quirk Q1)
+    unsigned int *cnt = reinterpret_cast<unsigned int *>(t32 + Tcap);                      // [Tcap] in-range null values below the statistic
+    unsigned int *queue = cnt + Tcap;                                                      // [kCrQueue] statistic << 13 | column in chunk
+    double *q_vi = reinterpret_cast<double *>(queue + kCrQueue);                           // [Qcap] exact null value at the skipped column (quirk Q1)
     long long *q_sc = reinterpret_cast<long long *>(q_vi + a.Qcap);                        // [Qcap] offset of the query's score row
     int *q_i = reinterpret_cast<int *>(q_sc + a.Qcap);                                     // [Qcap] hit position
     int *q_off = q_i + a.Qcap;                                                             // [Qcap] offset of the query's permutation in hit_rows
@@ -90,7 +98,8 @@ count_rows_kernel(RowCountArgs a) {
     __shared__ float s_min[kCrThreads / 32], s_max[kCrThreads / 32];
     __shared__ unsigned int s_warp[kCrThreads / 32];
     __shared__ float s_lo, s_scale;
-    __shared__ int s_any;
+    __shared__ int s_any, s_qn, s_ln;
+    __shared__ unsigned short longq[kCrLong];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     double *t64 = a.g_t64 + (long long)blockIdx.x * Tcap;
@@ -163,6 +172,7 @@ count_rows_kernel(RowCountArgs a) {
                     r = __ddiv_rn(0.25 * (double)sraw[e], __dmul_rn(sxu, sxc4[e]));
                     if (r != r) r = -99.0;                                  // coexfunctions.py:406-408
                 }
+                cnt[tt[e]] = 0;
                 if (r == -99.0) {                                           // diagonal, or 1-make-network.py:284-285
                     const long long w = q_sc[qq[e]] + jj[e];
                     a.scores[w] = (cc4[e] < 0) ? 0.0 : -log10(1.0);
@@ -187,6 +197,7 @@ count_rows_kernel(RowCountArgs a) {
             float mn = s_min[0], mx = s_max[0];
             for (int w = 1; w < kCrThreads / 32; ++w) { mn = fminf(mn, s_min[w]); mx = fmaxf(mx, s_max[w]); }
             s_any = (mn <= mx) ? 1 : 0;
+            s_qn = 0;
             // buckets 2 .. B-4 cover [min - pad, max + pad]; a range floor keeps the scale finite
             const float pad = 4.0f * kCrDelta;
             const float range = fmaxf(mx - mn, 1e-3f) + 2.0f * pad;
@@ -200,13 +211,11 @@ count_rows_kernel(RowCountArgs a) {
         const float blo = s_lo, bscale = s_scale;
         const float iu = (float)(0.5 / sxu);
         unsigned int n_below = 0;                           // values below every statistic of the item (bucket 0)
-        unsigned int cnt[KT];                               // in-range null values below statistic tid + k * 512
-#pragma unroll
-        for (int k = 0; k < KT; ++k) cnt[k] = 0;
         // ---- C. chunks of null values ----------------------------------------------------------------
         for (long long c0 = 0; c0 < N; c0 += kCrChunk) {
             const int clen = (int)((N - c0 < kCrChunk) ? (N - c0) : kCrChunk);
             for (int b = tid; b < kCrBuckets; b += kCrThreads) cum[b] = 0;
+            if (tid == 0) { s_qn = 0; s_ln = 0; }
             // strip row and column norms of the chunk: all loads issued before the first use
             constexpr int kIter = kCrChunk / (kCrThreads * 4);
             int4 s4[kIter];
@@ -271,28 +280,65 @@ count_rows_kernel(RowCountArgs a) {
                 }
             }
             __syncthreads();
-            // 4. every statistic against its bucket window
-#pragma unroll
-            for (int k = 0; k < KT; ++k) {
-                const int tt = tid + k * kCrThreads;
-                if (tt >= TP) continue;
-                const float t = t32[tt];
-                if (!(t == t)) continue;
-                const int bl = cr_bucket(t - kCrDelta, blo, bscale), bh = cr_bucket(t + kCrDelta, blo, bscale);
-                const unsigned int s = cum[bl > 0 ? bl - 1 : 0], e = cum[bh];   // 2 <= bl <= bh <= B-4 by construction
-                unsigned int less = s;
-                for (unsigned int m = s; m < e; ++m) {
-                    const int c = list[m];
-                    const float d = t - chunkv[c];
-                    if (d >= kCrDelta) {
-                        ++less;
-                    } else if (d > -kCrDelta) {                             // cannot be ordered in float: reference arithmetic
+            // 4. every statistic against its bucket window.  A value that cannot be ordered in float is NOT resolved
+            //    inline (one lane's double division and its two global loads would stall the other 31, and tied values
+            //    -- sparse rows share a few hundred identical correlations -- pile up on single statistics): the
+            //    (statistic, column) pair is queued and the whole CTA resolves the queue together.
+            auto scan_entry = [&](int tt, float t, float dl, unsigned int m) -> unsigned int {
+                const int c = list[m];
+                const float d = t - chunkv[c];
+                if (d >= dl) return 1u;
+                if (d > -dl) {                                              // cannot be ordered in float
+                    const int slot = atomicAdd(&s_qn, 1);
+                    if (slot < kCrQueue) {
+                        queue[slot] = ((unsigned int)tt << 13) | (unsigned int)c;
+                    } else {                                                // queue full: reference arithmetic in place
                         const long long col = c0 + c;
                         const double vv = __ddiv_rn(0.25 * (double)srow[col], __dmul_rn(sxu, a.sx[col]));
-                        less += (vv < t64[tt]) ? 1u : 0u;
+                        return (vv < t64[tt]) ? 1u : 0u;
                     }
                 }
-                cnt[k] += less;
+                return 0u;
+            };
+            for (int tt = tid; tt < TP; tt += kCrThreads) {
+                const float t = t32[tt];
+                if (!(t == t)) continue;
+                const float dl = cr_delta(t);
+                const int bl = cr_bucket(t - dl, blo, bscale), bh = cr_bucket(t + dl, blo, bscale);
+                const unsigned int s = cum[bl > 0 ? bl - 1 : 0], e = cum[bh];   // 2 <= bl <= bh <= B-4 by construction
+                unsigned int less = s;
+                if (e - s > (unsigned int)kCrInline) {
+                    // tied values (sparse rows share identical correlations) make a few windows hundreds of entries long:
+                    // those statistics are handed to whole warps so that one lane does not hold up the other 31
+                    const int slot = atomicAdd(&s_ln, 1);
+                    if (slot < kCrLong) { longq[slot] = (unsigned short)tt; cnt[tt] += less; continue; }
+                }
+                for (unsigned int m = s; m < e; ++m) less += scan_entry(tt, t, dl, m);
+                cnt[tt] += less;
+            }
+            __syncthreads();
+            {
+                const int ln = min(s_ln, kCrLong);
+                for (int x = wid; x < ln; x += kCrThreads / 32) {
+                    const int tt = longq[x];
+                    const float t = t32[tt];
+                    const float dl = cr_delta(t);
+                    const int bl = cr_bucket(t - dl, blo, bscale), bh = cr_bucket(t + dl, blo, bscale);
+                    const unsigned int s = cum[bl > 0 ? bl - 1 : 0], e = cum[bh];
+                    unsigned int less = 0;
+                    for (unsigned int m = s + lane; m < e; m += 32) less += scan_entry(tt, t, dl, m);
+                    less = __reduce_add_sync(0xffffffffu, less);
+                    if (lane == 0) cnt[tt] += less;
+                }
+            }
+            __syncthreads();
+            const int qn = min(s_qn, kCrQueue);
+            for (int x = tid; x < qn; x += kCrThreads) {
+                const unsigned int ent = queue[x];
+                const int tt = (int)(ent >> 13);
+                const long long col = c0 + (ent & 8191u);
+                const double vv = __ddiv_rn(0.25 * (double)srow[col], __dmul_rn(sxu, a.sx[col]));
+                if (vv < t64[tt]) atomicAdd(&cnt[tt], 1u);
             }
             __syncthreads();
         }
@@ -304,10 +350,7 @@ count_rows_kernel(RowCountArgs a) {
         __syncthreads();
         long long below = a.n_degenerate;                   // -99 < t always
         for (int w = 0; w < kCrThreads / 32; ++w) below += s_warp[w];
-#pragma unroll
-        for (int k = 0; k < KT; ++k) {
-            const int tt = tid + k * kCrThreads;
-            if (tt >= TP) continue;
+        for (int tt = tid; tt < TP; tt += kCrThreads) {
             const float tf = t32[tt];
             if (!(tf == tf)) continue;
             int lo = 0, hi = nq;
@@ -316,7 +359,7 @@ count_rows_kernel(RowCountArgs a) {
             const int i = q_i[lo];
             const double t = t64[tt];
             // all columns strictly below t, minus the skipped column i of this query if it is below t (quirk Q1)
-            long long idx = (long long)cnt[k] + below;
+            long long idx = (long long)cnt[tt] + below;
             long long len = N;
             if (i < N) { len = N - 1; if (q_vi[lo] < t) idx -= 1; }
             const long long w = q_sc[lo] + j;
