@@ -4,7 +4,7 @@ the reference does per pair in Python / scipy is NOT here -- it runs on the GPU 
 coexpression_b200.api.  Nothing in this module imports the oracle.
 
   readsettings ............ coexfunctions.py:49-74   settings.txt -> dict (float / bool coercion)
-  read_expression_file .... coexfunctions.py:201-233 (drop NA columns, first duplicate label wins)
+  read_expression_file .... coexfunctions.py:201-233 (drop NA columns, first duplicate label wins; optional binary cache, row N4)
   readfeaturecoordinates .. coexfunctions.py:235-274
   read_correlation_list ... 1-make-network.py:76-79
   read_snp_map ............ 1-make-network.py:131-177
@@ -73,16 +73,66 @@ class ExpressionTable:
         return list(self.values[self.index[key]])
 
 
-def read_expression_file(filename):
+def _expression_cache_key(filename):
+    """Identity of the text table for the binary cache: size, mtime and a hash of its first and last MiB."""
+    import hashlib
+    st = os.stat(filename)
+    h = hashlib.sha256()
+    h.update(("%d:%d:" % (st.st_size, st.st_mtime_ns)).encode())
+    with open(filename, "rb") as f:
+        h.update(f.read(1 << 20))
+        if st.st_size > (2 << 20):
+            f.seek(st.st_size - (1 << 20))
+            h.update(f.read(1 << 20))
+    return h.hexdigest()
+
+
+def read_expression_file(filename, cache=False):
     """Header row + label column, whitespace separated; columns with any NA are dropped and of
-    duplicated labels the first occurrence is kept (coexfunctions.py:217-231)."""
+    duplicated labels the first occurrence is kept (coexfunctions.py:217-231).
+
+    Row N4: every reference process re-parses the ~3 GB text table with pandas
+    (coexfunctions.py:217).  With cache=True the parsed result (AFTER the NA-column and duplicate-label
+    rules, so the semantics cannot drift) is kept next to the table as `<file>.b200cache/` -- float64
+    row-major `values.npy` opened memory-mapped, labels, header, and the identity key of the text file
+    (size, mtime, hash of the first and last MiB); a stale or foreign cache is ignored and rewritten."""
+    cdir = filename + ".b200cache"
+    key = None
+    if cache:
+        key = _expression_cache_key(filename)
+        try:
+            with open(os.path.join(cdir, "key.json")) as f:
+                meta = json.load(f)
+            if meta.get("key") == key and meta.get("format") == 1:
+                values = np.load(os.path.join(cdir, "values.npy"), mmap_mode="r")
+                with open(os.path.join(cdir, "names.txt")) as f:
+                    names = f.read().split("\n")[:-1]
+                with open(os.path.join(cdir, "header.txt")) as f:
+                    header = f.read().split("\n")[:-1]
+                if values.shape == (len(names), len(header)) and values.dtype == np.float64:
+                    return ExpressionTable(names, values, header), header
+        except (OSError, ValueError, KeyError):
+            pass
     import pandas as pd
     df = pd.read_table(filename, header=0)
     label_col = df.columns[0]
     df = df.dropna(axis=1)
     df = df.drop_duplicates(subset=label_col)
     df = df.set_index(label_col)
-    return ExpressionTable(list(df.index), df.values, list(df.columns.values)), list(df.columns.values)
+    table = ExpressionTable(list(df.index), df.values, list(df.columns.values))
+    if cache:
+        try:
+            os.makedirs(cdir, exist_ok=True)
+            np.save(os.path.join(cdir, "values.npy"), table.values)
+            with open(os.path.join(cdir, "names.txt"), "w") as f:
+                f.write("".join(str(nm) + "\n" for nm in table.names))
+            with open(os.path.join(cdir, "header.txt"), "w") as f:
+                f.write("".join(str(h) + "\n" for h in table.header))
+            with open(os.path.join(cdir, "key.json"), "w") as f:       # written last: a torn cache has no key
+                json.dump({"key": key, "format": 1, "rows": len(table.names), "samples": len(table.header)}, f)
+        except OSError:
+            pass                                                       # read-only source directory: no cache
+    return table, list(df.columns.values)
 
 
 def readfeaturecoordinates(featfile):

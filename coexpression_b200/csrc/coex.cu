@@ -146,7 +146,7 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     Qcap = (Qcap + 1) & ~1;
     COEX_TRY(c->dd_items.reserve(std::max<size_t>(items.size(), 1) * sizeof(DedupItem)));
     COEX_CUDA(cudaMemcpyAsync(c->dd_items.p, items.data(), items.size() * sizeof(DedupItem), cudaMemcpyHostToDevice, st));
-    const int bm_words = (N <= 262144) ? (int)((N + 31) / 32) : 0;     // hit-column bitmap (<= 32 KB)
+    const int bm_words = (N <= 262144) ? (int)((N + 31) / 32) : 0;     // hit-column bitmap (<= 32 KB: two CTAs per SM stay resident)
     if (tdbg) fprintf(stderr, "[coex host] dedupe plan: %.0f us (H=%lld U=%lld items=%zu)\n", now_us() - t_start, H, U, items.size());
     const size_t smem = rows_kernel ? rows_smem_bytes(Tcap, Qcap) : dedup_smem_bytes(Tcap, Qcap, bm_words);
     if (smem > 227 * 1024) COEX_FAIL("count kernel: too many queries of one table row for shared memory");

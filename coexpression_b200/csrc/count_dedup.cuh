@@ -27,7 +27,14 @@ namespace coex {
 constexpr int kDdThreads = 512;
 constexpr int kDdBuckets = 8192;
 constexpr int kDdQueue = 2048;
-constexpr float kDdDelta = 5e-7f;        // |v32 - v64| <= 3e-7, |t32 - t64| <= 6e-8  
+constexpr float kDdDelta = 5e-7f;        // |v32 - v64| <= 3e-7 |v|, |t32 - t64| <= 6e-8 |t|  
+constexpr int kDdSuper = 32768;          // columns streamed between two drains of the refinement queue (multiple of 4 * kDdThreads)
+
+// The float errors are RELATIVE (int -> float, two rounded reciprocal half-norms, two products: 5 * 2^-24 |v|; the
+// statistic is one rounding of its double: 2^-24 |t|).  If |t| < 1.13 |v| they add up to < 3.7e-7 |v|, otherwise
+// |t - v| > 0.1 |v| dwarfs them: a float difference of at least 5e-7 |v| decides the order.  The floor keeps exact
+// ties at zero out of the "certain" branch.
+__device__ __forceinline__ float dd_delta(float v) { return fmaxf(kDdDelta * fabsf(v), 1e-30f); }
 
 struct DedupItem {
     int urow;        // index into the strip (unique-row slot)
@@ -85,7 +92,7 @@ count_dedup_kernel(DedupArgs a) {
     int *q_off = q_i + a.Qcap;                   // [Qcap] offset of the query's permutation in hit_rows
     int *q_P = q_off + a.Qcap;                   // [Qcap] hits of that permutation
     int *q_toff = q_P + a.Qcap;                  // [Qcap+2] offset of the query's statistics in the item
-    unsigned int *bitmap = reinterpret_cast<unsigned int *>(q_toff + a.Qcap + 2);   // [2*bm_words] hit columns of this item: skip mask | claim mask
+    unsigned int *bitmap = reinterpret_cast<unsigned int *>(q_toff + a.Qcap + 2);   // [bm_words] hit columns of this item (skipped by the streaming pass)
     __shared__ int s_T, s_qn;
     __shared__ unsigned int s_warp[kDdThreads / 32];
 
@@ -129,7 +136,7 @@ count_dedup_kernel(DedupArgs a) {
         }
         if (tid == 0) { s_T = 0; s_qn = 0; }
         for (int b = tid; b <= kDdBuckets; b += kDdThreads) lut[b] = 0;
-        for (int wd = tid; wd < 2 * a.bm_words; wd += kDdThreads) bitmap[wd] = 0;       // skip mask | claim mask
+        for (int wd = tid; wd < a.bm_words; wd += kDdThreads) bitmap[wd] = 0;
         __syncthreads();
         if (tid == 0) {
             int acc = 0;
@@ -179,11 +186,7 @@ count_dedup_kernel(DedupArgs a) {
                     atomicAdd(&lut[dd_bucket64(r, a.R, bscale)], 1u);
                     // the null value of a hit column IS this statistic (same arithmetic): it is accounted
                     // exactly in step C' and skipped by the float streaming pass
-                    if (a.bm_words) {
-                        const unsigned int bit = 1u << (cc4[e] & 31);
-                        atomicOr(&bitmap[cc4[e] >> 5], bit);
-                        atomicOr(&bitmap[a.bm_words + (cc4[e] >> 5)], bit);
-                    }
+                    if (a.bm_words) atomicOr(&bitmap[cc4[e] >> 5], 1u << (cc4[e] & 31));
                 }
             }
         }
@@ -247,15 +250,19 @@ count_dedup_kernel(DedupArgs a) {
         }
         for (int p = tid; p <= T; p += kDdThreads) hist[p] = 0;
         __syncthreads();
-        // ---- C'. hit columns: value == statistic exactly; the first statistic to claim a column adds it
+        // ---- C'. hit columns: value == statistic exactly.  A column hit by several queries of the item appears as
+        // several EQUAL statistics (same row, same column, same arithmetic): the first of them in sorted order adds it.
         if (a.bm_words) {
             for (int sidx = tid; sidx < T; sidx += kDdThreads) {
                 const int c = col[sidx];
-                const unsigned int bit = 1u << (c & 31);
-                if (atomicAnd(&bitmap[a.bm_words + (c >> 5)], ~bit) & bit) {
-                    const double t = thr64[sidx];
+                const double t = thr64[sidx];
+                const float tf = thr32[sidx];                         // shared-memory filter in front of the L2-resident doubles
+                bool first = true;
+                for (int e1 = sidx - 1; e1 >= 0 && thr32[e1] == tf && thr64[e1] == t; --e1)
+                    if (col[e1] == c) { first = false; break; }
+                if (first) {
                     int e2 = sidx + 1;
-                    while (e2 < T && thr64[e2] == t) ++e2;            // statistics <= value: through the run of equals
+                    while (e2 < T && thr32[e2] == tf && thr64[e2] == t) ++e2;   // statistics <= value: through the run of equals
                     atomicAdd(&hist[e2], 1u);
                 }
             }
@@ -267,9 +274,14 @@ count_dedup_kernel(DedupArgs a) {
         const long long N = a.N;
         // Four columns per thread are handled in lockstep (independent shared-memory chains overlap)
         // and the next 16-byte strip / norm loads are issued before the current ones are consumed.
-        {
-            long long c0 = (long long)tid * 4;
-            bool have = c0 < N;
+        // The row is streamed in super-chunks of kDdSuper columns; the queue of columns that need the reference's
+        // double arithmetic is drained by the whole CTA after each of them (a long row of a zero-inflated table holds
+        // thousands of values TIED with a statistic, far more than one queue; refining them in place -- one lane's
+        // double division at a time -- is what it used to cost).
+        for (long long cb = 0; cb < N; cb += kDdSuper) {
+            const long long cend = (cb + kDdSuper < N) ? cb + kDdSuper : N;
+            long long c0 = cb + (long long)tid * 4;
+            bool have = c0 < cend;
             int4 s4n = make_int4(0, 0, 0, 0);
             float4 w4n = make_float4(0.f, 0.f, 0.f, 0.f);
             if (have) { s4n = *reinterpret_cast<const int4 *>(srow + c0); w4n = *reinterpret_cast<const float4 *>(a.icol + c0); }
@@ -279,7 +291,7 @@ count_dedup_kernel(DedupArgs a) {
                 const long long cc = c0;
                 const unsigned int skip4 = a.bm_words ? (bitmap[cc >> 5] >> (cc & 31)) & 15u : 0u;   // cc % 4 == 0
                 c0 += kDdThreads * 4;
-                have = c0 < N;
+                have = c0 < cend;
                 if (have) { s4n = *reinterpret_cast<const int4 *>(srow + c0); w4n = *reinterpret_cast<const float4 *>(a.icol + c0); }
                 float v[4];
                 int p[4], lo[4], hi[4], len[4];
@@ -314,7 +326,7 @@ count_dedup_kernel(DedupArgs a) {
                     // are at least a whole bucket away)
                     const float below = (p[e] > lo[e]) ? v[e] - thr32[p[e] - 1] : 1.0f;
                     const float above = (p[e] < hi[e]) ? thr32[p[e]] - v[e] : 1.0f;
-                    if (fminf(below, above) >= kDdDelta) {
+                    if (fminf(below, above) >= dd_delta(v[e])) {
                         atomicAdd(&hist[p[e]], 1u);
                     } else {
                         const int slot = atomicAdd(&s_qn, 1);
@@ -334,24 +346,27 @@ count_dedup_kernel(DedupArgs a) {
                     }
                 }
             }
-        }
-        __syncthreads();
-        DD_PHASE(3);
-        // ---- E. exact refinement of the queued columns ------------------------------------------
-        const int qn = min(s_qn, kDdQueue);
-        for (int x = tid; x < qn; x += kDdThreads) {
-            const int c = queue[x];
-            const double vv = __ddiv_rn(0.25 * (double)srow[c], __dmul_rn(sxu, a.sx[c]));
-            const int bb = dd_bucket64(vv, a.R, bscale);
-            int pp = (int)lut[bb];
-            int len = (int)lut[bb + 1] - pp;
-            while (len > 0) {
-                const int half = len >> 1;
-                if (thr64[pp + half] <= vv) { pp += half + 1; len -= half + 1; } else len = half;
+            __syncthreads();
+            // ---- E. exact refinement of the queued columns ------------------------------------------
+            const int qn = min(s_qn, kDdQueue);
+            for (int x = tid; x < qn; x += kDdThreads) {
+                const int c = queue[x];
+                const double vv = __ddiv_rn(0.25 * (double)srow[c], __dmul_rn(sxu, a.sx[c]));
+                const int bb = dd_bucket64(vv, a.R, bscale);
+                int pp = (int)lut[bb];
+                int len = (int)lut[bb + 1] - pp;
+                while (len > 0) {
+                    const int half = len >> 1;
+                    if (thr64[pp + half] <= vv) { pp += half + 1; len -= half + 1; } else len = half;
+                }
+                atomicAdd(&hist[pp], 1u);
             }
-            atomicAdd(&hist[pp], 1u);
+            if (a.phase_clk && tid == 0) atomicAdd(&a.phase_clk[7], (unsigned long long)s_qn);
+            __syncthreads();
+            if (tid == 0) s_qn = 0;
+            __syncthreads();
         }
-        __syncthreads();
+        DD_PHASE(3);
         DD_PHASE(4);
         // ---- F. inclusive prefix sum of hist[0..T), scores ----------------------------------------
         {
@@ -384,7 +399,7 @@ count_dedup_kernel(DedupArgs a) {
             if (a.counts) a.counts[w] = idx;
         }
         DD_PHASE(5);
-        if (a.phase_clk && tid == 0) { atomicAdd(&a.phase_clk[6], 1ULL); atomicAdd(&a.phase_clk[7], (unsigned long long)s_qn); }
+        if (a.phase_clk && tid == 0) atomicAdd(&a.phase_clk[6], 1ULL);
     }
 }
 
@@ -411,7 +426,7 @@ __global__ void icol_kernel(const double *__restrict__ sx, long long N, long lon
 
 inline size_t dedup_smem_bytes(int Tcap, int Qcap, int bm_words) {
     return (size_t)Qcap * 8 + (size_t)Tcap * 4 + (size_t)(Tcap + 4) * 4 + (size_t)(kDdBuckets + 4) * 4 +
-           (size_t)kDdQueue * 4 + (size_t)Qcap * 8 + (size_t)Qcap * 4 * 3 + (size_t)(Qcap + 2) * 4 + (size_t)bm_words * 8 + 16;
+           (size_t)kDdQueue * 4 + (size_t)Qcap * 8 + (size_t)Qcap * 4 * 3 + (size_t)(Qcap + 2) * 4 + (size_t)bm_words * 4 + 16;
 }
 
 }  // namespace coex
