@@ -68,8 +68,8 @@ static int prepare_impl(coex_ctx *c) {
     icol_kernel<<<(unsigned)((c->N_pad + 255) / 256), 256, 0, c->stream>>>(c->sx.p, N, c->N_pad, c->icol.p, c->d_ndeg.p);
     COEX_CUDA(cudaGetLastError());
     c->launches += 1;
-    COEX_CUDA(cudaMemcpyAsync(&c->n_degenerate, c->d_ndeg.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    COEX_CUDA(cudaStreamSynchronize(c->stream));
+    // no synchronisation here: the count of zero-variance rows stays on the device (the count kernels read it there),
+    // so the host can plan the next call while the rank transform is still running
     COEX_TRY(tc_invalidate(c));
     c->prepared = true;
     return 0;
@@ -89,26 +89,31 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     auto now_us = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
     const double t_start = now_us();
     // ---- counting sort of the queries by table row (host, O(N + H)) -------------------------------
-    std::vector<int> cnt((size_t)N + 1, 0);
+    // scratch reused across calls (no allocation or page faults in the steady state)
+    static thread_local std::vector<int> cnt, uniq, ustart, cursor, qlist, Pq;
+    cnt.assign((size_t)N + 1, 0);
     for (long long q = 0; q < H; ++q) {
         const int r = h_hits[q];
         if (r < 0 || r >= N) COEX_FAIL("hit row out of range");
         cnt[(size_t)r + 1]++;
     }
-    std::vector<int> uniq; uniq.reserve((size_t)std::min<long long>(H, N));
-    std::vector<int> ustart;                         // start of each unique row's queries in qlist
-    std::vector<int> cursor((size_t)N, -1);
+    uniq.clear(); ustart.clear();                    // ustart: start of each unique row's queries in qlist
+    cursor.resize((size_t)N);
     int acc = 0;
-    for (long long r = 0; r < N; ++r)
-        if (cnt[(size_t)r + 1]) { cursor[(size_t)r] = acc; ustart.push_back(acc); uniq.push_back((int)r); acc += cnt[(size_t)r + 1]; }
+    for (long long r = 0; r < N; ++r) {
+        const int cr = cnt[(size_t)r + 1];
+        if (cr) { cursor[(size_t)r] = acc; ustart.push_back(acc); uniq.push_back((int)r); acc += cr; }
+    }
     ustart.push_back(acc);
-    std::vector<int> qlist((size_t)H);
-    std::vector<int> Pq((size_t)H);
-    for (int k = 0; k < K; ++k)
+    qlist.resize((size_t)H);
+    Pq.resize((size_t)H);
+    for (int k = 0; k < K; ++k) {
+        const int Pk = (int)(perm_off[k + 1] - perm_off[k]);
         for (long long q = perm_off[k]; q < perm_off[k + 1]; ++q) {
             qlist[(size_t)cursor[(size_t)h_hits[q]]++] = (int)q;
-            Pq[(size_t)q] = (int)(perm_off[k + 1] - perm_off[k]);
+            Pq[(size_t)q] = Pk;
         }
+    }
     const long long U = (long long)uniq.size();
     const bool rows_kernel = (c->count_mode == 2);
     const int Tcap = rows_kernel ? std::max(4096, (int)round_up(Pmax, 512))
@@ -124,8 +129,9 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     COEX_CUDA(cudaMemcpyAsync(c->dd_uniq.p, uniq.data(), U * sizeof(int), cudaMemcpyHostToDevice, st));
     COEX_CUDA(cudaMemcpyAsync(c->dd_qlist.p, qlist.data(), H * sizeof(int), cudaMemcpyHostToDevice, st));
     // ---- work items: (unique row, run of its queries whose statistics fit Tcap) -------------------------
-    std::vector<DedupItem> items;
-    std::vector<long long> strip_item_begin;
+    static thread_local std::vector<DedupItem> items;
+    static thread_local std::vector<long long> strip_item_begin;
+    items.clear(); strip_item_begin.clear();
     int Qcap = 2;
     for (long long u0 = 0; u0 < U; u0 += Us) {
         strip_item_begin.push_back((long long)items.size());
@@ -186,7 +192,7 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
         da.uniq_rows = c->dd_uniq.p + u0; da.qlist = c->dd_qlist.p;
         da.perm_off = c->d_perm_off.p; da.sc_off = c->d_sc_off.p; da.K = K; da.hit_rows = d_hits;
         da.sx = c->sx.p; da.icol = c->icol.p; da.rawsum_pos = c->rawsum_pos.p; da.N = N;
-        da.n_degenerate = c->n_degenerate; da.anticor = prm->anticorrelation; da.scores = d_sc; da.counts = d_cn;
+        da.n_degenerate = c->d_ndeg.p; da.anticor = prm->anticorrelation; da.scores = d_sc; da.counts = d_cn;
         da.Tcap = Tcap; da.Qcap = Qcap;
         da.bm_words = bm_words;
         da.R = std::min(1.0, std::max(0.05, 8.0 / std::sqrt((double)std::max(c->n, 2)))); da.g_thr = c->dd_gthr.p; da.g_org = c->dd_gorg.p; da.score_tab = c->dd_tab.p; da.phase_clk = dbg ? phase.p : nullptr;
@@ -271,7 +277,7 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
     const long long SC = sc_off[K];
     if (prm->measure == 0 && prm->use_specific_p && c->n > 1860)
         COEX_FAIL("Spearman tensor path supports up to 1860 samples (int32 dot products)");
-    stage_reset(c);
+    stage_reset_from(c, ST_GATHER);
     cudaStream_t st = c->stream;
 
     // ---- buffers ----------------------------------------------------------------------------

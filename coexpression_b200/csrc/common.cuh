@@ -136,7 +136,6 @@ struct coex_ctx {
     coex::DevBuf<unsigned long long> w_best, w_cand;
     coex::DevBuf<float> icol;                 // [N_pad] (float)(0.5/sx), 0 for zero-variance rows
     coex::DevBuf<int> d_ndeg;                 // [1]
-    int n_degenerate = 0;
     coex::DevBuf<int> dd_uniq, dd_qlist, dd_qperm;   // de-duplicated query rows; permutation of every flat hit index
     coex::DevBuf<unsigned char> dd_items;     // DedupItem[]
     coex::DevBuf<double> dd_gthr, dd_tab;
@@ -182,6 +181,23 @@ inline void stage_reset(coex_ctx *c) {
     }
     c->spans.clear();
     for (int i = 0; i < kNumStages; ++i) {
+        c->stage_ms[i] = 0;
+        c->stage_launches[i] = 0;
+    }
+}
+// forget the spans and totals of stages >= first (a batch call keeps the spans of a prepare that nobody collected yet)
+inline void stage_reset_from(coex_ctx *c, int first) {
+    std::vector<StageSpan> keep;
+    for (auto &s : c->spans) {
+        if (s.stage >= first) {
+            cudaEventDestroy(s.a);
+            cudaEventDestroy(s.b);
+        } else {
+            keep.push_back(s);
+        }
+    }
+    c->spans.swap(keep);
+    for (int i = first; i < kNumStages; ++i) {
         c->stage_ms[i] = 0;
         c->stage_launches[i] = 0;
     }

@@ -56,7 +56,7 @@ struct DedupArgs {
     const float *icol;              // [N_pad] (float)(0.5 / sx), 0 for zero-variance / padding rows
     const unsigned char *rawsum_pos;
     long long N;
-    int n_degenerate;               // zero-variance table rows: their null value is -99 for every query
+    const int *n_degenerate;        // [1] device: zero-variance table rows, their null value is -99 for every query
     int anticor;
     double *scores;
     long long *counts;
@@ -107,6 +107,7 @@ count_dedup_kernel(DedupArgs a) {
     int *tmp_c = reinterpret_cast<int *>(org + a.Tcap);              // column of flat index t
     int *g_col = tmp_c + a.Tcap, *col = g_col + a.Tcap;              // grouped / sorted columns
 
+    const int n_deg = *a.n_degenerate;
     for (int it = blockIdx.x; it < a.n_items; it += gridDim.x) {
         const DedupItem item = a.items[it];
         const int nq = item.qe - item.qb;
@@ -391,7 +392,7 @@ count_dedup_kernel(DedupArgs a) {
             const double t = thr64[s];
             // all columns strictly below t: streamed values + zero-variance columns (-99 < t always),
             // minus the skipped column i of this query if it is below t (quirk Q1)
-            long long idx = (long long)hist[s] + a.n_degenerate;
+            long long idx = (long long)hist[s] + n_deg;
             long long len = N;
             if (i < N) { len = N - 1; if (q_vi[ql] < t) idx -= 1; }
             const long long w = q_sc[ql] + j;

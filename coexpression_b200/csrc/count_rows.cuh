@@ -53,7 +53,7 @@ struct RowCountArgs {
     const float *icol;              // [N_pad] (float)(0.5 / sx), 0 for zero-variance / padding rows
     const unsigned char *rawsum_pos;
     long long N;
-    int n_degenerate;               // zero-variance table rows: their null value is -99 for every query
+    const int *n_degenerate;        // [1] device: zero-variance table rows, their null value is -99 for every query
     int anticor;
     double *scores;
     long long *counts;
@@ -348,7 +348,7 @@ count_rows_kernel(RowCountArgs a) {
         for (int o = 16; o > 0; o >>= 1) n_below += __shfl_xor_sync(0xffffffffu, n_below, o);
         if (lane == 0) s_warp[wid] = n_below;
         __syncthreads();
-        long long below = a.n_degenerate;                   // -99 < t always
+        long long below = *a.n_degenerate;                  // -99 < t always
         for (int w = 0; w < kCrThreads / 32; ++w) below += s_warp[w];
         for (int tt = tid; tt < TP; tt += kCrThreads) {
             const float tf = t32[tt];

@@ -46,11 +46,12 @@ def result_path(store, mapfile, label):
 class Session:
     """Expression table resident on one GPU + everything a permutation needs besides its hits."""
 
-    def __init__(self, settings, device=0, verbose=False):
+    def __init__(self, settings, device=0, verbose=False, cache=False):
         self.settings = settings
         self.verbose = verbose
         self.options = options_from_settings(settings)
-        self.table, self.header = read_expression_file(settings["expression_file"])
+        # cache=True: binary cache of the parsed table next to the text file (row N4, coexfunctions.read_expression_file)
+        self.table, self.header = read_expression_file(settings["expression_file"], cache=cache)
         addresses, _, _ = readfeaturecoordinates(settings["feature_coordinates"])
         self.addresses = addresses
         glist = read_correlation_list(settings["correlationfile"])
@@ -103,13 +104,13 @@ class Session:
         return written
 
 
-def run_batch(working_files_dir, mapfiles=None, device=0, verbose=False, full_dump=True):
+def run_batch(working_files_dir, mapfiles=None, device=0, verbose=False, full_dump=True, cache=False):
     settings = readsettings(working_files_dir)
     perm_dir = os.path.join(working_files_dir, "permutation_store")
     if mapfiles is None:
         mapfiles = sorted((os.path.join(perm_dir, f) for f in os.listdir(perm_dir) if f.endswith(".bed")),
                           key=lambda p: int(p.split(".")[-2]))
-    sess = Session(settings, device, verbose)
+    sess = Session(settings, device, verbose, cache)
     try:
         return sess.run(mapfiles, os.path.join(working_files_dir, "perm_results_store"), full_dump)
     finally:
@@ -125,13 +126,15 @@ def main(argv=None):
                     help="accepted; the reference crashes on it (Q11) so nothing is recorded")
     ap.add_argument("--all", action="store_true", help="B200 extension: reduce every map file of permutation_store/")
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--cache", action="store_true", default=bool(os.environ.get("COEX_TABLE_CACHE")),
+                    help="B200 extension: keep a binary cache of the parsed expression table next to the text file")
     args = ap.parse_args(argv)
     settings = readsettings(args.working_files_dir)
     verbose = bool(settings.get("verbose", False))
     if args.all:
-        run_batch(args.working_files_dir, None, args.device, verbose)
+        run_batch(args.working_files_dir, None, args.device, verbose, cache=args.cache)
     else:
-        run_batch(args.working_files_dir, [args.mapfile], args.device, verbose)
+        run_batch(args.working_files_dir, [args.mapfile], args.device, verbose, cache=args.cache)
     return 0
 
 

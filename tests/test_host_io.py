@@ -28,6 +28,37 @@ def test_expression_reader_semantics(tmp_path):
     assert table[t.names[5]] == list(t.X[5]) and t.names[7] in table and "nope" not in table
 
 
+def test_expression_binary_cache_row_n4(tmp_path):
+    """Row N4: the cached table equals the parsed one bit for bit (same NA-column / duplicate-label rules), is
+    memory-mapped on the second read, and is rebuilt when the text file changes."""
+    t = synth.make_table(50, 7, seed=4)
+    path = tmp_path / "y.expression"
+    synth.write_expression_file(path, t)
+    lines = open(path).read().splitlines()
+    lines[0] += "\tbad"
+    for k in range(1, len(lines)):
+        lines[k] += "\t2.5" if k != 4 else "\tNA"
+    lines.append(lines[2].split("\t")[0] + "\t" + "\t".join(["7.0"] * 8))
+    open(path, "w").write("\n".join(lines) + "\n")
+    plain, h0 = read_expression_file(str(path))
+    first, h1 = read_expression_file(str(path), cache=True)          # parses and writes <file>.b200cache/
+    assert os.path.exists(str(path) + ".b200cache/key.json")
+    second, h2 = read_expression_file(str(path), cache=True)         # served from the cache
+    assert isinstance(second.values, np.memmap) or isinstance(second.values.base, np.memmap)
+    for tab, hd in ((first, h1), (second, h2)):
+        assert tab.names == plain.names and hd == h0 and tab.header == plain.header
+        assert tab.values.dtype == np.float64 and np.array_equal(np.asarray(tab.values), plain.values)
+        assert tab.index == plain.index
+    # a changed text file invalidates the cache
+    lines[1] = lines[1].split("\t")[0] + "\t" + "\t".join(["3.25"] * 8)
+    open(path, "w").write("\n".join(lines) + "\n")
+    os.utime(path, ns=(1, 1))                                         # even with an old mtime the size/hash key differs
+    third, _ = read_expression_file(str(path), cache=True)
+    assert np.all(np.asarray(third.values)[0] == 3.25)
+    fourth, _ = read_expression_file(str(path), cache=True)
+    assert np.array_equal(np.asarray(fourth.values), np.asarray(third.values))
+
+
 def test_feature_reader_and_map_reader(tmp_path):
     t = synth.make_table(60, 4, seed=3)
     bed = tmp_path / "f.bed"
