@@ -93,6 +93,7 @@ class CoexContext:
         self.h = h
         self.N = self.n = 0
         self._keep = []
+        self._feature_chroms = None
 
     def close(self):
         if self.h:
@@ -139,11 +140,48 @@ class CoexContext:
         (pandas sort on 'chromosome', coexfunctions.py:288; sorted(names), :314)."""
         chrom = np.asarray(chrom)
         uniq, chrom_id = np.unique(chrom, return_inverse=True)          # np.unique sorts
+        self._feature_chroms = [str(u) for u in uniq]
         order = np.argsort(np.asarray(names), kind="stable")
         name_rank = np.empty(len(names), dtype=np.int32)
         name_rank[order] = np.arange(len(names), dtype=np.int32)
         self.set_features_raw(chrom_id.astype(np.int32), np.asarray(start, dtype=np.int64),
                               np.asarray(end, dtype=np.int64), name_rank)
+
+    def permute_map(self, mode, snp_chrom, snp_addr, shifts, chromlist, chromrange, window, background=None,
+                    capacity=None):
+        """Row N1: the promoters of K permuted locus sets in one call (reference 0-prepare-coex.py:471-613 + windowBed).
+        snp_chrom: chromosome names of the real loci, snp_addr their addresses; shifts[k] == 0 is the real data;
+        chromlist / chromrange as built at 0-prepare-coex.py:319-330.  mode 'backcirc' needs `background` = the
+        list of (chrom, address) sorted by (genome-wide address, key) (0-prepare-coex.py:582), which must contain
+        every real locus.  -> list of K int32 arrays of table rows (first-appearance order)."""
+        if self._feature_chroms is None:
+            raise _lib.CoexError("permute_map: call set_features first")
+        cidx = {c: i for i, c in enumerate(chromlist)}
+        fid = {c: i for i, c in enumerate(self._feature_chroms)}
+        sc = np.ascontiguousarray([cidx[c] for c in snp_chrom], dtype=np.int32)
+        sa = np.ascontiguousarray(snp_addr, dtype=np.int64)
+        sh = np.ascontiguousarray(shifts, dtype=np.int64)
+        cs = np.ascontiguousarray([chromrange[c][0] for c in chromlist], dtype=np.int64)
+        ce = np.ascontiguousarray([chromrange[c][1] for c in chromlist], dtype=np.int64)
+        cf = np.ascontiguousarray([fid.get(c, -1) for c in chromlist], dtype=np.int32)
+        m = {"circular": 0, "backcirc": 1}[mode]
+        sb = bc = ba = None
+        nb = 0
+        if m == 1:
+            pos = {(c, int(a)): i for i, (c, a) in enumerate(background)}
+            sb = np.ascontiguousarray([pos[(c, int(a))] for c, a in zip(snp_chrom, snp_addr)], dtype=np.int64)
+            bc = np.ascontiguousarray([cidx[c] for c, _ in background], dtype=np.int32)
+            ba = np.ascontiguousarray([a for _, a in background], dtype=np.int64)
+            nb = len(background)
+        K, M = len(sh), len(sc)
+        cap = int(capacity if capacity is not None else max(1024, 64 * K * M))
+        off = np.zeros(K + 1, dtype=np.int64)
+        rows = np.zeros(cap, dtype=np.int32)
+        ptr = lambda x: x.ctypes.data if x is not None else None
+        check(self.lib.coex_permute_map(self.h, m, ptr(sc), ptr(sa), ptr(sb), M, ptr(sh), K, ptr(cs), ptr(ce), ptr(cf),
+                                        len(chromlist), ptr(bc), ptr(ba), nb, int(window), ptr(off), ptr(rows), cap, 0),
+              "coex_permute_map")
+        return [rows[off[k]:off[k + 1]].copy() for k in range(K)]
 
     def set_features_raw(self, chrom_id, start, end, name_rank):
         chrom_id = np.ascontiguousarray(chrom_id, dtype=np.int32)

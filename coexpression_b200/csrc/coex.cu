@@ -11,6 +11,7 @@
 #include "count_rows.cuh"
 #include "network.cuh"
 #include "allpairs.cuh"
+#include "permute.cuh"
 
 #include <algorithm>
 #include <ctime>
@@ -594,6 +595,7 @@ int coex_destroy(coex_ctx *c) {
     c->raw_own.release(); c->raw_sum.release(); c->raw_mean.release(); c->raw_xx.release(); c->rawsum_pos.release();
     c->rank2.release(); c->u_hi.release(); c->u_lo.release(); c->suu.release(); c->sx.release();
     c->z_planes.release(); c->z_ok.release(); c->z_l1.release(); c->z_inv_s.release();
+    c->feat_key.release(); c->feat_row.release(); c->pm_blob.release(); c->pm_counts.release(); c->pm_hits_tmp.release(); c->pm_off.release();
     c->chrom_id.release(); c->name_rank.release(); c->feat_start.release(); c->feat_end.release(); c->glist.release();
     c->a_hi.release(); c->a_lo.release(); c->strip.release(); c->strip_f64.release();
     c->d_perm_off.release(); c->d_sc_off.release(); c->d_warp_off.release(); c->d_hits.release(); c->d_ngroups.release(); c->d_grp.release();
@@ -662,8 +664,121 @@ int coex_set_features(coex_ctx *c, const int *chrom_id, const long long *start, 
     COEX_CUDA(cudaMemcpyAsync(c->name_rank.p, name_rank, N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     COEX_CUDA(cudaMemcpyAsync(c->feat_start.p, start, N * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
     COEX_CUDA(cudaMemcpyAsync(c->feat_end.p, end, N * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    {   // index for the locus -> promoter join: rows ordered by (chromosome id, start, row)
+        std::vector<std::pair<unsigned long long, int>> order((size_t)N);
+        long long maxlen = 0;
+        for (long long i = 0; i < N; ++i) {
+            order[(size_t)i] = {((unsigned long long)chrom_id[i] << 40) | (unsigned long long)start[i], (int)i};
+            maxlen = std::max(maxlen, end[i] - start[i]);
+        }
+        std::sort(order.begin(), order.end());
+        std::vector<unsigned long long> keys((size_t)N);
+        std::vector<int> rows((size_t)N);
+        for (long long i = 0; i < N; ++i) { keys[(size_t)i] = order[(size_t)i].first; rows[(size_t)i] = order[(size_t)i].second; }
+        COEX_TRY(c->feat_key.reserve(N)); COEX_TRY(c->feat_row.reserve(N));
+        COEX_CUDA(cudaMemcpyAsync(c->feat_key.p, keys.data(), N * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+        COEX_CUDA(cudaMemcpyAsync(c->feat_row.p, rows.data(), N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        c->feat_maxlen = maxlen;
+        COEX_CUDA(cudaStreamSynchronize(c->stream));
+    }
     COEX_CUDA(cudaStreamSynchronize(c->stream));
     c->have_features = true;
+    return 0;
+}
+
+int coex_permute_map(coex_ctx *c, int mode, const int *snp_chrom, const long long *snp_addr, const long long *snp_back,
+                     int M, const long long *shifts, int K, const long long *chrom_start, const long long *chrom_end,
+                     const int *chrom_fid, int n_chrom, const int *back_chrom, const long long *back_addr,
+                     long long n_back, long long window, long long *perm_off, int *hit_rows, long long capacity,
+                     int on_device) {
+    COEX_TRY(check_ctx(c));
+    if (!c->have_features) COEX_FAIL("coex_permute_map: call coex_set_features first");
+    if (mode != 0 && mode != 1) COEX_FAIL("coex_permute_map: mode 0 = circular, 1 = backcirc");
+    if (M <= 0 || K <= 0 || n_chrom <= 0 || !snp_chrom || !snp_addr || !shifts || !chrom_start || !chrom_end || !chrom_fid ||
+        !perm_off || (!hit_rows && capacity > 0))
+        COEX_FAIL("coex_permute_map: null or empty argument");
+    if (mode == 1 && (!snp_back || !back_chrom || !back_addr || n_back <= 0)) COEX_FAIL("coex_permute_map: backcirc needs the sorted background");
+    if (window < 0) COEX_FAIL("coex_permute_map: negative window");
+    for (int m = 0; m < M; ++m)
+        if (snp_chrom[m] < 0 || snp_chrom[m] >= n_chrom) COEX_FAIL("coex_permute_map: chromosome index out of range");
+    cudaStream_t st = c->stream;
+    // ---- stage the (small) inputs in one blob ------------------------------------------------------
+    auto al = [](size_t x) { return (x + 15) / 16 * 16; };
+    const size_t o_sc = 0, o_sa = al(o_sc + (size_t)M * 4), o_sb = al(o_sa + (size_t)M * 8), o_sh = al(o_sb + (size_t)M * 8),
+                 o_cs = al(o_sh + (size_t)K * 8), o_ce = al(o_cs + (size_t)n_chrom * 8), o_cf = al(o_ce + (size_t)n_chrom * 8),
+                 o_bc = al(o_cf + (size_t)n_chrom * 4), o_ba = al(o_bc + (size_t)std::max<long long>(n_back, 0) * 4),
+                 total = al(o_ba + (size_t)std::max<long long>(n_back, 0) * 8);
+    std::vector<unsigned char> blob(total, 0);
+    memcpy(&blob[o_sc], snp_chrom, (size_t)M * 4); memcpy(&blob[o_sa], snp_addr, (size_t)M * 8);
+    if (snp_back) memcpy(&blob[o_sb], snp_back, (size_t)M * 8);
+    memcpy(&blob[o_sh], shifts, (size_t)K * 8);
+    memcpy(&blob[o_cs], chrom_start, (size_t)n_chrom * 8); memcpy(&blob[o_ce], chrom_end, (size_t)n_chrom * 8);
+    memcpy(&blob[o_cf], chrom_fid, (size_t)n_chrom * 4);
+    if (mode == 1) {
+        for (long long i = 0; i < n_back; ++i)
+            if (back_chrom[i] < 0 || back_chrom[i] >= n_chrom) COEX_FAIL("coex_permute_map: background chromosome index out of range");
+        memcpy(&blob[o_bc], back_chrom, (size_t)n_back * 4); memcpy(&blob[o_ba], back_addr, (size_t)n_back * 8);
+    }
+    COEX_TRY(c->pm_blob.reserve(total));
+    COEX_CUDA(cudaMemcpyAsync(c->pm_blob.p, blob.data(), total, cudaMemcpyHostToDevice, st));
+    PermuteArgs pa{};
+    pa.mode = mode; pa.M = M; pa.K = K;
+    pa.snp_chrom = reinterpret_cast<const int *>(c->pm_blob.p + o_sc);
+    pa.snp_addr = reinterpret_cast<const long long *>(c->pm_blob.p + o_sa);
+    pa.snp_back = reinterpret_cast<const long long *>(c->pm_blob.p + o_sb);
+    pa.shifts = reinterpret_cast<const long long *>(c->pm_blob.p + o_sh);
+    pa.chrom_start = reinterpret_cast<const long long *>(c->pm_blob.p + o_cs);
+    pa.chrom_end = reinterpret_cast<const long long *>(c->pm_blob.p + o_ce);
+    pa.chrom_fid = reinterpret_cast<const int *>(c->pm_blob.p + o_cf);
+    pa.n_chrom = n_chrom;
+    pa.back_chrom = reinterpret_cast<const int *>(c->pm_blob.p + o_bc);
+    pa.back_addr = reinterpret_cast<const long long *>(c->pm_blob.p + o_ba);
+    pa.n_back = n_back; pa.window = window;
+    pa.fkey = c->feat_key.p; pa.frow = c->feat_row.p; pa.fstart = c->feat_start.p; pa.fend = c->feat_end.p;
+    pa.N = c->N; pa.maxlen = c->feat_maxlen;
+    COEX_TRY(c->pm_counts.reserve((size_t)2 * K + 1));
+    COEX_CUDA(cudaMemsetAsync(c->pm_counts.p, 0, ((size_t)2 * K + 1) * sizeof(int), st));
+    pa.cand_count = c->pm_counts.p; pa.hit_count = c->pm_counts.p + K; pa.overflow = c->pm_counts.p + 2 * K;
+    // ---- pass 1: candidate pairs per set -> shared-memory capacity ------------------------------------
+    const long long KM = (long long)K * M;
+    permute_count_kernel<<<(unsigned)((KM + 255) / 256), 256, 0, st>>>(pa);
+    COEX_KCHECK(st);
+    std::vector<int> cand((size_t)K);
+    COEX_CUDA(cudaMemcpyAsync(cand.data(), pa.cand_count, (size_t)K * sizeof(int), cudaMemcpyDeviceToHost, st));
+    COEX_CUDA(cudaStreamSynchronize(st));
+    int cmax = 1;
+    for (int k = 0; k < K; ++k) cmax = std::max(cmax, cand[(size_t)k]);
+    const int cap = std::max(256, next_pow2(cmax));
+    if (cap > 8192) COEX_FAIL("coex_permute_map: more than 8192 (locus, feature) pairs in one set");
+    pa.cap = cap;
+    COEX_TRY(c->pm_hits_tmp.reserve((size_t)K * cap));
+    pa.hits_tmp = c->pm_hits_tmp.p;
+    // ---- pass 2: hits of every set, then offsets and the packed list ------------------------------------
+    const size_t smem = (size_t)2 * cap * sizeof(unsigned long long);
+    COEX_CUDA(cudaFuncSetAttribute(permute_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    permute_map_kernel<<<K, 256, smem, st>>>(pa);
+    COEX_KCHECK(st);
+    long long *d_off = perm_off;
+    int *d_rows = hit_rows;
+    if (!on_device) { COEX_TRY(c->pm_off.reserve((size_t)K + 1)); d_off = c->pm_off.p; }
+    permute_scan_kernel<<<1, 32, 0, st>>>(pa.hit_count, K, d_off);
+    COEX_KCHECK(st);
+    std::vector<long long> h_off((size_t)K + 1);
+    COEX_CUDA(cudaMemcpyAsync(h_off.data(), d_off, ((size_t)K + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    COEX_CUDA(cudaStreamSynchronize(st));
+    const long long H = h_off[(size_t)K];
+    if (H > capacity) COEX_FAIL("coex_permute_map: hit_rows capacity too small (needs " + std::to_string(H) + ")");
+    if (!on_device) { COEX_TRY(c->d_hits.reserve((size_t)std::max<long long>(H, 1))); d_rows = c->d_hits.p; }
+    if (H > 0) {
+        permute_compact_kernel<<<K, 256, 0, st>>>(pa.hits_tmp, cap, d_off, K, d_rows);
+        COEX_KCHECK(st);
+    }
+    c->launches += 4;
+    if (!on_device) {
+        memcpy(perm_off, h_off.data(), ((size_t)K + 1) * sizeof(long long));
+        if (H > 0) COEX_CUDA(cudaMemcpyAsync(hit_rows, d_rows, (size_t)H * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    COEX_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
 

@@ -121,6 +121,13 @@ struct coex_ctx {
     coex::DevBuf<int> chrom_id, name_rank;
     coex::DevBuf<long long> feat_start, feat_end;
     bool have_features = false;
+    // feature index for the locus -> promoter join (permute.cuh): rows sorted by (chromosome id, start)
+    coex::DevBuf<unsigned long long> feat_key;
+    coex::DevBuf<int> feat_row;
+    long long feat_maxlen = 0;
+    coex::DevBuf<unsigned char> pm_blob;      // staged inputs of coex_permute_map
+    coex::DevBuf<int> pm_counts, pm_hits_tmp;
+    coex::DevBuf<long long> pm_off;
     coex::DevBuf<double> glist;
     long long glist_len = 0;
 

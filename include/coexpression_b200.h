@@ -66,6 +66,22 @@ int coex_set_features(coex_ctx *ctx, const int *chrom_id, const long long *start
 /* ascending global correlation list (<expr>.spearmanlist, 1-make-network.py:76-79) */
 int coex_set_global_list(coex_ctx *ctx, const double *sorted_values, long long len);
 
+/* Row N1: K permuted locus sets and their promoters in one call, replacing the per-permutation
+ * Python loops of 0-prepare-coex.py:548-593 (get_gwad / shift / get_address, coexfunctions.py:102-128; backcirc with
+ * listitem, :319-325) and the `windowBed -w window` subprocess that follows each of them (0-prepare-coex.py:357,609).
+ *   mode 0 = circular, 1 = backcirc; shifts[k] == 0 is the real data (always the circular arithmetic, as in the
+ *   reference).  snp_chrom[m] indexes the chromosome list (chromrange order, 0-prepare-coex.py:319-330) whose
+ *   genome-wide ranges are chrom_start / chrom_end; chrom_fid[c] is the chrom_id that chromosome has in
+ *   coex_set_features (-1 if no feature lies on it).  backcirc: snp_back[m] = index of SNP m in the background
+ *   sorted by (genome-wide address, key) (0-prepare-coex.py:582), back_chrom / back_addr its entries.
+ * Output: perm_off[K+1] and hit_rows (table rows, first-appearance order) exactly as coex_network_batch takes them;
+ * host arrays, or device arrays when on_device != 0.  Fails if capacity is too small. */
+int coex_permute_map(coex_ctx *ctx, int mode, const int *snp_chrom, const long long *snp_addr,
+                     const long long *snp_back, int M, const long long *shifts, int K,
+                     const long long *chrom_start, const long long *chrom_end, const int *chrom_fid, int n_chrom,
+                     const int *back_chrom, const long long *back_addr, long long n_back, long long window,
+                     long long *perm_off, int *hit_rows, long long capacity, int on_device);
+
 /* A1 on the resident table.  which: 0 = raw values (Pearson), 1 = ranks (Spearman).
  * idxa/idxb/out are host pointers (on_device == 0) or device pointers. */
 int coex_pairs(coex_ctx *ctx, int which, const int *idxa, const int *idxb, long long npairs,

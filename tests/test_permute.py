@@ -1,0 +1,128 @@
+"""Row N1: permutation generation + locus -> promoter mapping.
+CPU: the restated reference arithmetic against hand-computed answers.  GPU: coex_permute_map against the restatement."""
+import numpy as np
+import pytest
+
+from oracle import permute_oracle as po
+
+
+CHROMLIST = ["chr1", "chr2", "chr3"]
+LENGTHS = {"chr1": 1000, "chr2": 500, "chr3": 250}
+
+
+def test_gwad_and_address_known_answers():
+    cr = po.chromrange_from_lengths(CHROMLIST, LENGTHS)
+    assert cr == {"chr1": [0, 1000], "chr2": [1000, 1500], "chr3": [1500, 1750]}
+    assert po.get_gwad("chr2", 7, cr) == 1007
+    assert po.get_gwad("chr2", 500, cr) is None            # not < end: the reference returns None (coexfunctions.py:109-112)
+    assert po.get_gwad("chr2", -3, cr) == 997              # negative addresses pass
+    assert po.get_gwad("chrQ", 1, cr) is None
+    assert po.get_address(1007, cr, CHROMLIST) == ("chr2", 7)
+    assert po.get_address(1000, cr, CHROMLIST) == ("chr1", 1000)   # start < gwad <= end: a boundary belongs to the LEFT chromosome
+    assert po.get_address(1750 + 5, cr, CHROMLIST) == ("chr1", 5)  # wrap: while gwad > genome_max
+    assert po.get_address(2 * 1750, cr, CHROMLIST) == ("chr3", 250)
+    assert po.get_address(0, cr, CHROMLIST) == ("chr1", 0)         # nothing matches: the reference's fallback
+
+
+def test_listitem_rounds_halves_away_from_zero():
+    assert po.round_half_away(0.5) == 1.0 and po.round_half_away(-0.5) == -1.0 and po.round_half_away(2.5) == 3.0
+    assert po.round_half_away(0.49999999999999994) == 0.0
+    n = 10
+    assert [po.listitem_index(n, i) for i in range(0, 12)] == [0, 1, 2, 3, 4, -5, -4, -3, -2, -1, 0, 1]
+    for idx in (3, 17, 123456789, 10 ** 10 + 7):
+        assert po.listitem_index(n, idx) % n == idx % n
+
+
+def test_circular_and_window_known_answers():
+    cr = po.chromrange_from_lengths(CHROMLIST, LENGTHS)
+    snps = [("chr1", 990), ("chr2", 10), ("chr3", 249)]
+    assert po.circular_positions(snps, 0, cr, CHROMLIST) == [("chr1", 990), ("chr2", 10), ("chr3", 249)]
+    assert po.circular_positions(snps, 20, cr, CHROMLIST) == [("chr2", 10), ("chr2", 30), ("chr1", 19)]
+    fc, fs, fe = ["chr2", "chr2", "chr1", "chr2"], [0, 40, 15, 26], [8, 60, 18, 27]
+    pairs = po.window_bed([("chr2", 10), ("chr2", 30), ("chr1", 19), None], fc, fs, fe, 2)
+    # chr2:10 +-2 = [8, 13): feature 0 ends at 8 (not > 8) -> no hit; chr2:30 = [28, 33): none; chr1:19 = [17, 22): feature 2
+    assert pairs == [(2, 2)]
+    pairs = po.window_bed([("chr2", 10), ("chr2", 30), ("chr1", 19)], fc, fs, fe, 10)
+    assert pairs == [(0, 0), (1, 1), (1, 3), (2, 2)]
+    assert po.hit_rows(pairs + [(3, 0)]) == [0, 1, 3, 2]
+
+
+def _synthetic_inputs(seed, N=4000, n=8, M=120):
+    from coexpression_b200 import synth
+    t = synth.make_table(N, n, seed=seed)
+    chromlist = list(t.chrom_len)
+    cr = po.chromrange_from_lengths(chromlist, t.chrom_len)
+    rng = np.random.default_rng(seed + 1)
+    pick = rng.integers(0, N, size=M)
+    snps = []
+    for r in pick:
+        c = t.chrom[r]
+        a = int(np.clip(t.start[r] + rng.integers(-4000, 4000), 1, t.chrom_len[c] - 2))
+        snps.append((c, a))
+    snps = list(dict.fromkeys(snps))
+    return t, chromlist, cr, snps, rng
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("window", [0, 2000, 50000])
+def test_gpu_circular_matches_restatement(window):
+    from coexpression_b200.api import CoexContext
+    t, chromlist, cr, snps, rng = _synthetic_inputs(5)
+    gmax = cr[chromlist[-1]][1]
+    shifts = [0] + [int(rng.random() * 10000000000) for _ in range(6)] + [gmax, 1, gmax - 1]
+    with CoexContext() as ctx:
+        ctx.set_expression(t.X); ctx.prepare()
+        ctx.set_features(t.chrom, t.start, t.end, t.names)
+        got = ctx.permute_map("circular", [c for c, _ in snps], [a for _, a in snps], shifts, chromlist, cr, window)
+    for k, s in enumerate(shifts):
+        want = po.hit_rows(po.window_bed(po.circular_positions(snps, s, cr, chromlist), t.chrom, t.start, t.end, window))
+        assert got[k].tolist() == want, (k, s)
+    assert len(got[0]) > 0 or window == 0
+
+
+@pytest.mark.gpu
+def test_gpu_backcirc_matches_restatement():
+    from coexpression_b200.api import CoexContext
+    t, chromlist, cr, snps, rng = _synthetic_inputs(9)
+    # background = random positions plus the real loci (0-prepare-coex.py:520-528), sorted by (gwad, key)
+    backdict = {}
+    for _ in range(3000):
+        c = chromlist[int(rng.integers(0, len(chromlist)))]
+        a = int(rng.integers(1, t.chrom_len[c] - 1))
+        backdict["%s_%s" % (c, a)] = po.get_gwad(c, a, cr)
+    for c, a in snps:
+        backdict["%s_%s" % (c, a)] = po.get_gwad(c, a, cr)
+    sb = po.sorted_background(backdict)
+    background = [(k.split("_")[0], int(k.split("_")[1])) for k in sb]
+    shifts = [0] + [int(rng.random() * 10000000000) for _ in range(8)] + [len(sb) // 2, len(sb) // 2 + 1, len(sb)]
+    with CoexContext() as ctx:
+        ctx.set_expression(t.X); ctx.prepare()
+        ctx.set_features(t.chrom, t.start, t.end, t.names)
+        got = ctx.permute_map("backcirc", [c for c, _ in snps], [a for _, a in snps], shifts, chromlist, cr, 3000,
+                              background=background)
+    for k, s in enumerate(shifts):
+        pos = po.circular_positions(snps, 0, cr, chromlist) if s == 0 else po.backcirc_positions(snps, s, sb)
+        want = po.hit_rows(po.window_bed(pos, t.chrom, t.start, t.end, 3000))
+        assert got[k].tolist() == want, (k, s)
+
+
+@pytest.mark.gpu
+def test_gpu_mapped_sets_feed_the_network_batch():
+    """End to end on the device path: permute_map -> network_batch gives what host-made hit lists give."""
+    from coexpression_b200 import synth
+    from coexpression_b200.api import CoexContext, Options
+    t, chromlist, cr, snps, rng = _synthetic_inputs(21, N=3000, n=64, M=150)
+    shifts = [0] + [int(rng.random() * 10000000000) for _ in range(5)]
+    ga, gb = synth.global_pair_indices(t.names, 20000, seed=3)
+    with CoexContext() as ctx:
+        ctx.set_expression(t.X); ctx.prepare()
+        ctx.set_features(t.chrom, t.start, t.end, t.names)
+        g = ctx.pairs(ga, gb, ranked=True)
+        ctx.set_global_list(np.sort(np.where(np.isnan(g), -99.0, g)))
+        hits = ctx.permute_map("circular", [c for c, _ in snps], [a for _, a in snps], shifts, chromlist, cr, 5000)
+        want = [np.array(po.hit_rows(po.window_bed(po.circular_positions(snps, s, cr, chromlist), t.chrom, t.start,
+                                                   t.end, 5000)), dtype=np.int32) for s in shifts]
+        a = ctx.network_batch(hits, Options())
+        b = ctx.network_batch(want, Options())
+    assert np.array_equal(a.group_density, b.group_density) and np.array_equal(a.n_groups, b.n_groups)
+    assert sum(len(h) for h in hits) > 50
