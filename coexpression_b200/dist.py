@@ -69,3 +69,38 @@ def gather_densities(local_perm_ids, densities, numperms_total, device=None):
             if k >= 0:
                 out[k] = row[2:2 + int(row[1])].copy()
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# C3: all unordered row pairs.  Row block b = rows [b * block, (b + 1) * block) against every LATER row; the blocks
+# are independent (no exchange), their cost falls linearly with b, so they are dealt to the ranks in a zig-zag
+# (0, 1, .., w-1, w-1, .., 1, 0, 0, 1, ..) that balances the pair counts; the ONE collective is the reduction of the
+# per-rank histograms of r.
+# ------------------------------------------------------------------------------------------------
+def shard_row_blocks(n_rows, world, block=1024):
+    """-> list over ranks of lists of (row0, row1) blocks."""
+    blocks = [(r0, min(n_rows, r0 + block)) for r0 in range(0, n_rows, block)]
+    shards = [[] for _ in range(world)]
+    for b, blk in enumerate(blocks):
+        lap, pos = divmod(b, world)
+        shards[pos if lap % 2 == 0 else world - 1 - pos].append(blk)
+    return shards
+
+
+def pairs_of_blocks(n_rows, blocks):
+    """Unordered pairs (i < j) whose first row lies in one of the blocks."""
+    return int(sum((r1 - r0) * n_rows - (r0 + r1 - 1) * (r1 - r0) // 2 - (r1 - r0) for r0, r1 in blocks))
+
+
+def reduce_histogram(hist, nan_count, device=None):
+    """Sum of the per-rank histograms (uint64 counts carried as int64) and NaN-pair counts on every rank."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return np.asarray(hist, dtype=np.uint64), int(nan_count)
+    device = device or torch.device("cpu")
+    buf = torch.empty(len(hist) + 1, dtype=torch.int64, device=device)
+    buf[:-1] = torch.as_tensor(np.asarray(hist, dtype=np.uint64).view(np.int64), device=device)
+    buf[-1] = int(nan_count)
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    out = buf.cpu().numpy()
+    return out[:-1].view(np.uint64).copy(), int(out[-1])

@@ -8,7 +8,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from coexpression_b200.dist import gather_densities, shard_permutations
+from coexpression_b200.dist import (gather_densities, pairs_of_blocks, reduce_histogram, shard_permutations,
+                                    shard_row_blocks)
 
 
 def _free_port():
@@ -62,3 +63,43 @@ def test_gather_world2_gloo():
 def test_gather_single_process():
     out = gather_densities([0, 1, 2], [_fake_density(k) for k in range(3)], 3)
     assert all(np.array_equal(out[k], _fake_density(k)) for k in range(3))
+
+
+def test_row_block_shards_partition_all_pairs():
+    for n_rows, block in ((10, 3), (5000, 256), (200000, 1024)):
+        total = n_rows * (n_rows - 1) // 2
+        for world in (1, 2, 4, 8):
+            shards = shard_row_blocks(n_rows, world, block)
+            rows = sorted(r for s in shards for blk in s for r in range(*blk)) if n_rows <= 5000 else None
+            if rows is not None:
+                assert rows == list(range(n_rows))
+            per = [pairs_of_blocks(n_rows, s) for s in shards]
+            assert sum(per) == total
+            if n_rows >= 5000 and n_rows // block >= 8 * world:
+                assert max(per) <= 1.1 * min(per)                 # zig-zag deal: balanced pair counts
+
+
+def _hist_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(5 + rank)
+    h = rng.integers(0, 1 << 40, size=64).astype(np.uint64)
+    tot, nan = reduce_histogram(h, 10 + rank)
+    q.put((rank, h.tolist(), tot.tolist(), nan))
+    dist.destroy_process_group()
+
+
+def test_histogram_reduce_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_hist_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = [a + b for a, b in zip(got[0][1], got[1][1])]
+    assert got[0][2] == want and got[1][2] == want and got[0][3] == got[1][3] == 21
