@@ -9,6 +9,7 @@
 #include "count.cuh"
 #include "count_dedup.cuh"
 #include "count_rows.cuh"
+#include "plan.cuh"
 #include "network.cuh"
 #include "allpairs.cuh"
 #include "permute.cuh"
@@ -82,43 +83,45 @@ static int prepare_impl(coex_ctx *c) {
 static int run_strip_gemm(coex_ctx *c, const int *d_rows, long long nq, long long nq_pad);
 
 static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const long long *perm_off,
-                               const int *h_hits, const int *d_hits, int Pmax, double *d_sc, long long *d_cn) {
+                               const int *d_hits, int Pmax, double *d_sc, long long *d_cn) {
     const long long H = perm_off[K];
     const long long N = c->N;
     cudaStream_t st = c->stream;
     const bool tdbg = getenv("COEX_HOST_DEBUG") != nullptr;
     auto now_us = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
     const double t_start = now_us();
-    // ---- counting sort of the queries by table row (host, O(N + H)) -------------------------------
-    // scratch reused across calls (no allocation or page faults in the steady state)
-    static thread_local std::vector<int> cnt, uniq, ustart, cursor, qlist, Pq;
-    cnt.assign((size_t)N + 1, 0);
-    for (long long q = 0; q < H; ++q) {
-        const int r = h_hits[q];
-        if (r < 0 || r >= N) COEX_FAIL("hit row out of range");
-        cnt[(size_t)r + 1]++;
-    }
-    uniq.clear(); ustart.clear();                    // ustart: start of each unique row's queries in qlist
-    cursor.resize((size_t)N);
-    int acc = 0;
-    for (long long r = 0; r < N; ++r) {
-        const int cr = cnt[(size_t)r + 1];
-        if (cr) { cursor[(size_t)r] = acc; ustart.push_back(acc); uniq.push_back((int)r); acc += cr; }
-    }
-    ustart.push_back(acc);
-    qlist.resize((size_t)H);
-    Pq.resize((size_t)H);
-    for (int k = 0; k < K; ++k) {
-        const int Pk = (int)(perm_off[k + 1] - perm_off[k]);
-        for (long long q = perm_off[k]; q < perm_off[k + 1]; ++q) {
-            qlist[(size_t)cursor[(size_t)h_hits[q]]++] = (int)q;
-            Pq[(size_t)q] = Pk;
-        }
-    }
-    const long long U = (long long)uniq.size();
     const bool rows_kernel = (c->count_mode == 2);
     const int Tcap = rows_kernel ? std::max(4096, (int)round_up(Pmax, 512))
                                  : std::max(kDdBuckets / 2, (int)round_up(Pmax, 256));   // 2*Tcap >= buckets: the bucket cursors alias thr32|hist
+    const int Qcap = kPlanQcap;
+    {   // strips first (upper bound of the unique rows), so that the big buffers keep their place whatever the plan needs
+        long long Us0 = (c->strip_mb << 20) / (c->N_pad * 4);
+        Us0 = std::max<long long>(256, Us0 / 256 * 256);
+        Us0 = std::min<long long>(Us0, round_up(std::min<long long>(H, N), 256));
+        COEX_TRY(c->strip.reserve((size_t)Us0 * c->N_pad));
+        COEX_TRY(c->a_hi.reserve((size_t)Us0 * c->n_pad)); COEX_TRY(c->a_lo.reserve((size_t)Us0 * c->n_pad));
+    }
+    // ---- the plan, on the device (plan.cuh): queries grouped by table row, work items ------------------------
+    COEX_TRY(c->pl_cnt.reserve((size_t)N + 2)); COEX_TRY(c->pl_cursor.reserve((size_t)N));
+    COEX_TRY(c->dd_uniq.reserve((size_t)std::min<long long>(H, N) + 1)); COEX_TRY(c->pl_ustart.reserve((size_t)std::min<long long>(H, N) + 2));
+    COEX_TRY(c->dd_qlist.reserve((size_t)H)); COEX_TRY(c->dd_qperm.reserve((size_t)H));
+    COEX_TRY(c->pl_meta.reserve(4)); COEX_TRY(c->pl_err.reserve(1));
+    COEX_CUDA(cudaMemsetAsync(c->pl_cnt.p, 0, ((size_t)N + 2) * sizeof(int), st));
+    COEX_CUDA(cudaMemsetAsync(c->pl_err.p, 0, sizeof(int), st));
+    const unsigned hb = (unsigned)((H + 255) / 256);
+    plan_count_kernel<<<hb, 256, 0, st>>>(d_hits, c->d_perm_off.p, K, H, N, c->pl_cnt.p, c->dd_qperm.p, c->pl_err.p);
+    COEX_KCHECK(st);
+    plan_rows_kernel<<<1, kPlanThreads, 0, st>>>(c->pl_cnt.p, N, c->dd_uniq.p, c->pl_ustart.p, c->pl_cursor.p, c->pl_meta.p);
+    COEX_KCHECK(st);
+    long long h_meta[2] = {0, 0};
+    int h_err = 0;
+    COEX_CUDA(cudaMemcpyAsync(h_meta, c->pl_meta.p, sizeof h_meta, cudaMemcpyDeviceToHost, st));
+    COEX_CUDA(cudaMemcpyAsync(&h_err, c->pl_err.p, sizeof h_err, cudaMemcpyDeviceToHost, st));
+    plan_scatter_kernel<<<hb, 256, 0, st>>>(d_hits, H, c->pl_cursor.p, c->dd_qlist.p);
+    COEX_KCHECK(st);
+    COEX_CUDA(cudaStreamSynchronize(st));                  // the one read-back of the plan: U sizes the strips
+    if (h_err) COEX_FAIL("hit row out of range");
+    const long long U = h_meta[0];
     // ---- strips of unique rows ------------------------------------------------------------------------
     const long long ld = c->N_pad;
     long long Us = (c->strip_mb << 20) / (ld * 4);
@@ -126,37 +129,29 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     Us = std::min<long long>(Us, round_up(U, 256));
     COEX_TRY(c->strip.reserve((size_t)Us * ld));
     COEX_TRY(c->a_hi.reserve((size_t)Us * c->n_pad)); COEX_TRY(c->a_lo.reserve((size_t)Us * c->n_pad));
-    COEX_TRY(c->dd_uniq.reserve((size_t)std::max<long long>(U, 1))); COEX_TRY(c->dd_qlist.reserve((size_t)std::max<long long>(H, 1)));
-    COEX_CUDA(cudaMemcpyAsync(c->dd_uniq.p, uniq.data(), U * sizeof(int), cudaMemcpyHostToDevice, st));
-    COEX_CUDA(cudaMemcpyAsync(c->dd_qlist.p, qlist.data(), H * sizeof(int), cudaMemcpyHostToDevice, st));
-    // ---- work items: (unique row, run of its queries whose statistics fit Tcap) -------------------------
-    static thread_local std::vector<DedupItem> items;
-    static thread_local std::vector<long long> strip_item_begin;
-    items.clear(); strip_item_begin.clear();
-    int Qcap = 2;
-    for (long long u0 = 0; u0 < U; u0 += Us) {
-        strip_item_begin.push_back((long long)items.size());
-        const long long u1 = std::min(U, u0 + Us);
-        for (long long u = u0; u < u1; ++u) {
-            int qb = ustart[(size_t)u];
-            const int qend = ustart[(size_t)u + 1];
-            while (qb < qend) {
-                int qe = qb, T = 0;
-                while (qe < qend && (qe == qb || T + Pq[(size_t)qlist[(size_t)qe]] <= Tcap)) { T += Pq[(size_t)qlist[(size_t)qe]]; ++qe; }
-                items.push_back(DedupItem{(int)(u - u0), qb, qe, T});
-                Qcap = std::max(Qcap, qe - qb);
-                qb = qe;
-            }
-        }
-    }
-    strip_item_begin.push_back((long long)items.size());
-    Qcap = (Qcap + 1) & ~1;
-    COEX_TRY(c->dd_items.reserve(std::max<size_t>(items.size(), 1) * sizeof(DedupItem)));
-    COEX_CUDA(cudaMemcpyAsync(c->dd_items.p, items.data(), items.size() * sizeof(DedupItem), cudaMemcpyHostToDevice, st));
+    COEX_TRY(c->pl_nitems.reserve((size_t)U + 1)); COEX_TRY(c->pl_itemoff.reserve((size_t)U + 2));
+    COEX_TRY(c->dd_items.reserve((size_t)(H + 1) * sizeof(DedupItem)));       // at most one item per query
+    const unsigned ub = (unsigned)((U + 255) / 256);
+    plan_items_kernel<false><<<ub, 256, 0, st>>>(c->pl_ustart.p, c->dd_qlist.p, c->dd_qperm.p, c->d_perm_off.p, (int)U, Tcap, Us,
+                                                 c->pl_nitems.p, nullptr, nullptr, c->dd_qlist.p);
+    COEX_KCHECK(st);
+    plan_item_scan_kernel<<<1, kPlanThreads, 0, st>>>(c->pl_nitems.p, (int)U, c->pl_itemoff.p);
+    COEX_KCHECK(st);
+    plan_items_kernel<true><<<ub, 256, 0, st>>>(c->pl_ustart.p, c->dd_qlist.p, c->dd_qperm.p, c->d_perm_off.p, (int)U, Tcap, Us,
+                                                nullptr, c->pl_itemoff.p, reinterpret_cast<DedupItem *>(c->dd_items.p), nullptr);
+    COEX_KCHECK(st);
+    const int n_strips = (int)((U + Us - 1) / Us);
+    COEX_TRY(c->pl_bounds.reserve((size_t)n_strips + 1));
+    plan_bounds_kernel<<<(unsigned)(n_strips / 256 + 1), 256, 0, st>>>(c->pl_itemoff.p, (int)U, Us, n_strips, c->pl_bounds.p);
+    COEX_KCHECK(st);
+    std::vector<long long> strip_item_begin((size_t)n_strips + 1);
+    COEX_CUDA(cudaMemcpyAsync(strip_item_begin.data(), c->pl_bounds.p, ((size_t)n_strips + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    c->launches += 7;
     const int bm_words = (N <= 262144) ? (int)((N + 31) / 32) : 0;     // hit-column bitmap (<= 32 KB: two CTAs per SM stay resident)
-    if (tdbg) fprintf(stderr, "[coex host] dedupe plan: %.0f us (H=%lld U=%lld items=%zu)\n", now_us() - t_start, H, U, items.size());
-    const size_t smem = rows_kernel ? rows_smem_bytes(Tcap, Qcap) : dedup_smem_bytes(Tcap, Qcap, bm_words);
-    if (smem > 227 * 1024) COEX_FAIL("count kernel: too many queries of one table row for shared memory");
+    if (tdbg) fprintf(stderr, "[coex host] dedupe plan (device): %.0f us on the host incl. one sync (H=%lld U=%lld)\n", now_us() - t_start, H, U);
+    const int claim = (bm_words > 0 && bm_words <= 2048) ? 1 : 0;      // <= 8 KB for the second bitmap
+    const size_t smem = rows_kernel ? rows_smem_bytes(Tcap, Qcap) : dedup_smem_bytes(Tcap, Qcap, bm_words, claim);
+    if (smem > 227 * 1024) COEX_FAIL("count kernel: too many statistics per query for shared memory");
     int per_sm = 1;
     if (rows_kernel) {
         COEX_CUDA(cudaFuncSetAttribute(count_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -168,10 +163,6 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     const int grid_max = std::max(1, per_sm) * c->sm_count;
     if (rows_kernel) {
         COEX_TRY(c->dd_gthr.reserve((size_t)grid_max * Tcap));
-        COEX_TRY(c->dd_qperm.reserve((size_t)std::max<long long>(H, 1)));
-        query_perm_kernel<<<(unsigned)((H + 255) / 256), 256, 0, st>>>(c->d_perm_off.p, K, H, c->dd_qperm.p);
-        COEX_CUDA(cudaGetLastError());
-        c->launches += 1;
     } else {
         COEX_TRY(c->dd_gthr.reserve((size_t)grid_max * Tcap * 3)); COEX_TRY(c->dd_gorg.reserve((size_t)grid_max * Tcap * 5));
     }
@@ -186,36 +177,36 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     for (long long u0 = 0; u0 < U; u0 += Us, ++s_idx) {
         const long long nu = std::min(Us, U - u0);
         COEX_TRY(run_strip_gemm(c, c->dd_uniq.p + u0, nu, round_up(nu, 256)));
-        DedupArgs da{};
-        da.strip = c->strip.p; da.ld = ld;
-        da.items = reinterpret_cast<const DedupItem *>(c->dd_items.p) + strip_item_begin[s_idx];
-        da.n_items = (int)(strip_item_begin[s_idx + 1] - strip_item_begin[s_idx]);
-        da.uniq_rows = c->dd_uniq.p + u0; da.qlist = c->dd_qlist.p;
-        da.perm_off = c->d_perm_off.p; da.sc_off = c->d_sc_off.p; da.K = K; da.hit_rows = d_hits;
-        da.sx = c->sx.p; da.icol = c->icol.p; da.rawsum_pos = c->rawsum_pos.p; da.N = N;
-        da.n_degenerate = c->d_ndeg.p; da.anticor = prm->anticorrelation; da.scores = d_sc; da.counts = d_cn;
-        da.Tcap = Tcap; da.Qcap = Qcap;
-        da.bm_words = bm_words;
-        da.R = std::min(1.0, std::max(0.05, 8.0 / std::sqrt((double)std::max(c->n, 2)))); da.g_thr = c->dd_gthr.p; da.g_org = c->dd_gorg.p; da.score_tab = c->dd_tab.p; da.phase_clk = dbg ? phase.p : nullptr;
+        if (s_idx == 0) COEX_CUDA(cudaStreamSynchronize(st));        // second (and last) read-back of the plan; the first GEMM is queued already
+        const DedupItem *items_s = reinterpret_cast<const DedupItem *>(c->dd_items.p) + strip_item_begin[s_idx];
+        const int n_items_s = (int)(strip_item_begin[s_idx + 1] - strip_item_begin[s_idx]);
+        const int grid = std::min(grid_max, std::max(n_items_s, 1));
         COEX_TRY(stage_begin(c, ST_COUNT));
         if (rows_kernel) {
             RowCountArgs ra{};
-            ra.strip = da.strip; ra.ld = ld; ra.items = da.items; ra.n_items = da.n_items; ra.uniq_rows = da.uniq_rows;
-            ra.qlist = da.qlist; ra.q_perm = c->dd_qperm.p; ra.perm_off = da.perm_off; ra.sc_off = da.sc_off;
-            ra.hit_rows = d_hits; ra.sx = da.sx; ra.icol = da.icol; ra.rawsum_pos = da.rawsum_pos; ra.N = N;
-            ra.n_degenerate = da.n_degenerate; ra.anticor = da.anticor; ra.scores = d_sc; ra.counts = d_cn; ra.Tcap = Tcap; ra.Qcap = Qcap;
-            ra.g_t64 = c->dd_gthr.p; ra.score_tab = da.score_tab; ra.phase_clk = da.phase_clk;
-            const int grid = std::min(grid_max, std::max(ra.n_items, 1));
+            ra.strip = c->strip.p; ra.ld = ld; ra.items = items_s; ra.n_items = n_items_s; ra.uniq_rows = c->dd_uniq.p + u0;
+            ra.qlist = c->dd_qlist.p; ra.q_perm = c->dd_qperm.p; ra.perm_off = c->d_perm_off.p; ra.sc_off = c->d_sc_off.p;
+            ra.hit_rows = d_hits; ra.sx = c->sx.p; ra.icol = c->icol.p; ra.rawsum_pos = c->rawsum_pos.p; ra.N = N;
+            ra.n_degenerate = c->d_ndeg.p; ra.anticor = prm->anticorrelation; ra.scores = d_sc; ra.counts = d_cn; ra.Tcap = Tcap; ra.Qcap = Qcap;
+            ra.g_t64 = c->dd_gthr.p; ra.score_tab = c->dd_tab.p; ra.phase_clk = dbg ? phase.p : nullptr;
             count_rows_kernel<<<grid, kCrThreads, smem, st>>>(ra);
         } else {
-            count_dedup_kernel<<<std::min(grid_max, std::max(da.n_items, 1)), kDdThreads, smem, st>>>(da);
+            DedupArgs da{};
+            da.strip = c->strip.p; da.ld = ld; da.items = items_s; da.n_items = n_items_s;
+            da.uniq_rows = c->dd_uniq.p + u0; da.qlist = c->dd_qlist.p;
+            da.perm_off = c->d_perm_off.p; da.sc_off = c->d_sc_off.p; da.K = K; da.hit_rows = d_hits;
+            da.sx = c->sx.p; da.icol = c->icol.p; da.rawsum_pos = c->rawsum_pos.p; da.N = N;
+            da.n_degenerate = c->d_ndeg.p; da.anticor = prm->anticorrelation; da.scores = d_sc; da.counts = d_cn;
+            da.Tcap = Tcap; da.Qcap = Qcap; da.bm_words = bm_words; da.claim = claim;
+            da.R = std::min(1.0, std::max(0.05, 8.0 / std::sqrt((double)std::max(c->n, 2)))); da.g_thr = c->dd_gthr.p; da.g_org = c->dd_gorg.p;
+            da.score_tab = c->dd_tab.p; da.phase_clk = dbg ? phase.p : nullptr;
+            count_dedup_kernel<<<grid, kDdThreads, smem, st>>>(da);
         }
         COEX_KCHECK(st);
         COEX_TRY(stage_end(c, 1));
     }
-    // the host vectors above feed async copies: they must be consumed before this frame dies
-    COEX_CUDA(cudaStreamSynchronize(st));
     if (dbg) {
+        COEX_CUDA(cudaStreamSynchronize(st));
         unsigned long long h[8];
         COEX_CUDA(cudaMemcpy(h, phase.p, sizeof h, cudaMemcpyDeviceToHost));
         if (rows_kernel)
@@ -338,15 +329,7 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
                 COEX_TRY(stage_end(c, 1));
             }
             if (prm->measure == 0 && c->count_mode != 1) {
-                std::vector<int> hh;
-                const int *h_hits = hit_rows;
-                if (on_device) {
-                    hh.resize((size_t)H);
-                    COEX_CUDA(cudaMemcpyAsync(hh.data(), d_hits, H * sizeof(int), cudaMemcpyDeviceToHost, st));
-                    COEX_CUDA(cudaStreamSynchronize(st));
-                    h_hits = hh.data();
-                }
-                COEX_TRY(spearman_dedup_path(c, prm, K, perm_off, h_hits, d_hits, Pmax, d_sc, d_cn));
+                COEX_TRY(spearman_dedup_path(c, prm, K, perm_off, d_hits, Pmax, d_sc, d_cn));
             } else {
             const size_t smem = (size_t)T2max * 16;
             COEX_CUDA(cudaFuncSetAttribute(count_score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -603,7 +586,8 @@ int coex_destroy(coex_ctx *c) {
     c->d_aps.release(); c->d_scores.release(); c->w_s1.release(); c->w_d0.release(); c->w_w.release();
     c->d_counts.release(); c->w_gsize.release(); c->w_cursor.release(); c->w_act.release(); c->w_actn.release(); c->w_front.release(); c->w_best.release(); c->w_cand.release(); c->w_state.release(); c->p_idxa.release(); c->p_idxb.release();
     c->p_out.release(); c->icol.release(); c->d_ndeg.release(); c->dd_uniq.release(); c->dd_qlist.release();
-    c->dd_items.release(); c->dd_qperm.release(); c->dd_gthr.release(); c->dd_gorg.release(); c->dd_tab.release();
+    c->dd_items.release(); c->dd_qperm.release(); c->pl_cnt.release(); c->pl_cursor.release(); c->pl_ustart.release(); c->pl_nitems.release();
+    c->pl_itemoff.release(); c->pl_bounds.release(); c->pl_meta.release(); c->pl_err.release(); c->dd_gthr.release(); c->dd_gorg.release(); c->dd_tab.release();
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;

@@ -145,6 +145,8 @@ struct coex_ctx {
     coex::DevBuf<int> d_ndeg;                 // [1]
     coex::DevBuf<int> dd_uniq, dd_qlist, dd_qperm;   // de-duplicated query rows; permutation of every flat hit index
     coex::DevBuf<unsigned char> dd_items;     // DedupItem[]
+    coex::DevBuf<int> pl_cnt, pl_cursor, pl_ustart, pl_nitems, pl_err;   // device-side plan (plan.cuh)
+    coex::DevBuf<long long> pl_itemoff, pl_bounds, pl_meta;
     coex::DevBuf<double> dd_gthr, dd_tab;
     coex::DevBuf<unsigned int> dd_gorg;
     int count_mode = 0;                       // 0 = de-duplicated sorted-statistics kernel (count_dedup), 1 = per-query binary-search kernel, 2 = de-duplicated bucket-window kernel (count_rows)

@@ -45,7 +45,7 @@ struct DedupItem {
 struct DedupArgs {
     const int *strip;               // [rows_in_strip, ld]
     long long ld;
-    const DedupItem *items;         // items of this launch
+    const DedupItem *items;         // items of this launch (plan.cuh)
     int n_items;
     const int *uniq_rows;           // table row of each unique-row slot of the strip
     const int *qlist;               // flat hit indices grouped by unique row
@@ -63,6 +63,7 @@ struct DedupArgs {
     int Tcap, Qcap;                 // shared-memory capacities (statistics, queries per item)
     double R;                       // bucket range [-R, R]
     int bm_words;                   // 32-bit words of the hit-column bitmap (0 = table too long, bitmap disabled)
+    int claim;                      // 1: a second bitmap (claim mask) de-duplicates the hit columns (short tables only)
     double *g_thr;                  // scratch [gridDim.x, 3, Tcap]: unsorted | grouped | sorted statistics
     unsigned int *g_org;            // scratch [gridDim.x, 5, Tcap]: grouped | sorted origins, unsorted | grouped | sorted columns
     const double *score_tab;        // [N+1] edge score of every possible bisect index (len = N-1)
@@ -92,7 +93,7 @@ count_dedup_kernel(DedupArgs a) {
     int *q_off = q_i + a.Qcap;                   // [Qcap] offset of the query's permutation in hit_rows
     int *q_P = q_off + a.Qcap;                   // [Qcap] hits of that permutation
     int *q_toff = q_P + a.Qcap;                  // [Qcap+2] offset of the query's statistics in the item
-    unsigned int *bitmap = reinterpret_cast<unsigned int *>(q_toff + a.Qcap + 2);   // [bm_words] hit columns of this item (skipped by the streaming pass)
+    unsigned int *bitmap = reinterpret_cast<unsigned int *>(q_toff + a.Qcap + 2);   // [bm_words] hit columns of this item (skipped by the streaming pass) | [bm_words] claim mask if a.claim
     __shared__ int s_T, s_qn;
     __shared__ unsigned int s_warp[kDdThreads / 32];
 
@@ -137,7 +138,7 @@ count_dedup_kernel(DedupArgs a) {
         }
         if (tid == 0) { s_T = 0; s_qn = 0; }
         for (int b = tid; b <= kDdBuckets; b += kDdThreads) lut[b] = 0;
-        for (int wd = tid; wd < a.bm_words; wd += kDdThreads) bitmap[wd] = 0;
+        for (int wd = tid; wd < (a.claim ? 2 : 1) * a.bm_words; wd += kDdThreads) bitmap[wd] = 0;
         __syncthreads();
         if (tid == 0) {
             int acc = 0;
@@ -187,7 +188,11 @@ count_dedup_kernel(DedupArgs a) {
                     atomicAdd(&lut[dd_bucket64(r, a.R, bscale)], 1u);
                     // the null value of a hit column IS this statistic (same arithmetic): it is accounted
                     // exactly in step C' and skipped by the float streaming pass
-                    if (a.bm_words) atomicOr(&bitmap[cc4[e] >> 5], 1u << (cc4[e] & 31));
+                    if (a.bm_words) {
+                        const unsigned int bit = 1u << (cc4[e] & 31);
+                        atomicOr(&bitmap[cc4[e] >> 5], bit);
+                        if (a.claim) atomicOr(&bitmap[a.bm_words + (cc4[e] >> 5)], bit);
+                    }
                 }
             }
         }
@@ -252,15 +257,22 @@ count_dedup_kernel(DedupArgs a) {
         for (int p = tid; p <= T; p += kDdThreads) hist[p] = 0;
         __syncthreads();
         // ---- C'. hit columns: value == statistic exactly.  A column hit by several queries of the item appears as
-        // several EQUAL statistics (same row, same column, same arithmetic): the first of them in sorted order adds it.
+        // several EQUAL statistics (same row, same column, same arithmetic) and is added once: by the statistic that
+        // claims its bit in a second bitmap (short tables), or by the first of the equal statistics in sorted order
+        // (long tables, where a second bitmap would cost the second resident CTA).
         if (a.bm_words) {
             for (int sidx = tid; sidx < T; sidx += kDdThreads) {
                 const int c = col[sidx];
-                const double t = thr64[sidx];
                 const float tf = thr32[sidx];                         // shared-memory filter in front of the L2-resident doubles
                 bool first = true;
-                for (int e1 = sidx - 1; e1 >= 0 && thr32[e1] == tf && thr64[e1] == t; --e1)
-                    if (col[e1] == c) { first = false; break; }
+                if (a.claim) {                                        // short table: the first statistic to claim the column's bit
+                    const unsigned int bit = 1u << (c & 31);
+                    first = (atomicAnd(&bitmap[a.bm_words + (c >> 5)], ~bit) & bit) != 0;
+                }
+                const double t = thr64[sidx];
+                if (!a.claim)
+                    for (int e1 = sidx - 1; e1 >= 0 && thr32[e1] == tf && thr64[e1] == t; --e1)
+                        if (col[e1] == c) { first = false; break; }
                 if (first) {
                     int e2 = sidx + 1;
                     while (e2 < T && thr32[e2] == tf && thr64[e2] == t) ++e2;   // statistics <= value: through the run of equals
@@ -425,9 +437,9 @@ __global__ void icol_kernel(const double *__restrict__ sx, long long N, long lon
     if (threadIdx.x == 0 && deg) atomicAdd(n_degenerate, deg);
 }
 
-inline size_t dedup_smem_bytes(int Tcap, int Qcap, int bm_words) {
+inline size_t dedup_smem_bytes(int Tcap, int Qcap, int bm_words, int claim) {
     return (size_t)Qcap * 8 + (size_t)Tcap * 4 + (size_t)(Tcap + 4) * 4 + (size_t)(kDdBuckets + 4) * 4 +
-           (size_t)kDdQueue * 4 + (size_t)Qcap * 8 + (size_t)Qcap * 4 * 3 + (size_t)(Qcap + 2) * 4 + (size_t)bm_words * 4 + 16;
+           (size_t)kDdQueue * 4 + (size_t)Qcap * 8 + (size_t)Qcap * 4 * 3 + (size_t)(Qcap + 2) * 4 + (size_t)bm_words * 4 * (claim ? 2 : 1) + 16;
 }
 
 }  // namespace coex

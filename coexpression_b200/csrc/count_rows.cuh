@@ -42,7 +42,7 @@ constexpr int kCrQueue = 3072;          // (statistic, column) pairs per chunk t
 struct RowCountArgs {
     const int *strip;               // [rows_in_strip, ld]
     long long ld;
-    const DedupItem *items;
+    const DedupItem *items;         // items of this launch (plan.cuh)
     int n_items;
     const int *uniq_rows;           // table row of each unique-row slot of the strip
     const int *qlist;               // flat hit indices grouped by unique row
