@@ -55,6 +55,8 @@ SIGNATURES = {
                                   ctypes.c_void_p, ctypes.c_int]),
     "coex_allpairs_histogram": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_ll, c_ll, ctypes.c_int,
                                                ctypes.c_void_p, ctypes.c_void_p]),
+    "coex_allpairs_accumulate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_ll, c_ll, ctypes.c_int, ctypes.c_int]),
+    "coex_allpairs_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "coex_corr_block": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_ll, c_ll, ctypes.c_void_p]),
     "coex_set_pearson": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "coex_network_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(CoexParams), ctypes.c_int] +

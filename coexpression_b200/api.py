@@ -204,6 +204,19 @@ class CoexContext:
                                   out.ctypes.data, 0), "coex_pairs")
         return out
 
+    def allpairs_accumulate(self, ranked, row0, row1, nbins=1 << 20, reset=False):
+        """Adds the pairs (i < j) with i in [row0, row1) to the device-resident histogram; nothing is read back."""
+        check(self.lib.coex_allpairs_accumulate(self.h, 1 if ranked else 0, row0, row1, nbins, 1 if reset else 0),
+              "coex_allpairs_accumulate")
+
+    def allpairs_read(self, nbins=1 << 20, device_ptr=None, host=True):
+        """-> (hist uint64 [nbins], nan pairs) of everything accumulated; device_ptr (nbins + 1 int64 counters) gets a copy."""
+        hist = np.zeros(nbins, dtype=np.uint64) if host else None
+        nan = np.zeros(1, dtype=np.uint64)
+        check(self.lib.coex_allpairs_read(self.h, hist.ctypes.data if host else None, nan.ctypes.data, device_ptr),
+              "coex_allpairs_read")
+        return hist, int(nan[0])
+
     def allpairs_histogram(self, ranked, row0=0, row1=None, nbins=1 << 20):
         row1 = self.N if row1 is None else row1
         hist = np.zeros(nbins, dtype=np.uint64)

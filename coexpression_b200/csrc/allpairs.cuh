@@ -81,15 +81,19 @@ static int pearson_tensor_strip(coex_ctx *c, long long row0, long long m_rows, i
     return tc_gemm_digits<4>(c, c->z_planes.p, (long long)plane, row0, m_rows, c->strip_f64.p, c->N_pad, c->z_inv_s.p, upper_only);
 }
 
+// reset != 0: the resident histogram is cleared first.  hist / nan_count == nullptr: nothing is read back (the caller
+// accumulates several row blocks and fetches the result once, allpairs_read_impl).
 static int allpairs_histogram_impl(coex_ctx *c, int which, long long row0, long long row1, int nbins,
-                                   unsigned long long *hist, unsigned long long *nan_count) {
+                                   unsigned long long *hist, unsigned long long *nan_count, int reset) {
     if (row0 < 0 || row1 > c->N || row0 > row1 || nbins <= 0) COEX_FAIL("coex_allpairs_histogram: bad arguments");
     if (which == 1 && c->n > 1860) COEX_FAIL("Spearman tensor path supports up to 1860 samples");
     stage_reset(c);
     cudaStream_t st = c->stream;
-    DevBuf<unsigned long long> dh;
+    if (!reset && c->ap_nbins != nbins) COEX_FAIL("coex_allpairs_accumulate: nbins differs from the resident histogram (reset first)");
+    DevBuf<unsigned long long> &dh = c->ap_hist;
     COEX_TRY(dh.reserve((size_t)nbins + 1));
-    COEX_CUDA(cudaMemsetAsync(dh.p, 0, ((size_t)nbins + 1) * sizeof(unsigned long long), st));
+    if (reset) COEX_CUDA(cudaMemsetAsync(dh.p, 0, ((size_t)nbins + 1) * sizeof(unsigned long long), st));
+    c->ap_nbins = nbins;
     const bool ptensor = (which == 0 && c->pearson_mode == 0);
     const long long ld = (which == 1 || ptensor) ? c->N_pad : c->N;
     long long Hs = (c->strip_mb << 20) / (ld * (which == 1 ? 4 : 8));
@@ -118,7 +122,10 @@ static int allpairs_histogram_impl(coex_ctx *c, int which, long long row0, long 
             COEX_TRY(stage_end(c, 1));
             COEX_TRY(stage_begin(c, ST_GEMM));
             if (c->gemm_mode == 0) {
-                COEX_TRY(tc_gemm_i8(c, nq_pad));
+                c->gemm_col0 = r0;                          // only columns > row are histogrammed
+                const int gs = tc_gemm_i8(c, nq_pad);
+                c->gemm_col0 = 0;
+                COEX_TRY(gs);
             } else {
                 dim3 grid((unsigned)(c->N_pad / kSimtTile), (unsigned)(nq_pad / kSimtTile));
                 gemm_i8_simt_kernel<<<grid, 256, 0, st>>>(c->a_hi.p, c->a_lo.p, c->u_hi.p, c->u_lo.p, c->n_pad, c->strip.p,
@@ -147,12 +154,24 @@ static int allpairs_histogram_impl(coex_ctx *c, int which, long long row0, long 
         COEX_CUDA(cudaGetLastError());
         COEX_TRY(stage_end(c, 1));
     }
-    COEX_CUDA(cudaMemcpyAsync(hist, dh.p, (size_t)nbins * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    COEX_CUDA(cudaMemcpyAsync(nan_count, dh.p + nbins, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    COEX_CUDA(cudaStreamSynchronize(st));
-    dh.release();
-    if ((which == 1 && c->gemm_mode == 0) || ptensor) COEX_TRY(tc_check_error(c));
+    if (hist) COEX_CUDA(cudaMemcpyAsync(hist, dh.p, (size_t)nbins * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    if (nan_count) COEX_CUDA(cudaMemcpyAsync(nan_count, dh.p + nbins, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    if (hist || nan_count) {
+        COEX_CUDA(cudaStreamSynchronize(st));
+        if ((which == 1 && c->gemm_mode == 0) || ptensor) COEX_TRY(tc_check_error(c));
+    }
     return 0;
+}
+
+static int allpairs_read_impl(coex_ctx *c, unsigned long long *hist, unsigned long long *nan_count, void *device_copy) {
+    if (c->ap_nbins <= 0 || !c->ap_hist.p) COEX_FAIL("coex_allpairs_read: nothing accumulated");
+    cudaStream_t st = c->stream;
+    const size_t bytes = (size_t)c->ap_nbins * sizeof(unsigned long long);
+    if (device_copy) COEX_CUDA(cudaMemcpyAsync(device_copy, c->ap_hist.p, bytes + sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    if (hist) COEX_CUDA(cudaMemcpyAsync(hist, c->ap_hist.p, bytes, cudaMemcpyDeviceToHost, st));
+    if (nan_count) COEX_CUDA(cudaMemcpyAsync(nan_count, c->ap_hist.p + c->ap_nbins, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    COEX_CUDA(cudaStreamSynchronize(st));
+    return tc_check_error(c);
 }
 
 // expand a strip into r values (NaN where the reference yields NaN)

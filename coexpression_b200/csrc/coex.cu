@@ -578,7 +578,7 @@ int coex_destroy(coex_ctx *c) {
     c->raw_own.release(); c->raw_sum.release(); c->raw_mean.release(); c->raw_xx.release(); c->rawsum_pos.release();
     c->rank2.release(); c->u_hi.release(); c->u_lo.release(); c->suu.release(); c->sx.release();
     c->z_planes.release(); c->z_ok.release(); c->z_l1.release(); c->z_inv_s.release();
-    c->feat_key.release(); c->feat_row.release(); c->pm_blob.release(); c->pm_counts.release(); c->pm_hits_tmp.release(); c->pm_off.release();
+    c->ap_hist.release(); c->feat_key.release(); c->feat_row.release(); c->pm_blob.release(); c->pm_counts.release(); c->pm_hits_tmp.release(); c->pm_off.release();
     c->chrom_id.release(); c->name_rank.release(); c->feat_start.release(); c->feat_end.release(); c->glist.release();
     c->a_hi.release(); c->a_lo.release(); c->strip.release(); c->strip_f64.release();
     c->d_perm_off.release(); c->d_sc_off.release(); c->d_warp_off.release(); c->d_hits.release(); c->d_ngroups.release(); c->d_grp.release();
@@ -812,7 +812,18 @@ int coex_allpairs_histogram(coex_ctx *c, int which, long long row0, long long ro
                             unsigned long long *hist, unsigned long long *nan_count) {
     COEX_TRY(check_ctx(c));
     if (!c->prepared) COEX_FAIL("coex_allpairs_histogram: call coex_prepare first");
-    return allpairs_histogram_impl(c, which, row0, row1, nbins, hist, nan_count);
+    return allpairs_histogram_impl(c, which, row0, row1, nbins, hist, nan_count, 1);
+}
+
+int coex_allpairs_accumulate(coex_ctx *c, int which, long long row0, long long row1, int nbins, int reset) {
+    COEX_TRY(check_ctx(c));
+    if (!c->prepared) COEX_FAIL("coex_allpairs_accumulate: call coex_prepare first");
+    return allpairs_histogram_impl(c, which, row0, row1, nbins, nullptr, nullptr, reset);
+}
+
+int coex_allpairs_read(coex_ctx *c, unsigned long long *hist, unsigned long long *nan_count, void *device_copy) {
+    COEX_TRY(check_ctx(c));
+    return allpairs_read_impl(c, hist, nan_count, device_copy);
 }
 
 int coex_corr_block(coex_ctx *c, int which, long long row0, long long nrows, double *out) {

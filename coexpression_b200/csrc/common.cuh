@@ -154,6 +154,9 @@ struct coex_ctx {
     coex::DevBuf<double> p_out;
     long long strip_mb = 1024;
     int gemm_mode = 0;
+    long long gemm_col0 = 0;                  // persistent tcgen05 kernel: first table column to compute (0 except for upper-triangle strips)
+    coex::DevBuf<unsigned long long> ap_hist; // all-pairs histogram [nbins + 1] (+ NaN pairs), resident across calls
+    int ap_nbins = 0;
     int gemm_bn = 0;                          // tcgen05 kernel: 0 = persistent 128x64 tiles (default), 128 / 64 = one tile per CTA
 
     // ---- bookkeeping ------------------------------------------------------------------------

@@ -240,7 +240,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_i8_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                              const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
-                             int *__restrict__ out, long long ldo, int nkb, int m_tiles, long long n_tiles, int *err) {
+                             int *__restrict__ out, long long ldo, int nkb, int m_tiles, long long n_tiles, int col_tile0,
+                             int *err) {
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     const uint32_t bars = base + kPsStages * kPsStage;
@@ -271,7 +272,7 @@ gemm_i8_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_ah, const _
             bool ok = true;
             for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
                 const int m0 = (int)(tile % m_tiles) * kTcBM;           // query-row tile fastest
-                const int c0 = (int)(tile / m_tiles) * kPsBN;
+                const int c0 = ((int)(tile / m_tiles) + col_tile0) * kPsBN;
                 for (int kb = 0; kb < nkb; ++kb, ++g) {
                     const int s = (int)(g % kPsStages);
                     if (g >= kPsStages && !mbar_wait(bar_empty + 8 * s, (uint32_t)((g / kPsStages) - 1) & 1u, err, 1)) { ok = false; break; }
@@ -322,7 +323,7 @@ gemm_i8_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_ah, const _
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
             const int m0 = (int)(tile % m_tiles) * kTcBM;
-            const int c0 = (int)(tile / m_tiles) * kPsBN;
+            const int c0 = ((int)(tile / m_tiles) + col_tile0) * kPsBN;
             if (!mbar_wait(bar_tfull + 8 * buf, (uint32_t)(it >> 1) & 1u, err, 3)) break;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tl = tmem_base + buf * 256 + ((uint32_t)(quarter * 32) << 16);
@@ -557,10 +558,11 @@ inline int tc_gemm_i8_ptrs(coex_ctx *c, const int8_t *a_hi, const int8_t *a_lo, 
     }
     if (persistent) {
         const int m_tiles = (int)(m_rows / kTcBM);
-        const long long n_tiles = (long long)m_tiles * (c->N_pad / kPsBN);
+        const int col_tile0 = (int)std::min<long long>(c->gemm_col0 / kPsBN, c->N_pad / kPsBN - 1);   // upper-triangle callers skip the columns before their rows
+        const long long n_tiles = (long long)m_tiles * (c->N_pad / kPsBN - col_tile0);
         const unsigned ctas = (unsigned)std::min<long long>(n_tiles, c->sm_count);
         gemm_i8_tc_persistent_kernel<<<ctas, kTcThreads, kPsSmem, c->stream>>>(t->map_ah, t->map_al, t->map_bh, t->map_bl, out, ldo,
-                                                                               c->n_pad / kTcBK, m_tiles, n_tiles, t->d_err);
+                                                                               c->n_pad / kTcBK, m_tiles, n_tiles, col_tile0, t->d_err);
         COEX_CUDA(cudaGetLastError());
         return 0;
     }

@@ -92,6 +92,11 @@ int coex_pairs(coex_ctx *ctx, int which, const int *idxa, const int *idxb, long 
  * counted in nan_count.  which as in coex_pairs.  hist: host, unsigned long long [nbins]. */
 int coex_allpairs_histogram(coex_ctx *ctx, int which, long long row0, long long row1, int nbins,
                             unsigned long long *hist, unsigned long long *nan_count);
+/* The same reduction with the histogram RESIDENT on the device: row blocks are accumulated call after call (reset != 0
+ * clears it first) and fetched once -- to host arrays and / or to a device buffer of nbins + 1 counters (the last one
+ * is the NaN-pair count) that a multi-GPU caller hands to its all-reduce. */
+int coex_allpairs_accumulate(coex_ctx *ctx, int which, long long row0, long long row1, int nbins, int reset);
+int coex_allpairs_read(coex_ctx *ctx, unsigned long long *hist, unsigned long long *nan_count, void *device_copy);
 
 /* A block of the correlation matrix: table rows [row0, row0 + nrows) against every table row.
  * which: 1 = Spearman (exact integer tensor path, bit-identical to the reference on ranks),

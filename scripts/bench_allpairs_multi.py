@@ -33,7 +33,7 @@ def main():
     import torch.distributed as dist
     from coexpression_b200 import synth
     from coexpression_b200.api import CoexContext
-    from coexpression_b200.dist import pairs_of_blocks, reduce_histogram, shard_row_blocks
+    from coexpression_b200.dist import pairs_of_blocks, shard_row_blocks
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -62,17 +62,18 @@ def main():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        hist = np.zeros(a.nbins, dtype=np.uint64)
-        nan = 0
         dev_ms = 0.0
+        acc = torch.zeros(a.nbins + 1, dtype=torch.int64, device=dev)          # nbins counters + the NaN-pair count
         t0 = time.perf_counter()
-        for r0, r1 in mine:
-            h, nn = ctx.allpairs_histogram(ranked, r0, r1, a.nbins)
+        for i, (r0, r1) in enumerate(mine):
+            ctx.allpairs_accumulate(ranked, r0, r1, a.nbins, reset=(i == 0))   # histogram stays on the device
             st = ctx.stage_ms()
             dev_ms += st["corr_gemm"][0] + st["count_score"][0]
-            hist += h
-            nan += nn
-        tot, nan_tot = reduce_histogram(hist, nan, dev)
+        ctx.allpairs_read(a.nbins, device_ptr=acc.data_ptr(), host=False)
+        if world > 1:
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM)                         # the one collective of C3
+        out = acc.cpu().numpy()
+        tot, nan_tot = out[:-1].view(np.uint64), int(out[-1])
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
     pairs_mine = pairs_of_blocks(N, mine)

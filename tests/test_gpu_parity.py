@@ -266,6 +266,24 @@ def test_allpairs_histogram_small():
                 assert np.abs(hist_t.astype(np.int64) - want).sum() <= 2 * int(near_edge.sum())
 
 
+def test_allpairs_accumulate_equals_one_shot():
+    """Device-resident accumulation over row blocks (what the multi-GPU C3 driver does) == the one-shot histogram,
+    for the exact Spearman path (upper-triangle GEMM strips) and the Pearson tensor path."""
+    from coexpression_b200 import synth
+    from coexpression_b200.api import CoexContext
+    t = synth.make_table(2300, 200, seed=31)
+    with CoexContext() as ctx:
+        ctx.set_expression(t.X); ctx.prepare()
+        for ranked in (True, False):
+            want, want_nan = ctx.allpairs_histogram(ranked, 0, t.N, 4096)
+            blocks = [(0, 512), (512, 1408), (1408, t.N)]
+            for i, (r0, r1) in enumerate(blocks):
+                ctx.allpairs_accumulate(ranked, r0, r1, 4096, reset=(i == 0))
+            got, got_nan = ctx.allpairs_read(4096)
+            assert np.array_equal(got, want) and got_nan == want_nan
+            assert int(got.sum()) + got_nan == t.N * (t.N - 1) // 2
+
+
 def test_file_level_entry_point_matches_oracle(tmp_path):
     """The drop-in for `1-make-network.py -wd ... --all`: same inputs on disk (settings.txt, expression table,
     feature BED, correlation list, windowBed map files), same eight JSON objects per permutation."""
