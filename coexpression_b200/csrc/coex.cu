@@ -425,11 +425,16 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
     const int kRounds = 12;
     long long net_launches = 0;
     if (H > 0) {
-        const size_t gsmem = (size_t)T2max * 24;
-        COEX_CUDA(cudaFuncSetAttribute(net_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+        const size_t gsmem = (size_t)T2max * 36, lsmem = (size_t)T2max * 16;
+        COEX_CUDA(cudaFuncSetAttribute(net_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+        COEX_CUDA(cudaFuncSetAttribute(net_label_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
         COEX_CUDA(cudaFuncSetAttribute(net_removal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(T2max * 8)));
         COEX_TRY(stage_begin(c, ST_NETWORK));
-        net_group_kernel<<<K, kNetThreads, gsmem, st>>>(na);
+        net_sort_kernel<<<K, kNetThreads, gsmem, st>>>(na);
+        COEX_KCHECK(st);
+        net_pairs_kernel<<<(unsigned)((H * 32 + 255) / 256), 256, 0, st>>>(na, H);
+        COEX_KCHECK(st);
+        net_label_kernel<<<K, kNetThreads, lsmem, st>>>(na);
         COEX_KCHECK(st);
         net_rowsum_kernel<0><<<rs_blocks, rs_threads, 0, st>>>(na);
         COEX_KCHECK(st);
@@ -439,7 +444,7 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
         COEX_KCHECK(st);
         for (int r = 0; r < kRounds; ++r) COEX_TRY(pass2_round(r == kRounds - 1));
         COEX_TRY(density_tail());
-        net_launches = 4 + 3 * kRounds + (prm->noiter ? 4 : 5);
+        net_launches = 6 + 3 * kRounds + (prm->noiter ? 4 : 5);
         COEX_TRY(stage_end(c, net_launches));
     } else {
         COEX_CUDA(cudaMemsetAsync(d_ng, 0, K * sizeof(int), st));

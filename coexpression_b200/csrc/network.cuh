@@ -14,7 +14,7 @@
 
 namespace coex {
 
-constexpr int kNetThreads = 1024;   // net_group_kernel: one CTA per permutation, 32 warps share the in-cluster pairs
+constexpr int kNetThreads = 1024;   // net_sort_kernel / net_label_kernel: one CTA per permutation
 
 struct NetArgs {
     int K;
@@ -74,6 +74,15 @@ __device__ void bitonic_u64(unsigned long long *keys, int *idx, int P2) {
     }
 }
 
+__device__ __forceinline__ int perm_of(const long long *perm_off, int K, long long q) {
+    int lo = 0, hi = K;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (perm_off[mid] <= q) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
 __device__ __forceinline__ int uf_find(volatile int *parent, int x) {
     int p = parent[x];
     while (p != x) { x = p; p = parent[x]; }
@@ -112,13 +121,23 @@ __device__ double warp_correlation(const NetArgs &a, int ra, int rb, int lane) {
 }
 
 // ===========================================================================================
-// K4a  net_group_kernel: one CTA per permutation -- join_nearby (coexfunctions.py:277-316)
+// K4a  join_nearby (coexfunctions.py:277-316) in three kernels, so that the in-cluster correlations -- the expensive part,
+//      and very uneven: the real-data hit set is 2-3x larger than a permuted one -- are spread over the whole GPU:
+//   net_sort_kernel   one CTA per permutation: hits sorted by (chromosome, start); merge_ranges as two scans
+//   net_pairs_kernel  one WARP per sorted hit of ANY permutation: its later cluster partners -> correlation ->
+//                     bisect into the global list -> lock-free union-find (global memory), smaller name wins the root
+//   net_label_kernel  one CTA per permutation: roots, groups numbered by ascending label
 // ===========================================================================================
+// merge_ranges (coexfunctions.py:412-425) walks the sorted hits keeping `stop` = the largest end + soft_separation of the
+// current cluster and starts a new cluster when start > stop.  Because the hits are sorted by start and every earlier
+// cluster ended below the start that closed it, `stop` can be replaced by the prefix maximum over ALL earlier hits:
+// boundary after s-1  <=>  key[s] > max(ekey[0..s-1]).  That turns the sequential walk into a prefix-max scan and the
+// cluster ends into a suffix-min scan.
 __global__ void __launch_bounds__(kNetThreads)
-net_group_kernel(NetArgs a) {
+net_sort_kernel(NetArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int k = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const long long off = a.perm_off[k];
     const int P = (int)(a.perm_off[k + 1] - off);
     if (P < 2) {                     // individualscores empty -> no groups (1-make-network.py:333-338)
@@ -128,18 +147,13 @@ net_group_kernel(NetArgs a) {
     int P2 = 1;
     while (P2 < P) P2 <<= 1;
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);       // [P2]
-    unsigned long long *ekey = keys + a.P2max;                                          // [P2]
-    int *order = reinterpret_cast<int *>(ekey + a.P2max);                               // [P2]
-    int *clend = order + a.P2max;                                                       // [P2]
-    int *parent = reinterpret_cast<int *>(ekey);                                        // reuse after clustering
-    __shared__ int s_G;
-
+    unsigned long long *pm = keys + a.P2max;                                            // [P2] prefix max of ekey (ping)
+    unsigned long long *pm2 = pm + a.P2max;                                             // [P2] (pong)
+    int *order = reinterpret_cast<int *>(pm2 + a.P2max);                                // [P2]
+    int *nb = order + a.P2max;                                                          // [P2] next boundary (ping)
+    int *nb2 = nb + a.P2max;                                                            // [P2] (pong)
     const int *hits = a.hit_rows + off;
-    int *grp = a.group_of_hit + off;
-    int *label = a.group_label + off;
-    int *root = a.w_root + off;
 
-    // ---- (1) sort hits by (chromosome, start) ----------------------------------------------
     for (int p = tid; p < P2; p += kNetThreads) {
         if (p < P) {
             const int row = hits[p];
@@ -152,69 +166,110 @@ net_group_kernel(NetArgs a) {
     }
     __syncthreads();
     bitonic_u64(keys, order, P2);
+    for (int p = tid; p < P2; p += kNetThreads) {
+        unsigned long long e = 0;
+        if (p < P) {
+            const int row = hits[order[p]];
+            e = ((unsigned long long)a.chrom_id[row] << 40) | (unsigned long long)(a.feat_end[row] + a.softsep);
+        }
+        pm[p] = e;
+    }
+    __syncthreads();
+    // inclusive prefix maximum (Hillis-Steele, ping-pong)
+    unsigned long long *src = pm, *dst = pm2;
+    for (int o = 1; o < P2; o <<= 1) {
+        for (int p = tid; p < P2; p += kNetThreads) dst[p] = (p >= o) ? max(src[p], src[p - o]) : src[p];
+        __syncthreads();
+        unsigned long long *t = src; src = dst; dst = t;
+    }
+    // boundary after s  <=>  s == P-1 or key[s+1] > prefix max up to s;  nb[s] = s if boundary else "infinity"
+    for (int p = tid; p < P2; p += kNetThreads)
+        nb[p] = (p < P && (p == P - 1 || keys[p + 1] > src[p])) ? p : 0x7fffffff;
+    __syncthreads();
+    // suffix minimum: first boundary at or after s
+    int *ns = nb, *nd = nb2;
+    for (int o = 1; o < P2; o <<= 1) {
+        for (int p = tid; p < P2; p += kNetThreads) nd[p] = (p + o < P2) ? min(ns[p], ns[p + o]) : ns[p];
+        __syncthreads();
+        int *t = ns; ns = nd; nd = t;
+    }
     for (int p = tid; p < P; p += kNetThreads) {
-        const int row = hits[order[p]];
-        ekey[p] = ((unsigned long long)a.chrom_id[row] << 40) |
-                  (unsigned long long)(a.feat_end[row] + a.softsep);
+        a.w_act[off + p] = order[p];                  // sorted position -> hit position
+        a.w_cursor[off + p] = ns[p] + 1;              // end (exclusive) of the cluster of sorted position p
+        a.w_gsize[off + p] = p;                       // union-find parent, indexed by hit position
     }
-    __syncthreads();
-    // ---- (2) merge_ranges: clusters of consecutive sorted hits -----------------------------
-    if (tid == 0) {
-        unsigned long long stop = ekey[0];
-        for (int s = 1; s < P; ++s) {
-            if (keys[s] > stop) { clend[s - 1] = -1; stop = ekey[s]; }   // boundary after s-1
-            else { clend[s - 1] = 0; stop = max(stop, ekey[s]); }
+}
+
+__global__ void __launch_bounds__(256)
+net_pairs_kernel(NetArgs a, long long H) {
+    const int lane = threadIdx.x & 31;
+    const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // one warp per sorted hit
+    if (q >= H) return;
+    const int k = perm_of(a.perm_off, a.K, q);
+    const long long off = a.perm_off[k];
+    const int P = (int)(a.perm_off[k + 1] - off);
+    if (P < 2) return;
+    const int s = (int)(q - off);
+    const int cend = a.w_cursor[off + s];
+    if (cend <= s + 1) return;                        // last hit of its cluster
+    const int *hits = a.hit_rows + off;
+    const int *order = a.w_act + off;
+    volatile int *parent = a.w_gsize + off;
+    const int ha = order[s];
+    const int ra = hits[ha];
+    // the warp walks its partners t in batches of 32: the correlations of the batch are formed cooperatively, then
+    // every lane bisects its own pair into the global list (32 independent chains) and links the two trees
+    for (int t0 = s + 1; t0 < cend; t0 += 32) {
+        const int nbat = min(32, cend - t0);
+        double rmine = 0.0;
+        for (int b = 0; b < nbat; ++b) {
+            const double r = warp_correlation(a, ra, hits[order[t0 + b]], lane);
+            if (lane == b) rmine = r;
         }
-        int end = P;
-        for (int s = P - 1; s >= 0; --s) {
-            const bool boundary_after = (s == P - 1) || (clend[s] == -1);
-            if (boundary_after) end = s + 1;
-            clend[s] = end;
-        }
-    }
-    __syncthreads();
-    for (int p = tid; p < P; p += kNetThreads) parent[p] = p;     // indexed by hit position
-    __syncthreads();
-    // ---- (3) in-cluster pairs -> edges -> union-find (smaller name wins the root) ----------
-    // A warp owns sorted position s and walks its partners t in batches of 32: the correlations
-    // of the batch are formed cooperatively, then every lane bisects its own pair into the
-    // global list (32 independent chains) and links the two trees.
-    for (int s = warp; s < P; s += kNetThreads / 32) {
-        const int ha = order[s];
-        const int ra = hits[ha];
-        const int cend = clend[s];
-        for (int t0 = s + 1; t0 < cend; t0 += 32) {
-            const int nb = min(32, cend - t0);
-            double rmine = 0.0;
-            for (int b = 0; b < nb; ++b) {
-                const double r = warp_correlation(a, ra, hits[order[t0 + b]], lane);
-                if (lane == b) rmine = r;
-            }
-            if (lane < nb) {
-                const int hb = order[t0 + lane];
-                const long long idx = lower_bound_dev(a.glist, a.glist_len, rmine);
-                const double p1 = 1.0 - (double)idx / (double)a.glist_len;
-                double p = p1;
-                if (a.anticor) p = fmin(p1, (double)idx / (double)a.glist_len);
-                if (p < a.pvtj) {
-                    int x = ha, y = hb;
-                    while (true) {
-                        x = uf_find(parent, x);
-                        y = uf_find(parent, y);
-                        if (x == y) break;
-                        // attach the root with the larger name under the smaller one
-                        if (a.name_rank[hits[x]] < a.name_rank[hits[y]]) { const int tmp = x; x = y; y = tmp; }
-                        if (atomicCAS(&parent[x], x, y) == x) break;
-                    }
+        if (lane < nbat) {
+            const int hb = order[t0 + lane];
+            const long long idx = lower_bound_dev(a.glist, a.glist_len, rmine);
+            const double p1 = 1.0 - (double)idx / (double)a.glist_len;
+            double p = p1;
+            if (a.anticor) p = fmin(p1, (double)idx / (double)a.glist_len);
+            if (p < a.pvtj) {
+                int x = ha, y = hb;
+                while (true) {
+                    x = uf_find(parent, x);
+                    y = uf_find(parent, y);
+                    if (x == y) break;
+                    // attach the root with the larger name under the smaller one
+                    if (a.name_rank[hits[x]] < a.name_rank[hits[y]]) { const int tmp = x; x = y; y = tmp; }
+                    if (atomicCAS(const_cast<int *>(&parent[x]), x, y) == x) break;
                 }
             }
-            __syncwarp();
         }
+        __syncwarp();
     }
-    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kNetThreads)
+net_label_kernel(NetArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int k = blockIdx.x;
+    const int tid = threadIdx.x;
+    const long long off = a.perm_off[k];
+    const int P = (int)(a.perm_off[k + 1] - off);
+    if (P < 2) return;
+    int P2 = 1;
+    while (P2 < P) P2 <<= 1;
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);       // [P2]
+    int *order = reinterpret_cast<int *>(keys + a.P2max);                               // [P2]
+    int *gnum = order + a.P2max;                                                        // [P2] group number of a root
+    __shared__ int s_G;
+    const int *hits = a.hit_rows + off;
+    int *grp = a.group_of_hit + off;
+    int *label = a.group_label + off;
+    int *root = a.w_root + off;
+    volatile int *parent = a.w_gsize + off;
     for (int p = tid; p < P; p += kNetThreads) root[p] = uf_find(parent, p);
     __syncthreads();
-    // ---- (4) groups numbered in ascending label order --------------------------------------
+    // groups numbered in ascending label order (label = smallest member name = the root)
     for (int p = tid; p < P2; p += kNetThreads) {
         const bool is_root = (p < P) && (root[p] == p);
         keys[p] = is_root ? (unsigned long long)(unsigned)a.name_rank[hits[p]] : ~0ULL;
@@ -226,13 +281,13 @@ net_group_kernel(NetArgs a) {
     for (int p = tid; p < P; p += kNetThreads) {
         if (keys[p] != ~0ULL) {
             label[p] = order[p];
-            clend[order[p]] = p;               // group number of a root, indexed by hit position
+            gnum[order[p]] = p;                // group number of a root, indexed by hit position
             atomicAdd(&s_G, 1);
         }
     }
     __syncthreads();
     const int G = s_G;
-    for (int p = tid; p < P; p += kNetThreads) grp[p] = clend[root[p]];
+    for (int p = tid; p < P; p += kNetThreads) grp[p] = gnum[root[p]];
     for (int g = tid; g < P; g += kNetThreads) { a.w_best[off + g] = 0ULL; a.w_cand[off + g] = ~0ULL; }
     if (tid == 0) { a.n_groups[k] = G; a.w_state[k] = 1; }
 }
@@ -243,15 +298,6 @@ net_group_kernel(NetArgs a) {
 // the 32 lanes fetch 32 consecutive addends, lane order is then folded in with shuffles.
 // Skipped addends are replaced by +0.0, which leaves a non-negative running sum bit-identical.
 // ===========================================================================================
-__device__ __forceinline__ int perm_of(const long long *perm_off, int K, long long q) {
-    int lo = 0, hi = K;
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (perm_off[mid] <= q) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-
 // Ordered row sums, shared by pass 1, pass 2 and the density / removal sums.  A warp owns kRsRows
 // consecutive rows of ONE permutation.  For every chunk of 32 columns the warp fetches, row by
 // row, the 32 addends (lane = column: coalesced for pass 1, a near-contiguous gather of winner
