@@ -398,11 +398,8 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
     COEX_CUDA(cudaMemcpyAsync(c->d_warp_off.p, warp_off.data(), (K + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
     na.warp_off = c->d_warp_off.p;
     const unsigned rs_blocks = (unsigned)((warp_off[K] + kRsWarps - 1) / kRsWarps), rs_threads = kRsWarps * 32;
-    const unsigned thread_blocks = (unsigned)((H + 255) / 256);
     auto pass2_round = [&](bool last) -> int {
         net_rowsum_kernel<1><<<rs_blocks, rs_threads, 0, st>>>(na);
-        COEX_KCHECK(st);
-        net_pick_kernel<<<thread_blocks, 256, 0, st>>>(na, H, 0);
         COEX_KCHECK(st);
         if (last) COEX_CUDA(cudaMemsetAsync(na.w_flags, 0, sizeof(int), st));
         net_commit_kernel<<<K, 256, 0, st>>>(na, 0);
@@ -438,13 +435,11 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
         COEX_KCHECK(st);
         net_rowsum_kernel<0><<<rs_blocks, rs_threads, 0, st>>>(na);
         COEX_KCHECK(st);
-        net_pick_kernel<<<thread_blocks, 256, 0, st>>>(na, H, 1);
-        COEX_KCHECK(st);
         net_commit_kernel<<<K, 256, 0, st>>>(na, 1);
         COEX_KCHECK(st);
         for (int r = 0; r < kRounds; ++r) COEX_TRY(pass2_round(r == kRounds - 1));
         COEX_TRY(density_tail());
-        net_launches = 6 + 3 * kRounds + (prm->noiter ? 4 : 5);
+        net_launches = 5 + 2 * kRounds + (prm->noiter ? 4 : 5);
         COEX_TRY(stage_end(c, net_launches));
     } else {
         COEX_CUDA(cudaMemsetAsync(d_ng, 0, K * sizeof(int), st));
@@ -469,7 +464,7 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
         if (flag) {
             for (int guard = 0; flag && guard < 8192 + 2; ++guard) {
                 COEX_TRY(pass2_round(true));
-                c->launches += 3;
+                c->launches += 2;
                 COEX_CUDA(cudaStreamSynchronize(st));
                 COEX_CUDA(cudaMemcpy(&flag, na.w_flags, sizeof(int), cudaMemcpyDeviceToHost));
             }

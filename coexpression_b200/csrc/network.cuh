@@ -432,24 +432,8 @@ net_rowsum_kernel(NetArgs a) {
     }
 }
 
-// argmax tie-break: among the members reaching the group's best sum, the smallest name
-__global__ void __launch_bounds__(256)
-net_pick_kernel(NetArgs a, long long H, int first) {
-    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= H) return;
-    const int k = perm_of(a.perm_off, a.K, q);
-    if (!a.w_state[k]) return;
-    const long long off = a.perm_off[k];
-    if (a.perm_off[k + 1] - off < 2) return;
-    const int gi = a.group_of_hit[q];
-    // pass-2 rounds recompute the members of multi-member groups behind the frontier only
-    if (!first && (a.w_gsize[off + gi] < 2 || gi <= a.w_front[k])) return;
-    if ((unsigned long long)__double_as_longlong(a.w_s1[q]) == a.w_best[off + gi])
-        atomicMin(&a.w_cand[off + gi],
-                  ((unsigned long long)(unsigned)a.name_rank[a.hit_rows[q]] << 32) | (unsigned)(q - off));
-}
-
-// one CTA per permutation: commit the picked winners.
+// one CTA per permutation: pick and commit the winners.  Pick = argmax with the tie-break of the oracle: among the
+// members reaching the group's best sum (w_best, atomicMax of the row-sum kernel), the smallest name.
 // first != 0: pass-1 winners (w1 + working copy); it also counts the members of every group and lists the hits of
 // the multi-member groups by ascending group (the only rows pass 2 has to iterate on).
 // Otherwise one fixed-point round of pass 2.  Pass 2 is sequential in the reference (Gauss-Seidel over groups, quirk
@@ -470,6 +454,20 @@ net_commit_kernel(NetArgs a, int first) {
     const int *grp = a.group_of_hit + off;
     __shared__ int s_part[256];
     __shared__ int s_first;
+    {   // pick: pass 1 looks at every hit, a pass-2 round at the rows it recomputed (multi-member groups behind the frontier)
+        const int nrows = first ? P : a.w_actn[k];
+        const int front0 = first ? -1 : a.w_front[k];
+        for (int i = threadIdx.x; i < nrows; i += blockDim.x) {
+            const int p = first ? i : a.w_act[off + i];
+            const int gi = grp[p];
+            if (gi <= front0) continue;
+            if ((unsigned long long)__double_as_longlong(a.w_s1[off + p]) == a.w_best[off + gi])
+                atomicMin(&a.w_cand[off + gi],
+                          ((unsigned long long)(unsigned)a.name_rank[a.hit_rows[off + p]] << 32) | (unsigned)p);
+        }
+        __threadfence_block();
+        __syncthreads();
+    }
     if (first) {
         for (int g = threadIdx.x; g < G; g += blockDim.x) {
             const int w = (int)(a.w_cand[off + g] & 0xffffffffULL);
