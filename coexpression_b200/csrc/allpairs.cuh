@@ -54,7 +54,9 @@ static int pearson_pack(coex_ctx *c) {
     if (c->z_digits == D) return 0;
     const size_t plane = (size_t)c->N_pad * c->n_pad;
     COEX_TRY(c->z_planes.reserve(plane * D)); COEX_TRY(c->z_ok.reserve(c->N_pad)); COEX_TRY(c->z_l1.reserve(c->N_pad));
-    COEX_TRY(c->z_inv_s.reserve(c->N_pad));
+    COEX_TRY(c->z_inv_s.reserve(c->N_pad)); COEX_TRY(c->z_valid.reserve(c->N_pad)); COEX_TRY(c->z_ninv.reserve(1));
+    COEX_CUDA(cudaMemsetAsync(c->z_valid.p, 0, c->N_pad * sizeof(float), c->stream));
+    COEX_CUDA(cudaMemsetAsync(c->z_ninv.p, 0, sizeof(int), c->stream));
     COEX_CUDA(cudaMemsetAsync(c->z_inv_s.p, 0, c->N_pad * sizeof(double), c->stream));
     COEX_CUDA(cudaMemsetAsync(c->z_planes.p, 0, plane * D, c->stream));
     COEX_CUDA(cudaMemsetAsync(c->z_ok.p, 0, c->N_pad, c->stream));
@@ -62,10 +64,10 @@ static int pearson_pack(coex_ctx *c) {
     const unsigned blocks = (unsigned)((c->N * 32 + 255) / 256);
     if (D == 3)
         pearson_pack_kernel<3><<<blocks, 256, 0, c->stream>>>(c->raw, c->N, c->n, c->n_pad, c->raw_sum.p, c->raw_mean.p, c->raw_xx.p,
-                                                            c->z_planes.p, (long long)plane, c->z_ok.p, c->z_l1.p, c->z_inv_s.p);
+                                                            c->z_planes.p, (long long)plane, c->z_ok.p, c->z_l1.p, c->z_inv_s.p, c->z_valid.p, c->z_ninv.p);
     else
         pearson_pack_kernel<4><<<blocks, 256, 0, c->stream>>>(c->raw, c->N, c->n, c->n_pad, c->raw_sum.p, c->raw_mean.p, c->raw_xx.p,
-                                                            c->z_planes.p, (long long)plane, c->z_ok.p, c->z_l1.p, c->z_inv_s.p);
+                                                            c->z_planes.p, (long long)plane, c->z_ok.p, c->z_l1.p, c->z_inv_s.p, c->z_valid.p, c->z_ninv.p);
     COEX_KCHECK(c->stream);
     c->launches += 1;
     c->z_digits = D;

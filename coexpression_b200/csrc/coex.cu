@@ -81,6 +81,7 @@ static int prepare_impl(coex_ctx *c) {
 // de-duplicated Spearman null: unique hit rows -> GEMM strips -> count_dedup_kernel
 // ------------------------------------------------------------------------------------------
 static int run_strip_gemm(coex_ctx *c, const int *d_rows, long long nq, long long nq_pad);
+static int run_strip_gemm_pearson(coex_ctx *c, const int *d_rows, long long nq, long long nq_pad, long long a_rows);
 
 static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const long long *perm_off,
                                const int *d_hits, int Pmax, double *d_sc, long long *d_cn) {
@@ -90,7 +91,10 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     const bool tdbg = getenv("COEX_HOST_DEBUG") != nullptr;
     auto now_us = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
     const double t_start = now_us();
-    const bool rows_kernel = (c->count_mode == 2);
+    const bool pearson = (prm->measure == 1);
+    const int D = c->pearson_digits;
+    if (pearson) COEX_TRY(pearson_pack(c));
+    const bool rows_kernel = (c->count_mode == 2) && !pearson;
     const int Tcap = rows_kernel ? std::max(4096, (int)round_up(Pmax, 512))
                                  : std::max(kDdBuckets / 2, (int)round_up(Pmax, 256));   // 2*Tcap >= buckets: the bucket cursors alias thr32|hist
     const int Qcap = kPlanQcap;
@@ -124,11 +128,15 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     const long long U = h_meta[0];
     // ---- strips of unique rows ------------------------------------------------------------------------
     const long long ld = c->N_pad;
-    long long Us = (c->strip_mb << 20) / (ld * 4);
+    long long Us = (c->strip_mb << 20) / (ld * (pearson ? 8 : 4));     // Pearson: the float r strip + the int32 Spearman strip of the statistics
     Us = std::max<long long>(256, Us / 256 * 256);
     Us = std::min<long long>(Us, round_up(U, 256));
     COEX_TRY(c->strip.reserve((size_t)Us * ld));
     COEX_TRY(c->a_hi.reserve((size_t)Us * c->n_pad)); COEX_TRY(c->a_lo.reserve((size_t)Us * c->n_pad));
+    if (pearson) {
+        COEX_TRY(c->strip_f32.reserve((size_t)Us * ld));
+        COEX_TRY(c->za_planes.reserve((size_t)D * Us * c->n_pad)); COEX_TRY(c->za_inv_s.reserve((size_t)Us));
+    }
     COEX_TRY(c->pl_nitems.reserve((size_t)U + 1)); COEX_TRY(c->pl_itemoff.reserve((size_t)U + 2));
     COEX_TRY(c->dd_items.reserve((size_t)(H + 1) * sizeof(DedupItem)));       // at most one item per query
     const unsigned ub = (unsigned)((U + 255) / 256);
@@ -147,7 +155,8 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     std::vector<long long> strip_item_begin((size_t)n_strips + 1);
     COEX_CUDA(cudaMemcpyAsync(strip_item_begin.data(), c->pl_bounds.p, ((size_t)n_strips + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
     c->launches += 7;
-    const int bm_words = (N <= 262144) ? (int)((N + 31) / 32) : 0;     // hit-column bitmap (<= 32 KB: two CTAs per SM stay resident)
+    // hit-column bitmap (<= 32 KB: two CTAs per SM stay resident); Pearson null: a hit column's value is not its (Spearman) statistic
+    const int bm_words = (!pearson && N <= 262144) ? (int)((N + 31) / 32) : 0;
     if (tdbg) fprintf(stderr, "[coex host] dedupe plan (device): %.0f us on the host incl. one sync (H=%lld U=%lld)\n", now_us() - t_start, H, U);
     const int claim = (bm_words > 0 && bm_words <= 2048) ? 1 : 0;      // <= 8 KB for the second bitmap
     const size_t smem = rows_kernel ? rows_smem_bytes(Tcap, Qcap) : dedup_smem_bytes(Tcap, Qcap, bm_words, claim);
@@ -157,8 +166,13 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
         COEX_CUDA(cudaFuncSetAttribute(count_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_rows_kernel, kCrThreads, smem));
     } else {
-        COEX_CUDA(cudaFuncSetAttribute(count_dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_dedup_kernel, kDdThreads, smem));
+        if (pearson) {
+            COEX_CUDA(cudaFuncSetAttribute(count_dedup_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_dedup_kernel<true>, kDdThreads, smem));
+        } else {
+            COEX_CUDA(cudaFuncSetAttribute(count_dedup_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_dedup_kernel<false>, kDdThreads, smem));
+        }
     }
     const int grid_max = std::max(1, per_sm) * c->sm_count;
     if (rows_kernel) {
@@ -176,7 +190,8 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     size_t s_idx = 0;
     for (long long u0 = 0; u0 < U; u0 += Us, ++s_idx) {
         const long long nu = std::min(Us, U - u0);
-        COEX_TRY(run_strip_gemm(c, c->dd_uniq.p + u0, nu, round_up(nu, 256)));
+        COEX_TRY(run_strip_gemm(c, c->dd_uniq.p + u0, nu, round_up(nu, 256)));      // exact Spearman sums (statistics in both modes, Q2)
+        if (pearson) COEX_TRY(run_strip_gemm_pearson(c, c->dd_uniq.p + u0, nu, round_up(nu, 256), Us));
         if (s_idx == 0) COEX_CUDA(cudaStreamSynchronize(st));        // second (and last) read-back of the plan; the first GEMM is queued already
         const DedupItem *items_s = reinterpret_cast<const DedupItem *>(c->dd_items.p) + strip_item_begin[s_idx];
         const int n_items_s = (int)(strip_item_begin[s_idx + 1] - strip_item_begin[s_idx]);
@@ -200,7 +215,14 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
             da.Tcap = Tcap; da.Qcap = Qcap; da.bm_words = bm_words; da.claim = claim;
             da.R = std::min(1.0, std::max(0.05, 8.0 / std::sqrt((double)std::max(c->n, 2)))); da.g_thr = c->dd_gthr.p; da.g_org = c->dd_gorg.p;
             da.score_tab = c->dd_tab.p; da.phase_clk = dbg ? phase.p : nullptr;
-            count_dedup_kernel<<<grid, kDdThreads, smem, st>>>(da);
+            if (pearson) {
+                da.eps_row = c->z_valid.p;
+                da.strip_f32 = c->strip_f32.p; da.raw = c->raw; da.raw_sum = c->raw_sum.p; da.raw_mean = c->raw_mean.p;
+                da.raw_xx = c->raw_xx.p; da.n = c->n; da.icol = c->z_valid.p; da.n_degenerate = c->z_ninv.p;
+                count_dedup_kernel<true><<<grid, kDdThreads, smem, st>>>(da);
+            } else {
+                count_dedup_kernel<false><<<grid, kDdThreads, smem, st>>>(da);
+            }
         }
         COEX_KCHECK(st);
         COEX_TRY(stage_end(c, 1));
@@ -243,6 +265,39 @@ static int run_strip_gemm(coex_ctx *c, const int *d_rows, long long nq, long lon
                                                          c->strip.p, c->N_pad);
         COEX_CUDA(cudaGetLastError());
     }
+    COEX_TRY(stage_end(c, 1));
+    return 0;
+}
+
+__global__ void gather_f64_kernel(const double *__restrict__ src, const int *__restrict__ rows, long long nq, long long nq_pad,
+                                  double *__restrict__ dst) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nq_pad) dst[t] = (t < nq) ? src[rows[t]] : 0.0;
+}
+
+// Pearson r strip of arbitrary query rows on the tensor cores: gather their digit planes, D x D int8 products
+static int run_strip_gemm_pearson(coex_ctx *c, const int *d_rows, long long nq, long long nq_pad, long long a_rows) {
+    const int D = c->pearson_digits;
+    const size_t plane = (size_t)c->N_pad * c->n_pad, a_plane = (size_t)a_rows * c->n_pad;
+    COEX_TRY(stage_begin(c, ST_GATHER));
+    const long long total = nq_pad * (c->n_pad >> 4);
+    const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)c->sm_count * 16);
+    for (int d = 0; d < D; d += 2) {
+        const int d2 = std::min(d + 1, D - 1);
+        gather_rows_kernel<<<blocks, 256, 0, c->stream>>>(c->z_planes.p + d * plane, c->z_planes.p + d2 * plane, c->n_pad, d_rows, nq, nq_pad,
+                                                         c->za_planes.p + d * a_plane, c->za_planes.p + d2 * a_plane);
+        COEX_CUDA(cudaGetLastError());
+    }
+    gather_f64_kernel<<<(unsigned)((nq_pad + 255) / 256), 256, 0, c->stream>>>(c->z_inv_s.p, d_rows, nq, nq_pad, c->za_inv_s.p);
+    COEX_CUDA(cudaGetLastError());
+    COEX_TRY(stage_end(c, (D + 1) / 2 + 1));
+    COEX_TRY(stage_begin(c, ST_GEMM));
+    if (D == 3)
+        COEX_TRY(tc_gemm_digits_ab<3>(c, c->za_planes.p, (long long)a_plane, a_rows, c->za_inv_s.p, c->z_planes.p, (long long)plane, 0, nq_pad,
+                                      nullptr, c->N_pad, c->z_inv_s.p, 0, c->strip_f32.p));
+    else
+        COEX_TRY(tc_gemm_digits_ab<4>(c, c->za_planes.p, (long long)a_plane, a_rows, c->za_inv_s.p, c->z_planes.p, (long long)plane, 0, nq_pad,
+                                      nullptr, c->N_pad, c->z_inv_s.p, 0, c->strip_f32.p));
     COEX_TRY(stage_end(c, 1));
     return 0;
 }
@@ -316,19 +371,26 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
             long long Hs = (c->strip_mb << 20) / (ld * elt);
             Hs = std::max<long long>(256, Hs / 256 * 256);
             Hs = std::min<long long>(Hs, round_up(H, 256));
+            // -cm Pearson on the tensor cores: de-duplicated like Spearman, the tensor r is a filter and the reference's
+            // in-order arithmetic decides every value it cannot (count mode 1 / pearson mode 1 keep the exact strip)
+            const bool pearson_dedup = (prm->measure == 1 && c->count_mode != 1 && c->pearson_mode == 0);
             if (prm->measure == 0) {
-                COEX_TRY(c->strip.reserve((size_t)Hs * ld));
-                COEX_TRY(c->a_hi.reserve((size_t)Hs * c->n_pad)); COEX_TRY(c->a_lo.reserve((size_t)Hs * c->n_pad));
+                if (c->count_mode == 1) {
+                    COEX_TRY(c->strip.reserve((size_t)Hs * ld));
+                    COEX_TRY(c->a_hi.reserve((size_t)Hs * c->n_pad)); COEX_TRY(c->a_lo.reserve((size_t)Hs * c->n_pad));
+                }
             } else {
-                COEX_TRY(c->strip_f64.reserve((size_t)Hs * ld));
-                StatArgs sa{c->d_perm_off.p, c->d_sc_off.p, d_hits, c->rank2.p, c->n, c->sx.p, c->rawsum_pos.p, d_sc};
-                COEX_TRY(stage_begin(c, ST_COUNT));
-                dim3 g((unsigned)std::min<long long>(((long long)Pmax * Pmax * 32 + 255) / 256, 4096), (unsigned)K);
-                stat_rank_kernel<<<g, 256, 0, st>>>(sa);
-                COEX_CUDA(cudaGetLastError());
-                COEX_TRY(stage_end(c, 1));
+                if (!pearson_dedup) {
+                    COEX_TRY(c->strip_f64.reserve((size_t)Hs * ld));
+                    StatArgs sa{c->d_perm_off.p, c->d_sc_off.p, d_hits, c->rank2.p, c->n, c->sx.p, c->rawsum_pos.p, d_sc};
+                    COEX_TRY(stage_begin(c, ST_COUNT));
+                    dim3 g((unsigned)std::min<long long>(((long long)Pmax * Pmax * 32 + 255) / 256, 4096), (unsigned)K);
+                    stat_rank_kernel<<<g, 256, 0, st>>>(sa);
+                    COEX_CUDA(cudaGetLastError());
+                    COEX_TRY(stage_end(c, 1));
+                }
             }
-            if (prm->measure == 0 && c->count_mode != 1) {
+            if ((prm->measure == 0 && c->count_mode != 1) || pearson_dedup) {
                 COEX_TRY(spearman_dedup_path(c, prm, K, perm_off, d_hits, Pmax, d_sc, d_cn));
             } else {
             const size_t smem = (size_t)T2max * 16;
@@ -478,7 +540,7 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
             COEX_CUDA(cudaStreamSynchronize(st));
         }
     }
-    if (prm->measure == 0 && prm->use_specific_p && c->gemm_mode == 0) COEX_TRY(tc_check_error(c));
+    if (prm->use_specific_p && c->gemm_mode == 0) COEX_TRY(tc_check_error(c));
     return 0;
 }
 
@@ -577,10 +639,11 @@ int coex_destroy(coex_ctx *c) {
     tc_destroy(c);
     c->raw_own.release(); c->raw_sum.release(); c->raw_mean.release(); c->raw_xx.release(); c->rawsum_pos.release();
     c->rank2.release(); c->u_hi.release(); c->u_lo.release(); c->suu.release(); c->sx.release();
+    c->z_valid.release(); c->z_ninv.release(); c->za_planes.release(); c->za_inv_s.release();
     c->z_planes.release(); c->z_ok.release(); c->z_l1.release(); c->z_inv_s.release();
     c->ap_hist.release(); c->feat_key.release(); c->feat_row.release(); c->pm_blob.release(); c->pm_counts.release(); c->pm_hits_tmp.release(); c->pm_off.release();
     c->chrom_id.release(); c->name_rank.release(); c->feat_start.release(); c->feat_end.release(); c->glist.release();
-    c->a_hi.release(); c->a_lo.release(); c->strip.release(); c->strip_f64.release();
+    c->a_hi.release(); c->a_lo.release(); c->strip.release(); c->strip_f64.release(); c->strip_f32.release();
     c->d_perm_off.release(); c->d_sc_off.release(); c->d_warp_off.release(); c->d_hits.release(); c->d_ngroups.release(); c->d_grp.release();
     c->d_label.release(); c->d_win.release(); c->w_root.release(); c->w_pos.release(); c->d_dens.release();
     c->d_aps.release(); c->d_scores.release(); c->w_s1.release(); c->w_d0.release(); c->w_w.release();

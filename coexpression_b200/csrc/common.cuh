@@ -113,6 +113,10 @@ struct coex_ctx {
     coex::DevBuf<unsigned char> z_ok;         // [N_pad] 0 where the reference yields NaN
     coex::DevBuf<float> z_l1;                 // [N_pad] |z|_1 (error bound of the quantisation)
     coex::DevBuf<double> z_inv_s;             // [N_pad] 1 / per-row quantisation scale
+    coex::DevBuf<float> z_valid;              // [N_pad] 1 where the Pearson null value of the row is defined, else 0
+    coex::DevBuf<int> z_ninv;                 // [1] rows with an undefined Pearson null value
+    coex::DevBuf<int8_t> za_planes;           // gathered query rows of the digit planes [D][Us, n_pad]
+    coex::DevBuf<double> za_inv_s;            // [Us]
     int z_digits = 0;                         // digits currently packed (0 = none)
     int pearson_digits = 4;                   // requested: 4 (default, |r - ref| ~ 1e-8) or 3 (faster, ~ 1e-6)
     int pearson_mode = 0;                     // 0 = tensor-core digits, 1 = in-order double strip (bit-exact)
@@ -135,6 +139,7 @@ struct coex_ctx {
     coex::DevBuf<int8_t> a_hi, a_lo;          // gathered query rows [Hs, n_pad]
     coex::DevBuf<int> strip;                  // S strip [Hs, N_pad] int32
     coex::DevBuf<double> strip_f64;           // Pearson null strip [Hs, N]
+    coex::DevBuf<float> strip_f32;            // Pearson null strip of the de-duplicated path [Us, N_pad] (tensor r as float)
     coex::DevBuf<long long> d_perm_off, d_sc_off, d_warp_off;
     coex::DevBuf<int> d_hits, d_ngroups, d_grp, d_label, d_win, w_root, w_pos, w_state;
     coex::DevBuf<int> w_gsize, w_cursor, w_act, w_actn, w_front;   // pass-2 active rows (network.cuh)

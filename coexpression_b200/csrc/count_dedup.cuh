@@ -68,7 +68,26 @@ struct DedupArgs {
     unsigned int *g_org;            // scratch [gridDim.x, 5, Tcap]: grouped | sorted origins, unsorted | grouped | sorted columns
     const double *score_tab;        // [N+1] edge score of every possible bisect index (len = N-1)
     unsigned long long *phase_clk;  // optional [8]: summed clock64 per phase over all CTAs (profiling aid)
+    // ---- PEARSON == true (`-cm Pearson`: Pearson null, Spearman statistic -- quirk Q2) ---------------------------
+    const float *strip_f32;         // [rows_in_strip, ld] tensor-core Pearson r of the unique rows (|error| <= eps); `strip` still holds the
+                                    // exact Spearman sums the statistics are read from
+    const double *raw;              // [N, n] raw table and its in-order row statistics: the reference's exact arithmetic
+    const double *raw_sum, *raw_mean, *raw_xx;
+    int n;
+    const float *eps_row;           // [N_pad] per-row share of the bound of |tensor r - exact r| (= icol in this mode; 0 = undefined row):
+                                    // |error(u, c)| <= eps_row[u] + eps_row[c] (digit quantisation)
 };
+
+// Pearson r of two table rows exactly as coexpression_v2.c:89-113 computes it (in-order double sums); NaN -> -99.
+__device__ __forceinline__ double pearson_exact_thread(const DedupArgs &a, long long ra, long long rb) {
+    if (a.raw_sum[ra] == 0.0 || a.raw_sum[rb] == 0.0) return -99.0;
+    const double *pa = a.raw + ra * a.n, *pb = a.raw + rb * a.n;
+    const double ma = a.raw_mean[ra], mb = a.raw_mean[rb];
+    double xy = 0.0;
+    for (int c = 0; c < a.n; ++c) xy = __dadd_rn(xy, __dmul_rn(__dsub_rn(pa[c], ma), __dsub_rn(pb[c], mb)));
+    const double r = __ddiv_rn(xy, __dmul_rn(sqrt(a.raw_xx[ra]), sqrt(a.raw_xx[rb])));
+    return (r != r) ? -99.0 : r;
+}
 
 __device__ __forceinline__ int dd_bucket64(double t, double R, double scale) {
     const double f = (t + R) * scale;
@@ -76,6 +95,24 @@ __device__ __forceinline__ int dd_bucket64(double t, double R, double scale) {
     return f >= (double)kDdBuckets ? kDdBuckets - 1 : (int)f;
 }
 
+// the same for a whole warp: coalesced loads, the products added in order through shuffles (every lane gets the result)
+__device__ __forceinline__ double pearson_exact_warp(const DedupArgs &a, long long ra, long long rb, int lane) {
+    if (a.raw_sum[ra] == 0.0 || a.raw_sum[rb] == 0.0) return -99.0;
+    const double *pa = a.raw + ra * a.n, *pb = a.raw + rb * a.n;
+    const double ma = a.raw_mean[ra], mb = a.raw_mean[rb];
+    double xy = 0.0;
+    for (int c0 = 0; c0 < a.n; c0 += 32) {
+        const int c = c0 + lane;
+        double prod = 0.0;
+        if (c < a.n) prod = __dmul_rn(__dsub_rn(pa[c], ma), __dsub_rn(pb[c], mb));
+        const int lim = min(32, a.n - c0);
+        for (int l = 0; l < lim; ++l) xy = __dadd_rn(xy, __shfl_sync(0xffffffffu, prod, l));
+    }
+    const double r = __ddiv_rn(xy, __dmul_rn(sqrt(a.raw_xx[ra]), sqrt(a.raw_xx[rb])));
+    return (r != r) ? -99.0 : r;
+}
+
+template <bool PEARSON>
 __global__ void __launch_bounds__(kDdThreads)
 count_dedup_kernel(DedupArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -114,6 +151,7 @@ count_dedup_kernel(DedupArgs a) {
         const int nq = item.qe - item.qb;
         const int u = a.uniq_rows[item.urow];
         const int *srow = a.strip + (long long)item.urow * a.ld;
+        const float *frow = PEARSON ? a.strip_f32 + (long long)item.urow * a.ld : nullptr;
         const double sxu = a.sx[u];
         const bool posu = a.rawsum_pos[u] != 0;
         __syncthreads();                                   // previous item fully retired
@@ -132,9 +170,21 @@ count_dedup_kernel(DedupArgs a) {
             q_P[ql] = P;
             q_sc[ql] = a.sc_off[lo] + (long long)i * P;
             double vi = -99.0;                             // null value at table column i (quirk Q1)
-            const double sxc = a.sx[i];
-            if (sxu != 0.0 && sxc != 0.0) vi = __ddiv_rn(0.25 * (double)srow[i], __dmul_rn(sxu, sxc));
+            if (PEARSON) {
+                vi = 0.0;                                  // filled in by one warp per query below
+            } else {
+                const double sxc = a.sx[i];
+                if (sxu != 0.0 && sxc != 0.0) vi = __ddiv_rn(0.25 * (double)srow[i], __dmul_rn(sxu, sxc));
+            }
             q_vi[ql] = vi;
+        }
+        if (PEARSON) {
+            __syncthreads();
+            for (int ql = tid >> 5; ql < nq; ql += kDdThreads / 32) {
+                const int i = q_i[ql];
+                const double vi = (i < a.N) ? pearson_exact_warp(a, u, i, tid & 31) : -99.0;
+                if ((tid & 31) == 0) q_vi[ql] = vi;
+            }
         }
         if (tid == 0) { s_T = 0; s_qn = 0; }
         for (int b = tid; b <= kDdBuckets; b += kDdThreads) lut[b] = 0;
@@ -174,7 +224,7 @@ count_dedup_kernel(DedupArgs a) {
             for (int e = 0; e < 4; ++e) {
                 if (!live[e]) continue;
                 double r = -99.0;
-                if (cc4[e] >= 0 && posu && guard[e]) {                      // coexfunctions.py:389
+                if (cc4[e] >= 0 && posu && guard[e]) {                      // coexfunctions.py:389 (the statistic is Spearman in both modes, Q2)
                     r = __ddiv_rn(0.25 * (double)sraw[e], __dmul_rn(sxu, sxc4[e]));
                     if (r != r) r = -99.0;                                  // coexfunctions.py:406-408
                 }
@@ -284,6 +334,7 @@ count_dedup_kernel(DedupArgs a) {
         DD_PHASE(2);
         // ---- D. stream the null values of table row u (fp32 fast path) -----------------------------
         const float iu = (float)(0.5 / sxu);
+        const float eps_u = PEARSON ? a.eps_row[u] : 0.0f;
         const long long N = a.N;
         // Four columns per thread are handled in lockstep (independent shared-memory chains overlap)
         // and the next 16-byte strip / norm loads are issued before the current ones are consumed.
@@ -297,7 +348,12 @@ count_dedup_kernel(DedupArgs a) {
             bool have = c0 < cend;
             int4 s4n = make_int4(0, 0, 0, 0);
             float4 w4n = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (have) { s4n = *reinterpret_cast<const int4 *>(srow + c0); w4n = *reinterpret_cast<const float4 *>(a.icol + c0); }
+            auto fetch = [&](long long cpos) {
+                // Pearson: the four floats travel in the same registers as the four exact integer sums of the Spearman strip
+                s4n = PEARSON ? *reinterpret_cast<const int4 *>(frow + cpos) : *reinterpret_cast<const int4 *>(srow + cpos);
+                w4n = *reinterpret_cast<const float4 *>(a.icol + cpos);
+            };
+            if (have) fetch(c0);
             while (have) {
                 const int sv[4] = {s4n.x, s4n.y, s4n.z, s4n.w};
                 const float wv[4] = {w4n.x, w4n.y, w4n.z, w4n.w};
@@ -305,7 +361,7 @@ count_dedup_kernel(DedupArgs a) {
                 const unsigned int skip4 = a.bm_words ? (bitmap[cc >> 5] >> (cc & 31)) & 15u : 0u;   // cc % 4 == 0
                 c0 += kDdThreads * 4;
                 have = c0 < cend;
-                if (have) { s4n = *reinterpret_cast<const int4 *>(srow + c0); w4n = *reinterpret_cast<const float4 *>(a.icol + c0); }
+                if (have) fetch(c0);
                 float v[4];
                 int p[4], lo[4], hi[4], len[4];
                 bool act[4];
@@ -313,7 +369,7 @@ count_dedup_kernel(DedupArgs a) {
                 for (int e = 0; e < 4; ++e) {
                     // zero-variance column: -99, counted in bulk; hit column: accounted exactly in step C'
                     act[e] = (wv[e] != 0.0f) && (cc + e < N) && !((skip4 >> e) & 1u);
-                    v[e] = __int2float_rn(sv[e]) * (iu * wv[e]);
+                    v[e] = PEARSON ? __int_as_float(sv[e]) : __int2float_rn(sv[e]) * (iu * wv[e]);
                     // bucket of v, possibly off by one in float: search the bucket and both neighbours
                     const float f = (v[e] + R_f) * bscale_f;
                     int bkt = (f > 0.0f) ? (int)f : 0;
@@ -339,14 +395,15 @@ count_dedup_kernel(DedupArgs a) {
                     // are at least a whole bucket away)
                     const float below = (p[e] > lo[e]) ? v[e] - thr32[p[e] - 1] : 1.0f;
                     const float above = (p[e] < hi[e]) ? thr32[p[e]] - v[e] : 1.0f;
-                    if (fminf(below, above) >= dd_delta(v[e])) {
+                    if (fminf(below, above) >= (PEARSON ? dd_delta(v[e]) + eps_u + wv[e] : dd_delta(v[e]))) {
                         atomicAdd(&hist[p[e]], 1u);
                     } else {
                         const int slot = atomicAdd(&s_qn, 1);
                         if (slot < kDdQueue) {
                             queue[slot] = (int)(cc + e);
                         } else {                                          // queue full: refine in place
-                            const double vv = __ddiv_rn(0.25 * (double)sv[e], __dmul_rn(sxu, a.sx[cc + e]));
+                            const double vv = PEARSON ? pearson_exact_thread(a, u, cc + e)
+                                                      : __ddiv_rn(0.25 * (double)srow[cc + e], __dmul_rn(sxu, a.sx[cc + e]));
                             const int bb = dd_bucket64(vv, a.R, bscale);
                             int pp = (int)lut[bb];
                             int ln = (int)lut[bb + 1] - pp;
@@ -362,9 +419,11 @@ count_dedup_kernel(DedupArgs a) {
             __syncthreads();
             // ---- E. exact refinement of the queued columns ------------------------------------------
             const int qn = min(s_qn, kDdQueue);
+            // (a warp per queued column with shuffle-ordered additions was measured slower than a thread per column)
             for (int x = tid; x < qn; x += kDdThreads) {
                 const int c = queue[x];
-                const double vv = __ddiv_rn(0.25 * (double)srow[c], __dmul_rn(sxu, a.sx[c]));
+                const double vv = PEARSON ? pearson_exact_thread(a, u, c)
+                                          : __ddiv_rn(0.25 * (double)srow[c], __dmul_rn(sxu, a.sx[c]));
                 const int bb = dd_bucket64(vv, a.R, bscale);
                 int pp = (int)lut[bb];
                 int len = (int)lut[bb + 1] - pp;

@@ -381,7 +381,8 @@ struct TcMaps8 { CUtensorMap a[4]; CUtensorMap b[4]; };
 template <int D>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_digits_tc_kernel(const __grid_constant__ TcMaps8 maps, double *__restrict__ out, long long ldo, int nkb,
-                      long long a_row0, const double *__restrict__ inv_s, int upper_only, int *err) {
+                      long long a_row0, const double *__restrict__ inv_s_a, const double *__restrict__ inv_s, int upper_only,
+                      float *__restrict__ out32, int *err) {
     using T = TcDigits<D>;
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -449,7 +450,8 @@ gemm_digits_tc_kernel(const __grid_constant__ TcMaps8 maps, double *__restrict__
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16);
             double *orow = out + (long long)(m0 + quarter * 32 + lane) * ldo + c0;
-            const double inv_a = inv_s[a_row0 + m0 + quarter * 32 + lane];
+            float *orow32 = out32 + (long long)(m0 + quarter * 32 + lane) * ldo + c0;      // out32 != nullptr: float strip instead
+            const double inv_a = inv_s_a[a_row0 + m0 + quarter * 32 + lane];
 #pragma unroll 1
             for (int cc = 0; cc < T::BN; cc += 16) {
                 long long S[16];
@@ -470,7 +472,8 @@ gemm_digits_tc_kernel(const __grid_constant__ TcMaps8 maps, double *__restrict__
                     double2 w;
                     w.x = (double)S[j] * (inv_a * inv_s[c0 + cc + j]);
                     w.y = (double)S[j + 1] * (inv_a * inv_s[c0 + cc + j + 1]);
-                    *reinterpret_cast<double2 *>(orow + cc + j) = w;
+                    if (out32) *reinterpret_cast<float2 *>(orow32 + cc + j) = make_float2((float)w.x, (float)w.y);
+                    else *reinterpret_cast<double2 *>(orow + cc + j) = w;
                 }
             }
         }
@@ -581,25 +584,36 @@ inline int tc_gemm_i8(coex_ctx *c, long long m_rows) {
     return tc_gemm_i8_ptrs(c, c->a_hi.p, c->a_lo.p, (long long)(c->a_hi.cap / c->n_pad), m_rows, c->strip.p, c->N_pad);
 }
 
-// r strip [m_rows, ldo] (double) = rows [a_row0, a_row0 + m_rows) of the D-digit planes x all rows
+// r strip [m_rows, ldo] (double) = rows [a_row0, a_row0 + m_rows) of the A digit planes x all rows of the table's planes.
+// a_planes == planes: rows of the table itself (all-pairs strips); otherwise a gathered copy of arbitrary query rows
+// ([D][a_rows, n_pad], a_plane_stride apart) with its own per-row 1 / scale.
 template <int D>
-inline int tc_gemm_digits(coex_ctx *c, const int8_t *planes, long long plane_stride, long long a_row0, long long m_rows,
-                          double *out, long long ldo, const double *inv_s, int upper_only) {
+inline int tc_gemm_digits_ab(coex_ctx *c, const int8_t *a_planes, long long a_plane_stride, long long a_rows,
+                             const double *inv_s_a, const int8_t *planes, long long plane_stride, long long a_row0,
+                             long long m_rows, double *out, long long ldo, const double *inv_s, int upper_only,
+                             float *out32 = nullptr) {
     using T = TcDigits<D>;
     TcState *t = nullptr;
     COEX_TRY(tc_state(c, &t));
     if (m_rows % kTcBM) COEX_FAIL("tc_gemm_digits: rows must be a multiple of 128");
     TcMaps8 maps;
     for (int d = 0; d < D; ++d) {
-        COEX_TRY(tc_encode(t, &maps.a[d], planes + d * plane_stride, c->N_pad, c->n_pad, 128));
+        COEX_TRY(tc_encode(t, &maps.a[d], a_planes + d * a_plane_stride, a_rows, c->n_pad, 128));
         COEX_TRY(tc_encode(t, &maps.b[d], planes + d * plane_stride, c->N_pad, c->n_pad, T::BN));
     }
     COEX_CUDA(cudaFuncSetAttribute(gemm_digits_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::kSmem));
     dim3 grid((unsigned)(m_rows / kTcBM), (unsigned)(c->N_pad / T::BN));
-    gemm_digits_tc_kernel<D><<<grid, kTcThreads, T::kSmem, c->stream>>>(maps, out, ldo, c->n_pad / kTcBK, a_row0, inv_s,
-                                                                       upper_only, t->d_err);
+    gemm_digits_tc_kernel<D><<<grid, kTcThreads, T::kSmem, c->stream>>>(maps, out, ldo, c->n_pad / kTcBK, a_row0, inv_s_a, inv_s,
+                                                                       upper_only, out32, t->d_err);
     COEX_CUDA(cudaGetLastError());
     return 0;
+}
+
+template <int D>
+inline int tc_gemm_digits(coex_ctx *c, const int8_t *planes, long long plane_stride, long long a_row0, long long m_rows,
+                          double *out, long long ldo, const double *inv_s, int upper_only) {
+    return tc_gemm_digits_ab<D>(c, planes, plane_stride, c->N_pad, inv_s, planes, plane_stride, a_row0, m_rows, out, ldo, inv_s,
+                                upper_only);
 }
 
 // non-zero if any tensor-core kernel of this context hit its bounded-wait limit

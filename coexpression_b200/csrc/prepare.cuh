@@ -225,7 +225,8 @@ __global__ void __launch_bounds__(256)
 pearson_pack_kernel(const double *__restrict__ raw, long long N, int n, int n_pad,
                     const double *__restrict__ rsum, const double *__restrict__ rmean,
                     const double *__restrict__ rxx, int8_t *__restrict__ planes, long long plane_stride,
-                    unsigned char *__restrict__ ok_out, float *__restrict__ l1_out, double *__restrict__ inv_s_out) {
+                    unsigned char *__restrict__ ok_out, float *__restrict__ l1_out, double *__restrict__ inv_s_out,
+                    float *__restrict__ valid_out, int *__restrict__ n_invalid) {
     const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= N) return;
@@ -272,6 +273,12 @@ pearson_pack_kernel(const double *__restrict__ raw, long long N, int n, int n_pa
     for (int o = 16; o > 0; o >>= 1) l1 += __shfl_xor_sync(0xffffffffu, l1, o);
     if (lane == 0) {
         ok_out[row] = ok ? 1 : 0;
+        // the count kernel's column mask (like icol of the Spearman path) AND the row's share of the error bound of the
+        // tensor-core r: |sum q_a q_b / (s_a s_b) - r| <= 0.5 |z_a|_1 / s_b + 0.5 |z_b|_1 / s_a + n / (4 s_a s_b), every s >= smin
+        // = 0.98 ZScale.  0.51 |z|_1 / smin + n / (8 smin^2), rounded up, > 0 for every defined row.
+        const double smin = 0.98 * ZScale<D>::s;
+        valid_out[row] = ok ? (float)(1.02 * (0.51 * (l1 / srow) / smin + (double)n / (8.0 * smin * smin)) + 1e-12) : 0.0f;
+        if (!ok) atomicAdd(n_invalid, 1);                   // rows whose Pearson null value is NaN -> -99 for every query
         l1_out[row] = (float)(l1 / srow);
         inv_s_out[row] = 1.0 / srow;
     }
