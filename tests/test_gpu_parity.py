@@ -534,3 +534,100 @@ def test_global_correlation_list_row_n2(tmp_path):
     assert np.array_equal(got, want) and np.array_equal(read_correlation_list(path), want)
     assert np.array_equal(again, want)
     assert len(fewer) == 1000 and np.all(np.isin(fewer, want))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [11, 12])
+def test_pearson_null_tensor_filter_against_oracle(seed):
+    """`-cm Pearson` (Pearson null, Spearman statistic -- quirk Q2) through the de-duplicated tensor-core path: the tensor
+    r is only a filter, so every bisect index must equal the oracle's (reference C arithmetic), including duplicated
+    rows (exact ties between null values), all-zero / constant rows and a dense cluster."""
+    from coexpression_b200 import synth
+    from coexpression_b200.api import CoexContext, Options
+    from coexpression_b200.results import perm_objects
+    from oracle import network_oracle as no
+    rng = np.random.default_rng(300 + seed)
+    N, n = int(rng.integers(400, 900)), int(rng.integers(20, 140))
+    t = synth.make_table(N, n, seed=400 + seed, zero_row_frac=0.02, dup_rows=10)
+    X = t.X.copy()
+    X[5] = 2.5                                         # constant row: Pearson and Spearman undefined
+    R = no.rank_rows(X)
+    ga = rng.integers(0, N, 6000).astype(np.int32); gb = rng.integers(0, N, 6000).astype(np.int32)
+    g = no.get_pearson(X, ga, gb)
+    glist = np.sort(np.where(np.isnan(g), -99.0, g))
+    hit_sets = []
+    for k in range(6):
+        h = rng.choice(N, size=int(rng.integers(2, 80)), replace=False)
+        if k == 0:
+            h = np.concatenate([[5], h])
+        hit_sets.append(np.unique(h)[rng.permutation(len(np.unique(h)))].astype(np.int32))
+    anticor = bool(seed % 2)
+    opts = Options(correlationmeasure="Pearson", anticorrelation=anticor, pval_to_join=0.3)
+    with CoexContext() as ctx:
+        ctx.set_expression(X); ctx.prepare()
+        ctx.set_features(t.chrom, t.start, t.end, t.names)
+        ctx.set_global_list(glist)
+        res = ctx.network_batch(hit_sets, opts, want_scores=True, want_counts=True)
+        ctx.set_count_mode("per_query")                # the bit-exact in-order strip
+        ref = ctx.network_batch(hit_sets, opts, want_scores=True, want_counts=True)
+    assert np.array_equal(res.counts, ref.counts) and np.array_equal(res.scores, ref.scores)
+    assert np.array_equal(res.group_density, ref.group_density)
+    for k, h in enumerate(hit_sets):
+        want = no.make_network(t.names, X, [t.names[r] for r in h], t.addresses(), glist.tolist(), Xrank=R, return_counts=True,
+                               correlationmeasure="Pearson", anticorrelation=anticor, pval_to_join=0.3)
+        got = perm_objects(res, k, t.names)
+        assert np.array_equal(res.count_matrix(k), want["_counts"]), (seed, k)
+        assert got["prom_to_join"] == want["prom_to_join"] and got["winners"] == want["winners"]
+        for grp, v in want["indmeasure"].items():
+            assert abs(got["indmeasure"][grp] - v) <= 1e-6
+
+
+@pytest.mark.gpu
+def test_c4_like_backcirc_anticorrelation_device_mapping():
+    """Config C4 in miniature: hit sets drawn on the DEVICE by the backcirc rule from a background file, reduced with -a;
+    the hit lists equal the restated reference arithmetic and the densities equal the oracle's."""
+    from coexpression_b200 import synth
+    from coexpression_b200.api import CoexContext, Options
+    from coexpression_b200.results import perm_objects
+    from oracle import network_oracle as no
+    from oracle import permute_oracle as po
+    t = synth.make_table(2500, 48, seed=61)
+    chromlist = list(t.chrom_len)
+    cr = po.chromrange_from_lengths(chromlist, t.chrom_len)
+    rng = np.random.default_rng(62)
+    snps = []
+    for r in rng.integers(0, t.N, size=90):
+        c = t.chrom[r]
+        snps.append((c, int(np.clip(t.start[r] + rng.integers(-3000, 3000), 1, t.chrom_len[c] - 2))))
+    snps = list(dict.fromkeys(snps))
+    backdict = {"%s_%s" % (c, a): po.get_gwad(c, a, cr) for c, a in snps}
+    for r in rng.integers(0, t.N, size=4000):           # background variants near features, so that permuted sets map
+        c = t.chrom[r]
+        a = int(np.clip(t.start[r] + rng.integers(-20000, 20000), 1, t.chrom_len[c] - 2))
+        backdict["%s_%s" % (c, a)] = po.get_gwad(c, a, cr)
+    sb = po.sorted_background(backdict)
+    background = [(k.split("_")[0], int(k.split("_")[1])) for k in sb]
+    shifts = [0] + [int(rng.random() * 10000000000) for _ in range(4)]
+    R = no.rank_rows(t.X)
+    ga, gb = synth.global_pair_indices(t.names, 15000, seed=63)
+    g = no.get_pearson(R, ga, gb)
+    glist = np.sort(np.where(np.isnan(g), -99.0, g))
+    opts = Options(anticorrelation=True)
+    with CoexContext() as ctx:
+        ctx.set_expression(t.X); ctx.prepare()
+        ctx.set_features(t.chrom, t.start, t.end, t.names)
+        ctx.set_global_list(glist)
+        hits = ctx.permute_map("backcirc", [c for c, _ in snps], [a for _, a in snps], shifts, chromlist, cr, 5000,
+                               background=background)
+        res = ctx.network_batch(hits, opts, want_counts=True)
+    for k, s in enumerate(shifts):
+        pos = po.circular_positions(snps, 0, cr, chromlist) if s == 0 else po.backcirc_positions(snps, s, sb)
+        want_rows = po.hit_rows(po.window_bed(pos, t.chrom, t.start, t.end, 5000))
+        assert hits[k].tolist() == want_rows and len(want_rows) > 5, (k, len(want_rows))
+        want = no.make_network(t.names, t.X, [t.names[r] for r in want_rows], t.addresses(), glist.tolist(), Xrank=R,
+                               return_counts=True, anticorrelation=True)
+        got = perm_objects(res, k, t.names)
+        assert np.array_equal(res.count_matrix(k), want["_counts"])
+        assert got["prom_to_join"] == want["prom_to_join"] and got["winners"] == want["winners"]
+        for grp, v in want["indmeasure"].items():
+            assert abs(got["indmeasure"][grp] - v) <= 1e-6
