@@ -20,6 +20,9 @@ import sys
 # libgomp reads OMP_NUM_THREADS when it is loaded (the reference sets it before LoadLibrary,
 # 0-prepare-coex.py:148 then :223), so this must precede every import that may load it.
 os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
+if ("--impl" in sys.argv and "reference" in sys.argv) or "--impl=reference" in sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm runs on rank 0 alone and must get every host core
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
 
 import argparse
 import json
