@@ -484,7 +484,7 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
     const int kRounds = 12;
     long long net_launches = 0;
     if (H > 0) {
-        const size_t gsmem = (size_t)T2max * 36, lsmem = (size_t)T2max * 16;
+        const size_t gsmem = (size_t)T2max * 24, lsmem = (size_t)T2max * 16;
         COEX_CUDA(cudaFuncSetAttribute(net_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
         COEX_CUDA(cudaFuncSetAttribute(net_label_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
         COEX_CUDA(cudaFuncSetAttribute(net_removal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(T2max * 8)));

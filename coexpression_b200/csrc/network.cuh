@@ -147,11 +147,10 @@ net_sort_kernel(NetArgs a) {
     int P2 = 1;
     while (P2 < P) P2 <<= 1;
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);       // [P2]
-    unsigned long long *pm = keys + a.P2max;                                            // [P2] prefix max of ekey (ping)
-    unsigned long long *pm2 = pm + a.P2max;                                             // [P2] (pong)
-    int *order = reinterpret_cast<int *>(pm2 + a.P2max);                                // [P2]
-    int *nb = order + a.P2max;                                                          // [P2] next boundary (ping)
-    int *nb2 = nb + a.P2max;                                                            // [P2] (pong)
+    unsigned long long *pm = keys + a.P2max;                                            // [P2] prefix max of ekey
+    int *order = reinterpret_cast<int *>(pm + a.P2max);                                 // [P2]
+    int *nb = order + a.P2max;                                                          // [P2] next boundary
+    constexpr int kPer = 8192 / kNetThreads;                                            // scan values per thread (P2 <= 8192)
     const int *hits = a.hit_rows + off;
 
     for (int p = tid; p < P2; p += kNetThreads) {
@@ -175,24 +174,37 @@ net_sort_kernel(NetArgs a) {
         pm[p] = e;
     }
     __syncthreads();
-    // inclusive prefix maximum (Hillis-Steele, ping-pong)
-    unsigned long long *src = pm, *dst = pm2;
+    // inclusive prefix maximum (Hillis-Steele in place: read, barrier, write, barrier)
     for (int o = 1; o < P2; o <<= 1) {
-        for (int p = tid; p < P2; p += kNetThreads) dst[p] = (p >= o) ? max(src[p], src[p - o]) : src[p];
+        unsigned long long v[kPer];
+#pragma unroll
+        for (int e = 0; e < kPer; ++e) {
+            const int p = tid + e * kNetThreads;
+            v[e] = (p < P2) ? ((p >= o) ? max(pm[p], pm[p - o]) : pm[p]) : 0ULL;
+        }
         __syncthreads();
-        unsigned long long *t = src; src = dst; dst = t;
+#pragma unroll
+        for (int e = 0; e < kPer; ++e) { const int p = tid + e * kNetThreads; if (p < P2) pm[p] = v[e]; }
+        __syncthreads();
     }
     // boundary after s  <=>  s == P-1 or key[s+1] > prefix max up to s;  nb[s] = s if boundary else "infinity"
     for (int p = tid; p < P2; p += kNetThreads)
-        nb[p] = (p < P && (p == P - 1 || keys[p + 1] > src[p])) ? p : 0x7fffffff;
+        nb[p] = (p < P && (p == P - 1 || keys[p + 1] > pm[p])) ? p : 0x7fffffff;
     __syncthreads();
     // suffix minimum: first boundary at or after s
-    int *ns = nb, *nd = nb2;
     for (int o = 1; o < P2; o <<= 1) {
-        for (int p = tid; p < P2; p += kNetThreads) nd[p] = (p + o < P2) ? min(ns[p], ns[p + o]) : ns[p];
+        int v[kPer];
+#pragma unroll
+        for (int e = 0; e < kPer; ++e) {
+            const int p = tid + e * kNetThreads;
+            v[e] = (p < P2) ? ((p + o < P2) ? min(nb[p], nb[p + o]) : nb[p]) : 0;
+        }
         __syncthreads();
-        int *t = ns; ns = nd; nd = t;
+#pragma unroll
+        for (int e = 0; e < kPer; ++e) { const int p = tid + e * kNetThreads; if (p < P2) nb[p] = v[e]; }
+        __syncthreads();
     }
+    int *ns = nb;
     for (int p = tid; p < P; p += kNetThreads) {
         a.w_act[off + p] = order[p];                  // sorted position -> hit position
         a.w_cursor[off + p] = ns[p] + 1;              // end (exclusive) of the cluster of sorted position p

@@ -631,3 +631,34 @@ def test_c4_like_backcirc_anticorrelation_device_mapping():
         assert got["prom_to_join"] == want["prom_to_join"] and got["winners"] == want["winners"]
         for grp, v in want["indmeasure"].items():
             assert abs(got["indmeasure"][grp] - v) <= 1e-6
+
+
+@pytest.mark.gpu
+def test_large_hit_set_shared_memory_limits():
+    """One hit set of 4500 regions (config C5 territory: wide -w windows): the kernels whose shared memory scales with the
+    hit count (statistics capacity of the count kernels, sort / scan buffers of join_nearby, removal) at a size beyond
+    4096, checked by the three independent count kernels agreeing on every index, score, group and density."""
+    from coexpression_b200 import synth
+    from coexpression_b200.api import CoexContext, Options
+    t = synth.make_table(9000, 24, seed=71)
+    rng = np.random.default_rng(72)
+    hits = [rng.choice(t.N, size=4500, replace=False).astype(np.int32), rng.choice(t.N, size=300, replace=False).astype(np.int32),
+            rng.choice(t.N, size=2, replace=False).astype(np.int32)]
+    ga, gb = synth.global_pair_indices(t.names, 30000, seed=73)
+    out = {}
+    with CoexContext() as ctx:
+        ctx.set_expression(t.X); ctx.prepare()
+        g = ctx.pairs(ga, gb, ranked=True)
+        ctx.set_global_list(np.sort(np.where(np.isnan(g), -99.0, g)))
+        ctx.set_features(t.chrom, t.start, t.end, t.names)
+        for mode in ("dedup", "per_query", "dedup_window"):
+            ctx.set_count_mode(mode)
+            out[mode] = ctx.network_batch(hits, Options(pval_to_join=0.01), want_scores=True, want_counts=True)
+    a = out["dedup"]
+    assert int(a.n_groups[0]) > 100
+    for other in ("per_query", "dedup_window"):
+        b = out[other]
+        assert np.array_equal(a.counts, b.counts), other
+        assert np.array_equal(a.scores, b.scores), other
+        assert np.array_equal(a.n_groups, b.n_groups) and np.array_equal(a.group_of_hit, b.group_of_hit)
+        assert np.array_equal(a.group_winner, b.group_winner) and np.array_equal(a.group_density, b.group_density)
