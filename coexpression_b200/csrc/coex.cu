@@ -95,6 +95,7 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     const int D = c->pearson_digits;
     if (pearson) COEX_TRY(pearson_pack(c));
     const bool rows_kernel = (c->count_mode == 2) && !pearson;
+    bool rank_mode = (c->count_mode == 3) && !pearson;      // 3 = forced; count mode 0 decides below (cost model)
     const int Tcap = rows_kernel ? std::max(4096, (int)round_up(Pmax, 512))
                                  : std::max(kDdBuckets / 2, (int)round_up(Pmax, 256));   // 2*Tcap >= buckets: the bucket cursors alias thr32|hist
     const int Qcap = kPlanQcap;
@@ -188,11 +189,58 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     const bool dbg = getenv("COEX_COUNT_DEBUG") != nullptr;
     if (dbg) { COEX_TRY(phase.reserve(8)); COEX_CUDA(cudaMemsetAsync(phase.p, 0, 8 * sizeof(unsigned long long), st)); }
     size_t s_idx = 0;
+    int rank_grid_max = 1;
+    long long c_sc_total = 0;
+    for (int k = 0; k < K; ++k) c_sc_total += (perm_off[k + 1] - perm_off[k]) * (perm_off[k + 1] - perm_off[k]);
     for (long long u0 = 0; u0 < U; u0 += Us, ++s_idx) {
         const long long nu = std::min(Us, U - u0);
         COEX_TRY(run_strip_gemm(c, c->dd_uniq.p + u0, nu, round_up(nu, 256)));      // exact Spearman sums (statistics in both modes, Q2)
         if (pearson) COEX_TRY(run_strip_gemm_pearson(c, c->dd_uniq.p + u0, nu, round_up(nu, 256), Us));
-        if (s_idx == 0) COEX_CUDA(cudaStreamSynchronize(st));        // second (and last) read-back of the plan; the first GEMM is queued already
+        if (s_idx == 0) {
+            COEX_CUDA(cudaStreamSynchronize(st));     // second (and last) read-back of the plan; the first GEMM is queued already
+            // Regime switch: when the hit sets are so large that the queries of a row carry more statistics than the row has
+            // columns, rank every strip row once (count_dedup_kernel<2>) and let the queries look their indices up.
+            const long long SCtot = c_sc_total;
+            const double cost_items = (double)strip_item_begin[(size_t)n_strips] * (double)N;
+            const double cost_rank = (double)U * (double)((N + kRankTcap - 1) / kRankTcap) * (double)N + 2.0 * (double)SCtot;
+            if (c->count_mode == 0 && !pearson && bm_words > 0 && cost_rank < 0.6 * cost_items) rank_mode = true;
+            if (rank_mode && bm_words == 0) COEX_FAIL("rank mode needs the hit-column bitmap (table of at most 262144 rows)");
+            if (tdbg) fprintf(stderr, "[coex host] count: %lld items, cost items %.3g vs rank %.3g -> %s\n", strip_item_begin[(size_t)n_strips],
+                              cost_items, cost_rank, rank_mode ? "rank mode" : "query items");
+        }
+        if (rank_mode) {
+            const int rclaim = (bm_words <= 2048) ? 1 : 0;
+            const size_t rsmem = dedup_smem_bytes(kRankTcap, Qcap, bm_words, rclaim);
+            if (s_idx == 0) {
+                COEX_CUDA(cudaFuncSetAttribute(count_dedup_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+                int rper = 1;
+                COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rper, count_dedup_kernel<2>, kDdThreads, rsmem));
+                rank_grid_max = std::max(1, rper) * c->sm_count;
+                COEX_TRY(c->dd_gthr.reserve((size_t)rank_grid_max * kRankTcap * 3)); COEX_TRY(c->dd_gorg.reserve((size_t)rank_grid_max * kRankTcap * 5));
+                COEX_TRY(c->rank_strip.reserve((size_t)Us * ld));
+            }
+            const int nchunk = (int)((N + kRankTcap - 1) / kRankTcap);
+            DedupArgs da{};
+            da.strip = c->strip.p; da.ld = ld; da.items = nullptr; da.n_items = (int)(nu * nchunk);
+            da.uniq_rows = c->dd_uniq.p + u0; da.qlist = c->dd_qlist.p; da.perm_off = c->d_perm_off.p; da.sc_off = c->d_sc_off.p;
+            da.K = K; da.hit_rows = d_hits; da.sx = c->sx.p; da.icol = c->icol.p; da.rawsum_pos = c->rawsum_pos.p; da.N = N;
+            da.n_degenerate = c->d_ndeg.p; da.anticor = prm->anticorrelation; da.scores = d_sc; da.counts = d_cn;
+            da.Tcap = kRankTcap; da.Qcap = Qcap; da.bm_words = bm_words; da.claim = rclaim;
+            da.R = std::min(1.0, std::max(0.05, 8.0 / std::sqrt((double)std::max(c->n, 2)))); da.g_thr = c->dd_gthr.p; da.g_org = c->dd_gorg.p;
+            da.score_tab = c->dd_tab.p; da.phase_clk = nullptr; da.rank_out = c->rank_strip.p;
+            COEX_TRY(stage_begin(c, ST_COUNT));
+            count_dedup_kernel<2><<<std::min(rank_grid_max, std::max(da.n_items, 1)), kDdThreads, rsmem, st>>>(da);
+            COEX_KCHECK(st);
+            RankScoreArgs rs{};
+            rs.strip = c->strip.p; rs.rank = c->rank_strip.p; rs.ld = ld; rs.uniq_rows = c->dd_uniq.p + u0; rs.ustart = c->pl_ustart.p + u0;
+            rs.qlist = c->dd_qlist.p; rs.q_perm = c->dd_qperm.p; rs.u_count = nu; rs.perm_off = c->d_perm_off.p; rs.sc_off = c->d_sc_off.p;
+            rs.hit_rows = d_hits; rs.sx = c->sx.p; rs.rawsum_pos = c->rawsum_pos.p; rs.N = N; rs.anticor = prm->anticorrelation;
+            rs.scores = d_sc; rs.counts = d_cn; rs.score_tab = c->dd_tab.p;
+            rank_score_kernel<<<(unsigned)std::min<long long>(H, (long long)c->sm_count * 16), 256, 0, st>>>(rs);
+            COEX_KCHECK(st);
+            COEX_TRY(stage_end(c, 2));
+            continue;
+        }
         const DedupItem *items_s = reinterpret_cast<const DedupItem *>(c->dd_items.p) + strip_item_begin[s_idx];
         const int n_items_s = (int)(strip_item_begin[s_idx + 1] - strip_item_begin[s_idx]);
         const int grid = std::min(grid_max, std::max(n_items_s, 1));
@@ -219,9 +267,9 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
                 da.eps_row = c->z_valid.p;
                 da.strip_f32 = c->strip_f32.p; da.raw = c->raw; da.raw_sum = c->raw_sum.p; da.raw_mean = c->raw_mean.p;
                 da.raw_xx = c->raw_xx.p; da.n = c->n; da.icol = c->z_valid.p; da.n_degenerate = c->z_ninv.p;
-                count_dedup_kernel<true><<<grid, kDdThreads, smem, st>>>(da);
+                count_dedup_kernel<1><<<grid, kDdThreads, smem, st>>>(da);
             } else {
-                count_dedup_kernel<false><<<grid, kDdThreads, smem, st>>>(da);
+                count_dedup_kernel<0><<<grid, kDdThreads, smem, st>>>(da);
             }
         }
         COEX_KCHECK(st);
@@ -390,7 +438,7 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
                     COEX_TRY(stage_end(c, 1));
                 }
             }
-            if ((prm->measure == 0 && c->count_mode != 1) || pearson_dedup) {
+            if ((prm->measure == 0 && c->count_mode != 1) || pearson_dedup) {   // (count mode 3 with -cm Pearson: plain de-duplicated path)
                 COEX_TRY(spearman_dedup_path(c, prm, K, perm_off, d_hits, Pmax, d_sc, d_cn));
             } else {
             const size_t smem = (size_t)T2max * 16;
@@ -643,7 +691,7 @@ int coex_destroy(coex_ctx *c) {
     c->z_planes.release(); c->z_ok.release(); c->z_l1.release(); c->z_inv_s.release();
     c->ap_hist.release(); c->feat_key.release(); c->feat_row.release(); c->pm_blob.release(); c->pm_counts.release(); c->pm_hits_tmp.release(); c->pm_off.release();
     c->chrom_id.release(); c->name_rank.release(); c->feat_start.release(); c->feat_end.release(); c->glist.release();
-    c->a_hi.release(); c->a_lo.release(); c->strip.release(); c->strip_f64.release(); c->strip_f32.release();
+    c->a_hi.release(); c->a_lo.release(); c->strip.release(); c->strip_f64.release(); c->strip_f32.release(); c->rank_strip.release();
     c->d_perm_off.release(); c->d_sc_off.release(); c->d_warp_off.release(); c->d_hits.release(); c->d_ngroups.release(); c->d_grp.release();
     c->d_label.release(); c->d_win.release(); c->w_root.release(); c->w_pos.release(); c->d_dens.release();
     c->d_aps.release(); c->d_scores.release(); c->w_s1.release(); c->w_d0.release(); c->w_w.release();
@@ -943,8 +991,9 @@ int coex_set_gemm_mode(coex_ctx *c, int mode) {
 
 int coex_set_count_mode(coex_ctx *c, int mode) {
     if (!c) COEX_FAIL("null context");
-    if (mode != 0 && mode != 1 && mode != 2)
-        COEX_FAIL("coex_set_count_mode: 0 = de-duplicated sorted-statistics kernel, 1 = per-query kernel, 2 = de-duplicated bucket-window kernel");
+    if (mode != 0 && mode != 1 && mode != 2 && mode != 3)
+        COEX_FAIL("coex_set_count_mode: 0 = de-duplicated sorted-statistics kernel (row-rank mode chosen by cost), 1 = per-query kernel, "
+                  "2 = de-duplicated bucket-window kernel, 3 = row-rank mode forced");
     c->count_mode = mode;
     return 0;
 }

@@ -139,6 +139,7 @@ struct coex_ctx {
     coex::DevBuf<int8_t> a_hi, a_lo;          // gathered query rows [Hs, n_pad]
     coex::DevBuf<int> strip;                  // S strip [Hs, N_pad] int32
     coex::DevBuf<double> strip_f64;           // Pearson null strip [Hs, N]
+    coex::DevBuf<unsigned int> rank_strip;    // row-rank mode: number of null values strictly below each value of the strip [Us, N_pad]
     coex::DevBuf<float> strip_f32;            // Pearson null strip of the de-duplicated path [Us, N_pad] (tensor r as float)
     coex::DevBuf<long long> d_perm_off, d_sc_off, d_warp_off;
     coex::DevBuf<int> d_hits, d_ngroups, d_grp, d_label, d_win, w_root, w_pos, w_state;

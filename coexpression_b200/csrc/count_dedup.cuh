@@ -27,6 +27,7 @@ namespace coex {
 constexpr int kDdThreads = 512;
 constexpr int kDdBuckets = 8192;
 constexpr int kDdQueue = 2048;
+constexpr int kRankTcap = 8192;          // columns ranked per work item in row-rank mode
 constexpr float kDdDelta = 5e-7f;        // |v32 - v64| <= 3e-7 |v|, |t32 - t64| <= 6e-8 |t|  
 constexpr int kDdSuper = 32768;          // columns streamed between two drains of the refinement queue (multiple of 4 * kDdThreads)
 
@@ -74,6 +75,7 @@ struct DedupArgs {
     const double *raw;              // [N, n] raw table and its in-order row statistics: the reference's exact arithmetic
     const double *raw_sum, *raw_mean, *raw_xx;
     int n;
+    unsigned int *rank_out;         // MODE 2: [rows_in_strip, ld] number of null values strictly below each column's value
     const float *eps_row;           // [N_pad] per-row share of the bound of |tensor r - exact r| (= icol in this mode; 0 = undefined row):
                                     // |error(u, c)| <= eps_row[u] + eps_row[c] (digit quantisation)
 };
@@ -112,9 +114,16 @@ __device__ __forceinline__ double pearson_exact_warp(const DedupArgs &a, long lo
     return (r != r) ? -99.0 : r;
 }
 
-template <bool PEARSON>
+// MODE 0: Spearman null, statistics of the item's queries.  MODE 1: Pearson null (tensor filter), same items.
+// MODE 2: RANK of a whole strip row -- the "statistics" of an item are the null values of a run of Tcap table columns
+//         themselves, and the result is, for each of them, the number of null values strictly below it (rank_out).  Used
+//         when the hit sets are so large that a row's queries carry more statistics than the row has columns (config C5:
+//         wide windows, thousands of hits per set): every (query, hit) then only LOOKS UP the rank of its column
+//         (rank_score_kernel) instead of having the row streamed once per query.
+template <int MODE>
 __global__ void __launch_bounds__(kDdThreads)
 count_dedup_kernel(DedupArgs a) {
+    constexpr bool PEARSON = (MODE == 1), RANKROW = (MODE == 2);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: q_vi[Qcap] | thr32[Tcap] | hist[Tcap+4] (thr32|hist = cursor[B] during step B) | lut[B+4] | queue[kDdQueue] | q_k q_i q_toff
     // (the double statistics and their origins live in an L2-resident per-CTA scratch: they are only
@@ -146,8 +155,12 @@ count_dedup_kernel(DedupArgs a) {
     int *g_col = tmp_c + a.Tcap, *col = g_col + a.Tcap;              // grouped / sorted columns
 
     const int n_deg = *a.n_degenerate;
+    const int nchunk = RANKROW ? (int)((a.N + a.Tcap - 1) / a.Tcap) : 1;
     for (int it = blockIdx.x; it < a.n_items; it += gridDim.x) {
-        const DedupItem item = a.items[it];
+        DedupItem item;
+        if (RANKROW) { item.urow = it / nchunk; item.qb = item.qe = 0; item.T = 0; }
+        else item = a.items[it];
+        const int rank_c0 = RANKROW ? (it % nchunk) * a.Tcap : 0;        // first column of the run
         const int nq = item.qe - item.qb;
         const int u = a.uniq_rows[item.urow];
         const int *srow = a.strip + (long long)item.urow * a.ld;
@@ -196,7 +209,7 @@ count_dedup_kernel(DedupArgs a) {
             q_toff[nq] = acc;
         }
         __syncthreads();
-        const int TP = q_toff[nq];
+        const int TP = RANKROW ? (int)min((long long)a.Tcap, a.N - rank_c0) : q_toff[nq];
         DD_PHASE(0);
         // ---- B. statistics: evaluated once (four per thread in flight), counted per bucket ------
         for (int t0 = tid; t0 < TP; t0 += 4 * kDdThreads) {
@@ -208,7 +221,9 @@ count_dedup_kernel(DedupArgs a) {
                 tt[e] = t0 + e * kDdThreads;
                 live[e] = tt[e] < TP;
                 qq[e] = 0; jj[e] = 0; cc4[e] = -1;
-                if (live[e]) {
+                if (RANKROW) {
+                    if (live[e]) cc4[e] = rank_c0 + tt[e];
+                } else if (live[e]) {
                     int lo = 0, hi = nq;
                     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (q_toff[mid] <= tt[e]) lo = mid; else hi = mid; }
                     qq[e] = lo; jj[e] = tt[e] - q_toff[lo];
@@ -218,22 +233,27 @@ count_dedup_kernel(DedupArgs a) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 guard[e] = false; sraw[e] = 0; sxc4[e] = 0.0;
-                if (cc4[e] >= 0) { guard[e] = a.rawsum_pos[cc4[e]] != 0; sraw[e] = srow[cc4[e]]; sxc4[e] = a.sx[cc4[e]]; }
+                if (cc4[e] >= 0) { guard[e] = RANKROW || a.rawsum_pos[cc4[e]] != 0; sraw[e] = srow[cc4[e]]; sxc4[e] = a.sx[cc4[e]]; }
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 if (!live[e]) continue;
                 double r = -99.0;
-                if (cc4[e] >= 0 && posu && guard[e]) {                      // coexfunctions.py:389 (the statistic is Spearman in both modes, Q2)
+                if (RANKROW) {
+                    // the null value of the column itself (no raw-sum guard: that belongs to the statistic, rank_score_kernel)
+                    if (sxu != 0.0 && sxc4[e] != 0.0) r = __ddiv_rn(0.25 * (double)sraw[e], __dmul_rn(sxu, sxc4[e]));
+                } else if (cc4[e] >= 0 && posu && guard[e]) {               // coexfunctions.py:389 (the statistic is Spearman in both modes, Q2)
                     r = __ddiv_rn(0.25 * (double)sraw[e], __dmul_rn(sxu, sxc4[e]));
                     if (r != r) r = -99.0;                                  // coexfunctions.py:406-408
                 }
                 tmp_r[tt[e]] = r;
                 tmp_c[tt[e]] = cc4[e];
                 if (r == -99.0) {                                           // diagonal, or 1-make-network.py:284-285
-                    const long long w = q_sc[qq[e]] + jj[e];
-                    a.scores[w] = (cc4[e] < 0) ? 0.0 : -log10(1.0);
-                    if (a.counts) a.counts[w] = -1;
+                    if (!RANKROW) {
+                        const long long w = q_sc[qq[e]] + jj[e];
+                        a.scores[w] = (cc4[e] < 0) ? 0.0 : -log10(1.0);
+                        if (a.counts) a.counts[w] = -1;
+                    }
                 } else {
                     atomicAdd(&lut[dd_bucket64(r, a.R, bscale)], 1u);
                     // the null value of a hit column IS this statistic (same arithmetic): it is accounted
@@ -277,11 +297,11 @@ count_dedup_kernel(DedupArgs a) {
             const double r = tmp_r[t];
             if (r != -99.0) {
                 int lo = 0, hi = nq;
-                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (q_toff[mid] <= t) lo = mid; else hi = mid; }
+                if (!RANKROW) while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (q_toff[mid] <= t) lo = mid; else hi = mid; }
                 const int b = dd_bucket64(r, a.R, bscale);
                 const unsigned int pos = lut[b] + atomicAdd(&cursor[b], 1u);
                 g_thr[pos] = r;
-                g_org[pos] = ((unsigned int)lo << 13) | (unsigned int)(t - q_toff[lo]);
+                g_org[pos] = RANKROW ? (unsigned int)t : ((unsigned int)lo << 13) | (unsigned int)(t - q_toff[lo]);
                 g_col[pos] = tmp_c[t];
             }
         }
@@ -456,6 +476,11 @@ count_dedup_kernel(DedupArgs a) {
             for (int p = b0; p < b1; ++p) { base += hist[p]; hist[p] = base; }
         }
         __syncthreads();
+        if (RANKROW) {
+            // all columns strictly below the column's own value (zero-variance columns: -99 < everything)
+            unsigned int *rrow = a.rank_out + (long long)item.urow * a.ld + rank_c0;
+            for (int s = tid; s < T; s += kDdThreads) rrow[org[s]] = hist[s] + (unsigned int)n_deg;
+        } else
         for (int s = tid; s < T; s += kDdThreads) {
             const unsigned int o = org[s];
             const int ql = (int)(o >> 13), j = (int)(o & 8191u);
@@ -472,6 +497,71 @@ count_dedup_kernel(DedupArgs a) {
         }
         DD_PHASE(5);
         if (a.phase_clk && tid == 0) atomicAdd(&a.phase_clk[6], 1ULL);
+    }
+}
+
+// MODE 2 companion: every (query, hit) looks its bisect index up in the rank strip.  One CTA per query of the strip.
+//   idx = rank[u][column of hit j]  (= #null values of row u strictly below the statistic: the statistic IS that column's
+//   null value, same arithmetic) - [null value at the skipped column i below the statistic] (quirk Q1); guards, diagonal,
+//   -99 and the score exactly as in phase B / F of the query modes.
+struct RankScoreArgs {
+    const int *strip;
+    const unsigned int *rank;
+    long long ld;
+    const int *uniq_rows, *ustart, *qlist, *q_perm;   // unique rows of the strip (already offset), their query ranges
+    long long u_count;
+    const long long *perm_off, *sc_off;
+    const int *hit_rows;
+    const double *sx;
+    const unsigned char *rawsum_pos;
+    long long N;
+    int anticor;
+    double *scores;
+    long long *counts;
+    const double *score_tab;
+};
+
+__global__ void __launch_bounds__(256)
+rank_score_kernel(RankScoreArgs a) {
+    __shared__ int s_slot;
+    const long long q_begin = a.ustart[0], q_count = a.ustart[a.u_count] - q_begin;
+    for (long long x = blockIdx.x; x < q_count; x += gridDim.x) {
+        const long long q = a.qlist[q_begin + x];
+        const int k = a.q_perm[q];
+        const long long off = a.perm_off[k];
+        const int P = (int)(a.perm_off[k + 1] - off);
+        const int i = (int)(q - off);
+        const int u = a.hit_rows[q];
+        __syncthreads();
+        if (threadIdx.x == 0) {                       // slot of row u among the strip's unique rows (ascending)
+            long long lo = 0, hi = a.u_count;
+            while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if (a.uniq_rows[mid] <= u) lo = mid; else hi = mid; }
+            s_slot = (int)lo;
+        }
+        __syncthreads();
+        const int *srow = a.strip + (long long)s_slot * a.ld;
+        const unsigned int *rrow = a.rank + (long long)s_slot * a.ld;
+        const double sxu = a.sx[u];
+        const bool posu = a.rawsum_pos[u] != 0;
+        double vi = -99.0;                            // null value at table column i (quirk Q1)
+        if (i < a.N) { const double sxc = a.sx[i]; if (sxu != 0.0 && sxc != 0.0) vi = __ddiv_rn(0.25 * (double)srow[i], __dmul_rn(sxu, sxc)); }
+        double *sc = a.scores + a.sc_off[k] + (long long)i * P;
+        long long *cn = a.counts ? a.counts + a.sc_off[k] + (long long)i * P : nullptr;
+        for (int j = threadIdx.x; j < P; j += blockDim.x) {
+            if (j == i) { sc[j] = 0.0; if (cn) cn[j] = -1; continue; }
+            const int c = a.hit_rows[off + j];
+            double t = -99.0;
+            if (posu && a.rawsum_pos[c]) {
+                t = __ddiv_rn(0.25 * (double)srow[c], __dmul_rn(sxu, a.sx[c]));
+                if (t != t) t = -99.0;
+            }
+            if (t == -99.0) { sc[j] = -log10(1.0); if (cn) cn[j] = -1; continue; }
+            long long idx = rrow[c];
+            long long len = a.N;
+            if (i < a.N) { len = a.N - 1; if (vi < t) idx -= 1; }
+            sc[j] = (len == a.N - 1) ? a.score_tab[idx] : edge_score_dev(idx, len, a.anticor);
+            if (cn) cn[j] = idx;
+        }
     }
 }
 

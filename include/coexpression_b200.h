@@ -156,7 +156,9 @@ int coex_stage_ms(coex_ctx *ctx, int stage, double *ms, long long *launches);
  * 64 / 128 = one-tile-per-CTA tcgen05 kernel with that table-column tile */
 int coex_set_gemm_mode(coex_ctx *ctx, int mode);
 /* 0 = de-duplicated sorted-statistics count kernel (default, count_dedup.cuh), 1 = per-query binary-search kernel,
- * 2 = de-duplicated bucket-window kernel (count_rows.cuh): three independent implementations of the same counts */
+ * 2 = de-duplicated bucket-window kernel (count_rows.cuh): three independent implementations of the same counts.
+ * Mode 0 switches by itself to ROW-RANK mode (every strip row ranked once, the queries look their bisect indices up) when the hit
+ * sets are so large that this is cheaper (config C5: thousands of hits per set); 3 forces that mode. */
 int coex_set_count_mode(coex_ctx *ctx, int mode);
 int coex_set_workspace_mb(coex_ctx *ctx, long long strip_mb);
 /* On-device cross-check: the first m_rows table rows against the whole table through the tcgen05
