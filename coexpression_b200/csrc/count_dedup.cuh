@@ -12,13 +12,15 @@
 //  2. Bucket table instead of a 10..13-step binary search: statistics are counting-sorted into
 //     8192 uniform buckets of [-R, R] (R ~ 8 standard deviations of a null correlation; values
 //     outside land in the edge buckets) and ranked inside their bucket; a streamed value finds its
-//     bucket with one multiply-add and searches only the statistics of that bucket and its two
-//     neighbours (so a float bucket index that is off by one is harmless).
+//     bucket with one multiply-add and searches only the statistics of that bucket: statistics and
+//     values go through the SAME monotone float bucket function (dd_bucket32), so the order of two
+//     numbers never contradicts the order of their buckets.
 //  3. fp32 pre-filter with exact fp64 refinement: the value and the search are done in float;
 //     whenever the float result could differ from the double one (a statistic within 5e-7 of the
 //     value, < 1 % of values) the column is queued and redone in double with the reference's
 //     exact arithmetic.  Counts are therefore still EXACT.
 #pragma once
+#include <math_constants.h>
 #include "common.cuh"
 #include "count.cuh"
 
@@ -91,11 +93,17 @@ __device__ __forceinline__ double pearson_exact_thread(const DedupArgs &a, long 
     return (r != r) ? -99.0 : r;
 }
 
-__device__ __forceinline__ int dd_bucket64(double t, double R, double scale) {
-    const double f = (t + R) * scale;
-    if (!(f > 0.0)) return 0;
-    return f >= (double)kDdBuckets ? kDdBuckets - 1 : (int)f;
+// Bucket of a value: ONE float function for statistics (rounded to float first), streamed float values and exactly
+// refined doubles (rounded to float first).  Every step (double -> float, the fused multiply-add, the truncation, the
+// clamps) is monotone non-decreasing, so  t <= v  =>  bucket(t) <= bucket(v)  and  t > v  =>  bucket(t) >= bucket(v)
+// both for the float compare of the fast path and for the double compare of the refinement: the statistics <= v are
+// all the statistics of the lower buckets plus some of v's OWN bucket -- a one-bucket search window with no
+// "off by one bucket in float" case.
+__device__ __forceinline__ int dd_bucket32(float x, float scale) {
+    const int b = __float2int_rz(__fmaf_rn(x, scale, (float)(kDdBuckets / 2)));
+    return min(max(b, 0), kDdBuckets - 1);
 }
+__device__ __forceinline__ int dd_bucket(double t, float scale) { return dd_bucket32(__double2float_rn(t), scale); }
 
 // the same for a whole warp: coalesced loads, the products added in order through shuffles (every lane gets the result)
 __device__ __forceinline__ double pearson_exact_warp(const DedupArgs &a, long long ra, long long rb, int lane) {
@@ -125,14 +133,14 @@ __global__ void __launch_bounds__(kDdThreads)
 count_dedup_kernel(DedupArgs a) {
     constexpr bool PEARSON = (MODE == 1), RANKROW = (MODE == 2);
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: q_vi[Qcap] | thr32[Tcap] | hist[Tcap+4] (thr32|hist = cursor[B] during step B) | lut[B+4] | queue[kDdQueue] | q_k q_i q_toff
+    // layout: q_vi[Qcap] | thr32[Tcap+4] | hist[Tcap+4] (thr32|hist = cursor[B] during step B) | lut[B+4] | queue[kDdQueue] | q_k q_i q_toff
     // (the double statistics and their origins live in an L2-resident per-CTA scratch: they are only
     //  touched by the rare exact refinements and by the final scoring)
     double *q_vi = reinterpret_cast<double *>(smem_raw);                      // [Qcap] exact null value at the skipped column
-    float *thr32 = reinterpret_cast<float *>(q_vi + a.Qcap);
-    unsigned int *hist = reinterpret_cast<unsigned int *>(thr32 + a.Tcap);
+    float *thr32 = reinterpret_cast<float *>(q_vi + a.Qcap) + 1;             // [-1 .. Tcap+2]: thr32[-1] = -inf, thr32[T] = +inf (sentinels)
+    unsigned int *hist = reinterpret_cast<unsigned int *>(thr32 + a.Tcap + 3);
     unsigned int *lut = hist + a.Tcap + 4;
-    unsigned int *cursor = reinterpret_cast<unsigned int *>(thr32);   // bucket cursors alias thr32|hist (both dead until step C; 2*Tcap >= buckets)
+    unsigned int *cursor = reinterpret_cast<unsigned int *>(thr32 - 1);   // bucket cursors alias thr32|hist (both dead until step C; 2*Tcap >= buckets)
     int *queue = reinterpret_cast<int *>(lut + kDdBuckets + 4);
     long long *q_sc = reinterpret_cast<long long *>(queue + kDdQueue);   // [Qcap] offset of the query's score row
     int *q_i = reinterpret_cast<int *>(q_sc + a.Qcap);                     // [Qcap] hit position
@@ -144,8 +152,7 @@ count_dedup_kernel(DedupArgs a) {
     __shared__ unsigned int s_warp[kDdThreads / 32];
 
     const int tid = threadIdx.x;
-    const double bscale = (double)kDdBuckets / (2.0 * a.R);
-    const float bscale_f = (float)bscale, R_f = (float)a.R;
+    const float bscale_f = (float)((double)kDdBuckets / (2.0 * a.R));
     double *tmp_r = a.g_thr + (long long)blockIdx.x * 3 * a.Tcap;      // statistic of flat index t (-99 = undefined)
     double *g_thr = tmp_r + a.Tcap;                                    // grouped by bucket
     double *thr64 = g_thr + a.Tcap;                                    // sorted
@@ -255,7 +262,7 @@ count_dedup_kernel(DedupArgs a) {
                         if (a.counts) a.counts[w] = -1;
                     }
                 } else {
-                    atomicAdd(&lut[dd_bucket64(r, a.R, bscale)], 1u);
+                    atomicAdd(&lut[dd_bucket(r, bscale_f)], 1u);
                     // the null value of a hit column IS this statistic (same arithmetic): it is accounted
                     // exactly in step C' and skipped by the float streaming pass
                     if (a.bm_words) {
@@ -298,7 +305,7 @@ count_dedup_kernel(DedupArgs a) {
             if (r != -99.0) {
                 int lo = 0, hi = nq;
                 if (!RANKROW) while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (q_toff[mid] <= t) lo = mid; else hi = mid; }
-                const int b = dd_bucket64(r, a.R, bscale);
+                const int b = dd_bucket(r, bscale_f);
                 const unsigned int pos = lut[b] + atomicAdd(&cursor[b], 1u);
                 g_thr[pos] = r;
                 g_org[pos] = RANKROW ? (unsigned int)t : ((unsigned int)lo << 13) | (unsigned int)(t - q_toff[lo]);
@@ -307,13 +314,17 @@ count_dedup_kernel(DedupArgs a) {
         }
         __syncthreads();
         const int T = s_T;
+        // lut[b] = first statistic of bucket b | number of statistics in it << 16 (the cursors have counted them; T <= 8192):
+        // one shared-memory load per streamed value gives its whole search window
+        for (int b = tid; b < kDdBuckets; b += kDdThreads) lut[b] |= cursor[b] << 16;
+        __syncthreads();                                    // the cursors (aliasing thr32 | hist) are dead from here on
         DD_PHASE(1);
         if (T == 0) continue;                               // every statistic undefined: scores already written
         // ---- C. rank inside the bucket -> fully sorted statistics -------------------------------------
         for (int e = tid; e < T; e += kDdThreads) {
             const double t = g_thr[e];
-            const int b = dd_bucket64(t, a.R, bscale);
-            const int lo = (int)lut[b], hi = (int)lut[b + 1];
+            const unsigned int pk = lut[dd_bucket(t, bscale_f)];
+            const int lo = (int)(pk & 0xffffu), hi = lo + (int)(pk >> 16);
             int rank = 0;
             for (int m = lo; m < hi; ++m) {
                 const double x = g_thr[m];
@@ -325,6 +336,7 @@ count_dedup_kernel(DedupArgs a) {
             col[lo + rank] = g_col[e];
         }
         for (int p = tid; p <= T; p += kDdThreads) hist[p] = 0;
+        if (tid == 0) { thr32[-1] = -CUDART_INF_F; thr32[T] = CUDART_INF_F; }
         __syncthreads();
         // ---- C'. hit columns: value == statistic exactly.  A column hit by several queries of the item appears as
         // several EQUAL statistics (same row, same column, same arithmetic) and is added once: by the statistic that
@@ -383,23 +395,20 @@ count_dedup_kernel(DedupArgs a) {
                 have = c0 < cend;
                 if (have) fetch(c0);
                 float v[4];
-                int p[4], lo[4], hi[4], len[4];
+                int p[4], len[4];
                 bool act[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    // zero-variance column: -99, counted in bulk; hit column: accounted exactly in step C'
-                    act[e] = (wv[e] != 0.0f) && (cc + e < N) && !((skip4 >> e) & 1u);
+                    // zero-variance column (and the padding behind column N): mask 0 -> -99, counted in bulk; hit column:
+                    // accounted exactly in step C'
+                    act[e] = (wv[e] != 0.0f) && !((skip4 >> e) & 1u);
                     v[e] = PEARSON ? __int_as_float(sv[e]) : __int2float_rn(sv[e]) * (iu * wv[e]);
-                    // bucket of v, possibly off by one in float: search the bucket and both neighbours
-                    const float f = (v[e] + R_f) * bscale_f;
-                    int bkt = (f > 0.0f) ? (int)f : 0;
-                    bkt = bkt >= kDdBuckets ? kDdBuckets - 1 : bkt;
-                    lo[e] = (int)lut[bkt > 0 ? bkt - 1 : 0];
-                    hi[e] = (int)lut[bkt + 2 <= kDdBuckets ? bkt + 2 : kDdBuckets];
-                    p[e] = lo[e];
-                    len[e] = act[e] ? hi[e] - lo[e] : 0;
+                    // the statistics <= v are those of the lower buckets and some of v's own bucket (dd_bucket32 is monotone)
+                    const unsigned int pk = lut[dd_bucket32(v[e], bscale_f)];
+                    p[e] = (int)(pk & 0xffffu);
+                    len[e] = act[e] ? (int)(pk >> 16) : 0;
                 }
-                while ((len[0] | len[1] | len[2] | len[3]) > 0) {         // statistics <= v in [lo, hi)
+                while ((len[0] | len[1] | len[2] | len[3]) > 0) {         // statistics <= v inside the bucket
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         if (len[e] > 0) {
@@ -411,10 +420,10 @@ count_dedup_kernel(DedupArgs a) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     if (!act[e]) continue;
-                    // a statistic closer than delta cannot be ordered in float (those outside [lo, hi)
-                    // are at least a whole bucket away)
-                    const float below = (p[e] > lo[e]) ? v[e] - thr32[p[e] - 1] : 1.0f;
-                    const float above = (p[e] < hi[e]) ? thr32[p[e]] - v[e] : 1.0f;
+                    // a statistic closer than delta cannot be ordered in float: the two neighbours of v in the sorted
+                    // statistics decide (sentinels -inf / +inf at both ends)
+                    const float below = v[e] - thr32[p[e] - 1];
+                    const float above = thr32[p[e]] - v[e];
                     if (fminf(below, above) >= (PEARSON ? dd_delta(v[e]) + eps_u + wv[e] : dd_delta(v[e]))) {
                         atomicAdd(&hist[p[e]], 1u);
                     } else {
@@ -424,9 +433,9 @@ count_dedup_kernel(DedupArgs a) {
                         } else {                                          // queue full: refine in place
                             const double vv = PEARSON ? pearson_exact_thread(a, u, cc + e)
                                                       : __ddiv_rn(0.25 * (double)srow[cc + e], __dmul_rn(sxu, a.sx[cc + e]));
-                            const int bb = dd_bucket64(vv, a.R, bscale);
-                            int pp = (int)lut[bb];
-                            int ln = (int)lut[bb + 1] - pp;
+                            const unsigned int pk = lut[dd_bucket(vv, bscale_f)];
+                            int pp = (int)(pk & 0xffffu);
+                            int ln = (int)(pk >> 16);
                             while (ln > 0) {
                                 const int half = ln >> 1;
                                 if (thr64[pp + half] <= vv) { pp += half + 1; ln -= half + 1; } else ln = half;
@@ -444,9 +453,9 @@ count_dedup_kernel(DedupArgs a) {
                 const int c = queue[x];
                 const double vv = PEARSON ? pearson_exact_thread(a, u, c)
                                           : __ddiv_rn(0.25 * (double)srow[c], __dmul_rn(sxu, a.sx[c]));
-                const int bb = dd_bucket64(vv, a.R, bscale);
-                int pp = (int)lut[bb];
-                int len = (int)lut[bb + 1] - pp;
+                const unsigned int pk = lut[dd_bucket(vv, bscale_f)];
+                int pp = (int)(pk & 0xffffu);
+                int len = (int)(pk >> 16);
                 while (len > 0) {
                     const int half = len >> 1;
                     if (thr64[pp + half] <= vv) { pp += half + 1; len -= half + 1; } else len = half;
@@ -587,7 +596,7 @@ __global__ void icol_kernel(const double *__restrict__ sx, long long N, long lon
 }
 
 inline size_t dedup_smem_bytes(int Tcap, int Qcap, int bm_words, int claim) {
-    return (size_t)Qcap * 8 + (size_t)Tcap * 4 + (size_t)(Tcap + 4) * 4 + (size_t)(kDdBuckets + 4) * 4 +
+    return (size_t)Qcap * 8 + (size_t)(Tcap + 4) * 4 + (size_t)(Tcap + 4) * 4 + (size_t)(kDdBuckets + 4) * 4 +
            (size_t)kDdQueue * 4 + (size_t)Qcap * 8 + (size_t)Qcap * 4 * 3 + (size_t)(Qcap + 2) * 4 + (size_t)bm_words * 4 * (claim ? 2 : 1) + 16;
 }
 
