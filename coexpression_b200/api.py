@@ -12,7 +12,7 @@ import numpy as np
 from . import _lib
 from ._lib import CoexParams, check
 
-STAGES = ["rank_pack", "rowstats", "gather", "corr_gemm", "count_score", "network"]
+STAGES = ["rank_pack", "rowstats", "gather", "corr_gemm", "count_score", "network", "stat_sort"]
 
 
 @dataclass
@@ -299,7 +299,7 @@ class CoexContext:
               "coex_set_gemm_mode")
 
     def set_count_mode(self, mode):
-        check(self.lib.coex_set_count_mode(self.h, {"dedup": 0, "per_query": 1, "dedup_window": 2, "row_rank": 3}.get(mode, mode)), "coex_set_count_mode")
+        check(self.lib.coex_set_count_mode(self.h, {"dedup": 0, "per_query": 1, "dedup_window": 2, "row_rank": 3, "dedup_split": 4}.get(mode, mode)), "coex_set_count_mode")
 
     def set_workspace_mb(self, mb):
         check(self.lib.coex_set_workspace_mb(self.h, int(mb)), "coex_set_workspace_mb")

@@ -9,8 +9,10 @@
 #include "count.cuh"
 #include "count_dedup.cuh"
 #include "count_rows.cuh"
+#include "count_split.cuh"
 #include "plan.cuh"
 #include "network.cuh"
+static_assert(coex::kPlanQcap == coex::kPlanQcapSplit, "stat_sort_kernel holds one item's queries in fixed shared arrays");
 #include "allpairs.cuh"
 #include "permute.cuh"
 
@@ -65,9 +67,9 @@ static int prepare_impl(coex_ctx *c) {
         c->raw, N, n, c->raw_sum.p, c->raw_mean.p, c->raw_xx.p, c->rawsum_pos.p);
     COEX_CUDA(cudaGetLastError());
     COEX_TRY(stage_end(c, 1));
-    COEX_TRY(c->icol.reserve(c->N_pad)); COEX_TRY(c->d_ndeg.reserve(1));
+    COEX_TRY(c->icol.reserve(c->N_pad)); COEX_TRY(c->d_ndeg.reserve(1)); COEX_TRY(c->sxg.reserve(c->N_pad));
     COEX_CUDA(cudaMemsetAsync(c->d_ndeg.p, 0, sizeof(int), c->stream));
-    icol_kernel<<<(unsigned)((c->N_pad + 255) / 256), 256, 0, c->stream>>>(c->sx.p, N, c->N_pad, c->icol.p, c->d_ndeg.p);
+    icol_kernel<<<(unsigned)((c->N_pad + 255) / 256), 256, 0, c->stream>>>(c->sx.p, c->rawsum_pos.p, N, c->N_pad, c->icol.p, c->sxg.p, c->d_ndeg.p);
     COEX_CUDA(cudaGetLastError());
     c->launches += 1;
     // no synchronisation here: the count of zero-variance rows stays on the device (the count kernels read it there),
@@ -99,6 +101,9 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     const int Tcap = rows_kernel ? std::max(4096, (int)round_up(Pmax, 512))
                                  : std::max(kDdBuckets / 2, (int)round_up(Pmax, 256));   // 2*Tcap >= buckets: the bucket cursors alias thr32|hist
     const int Qcap = kPlanQcap;
+    // count mode 4: set-up phases (statistics + sort) of all work items of a strip in a kernel of their own, scores scattered by a
+    // third one (count_split.cuh) -- measured slower than the fused kernel at C2 (profiles/r01_count_split.md), kept as a cross-check
+    const bool split = !pearson && !rows_kernel && c->count_mode == 4 && Tcap <= 8192;
     {   // strips first (upper bound of the unique rows), so that the big buffers keep their place whatever the plan needs
         long long Us0 = (c->strip_mb << 20) / (c->N_pad * 4);
         Us0 = std::max<long long>(256, Us0 / 256 * 256);
@@ -171,14 +176,28 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
             COEX_CUDA(cudaFuncSetAttribute(count_dedup_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_dedup_kernel<true>, kDdThreads, smem));
         } else {
+            if (split) {
+                COEX_CUDA(cudaFuncSetAttribute(count_dedup_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_dedup_kernel<3>, kDdThreads, smem));
+            } else {
             COEX_CUDA(cudaFuncSetAttribute(count_dedup_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_dedup_kernel<false>, kDdThreads, smem));
+            }
         }
     }
     const int grid_max = std::max(1, per_sm) * c->sm_count;
+    const size_t ssmem = sort_smem_bytes(Tcap);
+    int sort_grid_max = 1;
+    if (split) {
+        int sper = 1;
+        COEX_CUDA(cudaFuncSetAttribute(stat_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
+        COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sper, stat_sort_kernel, kSsThreads, ssmem));
+        sort_grid_max = std::max(1, sper) * c->sm_count;
+    }
+    unsigned long long st_cap = 0;
     if (rows_kernel) {
         COEX_TRY(c->dd_gthr.reserve((size_t)grid_max * Tcap));
-    } else {
+    } else if (!split) {
         COEX_TRY(c->dd_gthr.reserve((size_t)grid_max * Tcap * 3)); COEX_TRY(c->dd_gorg.reserve((size_t)grid_max * Tcap * 5));
     }
     COEX_TRY(c->dd_tab.reserve((size_t)N + 1));
@@ -187,7 +206,7 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     c->launches += 1;
     DevBuf<unsigned long long> phase;
     const bool dbg = getenv("COEX_COUNT_DEBUG") != nullptr;
-    if (dbg) { COEX_TRY(phase.reserve(8)); COEX_CUDA(cudaMemsetAsync(phase.p, 0, 8 * sizeof(unsigned long long), st)); }
+    if (dbg) { COEX_TRY(phase.reserve(16)); COEX_CUDA(cudaMemsetAsync(phase.p, 0, 16 * sizeof(unsigned long long), st)); }
     size_t s_idx = 0;
     int rank_grid_max = 1;
     long long c_sc_total = 0;
@@ -207,6 +226,15 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
             if (rank_mode && bm_words == 0) COEX_FAIL("rank mode needs the hit-column bitmap (table of at most 262144 rows)");
             if (tdbg) fprintf(stderr, "[coex host] count: %lld items, cost items %.3g vs rank %.3g -> %s\n", strip_item_begin[(size_t)n_strips],
                               cost_items, cost_rank, rank_mode ? "rank mode" : "query items");
+            if (split && !rank_mode) {
+                // every statistic belongs to exactly one item (sum over the strips <= sum P^2) and an item holds at most Tcap
+                long long max_items = 1;
+                for (int s = 0; s < n_strips; ++s) max_items = std::max(max_items, strip_item_begin[(size_t)s + 1] - strip_item_begin[(size_t)s]);
+                st_cap = (unsigned long long)std::max<long long>(1, std::min<long long>(SCtot, max_items * (long long)Tcap));
+                COEX_TRY(c->st_thr.reserve(st_cap)); COEX_TRY(c->st_w.reserve(st_cap)); COEX_TRY(c->st_col.reserve(st_cap));
+                COEX_TRY(c->st_cnt.reserve(st_cap)); COEX_TRY(c->st_cursor.reserve(1));
+                COEX_TRY(c->st_itemoff.reserve((size_t)max_items)); COEX_TRY(c->st_itemT.reserve((size_t)max_items));
+            }
         }
         if (rank_mode) {
             const int rclaim = (bm_words <= 2048) ? 1 : 0;
@@ -244,6 +272,22 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
         const DedupItem *items_s = reinterpret_cast<const DedupItem *>(c->dd_items.p) + strip_item_begin[s_idx];
         const int n_items_s = (int)(strip_item_begin[s_idx + 1] - strip_item_begin[s_idx]);
         const int grid = std::min(grid_max, std::max(n_items_s, 1));
+        const double R = std::min(1.0, std::max(0.05, 8.0 / std::sqrt((double)std::max(c->n, 2))));
+        if (split) {
+            COEX_TRY(stage_begin(c, ST_STATSORT));
+            COEX_CUDA(cudaMemsetAsync(c->st_cursor.p, 0, sizeof(unsigned long long), st));
+            SortArgs sa{};
+            sa.strip = c->strip.p; sa.ld = ld; sa.items = items_s; sa.n_items = n_items_s; sa.uniq_rows = c->dd_uniq.p + u0;
+            sa.qlist = c->dd_qlist.p; sa.q_perm = c->dd_qperm.p; sa.perm_off = c->d_perm_off.p; sa.sc_off = c->d_sc_off.p;
+            sa.hit_rows = d_hits; sa.sx = c->sx.p; sa.sxg = c->sxg.p; sa.rawsum_pos = c->rawsum_pos.p; sa.N = N; sa.scores = d_sc; sa.counts = d_cn;
+            sa.Tcap = Tcap; sa.bscale = (float)((double)kDdBuckets / (2.0 * R));
+            sa.st_thr = c->st_thr.p; sa.st_w = c->st_w.p; sa.st_col = c->st_col.p; sa.st_cap = st_cap; sa.st_cursor = c->st_cursor.p;
+            sa.err = c->pl_err.p; sa.item_soff = c->st_itemoff.p; sa.item_T = c->st_itemT.p;
+            sa.phase_clk = dbg ? phase.p + 8 : nullptr;
+            stat_sort_kernel<<<std::min(sort_grid_max, std::max(n_items_s, 1)), kSsThreads, ssmem, st>>>(sa);
+            COEX_KCHECK(st);
+            COEX_TRY(stage_end(c, 1));
+        }
         COEX_TRY(stage_begin(c, ST_COUNT));
         if (rows_kernel) {
             RowCountArgs ra{};
@@ -261,9 +305,19 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
             da.sx = c->sx.p; da.icol = c->icol.p; da.rawsum_pos = c->rawsum_pos.p; da.N = N;
             da.n_degenerate = c->d_ndeg.p; da.anticor = prm->anticorrelation; da.scores = d_sc; da.counts = d_cn;
             da.Tcap = Tcap; da.Qcap = Qcap; da.bm_words = bm_words; da.claim = claim;
-            da.R = std::min(1.0, std::max(0.05, 8.0 / std::sqrt((double)std::max(c->n, 2)))); da.g_thr = c->dd_gthr.p; da.g_org = c->dd_gorg.p;
+            da.R = R; da.g_thr = c->dd_gthr.p; da.g_org = c->dd_gorg.p;
             da.score_tab = c->dd_tab.p; da.phase_clk = dbg ? phase.p : nullptr;
-            if (pearson) {
+            if (split) {
+                da.st_thr = c->st_thr.p; da.st_cnt = c->st_cnt.p; da.st_col = c->st_col.p; da.item_soff = c->st_itemoff.p;
+                da.item_T = c->st_itemT.p;
+                count_dedup_kernel<3><<<grid, kDdThreads, smem, st>>>(da);
+                COEX_KCHECK(st);
+                ScatterArgs sc{};
+                sc.st_w = c->st_w.p; sc.st_cnt = c->st_cnt.p; sc.st_total = c->st_cursor.p; sc.n_degenerate = c->d_ndeg.p; sc.N = N;
+                sc.anticor = prm->anticorrelation; sc.score_tab = c->dd_tab.p; sc.scores = d_sc; sc.counts = d_cn;
+                score_scatter_kernel<<<c->sm_count * 8, 256, 0, st>>>(sc);
+                c->launches += 1; c->stage_launches[ST_COUNT] += 1;
+            } else if (pearson) {
                 da.eps_row = c->z_valid.p;
                 da.strip_f32 = c->strip_f32.p; da.raw = c->raw; da.raw_sum = c->raw_sum.p; da.raw_mean = c->raw_mean.p;
                 da.raw_xx = c->raw_xx.p; da.n = c->n; da.icol = c->z_valid.p; da.n_degenerate = c->z_ninv.p;
@@ -277,8 +331,11 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     }
     if (dbg) {
         COEX_CUDA(cudaStreamSynchronize(st));
-        unsigned long long h[8];
+        unsigned long long h[16];
         COEX_CUDA(cudaMemcpy(h, phase.p, sizeof h, cudaMemcpyDeviceToHost));
+        if (split && h[15])
+            fprintf(stderr, "[coex stat_sort] items=%llu cycles/item: meta=%llu stats=%llu scan=%llu group=%llu rank=%llu write=%llu (grid<=%d, smem=%zu)\n",
+                    h[15], h[8] / h[15], h[9] / h[15], h[10] / h[15], h[11] / h[15], h[12] / h[15], h[13] / h[15], sort_grid_max, ssmem);
         if (rows_kernel)
             fprintf(stderr, "[coex count rows] items=%llu cycles/item: meta=%llu stats=%llu chunks=%llu score=%llu (Tcap=%d Qcap=%d grid<=%d smem=%zu)\n",
                     h[6], h[0] / std::max(1ULL, h[6]), h[1] / std::max(1ULL, h[6]), h[2] / std::max(1ULL, h[6]), h[3] / std::max(1ULL, h[6]), Tcap, Qcap, grid_max, smem);
@@ -688,6 +745,8 @@ int coex_destroy(coex_ctx *c) {
     c->raw_own.release(); c->raw_sum.release(); c->raw_mean.release(); c->raw_xx.release(); c->rawsum_pos.release();
     c->rank2.release(); c->u_hi.release(); c->u_lo.release(); c->suu.release(); c->sx.release();
     c->z_valid.release(); c->z_ninv.release(); c->za_planes.release(); c->za_inv_s.release();
+    c->st_thr.release(); c->st_w.release(); c->st_col.release(); c->st_cnt.release(); c->st_itemoff.release(); c->st_itemT.release();
+    c->st_cursor.release(); c->sxg.release();
     c->z_planes.release(); c->z_ok.release(); c->z_l1.release(); c->z_inv_s.release();
     c->ap_hist.release(); c->feat_key.release(); c->feat_row.release(); c->pm_blob.release(); c->pm_counts.release(); c->pm_hits_tmp.release(); c->pm_off.release();
     c->chrom_id.release(); c->name_rank.release(); c->feat_start.release(); c->feat_end.release(); c->glist.release();
@@ -991,9 +1050,9 @@ int coex_set_gemm_mode(coex_ctx *c, int mode) {
 
 int coex_set_count_mode(coex_ctx *c, int mode) {
     if (!c) COEX_FAIL("null context");
-    if (mode != 0 && mode != 1 && mode != 2 && mode != 3)
+    if (mode < 0 || mode > 4)
         COEX_FAIL("coex_set_count_mode: 0 = de-duplicated sorted-statistics kernel (row-rank mode chosen by cost), 1 = per-query kernel, "
-                  "2 = de-duplicated bucket-window kernel, 3 = row-rank mode forced");
+                  "2 = de-duplicated bucket-window kernel, 3 = row-rank mode forced, 4 = mode 0 split into sort / stream / score kernels");
     c->count_mode = mode;
     return 0;
 }

@@ -50,8 +50,8 @@ inline bool debug_sync() {
     return on;
 }
 
-constexpr int kNumStages = 6;
-enum Stage { ST_RANK = 0, ST_ROWSTATS = 1, ST_GATHER = 2, ST_GEMM = 3, ST_COUNT = 4, ST_NETWORK = 5 };
+constexpr int kNumStages = 7;
+enum Stage { ST_RANK = 0, ST_ROWSTATS = 1, ST_GATHER = 2, ST_GEMM = 3, ST_COUNT = 4, ST_NETWORK = 5, ST_STATSORT = 6 };
 
 struct StageSpan {
     int stage;
@@ -153,9 +153,15 @@ struct coex_ctx {
     coex::DevBuf<unsigned char> dd_items;     // DedupItem[]
     coex::DevBuf<int> pl_cnt, pl_cursor, pl_ustart, pl_nitems, pl_err;   // device-side plan (plan.cuh)
     coex::DevBuf<long long> pl_itemoff, pl_bounds, pl_meta;
+    // sorted statistics of a strip's work items (count_split.cuh: stat_sort_kernel -> count_dedup_kernel<3>)
+    coex::DevBuf<double> st_thr, sxg;
+    coex::DevBuf<unsigned int> st_cnt;
+    coex::DevBuf<int> st_col, st_itemT;
+    coex::DevBuf<long long> st_itemoff;
+    coex::DevBuf<unsigned long long> st_cursor, st_w;
     coex::DevBuf<double> dd_gthr, dd_tab;
     coex::DevBuf<unsigned int> dd_gorg;
-    int count_mode = 0;                       // 0 = de-duplicated sorted-statistics kernel (count_dedup), 1 = per-query binary-search kernel, 2 = de-duplicated bucket-window kernel (count_rows)
+    int count_mode = 0;                       // 0 = de-duplicated sorted-statistics kernel (count_dedup<0>), 1 = per-query binary-search kernel, 2 = de-duplicated bucket-window kernel (count_rows), 3 = row-rank forced, 4 = split form of 0 (stat_sort + count_dedup<3> + score_scatter)
     coex::DevBuf<int> p_idxa, p_idxb;         // coex_pairs staging
     coex::DevBuf<double> p_out;
     long long strip_mb = 1024;

@@ -78,6 +78,13 @@ struct DedupArgs {
     const double *raw_sum, *raw_mean, *raw_xx;
     int n;
     unsigned int *rank_out;         // MODE 2: [rows_in_strip, ld] number of null values strictly below each column's value
+    // ---- MODE 3: the item's statistics arrive SORTED from stat_sort_kernel (count_split.cuh) ----------------------
+    const double *st_thr;           // sorted statistics of every item of the launch, item `it` at item_soff[it] .. + item_T[it]
+    const int *st_col;              // table column of the statistic
+    unsigned int *st_cnt;           // OUT: number of streamed + hit columns strictly below the statistic (score_scatter_kernel
+                                    //      turns it into the bisect index and the edge score)
+    const long long *item_soff;     // [n_items]
+    const int *item_T;              // [n_items]
     const float *eps_row;           // [N_pad] per-row share of the bound of |tensor r - exact r| (= icol in this mode; 0 = undefined row):
                                     // |error(u, c)| <= eps_row[u] + eps_row[c] (digit quantisation)
 };
@@ -128,10 +135,14 @@ __device__ __forceinline__ double pearson_exact_warp(const DedupArgs &a, long lo
 //         when the hit sets are so large that a row's queries carry more statistics than the row has columns (config C5:
 //         wide windows, thousands of hits per set): every (query, hit) then only LOOKS UP the rank of its column
 //         (rank_score_kernel) instead of having the row streamed once per query.
+// MODE 3: Spearman null as MODE 0, but phases A - C (query metadata, statistics, sort) were done for ALL items of the launch by
+//         stat_sort_kernel (count_split.cuh), whose shared memory holds the statistics during the sort and which keeps many more
+//         items in flight per SM than this kernel's two CTAs: the set-up phases were latency bound and half of this kernel's
+//         cycles (profiles/r01_count_split.md).  What is left here: load the sorted statistics, build the bucket table, stream.
 template <int MODE>
 __global__ void __launch_bounds__(kDdThreads)
 count_dedup_kernel(DedupArgs a) {
-    constexpr bool PEARSON = (MODE == 1), RANKROW = (MODE == 2);
+    constexpr bool PEARSON = (MODE == 1), RANKROW = (MODE == 2), PRE = (MODE == 3);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: q_vi[Qcap] | thr32[Tcap+4] | hist[Tcap+4] (thr32|hist = cursor[B] during step B) | lut[B+4] | queue[kDdQueue] | q_k q_i q_toff
     // (the double statistics and their origins live in an L2-resident per-CTA scratch: they are only
@@ -153,13 +164,16 @@ count_dedup_kernel(DedupArgs a) {
 
     const int tid = threadIdx.x;
     const float bscale_f = (float)((double)kDdBuckets / (2.0 * a.R));
-    double *tmp_r = a.g_thr + (long long)blockIdx.x * 3 * a.Tcap;      // statistic of flat index t (-99 = undefined)
+    double *tmp_r = PRE ? nullptr : a.g_thr + (long long)blockIdx.x * 3 * a.Tcap;      // statistic of flat index t (-99 = undefined)
     double *g_thr = tmp_r + a.Tcap;                                    // grouped by bucket
-    double *thr64 = g_thr + a.Tcap;                                    // sorted
-    unsigned int *g_org = a.g_org + (long long)blockIdx.x * 5 * a.Tcap;
-    unsigned int *org = g_org + a.Tcap;
-    int *tmp_c = reinterpret_cast<int *>(org + a.Tcap);              // column of flat index t
-    int *g_col = tmp_c + a.Tcap, *col = g_col + a.Tcap;              // grouped / sorted columns
+    double *thr64_w = g_thr + a.Tcap;                                  // sorted
+    unsigned int *g_org = PRE ? nullptr : a.g_org + (long long)blockIdx.x * 5 * a.Tcap;
+    unsigned int *org_w = g_org + a.Tcap;
+    int *tmp_c = reinterpret_cast<int *>(org_w + a.Tcap);            // column of flat index t
+    int *g_col = tmp_c + a.Tcap, *col_w = g_col + a.Tcap;            // grouped / sorted columns
+    const double *thr64 = thr64_w;                                   // (MODE 3: the item's slice of the pre-sorted arrays)
+    const unsigned int *org = org_w;
+    const int *col = col_w;
 
     const int n_deg = *a.n_degenerate;
     const int nchunk = RANKROW ? (int)((a.N + a.Tcap - 1) / a.Tcap) : 1;
@@ -177,6 +191,76 @@ count_dedup_kernel(DedupArgs a) {
         __syncthreads();                                   // previous item fully retired
         long long tclk = clock64();
 #define DD_PHASE(id) do { if (a.phase_clk && tid == 0) { const long long now = clock64(); atomicAdd(&a.phase_clk[id], (unsigned long long)(now - tclk)); tclk = now; } } while (0)
+        int T = 0;
+        long long soff = 0;
+        if constexpr (PRE) {
+            // ---- A'. the item's sorted statistics and query metadata come from stat_sort_kernel -------------------
+            T = a.item_T[it];
+            soff = a.item_soff[it];
+            thr64 = a.st_thr + soff; col = a.st_col + soff;
+            if (T == 0) continue;                           // every statistic undefined: scores already written
+            // the item's statistics: every load of the thread issued before the first is used (T <= 16 * kDdThreads)
+            double t_in[4];
+            int c_in[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int s = tid + e * kDdThreads;
+                t_in[e] = (s < T) ? thr64[s] : 0.0;
+                c_in[e] = (s < T && a.bm_words) ? col[s] : 0;
+            }
+            if (tid == 0) s_qn = 0;
+            for (int b = tid; b < kDdBuckets; b += kDdThreads) lut[b] = 0;
+            for (int wd = tid; wd < (a.claim ? 2 : 1) * a.bm_words; wd += kDdThreads) bitmap[wd] = 0;
+            __syncthreads();
+            for (int s0 = 0; s0 < T; s0 += 4 * kDdThreads) {
+                if (s0) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int s = s0 + tid + e * kDdThreads;
+                        t_in[e] = (s < T) ? thr64[s] : 0.0;
+                        c_in[e] = (s < T && a.bm_words) ? col[s] : 0;
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int s = s0 + tid + e * kDdThreads;
+                    if (s >= T) continue;
+                    thr32[s] = (float)t_in[e];
+                    hist[s] = 0;
+                    atomicAdd(&lut[dd_bucket(t_in[e], bscale_f)], 1u);
+                    if (a.bm_words) {
+                        const unsigned int bit = 1u << (c_in[e] & 31);
+                        atomicOr(&bitmap[c_in[e] >> 5], bit);
+                        if (a.claim) atomicOr(&bitmap[a.bm_words + (c_in[e] >> 5)], bit);
+                    }
+                }
+            }
+            if (tid == 0) { hist[T] = 0; thr32[-1] = -CUDART_INF_F; thr32[T] = CUDART_INF_F; }
+            __syncthreads();
+            DD_PHASE(0);
+            {   // exclusive scan of the bucket counts, start | count << 16 (as the fused modes leave it)
+                constexpr int kWarps = kDdThreads / 32, kPerWarp = kDdBuckets / kWarps;
+                const int wid = tid >> 5, ln = tid & 31;
+                unsigned int carry = 0;
+                for (int c = 0; c < kPerWarp; c += 32) {
+                    const int b = wid * kPerWarp + c + ln;
+                    const unsigned int v = lut[b];
+                    unsigned int incl = v;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const unsigned int x = __shfl_up_sync(0xffffffffu, incl, o); if (ln >= o) incl += x; }
+                    lut[b] = (carry + incl - v) | (v << 16);
+                    carry += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                if (ln == 0) s_warp[wid] = carry;
+                __syncthreads();
+                unsigned int base = 0;
+                for (int w = 0; w < wid; ++w) base += s_warp[w];
+                if (base)
+                    for (int c = 0; c < kPerWarp; c += 32) lut[wid * kPerWarp + c + ln] += base;
+                __syncthreads();
+            }
+            DD_PHASE(1);
+        } else {
         // ---- A. query metadata ----------------------------------------------------------------
         for (int ql = tid; ql < nq; ql += kDdThreads) {
             const long long q = a.qlist[item.qb + ql];
@@ -313,7 +397,7 @@ count_dedup_kernel(DedupArgs a) {
             }
         }
         __syncthreads();
-        const int T = s_T;
+        T = s_T;
         // lut[b] = first statistic of bucket b | number of statistics in it << 16 (the cursors have counted them; T <= 8192):
         // one shared-memory load per streamed value gives its whole search window
         for (int b = tid; b < kDdBuckets; b += kDdThreads) lut[b] |= cursor[b] << 16;
@@ -330,28 +414,41 @@ count_dedup_kernel(DedupArgs a) {
                 const double x = g_thr[m];
                 rank += (x < t) || (x == t && m < e);
             }
-            thr64[lo + rank] = t;
+            thr64_w[lo + rank] = t;
             thr32[lo + rank] = (float)t;
-            org[lo + rank] = g_org[e];
-            col[lo + rank] = g_col[e];
+            org_w[lo + rank] = g_org[e];
+            col_w[lo + rank] = g_col[e];
         }
         for (int p = tid; p <= T; p += kDdThreads) hist[p] = 0;
         if (tid == 0) { thr32[-1] = -CUDART_INF_F; thr32[T] = CUDART_INF_F; }
         __syncthreads();
+        }   // !PRE
         // ---- C'. hit columns: value == statistic exactly.  A column hit by several queries of the item appears as
         // several EQUAL statistics (same row, same column, same arithmetic) and is added once: by the statistic that
         // claims its bit in a second bitmap (short tables), or by the first of the equal statistics in sorted order
         // (long tables, where a second bitmap would cost the second resident CTA).
         if (a.bm_words) {
-            for (int sidx = tid; sidx < T; sidx += kDdThreads) {
-                const int c = col[sidx];
+            for (int s0 = 0; s0 < T; s0 += 4 * kDdThreads) {
+              int c4[4];
+              double t4[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {                           // the thread's four global loads in flight together
+                  const int sidx = s0 + tid + e * kDdThreads;
+                  c4[e] = (sidx < T) ? col[sidx] : 0;
+                  t4[e] = (sidx < T) ? thr64[sidx] : 0.0;
+              }
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int sidx = s0 + tid + e * kDdThreads;
+                if (sidx >= T) continue;
+                const int c = c4[e];
                 const float tf = thr32[sidx];                         // shared-memory filter in front of the L2-resident doubles
                 bool first = true;
                 if (a.claim) {                                        // short table: the first statistic to claim the column's bit
                     const unsigned int bit = 1u << (c & 31);
                     first = (atomicAnd(&bitmap[a.bm_words + (c >> 5)], ~bit) & bit) != 0;
                 }
-                const double t = thr64[sidx];
+                const double t = t4[e];
                 if (!a.claim)
                     for (int e1 = sidx - 1; e1 >= 0 && thr32[e1] == tf && thr64[e1] == t; --e1)
                         if (col[e1] == c) { first = false; break; }
@@ -360,6 +457,7 @@ count_dedup_kernel(DedupArgs a) {
                     while (e2 < T && thr32[e2] == tf && thr64[e2] == t) ++e2;   // statistics <= value: through the run of equals
                     atomicAdd(&hist[e2], 1u);
                 }
+              }
             }
             __syncthreads();
         }
@@ -489,6 +587,9 @@ count_dedup_kernel(DedupArgs a) {
             // all columns strictly below the column's own value (zero-variance columns: -99 < everything)
             unsigned int *rrow = a.rank_out + (long long)item.urow * a.ld + rank_c0;
             for (int s = tid; s < T; s += kDdThreads) rrow[org[s]] = hist[s] + (unsigned int)n_deg;
+        } else if (PRE) {
+            // streamed + hit columns strictly below each sorted statistic; score_scatter_kernel does the rest
+            for (int s = tid; s < T; s += kDdThreads) a.st_cnt[soff + s] = hist[s];
         } else
         for (int s = tid; s < T; s += kDdThreads) {
             const unsigned int o = org[s];
@@ -581,14 +682,17 @@ __global__ void score_table_kernel(double *tab, long long N, int anticor) {
 }
 
 // float reciprocal half-norms for the fp32 fast path + number of zero-variance rows
-__global__ void icol_kernel(const double *__restrict__ sx, long long N, long long N_pad, float *__restrict__ icol,
-                            int *__restrict__ n_degenerate) {
+// sxg: the half-norm with the raw-sum guard of the hit-vs-hit statistic folded in (coexfunctions.py:389): NaN for a row
+// whose raw values sum to <= 0, so that the statistic's own division yields NaN -> -99 without a second gather.
+__global__ void icol_kernel(const double *__restrict__ sx, const unsigned char *__restrict__ rawsum_pos, long long N,
+                            long long N_pad, float *__restrict__ icol, double *__restrict__ sxg, int *__restrict__ n_degenerate) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int deg = 0;
     if (t < N_pad) {
         const double s = sx[t];
         const bool ok = (t < N) && (s != 0.0);
         icol[t] = ok ? (float)(0.5 / s) : 0.0f;
+        sxg[t] = (t < N && rawsum_pos[t] != 0) ? s : CUDART_NAN;
         deg = (t < N && s == 0.0) ? 1 : 0;
     }
     deg = __syncthreads_count(deg);

@@ -148,14 +148,16 @@ int coex_network_batch(coex_ctx *ctx, const coex_params *params, int K,
 
 /* Introspection for bench.py: kernels launched by ctx so far, and per-stage device time (ms,
  * CUDA events on coex_stream) of the last coex_network_batch / coex_prepare call.
- * stage ids: 0 rank+pack, 1 row stats, 2 gather, 3 correlation GEMM, 4 count+score, 5 network */
+ * stage ids: 0 rank+pack, 1 row stats, 2 gather, 3 correlation GEMM, 4 count+score, 5 network, 6 statistics + sort
+ * (the set-up half of the count stage, stat_sort_kernel) */
 long long coex_launch_count(coex_ctx *ctx);
 int coex_stage_ms(coex_ctx *ctx, int stage, double *ms, long long *launches);
 /* 0 = tcgen05/TMA tensor-core GEMM (default: persistent kernel, 128 x 64 tiles, double-buffered TMEM),
  * 1 = SIMT dp4a GEMM (validation path), 2 = persistent tcgen05 kernel explicitly,
  * 64 / 128 = one-tile-per-CTA tcgen05 kernel with that table-column tile */
 int coex_set_gemm_mode(coex_ctx *ctx, int mode);
-/* 0 = de-duplicated sorted-statistics count kernel (default, count_dedup.cuh), 1 = per-query binary-search kernel,
+/* 0 = de-duplicated sorted-statistics count kernel (default, count_dedup.cuh; 4 = the same split into a sort, a streaming and
+ * a score kernel, count_split.cuh -- a cross-check, slower at the bench shape), 1 = per-query binary-search kernel,
  * 2 = de-duplicated bucket-window kernel (count_rows.cuh): three independent implementations of the same counts.
  * Mode 0 switches by itself to ROW-RANK mode (every strip row ranked once, the queries look their bisect indices up) when the hit
  * sets are so large that this is cheaper (config C5: thousands of hits per set); 3 forces that mode. */
