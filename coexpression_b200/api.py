@@ -148,12 +148,15 @@ class CoexContext:
                               np.asarray(end, dtype=np.int64), name_rank)
 
     def permute_map(self, mode, snp_chrom, snp_addr, shifts, chromlist, chromrange, window, background=None,
-                    capacity=None):
+                    capacity=None, picks=None):
         """Row N1: the promoters of K permuted locus sets in one call (reference 0-prepare-coex.py:471-613 + windowBed).
         snp_chrom: chromosome names of the real loci, snp_addr their addresses; shifts[k] == 0 is the real data;
         chromlist / chromrange as built at 0-prepare-coex.py:319-330.  mode 'backcirc' needs `background` = the
         list of (chrom, address) sorted by (genome-wide address, key) (0-prepare-coex.py:582), which must contain
-        every real locus.  -> list of K int32 arrays of table rows (first-appearance order)."""
+        every real locus.  mode 'background' (0-prepare-coex.py:564-578): `background` = (chrom, address) of every line
+        of the background file in file order (column 0, column 2) and `picks[k]` = the M line numbers
+        `random.sample(range(len(background)), M)` drew for set k (ignored where shifts[k] == 0).
+        -> list of K int32 arrays of table rows (first-appearance order)."""
         if self._feature_chroms is None:
             raise _lib.CoexError("permute_map: call set_features first")
         cidx = {c: i for i, c in enumerate(chromlist)}
@@ -164,7 +167,7 @@ class CoexContext:
         cs = np.ascontiguousarray([chromrange[c][0] for c in chromlist], dtype=np.int64)
         ce = np.ascontiguousarray([chromrange[c][1] for c in chromlist], dtype=np.int64)
         cf = np.ascontiguousarray([fid.get(c, -1) for c in chromlist], dtype=np.int32)
-        m = {"circular": 0, "backcirc": 1}[mode]
+        m = {"circular": 0, "backcirc": 1, "background": 2}[mode]
         sb = bc = ba = None
         nb = 0
         if m == 1:
@@ -174,6 +177,11 @@ class CoexContext:
             ba = np.ascontiguousarray([a for _, a in background], dtype=np.int64)
             nb = len(background)
         K, M = len(sh), len(sc)
+        if m == 2:
+            sb = np.ascontiguousarray(picks, dtype=np.int64).reshape(K, M)
+            bc = np.ascontiguousarray([cidx[c] for c, _ in background], dtype=np.int32)
+            ba = np.ascontiguousarray([a for _, a in background], dtype=np.int64)
+            nb = len(background)
         cap = int(capacity if capacity is not None else max(1024, 64 * K * M))
         off = np.zeros(K + 1, dtype=np.int64)
         rows = np.zeros(cap, dtype=np.int32)

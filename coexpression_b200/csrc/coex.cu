@@ -847,28 +847,29 @@ int coex_permute_map(coex_ctx *c, int mode, const int *snp_chrom, const long lon
                      int on_device) {
     COEX_TRY(check_ctx(c));
     if (!c->have_features) COEX_FAIL("coex_permute_map: call coex_set_features first");
-    if (mode != 0 && mode != 1) COEX_FAIL("coex_permute_map: mode 0 = circular, 1 = backcirc");
+    if (mode != 0 && mode != 1 && mode != 2) COEX_FAIL("coex_permute_map: mode 0 = circular, 1 = backcirc, 2 = background");
     if (M <= 0 || K <= 0 || n_chrom <= 0 || !snp_chrom || !snp_addr || !shifts || !chrom_start || !chrom_end || !chrom_fid ||
         !perm_off || (!hit_rows && capacity > 0))
         COEX_FAIL("coex_permute_map: null or empty argument");
-    if (mode == 1 && (!snp_back || !back_chrom || !back_addr || n_back <= 0)) COEX_FAIL("coex_permute_map: backcirc needs the sorted background");
+    if (mode >= 1 && (!snp_back || !back_chrom || !back_addr || n_back <= 0)) COEX_FAIL("coex_permute_map: backcirc / background need the background");
+    const size_t n_sb = (mode == 2) ? (size_t)K * M : (size_t)M;     // background: one drawn line per (set, locus)
     if (window < 0) COEX_FAIL("coex_permute_map: negative window");
     for (int m = 0; m < M; ++m)
         if (snp_chrom[m] < 0 || snp_chrom[m] >= n_chrom) COEX_FAIL("coex_permute_map: chromosome index out of range");
     cudaStream_t st = c->stream;
     // ---- stage the (small) inputs in one blob ------------------------------------------------------
     auto al = [](size_t x) { return (x + 15) / 16 * 16; };
-    const size_t o_sc = 0, o_sa = al(o_sc + (size_t)M * 4), o_sb = al(o_sa + (size_t)M * 8), o_sh = al(o_sb + (size_t)M * 8),
+    const size_t o_sc = 0, o_sa = al(o_sc + (size_t)M * 4), o_sb = al(o_sa + (size_t)M * 8), o_sh = al(o_sb + n_sb * 8),
                  o_cs = al(o_sh + (size_t)K * 8), o_ce = al(o_cs + (size_t)n_chrom * 8), o_cf = al(o_ce + (size_t)n_chrom * 8),
                  o_bc = al(o_cf + (size_t)n_chrom * 4), o_ba = al(o_bc + (size_t)std::max<long long>(n_back, 0) * 4),
                  total = al(o_ba + (size_t)std::max<long long>(n_back, 0) * 8);
     std::vector<unsigned char> blob(total, 0);
     memcpy(&blob[o_sc], snp_chrom, (size_t)M * 4); memcpy(&blob[o_sa], snp_addr, (size_t)M * 8);
-    if (snp_back) memcpy(&blob[o_sb], snp_back, (size_t)M * 8);
+    if (snp_back) memcpy(&blob[o_sb], snp_back, n_sb * 8);
     memcpy(&blob[o_sh], shifts, (size_t)K * 8);
     memcpy(&blob[o_cs], chrom_start, (size_t)n_chrom * 8); memcpy(&blob[o_ce], chrom_end, (size_t)n_chrom * 8);
     memcpy(&blob[o_cf], chrom_fid, (size_t)n_chrom * 4);
-    if (mode == 1) {
+    if (mode >= 1) {
         for (long long i = 0; i < n_back; ++i)
             if (back_chrom[i] < 0 || back_chrom[i] >= n_chrom) COEX_FAIL("coex_permute_map: background chromosome index out of range");
         memcpy(&blob[o_bc], back_chrom, (size_t)n_back * 4); memcpy(&blob[o_ba], back_addr, (size_t)n_back * 8);

@@ -6,6 +6,9 @@
 //   shift + get_address . reference 0-prepare-coex.py:548-563 (circular, and every mode's real data: shift == 0),
 //                         coexfunctions.py:115-128 (`while gwad > genome_max`, `start < gwad <= end`, else chr1:0)
 //   backcirc ............ reference 0-prepare-coex.py:579-593 with listitem, coexfunctions.py:319-325 (C round())
+//   background .......... reference 0-prepare-coex.py:564-578: every locus of a permuted set is a line of the background
+//                         file drawn by `random.sample` (the draw itself stays on the host: it is the reference's RNG
+//                         stream); chromosome = column 0, address = column 2 of that line
 //   windowBed -w W ...... bedtools window: A = [address, address + 1) widened by W (start clamped at 0), every
 //                         feature with a.start' < b.end and b.start < a.end' on the same chromosome
 //   promoters ........... first-appearance order over (locus in input order, feature in ascending table row), the
@@ -21,11 +24,11 @@
 namespace coex {
 
 struct PermuteArgs {
-    int mode;                        // 0 circular, 1 backcirc
+    int mode;                        // 0 circular, 1 backcirc, 2 background
     int M, K;
     const int *snp_chrom;            // [M] index into the chromosome list
     const long long *snp_addr;       // [M] address on that chromosome
-    const long long *snp_back;       // [M] index of the SNP in the sorted background (mode 1)
+    const long long *snp_back;       // mode 1: [M] index of the SNP in the sorted background; mode 2: [K, M] drawn background lines
     const long long *shifts;         // [K]
     const long long *chrom_start, *chrom_end;   // [n_chrom] genome-wide range of every chromosome of the list
     const int *chrom_fid;            // [n_chrom] id of the chromosome among the feature chromosomes (-1 = none)
@@ -53,7 +56,12 @@ __device__ __forceinline__ void permuted_position(const PermuteArgs &a, int k, i
     const long long shift = a.shifts[k];
     int ci;
     long long ad;
-    if (a.mode == 1 && shift != 0) {
+    if (a.mode == 2 && shift != 0) {
+        const long long d = a.snp_back[(long long)k * a.M + m];     // the line random.sample drew for this locus
+        if (d < 0 || d >= a.n_back) { fid = -1; addr = 0; return; }
+        ci = a.back_chrom[d];
+        ad = a.back_addr[d];
+    } else if (a.mode == 1 && shift != 0) {
         // listitem(sortedbackground, index + shift), coexfunctions.py:319-325
         const double n = (double)a.n_back;
         const double x = (double)(a.snp_back[m] + shift) / n;

@@ -69,11 +69,14 @@ int coex_set_global_list(coex_ctx *ctx, const double *sorted_values, long long l
 /* Row N1: K permuted locus sets and their promoters in one call, replacing the per-permutation
  * Python loops of 0-prepare-coex.py:548-593 (get_gwad / shift / get_address, coexfunctions.py:102-128; backcirc with
  * listitem, :319-325) and the `windowBed -w window` subprocess that follows each of them (0-prepare-coex.py:357,609).
- *   mode 0 = circular, 1 = backcirc; shifts[k] == 0 is the real data (always the circular arithmetic, as in the
- *   reference).  snp_chrom[m] indexes the chromosome list (chromrange order, 0-prepare-coex.py:319-330) whose
+ *   mode 0 = circular, 1 = backcirc, 2 = background (0-prepare-coex.py:564-578); shifts[k] == 0 is the real data
+ *   (always the circular arithmetic, as in the reference).  snp_chrom[m] indexes the chromosome list (chromrange order, 0-prepare-coex.py:319-330) whose
  *   genome-wide ranges are chrom_start / chrom_end; chrom_fid[c] is the chrom_id that chromosome has in
  *   coex_set_features (-1 if no feature lies on it).  backcirc: snp_back[m] = index of SNP m in the background
  *   sorted by (genome-wide address, key) (0-prepare-coex.py:582), back_chrom / back_addr its entries.
+ *   background: back_chrom / back_addr = column 0 / column 2 of every line of the background file in FILE order and
+ *   snp_back[k * M + m] = the line `random.sample(range(n_back), M)` drew for locus m of set k (the draw stays with the
+ *   caller: it is the reference's RNG stream); any non-zero shifts[k] marks a permuted set.
  * Output: perm_off[K+1] and hit_rows (table rows, first-appearance order) exactly as coex_network_batch takes them;
  * host arrays, or device arrays when on_device != 0.  Fails if capacity is too small. */
 int coex_permute_map(coex_ctx *ctx, int mode, const int *snp_chrom, const long long *snp_addr,

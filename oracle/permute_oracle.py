@@ -9,6 +9,7 @@ Follows, with explicit orders where the reference iterates Python-2 dicts:
                          `round()` rounds halves AWAY from zero, Python 3 to even: restated explicitly.
   circular mode ........ reference 0-prepare-coex.py:548-563
   backcirc mode ........ reference 0-prepare-coex.py:579-593  (sorted background by (gwad, key), :582)
+  background mode ...... reference 0-prepare-coex.py:564-578  (random.sample of background lines; the draw is an input here)
   temporary BED ........ reference 0-prepare-coex.py:598-607  `chrom(without chr) address address+1 name`
   windowBed -w W ....... bedtools (v2.x, README.md:24; NOT under /root/reference and not installed here): published
                          semantics restated -- A is widened by W on both sides (start clamped at 0) and every B with
@@ -94,6 +95,17 @@ def backcirc_positions(snps, shift, sortedbackground):
         idx = listitem_index(n, pos["%s_%s" % (chrom, address)] + shift)
         new = sortedbackground[idx].split("_")
         out.append((new[0], int(new[1])))
+    return out
+
+
+def background_positions(backlines, picks):
+    """0-prepare-coex.py:564-578: backlines = the background file's lines split on tabs, picks = the line numbers
+    random.sample drew.  chrom = column 0 without `chr` (the `chr` is put back here: window_bed matches feature
+    chromosomes WITH the prefix, as the feature BED is written without it on both sides), address = column 2."""
+    out = []
+    for linenum in picks:
+        line = backlines[linenum]
+        out.append(("chr" + line[0].replace("chr", ""), int(line[2])))
     return out
 
 

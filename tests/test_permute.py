@@ -106,6 +106,44 @@ def test_gpu_backcirc_matches_restatement():
         assert got[k].tolist() == want, (k, s)
 
 
+def test_background_positions_known_answers():
+    # 0-prepare-coex.py:568-572: chrom = column 0 without chr, address = column 2 (the END column), one locus per drawn line
+    backlines = [["chr1", "99", "100", "x", "rsA"], ["2", "500", "501", "x", "rsB"], ["chrX", "7", "8", "x", "rsC"]]
+    assert po.background_positions(backlines, [2, 0]) == [("chrX", 8), ("chr1", 100)]
+    assert po.background_positions(backlines, [1]) == [("chr2", 501)]
+
+
+@pytest.mark.gpu
+def test_gpu_background_matches_restatement():
+    import random
+    from coexpression_b200.api import CoexContext
+    t, chromlist, cr, snps, rng = _synthetic_inputs(11)
+    # a background file: 4000 lines `chrom start end id snp`, some of them next to features, duplicates allowed
+    backlines = []
+    for _ in range(4000):
+        c = chromlist[int(rng.integers(0, len(chromlist)))]
+        a = int(rng.integers(1, t.chrom_len[c] - 1))
+        backlines.append([c.replace("chr", ""), str(a - 1), str(a), "bg", "rs%d" % a])
+    backlines += backlines[:50]
+    pyrand = random.Random(17)
+    K = 9
+    shifts = [0] + list(range(1, K))                       # 0-prepare-coex.py:486-489: shift = i + 1, 0 = real data
+    picks = [pyrand.sample(range(len(backlines)), len(snps)) for _ in range(K)]
+    background = [("chr" + l[0], int(l[2])) for l in backlines]
+    with CoexContext() as ctx:
+        ctx.set_expression(t.X); ctx.prepare()
+        ctx.set_features(t.chrom, t.start, t.end, t.names)
+        got = ctx.permute_map("background", [c for c, _ in snps], [a for _, a in snps], shifts, chromlist, cr, 20000,
+                              background=background, picks=picks)
+    n_hits = 0
+    for k, s in enumerate(shifts):
+        pos = po.circular_positions(snps, 0, cr, chromlist) if s == 0 else po.background_positions(backlines, picks[k])
+        want = po.hit_rows(po.window_bed(pos, t.chrom, t.start, t.end, 20000))
+        assert got[k].tolist() == want, (k, s)
+        n_hits += len(want)
+    assert n_hits > K
+
+
 @pytest.mark.gpu
 def test_gpu_mapped_sets_feed_the_network_batch():
     """End to end on the device path: permute_map -> network_batch gives what host-made hit lists give."""
