@@ -284,9 +284,16 @@ def make_network(names, X, promoters, addresses, globalcorrelationlist,
                  correlationmeasure="Spearman", anticorrelation=False, noiter=False,
                  pval_to_join=0.1, soft_separation=100000, nsp=1.0, useaverage=False,
                  selectionthreshold=0.0, selectionthreshold_is_j=False,
-                 mode="consistent", kind=None, Xrank=None, return_counts=False):
+                 mode="consistent", kind=None, Xrank=None, return_counts=False, group_order=None,
+                 indjoined_order="groups"):
     """One permutation.  names: row labels in table order; X: float64 [N, n] raw table;
     promoters: hit labels in map-file first-appearance order (all present in `names`).
+    group_order: the order in which the groups are visited (quirk Q6: the second winner pass depends on it; the
+    reference takes whatever order its `prom_to_join` dict has).  Default: ascending label, the order this repo fixes
+    for both sides; tests/test_reference_pin.py passes the order an executed reference run used.
+    indjoined_order: order of the addends of a density (`indjoined[g]` is summed in its dict order, :456-482).
+    "groups" = the group order (what this repo fixes for both sides); "insertion" = the order in which the loops at
+    :437-452 insert the keys into an insertion-ordered dict, i.e. what the reference does under Python 3.
     Returns the objects 1-make-network.py:523-532 dumps (without snp_map)."""
     names = list(names)
     X = np.ascontiguousarray(X, dtype=np.float64)
@@ -363,6 +370,9 @@ def make_network(names, X, promoters, addresses, globalcorrelationlist,
     prom_to_join = join_nearby(all_proms, addresses, globalcorrelationlist, corr, row_of,
                                pval_to_join, correlationmeasure, soft_separation,
                                anticorrelation)                          # :347-348
+    if group_order is not None:
+        assert sorted(group_order) == sorted(prom_to_join), "group_order must list exactly the group labels"
+        prom_to_join = {k: prom_to_join[k] for k in group_order}
     joining_instructions = {}
     for label in prom_to_join:
         for prom in prom_to_join[label]:
@@ -398,15 +408,27 @@ def make_network(names, X, promoters, addresses, globalcorrelationlist,
             winners[label] = best
 
     indjoined = {}                                                        # :437-452
-    for label in prom_to_join:
-        if winners.get(label) is None:
-            continue
-        indjoined[label] = {}
-        for other in prom_to_join:
-            if other == label:
-                continue
-            chosen, other_chosen = winners[label], winners[other]
-            indjoined[label][other] = individualscores[chosen][other_chosen]
+    if indjoined_order == "insertion":
+        for prom in individualscores:
+            label = joining_instructions[prom]
+            chosen = winners[label]
+            if label not in indjoined:
+                indjoined[label] = {}
+            for other_prom in individualscores[prom]:
+                other = joining_instructions[other_prom]
+                other_chosen = winners[other]
+                if chosen != other_chosen:
+                    indjoined[label][other] = individualscores[chosen][other_chosen]
+    else:
+      for label in prom_to_join:
+          if winners.get(label) is None:
+              continue
+          indjoined[label] = {}
+          for other in prom_to_join:
+              if other == label:
+                  continue
+              chosen, other_chosen = winners[label], winners[other]
+              indjoined[label][other] = individualscores[chosen][other_chosen]
 
     indmeasure = {}                                                       # :456-462
     for g in indjoined:

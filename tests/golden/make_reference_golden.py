@@ -1,0 +1,153 @@
+"""Golden vectors from the reference's OWN Python, executed in this container (tests/golden/run_reference_py3.py).
+
+Run HERE, where /root/reference exists:
+    make -C oracle && PYTHONHASHSEED=0 python tests/golden/make_reference_golden.py
+
+Writes tests/golden/reference_run_<case>.json.gz: the inputs (table, features, global list, map-file promoters) and the
+seven result objects `1-make-network.py` dumped for them (perm_results_store/<feat>.<object>.<k>), plus
+tests/golden/reference_functions.json: known answers of the reference's `coexfunctions` helpers (get_gwad, get_address,
+merge_ranges, empiricalp, fdr_correction) called directly.  tests/test_reference_pin.py checks oracle/network_oracle.py
+and oracle/permute_oracle.py against them -- nothing there reads /root/reference.
+"""
+import gzip
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+from coexpression_b200 import synth  # noqa: E402
+from oracle import network_oracle as no  # noqa: E402
+
+OBJECTS = ("indmeasure", "individualscores", "prom_to_join", "indjoined", "joining_instructions", "winners",
+           "allpromoterscores", "snp_map")
+
+# name: (table seed, N, n, loci, window, settings overrides)
+CASES = {
+    "spearman_default": (44, 300, 24, 24, 30000, {}),
+    "spearman_anticor": (45, 300, 24, 24, 30000, {"anticorrelation": "True"}),
+    "spearman_noiter_j001": (46, 260, 31, 22, 40000, {"noiter": "True", "pval_to_join": 0.01}),
+    "spearman_useavg_m": (47, 260, 20, 22, 40000, {"useaverage": "True", "selectionthreshold_is_j": "True"}),
+    "pearson_default": (48, 240, 24, 20, 30000, {"correlationmeasure": "Pearson"}),
+    "spearman_global_nsp0": (49, 240, 24, 20, 30000, {"nsp": 0.0}),
+    "spearman_wide_join": (50, 300, 16, 26, 60000, {"pval_to_join": 0.6, "soft_separation": 400000}),
+}
+
+
+def run_case(name, seed, N, n, n_loci, window, overrides):
+    t = synth.make_table(N, n, seed=seed)
+    measure = overrides.get("correlationmeasure", "Spearman")
+    with tempfile.TemporaryDirectory() as tmp:
+        wd = os.path.join(tmp, "work")
+        os.makedirs(os.path.join(wd, "permutation_store"))
+        os.makedirs(os.path.join(wd, "perm_results_store"))
+        expr, bed = os.path.join(tmp, "t.expression"), os.path.join(tmp, "f5ep.bed")
+        clist = os.path.join(tmp, "t.expression.%s" % ("spearmanlist" if measure == "Spearman" else "correlationlist"))
+        synth.write_expression_file(expr, t)
+        synth.write_feature_bed(bed, t)
+        data = no.rank_rows(t.X) if measure == "Spearman" else t.X
+        ga, gb = synth.global_pair_indices(t.names, 4000, seed=seed + 100)
+        g = no.get_pearson(data, ga, gb, "reference")
+        glist = np.sort(np.where(np.isnan(g), -99.0, g))
+        with open(clist, "w") as o:
+            for v in glist:
+                o.write("%s\n" % (int(v) if v == -99 else repr(float(v))))
+        m = synth.Mapper(t)
+        loci = synth.make_loci(t, n_loci, seed=seed + 200)
+        sets = synth.circular_shifts(loci, m.genome_len, 1, seed=seed + 300)
+        mapfiles = []
+        for k, gw in enumerate(sets):
+            mf = os.path.join(wd, "permutation_store", "f5ep.%d.bed" % k)
+            synth.write_map_file(mf, t, m, gw, window, prefix="rs" if k == 0 else "rand_rs")
+            mapfiles.append(mf)
+        cfg = os.path.join(tmp, "app.cfg")
+        with open(cfg, "w") as o:
+            o.write("[directorypaths]\nsourcefilesdir=%s\nresdir=%s\npathtobedtools=/nonexistent\n" % (tmp, tmp))
+        settings = {"verbose": "False", "feature_coordinates": bed, "correlationfile": clist, "expression_file": expr,
+                    "supplementary_label": "x", "correlationmeasure": "Spearman", "soft_separation": 100000, "nsp": 1.0,
+                    "seedfile": "none", "pval_to_join": 0.1, "useaverage": "False", "anticorrelation": "False",
+                    "noiter": "False", "selectionthreshold": 0, "selectionthreshold_is_j": "False", "config_file": cfg}
+        settings.update(overrides)
+        with open(os.path.join(wd, "settings.txt"), "w") as o:
+            json.dump(settings, o)
+        runs = []
+        for k, mf in enumerate(mapfiles):
+            r = subprocess.run([sys.executable, os.path.join(HERE, "run_reference_py3.py"), os.path.join(tmp, "app"), wd, mf],
+                               capture_output=True, text=True, env=dict(os.environ, PYTHONHASHSEED="0"))
+            assert r.returncode == 0, r.stderr[-3000:]
+            store = os.path.join(wd, "perm_results_store")
+            runs.append({obj: json.load(open(os.path.join(store, "f5ep.%s.%d" % (obj, k)))) for obj in OBJECTS})
+        out = {
+            "case": name, "settings": {k: v for k, v in settings.items() if k not in
+                                       ("feature_coordinates", "correlationfile", "expression_file", "config_file")},
+            "names": list(t.names), "X": [[float(v) for v in row] for row in t.X],
+            "addresses": {nm: list(a) for nm, a in t.addresses().items()},
+            "glist": [float(v) for v in glist], "runs": runs,
+            "how": "unmodified /root/reference/coexfunctions.py + mechanically 2to3-rewritten /root/reference/1-make-network.py, "
+                   "executed by tests/golden/run_reference_py3.py against the unmodified reference C build",
+        }
+        path = os.path.join(HERE, "reference_run_%s.json.gz" % name)
+        with gzip.open(path, "wt") as o:
+            json.dump(out, o)
+        print(name, "P =", [len(r["snp_map"]) for r in runs], "groups =", [len(r["prom_to_join"]) for r in runs],
+              os.path.getsize(path), "bytes")
+
+
+def function_vectors():
+    from run_reference_py3 import import_reference_coexfunctions
+    cf = import_reference_coexfunctions()
+    rng = np.random.default_rng(7)
+    chromlist = ["chr1", "chr2", "chr3", "chrX"]
+    lengths = {"chr1": 1000, "chr2": 750, "chr3": 10, "chrX": 333}
+    chromrange, acc = {}, 0
+    for c in chromlist:
+        chromrange[c] = [acc, acc + lengths[c]]
+        acc += lengths[c]
+    gw = []
+    for _ in range(200):
+        c = chromlist[int(rng.integers(0, 4))]
+        a = int(rng.integers(-5, lengths[c] + 5))
+        gw.append([c, a, cf.get_gwad(c, a, chromrange)])
+    ad = []
+    for g in list(range(-3, 12)) + [int(v) for v in rng.integers(0, 3 * acc, 200)] + [acc, acc + 1, 2 * acc, 2 * acc + 1]:
+        ad.append([g, list(cf.get_address(g, chromrange, chromlist))])
+    mr = []
+    for _ in range(40):
+        k = int(rng.integers(1, 12))
+        starts = np.sort(rng.integers(0, 2000, k))
+        rngs = np.stack([starts, starts + rng.integers(1, 60, k)], axis=1)
+        ss = int(rng.choice([0, 10, 100, 500]))
+        merged = [[int(a), int(b)] for a, b in cf.merge_ranges(rngs, ss)]
+        mr.append([rngs.tolist(), ss, merged])
+    ep = []
+    for _ in range(60):
+        coll = [float(v) for v in np.round(rng.normal(0, 3, int(rng.integers(0, 30))), 1)]
+        v = float(np.round(rng.normal(0, 3), 1))
+        ep.append([v, coll, cf.empiricalp(v, list(coll))])
+    fd = []
+    for method in ("indep", "negcorr"):
+        for _ in range(15):
+            p = [float(v) for v in rng.random(int(rng.integers(1, 40))) ** 3]
+            rej, corr = cf.fdr_correction(p, 0.05, method)
+            fd.append([p, method, [bool(x) for x in rej], [float(x) for x in corr]])
+    with open(os.path.join(HERE, "reference_functions.json"), "w") as o:
+        json.dump({"chromlist": chromlist, "chromrange": chromrange, "get_gwad": gw, "get_address": ad,
+                   "merge_ranges": mr, "empiricalp": ep, "fdr_correction": fd,
+                   "how": "direct calls of the unmodified /root/reference/coexfunctions.py under Python 3"}, o)
+    print("reference_functions.json", len(gw), len(ad), len(mr), len(ep), len(fd))
+
+
+if __name__ == "__main__":
+    assert "reference" in no.available_kinds(), "build oracle/_ref/coexpression_v2.so first (make -C oracle)"
+    function_vectors()
+    for name, spec in CASES.items():
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue
+        run_case(name, *spec)
