@@ -30,13 +30,21 @@ Parity status
   * A2 is PINNED against scipy.stats.rankdata (the reference's own third-party call,
     scipy 0.19.0 in environment.yml:58; `method='average'` semantics are unchanged in the
     scipy 1.18 installed here).
-  * A3-A14: the reference ships NO tests, golden vectors or fixtures for this path and its
-    Python-2 drivers cannot run in this image, so the Python
-    part of this restatement is "parity unpinned" against executed reference output; it is
-    anchored on the reference's call sites cited above, on the pandas/networkx
-    transliteration of join_nearby in tests/test_oracle.py, and on golden fixtures
-    generated from THIS restatement driving the reference C build
-    (tests/golden/make_golden.py).
+  * A3-A13 are PINNED against the reference's own Python EXECUTED in the build container:
+    the reference ships no tests or fixtures and its drivers are Python 2,
+    but `coexfunctions.py` imports unmodified under Python 3 (matplotlib stubbed) and
+    `1-make-network.py` runs after a mechanical, line-local 2 -> 3 rewrite of its text
+    (tests/golden/run_reference_py3.py: print statements, iteritems, xrange, keys(), one tuple
+    lambda, ConfigParser; Python 2.7's plain `sum` restored), driving the unmodified reference C
+    build.  tests/golden/make_reference_golden.py committed its seven result objects for seven
+    option sets x two hit sets; the *faithful* mode below reproduces every one of them BIT FOR
+    BIT, dict key orders included, when given the two dict orders that run had
+    (`group_order`, `indjoined_order="insertion"`; tests/test_reference_pin.py).
+  * A8 additionally against a pandas/networkx transliteration (tests/test_oracle.py); A14's
+    `empiricalp` / `fdr_correction` and `merge_ranges` against direct calls of the reference's
+    functions (tests/golden/reference_functions.json).
+  * the fixtures of tests/golden/make_golden.py (larger shapes) come from THIS restatement
+    driving the reference C build.
 
 Two modes:
   faithful   -- the hit-vs-hit statistic comes from scipy.stats.spearmanr / pearsonr exactly

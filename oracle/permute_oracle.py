@@ -7,6 +7,9 @@ Follows, with explicit orders where the reference iterates Python-2 dicts:
                          `while gwad > genome_max` wrap and the half-open test `start < gwad <= end`)
   listitem ............. reference coexfunctions.py:319-325   index wrap used by the 'backcirc' mode.  Python 2
                          `round()` rounds halves AWAY from zero, Python 3 to even: restated explicitly.
+                         get_gwad / get_address / listitem are PINNED against direct calls of the reference's own
+                         functions (tests/golden/reference_functions.json, tests/test_reference_pin.py; listitem on
+                         the indices where Python 2 and 3 rounding agree, the half-away rule by its own test).
   circular mode ........ reference 0-prepare-coex.py:548-563
   backcirc mode ........ reference 0-prepare-coex.py:579-593  (sorted background by (gwad, key), :582)
   background mode ...... reference 0-prepare-coex.py:564-578  (random.sample of background lines; the draw is an input here)

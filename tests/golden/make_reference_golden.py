@@ -6,11 +6,12 @@ Run HERE, where /root/reference exists:
 Writes tests/golden/reference_run_<case>.json.gz: the inputs (table, features, global list, map-file promoters) and the
 seven result objects `1-make-network.py` dumped for them (perm_results_store/<feat>.<object>.<k>), plus
 tests/golden/reference_functions.json: known answers of the reference's `coexfunctions` helpers (get_gwad, get_address,
-merge_ranges, empiricalp, fdr_correction) called directly.  tests/test_reference_pin.py checks oracle/network_oracle.py
+listitem, merge_ranges, empiricalp, fdr_correction) called directly.  tests/test_reference_pin.py checks oracle/network_oracle.py
 and oracle/permute_oracle.py against them -- nothing there reads /root/reference.
 """
 import gzip
 import json
+import math
 import os
 import subprocess
 import sys
@@ -137,8 +138,21 @@ def function_vectors():
             p = [float(v) for v in rng.random(int(rng.integers(1, 40))) ** 3]
             rej, corr = cf.fdr_correction(p, 0.05, method)
             fd.append([p, method, [bool(x) for x in rej], [float(x) for x in corr]])
+    # listitem (coexfunctions.py:319-325) rounds with the built-in round(): half away from zero in Python 2.7, half to
+    # even in Python 3.  Only indices on which the two agree are recorded (no exact halves): the half-away rule of the
+    # restatement is covered by its own known-answer test (tests/test_permute.py).
+    li = []
+    for _ in range(300):
+        n_items = int(rng.integers(1, 400))
+        index = int(rng.integers(-3 * n_items, 10_000_000_000))
+        a = float(index) / n_items
+        b = a - int(round(a, 0))
+        c = b * n_items
+        if abs(abs(a - math.floor(a)) - 0.5) < 1e-9 or abs(abs(c - math.floor(c)) - 0.5) < 1e-9:
+            continue
+        li.append([n_items, index, cf.listitem(list(range(n_items)), index)])
     with open(os.path.join(HERE, "reference_functions.json"), "w") as o:
-        json.dump({"chromlist": chromlist, "chromrange": chromrange, "get_gwad": gw, "get_address": ad,
+        json.dump({"chromlist": chromlist, "chromrange": chromrange, "get_gwad": gw, "get_address": ad, "listitem": li,
                    "merge_ranges": mr, "empiricalp": ep, "fdr_correction": fd,
                    "how": "direct calls of the unmodified /root/reference/coexfunctions.py under Python 3"}, o)
     print("reference_functions.json", len(gw), len(ad), len(mr), len(ep), len(fd))
@@ -147,6 +161,8 @@ def function_vectors():
 if __name__ == "__main__":
     assert "reference" in no.available_kinds(), "build oracle/_ref/coexpression_v2.so first (make -C oracle)"
     function_vectors()
+    if len(sys.argv) > 1 and sys.argv[1] == "functions":
+        sys.exit(0)
     for name, spec in CASES.items():
         if len(sys.argv) > 1 and name not in sys.argv[1:]:
             continue

@@ -100,6 +100,10 @@ def test_reference_helper_functions_known_answers():
         assert po.get_gwad(chrom, address, cr) == want
     for gwad, want in fx["get_address"]:
         assert list(po.get_address(gwad, cr, cl)) == want
+    for n_items, index, want in fx["listitem"]:
+        d = po.listitem_index(n_items, index)           # may be negative: Python indexes from the end
+        assert list(range(n_items))[d] == want
+    assert len(fx["listitem"]) > 200
     for ranges, ss, want in fx["merge_ranges"]:
         assert [[int(a), int(b)] for a, b in no.merge_ranges([tuple(r) for r in ranges], ss)] == want
     for v, coll, want in fx["empiricalp"]:
