@@ -198,7 +198,7 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     if (rows_kernel) {
         COEX_TRY(c->dd_gthr.reserve((size_t)grid_max * Tcap));
     } else if (!split) {
-        COEX_TRY(c->dd_gthr.reserve((size_t)grid_max * Tcap * 3)); COEX_TRY(c->dd_gorg.reserve((size_t)grid_max * Tcap * 5));
+        COEX_TRY(c->dd_gthr.reserve((size_t)grid_max * Tcap * 6));      // 3 x Tcap records of 16 bytes per CTA
     }
     COEX_TRY(c->dd_tab.reserve((size_t)N + 1));
     score_table_kernel<<<(unsigned)((N + 256) / 256), 256, 0, st>>>(c->dd_tab.p, N, prm->anticorrelation);
@@ -231,7 +231,7 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
                 long long max_items = 1;
                 for (int s = 0; s < n_strips; ++s) max_items = std::max(max_items, strip_item_begin[(size_t)s + 1] - strip_item_begin[(size_t)s]);
                 st_cap = (unsigned long long)std::max<long long>(1, std::min<long long>(SCtot, max_items * (long long)Tcap));
-                COEX_TRY(c->st_thr.reserve(st_cap)); COEX_TRY(c->st_w.reserve(st_cap)); COEX_TRY(c->st_col.reserve(st_cap));
+                COEX_TRY(c->st_thr.reserve(2 * st_cap)); COEX_TRY(c->st_w.reserve(st_cap));
                 COEX_TRY(c->st_cnt.reserve(st_cap)); COEX_TRY(c->st_cursor.reserve(1));
                 COEX_TRY(c->st_itemoff.reserve((size_t)max_items)); COEX_TRY(c->st_itemT.reserve((size_t)max_items));
             }
@@ -244,17 +244,17 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
                 int rper = 1;
                 COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rper, count_dedup_kernel<2>, kDdThreads, rsmem));
                 rank_grid_max = std::max(1, rper) * c->sm_count;
-                COEX_TRY(c->dd_gthr.reserve((size_t)rank_grid_max * kRankTcap * 3)); COEX_TRY(c->dd_gorg.reserve((size_t)rank_grid_max * kRankTcap * 5));
+                COEX_TRY(c->dd_gthr.reserve((size_t)rank_grid_max * kRankTcap * 6));
                 COEX_TRY(c->rank_strip.reserve((size_t)Us * ld));
             }
             const int nchunk = (int)((N + kRankTcap - 1) / kRankTcap);
             DedupArgs da{};
             da.strip = c->strip.p; da.ld = ld; da.items = nullptr; da.n_items = (int)(nu * nchunk);
             da.uniq_rows = c->dd_uniq.p + u0; da.qlist = c->dd_qlist.p; da.perm_off = c->d_perm_off.p; da.sc_off = c->d_sc_off.p;
-            da.K = K; da.hit_rows = d_hits; da.sx = c->sx.p; da.icol = c->icol.p; da.rawsum_pos = c->rawsum_pos.p; da.N = N;
+            da.K = K; da.hit_rows = d_hits; da.sx = c->sx.p; da.sxg = c->sxg.p; da.icol = c->icol.p; da.rawsum_pos = c->rawsum_pos.p; da.N = N;
             da.n_degenerate = c->d_ndeg.p; da.anticor = prm->anticorrelation; da.scores = d_sc; da.counts = d_cn;
             da.Tcap = kRankTcap; da.Qcap = Qcap; da.bm_words = bm_words; da.claim = rclaim;
-            da.R = std::min(1.0, std::max(0.05, 8.0 / std::sqrt((double)std::max(c->n, 2)))); da.g_thr = c->dd_gthr.p; da.g_org = c->dd_gorg.p;
+            da.R = std::min(1.0, std::max(0.05, 8.0 / std::sqrt((double)std::max(c->n, 2)))); da.g_rec = reinterpret_cast<StatRec *>(c->dd_gthr.p);
             da.score_tab = c->dd_tab.p; da.phase_clk = nullptr; da.rank_out = c->rank_strip.p;
             COEX_TRY(stage_begin(c, ST_COUNT));
             count_dedup_kernel<2><<<std::min(rank_grid_max, std::max(da.n_items, 1)), kDdThreads, rsmem, st>>>(da);
@@ -281,7 +281,7 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
             sa.qlist = c->dd_qlist.p; sa.q_perm = c->dd_qperm.p; sa.perm_off = c->d_perm_off.p; sa.sc_off = c->d_sc_off.p;
             sa.hit_rows = d_hits; sa.sx = c->sx.p; sa.sxg = c->sxg.p; sa.rawsum_pos = c->rawsum_pos.p; sa.N = N; sa.scores = d_sc; sa.counts = d_cn;
             sa.Tcap = Tcap; sa.bscale = (float)((double)kDdBuckets / (2.0 * R));
-            sa.st_thr = c->st_thr.p; sa.st_w = c->st_w.p; sa.st_col = c->st_col.p; sa.st_cap = st_cap; sa.st_cursor = c->st_cursor.p;
+            sa.st_rec = reinterpret_cast<StatRec *>(c->st_thr.p); sa.st_w = c->st_w.p; sa.st_cap = st_cap; sa.st_cursor = c->st_cursor.p;
             sa.err = c->pl_err.p; sa.item_soff = c->st_itemoff.p; sa.item_T = c->st_itemT.p;
             sa.phase_clk = dbg ? phase.p + 8 : nullptr;
             stat_sort_kernel<<<std::min(sort_grid_max, std::max(n_items_s, 1)), kSsThreads, ssmem, st>>>(sa);
@@ -302,13 +302,13 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
             da.strip = c->strip.p; da.ld = ld; da.items = items_s; da.n_items = n_items_s;
             da.uniq_rows = c->dd_uniq.p + u0; da.qlist = c->dd_qlist.p;
             da.perm_off = c->d_perm_off.p; da.sc_off = c->d_sc_off.p; da.K = K; da.hit_rows = d_hits;
-            da.sx = c->sx.p; da.icol = c->icol.p; da.rawsum_pos = c->rawsum_pos.p; da.N = N;
+            da.sx = c->sx.p; da.sxg = c->sxg.p; da.icol = c->icol.p; da.rawsum_pos = c->rawsum_pos.p; da.N = N;
             da.n_degenerate = c->d_ndeg.p; da.anticor = prm->anticorrelation; da.scores = d_sc; da.counts = d_cn;
             da.Tcap = Tcap; da.Qcap = Qcap; da.bm_words = bm_words; da.claim = claim;
-            da.R = R; da.g_thr = c->dd_gthr.p; da.g_org = c->dd_gorg.p;
+            da.R = R; da.g_rec = reinterpret_cast<StatRec *>(c->dd_gthr.p);
             da.score_tab = c->dd_tab.p; da.phase_clk = dbg ? phase.p : nullptr;
             if (split) {
-                da.st_thr = c->st_thr.p; da.st_cnt = c->st_cnt.p; da.st_col = c->st_col.p; da.item_soff = c->st_itemoff.p;
+                da.st_rec = reinterpret_cast<const StatRec *>(c->st_thr.p); da.st_cnt = c->st_cnt.p; da.item_soff = c->st_itemoff.p;
                 da.item_T = c->st_itemT.p;
                 count_dedup_kernel<3><<<grid, kDdThreads, smem, st>>>(da);
                 COEX_KCHECK(st);

@@ -39,6 +39,15 @@ constexpr int kDdSuper = 32768;          // columns streamed between two drains 
 // ties at zero out of the "certain" branch.
 __device__ __forceinline__ float dd_delta(float v) { return fmaxf(kDdDelta * fabsf(v), 1e-30f); }
 
+// One statistic in the L2-resident scratch of a work item: 16 bytes = ONE sector access where three parallel arrays
+// (double statistic, origin, column) cost three -- the set-up phases are bound by the number of uncoalesced global accesses
+// per statistic (~1 SM-cycle each, profiles/r01_count_split.md), not by their bytes.
+struct __align__(16) StatRec {
+    double r;            // the statistic (-99 = undefined, never sorted)
+    unsigned int org;    // (query of the item << 13) | hit position j   (row-rank mode: column offset inside the run)
+    int col;             // table column of the statistic
+};
+
 struct DedupItem {
     int urow;        // index into the strip (unique-row slot)
     int qb, qe;      // range in qlist
@@ -56,6 +65,7 @@ struct DedupArgs {
     int K;
     const int *hit_rows;
     const double *sx;               // [N_pad]
+    const double *sxg;              // [N_pad] sx, NaN where the raw row sums to <= 0 (icol_kernel): the statistic's guard in one gather
     const float *icol;              // [N_pad] (float)(0.5 / sx), 0 for zero-variance / padding rows
     const unsigned char *rawsum_pos;
     long long N;
@@ -67,8 +77,7 @@ struct DedupArgs {
     double R;                       // bucket range [-R, R]
     int bm_words;                   // 32-bit words of the hit-column bitmap (0 = table too long, bitmap disabled)
     int claim;                      // 1: a second bitmap (claim mask) de-duplicates the hit columns (short tables only)
-    double *g_thr;                  // scratch [gridDim.x, 3, Tcap]: unsorted | grouped | sorted statistics
-    unsigned int *g_org;            // scratch [gridDim.x, 5, Tcap]: grouped | sorted origins, unsorted | grouped | sorted columns
+    StatRec *g_rec;                 // scratch [gridDim.x, 3, Tcap]: unsorted | grouped by bucket | sorted statistics
     const double *score_tab;        // [N+1] edge score of every possible bisect index (len = N-1)
     unsigned long long *phase_clk;  // optional [8]: summed clock64 per phase over all CTAs (profiling aid)
     // ---- PEARSON == true (`-cm Pearson`: Pearson null, Spearman statistic -- quirk Q2) ---------------------------
@@ -79,8 +88,7 @@ struct DedupArgs {
     int n;
     unsigned int *rank_out;         // MODE 2: [rows_in_strip, ld] number of null values strictly below each column's value
     // ---- MODE 3: the item's statistics arrive SORTED from stat_sort_kernel (count_split.cuh) ----------------------
-    const double *st_thr;           // sorted statistics of every item of the launch, item `it` at item_soff[it] .. + item_T[it]
-    const int *st_col;              // table column of the statistic
+    const StatRec *st_rec;          // sorted statistics of every item of the launch, item `it` at item_soff[it] .. + item_T[it]
     unsigned int *st_cnt;           // OUT: number of streamed + hit columns strictly below the statistic (score_scatter_kernel
                                     //      turns it into the bisect index and the edge score)
     const long long *item_soff;     // [n_items]
@@ -164,16 +172,10 @@ count_dedup_kernel(DedupArgs a) {
 
     const int tid = threadIdx.x;
     const float bscale_f = (float)((double)kDdBuckets / (2.0 * a.R));
-    double *tmp_r = PRE ? nullptr : a.g_thr + (long long)blockIdx.x * 3 * a.Tcap;      // statistic of flat index t (-99 = undefined)
-    double *g_thr = tmp_r + a.Tcap;                                    // grouped by bucket
-    double *thr64_w = g_thr + a.Tcap;                                  // sorted
-    unsigned int *g_org = PRE ? nullptr : a.g_org + (long long)blockIdx.x * 5 * a.Tcap;
-    unsigned int *org_w = g_org + a.Tcap;
-    int *tmp_c = reinterpret_cast<int *>(org_w + a.Tcap);            // column of flat index t
-    int *g_col = tmp_c + a.Tcap, *col_w = g_col + a.Tcap;            // grouped / sorted columns
-    const double *thr64 = thr64_w;                                   // (MODE 3: the item's slice of the pre-sorted arrays)
-    const unsigned int *org = org_w;
-    const int *col = col_w;
+    StatRec *rec_tmp = PRE ? nullptr : a.g_rec + (long long)blockIdx.x * 3 * a.Tcap;   // statistic of flat index t
+    StatRec *rec_grp = rec_tmp + a.Tcap;                             // grouped by bucket
+    StatRec *srt_w = rec_grp + a.Tcap;                               // sorted
+    const StatRec *srt = srt_w;                                      // (MODE 3: the item's slice of the pre-sorted array)
 
     const int n_deg = *a.n_degenerate;
     const int nchunk = RANKROW ? (int)((a.N + a.Tcap - 1) / a.Tcap) : 1;
@@ -197,7 +199,7 @@ count_dedup_kernel(DedupArgs a) {
             // ---- A'. the item's sorted statistics and query metadata come from stat_sort_kernel -------------------
             T = a.item_T[it];
             soff = a.item_soff[it];
-            thr64 = a.st_thr + soff; col = a.st_col + soff;
+            srt = a.st_rec + soff;
             if (T == 0) continue;                           // every statistic undefined: scores already written
             // the item's statistics: every load of the thread issued before the first is used (T <= 16 * kDdThreads)
             double t_in[4];
@@ -205,8 +207,9 @@ count_dedup_kernel(DedupArgs a) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int s = tid + e * kDdThreads;
-                t_in[e] = (s < T) ? thr64[s] : 0.0;
-                c_in[e] = (s < T && a.bm_words) ? col[s] : 0;
+                StatRec x = {0.0, 0u, 0};
+                if (s < T) x = srt[s];
+                t_in[e] = x.r; c_in[e] = x.col;
             }
             if (tid == 0) s_qn = 0;
             for (int b = tid; b < kDdBuckets; b += kDdThreads) lut[b] = 0;
@@ -217,8 +220,9 @@ count_dedup_kernel(DedupArgs a) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int s = s0 + tid + e * kDdThreads;
-                        t_in[e] = (s < T) ? thr64[s] : 0.0;
-                        c_in[e] = (s < T && a.bm_words) ? col[s] : 0;
+                        StatRec x = {0.0, 0u, 0};
+                        if (s < T) x = srt[s];
+                        t_in[e] = x.r; c_in[e] = x.col;
                     }
                 }
 #pragma unroll
@@ -323,8 +327,12 @@ count_dedup_kernel(DedupArgs a) {
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                guard[e] = false; sraw[e] = 0; sxc4[e] = 0.0;
-                if (cc4[e] >= 0) { guard[e] = RANKROW || a.rawsum_pos[cc4[e]] != 0; sraw[e] = srow[cc4[e]]; sxc4[e] = a.sx[cc4[e]]; }
+                guard[e] = RANKROW; sraw[e] = 0; sxc4[e] = 0.0;
+                if (cc4[e] >= 0) {
+                    sraw[e] = srow[cc4[e]];
+                    sxc4[e] = RANKROW ? a.sx[cc4[e]] : a.sxg[cc4[e]];        // NaN = raw sum <= 0 (coexfunctions.py:389)
+                    guard[e] = RANKROW || sxc4[e] == sxc4[e];
+                }
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -337,8 +345,7 @@ count_dedup_kernel(DedupArgs a) {
                     r = __ddiv_rn(0.25 * (double)sraw[e], __dmul_rn(sxu, sxc4[e]));
                     if (r != r) r = -99.0;                                  // coexfunctions.py:406-408
                 }
-                tmp_r[tt[e]] = r;
-                tmp_c[tt[e]] = cc4[e];
+                rec_tmp[tt[e]] = StatRec{r, 0u, cc4[e]};
                 if (r == -99.0) {                                           // diagonal, or 1-make-network.py:284-285
                     if (!RANKROW) {
                         const long long w = q_sc[qq[e]] + jj[e];
@@ -385,15 +392,14 @@ count_dedup_kernel(DedupArgs a) {
         }
         // group by bucket
         for (int t = tid; t < TP; t += kDdThreads) {
-            const double r = tmp_r[t];
+            const StatRec x = rec_tmp[t];
+            const double r = x.r;
             if (r != -99.0) {
                 int lo = 0, hi = nq;
                 if (!RANKROW) while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (q_toff[mid] <= t) lo = mid; else hi = mid; }
                 const int b = dd_bucket(r, bscale_f);
                 const unsigned int pos = lut[b] + atomicAdd(&cursor[b], 1u);
-                g_thr[pos] = r;
-                g_org[pos] = RANKROW ? (unsigned int)t : ((unsigned int)lo << 13) | (unsigned int)(t - q_toff[lo]);
-                g_col[pos] = tmp_c[t];
+                rec_grp[pos] = StatRec{r, RANKROW ? (unsigned int)t : ((unsigned int)lo << 13) | (unsigned int)(t - q_toff[lo]), x.col};
             }
         }
         __syncthreads();
@@ -406,18 +412,17 @@ count_dedup_kernel(DedupArgs a) {
         if (T == 0) continue;                               // every statistic undefined: scores already written
         // ---- C. rank inside the bucket -> fully sorted statistics -------------------------------------
         for (int e = tid; e < T; e += kDdThreads) {
-            const double t = g_thr[e];
+            const StatRec x = rec_grp[e];
+            const double t = x.r;
             const unsigned int pk = lut[dd_bucket(t, bscale_f)];
             const int lo = (int)(pk & 0xffffu), hi = lo + (int)(pk >> 16);
             int rank = 0;
             for (int m = lo; m < hi; ++m) {
-                const double x = g_thr[m];
-                rank += (x < t) || (x == t && m < e);
+                const double y = rec_grp[m].r;
+                rank += (y < t) || (y == t && m < e);
             }
-            thr64_w[lo + rank] = t;
+            srt_w[lo + rank] = x;
             thr32[lo + rank] = (float)t;
-            org_w[lo + rank] = g_org[e];
-            col_w[lo + rank] = g_col[e];
         }
         for (int p = tid; p <= T; p += kDdThreads) hist[p] = 0;
         if (tid == 0) { thr32[-1] = -CUDART_INF_F; thr32[T] = CUDART_INF_F; }
@@ -434,8 +439,9 @@ count_dedup_kernel(DedupArgs a) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {                           // the thread's four global loads in flight together
                   const int sidx = s0 + tid + e * kDdThreads;
-                  c4[e] = (sidx < T) ? col[sidx] : 0;
-                  t4[e] = (sidx < T) ? thr64[sidx] : 0.0;
+                  StatRec x = {0.0, 0u, 0};
+                  if (sidx < T) x = srt[sidx];
+                  c4[e] = x.col; t4[e] = x.r;
               }
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -450,11 +456,11 @@ count_dedup_kernel(DedupArgs a) {
                 }
                 const double t = t4[e];
                 if (!a.claim)
-                    for (int e1 = sidx - 1; e1 >= 0 && thr32[e1] == tf && thr64[e1] == t; --e1)
-                        if (col[e1] == c) { first = false; break; }
+                    for (int e1 = sidx - 1; e1 >= 0 && thr32[e1] == tf && srt[e1].r == t; --e1)
+                        if (srt[e1].col == c) { first = false; break; }
                 if (first) {
                     int e2 = sidx + 1;
-                    while (e2 < T && thr32[e2] == tf && thr64[e2] == t) ++e2;   // statistics <= value: through the run of equals
+                    while (e2 < T && thr32[e2] == tf && srt[e2].r == t) ++e2;   // statistics <= value: through the run of equals
                     atomicAdd(&hist[e2], 1u);
                 }
               }
@@ -536,7 +542,7 @@ count_dedup_kernel(DedupArgs a) {
                             int ln = (int)(pk >> 16);
                             while (ln > 0) {
                                 const int half = ln >> 1;
-                                if (thr64[pp + half] <= vv) { pp += half + 1; ln -= half + 1; } else ln = half;
+                                if (srt[pp + half].r <= vv) { pp += half + 1; ln -= half + 1; } else ln = half;
                             }
                             atomicAdd(&hist[pp], 1u);
                         }
@@ -556,7 +562,7 @@ count_dedup_kernel(DedupArgs a) {
                 int len = (int)(pk >> 16);
                 while (len > 0) {
                     const int half = len >> 1;
-                    if (thr64[pp + half] <= vv) { pp += half + 1; len -= half + 1; } else len = half;
+                    if (srt[pp + half].r <= vv) { pp += half + 1; len -= half + 1; } else len = half;
                 }
                 atomicAdd(&hist[pp], 1u);
             }
@@ -586,16 +592,17 @@ count_dedup_kernel(DedupArgs a) {
         if (RANKROW) {
             // all columns strictly below the column's own value (zero-variance columns: -99 < everything)
             unsigned int *rrow = a.rank_out + (long long)item.urow * a.ld + rank_c0;
-            for (int s = tid; s < T; s += kDdThreads) rrow[org[s]] = hist[s] + (unsigned int)n_deg;
+            for (int s = tid; s < T; s += kDdThreads) rrow[srt[s].org] = hist[s] + (unsigned int)n_deg;
         } else if (PRE) {
             // streamed + hit columns strictly below each sorted statistic; score_scatter_kernel does the rest
             for (int s = tid; s < T; s += kDdThreads) a.st_cnt[soff + s] = hist[s];
         } else
         for (int s = tid; s < T; s += kDdThreads) {
-            const unsigned int o = org[s];
+            const StatRec x = srt[s];
+            const unsigned int o = x.org;
             const int ql = (int)(o >> 13), j = (int)(o & 8191u);
             const int i = q_i[ql];
-            const double t = thr64[s];
+            const double t = x.r;
             // all columns strictly below t: streamed values + zero-variance columns (-99 < t always),
             // minus the skipped column i of this query if it is below t (quirk Q1)
             long long idx = (long long)hist[s] + n_deg;

@@ -46,8 +46,7 @@ struct SortArgs {
     long long *counts;
     int Tcap;
     float bscale;                   // kDdBuckets / (2 R), the same float the streaming kernel uses
-    double *st_thr;
-    int *st_col;
+    StatRec *st_rec;                // {statistic, -, column}
     unsigned long long *st_w;
     unsigned long long st_cap;      // capacity of the arrays
     unsigned long long *st_cursor;  // [1] bump allocator, zeroed before the launch
@@ -249,8 +248,7 @@ stat_sort_kernel(SortArgs a) {
                 const int ql = ql4[k];
                 unsigned long long w = (unsigned long long)(q_sc[ql] + (tt[k] - q_toff[ql]));
                 if (q_i[ql] < a.N) w |= (1ULL << 63) | ((q_vi[ql] < r) ? (1ULL << 62) : 0ULL);
-                a.st_thr[g] = r;
-                a.st_col[g] = col4[k];
+                a.st_rec[g] = StatRec{r, 0u, col4[k]};
                 a.st_w[g] = w;
             }
         }
