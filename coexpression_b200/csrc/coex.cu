@@ -250,7 +250,7 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
             const int nchunk = (int)((N + kRankTcap - 1) / kRankTcap);
             DedupArgs da{};
             da.strip = c->strip.p; da.ld = ld; da.items = nullptr; da.n_items = (int)(nu * nchunk);
-            da.uniq_rows = c->dd_uniq.p + u0; da.qlist = c->dd_qlist.p; da.perm_off = c->d_perm_off.p; da.sc_off = c->d_sc_off.p;
+            da.uniq_rows = c->dd_uniq.p + u0; da.qlist = c->dd_qlist.p; da.q_perm = c->dd_qperm.p; da.perm_off = c->d_perm_off.p; da.sc_off = c->d_sc_off.p;
             da.K = K; da.hit_rows = d_hits; da.sx = c->sx.p; da.sxg = c->sxg.p; da.icol = c->icol.p; da.rawsum_pos = c->rawsum_pos.p; da.N = N;
             da.n_degenerate = c->d_ndeg.p; da.anticor = prm->anticorrelation; da.scores = d_sc; da.counts = d_cn;
             da.Tcap = kRankTcap; da.Qcap = Qcap; da.bm_words = bm_words; da.claim = rclaim;
@@ -300,7 +300,7 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
         } else {
             DedupArgs da{};
             da.strip = c->strip.p; da.ld = ld; da.items = items_s; da.n_items = n_items_s;
-            da.uniq_rows = c->dd_uniq.p + u0; da.qlist = c->dd_qlist.p;
+            da.uniq_rows = c->dd_uniq.p + u0; da.qlist = c->dd_qlist.p; da.q_perm = c->dd_qperm.p;
             da.perm_off = c->d_perm_off.p; da.sc_off = c->d_sc_off.p; da.K = K; da.hit_rows = d_hits;
             da.sx = c->sx.p; da.sxg = c->sxg.p; da.icol = c->icol.p; da.rawsum_pos = c->rawsum_pos.p; da.N = N;
             da.n_degenerate = c->d_ndeg.p; da.anticor = prm->anticorrelation; da.scores = d_sc; da.counts = d_cn;

@@ -61,6 +61,7 @@ struct DedupArgs {
     int n_items;
     const int *uniq_rows;           // table row of each unique-row slot of the strip
     const int *qlist;               // flat hit indices grouped by unique row
+    const int *q_perm;              // [H] permutation of every flat hit index (plan_count_kernel)
     const long long *perm_off, *sc_off;
     int K;
     const int *hit_rows;
@@ -268,8 +269,7 @@ count_dedup_kernel(DedupArgs a) {
         // ---- A. query metadata ----------------------------------------------------------------
         for (int ql = tid; ql < nq; ql += kDdThreads) {
             const long long q = a.qlist[item.qb + ql];
-            int lo = 0, hi = a.K;
-            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (a.perm_off[mid] <= q) lo = mid; else hi = mid; }
+            const int lo = a.q_perm[q];                    // (was a binary search over perm_off: seven dependent global loads)
             const long long off = a.perm_off[lo];
             const int P = (int)(a.perm_off[lo + 1] - off);
             const int i = (int)(q - off);
@@ -597,20 +597,37 @@ count_dedup_kernel(DedupArgs a) {
             // streamed + hit columns strictly below each sorted statistic; score_scatter_kernel does the rest
             for (int s = tid; s < T; s += kDdThreads) a.st_cnt[soff + s] = hist[s];
         } else
-        for (int s = tid; s < T; s += kDdThreads) {
-            const StatRec x = srt[s];
-            const unsigned int o = x.org;
-            const int ql = (int)(o >> 13), j = (int)(o & 8191u);
-            const int i = q_i[ql];
-            const double t = x.r;
-            // all columns strictly below t: streamed values + zero-variance columns (-99 < t always),
-            // minus the skipped column i of this query if it is below t (quirk Q1)
-            long long idx = (long long)hist[s] + n_deg;
-            long long len = N;
-            if (i < N) { len = N - 1; if (q_vi[ql] < t) idx -= 1; }
-            const long long w = q_sc[ql] + j;
-            a.scores[w] = (len == N - 1) ? a.score_tab[idx] : edge_score_dev(idx, len, a.anticor);
-            if (a.counts) a.counts[w] = idx;
+        for (int s0 = 0; s0 < T; s0 += 4 * kDdThreads) {
+            // four statistics per thread: record loads, then score-table gathers, then stores -- each kind in flight together
+            long long idx4[4], w4[4];
+            double sc4[4];
+            bool tab4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int s = s0 + tid + e * kDdThreads;
+                w4[e] = -1; idx4[e] = 0; tab4[e] = true;
+                if (s < T) {
+                    const StatRec x = srt[s];
+                    const unsigned int o = x.org;
+                    const int ql = (int)(o >> 13), j = (int)(o & 8191u);
+                    const int i = q_i[ql];
+                    // all columns strictly below t: streamed values + zero-variance columns (-99 < t always),
+                    // minus the skipped column i of this query if it is below t (quirk Q1)
+                    long long idx = (long long)hist[s] + n_deg;
+                    if (i < N) { if (q_vi[ql] < x.r) idx -= 1; } else tab4[e] = false;     // no skipped column: N values
+                    idx4[e] = idx;
+                    w4[e] = q_sc[ql] + j;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                sc4[e] = (w4[e] < 0) ? 0.0 : (tab4[e] ? a.score_tab[idx4[e]] : edge_score_dev(idx4[e], N, a.anticor));
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (w4[e] < 0) continue;
+                a.scores[w4[e]] = sc4[e];
+                if (a.counts) a.counts[w4[e]] = idx4[e];
+            }
         }
         DD_PHASE(5);
         if (a.phase_clk && tid == 0) atomicAdd(&a.phase_clk[6], 1ULL);
