@@ -410,7 +410,7 @@ def run_ours(args):
         main["kernel"] = dominant if dominant in roof else "corr_gemm"
         main["peak_source"] = peak_src
         main["note"] = ("roofline of the kernel with the largest share of the step (CUDA events per launch on the library "
-                        "stream); traffic = ncu dram read+write per launch (profiles/r01_final_summary.md), null off the default config")
+                        "stream); traffic = ncu dram read+write per launch (profiles/r01_end_summary.md), null off the default config")
         total_perms = K * world
         line = {
             "metric": "permutations_per_sec", "value": total_perms / (step_ms_max * 1e-3), "unit": "permutations/s",
