@@ -307,6 +307,11 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
             da.Tcap = Tcap; da.Qcap = Qcap; da.bm_words = bm_words; da.claim = claim;
             da.R = R; da.g_rec = reinterpret_cast<StatRec *>(c->dd_gthr.p);
             da.score_tab = c->dd_tab.p; da.phase_clk = dbg ? phase.p : nullptr;
+            if (!getenv("COEX_STATIC_ITEMS")) {
+                COEX_TRY(c->dd_work.reserve(1));
+                COEX_CUDA(cudaMemsetAsync(c->dd_work.p, 0, sizeof(int), st));
+                da.work_counter = c->dd_work.p;
+            }
             if (split) {
                 da.st_rec = reinterpret_cast<const StatRec *>(c->st_thr.p); da.st_cnt = c->st_cnt.p; da.item_soff = c->st_itemoff.p;
                 da.item_T = c->st_itemT.p;
@@ -746,7 +751,7 @@ int coex_destroy(coex_ctx *c) {
     c->rank2.release(); c->u_hi.release(); c->u_lo.release(); c->suu.release(); c->sx.release();
     c->z_valid.release(); c->z_ninv.release(); c->za_planes.release(); c->za_inv_s.release();
     c->st_thr.release(); c->st_w.release(); c->st_col.release(); c->st_cnt.release(); c->st_itemoff.release(); c->st_itemT.release();
-    c->st_cursor.release(); c->sxg.release();
+    c->st_cursor.release(); c->sxg.release(); c->dd_work.release();
     c->z_planes.release(); c->z_ok.release(); c->z_l1.release(); c->z_inv_s.release();
     c->ap_hist.release(); c->feat_key.release(); c->feat_row.release(); c->pm_blob.release(); c->pm_counts.release(); c->pm_hits_tmp.release(); c->pm_off.release();
     c->chrom_id.release(); c->name_rank.release(); c->feat_start.release(); c->feat_end.release(); c->glist.release();

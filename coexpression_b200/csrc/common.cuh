@@ -156,7 +156,7 @@ struct coex_ctx {
     // sorted statistics of a strip's work items (count_split.cuh: stat_sort_kernel -> count_dedup_kernel<3>)
     coex::DevBuf<double> st_thr, sxg;
     coex::DevBuf<unsigned int> st_cnt;
-    coex::DevBuf<int> st_col, st_itemT;
+    coex::DevBuf<int> st_col, st_itemT, dd_work;
     coex::DevBuf<long long> st_itemoff;
     coex::DevBuf<unsigned long long> st_cursor, st_w;
     coex::DevBuf<double> dd_gthr, dd_tab;

@@ -81,6 +81,9 @@ struct DedupArgs {
     StatRec *g_rec;                 // scratch [gridDim.x, 3, Tcap]: unsorted | grouped by bucket | sorted statistics
     const double *score_tab;        // [N+1] edge score of every possible bisect index (len = N-1)
     unsigned long long *phase_clk;  // optional [8]: summed clock64 per phase over all CTAs (profiling aid)
+    int *work_counter;              // [1] zeroed before the launch: a CTA takes its first item by its index and every further one
+                                    // from this counter (items differ 7-fold in their number of statistics: a static
+                                    // round-robin leaves a tail); nullptr = static round-robin
     // ---- PEARSON == true (`-cm Pearson`: Pearson null, Spearman statistic -- quirk Q2) ---------------------------
     const float *strip_f32;         // [rows_in_strip, ld] tensor-core Pearson r of the unique rows (|error| <= eps); `strip` still holds the
                                     // exact Spearman sums the statistics are read from
@@ -168,7 +171,7 @@ count_dedup_kernel(DedupArgs a) {
     int *q_P = q_off + a.Qcap;                   // [Qcap] hits of that permutation
     int *q_toff = q_P + a.Qcap;                  // [Qcap+2] offset of the query's statistics in the item
     unsigned int *bitmap = reinterpret_cast<unsigned int *>(q_toff + a.Qcap + 2);   // [bm_words] hit columns of this item (skipped by the streaming pass) | [bm_words] claim mask if a.claim
-    __shared__ int s_T, s_qn;
+    __shared__ int s_T, s_qn, s_next;
     __shared__ unsigned int s_warp[kDdThreads / 32];
 
     const int tid = threadIdx.x;
@@ -180,7 +183,14 @@ count_dedup_kernel(DedupArgs a) {
 
     const int n_deg = *a.n_degenerate;
     const int nchunk = RANKROW ? (int)((a.N + a.Tcap - 1) / a.Tcap) : 1;
-    for (int it = blockIdx.x; it < a.n_items; it += gridDim.x) {
+    auto next_item = [&](int it) {
+        if (!a.work_counter) return it + (int)gridDim.x;
+        __syncthreads();
+        if (threadIdx.x == 0) s_next = (int)gridDim.x + atomicAdd(a.work_counter, 1);
+        __syncthreads();
+        return s_next;
+    };
+    for (int it = blockIdx.x; it < a.n_items; it = next_item(it)) {
         DedupItem item;
         if (RANKROW) { item.urow = it / nchunk; item.qb = item.qe = 0; item.T = 0; }
         else item = a.items[it];
