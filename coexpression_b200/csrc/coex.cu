@@ -736,6 +736,7 @@ int coex_create(coex_ctx **out, int device) {
     COEX_CUDA(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     COEX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    if (const char *e = getenv("COEX_STRIP_MB")) { const long long mb = atoll(e); if (mb >= 16) c->strip_mb = mb; }   // profiling aid: same as coex_set_workspace_mb
     if (const char *e = getenv("COEX_COUNT_MODE")) c->count_mode = atoi(e);      // profiling aid (scripts/): same as coex_set_count_mode
     *out = c;
     return 0;
