@@ -158,9 +158,59 @@ def function_vectors():
     print("reference_functions.json", len(gw), len(ad), len(mr), len(ep), len(fd))
 
 
+def global_list_vectors():
+    """Row N2: the global correlation list, by EXECUTING lines 623-716 of the reference's 0-prepare-coex.py (the block that
+    draws random row pairs, calls getPearson and writes <expr>.spearmanlist) in a namespace that holds what the lines
+    before it would have set up.  `random` is seeded, so coexfunctions.make_correlation_list (same call sequence on a
+    random.Random(seed)) must draw the same pairs."""
+    import ctypes
+    import random
+    import types
+    from run_reference_py3 import convert_py2, import_reference_coexfunctions, REF
+    cf = import_reference_coexfunctions()
+    with open(os.path.join(REF, "0-prepare-coex.py")) as f:
+        lines = f.read().split("\n")
+    first = next(i for i, l in enumerate(lines) if l.startswith('if verbose: print ("reading correlation lists:"'))
+    last = next(i for i, l in enumerate(lines) if "Correlation Centile at" in l)
+    assert (first, last) == (622, 715), (first, last)    # file lines 623..716 of the reference as surveyed
+    block = "\n".join(lines[first:last + 1])
+    code = compile(convert_py2(block), "0-prepare-coex.py[623:716]", "exec")
+    out = []
+    for case, (measure, seed, pre_existing) in {"spearman_fresh": ("Spearman", 5, 0), "pearson_fresh": ("Pearson", 6, 0),
+                                                "spearman_topup": ("Spearman", 7, 700)}.items():
+        t = synth.make_table(220, 18, seed=60 + seed)
+        with tempfile.TemporaryDirectory() as tmp:
+            expr = os.path.join(tmp, "t.expression")
+            synth.write_expression_file(expr, t)
+            corrfile = os.path.join(tmp, "t.expression.list")
+            existing = []
+            if pre_existing:
+                rng = np.random.default_rng(seed)
+                existing = sorted(float(np.round(v, 6)) for v in rng.uniform(-0.9, 0.9, pre_existing))
+                with open(corrfile, "w") as o:
+                    for v in existing:
+                        o.write("%s\n" % v)
+            ns = {name: getattr(cf, name) for name in dir(cf) if not name.startswith("__")}
+            ns.update({name: getattr(ctypes, name) for name in ("c_double", "c_int", "byref", "cdll")})
+            random.seed(seed)
+            ns.update(verbose=False, correlationmeasure=measure, correlationfile=corrfile, gpl_len=2000,
+                      permutationmode="circular", args=types.SimpleNamespace(expression_file=expr), random=random,
+                      coexpression=ctypes.cdll.LoadLibrary(os.path.join(ROOT, "oracle", "_ref", "coexpression_v2.so")))
+            exec(code, ns)
+            with open(corrfile) as f:
+                values = [float(x) for x in f if x.strip()]
+        out.append({"case": case, "measure": measure, "seed": seed, "gpl_len": 2000, "existing": existing,
+                    "names": list(t.names), "X": [[float(v) for v in row] for row in t.X], "values": values})
+        print("global list", case, len(values), "values")
+    with gzip.open(os.path.join(HERE, "reference_global_list.json.gz"), "wt") as o:
+        json.dump({"runs": out, "how": "lines 623-716 of /root/reference/0-prepare-coex.py, mechanically 2to3-rewritten, executed with a "
+                                       "seeded `random` against the unmodified coexfunctions.py and the unmodified reference C build"}, o)
+
+
 if __name__ == "__main__":
     assert "reference" in no.available_kinds(), "build oracle/_ref/coexpression_v2.so first (make -C oracle)"
     function_vectors()
+    global_list_vectors()
     if len(sys.argv) > 1 and sys.argv[1] == "functions":
         sys.exit(0)
     for name, spec in CASES.items():

@@ -163,3 +163,51 @@ def test_gpu_path_against_executed_reference(path):
         assert got["winners"] == want["winners"]
         for g, v in want["indmeasure"].items():
             assert abs(got["indmeasure"][g] - v) <= 1e-6
+
+
+# ---- row N2: the global correlation list against the executed block 0-prepare-coex.py:623-716 -----------------------
+def _global_list_runs():
+    with gzip.open(os.path.join(HERE, "golden", "reference_global_list.json.gz"), "rt") as f:
+        return json.load(f)["runs"]
+
+
+class _OraclePairs:
+    """Stands in for CoexContext in the CPU test: `pairs` through the unmodified reference C build (or its port)."""
+    def __init__(self, X):
+        self.X = np.ascontiguousarray(X, dtype=np.float64)
+        self.R = no.rank_rows(self.X)
+
+    def pairs(self, ia, ib, ranked):
+        return no.get_pearson(self.R if ranked else self.X, ia, ib)
+
+
+def _check_global_list(run, ctx, tmp_path):
+    from coexpression_b200.coexfunctions import make_correlation_list
+    corrfile = tmp_path / ("%s.list" % run["case"])
+    if run["existing"]:
+        with open(corrfile, "w") as o:
+            for v in run["existing"]:
+                o.write("%s\n" % v)
+    got = make_correlation_list(ctx, run["names"], str(corrfile), run["measure"], run["gpl_len"], seed=run["seed"])
+    want = np.asarray(run["values"], dtype=np.float64)
+    assert got.shape == want.shape and len(want) > run["gpl_len"]
+    assert np.array_equal(got, want)                    # same pairs drawn, same getPearson bits, same order
+    with open(corrfile) as f:
+        on_disk = np.asarray([float(x) for x in f if x.strip()], dtype=np.float64)
+    assert np.array_equal(on_disk, want)                # the file 1-make-network.py:76-79 reads back
+
+
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_global_list_host_logic_reproduces_executed_reference(k, tmp_path):
+    run = _global_list_runs()[k]
+    _check_global_list(run, _OraclePairs(run["X"]), tmp_path)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_gpu_global_list_reproduces_executed_reference(k, tmp_path):
+    from coexpression_b200.api import CoexContext
+    run = _global_list_runs()[k]
+    with CoexContext() as ctx:
+        ctx.set_expression(np.asarray(run["X"], dtype=np.float64)); ctx.prepare()
+        _check_global_list(run, ctx, tmp_path)
