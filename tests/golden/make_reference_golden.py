@@ -151,8 +151,32 @@ def function_vectors():
         if abs(abs(a - math.floor(a)) - 0.5) < 1e-9 or abs(abs(c - math.floor(c)) - 0.5) < 1e-9:
             continue
         li.append([n_items, index, cf.listitem(list(range(n_items)), index)])
+    # file readers (coexfunctions.py:201-274): an expression table with an NA column, a duplicated label and odd number
+    # formats; a feature BED with header lines, a reversed interval and two features sharing a start
+    expr_text = ("sample\ts0\ts1\tbad\ts2\n"
+                 "chr1:10..20,+\t0.0\t1.5\t1\t2e-3\n"
+                 "chr1:30..40,-\t3\t0.25\tNA\t7.125\n"
+                 "chr2:5..9,+\t1e2\t0\t3\t0.1\n"
+                 "chr1:10..20,+\t9\t9\t9\t9\n"
+                 "chrX:1..2,-\t-0.0\t4.75\t5\t12345.678\n")
+    bed_text = ("track name=features\n#chrom\tstart\tend\tname\n"
+                "chr1\t10\t20\tx\t0\t+\tchr1:10..20,+\n"
+                "chr1\t40\t30\tx\t0\t-\tchr1:30..40,-\n"
+                "chr2\t5\t9\tx\t0\t+\tchr2:5..9,+\n"
+                "chr2\t5\t12\tx\t0\t+\tchr2:5..12,+\n"
+                "chrX\t1\t2\tx\t0\t-\tchrX:1..2,-\n")
+    with tempfile.TemporaryDirectory() as tmp:
+        expr_path, bed_path = os.path.join(tmp, "e.expression"), os.path.join(tmp, "f.bed")
+        open(expr_path, "w").write(expr_text)
+        open(bed_path, "w").write(bed_text)
+        ed, header = cf.read_expression_file(expr_path)
+        names = list(dict.keys(ed))
+        readers = {"expr_text": expr_text, "names": names, "header": [str(h) for h in header],
+                   "values": [[float(v) for v in ed[nm]] for nm in names], "bed_text": bed_text}
+        r_pa, r_fd, r_sl = cf.readfeaturecoordinates(bed_path)
+        readers.update(pa=r_pa, fd={c: {str(k): v for k, v in d.items()} for c, d in r_fd.items()}, sl=r_sl)
     with open(os.path.join(HERE, "reference_functions.json"), "w") as o:
-        json.dump({"chromlist": chromlist, "chromrange": chromrange, "get_gwad": gw, "get_address": ad, "listitem": li,
+        json.dump({"readers": readers, "chromlist": chromlist, "chromrange": chromrange, "get_gwad": gw, "get_address": ad, "listitem": li,
                    "merge_ranges": mr, "empiricalp": ep, "fdr_correction": fd,
                    "how": "direct calls of the unmodified /root/reference/coexfunctions.py under Python 3"}, o)
     print("reference_functions.json", len(gw), len(ad), len(mr), len(ep), len(fd))

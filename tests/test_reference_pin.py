@@ -91,6 +91,24 @@ def test_consistent_oracle_differs_only_by_documented_index_flips(path):
     assert n_all > 400 and n_diff < 0.6 * n_all
 
 
+def test_file_readers_against_reference_functions(tmp_path):
+    """read_expression_file / readfeaturecoordinates (coexfunctions.py:201-274) on the same text the reference's own
+    functions parsed when the fixture was made: NA column dropped, duplicated label keeps its first row, BED header
+    lines skipped, label = last column, {chrom: {start: greatest end}}."""
+    from coexpression_b200.coexfunctions import read_expression_file, readfeaturecoordinates
+    with open(os.path.join(HERE, "golden", "reference_functions.json")) as f:
+        rd = json.load(f)["readers"]
+    ep, bp = tmp_path / "e.expression", tmp_path / "f.bed"
+    ep.write_text(rd["expr_text"]); bp.write_text(rd["bed_text"])
+    table, header = read_expression_file(str(ep))
+    assert list(table.names) == rd["names"] and [str(h) for h in header] == rd["header"]
+    assert np.array_equal(np.asarray(table.values, dtype=np.float64), np.asarray(rd["values"], dtype=np.float64))
+    assert np.array_equal(np.signbit(np.asarray(table.values, dtype=np.float64)), np.signbit(np.asarray(rd["values"])))
+    pa, fd, sl = readfeaturecoordinates(str(bp))
+    assert pa == rd["pa"] and sl == rd["sl"]
+    assert {c: {str(k): v for k, v in d.items()} for c, d in fd.items()} == rd["fd"]
+
+
 def test_reference_helper_functions_known_answers():
     with open(os.path.join(HERE, "golden", "reference_functions.json")) as f:
         fx = json.load(f)
