@@ -10,6 +10,9 @@ Follows, with explicit orders where the reference iterates Python-2 dicts:
                          get_gwad / get_address / listitem are PINNED against direct calls of the reference's own
                          functions (tests/golden/reference_functions.json, tests/test_reference_pin.py; listitem on
                          the indices where Python 2 and 3 rounding agree, the half-away rule by its own test).
+                         The three modes below are PINNED against the reference's own permutation block
+                         (0-prepare-coex.py:471-613) executed with a seeded RNG and a stand-in for the windowBed binary that
+                         captures the temporary BED of every set (tests/golden/reference_permutations.json).
   circular mode ........ reference 0-prepare-coex.py:548-563
   backcirc mode ........ reference 0-prepare-coex.py:579-593  (sorted background by (gwad, key), :582)
   background mode ...... reference 0-prepare-coex.py:564-578  (random.sample of background lines; the draw is an input here)

@@ -6,7 +6,9 @@ Run HERE, where /root/reference exists:
 Writes tests/golden/reference_run_<case>.json.gz: the inputs (table, features, global list, map-file promoters) and the
 seven result objects `1-make-network.py` dumped for them (perm_results_store/<feat>.<object>.<k>), plus
 tests/golden/reference_functions.json: known answers of the reference's `coexfunctions` helpers (get_gwad, get_address,
-listitem, merge_ranges, empiricalp, fdr_correction) called directly.  tests/test_reference_pin.py checks oracle/network_oracle.py
+listitem, merge_ranges, empiricalp, fdr_correction, read_expression_file, readfeaturecoordinates) called directly,
+tests/golden/reference_global_list.json.gz (row N2: lines 623-716 of 0-prepare-coex.py executed) and
+tests/golden/reference_permutations.json (row N1: lines 471-613 executed, windowBed replaced by an echo of its -a file).  tests/test_reference_pin.py checks oracle/network_oracle.py
 and oracle/permute_oracle.py against them -- nothing there reads /root/reference.
 """
 import gzip
@@ -182,6 +184,84 @@ def function_vectors():
     print("reference_functions.json", len(gw), len(ad), len(mr), len(ep), len(fd))
 
 
+def permutation_vectors():
+    """Row N1: the permuted locus positions, by EXECUTING the reference's permutation block (0-prepare-coex.py, from
+    `writequeue('Starting to make permutations` to the `windowBed` call of every set) for the circular, backcirc and
+    background modes with a seeded `random`.  `windowbed` is pointed at a two-line script that copies its `-a` file (the
+    temporary BED of the shifted loci) to stdout, so every `permutation_store/<feat>.<k>.bed` the block writes holds the
+    positions it handed to windowBed -- the join itself is bedtools' and stays unpinned."""
+    import random
+    import subprocess
+    import types
+    from subprocess import PIPE, STDOUT
+    from run_reference_py3 import convert_py2, import_reference_coexfunctions, REF
+    cf = import_reference_coexfunctions()
+    with open(os.path.join(REF, "0-prepare-coex.py")) as f:
+        lines = f.read().split("\n")
+    first = next(i for i, l in enumerate(lines) if l.startswith("writequeue('Starting to make permutations"))
+    last = next(i for i, l in enumerate(lines) if i > first and l.strip().startswith("print output  # so that errors"))
+    assert (first, last) == (470, 612), (first, last)    # file lines 471..613 of the reference as surveyed
+    code = compile(convert_py2("\n".join(lines[first:last + 1])), "0-prepare-coex.py[471:613]", "exec")
+    chromlist = ["chr1", "chr2", "chr3", "chrX"]
+    lengths = {"chr1": 5000, "chr2": 3000, "chr3": 800, "chrX": 1200}
+    chromrange, acc = {}, 0
+    for c in chromlist:
+        chromrange[c] = [acc, acc + lengths[c]]
+        acc += lengths[c]
+    rng = np.random.default_rng(21)
+    snps = []
+    for i in range(40):
+        c = chromlist[int(rng.integers(0, 4))]
+        snps.append((c, int(rng.integers(1, lengths[c] - 1)), "rs%d" % i))
+    snp_bed_data = {}
+    for c, a, name in snps:
+        snp_bed_data.setdefault(c, {})[a] = name
+    flat = [(c, a) for c in snp_bed_data for a in snp_bed_data[c]]      # the iteration order of the block's loops
+    backlines = []
+    for i in range(600):
+        c = chromlist[int(rng.integers(0, 4))]
+        a = int(rng.integers(1, lengths[c] - 1))
+        backlines.append("%s\t%d\t%d\tbg%d\trsb%d\n" % (c, a, a + 1, i, i))
+    out = []
+    for mode, seed in (("circular", 31), ("backcirc", 32), ("background", 33)):
+        with tempfile.TemporaryDirectory() as tmp:
+            store = os.path.join(tmp, "permutation_store")
+            os.makedirs(store)
+            cap = os.path.join(tmp, "capture.py")
+            with open(cap, "w") as o:
+                o.write("import sys\nsys.stdout.write(open(sys.argv[sys.argv.index('-a') + 1]).read())\n")
+            bgfile = os.path.join(tmp, "background.bed")
+            with open(bgfile, "w") as o:
+                o.writelines(backlines)
+            ns = {name: getattr(cf, name) for name in dir(cf) if not name.startswith("__")}
+            random.seed(seed)
+            numperms = 6
+            ns.update(writequeue=lambda *a, **k: None, queuefile=os.path.join(tmp, "q"), permutationmode=mode, verbose=False,
+                      snps_mapped=os.path.join(store, "f5ep.0.bed"), primary_dict={"a": 1, "b": 2}, random=random,
+                      numperms=numperms, storage_dir_permutations=store, feature_label="f5ep", backgroundfile=bgfile,
+                      snp_bed_data=snp_bed_data, chromrange=chromrange, chromlist=chromlist, snp_count=len(flat),
+                      doitagain=False, working_files_dir=tmp, windowbed="%s %s" % (sys.executable, cap), window=1234,
+                      args=types.SimpleNamespace(feature_coordinates=os.path.join(tmp, "feat.bed")),
+                      subprocess=subprocess, PIPE=PIPE, STDOUT=STDOUT)
+            import contextlib, io
+            with contextlib.redirect_stdout(io.StringIO()):
+                exec(code, ns)
+            shifts = list(ns["shifts"])
+            sets = []
+            for k, shift in enumerate(shifts):
+                path = ns["mapfiles"][shift]
+                rows = [l.rstrip("\n").split("\t") for l in open(path)]
+                sets.append({"shift": int(shift), "file": os.path.basename(path),
+                             "positions": [["chr" + r[0].replace("chr", ""), int(r[1]), int(r[2]), r[3]] for r in rows]})
+        out.append({"mode": mode, "seed": seed, "numperms": numperms, "snps": [list(x) for x in flat],
+                    "backlines": backlines if mode != "circular" else [], "sets": sets})
+        print("permutation block", mode, "shifts", shifts[:3], "...", [len(s["positions"]) for s in sets])
+    with open(os.path.join(HERE, "reference_permutations.json"), "w") as o:
+        json.dump({"chromlist": chromlist, "chromrange": chromrange, "runs": out,
+                   "how": "lines 471-613 of /root/reference/0-prepare-coex.py, mechanically 2to3-rewritten, executed with a seeded "
+                          "`random`; windowbed replaced by a script that echoes its -a file"}, o)
+
+
 def global_list_vectors():
     """Row N2: the global correlation list, by EXECUTING lines 623-716 of the reference's 0-prepare-coex.py (the block that
     draws random row pairs, calls getPearson and writes <expr>.spearmanlist) in a namespace that holds what the lines
@@ -235,6 +315,7 @@ if __name__ == "__main__":
     assert "reference" in no.available_kinds(), "build oracle/_ref/coexpression_v2.so first (make -C oracle)"
     function_vectors()
     global_list_vectors()
+    permutation_vectors()
     if len(sys.argv) > 1 and sys.argv[1] == "functions":
         sys.exit(0)
     for name, spec in CASES.items():

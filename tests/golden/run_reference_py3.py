@@ -61,6 +61,25 @@ def _balanced(s):
     return depth
 
 
+def _comment_start(s):
+    """index of a trailing # comment outside string literals (len(s) if none)"""
+    quote = None
+    i = 0
+    while i < len(s):
+        ch = s[i]
+        if quote:
+            if ch == "\\":
+                i += 1
+            elif ch == quote:
+                quote = None
+        elif ch in "\"'":
+            quote = ch
+        elif ch == "#":
+            return i
+        i += 1
+    return len(s)
+
+
 _PRINT = re.compile(r"^(?P<head>\s*(?:(?:if|elif)\s[^:]*:\s*|else:\s*)?)print(?P<sp>\s+)(?P<rest>\S.*)$")
 
 
@@ -76,7 +95,9 @@ def convert_py2(src):
             while _balanced(rest) > 0 or rest.rstrip().endswith("\\"):      # continuation lines of the statement
                 i += 1
                 rest = rest.rstrip().rstrip("\\") + " " + lines[i].strip()
-            line = "%sprint(%s)" % (m.group("head"), rest.rstrip())
+            cut = _comment_start(rest)
+            comment = "  " + rest[cut:] if cut < len(rest) else ""
+            line = "%sprint(%s)%s" % (m.group("head"), rest[:cut].rstrip(), comment)
         out.append(line)
         i += 1
     s = "\n".join(out)

@@ -229,3 +229,57 @@ def test_gpu_global_list_reproduces_executed_reference(k, tmp_path):
     with CoexContext() as ctx:
         ctx.set_expression(np.asarray(run["X"], dtype=np.float64)); ctx.prepare()
         _check_global_list(run, ctx, tmp_path)
+
+
+# ---- row N1: permuted locus positions against the executed permutation block 0-prepare-coex.py:471-613 --------------
+def _permutation_runs():
+    with open(os.path.join(HERE, "golden", "reference_permutations.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("mode", ["circular", "backcirc", "background"])
+def test_permuted_positions_reproduce_executed_reference_block(mode):
+    """The positions the reference hands to windowBed for every locus set (its temporary BED, captured by standing in
+    for the windowBed binary) against oracle/permute_oracle.py, which the CUDA path (coex_permute_map) is compared with in
+    tests/test_permute.py.  The reference keeps the loci of a set in a {chrom: {address: name}} dict, so two loci that land
+    on one position collapse and the order is the dict's: positions are compared as sets."""
+    import random
+    fx = _permutation_runs()
+    cr = {k: tuple(v) for k, v in fx["chromrange"].items()}
+    cl = fx["chromlist"]
+    run = next(r for r in fx["runs"] if r["mode"] == mode)
+    snps = [(c, int(a)) for c, a in run["snps"]]
+    backlines = [l.rstrip("\n").split("\t") for l in run["backlines"]]
+    rnd = random.Random(run["seed"])
+    if mode == "backcirc":
+        backdict = {}
+        for line in backlines:                                          # 0-prepare-coex.py:501-519: column 1 is the address
+            chrom, address = "chr" + line[0].replace("chr", ""), int(float(line[1]))
+            backdict["%s_%s" % (chrom, address)] = po.get_gwad(chrom, address, cr)
+        for chrom, address in snps:                                     # :521-528: the real loci join the background
+            backdict.setdefault("%s_%s" % (chrom, address), po.get_gwad(chrom, address, cr))
+        sb = po.sorted_background(backdict)
+    assert [s["shift"] for s in run["sets"]][-1] == 0 and len(run["sets"]) == run["numperms"] + 1
+    if mode != "background":                                            # :476-497: the shifts come first off the RNG stream
+        assert [s["shift"] for s in run["sets"]][:-1] == [int(rnd.random() * 10000000000) for _ in range(run["numperms"])]
+    for k, s in enumerate(run["sets"]):
+        got = {(p[0], p[1]) for p in s["positions"]}
+        assert all(p[2] == p[1] + 1 for p in s["positions"])            # A = [address, address + 1)
+        if s["shift"] == 0 or mode == "circular":
+            want = {p for p in po.circular_positions(snps, s["shift"], cr, cl) if p is not None}
+            assert all(p[3].startswith("rand_") == (s["shift"] != 0) for p in s["positions"])
+        elif mode == "backcirc":
+            want = set(po.backcirc_positions(snps, s["shift"], sb))
+            if got != want:
+                # Python 3 rounds exact halves to even, Python 2.7 (and the restatement) away from zero: the executed run can
+                # differ from a real Python-2 run -- and from the restatement -- only on such indices
+                n = len(sb)
+                pos = {key: i for i, key in enumerate(sb)}
+                halves = [c for c, a in snps if abs(((pos["%s_%s" % (c, a)] + s["shift"]) / n) % 1 - 0.5) < 1e-12 or
+                          abs(((((pos["%s_%s" % (c, a)] + s["shift"]) / n) - round((pos["%s_%s" % (c, a)] + s["shift"]) / n)) * n) % 1 - 0.5) < 1e-9]
+                assert halves and len(got ^ want) <= 2 * len(halves), (k, got ^ want)
+                continue
+        else:
+            picks = rnd.sample(range(len(backlines)), len(snps))        # :568, one draw per permuted set, in loop order
+            want = set(po.background_positions(backlines, picks))
+        assert got == want, (mode, k, s["shift"], sorted(got ^ want)[:6])
