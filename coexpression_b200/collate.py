@@ -7,6 +7,8 @@
   table .............. `<label>.individual_scores`: groups by (score, name) descending, the i-th largest score is
                        paired with the i-th smallest p (:176-244); reported score = indmeasure / len(indmeasure) (:242)
 
+  allscores.txt ...... one line per hit: address, group, allpromoterscores, group density, group FDR (:264-283)
+
 The HTML / BioLayout / network writers of the reference (:165-430) are reporting only and are not rebuilt.
 Same command line: `2-collate-results.py -wd <working_files_dir> [-t N]`.
 """
@@ -17,7 +19,7 @@ import json
 import os
 import sys
 
-from .coexfunctions import empiricalp, fdr_correction, readsettings
+from .coexfunctions import empiricalp, fdr_correction, readfeaturecoordinates, readsettings
 
 
 def load_store(store):
@@ -73,6 +75,19 @@ def write_individual_scores(path, real, numbers):
     return fdrstore
 
 
+def write_allscores(path, real, fdrstore, prom_addresses):
+    """2-collate-results.py:264-283: sorted by start, then (stably) by chromosome string."""
+    ji, indmeasure = real["joining_instructions"], real["indmeasure"]
+    rows = [[prom_addresses[prom][0], prom_addresses[prom][1], prom_addresses[prom][2], prom, ji[prom],
+             real["allpromoterscores"][prom], indmeasure[ji[prom]], fdrstore[ji[prom]]] for prom in ji]
+    rows.sort(key=lambda x: int(x[1]))
+    rows.sort(key=lambda x: x[0])
+    with open(path, "w") as o:
+        o.write("chrom\tstart\tend\tname\tgroup_name\traw_coex\tgroup_coex\tgroup_FDR\n")
+        for row in rows:
+            o.write("%s\n" % ("\t".join(str(x) for x in row)))
+
+
 def collate(working_files_dir):
     settings = readsettings(working_files_dir)
     pool, real, n_perm = load_store(os.path.join(working_files_dir, "perm_results_store"))
@@ -80,6 +95,10 @@ def collate(working_files_dir):
     label = str(settings.get("supplementary_label", "coex"))
     out = os.path.join(working_files_dir, label + ".individual_scores")
     numbers["fdrstore"] = write_individual_scores(out, real, numbers)
+    feat = settings.get("feature_coordinates")
+    if feat and os.path.exists(str(feat)):
+        write_allscores(os.path.join(working_files_dir, "allscores.txt"), real, numbers["fdrstore"],
+                        readfeaturecoordinates(str(feat))[0])
     numbers["num_completed_perms"] = n_perm
     numbers["individual_scores_file"] = out
     return numbers

@@ -184,6 +184,60 @@ def function_vectors():
     print("reference_functions.json", len(gw), len(ad), len(mr), len(ep), len(fd))
 
 
+def collate_vectors():
+    """Row N3: the reference's 2-collate-results.py executed on a perm_results_store that its own 1-make-network.py wrote
+    (one real hit set + three permuted ones); the main table `<label>.individual_scores` and `allscores.txt` it writes are
+    the known answers for coexpression_b200/collate.py."""
+    t = synth.make_table(260, 20, seed=71)
+    with tempfile.TemporaryDirectory() as tmp:
+        wd = os.path.join(tmp, "work")
+        os.makedirs(os.path.join(wd, "permutation_store"))
+        os.makedirs(os.path.join(wd, "perm_results_store"))
+        expr, bed = os.path.join(tmp, "t.expression"), os.path.join(tmp, "f5ep.bed")
+        clist = os.path.join(tmp, "t.expression.spearmanlist")
+        synth.write_expression_file(expr, t)
+        synth.write_feature_bed(bed, t)
+        ga, gb = synth.global_pair_indices(t.names, 4000, seed=171)
+        g = no.get_pearson(no.rank_rows(t.X), ga, gb, "reference")
+        glist = np.sort(np.where(np.isnan(g), -99.0, g))
+        with open(clist, "w") as o:
+            for v in glist:
+                o.write("%s\n" % (int(v) if v == -99 else repr(float(v))))
+        m = synth.Mapper(t)
+        loci = synth.make_loci(t, 18, seed=271)
+        sets = synth.circular_shifts(loci, m.genome_len, 3, seed=371)
+        cfg = os.path.join(tmp, "app.cfg")
+        with open(cfg, "w") as o:
+            o.write("[directorypaths]\nsourcefilesdir=%s\nresdir=%s\npathtobedtools=/nonexistent\nf5resource=http://x/\n" % (tmp, tmp))
+        settings = {"verbose": "False", "feature_coordinates": bed, "correlationfile": clist, "expression_file": expr,
+                    "supplementary_label": "golden", "correlationmeasure": "Spearman", "soft_separation": 100000, "nsp": 1.0,
+                    "seedfile": "none", "pval_to_join": 0.1, "useaverage": "False", "anticorrelation": "False",
+                    "noiter": "False", "selectionthreshold": 0, "selectionthreshold_is_j": "False", "config_file": cfg,
+                    "useremail": "none", "snp_count": 18, "genome_length": int(m.genome_len)}
+        with open(os.path.join(wd, "settings.txt"), "w") as o:
+            json.dump(settings, o)
+        env = dict(os.environ, PYTHONHASHSEED="0")
+        for k, gw in enumerate(sets):
+            mf = os.path.join(wd, "permutation_store", "f5ep.%d.bed" % k)
+            synth.write_map_file(mf, t, m, gw, 30000, prefix="rs" if k == 0 else "rand_rs")
+            r = subprocess.run([sys.executable, os.path.join(HERE, "run_reference_py3.py"), os.path.join(tmp, "app"), wd, mf],
+                               capture_output=True, text=True, env=env)
+            assert r.returncode == 0, r.stderr[-3000:]
+        r = subprocess.run([sys.executable, os.path.join(HERE, "run_reference_py3.py"), "collate", os.path.join(tmp, "app"), wd],
+                           capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr[-3000:]
+        store = os.path.join(wd, "perm_results_store")
+        files = {f: open(os.path.join(store, f)).read() for f in sorted(os.listdir(store))
+                 if f.endswith(".0") or ".indmeasure." in f}
+        out = {"store": files, "settings": {k: v for k, v in settings.items() if k in ("supplementary_label", "verbose")},
+               "individual_scores": open(os.path.join(wd, "golden.individual_scores")).read(),
+               "allscores": open(os.path.join(wd, "allscores.txt")).read(), "feature_bed": open(bed).read(),
+               "how": "unmodified coexfunctions.py + mechanically 2to3-rewritten 1-make-network.py and 2-collate-results.py"}
+    with gzip.open(os.path.join(HERE, "reference_collate.json.gz"), "wt") as o:
+        json.dump(out, o)
+    print("collate:", len(out["individual_scores"].splitlines()) - 1, "groups,", len(files), "store files")
+
+
 def permutation_vectors():
     """Row N1: the permuted locus positions, by EXECUTING the reference's permutation block (0-prepare-coex.py, from
     `writequeue('Starting to make permutations` to the `windowBed` call of every set) for the circular, backcirc and
@@ -316,6 +370,7 @@ if __name__ == "__main__":
     function_vectors()
     global_list_vectors()
     permutation_vectors()
+    collate_vectors()
     if len(sys.argv) > 1 and sys.argv[1] == "functions":
         sys.exit(0)
     for name, spec in CASES.items():

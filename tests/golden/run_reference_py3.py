@@ -167,5 +167,26 @@ def run_make_network(appdir, working_dir, mapfile):
         sys.argv = argv
 
 
+def run_collate(appdir, working_dir):
+    """Executes the converted 2-collate-results.py as __main__ with `-wd working_dir`."""
+    install_py2_shims()
+    os.makedirs(appdir, exist_ok=True)
+    script = os.path.join(appdir, "2-collate-results.py")
+    with open(os.path.join(REF, "2-collate-results.py")) as f:
+        converted = convert_py2(f.read())
+    with open(script, "w") as o:
+        o.write(converted)
+    argv = sys.argv
+    sys.argv = [script, "-wd", working_dir]
+    try:
+        import_reference_coexfunctions()
+        return runpy.run_path(script, init_globals={"sum": py27_sum}, run_name="__main__")
+    finally:
+        sys.argv = argv
+
+
 if __name__ == "__main__":
-    run_make_network(sys.argv[1], sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "collate":
+        run_collate(sys.argv[2], sys.argv[3])
+    else:
+        run_make_network(sys.argv[1], sys.argv[2], sys.argv[3])

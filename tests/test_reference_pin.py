@@ -283,3 +283,26 @@ def test_permuted_positions_reproduce_executed_reference_block(mode):
             picks = rnd.sample(range(len(backlines)), len(snps))        # :568, one draw per permuted set, in loop order
             want = set(po.background_positions(backlines, picks))
         assert got == want, (mode, k, s["shift"], sorted(got ^ want)[:6])
+
+
+# ---- row N3: collation against the executed 2-collate-results.py ------------------------------------------------------
+def test_collate_reproduces_executed_reference_tables(tmp_path):
+    """coexpression_b200/collate.py on the perm_results_store the reference's own 1-make-network.py wrote, against the
+    `<label>.individual_scores` table and `allscores.txt` the reference's own 2-collate-results.py made of it: pooled null,
+    empirical p, Benjamini-Hochberg column, score / number of groups, the (score, name) order -- text for text."""
+    from coexpression_b200.collate import collate
+    with gzip.open(os.path.join(HERE, "golden", "reference_collate.json.gz"), "rt") as f:
+        fx = json.load(f)
+    wd = tmp_path / "work"
+    (wd / "perm_results_store").mkdir(parents=True)
+    for name, text in fx["store"].items():
+        (wd / "perm_results_store" / name).write_text(text)
+    bed = tmp_path / "f5ep.bed"
+    bed.write_text(fx["feature_bed"])
+    settings = dict(fx["settings"], feature_coordinates=str(bed))
+    (wd / "settings.txt").write_text(json.dumps(settings))
+    res = collate(str(wd))
+    assert res["num_completed_perms"] == 3
+    assert open(res["individual_scores_file"]).read() == fx["individual_scores"]
+    assert (wd / "allscores.txt").read_text() == fx["allscores"]
+    assert len(fx["individual_scores"].splitlines()) > 40
