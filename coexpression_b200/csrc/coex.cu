@@ -751,7 +751,7 @@ int coex_destroy(coex_ctx *c) {
     c->raw_own.release(); c->raw_sum.release(); c->raw_mean.release(); c->raw_xx.release(); c->rawsum_pos.release();
     c->rank2.release(); c->u_hi.release(); c->u_lo.release(); c->suu.release(); c->sx.release();
     c->z_valid.release(); c->z_ninv.release(); c->za_planes.release(); c->za_inv_s.release();
-    c->st_thr.release(); c->st_w.release(); c->st_col.release(); c->st_cnt.release(); c->st_itemoff.release(); c->st_itemT.release();
+    c->st_thr.release(); c->st_w.release(); c->st_cnt.release(); c->st_itemoff.release(); c->st_itemT.release();
     c->st_cursor.release(); c->sxg.release(); c->dd_work.release();
     c->z_planes.release(); c->z_ok.release(); c->z_l1.release(); c->z_inv_s.release();
     c->ap_hist.release(); c->feat_key.release(); c->feat_row.release(); c->pm_blob.release(); c->pm_counts.release(); c->pm_hits_tmp.release(); c->pm_off.release();
@@ -763,7 +763,7 @@ int coex_destroy(coex_ctx *c) {
     c->d_counts.release(); c->w_gsize.release(); c->w_cursor.release(); c->w_act.release(); c->w_actn.release(); c->w_front.release(); c->w_best.release(); c->w_cand.release(); c->w_state.release(); c->p_idxa.release(); c->p_idxb.release();
     c->p_out.release(); c->icol.release(); c->d_ndeg.release(); c->dd_uniq.release(); c->dd_qlist.release();
     c->dd_items.release(); c->dd_qperm.release(); c->pl_cnt.release(); c->pl_cursor.release(); c->pl_ustart.release(); c->pl_nitems.release();
-    c->pl_itemoff.release(); c->pl_bounds.release(); c->pl_meta.release(); c->pl_err.release(); c->dd_gthr.release(); c->dd_gorg.release(); c->dd_tab.release();
+    c->pl_itemoff.release(); c->pl_bounds.release(); c->pl_meta.release(); c->pl_err.release(); c->dd_gthr.release(); c->dd_tab.release();
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;

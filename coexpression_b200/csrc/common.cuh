@@ -156,11 +156,10 @@ struct coex_ctx {
     // sorted statistics of a strip's work items (count_split.cuh: stat_sort_kernel -> count_dedup_kernel<3>)
     coex::DevBuf<double> st_thr, sxg;
     coex::DevBuf<unsigned int> st_cnt;
-    coex::DevBuf<int> st_col, st_itemT, dd_work;
+    coex::DevBuf<int> st_itemT, dd_work;
     coex::DevBuf<long long> st_itemoff;
     coex::DevBuf<unsigned long long> st_cursor, st_w;
     coex::DevBuf<double> dd_gthr, dd_tab;
-    coex::DevBuf<unsigned int> dd_gorg;
     int count_mode = 0;                       // 0 = de-duplicated sorted-statistics kernel (count_dedup<0>), 1 = per-query binary-search kernel, 2 = de-duplicated bucket-window kernel (count_rows), 3 = row-rank forced, 4 = split form of 0 (stat_sort + count_dedup<3> + score_scatter)
     coex::DevBuf<int> p_idxa, p_idxb;         // coex_pairs staging
     coex::DevBuf<double> p_out;

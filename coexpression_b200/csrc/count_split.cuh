@@ -13,7 +13,7 @@
 // coalesced write of the result.
 //
 // Output per item `it` of the launch: item_T[it] sorted statistics at item_soff[it] (a bump allocation from *st_cursor):
-// st_thr (the statistic), st_col (its table column) for the streaming kernel, and st_w for score_scatter_kernel: the
+// st_rec (16-byte records: the statistic and its table column) for the streaming kernel, and st_w for score_scatter_kernel: the
 // address of the statistic's edge score, with the two per-query facts of quirk Q1 already decided (bit 62: the null value
 // at the skipped column lies below the statistic; bit 63: a column was skipped, the null list holds N - 1 values).
 // The streaming kernel adds st_cnt (columns strictly below the statistic); score_scatter_kernel, one thread per
