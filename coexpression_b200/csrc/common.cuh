@@ -169,7 +169,7 @@ struct coex_ctx {
     long long gemm_col0 = 0;                  // persistent tcgen05 kernel: first table column to compute (0 except for upper-triangle strips)
     coex::DevBuf<unsigned long long> ap_hist; // all-pairs histogram [nbins + 1] (+ NaN pairs), resident across calls
     int ap_nbins = 0;
-    int gemm_bn = 0;                          // tcgen05 kernel: 0 = persistent 128x64 tiles (default), 128 / 64 = one tile per CTA
+    int gemm_bn = 0;                          // tcgen05 kernel: 0 = persistent, 128 x 64 tiles or 128 x 128 for rows of >= 1024 samples (default); -64 / -128 = that persistent kernel forced; 128 / 64 = one tile per CTA
 
     // ---- bookkeeping ------------------------------------------------------------------------
     long long launches = 0;

@@ -359,6 +359,142 @@ gemm_i8_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_ah, const _
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent variant with 128 x 128 tiles for long rows (K >= 1024 bytes).  The 128 x 64 kernel above moves
+// 28 KB through shared memory per 32-byte K step (12 KB written by TMA, 16 KB read by two M128 N128 MMAs = 219 B/clk at
+// the tensor rate) and stalls on it (tensor pipe 61 % at the FANTOM5 shape); with N = 256 MMAs it is 40 KB per TWO such
+// steps of time (156 B/clk), which the one-tile-per-CTA kernel sustains at the full tensor rate -- but that kernel pays
+// TMEM allocation, barrier set-up, the first TMA latency and a 4-warp epilogue per tile with nothing overlapped (44 % of
+// a tile).  A tile's four partial sums fill all 512 TMEM columns, so the accumulators cannot be double-buffered; here
+//   * the TMA producer keeps the 3-stage ring (64 KB / stage) running across tile boundaries, so the operands of tile
+//     t+1 are in shared memory when the epilogue of tile t hands the accumulators back,
+//   * EIGHT epilogue warps drain them (two per TMEM lane quarter, 64 columns each), halving the only serial part,
+//   * allocation and barrier set-up happen once per CTA.
+//   barriers: full[3] / empty[3] (TMA <-> MMA), tmem_full (MMA -> epilogue), tmem_empty (8 epilogue warps -> MMA)
+// ---------------------------------------------------------------------------------------------
+constexpr int kP8Threads = 320, kP8BN = 128;
+
+__global__ void __launch_bounds__(kP8Threads, 1)
+gemm_i8_tc_persistent128_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                                const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+                                int *__restrict__ out, long long ldo, int nkb, int m_tiles, long long n_tiles, int col_tile0,
+                                int *err) {
+    using C = TcCfg<128>;
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    const uint32_t bars = base + C::kStages * C::kStage;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * C::kStages;
+    const uint32_t bar_tfull = bars + 16 * C::kStages, bar_tempty = bar_tfull + 8;
+    const uint32_t tmem_slot = bar_tempty + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tempty, 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ===== TMA producer: the stage ring runs continuously over all tiles of this CTA =====
+        if (lane == 0) {
+            long long g = 0;
+            bool ok = true;
+            for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+                const int m0 = (int)(tile % m_tiles) * kTcBM;           // query-row tile fastest
+                const int c0 = ((int)(tile / m_tiles) + col_tile0) * kP8BN;
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = (int)(g % C::kStages);
+                    if (g >= C::kStages && !mbar_wait(bar_empty + 8 * s, (uint32_t)((g / C::kStages) - 1) & 1u, err, 1)) { ok = false; break; }
+                    const uint32_t st = base + s * C::kStage;
+                    mbar_expect_tx(bar_full + 8 * s, C::kStage);
+                    tma_load_2d(st, &map_ah, bar_full + 8 * s, kb * kTcBK, m0);
+                    tma_load_2d(st + 16384, &map_al, bar_full + 8 * s, kb * kTcBK, m0);
+                    tma_load_2d(st + 32768, &map_bh, bar_full + 8 * s, kb * kTcBK, c0);
+                    tma_load_2d(st + 32768 + kP8BN * 128, &map_bl, bar_full + 8 * s, kb * kTcBK, c0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one accumulator set, handed back by the epilogue before the next tile starts =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_i8(128, 2 * kP8BN);
+            long long g = 0;
+            int it = 0;
+            bool ok = true;
+            for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++it) {
+                if (it >= 1 && !mbar_wait(bar_tempty, (uint32_t)(it - 1) & 1u, err, 4)) { ok = false; break; }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = (int)(g % C::kStages);
+                    if (!mbar_wait(bar_full + 8 * s, (uint32_t)(g / C::kStages) & 1u, err, 2)) { ok = false; break; }
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = base + s * C::kStage;
+#pragma unroll
+                    for (int ks = 0; ks < kTcBK / 32; ++ks) {
+                        const uint64_t a_hi = umma_desc_sw128(st + ks * 32);
+                        const uint64_t a_lo = umma_desc_sw128(st + 16384 + ks * 32);
+                        const uint64_t b_cat = umma_desc_sw128(st + 32768 + ks * 32);
+                        const uint32_t acc = (kb | ks) ? 1u : 0u;
+                        umma_i8(tmem_base, a_hi, b_cat, idesc, acc);                    // [hi.hi | hi.lo]
+                        umma_i8(tmem_base + 2 * kP8BN, a_lo, b_cat, idesc, acc);        // [lo.hi | lo.lo]
+                    }
+                    umma_commit(bar_empty + 8 * s);
+                }
+                if (ok) umma_commit(bar_tfull);
+            }
+        }
+    } else {
+        // ===== epilogue: 8 warps; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int m0 = (int)(tile % m_tiles) * kTcBM;
+            const int c0 = ((int)(tile / m_tiles) + col_tile0) * kP8BN;
+            if (!mbar_wait(bar_tfull, (uint32_t)it & 1u, err, 3)) break;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16);
+            int *orow = out + (long long)(m0 + quarter * 32 + lane) * ldo + c0;
+#pragma unroll 1
+            for (int cc = half * 64; cc < half * 64 + 64; cc += 16) {
+                uint32_t hh[16], hl[16], lh[16], ll[16];
+                tmem_ld16(tl + cc, hh);
+                tmem_ld16(tl + kP8BN + cc, hl);
+                tmem_ld16(tl + 2 * kP8BN + cc, lh);
+                tmem_ld16(tl + 3 * kP8BN + cc, ll);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    int4 v;
+                    v.x = (int)(16384LL * (int)hh[j] + 128LL * ((long long)(int)hl[j] + (int)lh[j]) + (int)ll[j]);
+                    v.y = (int)(16384LL * (int)hh[j + 1] + 128LL * ((long long)(int)hl[j + 1] + (int)lh[j + 1]) + (int)ll[j + 1]);
+                    v.z = (int)(16384LL * (int)hh[j + 2] + 128LL * ((long long)(int)hl[j + 2] + (int)lh[j + 2]) + (int)ll[j + 2]);
+                    v.w = (int)(16384LL * (int)hh[j + 3] + 128LL * ((long long)(int)hl[j + 3] + (int)lh[j + 3]) + (int)ll[j + 3]);
+                    *reinterpret_cast<int4 *>(orow + cc + j) = v;
+                }
+            }
+            // this warp's TMEM reads have completed (wait::ld): hand the accumulators back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
 // =============================================================================================
 // Generic D-digit variant (Pearson): z-scores quantised to D base-128 int8 digits
 // (prepare.cuh: pearson_pack_kernel).  One CTA per 128 x 32 output tile; per 32-byte K step
@@ -540,8 +676,11 @@ inline int tc_gemm_i8_ptrs(coex_ctx *c, const int8_t *a_hi, const int8_t *a_lo, 
     TcState *t = nullptr;
     COEX_TRY(tc_state(c, &t));
     if (m_rows % kTcBM) COEX_FAIL("tc_gemm: query rows must be padded to 128");
-    const bool persistent = (c->gemm_bn == 0);
-    const int BN = persistent ? kPsBN : c->gemm_bn;
+    // gemm_bn: 0 = persistent (128 x 64 tiles; 128 x 128 tiles for long rows), -64 / -128 = that persistent kernel forced,
+    //          64 / 128 = one-tile-per-CTA kernel with that table-column tile
+    const bool persistent = (c->gemm_bn <= 0);
+    const bool wide = persistent && (c->gemm_bn == -128 || (c->gemm_bn == 0 && c->n_pad >= 1024));
+    const int BN = persistent ? (wide ? kP8BN : kPsBN) : c->gemm_bn;
     if (t->bh != c->u_hi.p || t->bl != c->u_lo.p || t->b_rows != c->N_pad || t->n_pad != c->n_pad || t->bn != BN) {
         COEX_TRY(tc_encode(t, &t->map_bh, c->u_hi.p, c->N_pad, c->n_pad, BN));
         COEX_TRY(tc_encode(t, &t->map_bl, c->u_lo.p, c->N_pad, c->n_pad, BN));
@@ -557,7 +696,19 @@ inline int tc_gemm_i8_ptrs(coex_ctx *c, const int8_t *a_hi, const int8_t *a_lo, 
         COEX_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmem));
         COEX_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::kSmem));
         COEX_CUDA(cudaFuncSetAttribute(gemm_i8_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPsSmem));
+        COEX_CUDA(cudaFuncSetAttribute(gemm_i8_tc_persistent128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmem));
         t->attr_set = true;
+    }
+    if (wide) {
+        const int m_tiles = (int)(m_rows / kTcBM);
+        const int col_tile0 = (int)std::min<long long>(c->gemm_col0 / kP8BN, c->N_pad / kP8BN - 1);
+        const long long n_tiles = (long long)m_tiles * (c->N_pad / kP8BN - col_tile0);
+        const unsigned ctas = (unsigned)std::min<long long>(n_tiles, c->sm_count);
+        gemm_i8_tc_persistent128_kernel<<<ctas, kP8Threads, TcCfg<128>::kSmem, c->stream>>>(t->map_ah, t->map_al, t->map_bh, t->map_bl,
+                                                                                          out, ldo, c->n_pad / kTcBK, m_tiles, n_tiles,
+                                                                                          col_tile0, t->d_err);
+        COEX_CUDA(cudaGetLastError());
+        return 0;
     }
     if (persistent) {
         const int m_tiles = (int)(m_rows / kTcBM);

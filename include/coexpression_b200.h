@@ -155,8 +155,9 @@ int coex_network_batch(coex_ctx *ctx, const coex_params *params, int K,
  * (the set-up half of the count stage, stat_sort_kernel) */
 long long coex_launch_count(coex_ctx *ctx);
 int coex_stage_ms(coex_ctx *ctx, int stage, double *ms, long long *launches);
-/* 0 = tcgen05/TMA tensor-core GEMM (default: persistent kernel, 128 x 64 tiles, double-buffered TMEM),
- * 1 = SIMT dp4a GEMM (validation path), 2 = persistent tcgen05 kernel explicitly,
+/* 0 = tcgen05/TMA tensor-core GEMM (default: persistent kernel; 128 x 64 tiles with double-buffered TMEM accumulators, or
+ * 128 x 128 tiles with eight epilogue warps when a row has >= 1024 samples), 1 = SIMT dp4a GEMM (validation path),
+ * 2 / 3 = the persistent tcgen05 kernel with 128 x 64 / 128 x 128 tiles explicitly,
  * 64 / 128 = one-tile-per-CTA tcgen05 kernel with that table-column tile */
 int coex_set_gemm_mode(coex_ctx *ctx, int mode);
 /* 0 = de-duplicated sorted-statistics count kernel (default, count_dedup.cuh; 4 = the same split into a sort, a streaming and
