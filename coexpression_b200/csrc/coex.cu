@@ -54,7 +54,7 @@ static int prepare_impl(coex_ctx *c) {
     COEX_CUDA(cudaMemsetAsync(c->sx.p, 0, c->N_pad * sizeof(double), c->stream));
 
     COEX_TRY(stage_begin(c, ST_RANK));
-    const int P2 = next_pow2(n);
+    const int P2 = std::max(32, next_pow2(n));         // at least one warp-wide block of the in-register sort stages
     const size_t smem = (size_t)P2 * 10 + (size_t)c->n_pad * 2;
     COEX_CUDA(cudaFuncSetAttribute(rank_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rank_pack_kernel<<<(unsigned)N, kRankThreads, smem, c->stream>>>(

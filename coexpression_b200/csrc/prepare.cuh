@@ -70,7 +70,7 @@ rank_pack_kernel(const double *__restrict__ raw, long long N, int n, int n_pad, 
         __syncthreads();
     }
     const int m0 = n - m;                                 // samples equal to the row minimum
-    P2 = 1;
+    P2 = 32;                                              // at least one warp-wide block (see below)
     while (P2 < m) P2 <<= 1;
     for (int p = m + tid; p < P2; p += kRankThreads) {
         keys[p] = __longlong_as_double(0x7ff0000000000000LL);
@@ -78,8 +78,33 @@ rank_pack_kernel(const double *__restrict__ raw, long long N, int n, int n_pad, 
     }
     __syncthreads();
 
-    for (int k = 2; k <= P2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
+    // Bitonic sort of (key, column).  The kernel is bound by shared-memory wavefronts (LSU 98 % of peak at the FANTOM5 shape,
+    // profiles/r01_gemm_fullshape.md), so every compare-exchange whose partners are less than 32 apart is done on registers:
+    // a warp owns 32 consecutive elements (one per lane, conflict-free loads), exchanges with shuffles for the strides 16..1
+    // of a merge phase -- and for ALL strides of the phases k <= 32 -- and writes the block back once.  21 shared-memory
+    // passes instead of 55 for 1024 elements.
+    const int lane = tid & 31, wrp = tid >> 5;
+    auto exchange = [&](double &key, int &col, int i, int k, int j) {      // compare-exchange with lane ^ j, element index i
+        const double pk = __shfl_xor_sync(0xffffffffu, key, j);
+        const int pc = __shfl_xor_sync(0xffffffffu, col, j);
+        const bool gt = (key > pk) || (key == pk && col > pc);
+        const bool lower = (i & j) == 0, up = (i & k) == 0;
+        if ((lower == up) ? gt : !gt) { key = pk; col = pc; }
+    };
+    for (int b0 = wrp * 32; b0 < P2; b0 += kRankThreads) {                  // phases k = 2 .. 32 entirely inside the warp
+        const int i = b0 + lane;
+        double key = keys[i];
+        int col = idx[i];
+#pragma unroll
+        for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) exchange(key, col, i, k, j);
+        keys[i] = key;
+        idx[i] = (uint16_t)col;
+    }
+    __syncthreads();
+    for (int k = 64; k <= P2; k <<= 1) {
+        for (int j = k >> 1; j >= 32; j >>= 1) {                            // partners in different warp blocks: shared memory
             for (int t = tid; t < (P2 >> 1); t += kRankThreads) {
                 const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                 const int l = i | j;
@@ -94,6 +119,16 @@ rank_pack_kernel(const double *__restrict__ raw, long long N, int n, int n_pad, 
             }
             __syncthreads();
         }
+        for (int b0 = wrp * 32; b0 < P2; b0 += kRankThreads) {              // strides 16 .. 1 of this phase on registers
+            const int i = b0 + lane;
+            double key = keys[i];
+            int col = idx[i];
+#pragma unroll
+            for (int j = 16; j > 0; j >>= 1) exchange(key, col, i, k, j);
+            keys[i] = key;
+            idx[i] = (uint16_t)col;
+        }
+        __syncthreads();
     }
 
     // tie run of sorted position p = [lower_bound(key), upper_bound(key)) within the m sorted keys;
