@@ -262,7 +262,7 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
             RankScoreArgs rs{};
             rs.strip = c->strip.p; rs.rank = c->rank_strip.p; rs.ld = ld; rs.uniq_rows = c->dd_uniq.p + u0; rs.ustart = c->pl_ustart.p + u0;
             rs.qlist = c->dd_qlist.p; rs.q_perm = c->dd_qperm.p; rs.u_count = nu; rs.perm_off = c->d_perm_off.p; rs.sc_off = c->d_sc_off.p;
-            rs.hit_rows = d_hits; rs.sx = c->sx.p; rs.rawsum_pos = c->rawsum_pos.p; rs.N = N; rs.anticor = prm->anticorrelation;
+            rs.hit_rows = d_hits; rs.sx = c->sx.p; rs.sxg = c->sxg.p; rs.rawsum_pos = c->rawsum_pos.p; rs.N = N; rs.anticor = prm->anticorrelation;
             rs.scores = d_sc; rs.counts = d_cn; rs.score_tab = c->dd_tab.p;
             rank_score_kernel<<<(unsigned)std::min<long long>(H, (long long)c->sm_count * 16), 256, 0, st>>>(rs);
             COEX_KCHECK(st);

@@ -657,6 +657,7 @@ struct RankScoreArgs {
     const long long *perm_off, *sc_off;
     const int *hit_rows;
     const double *sx;
+    const double *sxg;              // sx, NaN where the raw row sums to <= 0 (the statistic's guard in one gather)
     const unsigned char *rawsum_pos;
     long long N;
     int anticor;
@@ -686,7 +687,7 @@ rank_score_kernel(RankScoreArgs a) {
         const int *srow = a.strip + (long long)s_slot * a.ld;
         const unsigned int *rrow = a.rank + (long long)s_slot * a.ld;
         const double sxu = a.sx[u];
-        const bool posu = a.rawsum_pos[u] != 0;
+        const double sxu_g = a.sxg[u];
         double vi = -99.0;                            // null value at table column i (quirk Q1)
         if (i < a.N) { const double sxc = a.sx[i]; if (sxu != 0.0 && sxc != 0.0) vi = __ddiv_rn(0.25 * (double)srow[i], __dmul_rn(sxu, sxc)); }
         double *sc = a.scores + a.sc_off[k] + (long long)i * P;
@@ -694,11 +695,9 @@ rank_score_kernel(RankScoreArgs a) {
         for (int j = threadIdx.x; j < P; j += blockDim.x) {
             if (j == i) { sc[j] = 0.0; if (cn) cn[j] = -1; continue; }
             const int c = a.hit_rows[off + j];
-            double t = -99.0;
-            if (posu && a.rawsum_pos[c]) {
-                t = __ddiv_rn(0.25 * (double)srow[c], __dmul_rn(sxu, a.sx[c]));
-                if (t != t) t = -99.0;
-            }
+            // coexfunctions.py:389 (either raw sum <= 0 -> NaN through sxg) and :406-408 (NaN -> -99)
+            double t = __ddiv_rn(0.25 * (double)srow[c], __dmul_rn(sxu_g, a.sxg[c]));
+            if (t != t) t = -99.0;
             if (t == -99.0) { sc[j] = -log10(1.0); if (cn) cn[j] = -1; continue; }
             long long idx = rrow[c];
             long long len = a.N;
