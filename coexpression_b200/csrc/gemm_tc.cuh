@@ -97,6 +97,28 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr));
 }
 
+// Epilogue store of 16 consecutive int32 columns of this lane's row.  A lane owns one strip row (the TMEM lane), so a plain 16-byte
+// store per lane touches 32 different rows and writes HALF a 32-byte sector each: twice the L2 write requests of the bytes moved
+// (the kernel is bound by the strip it writes when rows are short: L2 67 % busy at K = 256).  Lane pairs exchange halves through
+// shuffles instead, so that every store instruction writes whole sectors: the even lane's row in two instructions, the odd
+// lane's row in the other two.
+__device__ __forceinline__ void store_chunk16_paired(int *orow_own, long long ldo, int cc, const int (&v)[16], int lane) {
+    const bool odd = (lane & 1) != 0;
+    int r[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int b = (q & 3) + 8 * (q >> 2);
+        r[q] = __shfl_xor_sync(0xffffffffu, odd ? v[b] : v[b + 4], 1);   // even gets B[0..3], B[8..11]; odd gets A[4..7], A[12..15]
+    }
+    int *pown = orow_own + cc;
+    int *ppar = pown + (odd ? -ldo : ldo);
+    // instructions 0 / 1: the even lane's row (A); 2 / 3: the odd lane's row (B)
+    *reinterpret_cast<int4 *>(odd ? ppar + 4 : pown) = odd ? make_int4(r[0], r[1], r[2], r[3]) : make_int4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<int4 *>(odd ? ppar + 12 : pown + 8) = odd ? make_int4(r[4], r[5], r[6], r[7]) : make_int4(v[8], v[9], v[10], v[11]);
+    *reinterpret_cast<int4 *>(odd ? pown + 4 : ppar) = odd ? make_int4(v[4], v[5], v[6], v[7]) : make_int4(r[0], r[1], r[2], r[3]);
+    *reinterpret_cast<int4 *>(odd ? pown + 12 : ppar + 8) = odd ? make_int4(v[12], v[13], v[14], v[15]) : make_int4(r[4], r[5], r[6], r[7]);
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start address >> 4 in
 // bits [0,14), LBO (unused for swizzled K-major) = 1 in [16,30), SBO = 1024 B (8 rows x 128 B)
 // >> 4 in [32,46), descriptor version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
@@ -336,15 +358,11 @@ gemm_i8_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_ah, const _
                 tmem_ld16(tl + 2 * kPsBN + cc, lh);
                 tmem_ld16(tl + 3 * kPsBN + cc, ll);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                int v[16];
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    int4 v;
-                    v.x = (int)(16384LL * (int)hh[j] + 128LL * ((long long)(int)hl[j] + (int)lh[j]) + (int)ll[j]);
-                    v.y = (int)(16384LL * (int)hh[j + 1] + 128LL * ((long long)(int)hl[j + 1] + (int)lh[j + 1]) + (int)ll[j + 1]);
-                    v.z = (int)(16384LL * (int)hh[j + 2] + 128LL * ((long long)(int)hl[j + 2] + (int)lh[j + 2]) + (int)ll[j + 2]);
-                    v.w = (int)(16384LL * (int)hh[j + 3] + 128LL * ((long long)(int)hl[j + 3] + (int)lh[j + 3]) + (int)ll[j + 3]);
-                    *reinterpret_cast<int4 *>(orow + cc + j) = v;
-                }
+                for (int j = 0; j < 16; ++j)
+                    v[j] = (int)(16384LL * (int)hh[j] + 128LL * ((long long)(int)hl[j] + (int)lh[j]) + (int)ll[j]);
+                store_chunk16_paired(orow, ldo, cc, v, lane);
             }
             // this warp's TMEM reads have completed (wait::ld): hand the buffer back to the MMA warp
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -472,15 +490,11 @@ gemm_i8_tc_persistent128_kernel(const __grid_constant__ CUtensorMap map_ah, cons
                 tmem_ld16(tl + 2 * kP8BN + cc, lh);
                 tmem_ld16(tl + 3 * kP8BN + cc, ll);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                int v[16];
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    int4 v;
-                    v.x = (int)(16384LL * (int)hh[j] + 128LL * ((long long)(int)hl[j] + (int)lh[j]) + (int)ll[j]);
-                    v.y = (int)(16384LL * (int)hh[j + 1] + 128LL * ((long long)(int)hl[j + 1] + (int)lh[j + 1]) + (int)ll[j + 1]);
-                    v.z = (int)(16384LL * (int)hh[j + 2] + 128LL * ((long long)(int)hl[j + 2] + (int)lh[j + 2]) + (int)ll[j + 2]);
-                    v.w = (int)(16384LL * (int)hh[j + 3] + 128LL * ((long long)(int)hl[j + 3] + (int)lh[j + 3]) + (int)ll[j + 3]);
-                    *reinterpret_cast<int4 *>(orow + cc + j) = v;
-                }
+                for (int j = 0; j < 16; ++j)
+                    v[j] = (int)(16384LL * (int)hh[j] + 128LL * ((long long)(int)hl[j] + (int)lh[j]) + (int)ll[j]);
+                store_chunk16_paired(orow, ldo, cc, v, lane);
             }
             // this warp's TMEM reads have completed (wait::ld): hand the accumulators back to the MMA warp
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
