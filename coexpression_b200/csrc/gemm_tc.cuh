@@ -617,13 +617,20 @@ gemm_digits_tc_kernel(const __grid_constant__ TcMaps8 maps, double *__restrict__
 #pragma unroll
                         for (int j = 0; j < 16; ++j) S[j] += (long long)(int)v[j] * (1LL << (7 * (i + l)));
                     }
+                if (out32) {
+                    // float strip: whole sectors per store instruction (see store_chunk16_paired), not 8 bytes per lane and row
+                    int vf[16];
 #pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                    double2 w;
-                    w.x = (double)S[j] * (inv_a * inv_s[c0 + cc + j]);
-                    w.y = (double)S[j + 1] * (inv_a * inv_s[c0 + cc + j + 1]);
-                    if (out32) *reinterpret_cast<float2 *>(orow32 + cc + j) = make_float2((float)w.x, (float)w.y);
-                    else *reinterpret_cast<double2 *>(orow + cc + j) = w;
+                    for (int j = 0; j < 16; ++j) vf[j] = __float_as_int((float)((double)S[j] * (inv_a * inv_s[c0 + cc + j])));
+                    store_chunk16_paired(reinterpret_cast<int *>(orow32), ldo, cc, vf, lane);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) {
+                        double2 w;
+                        w.x = (double)S[j] * (inv_a * inv_s[c0 + cc + j]);
+                        w.y = (double)S[j + 1] * (inv_a * inv_s[c0 + cc + j + 1]);
+                        *reinterpret_cast<double2 *>(orow + cc + j) = w;
+                    }
                 }
             }
         }
