@@ -624,12 +624,29 @@ gemm_digits_tc_kernel(const __grid_constant__ TcMaps8 maps, double *__restrict__
                     for (int j = 0; j < 16; ++j) vf[j] = __float_as_int((float)((double)S[j] * (inv_a * inv_s[c0 + cc + j])));
                     store_chunk16_paired(reinterpret_cast<int *>(orow32), ldo, cc, vf, lane);
                 } else {
+                    // double strip, the same way: the even lane's row in four store instructions, the odd lane's row in the other
+                    // four, each lane pair writing one whole 32-byte sector per instruction
+                    double w[16];
 #pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                        double2 w;
-                        w.x = (double)S[j] * (inv_a * inv_s[c0 + cc + j]);
-                        w.y = (double)S[j + 1] * (inv_a * inv_s[c0 + cc + j + 1]);
-                        *reinterpret_cast<double2 *>(orow + cc + j) = w;
+                    for (int j = 0; j < 16; ++j) w[j] = (double)S[j] * (inv_a * inv_s[c0 + cc + j]);
+                    const bool odd = (lane & 1) != 0;
+                    double r[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int b = 4 * (q >> 1) + (q & 1);
+                        r[q] = __shfl_xor_sync(0xffffffffu, odd ? w[b] : w[b + 2], 1);   // even gets B[4k], B[4k+1]; odd gets A[4k+2], A[4k+3]
+                    }
+                    double *pown = orow + cc;
+                    double *ppar = pown + (odd ? -ldo : ldo);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {          // row A (the even lane's)
+                        *reinterpret_cast<double2 *>(odd ? ppar + 4 * k + 2 : pown + 4 * k) =
+                            odd ? make_double2(r[2 * k], r[2 * k + 1]) : make_double2(w[4 * k], w[4 * k + 1]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {          // row B (the odd lane's)
+                        *reinterpret_cast<double2 *>(odd ? pown + 4 * k + 2 : ppar + 4 * k) =
+                            odd ? make_double2(w[4 * k + 2], w[4 * k + 3]) : make_double2(r[2 * k], r[2 * k + 1]);
                     }
                 }
             }
