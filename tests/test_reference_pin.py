@@ -306,3 +306,40 @@ def test_collate_reproduces_executed_reference_tables(tmp_path):
     assert open(res["individual_scores_file"]).read() == fx["individual_scores"]
     assert (wd / "allscores.txt").read_text() == fx["allscores"]
     assert len(fx["individual_scores"].splitlines()) > 40
+
+
+def test_py2_rewrite_is_line_local_and_mechanical():
+    """The 2 -> 3 rewrite used to execute the reference's scripts (tests/golden/run_reference_py3.py): only the listed
+    syntactic forms change, everything else passes through byte for byte."""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    from run_reference_py3 import convert_py2, py27_sum
+    src = "\n".join([
+        'if verbose: print "x", y  # note',
+        'print "a %s" % (len(',
+        '    z))',
+        'print ("already", "a call")',
+        'for k, v in d.iteritems():',
+        '    for i in xrange(3): pass',
+        'ptcf = exp_dict.keys()',
+        'order = sorted(m.iteritems(), key=lambda (k, v): (v, k), reverse=True)',
+        'import ConfigParser',
+        'x = 1 / 2  # untouched: no arithmetic is rewritten',
+    ])
+    out = convert_py2(src).split("\n")
+    assert out == [
+        'if verbose: print("x", y)  # note',
+        'print("a %s" % (len( z)))',
+        'print ("already", "a call")',
+        'for k, v in d.items():',
+        '    for i in range(3): pass',
+        'ptcf = list(exp_dict.keys())',
+        'order = sorted(m.items(), key=lambda kv: (kv[1], kv[0]), reverse=True)',
+        'import configparser as ConfigParser',
+        'x = 1 / 2  # untouched: no arithmetic is rewritten',
+    ]
+    vals = [0.1] * 10 + [1e16, -1e16]
+    acc = 0
+    for v in vals:
+        acc = acc + v
+    assert py27_sum(vals) == acc                         # plain left-to-right, unlike Python >= 3.12's compensated sum
