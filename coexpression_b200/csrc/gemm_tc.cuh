@@ -113,10 +113,11 @@ __device__ __forceinline__ void store_chunk16_paired(int *orow_own, long long ld
     int *pown = orow_own + cc;
     int *ppar = pown + (odd ? -ldo : ldo);
     // instructions 0 / 1: the even lane's row (A); 2 / 3: the odd lane's row (B)
-    *reinterpret_cast<int4 *>(odd ? ppar + 4 : pown) = odd ? make_int4(r[0], r[1], r[2], r[3]) : make_int4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<int4 *>(odd ? ppar + 12 : pown + 8) = odd ? make_int4(r[4], r[5], r[6], r[7]) : make_int4(v[8], v[9], v[10], v[11]);
-    *reinterpret_cast<int4 *>(odd ? pown + 4 : ppar) = odd ? make_int4(v[4], v[5], v[6], v[7]) : make_int4(r[0], r[1], r[2], r[3]);
-    *reinterpret_cast<int4 *>(odd ? pown + 12 : ppar + 8) = odd ? make_int4(v[12], v[13], v[14], v[15]) : make_int4(r[4], r[5], r[6], r[7]);
+    // streaming stores: the strip is written once and read once, much later -- it should not displace the operand tiles in L2
+    __stcs(reinterpret_cast<int4 *>(odd ? ppar + 4 : pown), odd ? make_int4(r[0], r[1], r[2], r[3]) : make_int4(v[0], v[1], v[2], v[3]));
+    __stcs(reinterpret_cast<int4 *>(odd ? ppar + 12 : pown + 8), odd ? make_int4(r[4], r[5], r[6], r[7]) : make_int4(v[8], v[9], v[10], v[11]));
+    __stcs(reinterpret_cast<int4 *>(odd ? pown + 4 : ppar), odd ? make_int4(v[4], v[5], v[6], v[7]) : make_int4(r[0], r[1], r[2], r[3]));
+    __stcs(reinterpret_cast<int4 *>(odd ? pown + 12 : ppar + 8), odd ? make_int4(v[12], v[13], v[14], v[15]) : make_int4(r[4], r[5], r[6], r[7]));
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start address >> 4 in
