@@ -408,6 +408,9 @@ def run_ours(args):
         dominant = max(("corr_gemm", "count_score", "rank_pack", "network"), key=lambda s: per[s][0])
         main = dict(roof.get(dominant) or roof.get("corr_gemm") or {})
         main["kernel"] = dominant if dominant in roof else "corr_gemm"
+        main["kernel_symbol"] = {"count_score": "count_dedup_kernel<0> (row-rank regime: count_dedup_kernel<2> + rank_score_kernel)",
+                                 "corr_gemm": "gemm_i8_tc_persistent_kernel / gemm_i8_tc_persistent128_kernel (rows of >= 1024 samples)",
+                                 "rank_pack": "rank_pack_kernel"}.get(main["kernel"], main["kernel"])
         main["peak_source"] = peak_src
         main["note"] = ("roofline of the kernel with the largest share of the step (CUDA events per launch on the library "
                         "stream); traffic = ncu dram read+write per launch (profiles/r01_end_summary.md), null off the default config")
