@@ -69,6 +69,9 @@ def run_case(name, seed, N, n, n_loci, window, overrides):
         for k, gw in enumerate(sets):
             mf = os.path.join(wd, "permutation_store", "f5ep.%d.bed" % k)
             synth.write_map_file(mf, t, m, gw, window, prefix="rs" if k == 0 else "rand_rs")
+            with open(mf, "a") as o:                       # lines the reader must skip (1-make-network.py:139-146)
+                o.write("1\t5\t6\trsNOTABLE\t1\t1\t2\tx\t0\t+\tchr1:1..2,+not_in_table\n")
+                o.write("too\tshort\tline\n")
             mapfiles.append(mf)
         cfg = os.path.join(tmp, "app.cfg")
         with open(cfg, "w") as o:
@@ -92,7 +95,7 @@ def run_case(name, seed, N, n, n_loci, window, overrides):
                                        ("feature_coordinates", "correlationfile", "expression_file", "config_file")},
             "names": list(t.names), "X": [[float(v) for v in row] for row in t.X],
             "addresses": {nm: list(a) for nm, a in t.addresses().items()},
-            "glist": [float(v) for v in glist], "runs": runs,
+            "glist": [float(v) for v in glist], "runs": runs, "mapfiles": [open(mf).read() for mf in mapfiles],
             "how": "unmodified /root/reference/coexfunctions.py + mechanically 2to3-rewritten /root/reference/1-make-network.py, "
                    "executed by tests/golden/run_reference_py3.py against the unmodified reference C build",
         }

@@ -343,3 +343,21 @@ def test_py2_rewrite_is_line_local_and_mechanical():
     for v in vals:
         acc = acc + v
     assert py27_sum(vals) == acc                         # plain left-to-right, unlike Python >= 3.12's compensated sum
+
+
+@pytest.mark.parametrize("path", RUNS, ids=[os.path.basename(p)[14:-8] for p in RUNS])
+def test_map_file_reader_reproduces_executed_reference_snp_map(path, tmp_path):
+    """read_snp_map (1-make-network.py:131-164) on the windowBed-style map files the executed reference read: same
+    promoters in the same (first-appearance) order, same `snps` strings, `p` left at -9999; the line of a promoter that is
+    not in the expression table and the line with fewer than four columns are skipped."""
+    from coexpression_b200.coexfunctions import read_snp_map
+    with gzip.open(path, "rt") as f:
+        fx = json.load(f)
+    table = set(fx["names"])
+    for k, text in enumerate(fx["mapfiles"]):
+        assert "not_in_table" in text and "too\tshort\tline" in text
+        mf = tmp_path / ("f5ep.%d.bed" % k)
+        mf.write_text(text)
+        got = read_snp_map(str(mf), table)
+        want = fx["runs"][k]["snp_map"]
+        assert got == want and list(got) == list(want)
