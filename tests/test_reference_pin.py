@@ -361,3 +361,60 @@ def test_map_file_reader_reproduces_executed_reference_snp_map(path, tmp_path):
         got = read_snp_map(str(mf), table)
         want = fx["runs"][k]["snp_map"]
         assert got == want and list(got) == list(want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["spearman_default", "pearson_default", "spearman_global_nsp0"])
+def test_gpu_file_level_drop_in_against_executed_reference(case, tmp_path):
+    """The whole drop-in at the file level: the files the reference's `1-make-network.py` read when the fixture was made
+    (settings.txt, expression table, feature BED, correlation list, windowBed map files) go into
+    coexpression_b200.make_network.run_batch, and the JSON objects it writes into perm_results_store/ are compared with
+    the ones the reference wrote: snp_map, groups and joining instructions identical, every edge score identical or one
+    documented bisect flip away."""
+    from coexpression_b200.make_network import run_batch
+    path = os.path.join(HERE, "golden", "reference_run_%s.json.gz" % case)
+    with gzip.open(path, "rt") as f:
+        fx = json.load(f)
+    names, X = fx["names"], np.asarray(fx["X"], dtype=np.float64)
+    wd = tmp_path / "work"
+    (wd / "permutation_store").mkdir(parents=True)
+    expr, bed, clist = tmp_path / "t.expression", tmp_path / "f5ep.bed", tmp_path / "t.expression.list"
+    with open(expr, "w") as o:
+        o.write("sample\t" + "\t".join("s%d" % j for j in range(X.shape[1])) + "\n")
+        for nm, row in zip(names, X):
+            o.write(nm + "\t" + "\t".join(repr(float(v)) for v in row) + "\n")
+    with open(bed, "w") as o:
+        for nm in names:
+            c, s, e = fx["addresses"][nm]
+            o.write("%s\t%s\t%s\t%s\n" % (c, s, e, nm))
+    with open(clist, "w") as o:
+        for v in fx["glist"]:
+            o.write("%s\n" % (int(v) if v == -99 else repr(float(v))))
+    for k, text in enumerate(fx["mapfiles"]):
+        (wd / "permutation_store" / ("f5ep.%d.bed" % k)).write_text(text)
+    settings = dict(fx["settings"], feature_coordinates=str(bed), correlationfile=str(clist), expression_file=str(expr),
+                    config_file="app.cfg")
+    (wd / "settings.txt").write_text(json.dumps(settings))
+    written = run_batch(str(wd))
+    assert len(written) == 8 * len(fx["mapfiles"])
+    store = wd / "perm_results_store"
+    L = (len(names) - 1) if float(fx["settings"]["nsp"]) > 0 else len(fx["glist"])
+    for k, run in enumerate(fx["runs"]):
+        got = {obj: json.load(open(store / ("f5ep.%s.%d" % (obj, k)))) for obj in
+               ("snp_map", "prom_to_join", "joining_instructions", "individualscores", "winners", "indmeasure")}
+        assert got["snp_map"] == run["snp_map"] and list(got["snp_map"]) == list(run["snp_map"])
+        assert got["prom_to_join"] == run["prom_to_join"]
+        assert got["joining_instructions"] == run["joining_instructions"]
+        assert set(got["winners"]) == set(run["winners"]) and set(got["indmeasure"]) == set(run["indmeasure"])
+        n_same = n_all = 0
+        for a in run["individualscores"]:
+            for b, v in run["individualscores"][a].items():
+                w = got["individualscores"][a][b]
+                n_all += 1
+                if abs(w - v) <= 1e-12:
+                    n_same += 1
+                    continue
+                cands = [abs(10.0 ** -w - pv) * L for pv in ([1.0, 0.0] if v == 0 else [10.0 ** -v])]
+                cands += [abs(pw - 10.0 ** -v) * L for pw in ([1.0, 0.0] if w == 0 else [])]
+                assert any(abs(st - round(st)) < 1e-6 and 1 <= round(st) <= 64 for st in cands), (a, b, v, w)
+        assert n_all > 1000 and n_same > 0.4 * n_all
