@@ -10,9 +10,20 @@ per permutation), then -- on N > 1 GPUs -- one NCCL gather of the density vector
     python bench.py --gpus N --steps K --warmup W            # our arm
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path
 
-Prints ONE JSON line (see the contract in the task description).  Multi-GPU is weak scaling:
-every rank reduces its own 101 hit sets (independent permutations, no data-path collective);
-`value` = permutations all ranks processed / max-over-ranks device time.
+Prints ONE JSON line (see the contract in the task description).  The headline (`value`, `e2e`,
+`roofline`, `cpu_baseline`) is C2; multi-GPU is weak scaling there: every rank reduces its own
+101 hit sets (independent permutations, no data-path collective) and `value` = permutations all
+ranks processed / max-over-ranks device time.  The same line carries, unless --no-extras:
+
+  parity      GPU result of the cpu_baseline's sample hit sets against the oracle (every bisect
+              index, groups, winners, densities), the same sets inside the big batch, and on
+              N > 1 ranks the gathered density block against every rank's own vector; the
+              process exits non-zero if any of it fails
+  strong      (N > 1) ONE fixed list of hit sets sharded over the ranks (dist.shard_permutations)
+              and gathered (dist.gather_densities); checked against rank 0 doing the list alone
+  full_shape  the north-star target: 200 000 x 1 829 table, 1 001 hit sets of ~500 loci (all
+              ranks share the job when N > 1), stage times, rooflines, a sampled oracle check
+  allpairs    config C3 on the same resident table: all N (N - 1) / 2 pairs, Spearman and Pearson
 """
 import os
 import sys
@@ -55,6 +66,11 @@ def parse():
     ap.add_argument("--gemm", default="tcgen05", choices=["tcgen05", "simt", "tcgen05_bn64", "tcgen05_bn128", "tcgen05_persistent", "tcgen05_persistent128"])
     ap.add_argument("--cpu-sample-perms", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the full_shape / allpairs / strong objects")
+    ap.add_argument("--full-rows", type=int, default=200000)
+    ap.add_argument("--full-samples", type=int, default=1829)
+    ap.add_argument("--full-perms", type=int, default=1000)
+    ap.add_argument("--full-steps", type=int, default=2)
     ap.add_argument("--seed", type=int, default=1234)
     return ap.parse_args()
 
@@ -149,19 +165,24 @@ class ClockSampler:
 # CPU arm: the reference's own path (unmodified C file through ctypes + the Python-3
 # restatement of 1-make-network.py), one process, all host threads
 # ------------------------------------------------------------------------------------------------
-def cpu_permutations(t, hit_sets, glist, args):
+def cpu_permutations(t, hit_sets, glist, args, keep=False):
     """Runs the oracle per permutation exactly as a 1-make-network.py process would: the rank
-    transform of the whole table is redone for every permutation (1-make-network.py:108-111)."""
+    transform of the whole table is redone for every permutation (1-make-network.py:108-111).
+    keep: also return the result objects (bench.py's parity check of the GPU path)."""
     from oracle import network_oracle as no
     t0 = time.perf_counter()
     pairs = 0
+    results = []
     for h in hit_sets:
         R = no.rank_rows(t.X)
-        no.make_network(t.names, t.X, [t.names[r] for r in h], t.addresses(), glist,
-                        anticorrelation=args.anticorrelation, pval_to_join=args.pval_to_join, Xrank=R)
+        w = no.make_network(t.names, t.X, [t.names[r] for r in h], t.addresses(), glist,
+                            anticorrelation=args.anticorrelation, pval_to_join=args.pval_to_join, Xrank=R,
+                            return_counts=keep)
+        if keep:
+            results.append(w)
         pairs += len(h) * (t.N - 1)
     dt = time.perf_counter() - t0
-    return dt, pairs
+    return (dt, pairs, results) if keep else (dt, pairs)
 
 
 def cpu_global_list(t, ga, gb):
@@ -183,8 +204,6 @@ def run_reference(args):
     sample = hits[1:1 + max(1, args.cpu_sample_perms // 2)] or hits[:1]
     times, pairs = [], 0
     for i in range(args.warmup + args.steps):
-        if i == min(args.warmup, 1) and args.warmup > 1:
-            pass
         dt, pr = cpu_permutations(t, sample, glist, args)
         if i >= args.warmup:
             times.append(dt); pairs += pr
@@ -210,39 +229,134 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from coexpression_b200.api import CoexContext, Options, STAGES
+class Env:
+    """torch / NCCL plumbing shared by the parts of the run."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        # NCCL prints its version banner on fd 1 when the communicator is created; stdout must
-        # carry ONE JSON line, so fd 1 points at stderr while NCCL initialises
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=dev)
-            warm = torch.zeros(1, device=dev)
-            dist.all_reduce(warm)
-            torch.cuda.synchronize()
-        finally:
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            # NCCL prints its version banner on fd 1 when the communicator is created; stdout must
+            # carry ONE JSON line, so fd 1 points at stderr while NCCL initialises
             sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group("nccl", device_id=self.dev)
+                warm = torch.zeros(1, device=self.dev)
+                dist.all_reduce(warm)
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+        self.peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                self.peaks = json.load(f)
+        except Exception:
+            pass
+        self.hbm_peak = self.peaks.get("hbm_gbs", 6650.0)
+        self.tc_peak = self.peaks.get("bf16_tflops", 1590.0)
+        self.tc_sustained = self.peaks.get("bf16_tflops_sustained", self.tc_peak)
+        self.peak_src = "measured (MEASURED_PEAKS.json, burst)" if self.peaks else "fallback (B200_PROFILING.md)"
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def log(self, msg):
+        if os.environ.get("COEX_BENCH_DEBUG") or os.environ.get("COEX_BENCH_VERBOSE"):
+            print(f"[bench rank {self.rank} +{time.time() - T_START:.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+T_START = time.time()
+
+
+class DeviceJob:
+    """K hit sets and their device-resident outputs, reused across timed steps."""
+
+    def __init__(self, env, ctx, hits, Hpad=None):
+        torch = env.torch
+        self.hits = hits
+        self.K = len(hits)
+        self.perm_off = np.zeros(self.K + 1, dtype=np.int64)
+        self.perm_off[1:] = np.cumsum([len(h) for h in hits])
+        self.H = int(self.perm_off[-1])
+        self.hit_rows = (np.concatenate(hits).astype(np.int32) if self.H else np.zeros(0, dtype=np.int32))
+        H1 = max(self.H, 1)
+        self.hits_dev = torch.from_numpy(self.hit_rows if self.H else np.zeros(1, dtype=np.int32)).to(env.dev)
+        self.o_ng = torch.zeros(max(self.K, 1), dtype=torch.int32, device=env.dev)
+        self.o_grp = torch.zeros(H1, dtype=torch.int32, device=env.dev)
+        self.o_lab = torch.zeros(H1, dtype=torch.int32, device=env.dev)
+        self.o_win = torch.zeros(H1, dtype=torch.int32, device=env.dev)
+        self.Hpad = max(int(Hpad or 0), H1)
+        self.o_den = torch.zeros(self.Hpad, dtype=torch.float64, device=env.dev)
+        self.o_aps = torch.zeros(H1, dtype=torch.float64, device=env.dev)
+        self.ptrs = dict(hit_rows=self.hits_dev.data_ptr(), n_groups=self.o_ng.data_ptr(), group_of_hit=self.o_grp.data_ptr(),
+                         group_label=self.o_lab.data_ptr(), group_winner=self.o_win.data_ptr(),
+                         group_density=self.o_den.data_ptr(), hit_score=self.o_aps.data_ptr())
+        self.ctx = ctx
+
+    def run(self, opts):
+        if self.K:
+            self.ctx.network_batch_device(opts, self.K, self.perm_off, self.ptrs)
+
+    def densities(self):
+        """-> list over the K sets of float64 arrays (host)."""
+        den = self.o_den.cpu().numpy()
+        ng = self.o_ng.cpu().numpy()
+        return [den[int(self.perm_off[k]):int(self.perm_off[k]) + int(ng[k])].copy() for k in range(self.K)]
+
+
+def compare_with_oracle(res, k, want, names, hits_k):
+    """GPU result of hit set k (api.BatchResult with scores + counts) against an oracle object of make_network."""
+    from coexpression_b200.results import perm_objects
+    got = perm_objects(res, k, names)
+    out = {"groups_equal": got["prom_to_join"] == want["prom_to_join"], "winners_equal": got["winners"] == want["winners"],
+           "indices_equal": True, "max_abs_density_err": 0.0, "max_abs_hit_score_err": 0.0}
+    if len(hits_k) > 1:
+        out["indices_equal"] = bool(np.array_equal(res.count_matrix(k), want["_counts"]))
+    if set(got["indmeasure"]) != set(want["indmeasure"]):
+        out["groups_equal"] = False
+    else:
+        for g, v in want["indmeasure"].items():
+            out["max_abs_density_err"] = max(out["max_abs_density_err"], abs(got["indmeasure"][g] - v))
+        for p_, v in want["allpromoterscores"].items():
+            out["max_abs_hit_score_err"] = max(out["max_abs_hit_score_err"], abs(got["allpromoterscores"].get(p_, float("inf")) - v))
+    return out
+
+
+def run_ours(args):
+    env = Env()
+    torch, dist = env.torch, env.dist
+    from coexpression_b200.api import CoexContext, Options, STAGES
+    world, rank, local, dev = env.world, env.rank, env.local, env.dev
 
     t, hits, ga, gb = workload(args, rank)
     K = len(hits)
     opts = Options(anticorrelation=args.anticorrelation, pval_to_join=args.pval_to_join)
-    perm_off = np.zeros(K + 1, dtype=np.int64)
-    perm_off[1:] = np.cumsum([len(h) for h in hits])
-    H = int(perm_off[-1])
-    hit_rows = np.concatenate(hits).astype(np.int32)
     pairs_per_step = int(sum(len(h) * (t.N - 1) for h in hits))
 
     ctx = CoexContext(local)
@@ -256,51 +370,34 @@ def run_ours(args):
 
     # ---- device-resident inputs / outputs for `value` -------------------------------------------
     X_dev = torch.from_numpy(t.X).to(dev)
-    hits_dev = torch.from_numpy(hit_rows).to(dev)
-    o_ng = torch.zeros(K, dtype=torch.int32, device=dev)
-    o_grp = torch.zeros(H, dtype=torch.int32, device=dev)
-    o_lab = torch.zeros(H, dtype=torch.int32, device=dev)
-    o_win = torch.zeros(H, dtype=torch.int32, device=dev)
     # the gathered density block must have one size on every rank: pad to the largest hit count
-    hpad = torch.tensor([H], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(hpad, op=dist.ReduceOp.MAX)
-    Hpad = int(hpad.item())
-    o_den = torch.zeros(Hpad, dtype=torch.float64, device=dev)
-    o_aps = torch.zeros(H, dtype=torch.float64, device=dev)
-    ptrs = dict(hit_rows=hits_dev.data_ptr(), n_groups=o_ng.data_ptr(), group_of_hit=o_grp.data_ptr(),
-                group_label=o_lab.data_ptr(), group_winner=o_win.data_ptr(), group_density=o_den.data_ptr(),
-                hit_score=o_aps.data_ptr())
+    Hpad = int(env.max_over_ranks(sum(len(h) for h in hits)))
+    job = DeviceJob(env, ctx, hits, Hpad)
+    H, perm_off, hit_rows = job.H, job.perm_off, job.hit_rows
     stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush = env.flush
     gather_buf = torch.zeros(world * Hpad, dtype=torch.float64, device=dev) if world > 1 else None
 
     def step_device():
         ctx.set_expression_device(X_dev.data_ptr(), t.N, t.n, keepalive=X_dev)
         ctx.prepare()
-        ctx.network_batch_device(opts, K, perm_off, ptrs)
+        job.run(opts)
         if world > 1:
             # the one collective of the path: density vectors of every rank (2-collate pools them).
             # coex_network_batch has drained the library stream when it returns, so the gather can
             # be queued on torch's current stream.
-            dist.all_gather_into_tensor(gather_buf, o_den)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            dist.all_gather_into_tensor(gather_buf, job.o_den)
 
     stage_tot = {s: 0.0 for s in STAGES}
     stage_launch = {s: 0 for s in STAGES}
     for _ in range(args.warmup):
         step_device()
-    barrier()
+    env.barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    barrier()                                                # every rank enters the timed steps together
+    env.barrier()                                            # every rank enters the timed steps together
     launches0 = ctx.launch_count()
     t_wall0 = time.time()
     ms = []
@@ -309,18 +406,11 @@ def run_ours(args):
         torch.cuda.synchronize()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        h0 = time.perf_counter()
         ctx.set_expression_device(X_dev.data_ptr(), t.N, t.n, keepalive=X_dev)
-        ctx.prepare()
-        h1 = time.perf_counter()
-        h2 = h1                                              # (prepare does not synchronise: the host plans the batch meanwhile)
-        ctx.network_batch_device(opts, K, perm_off, ptrs)
-        h3 = time.perf_counter()
-        if os.environ.get("COEX_BENCH_DEBUG"):
-            print(f"[rank {rank}] host ms: prepare {1e3*(h1-h0):.2f} stage_ms {1e3*(h2-h1):.2f} network_batch {1e3*(h3-h2):.2f}",
-                  file=sys.stderr)
+        ctx.prepare()                                        # (does not synchronise: the host plans the batch meanwhile)
+        job.run(opts)
         if world > 1:
-            dist.all_gather_into_tensor(gather_buf, o_den)
+            dist.all_gather_into_tensor(gather_buf, job.o_den)
             e1.record()                                      # torch's current stream (after the gather)
         else:
             e1.record(stream)
@@ -331,49 +421,73 @@ def run_ours(args):
             stage_tot[s] += st[s][0]; stage_launch[s] += st[s][1]
     t_wall1 = time.time()
     launches = ctx.launch_count() - launches0
-    barrier()
+    env.barrier()
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     step_ms = float(np.mean(ms))
-    tmax = torch.tensor([step_ms], device=dev)
+    step_ms_max = env.max_over_ranks(step_ms)
+    parity = {"ok": True}
     if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    step_ms_max = float(tmax.item())
+        # the gathered block against every rank's own density vector (outside the timed region)
+        mine = gather_buf[rank * Hpad:(rank + 1) * Hpad]
+        bad = int((mine != job.o_den).sum().item())
+        bad_all = int(env.sum_over_ranks(bad))
+        parity["gathered_block_equals_every_ranks_densities"] = bad_all == 0
+        parity["ok"] &= bad_all == 0
+    dens_resident = job.densities()                          # of the last timed step
 
     # ---- e2e: host buffers through the public API, copies inside the timed region ----------------
-    X_pin = torch.from_numpy(t.X).pin_memory()
-    Xh = X_pin.numpy()
+    # N > 1: the table is uploaded ONCE (rank 0, pinned host memory) and broadcast over NVLink (NCCL); every rank then
+    # ranks / packs its copy, reduces its own hit sets (host lists), and the density vectors are gathered on the device
+    # and read back once.
+    X_pin = torch.from_numpy(t.X).pin_memory() if rank == 0 else None
+    Xh = X_pin.numpy() if rank == 0 else None
+    X_bc = torch.empty((t.N, t.n), dtype=torch.float64, device=dev) if world > 1 else None
     e2e_ms = []
-    h2d = Xh.nbytes + hit_rows.nbytes + perm_off.nbytes
+    h2d = t.X.nbytes + hit_rows.nbytes + perm_off.nbytes
     d2h = 4 * K + 3 * 4 * H + 2 * 8 * H
+    res = None
     for i in range(2 + max(2, args.steps // 2)):
-        torch.cuda.synchronize()
+        env.barrier()
         w0 = time.perf_counter()
-        ctx.set_expression(Xh)
+        if world == 1:
+            ctx.set_expression(Xh)
+        else:
+            if rank == 0:
+                X_bc.copy_(X_pin, non_blocking=True)
+            dist.broadcast(X_bc, src=0)
+            torch.cuda.current_stream().synchronize()
+            ctx.set_expression_device(X_bc.data_ptr(), t.N, t.n, keepalive=X_bc)
         ctx.prepare()
         res = ctx.network_batch(hits, opts)
-        dens = res.group_density
         if world > 1:
-            o_den[:H].copy_(torch.from_numpy(dens))
-            dist.all_gather_into_tensor(gather_buf, o_den)
-            all_dens = gather_buf.cpu()
+            job.o_den[:H].copy_(torch.from_numpy(res.group_density), non_blocking=False)
+            dist.all_gather_into_tensor(gather_buf, job.o_den)
+            if rank == 0:
+                all_dens = gather_buf.cpu()
+            else:
+                torch.cuda.synchronize()
         w1 = time.perf_counter()
         if i >= 2:
             e2e_ms.append(1e3 * (w1 - w0))
-    e2e_t = torch.tensor([float(np.mean(e2e_ms))], device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_step_ms = float(e2e_t.item())
+    e2e_step_ms = env.max_over_ranks(float(np.mean(e2e_ms)))
+    for k in range(K):                                       # host-buffer API == resident API, bit for bit
+        a, b = int(perm_off[k]), int(perm_off[k]) + int(res.n_groups[k])
+        if not np.array_equal(res.group_density[a:b], dens_resident[k]):
+            parity["ok"] = False
+            parity["e2e_equals_resident"] = False
+            break
+    else:
+        parity["e2e_equals_resident"] = True
 
+    # ---- strong scaling: ONE fixed list of hit sets sharded over the ranks ------------------------------------
+    strong = None
+    if world > 1 and not args.no_extras:
+        strong = strong_scaling(env, ctx, args, t, X_dev, opts, step_ms if rank == 0 else 0.0, dens_resident if rank == 0 else None)
+        parity["ok"] &= strong.pop("_ok")
+
+    line = None
     if rank == 0:
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                peaks = json.load(f)
-        except Exception:
-            pass
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        tc_peak = peaks.get("bf16_tflops", 1590.0)
-        peak_src = "measured (MEASURED_PEAKS.json, burst)" if peaks else "fallback (B200_PROFILING.md)"
+        hbm_peak, tc_peak, peak_src = env.hbm_peak, env.tc_peak, env.peak_src
         per = {s: (stage_tot[s] / args.steps, stage_launch[s] / args.steps) for s in STAGES}
         # algorithmic work per step
         # the correlation strips are formed once per UNIQUE hit row (queries of several permutations share it)
@@ -385,8 +499,12 @@ def run_ours(args):
                       args.window == 10000 and args.seed == 1234 and world == 1)
         try:
             if is_default:
-                with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-                    traffic = json.load(f)
+                for name in ("r02_traffic.json", "r01_traffic.json"):
+                    path = os.path.join(ROOT, "profiles", name)
+                    if os.path.exists(path):
+                        with open(path) as f:
+                            traffic = json.load(f)
+                        break
         except Exception:
             traffic = {}
         rank_bytes = float(t.N) * t.n * (8 + 2 + 2)
@@ -405,6 +523,14 @@ def run_ours(args):
             a = rank_bytes / (per["rank_pack"][0] * 1e-3) / 1e9
             roof["rank_pack"] = {"bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak,
                                  "traffic": traffic.get("rank_pack"), "ms_per_step": per["rank_pack"][0], "launches_per_step": per["rank_pack"][1]}
+        if per["rowstats"][0] > 0:
+            a = float(t.N) * t.n * 16 / (per["rowstats"][0] * 1e-3) / 1e9
+            roof["rowstats"] = {"bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak, "traffic": None,
+                                "ms_per_step": per["rowstats"][0], "launches_per_step": per["rowstats"][1]}
+        if per["gather"][0] > 0:
+            a = 2.0 * 2.0 * U * ctx_n_pad(t.n) / (per["gather"][0] * 1e-3) / 1e9     # two int8 digit planes, read + written
+            roof["gather"] = {"bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak, "traffic": None,
+                              "ms_per_step": per["gather"][0], "launches_per_step": per["gather"][1]}
         dominant = max(("corr_gemm", "count_score", "rank_pack", "network"), key=lambda s: per[s][0])
         main = dict(roof.get(dominant) or roof.get("corr_gemm") or {})
         main["kernel"] = dominant if dominant in roof else "corr_gemm"
@@ -413,11 +539,15 @@ def run_ours(args):
                                  "rank_pack": "rank_pack_kernel"}.get(main["kernel"], main["kernel"])
         main["peak_source"] = peak_src
         main["note"] = ("roofline of the kernel with the largest share of the step (CUDA events per launch on the library "
-                        "stream); traffic = ncu dram read+write per launch (profiles/r01_end_summary.md), null off the default config")
+                        "stream); traffic = ncu dram read+write per launch (profiles/), null off the default config")
         total_perms = K * world
         line = {
             "metric": "permutations_per_sec", "value": total_perms / (step_ms_max * 1e-3), "unit": "permutations/s",
             "pairs_per_sec": pairs_per_step * world / (step_ms_max * 1e-3),
+            "pairs_per_sec_contracted": float(U) * t.N * world / (step_ms_max * 1e-3),
+            "pairs_note": "pairs_per_sec counts the pairs the reference would correlate for these hit sets, P (N - 1) per permutation "
+                          "(1-make-network.py:208-213); pairs_per_sec_contracted counts the dot products the GEMM really forms after "
+                          "de-duplication (unique hit rows x table rows, rank 0's count x ranks)",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms_max,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s8 x s8 -> s32 (exact), f64 epilogue",
             "data": "synthetic",
@@ -427,25 +557,390 @@ def run_ours(args):
             "stage_ms_per_step": {s: per[s][0] for s in STAGES},
             "e2e": {"value": total_perms / (e2e_step_ms * 1e-3), "unit": "permutations/s", "ms_per_step": e2e_step_ms,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": "CoexContext.set_expression + prepare + network_batch (pinned host table, host hit lists)"},
+                    "api": ("CoexContext.set_expression + prepare + network_batch (pinned host table, host hit lists)" if world == 1 else
+                            "rank 0 uploads the pinned host table once, NCCL broadcast over NVLink, then per rank prepare + "
+                            "network_batch (host hit lists) and one NCCL all-gather of the densities read back on rank 0")},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if strong is not None:
+            line["strong"] = strong
         if not args.no_cpu_baseline and world == 1:
             from oracle import network_oracle as no
-            sample = hits[1:1 + args.cpu_sample_perms] or hits[:1]
-            dt, pr = cpu_permutations(t, sample, glist.tolist(), args)
+            ks = list(range(1, 1 + args.cpu_sample_perms)) if K > 1 else [0]
+            ks = [k for k in ks if k < K]
+            sample = [hits[k] for k in ks]
+            dt, pr, want = cpu_permutations(t, sample, glist.tolist(), args, keep=True)
             line["cpu_baseline"] = {
                 "value": len(sample) / dt, "unit": "permutations/s", "cores": no.num_threads(), "kind": no.default_kind(),
                 "pairs_per_sec": pr / dt,
                 "sample": f"{len(sample)} permuted hit sets of this workload (hits {[len(h) for h in sample]}), "
                           "rank transform redone per permutation as every reference process does; consistent oracle "
                           "(statistic from the C library, faster than the reference's P^2 scipy calls)"}
-        print(json.dumps(line))
+            # ---- parity of the timed configuration: the same sets through the GPU path, alone and inside the batch ----
+            res_s = ctx.network_batch(sample, opts, want_scores=True, want_counts=True)
+            agg = {"groups_equal": True, "winners_equal": True, "indices_equal": True, "max_abs_density_err": 0.0,
+                   "max_abs_hit_score_err": 0.0}
+            for j, k in enumerate(ks):
+                c = compare_with_oracle(res_s, j, want[j], t.names, sample[j])
+                for key in ("groups_equal", "winners_equal", "indices_equal"):
+                    agg[key] &= c[key]
+                for key in ("max_abs_density_err", "max_abs_hit_score_err"):
+                    agg[key] = max(agg[key], c[key])
+                in_batch = np.array_equal(res_s.perm(j)["density"], dens_resident[k])
+                agg["batch_of_%d_equals_alone" % K] = agg.get("batch_of_%d_equals_alone" % K, True) and bool(in_batch)
+            agg["sets"] = len(ks)
+            agg["bisect_indices_compared"] = int(sum(len(h) * (len(h) - 1) for h in sample))
+            agg["tolerance"] = 1e-6
+            ok = (agg["groups_equal"] and agg["winners_equal"] and agg["indices_equal"] and agg["max_abs_density_err"] <= 1e-6
+                  and agg["max_abs_hit_score_err"] <= 1e-6 and agg["batch_of_%d_equals_alone" % K])
+            parity.update(agg)
+            parity["ok"] &= bool(ok)
     ctx.close()
+    del X_dev, job
+
+    # ---- the north-star target and C3 on the full FANTOM5 shape -----------------------------------------------
+    if not args.no_extras:
+        try:
+            full, allp = full_shape(env, args)
+            if rank == 0:
+                line["full_shape"] = full
+                if allp is not None:
+                    line["allpairs"] = allp
+                if not full.get("parity", {}).get("ok", True) or (allp is not None and not allp.get("ok", True)):
+                    parity["ok"] = False
+        except Exception as e:                               # the headline stays valid; the failure is visible in the line
+            if rank == 0:
+                line["full_shape"] = {"error": f"{type(e).__name__}: {e}"}
+                parity["ok"] = False
+    rc = 0
+    if rank == 0:
+        line["parity"] = parity
+        print(json.dumps(line))
+        rc = 0 if parity["ok"] else 1
+    rc = int(env.max_over_ranks(rc))
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return rc
+
+
+def ctx_n_pad(n):
+    return (n + 127) // 128 * 128
+
+
+def strong_scaling(env, ctx, args, t, X_dev, opts, one_gpu_ms, dens_one_gpu):
+    """ONE fixed job (rank 0's 101 hit sets) split over the ranks: what runlocal.py:19,78-79 does with processes."""
+    from coexpression_b200 import synth
+    from coexpression_b200.dist import shard_permutations, gather_densities
+    torch = env.torch
+    hits, _, _ = synth.make_permutation_hits(t, args.loci, args.perms, window=args.window, seed=args.seed + 17)   # rank 0's list
+    shards = shard_permutations([len(h) for h in hits], env.world)
+    mine = shards[env.rank]
+    job = DeviceJob(env, ctx, [hits[k] for k in mine])
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=env.dev)
+
+    def step():
+        ctx.set_expression_device(X_dev.data_ptr(), t.N, t.n, keepalive=X_dev)
+        ctx.prepare()
+        job.run(opts)
+
+    for _ in range(max(1, args.warmup)):
+        step()
+    env.barrier()
+    ms = []
+    for _ in range(args.steps):
+        env.flush.fill_(1)
+        env.barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    dev_ms = env.max_over_ranks(float(np.mean(ms)))
+    # the gather (outside the device timing: it is the same single collective as in the weak run) and the check
+    w0 = time.perf_counter()
+    allden = gather_densities(mine, job.densities(), len(hits), device=env.dev)
+    gather_ms = env.max_over_ranks(1e3 * (time.perf_counter() - w0))
+    ok = True
+    if env.rank == 0:
+        ok = all(allden[k] is not None and np.array_equal(allden[k], dens_one_gpu[k]) for k in range(len(hits)))
+    ok = env.max_over_ranks(0.0 if ok else 1.0) == 0.0
+    uniq = env.sum_over_ranks(float(np.unique(job.hit_rows).size))
+    out = {"workload": f"the {len(hits)} hit sets of rank 0's C2 job, sharded by dist.shard_permutations (longest P^2 first)",
+           "ms_per_step": dev_ms, "permutations_per_sec": len(hits) / (dev_ms * 1e-3),
+           "one_gpu_ms_per_step": env.max_over_ranks(one_gpu_ms),
+           "speedup_vs_one_gpu": env.max_over_ranks(one_gpu_ms) / dev_ms,
+           "unique_hit_rows_summed_over_ranks": int(uniq),
+           "gather_ms_host_clock": gather_ms,
+           "gathered_equals_one_gpu_bit_for_bit": bool(ok), "_ok": bool(ok)}
+    return out
+
+
+def full_shape(env, args):
+    """North-star target (BASELINE.json): 200 000 x 1 829 synthetic table, 1 000 permutations + the real set, Spearman;
+    then config C3 (all unordered pairs, Spearman + Pearson) on the same resident table.  N > 1: rank 0 makes the table,
+    uploads it once and broadcasts it (NCCL); the hit sets are sharded over the ranks (strong scaling of ONE job); the
+    all-pairs row blocks are dealt to the ranks and the histograms all-reduced."""
+    torch, dist = env.torch, env.dist
+    from coexpression_b200 import synth
+    from coexpression_b200.api import CoexContext, Options, STAGES
+    from coexpression_b200.dist import shard_permutations, gather_densities, shard_row_blocks, pairs_of_blocks
+    world, rank, dev = env.world, env.rank, env.dev
+    N, n = args.full_rows, args.full_samples
+    opts = Options()
+    seed = args.seed + 99
+    t = None
+    t_gen0 = time.time()
+    if rank == 0:
+        t = synth.make_table(N, n, seed=seed)
+        hits, _, _ = synth.make_permutation_hits(t, 500, args.full_perms, window=10000, seed=seed + 17)
+        ga, gb = synth.global_pair_indices(t.names, 200000, seed=seed + 5)
+        uniq, chrom_id = np.unique(np.asarray(t.chrom), return_inverse=True)
+        order = np.argsort(np.asarray(t.names), kind="stable")
+        name_rank = np.empty(N, dtype=np.int32); name_rank[order] = np.arange(N, dtype=np.int32)
+        feats = [chrom_id.astype(np.int32), t.start.astype(np.int64), t.end.astype(np.int64), name_rank]
+        X_pin = torch.from_numpy(t.X).pin_memory()
+    env.log(f"full-shape inputs made in {time.time() - t_gen0:.1f} s")
+    X_dev = torch.empty((N, n), dtype=torch.float64, device=dev)
+    if rank == 0:
+        X_dev.copy_(X_pin)
+    if world > 1:
+        dist.broadcast(X_dev, src=0)
+        box = [None]
+        if rank == 0:
+            box = [(hits, ga, gb, feats)]
+        dist.broadcast_object_list(box, src=0)
+        hits, ga, gb, feats = box[0]
+    torch.cuda.synchronize()
+
+    ctx = CoexContext(env.local)
+    ctx.set_expression_device(X_dev.data_ptr(), N, n, keepalive=X_dev)
+    ctx.prepare()
+    ctx.set_features_raw(*feats)
+    g = ctx.pairs(ga, gb, ranked=True)
+    glist = np.sort(np.where(np.isnan(g), -99.0, g))
+    ctx.set_global_list(glist)
+    Kall = len(hits)
+    shards = shard_permutations([len(h) for h in hits], world)
+    mine = shards[rank]
+    job = DeviceJob(env, ctx, [hits[k] for k in mine])
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=dev)
+
+    def step():
+        ctx.set_expression_device(X_dev.data_ptr(), N, n, keepalive=X_dev)
+        ctx.prepare()
+        job.run(opts)
+
+    step()                                                   # warm-up (allocations, tensor maps)
+    env.barrier()
+    sampler = ClockSampler(env.local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.2)
+    env.barrier()
+    stage_tot = {s: 0.0 for s in STAGES}
+    stage_launch = {s: 0 for s in STAGES}
+    ms = []
+    t_w0 = time.time()
+    for _ in range(args.full_steps):
+        env.flush.fill_(1)
+        env.barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+        st = ctx.stage_ms()
+        for s in STAGES:
+            stage_tot[s] += st[s][0]; stage_launch[s] += st[s][1]
+    t_w1 = time.time()
+    clocks = sampler.stop(t_w0, t_w1) if rank == 0 else None
+    dev_ms = env.max_over_ranks(float(np.mean(ms)))
+    env.log(f"full shape: {dev_ms:.1f} ms per job")
+    w0 = time.perf_counter()
+    dens_mine = job.densities()
+    allden = gather_densities(mine, dens_mine, Kall, device=dev)
+    gather_ms = env.max_over_ranks(1e3 * (time.perf_counter() - w0))
+    U_mine = int(np.unique(job.hit_rows).size)
+    U_sum = env.sum_over_ranks(U_mine)
+    per = {s: (stage_tot[s] / args.full_steps, stage_launch[s] / args.full_steps) for s in STAGES}
+
+    # ---- e2e through the host-buffer API (one GPU only: pinned table of 2.9 GB + host hit lists) ---------------
+    e2e = None
+    if world == 1:
+        Xh = X_pin.numpy()
+        w = []
+        for i in range(2):
+            torch.cuda.synchronize()
+            a0 = time.perf_counter()
+            ctx.set_expression(Xh)
+            ctx.prepare()
+            res_e = ctx.network_batch(hits, opts)
+            a1 = time.perf_counter()
+            w.append(1e3 * (a1 - a0))
+        e2e = {"ms": w[-1], "permutations_per_sec": Kall / (w[-1] * 1e-3), "h2d_bytes": int(Xh.nbytes + job.hit_rows.nbytes),
+               "d2h_bytes": int(4 * Kall + 28 * job.H)}
+        ctx.set_expression_device(X_dev.data_ptr(), N, n, keepalive=X_dev)
+        ctx.prepare()
+
+    # ---- parity at this shape --------------------------------------------------------------------------------------
+    parity = {"ok": True}
+    bad, first = ctx.selftest_gemm(512)                      # tcgen05 strip == dp4a strip, exact integers, on the device
+    parity["tcgen05_vs_dp4a_mismatches_512_rows"] = int(bad)
+    parity["ok"] &= bad == 0
+    # the first sets of this rank alone (with bisect indices) against the same sets inside the big batch
+    nchk = min(3, len(mine))
+    res_s = ctx.network_batch([hits[k] for k in mine[:nchk]], opts, want_scores=True, want_counts=True)
+    alone = all(np.array_equal(res_s.perm(j)["density"], dens_mine[j]) for j in range(nchk))
+    parity["sets_alone_equal_sets_in_batch"] = bool(alone)
+    parity["ok"] &= bool(alone)
+    if world > 1:
+        okg = True
+        for j, k in enumerate(mine):
+            okg &= allden[k] is not None and np.array_equal(allden[k], dens_mine[j])
+        okg = env.max_over_ranks(0.0 if okg else 1.0) == 0.0
+        parity["gathered_equals_local"] = bool(okg)
+        parity["ok"] &= bool(okg)
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import network_oracle as no
+        # sampled oracle check: ranks of 512 random rows against scipy, then whole queries (one hit against ALL rows)
+        Rk = ctx.ranks()
+        rng = np.random.default_rng(5)
+        rows = rng.choice(N, size=512, replace=False)
+        ranks_ok = bool(np.array_equal(Rk[rows], no.rank_rows(t.X[rows])))
+        parity["ranks_equal_scipy_512_rows"] = ranks_ok
+        k0 = mine[1] if len(mine) > 1 else mine[0]
+        j0 = mine.index(k0)
+        h = hits[k0]
+        qs = sorted(set(int(x) for x in rng.choice(len(h), size=min(3, len(h)), replace=False)))
+        idx_ok = True
+        sc_err = 0.0
+        c0 = time.perf_counter()
+        npairs_cpu = 0
+        if j0 < nchk:
+            for i in qs:
+                cnt, sc = no.query_counts(t.X, Rk, h, i)
+                npairs_cpu += N - 1 + len(h) - 1
+                idx_ok &= bool(np.array_equal(res_s.count_matrix(j0)[i], cnt))
+                sc_err = max(sc_err, float(np.max(np.abs(res_s.score_matrix(j0)[i] - sc))))
+        cpu_s = time.perf_counter() - c0
+        parity["oracle_queries_checked"] = len(qs) if j0 < nchk else 0
+        parity["oracle_bisect_indices_equal"] = bool(idx_ok)
+        parity["oracle_max_abs_score_err"] = sc_err
+        parity["ok"] &= ranks_ok and idx_ok and sc_err <= 1e-6
+        # CPU baseline EXTRAPOLATED from the measured host rate of the reference C file on this table
+        pps = npairs_cpu / cpu_s if cpu_s > 0 and npairs_cpu else None
+        if pps:
+            mean_hits = float(np.mean([len(x) for x in hits]))
+            cpu = {"kind": no.default_kind(), "cores": no.num_threads(), "pairs_per_sec": pps,
+                   "extrapolated": True,
+                   "permutations_per_sec": 1.0 / (mean_hits * (N - 1) / pps),
+                   "sample": f"{npairs_cpu} pairs of getPearson on this table ({len(qs)} whole queries); one permutation = "
+                             f"{mean_hits:.0f} x {N - 1} pairs at that rate, rank transform / sorts / statistics NOT counted "
+                             "(an upper bound of the reference's speed)"}
+        del Rk
+    flag = env.max_over_ranks(0.0 if parity["ok"] else 1.0) == 0.0
+    parity["ok"] = bool(flag)
+
+    # ---- C3: all unordered pairs on the resident table ------------------------------------------------------------
+    allp = None
+    try:
+        allp = allpairs(env, ctx, N, n, cpu)
+    except Exception as e:
+        allp = {"ok": False, "error": f"{type(e).__name__}: {e}"}
+
+    full = None
+    if rank == 0:
+        mean_hits = float(np.mean([len(x) for x in hits]))
+        pairs_ref = float(sum(len(x) * (N - 1) for x in hits))
+        gemm_flops = 2.0 * n * U_mine * N                   # rank 0's strips (the stage times are rank 0's too)
+        count_bytes = 4.0 * U_mine * N + 8.0 * float(np.sum(np.diff(job.perm_off) ** 2))
+        roof = {}
+        if per["corr_gemm"][0] > 0:
+            a = gemm_flops / (per["corr_gemm"][0] * 1e-3) / 1e12
+            roof["corr_gemm"] = {"bound": "tensor", "achieved": a, "peak": env.tc_sustained, "unit": "TFLOP/s", "frac": a / env.tc_sustained,
+                                 "peak_kind": "sustained bf16 (kernel timed inside a long step)", "frac_of_burst": a / env.tc_peak,
+                                 "ms": per["corr_gemm"][0], "launches": per["corr_gemm"][1]}
+        if per["count_score"][0] > 0:
+            a = count_bytes / (per["count_score"][0] * 1e-3) / 1e9
+            roof["count_score"] = {"bound": "hbm", "achieved": a, "peak": env.hbm_peak, "unit": "GB/s", "frac": a / env.hbm_peak,
+                                   "ms": per["count_score"][0], "launches": per["count_score"][1]}
+        if per["rank_pack"][0] > 0:
+            a = float(N) * n * 12 / (per["rank_pack"][0] * 1e-3) / 1e9
+            roof["rank_pack"] = {"bound": "hbm", "achieved": a, "peak": env.hbm_peak, "unit": "GB/s", "frac": a / env.hbm_peak,
+                                 "ms": per["rank_pack"][0]}
+        if per["rowstats"][0] > 0:
+            a = float(N) * n * 16 / (per["rowstats"][0] * 1e-3) / 1e9
+            roof["rowstats"] = {"bound": "hbm", "achieved": a, "peak": env.hbm_peak, "unit": "GB/s", "frac": a / env.hbm_peak,
+                                "ms": per["rowstats"][0]}
+        full = {
+            "workload": f"north-star target: {N} x {n} synthetic table, {Kall} hit sets (real + {Kall - 1} circular permutations of 500 loci, "
+                        f"-w 10000, mean {mean_hits:.0f} hit regions), Spearman, defaults; "
+                        + ("one GPU" if world == 1 else f"ONE job sharded over {world} GPUs by dist.shard_permutations (strong scaling)"),
+            "n_gpus": world, "steps": args.full_steps, "warmup": 1,
+            "ms": dev_ms, "permutations_per_sec": Kall / (dev_ms * 1e-3),
+            "pairs_per_sec_reference_equivalent": pairs_ref / (dev_ms * 1e-3),
+            "pairs_per_sec_contracted": U_sum * N / (dev_ms * 1e-3),
+            "unique_hit_rows_summed_over_ranks": int(U_sum),
+            "stage_ms_rank0": {s: per[s][0] for s in STAGES},
+            "roofline_all": roof,
+            "gather_ms_host_clock": gather_ms,
+            "e2e": e2e,
+            "clocks": clocks,
+            "parity": parity,
+            "cpu_baseline": cpu,
+        }
+    ctx.close()
+    return full, allp
+
+
+def allpairs(env, ctx, N, n, cpu):
+    """Config C3: histogram of r over all N (N - 1) / 2 unordered pairs; row blocks dealt to the ranks, one all-reduce."""
+    torch, dist = env.torch, env.dist
+    from coexpression_b200.dist import shard_row_blocks, pairs_of_blocks
+    nbins = 1 << 20
+    out = {"workload": f"C3: all unordered pairs of the {N} x {n} table reduced on the device to a histogram of r over {nbins} bins",
+           "n_gpus": env.world, "ok": True}
+    mine = shard_row_blocks(N, env.world, 4096)[env.rank]
+    pairs_all = N * (N - 1) // 2
+    for name, ranked in (("spearman", True), ("pearson", False)):
+        ctx.set_workspace_mb(2048)
+        ctx.set_pearson(4, "tensor")
+        ctx.allpairs_histogram(ranked, mine[0][0], mine[0][1], nbins)          # warm-up (packing, tensor maps)
+        env.barrier()
+        acc = torch.zeros(nbins + 1, dtype=torch.int64, device=env.dev)
+        dev_ms = 0.0
+        t0 = time.perf_counter()
+        for i, (r0, r1) in enumerate(mine):
+            ctx.allpairs_accumulate(ranked, r0, r1, nbins, reset=(i == 0))
+            st = ctx.stage_ms()
+            dev_ms += st["corr_gemm"][0] + st["count_score"][0]
+        ctx.allpairs_read(nbins, device_ptr=acc.data_ptr(), host=False)
+        if env.world > 1:
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+        h = acc.cpu().numpy()
+        torch.cuda.synchronize()
+        wall = env.max_over_ranks(time.perf_counter() - t0)
+        dev_s = env.max_over_ranks(dev_ms * 1e-3)
+        tot, nan_tot = h[:-1].view(np.uint64), int(h[-1])
+        complete = int(tot.sum()) + nan_tot == pairs_all
+        # checksum of the histogram: sum of bin index x count (identical for any sharding of the row blocks)
+        chk = int((np.arange(nbins, dtype=np.uint64) * tot).sum() % (1 << 61))
+        out[name] = {"wall_s": wall, "device_s": dev_s, "pairs_per_sec": pairs_all / wall,
+                     "algorithmic_tflops_device": 2.0 * n * pairs_all / dev_s / 1e12,
+                     "frac_of_bf16_sustained_all_gpus": 2.0 * n * pairs_all / dev_s / 1e12 / (env.world * env.tc_sustained),
+                     "hist_plus_nan_equals_all_pairs": bool(complete), "nan_pairs": nan_tot, "histogram_checksum": chk}
+        out["ok"] &= bool(complete)
+    ctx.set_workspace_mb(4096)
+    if cpu and cpu.get("pairs_per_sec"):
+        out["cpu_baseline"] = {"kind": cpu["kind"], "cores": cpu["cores"], "pairs_per_sec": cpu["pairs_per_sec"], "extrapolated": True,
+                               "all_pairs_seconds": pairs_all / cpu["pairs_per_sec"],
+                               "note": "the reference has no all-pairs entry point (getPearson takes at most 2^31 pairs per call); "
+                                       "time = N (N - 1) / 2 pairs at the host rate measured above"}
+    return out
 
 
 if __name__ == "__main__":

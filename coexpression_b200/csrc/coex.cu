@@ -483,7 +483,9 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
             Hs = std::min<long long>(Hs, round_up(H, 256));
             // -cm Pearson on the tensor cores: de-duplicated like Spearman, the tensor r is a filter and the reference's
             // in-order arithmetic decides every value it cannot (count mode 1 / pearson mode 1 keep the exact strip)
-            const bool pearson_dedup = (prm->measure == 1 && c->count_mode != 1 && c->pearson_mode == 0);
+            // (rows of more than 1860 samples: the int32 Spearman strip the de-duplicated path reads its statistics from could
+            //  overflow, so such tables take the exact strip + stat_rank_kernel, whose sums are 64-bit)
+            const bool pearson_dedup = (prm->measure == 1 && c->count_mode != 1 && c->pearson_mode == 0 && c->n <= 1860);
             if (prm->measure == 0) {
                 if (c->count_mode == 1) {
                     COEX_TRY(c->strip.reserve((size_t)Hs * ld));
@@ -650,7 +652,7 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
             COEX_CUDA(cudaStreamSynchronize(st));
         }
     }
-    if (prm->use_specific_p && c->gemm_mode == 0) COEX_TRY(tc_check_error(c));
+    if (prm->use_specific_p && (c->gemm_mode == 0 || prm->measure == 1)) COEX_TRY(tc_check_error(c));   // (-cm Pearson runs the tcgen05 digit GEMM in every gemm mode)
     return 0;
 }
 

@@ -26,6 +26,13 @@ from .results import perm_objects
 
 def options_from_settings(st):
     """settings.txt keys read at 1-make-network.py:35-49 (values arrive as floats / bools, Q9)."""
+    seed = st.get("seedfile", "none")
+    if isinstance(seed, str) and seed != "none" and os.path.exists(seed):      # the reference's own test, 1-make-network.py:85-86
+        # the "obselete" -seed feature (1-make-network.py:82-97, 169-171, 484-505) adds the seed promoters to snp_map and
+        # prunes them after the densities: it is out of scope here (SURVEY.md section 2 row 21), and silently ignoring it
+        # would write different perm_results_store objects than the reference does
+        raise NotImplementedError("settings.txt names a seedfile (%r): seed-promoter pruning (reference 1-make-network.py:"
+                                  "82-97,484-505) is not supported by the B200 drop-in; rerun 0-prepare without -seed" % (seed,))
     return Options(
         correlationmeasure=st.get("correlationmeasure", "Spearman"),
         anticorrelation=bool(st.get("anticorrelation", False)),

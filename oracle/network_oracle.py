@@ -474,6 +474,37 @@ def make_network(names, X, promoters, addresses, globalcorrelationlist,
     return out
 
 
+def query_counts(X, Xrank, hit_rows, i, kind=None, anticorrelation=False):
+    """ONE hit of one permutation: row i of the bisect-index matrix and of `individualscores`
+    (1-make-network.py:208-258 and :273-327 restricted to hit position i, Spearman, nsp = 1,
+    consistent mode).  make_network above does exactly this for every i; this entry exists so that
+    a SAMPLE of queries can be checked at shapes where a whole permutation is too slow on the CPU
+    (bench.py, full FANTOM5 shape).  X: raw table (only the rows of the hits are read: raw-sum
+    guard of coexfunctions.py:389), Xrank: ranked table.  -> (counts [P] int64, -1 where the
+    statistic is -99 or j == i; scores [P] float64, 0 at j == i)."""
+    hit_rows = np.asarray(hit_rows, dtype=np.int32)
+    N, P = Xrank.shape[0], len(hit_rows)
+    u = int(hit_rows[i])
+    cols = np.arange(N, dtype=np.int32)
+    keep = cols != i                                                      # Q1: the INDEX i, not the row u
+    r = get_pearson(Xrank, np.full(int(keep.sum()), u, dtype=np.int32), cols[keep], kind)
+    lst = np.sort(np.where(np.isnan(r), -99.0, r))                        # :240-258
+    pos = np.array([py2_sum(X[int(h)].tolist()) > 0 for h in hit_rows], dtype=bool)
+    counts = np.full(P, -1, dtype=np.int64)
+    scores = np.zeros(P)
+    others = np.array([j for j in range(P) if j != i], dtype=np.int64)
+    t = get_pearson(Xrank, np.full(len(others), u, dtype=np.int32), hit_rows[others], kind) if len(others) else np.empty(0)
+    for j, c in zip(others, t):
+        c = -99.0 if (np.isnan(c) or not (pos[i] and pos[j])) else float(c)
+        if c == -99:
+            scores[j] = -math.log(1, 10)
+        else:
+            idx = int(np.searchsorted(lst, c, side="left"))
+            counts[j] = idx
+            scores[j] = edge_score(idx, len(lst), anticorrelation)
+    return counts, scores
+
+
 # --------------------------------------------------------------------------------------
 # A14  pooled null, empirical p, FDR (2-collate-results.py:67-76,142,161-163)
 # --------------------------------------------------------------------------------------

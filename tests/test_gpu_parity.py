@@ -662,3 +662,102 @@ def test_large_hit_set_shared_memory_limits():
         assert np.array_equal(a.scores, b.scores), other
         assert np.array_equal(a.n_groups, b.n_groups) and np.array_equal(a.group_of_hit, b.group_of_hit)
         assert np.array_equal(a.group_winner, b.group_winner) and np.array_equal(a.group_density, b.group_density)
+
+
+# ---------------------------------------------------------------------------------------------
+# Round 2: the timed configurations themselves against the oracle
+# ---------------------------------------------------------------------------------------------
+def _oracle_vs_gpu(t, hits, opts, glist, R, ctx, **okw):
+    from coexpression_b200.results import perm_objects
+    from oracle import network_oracle as no
+    res = ctx.network_batch(hits, opts, want_scores=True, want_counts=True)
+    addresses = t.addresses()
+    worst = 0.0
+    for k, h in enumerate(hits):
+        want = no.make_network(t.names, t.X, [t.names[r] for r in h], addresses, glist.tolist(), Xrank=R, return_counts=True,
+                               anticorrelation=opts.anticorrelation, pval_to_join=opts.pval_to_join,
+                               correlationmeasure=opts.correlationmeasure, **okw)
+        got = perm_objects(res, k, t.names)
+        assert got["prom_to_join"] == want["prom_to_join"], k
+        assert got["winners"] == want["winners"], k
+        if len(h) > 1:
+            assert np.array_equal(res.count_matrix(k), want["_counts"]), k
+        assert set(got["indmeasure"]) == set(want["indmeasure"])
+        for grp, v in want["indmeasure"].items():
+            worst = max(worst, abs(got["indmeasure"][grp] - v))
+        for p_, v in want["allpromoterscores"].items():
+            worst = max(worst, abs(got["allpromoterscores"][p_] - v))
+    assert worst <= 1e-6, worst                                # north_star tolerance
+    return res
+
+
+def test_network_at_1829_samples_default_gemm_against_oracle():
+    """The FANTOM5 row length through the kernels the full-shape run uses (n >= 1024 -> gemm_i8_tc_persistent128_kernel,
+    count_dedup float filter at sigma = 1 / sqrt(1829)): 3000 x 1829 table, 3 hit sets, every bisect index vs the oracle."""
+    from coexpression_b200 import synth
+    from coexpression_b200.api import CoexContext, Options
+    from oracle import network_oracle as no
+    t = synth.make_table(3000, 1829, seed=1829)
+    hits, _, _ = synth.make_permutation_hits(t, 120, 2, window=9000, seed=18)
+    assert min(len(h) for h in hits) > 20
+    R = no.rank_rows(t.X)
+    ga, gb = synth.global_pair_indices(t.names, 60000, seed=29)
+    g = no.get_pearson(R, ga, gb)
+    glist = np.sort(np.where(np.isnan(g), -99.0, g))
+    for opts in (Options(), Options(anticorrelation=True)):
+        with CoexContext() as ctx:
+            ctx.set_expression(t.X); ctx.prepare()
+            assert np.array_equal(ctx.ranks(), R)
+            ctx.set_features(t.chrom, t.start, t.end, t.names)
+            ctx.set_global_list(glist)
+            _oracle_vs_gpu(t, hits, opts, glist, R, ctx)
+
+
+def test_bench_c2_inputs_two_hit_sets_against_oracle():
+    """bench.py's own default workload (20000 x 256, seed 1234, 500 loci, -w 10000): the real set and one permuted set
+    against the oracle, alone and inside the 101-set batch the benchmark times (de-duplication regime)."""
+    import argparse
+    import bench
+    from coexpression_b200.api import CoexContext, Options
+    from oracle import network_oracle as no
+    args = argparse.Namespace(shape="minimal", rows=0, samples=0, loci=500, perms=100, window=10000, seed=1234)
+    t, hits, ga, gb = bench.workload(args, 0)
+    assert len(hits) == 101 and len(hits[0]) > 1000
+    R = no.rank_rows(t.X)
+    with CoexContext() as ctx:
+        ctx.set_expression(t.X); ctx.prepare()
+        ctx.set_features(t.chrom, t.start, t.end, t.names)
+        g = ctx.pairs(ga, gb, ranked=True)
+        assert _same_doubles(g, no.get_pearson(R, ga, gb))
+        glist = np.sort(np.where(np.isnan(g), -99.0, g))
+        ctx.set_global_list(glist)
+        small = _oracle_vs_gpu(t, [hits[0], hits[1]], Options(), glist, R, ctx)
+        big = ctx.network_batch(hits, Options(), want_scores=False, want_counts=True)
+    for k in (0, 1):
+        assert np.array_equal(big.count_matrix(k), small.count_matrix(k))
+        assert np.array_equal(big.perm(k)["density"], small.perm(k)["density"])       # bit for bit, whatever the batch
+        assert np.array_equal(big.perm(k)["winner"], small.perm(k)["winner"])
+
+
+def test_pearson_null_more_than_1860_samples_takes_the_exact_strip():
+    """with -cm Pearson the de-duplicated path reads its (Spearman, quirk Q2) statistics from the int32 strip,
+    which overflows for rows of more than 1860 samples; such tables must take the 64-bit statistic kernel."""
+    from coexpression_b200 import synth
+    from coexpression_b200.api import CoexContext, Options
+    from coexpression_b200._lib import CoexError
+    from oracle import network_oracle as no
+    t = synth.make_table(700, 2100, seed=2100, zero_row_frac=0.01)
+    # strongly correlated rows: |S_ab| exceeds 2^31 for |r| > 0.7 at n = 2100
+    t.X[10] = t.X[11] * 3.0 + 0.01
+    hits = [np.array([10, 11, 40, 41, 300, 301, 302, 650], dtype=np.int32), np.arange(5, 60, 3, dtype=np.int32)]
+    R = no.rank_rows(t.X)
+    ga, gb = synth.global_pair_indices(t.names, 20000, seed=3)
+    g = no.get_pearson(t.X, ga, gb)
+    glist = np.sort(np.where(np.isnan(g), -99.0, g))
+    with CoexContext() as ctx:
+        ctx.set_expression(t.X); ctx.prepare()
+        ctx.set_features(t.chrom, t.start, t.end, t.names)
+        ctx.set_global_list(glist)
+        _oracle_vs_gpu(t, hits, Options(correlationmeasure="Pearson"), glist, R, ctx)
+        with pytest.raises(CoexError):                          # Spearman null: refused loudly, never wrong silently
+            ctx.network_batch(hits, Options())

@@ -217,3 +217,25 @@ def test_faithful_vs_consistent_is_a_reference_property():
     moved = a["_counts"] != b["_counts"]
     assert not np.any(moved & (a["_stat"] == b["_stat"]))
     assert 0 < moved.mean() < 0.6
+
+
+def test_query_counts_is_one_row_of_make_network():
+    """oracle.query_counts (the sampled check of bench.py at the full FANTOM5 shape) == row i of make_network's
+    bisect-index matrix and of individualscores, including -99 statistics (all-zero hit row) and quirk Q1."""
+    from coexpression_b200 import synth
+    t = synth.make_table(600, 48, seed=3)
+    hits, _, _ = synth.make_permutation_hits(t, 40, 1, window=8000, seed=4)
+    zero = int(np.flatnonzero(t.X.sum(axis=1) == 0)[0])
+    h = np.concatenate([hits[1], [zero]]).astype(np.int32)
+    R = no.rank_rows(t.X)
+    ga, gb = synth.global_pair_indices(t.names, 5000, seed=2)
+    g = no.get_pearson(R, ga, gb)
+    gl = np.sort(np.where(np.isnan(g), -99.0, g)).tolist()
+    for anticor in (False, True):
+        w = no.make_network(t.names, t.X, [t.names[r] for r in h], t.addresses(), gl, Xrank=R, return_counts=True,
+                            anticorrelation=anticor)
+        for i in range(len(h)):
+            c, s = no.query_counts(t.X, R, h, i, anticorrelation=anticor)
+            assert np.array_equal(c, w["_counts"][i])
+            want = np.array([0.0 if j == i else w["individualscores"][t.names[h[i]]][t.names[h[j]]] for j in range(len(h))])
+            assert np.array_equal(s, want)
