@@ -46,11 +46,12 @@ SIGNATURES = {
     "coex_prepare": (ctypes.c_int, [ctypes.c_void_p]),
     "coex_get_ranks": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "coex_set_features": (ctypes.c_int, [ctypes.c_void_p] * 5 + [c_ll]),
+    "coex_set_feature_order": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_ll]),
     "coex_set_global_list": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_ll]),
     "coex_permute_map": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, c_ll, c_ll,
-                                        ctypes.c_void_p, ctypes.c_void_p, c_ll, ctypes.c_int]),
+                                        ctypes.c_void_p, ctypes.c_void_p, c_ll, ctypes.c_int, ctypes.c_void_p]),
     "coex_pairs": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, c_ll,
                                   ctypes.c_void_p, ctypes.c_int]),
     "coex_allpairs_histogram": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_ll, c_ll, ctypes.c_int,

@@ -148,7 +148,7 @@ class CoexContext:
                               np.asarray(end, dtype=np.int64), name_rank)
 
     def permute_map(self, mode, snp_chrom, snp_addr, shifts, chromlist, chromrange, window, background=None,
-                    capacity=None, picks=None):
+                    capacity=None, picks=None, with_loci=False):
         """Row N1: the promoters of K permuted locus sets in one call (reference 0-prepare-coex.py:471-613 + windowBed).
         snp_chrom: chromosome names of the real loci, snp_addr their addresses; shifts[k] == 0 is the real data;
         chromlist / chromrange as built at 0-prepare-coex.py:319-330.  mode 'backcirc' needs `background` = the
@@ -156,7 +156,8 @@ class CoexContext:
         every real locus.  mode 'background' (0-prepare-coex.py:564-578): `background` = (chrom, address) of every line
         of the background file in file order (column 0, column 2) and `picks[k]` = the M line numbers
         `random.sample(range(len(background)), M)` drew for set k (ignored where shifts[k] == 0).
-        -> list of K int32 arrays of table rows (first-appearance order)."""
+        -> list of K int32 arrays of table rows (first-appearance order); with_loci: also a list of K int32 [P, 2] arrays
+        holding, per hit, the first and the last locus (input order) that map to it."""
         if self._feature_chroms is None:
             raise _lib.CoexError("permute_map: call set_features first")
         cidx = {c: i for i, c in enumerate(chromlist)}
@@ -186,10 +187,14 @@ class CoexContext:
         off = np.zeros(K + 1, dtype=np.int64)
         rows = np.zeros(cap, dtype=np.int32)
         ptr = lambda x: x.ctypes.data if x is not None else None
+        loci = np.zeros(2 * cap, dtype=np.int32) if with_loci else None
         check(self.lib.coex_permute_map(self.h, m, ptr(sc), ptr(sa), ptr(sb), M, ptr(sh), K, ptr(cs), ptr(ce), ptr(cf),
-                                        len(chromlist), ptr(bc), ptr(ba), nb, int(window), ptr(off), ptr(rows), cap, 0),
+                                        len(chromlist), ptr(bc), ptr(ba), nb, int(window), ptr(off), ptr(rows), cap, 0, ptr(loci)),
               "coex_permute_map")
-        return [rows[off[k]:off[k + 1]].copy() for k in range(K)]
+        out = [rows[off[k]:off[k + 1]].copy() for k in range(K)]
+        if with_loci:
+            return out, [loci[2 * off[k]:2 * off[k + 1]].reshape(-1, 2).copy() for k in range(K)]
+        return out
 
     def set_features_raw(self, chrom_id, start, end, name_rank):
         chrom_id = np.ascontiguousarray(chrom_id, dtype=np.int32)
@@ -198,6 +203,13 @@ class CoexContext:
         name_rank = np.ascontiguousarray(name_rank, dtype=np.int32)
         check(self.lib.coex_set_features(self.h, chrom_id.ctypes.data, start.ctypes.data, end.ctypes.data,
                                          name_rank.ctypes.data, len(chrom_id)), "coex_set_features")
+
+    def set_feature_order(self, bed_index):
+        """bed_index[row] = line number of the row's feature in the feature BED (the B file of windowBed): `bedtools window`
+        reports the features of one locus by (UCSC-bin level, bin, line), which fixes the order of a permutation's promoters.
+        Default (after set_features): the BED lists the rows in table order."""
+        b = np.ascontiguousarray(bed_index, dtype=np.int32)
+        check(self.lib.coex_set_feature_order(self.h, b.ctypes.data, b.size), "coex_set_feature_order")
 
     def set_global_list(self, values):
         v = np.ascontiguousarray(values, dtype=np.float64)
@@ -307,7 +319,7 @@ class CoexContext:
               "coex_set_gemm_mode")
 
     def set_count_mode(self, mode):
-        check(self.lib.coex_set_count_mode(self.h, {"dedup": 0, "per_query": 1, "dedup_window": 2, "row_rank": 3, "dedup_split": 4}.get(mode, mode)), "coex_set_count_mode")
+        check(self.lib.coex_set_count_mode(self.h, {"dedup": 0, "per_query": 1, "row_rank": 3}.get(mode, mode)), "coex_set_count_mode")
 
     def set_workspace_mb(self, mb):
         check(self.lib.coex_set_workspace_mb(self.h, int(mb)), "coex_set_workspace_mb")

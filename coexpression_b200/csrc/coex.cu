@@ -8,11 +8,8 @@
 #include "gemm_tc.cuh"
 #include "count.cuh"
 #include "count_dedup.cuh"
-#include "count_rows.cuh"
-#include "count_split.cuh"
 #include "plan.cuh"
 #include "network.cuh"
-static_assert(coex::kPlanQcap == coex::kPlanQcapSplit, "stat_sort_kernel holds one item's queries in fixed shared arrays");
 #include "allpairs.cuh"
 #include "permute.cuh"
 
@@ -22,6 +19,35 @@ static_assert(coex::kPlanQcap == coex::kPlanQcapSplit, "stat_sort_kernel holds o
 
 namespace coex {
 thread_local std::string g_last_error;
+
+// `bedtools window` keeps the B file in the UCSC binning scheme (bedtools2 bedFile.h: _binFirstShift 14, _binNextShift 3, 7 levels;
+// getBin = the smallest bin that contains [start, end - 1]) and BedFile::allHits walks, for one A record, the levels from the finest
+// up, the bins of a level in ascending order and the records of a bin in B-FILE order.  For the B records overlapping one A record
+// that is the ascending order of (level, bin, line number in the B file): a global order of the features, whose rank per table
+// row is what permute_map_kernel sorts the promoters of a locus by (the order decides which null column quirk Q1 skips).
+static int upload_window_order(coex_ctx *c) {
+    const long long N = c->N;
+    std::vector<unsigned long long> k1((size_t)N);
+    for (long long i = 0; i < N; ++i) {
+        long long s = c->h_feat_start[(size_t)i] >> 14, e = (std::max(c->h_feat_end[(size_t)i], c->h_feat_start[(size_t)i] + 1) - 1) >> 14;
+        int level = 0;
+        while (level < 6 && s != e) { s >>= 3; e >>= 3; ++level; }
+        k1[(size_t)i] = ((unsigned long long)c->h_chrom_id[(size_t)i] << 40) | ((unsigned long long)level << 36) | (unsigned long long)s;
+    }
+    std::vector<int> order((size_t)N), rank((size_t)N);
+    for (long long i = 0; i < N; ++i) order[(size_t)i] = (int)i;
+    std::sort(order.begin(), order.end(), [&](int x, int y) {
+        if (k1[(size_t)x] != k1[(size_t)y]) return k1[(size_t)x] < k1[(size_t)y];
+        if (c->h_bed_index[(size_t)x] != c->h_bed_index[(size_t)y]) return c->h_bed_index[(size_t)x] < c->h_bed_index[(size_t)y];
+        return x < y;
+    });
+    for (long long r = 0; r < N; ++r) rank[(size_t)order[(size_t)r]] = (int)r;
+    COEX_TRY(c->feat_wrank.reserve(N)); COEX_TRY(c->feat_wrow.reserve(N));
+    COEX_CUDA(cudaMemcpyAsync(c->feat_wrank.p, rank.data(), N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    COEX_CUDA(cudaMemcpyAsync(c->feat_wrow.p, order.data(), N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    COEX_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
 
 static int check_ctx(coex_ctx *c) {
     if (!c) COEX_FAIL("null context");
@@ -96,14 +122,9 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     const bool pearson = (prm->measure == 1);
     const int D = c->pearson_digits;
     if (pearson) COEX_TRY(pearson_pack(c));
-    const bool rows_kernel = (c->count_mode == 2) && !pearson;
     bool rank_mode = (c->count_mode == 3) && !pearson;      // 3 = forced; count mode 0 decides below (cost model)
-    const int Tcap = rows_kernel ? std::max(4096, (int)round_up(Pmax, 512))
-                                 : std::max(kDdBuckets / 2, (int)round_up(Pmax, 256));   // 2*Tcap >= buckets: the bucket cursors alias thr32|hist
+    const int Tcap = std::max(kDdBuckets / 2, (int)round_up(Pmax, 256));   // 2*Tcap >= buckets: the bucket cursors alias thr32|hist
     const int Qcap = kPlanQcap;
-    // count mode 4: set-up phases (statistics + sort) of all work items of a strip in a kernel of their own, scores scattered by a
-    // third one (count_split.cuh) -- measured slower than the fused kernel at C2 (profiles/r01_count_split.md), kept as a cross-check
-    const bool split = !pearson && !rows_kernel && c->count_mode == 4 && Tcap <= 8192;
     {   // strips first (upper bound of the unique rows), so that the big buffers keep their place whatever the plan needs
         long long Us0 = (c->strip_mb << 20) / (c->N_pad * 4);
         Us0 = std::max<long long>(256, Us0 / 256 * 256);
@@ -161,45 +182,27 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     std::vector<long long> strip_item_begin((size_t)n_strips + 1);
     COEX_CUDA(cudaMemcpyAsync(strip_item_begin.data(), c->pl_bounds.p, ((size_t)n_strips + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
     c->launches += 7;
-    // hit-column bitmap (<= 32 KB: two CTAs per SM stay resident); Pearson null: a hit column's value is not its (Spearman) statistic
-    const int bm_words = (!pearson && N <= 262144) ? (int)((N + 31) / 32) : 0;
+    // hit-column bitmap (the hit columns' values ARE statistics: accounted exactly in phase C' and skipped by the streaming pass).  On a
+    // long table it would cost the second resident CTA (8 KB at 65536 rows) while the hit columns are a vanishing share of the row:
+    // there they take the ordinary route (flagged virtual bucket -> float tie with their own statistic -> exact refinement).
+    // Pearson null: a hit column's value is not its (Spearman) statistic.  Row-rank mode ranks EVERY column of a run, so it keeps the bitmap.
+    const int bm_words = (!pearson && N <= 65536) ? (int)((N + 31) / 32) : 0;
+    const int bm_words_rank = (!pearson && N <= 262144) ? (int)((N + 31) / 32) : 0;
     if (tdbg) fprintf(stderr, "[coex host] dedupe plan (device): %.0f us on the host incl. one sync (H=%lld U=%lld)\n", now_us() - t_start, H, U);
     const int claim = (bm_words > 0 && bm_words <= 2048) ? 1 : 0;      // <= 8 KB for the second bitmap
-    const size_t smem = rows_kernel ? rows_smem_bytes(Tcap, Qcap) : dedup_smem_bytes(Tcap, Qcap, bm_words, claim);
+    const size_t smem = dedup_smem_bytes(Tcap, Qcap, bm_words, claim);
     if (smem > 227 * 1024) COEX_FAIL("count kernel: too many statistics per query for shared memory");
     int per_sm = 1;
-    if (rows_kernel) {
-        COEX_CUDA(cudaFuncSetAttribute(count_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_rows_kernel, kCrThreads, smem));
+    if (pearson) {
+        COEX_CUDA(cudaFuncSetAttribute(count_dedup_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_dedup_kernel<1>, kDdThreads, smem));
     } else {
-        if (pearson) {
-            COEX_CUDA(cudaFuncSetAttribute(count_dedup_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_dedup_kernel<true>, kDdThreads, smem));
-        } else {
-            if (split) {
-                COEX_CUDA(cudaFuncSetAttribute(count_dedup_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_dedup_kernel<3>, kDdThreads, smem));
-            } else {
-            COEX_CUDA(cudaFuncSetAttribute(count_dedup_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_dedup_kernel<false>, kDdThreads, smem));
-            }
-        }
+        COEX_CUDA(cudaFuncSetAttribute(count_dedup_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_dedup_kernel<0>, kDdThreads, smem));
     }
     const int grid_max = std::max(1, per_sm) * c->sm_count;
-    const size_t ssmem = sort_smem_bytes(Tcap);
-    int sort_grid_max = 1;
-    if (split) {
-        int sper = 1;
-        COEX_CUDA(cudaFuncSetAttribute(stat_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
-        COEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sper, stat_sort_kernel, kSsThreads, ssmem));
-        sort_grid_max = std::max(1, sper) * c->sm_count;
-    }
-    unsigned long long st_cap = 0;
-    if (rows_kernel) {
-        COEX_TRY(c->dd_gthr.reserve((size_t)grid_max * Tcap));
-    } else if (!split) {
-        COEX_TRY(c->dd_gthr.reserve((size_t)grid_max * Tcap * 6));      // 3 x Tcap records of 16 bytes per CTA
-    }
+    COEX_TRY(c->dd_gthr.reserve((size_t)grid_max * Tcap * 6));      // 3 x Tcap records of 16 bytes per CTA
+    if (tdbg) fprintf(stderr, "[coex host] count kernel: %zu bytes of shared memory, %d CTA(s) per SM, Tcap %d, bitmap words %d\n", smem, per_sm, Tcap, bm_words);
     COEX_TRY(c->dd_tab.reserve((size_t)N + 1));
     score_table_kernel<<<(unsigned)((N + 256) / 256), 256, 0, st>>>(c->dd_tab.p, N, prm->anticorrelation);
     COEX_CUDA(cudaGetLastError());
@@ -222,23 +225,14 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
             const long long SCtot = c_sc_total;
             const double cost_items = (double)strip_item_begin[(size_t)n_strips] * (double)N;
             const double cost_rank = (double)U * (double)((N + kRankTcap - 1) / kRankTcap) * (double)N + 2.0 * (double)SCtot;
-            if (c->count_mode == 0 && !pearson && bm_words > 0 && cost_rank < 0.6 * cost_items) rank_mode = true;
-            if (rank_mode && bm_words == 0) COEX_FAIL("rank mode needs the hit-column bitmap (table of at most 262144 rows)");
+            if (c->count_mode == 0 && !pearson && bm_words_rank > 0 && cost_rank < 0.6 * cost_items) rank_mode = true;
+            if (rank_mode && bm_words_rank == 0) COEX_FAIL("rank mode needs the hit-column bitmap (table of at most 262144 rows)");
             if (tdbg) fprintf(stderr, "[coex host] count: %lld items, cost items %.3g vs rank %.3g -> %s\n", strip_item_begin[(size_t)n_strips],
                               cost_items, cost_rank, rank_mode ? "rank mode" : "query items");
-            if (split && !rank_mode) {
-                // every statistic belongs to exactly one item (sum over the strips <= sum P^2) and an item holds at most Tcap
-                long long max_items = 1;
-                for (int s = 0; s < n_strips; ++s) max_items = std::max(max_items, strip_item_begin[(size_t)s + 1] - strip_item_begin[(size_t)s]);
-                st_cap = (unsigned long long)std::max<long long>(1, std::min<long long>(SCtot, max_items * (long long)Tcap));
-                COEX_TRY(c->st_thr.reserve(2 * st_cap)); COEX_TRY(c->st_w.reserve(st_cap));
-                COEX_TRY(c->st_cnt.reserve(st_cap)); COEX_TRY(c->st_cursor.reserve(1));
-                COEX_TRY(c->st_itemoff.reserve((size_t)max_items)); COEX_TRY(c->st_itemT.reserve((size_t)max_items));
-            }
         }
         if (rank_mode) {
-            const int rclaim = (bm_words <= 2048) ? 1 : 0;
-            const size_t rsmem = dedup_smem_bytes(kRankTcap, Qcap, bm_words, rclaim);
+            const int rclaim = (bm_words_rank <= 2048) ? 1 : 0;
+            const size_t rsmem = dedup_smem_bytes(kRankTcap, Qcap, bm_words_rank, rclaim);
             if (s_idx == 0) {
                 COEX_CUDA(cudaFuncSetAttribute(count_dedup_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
                 int rper = 1;
@@ -253,7 +247,7 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
             da.uniq_rows = c->dd_uniq.p + u0; da.qlist = c->dd_qlist.p; da.q_perm = c->dd_qperm.p; da.perm_off = c->d_perm_off.p; da.sc_off = c->d_sc_off.p;
             da.K = K; da.hit_rows = d_hits; da.sx = c->sx.p; da.sxg = c->sxg.p; da.icol = c->icol.p; da.rawsum_pos = c->rawsum_pos.p; da.N = N;
             da.n_degenerate = c->d_ndeg.p; da.anticor = prm->anticorrelation; da.scores = d_sc; da.counts = d_cn;
-            da.Tcap = kRankTcap; da.Qcap = Qcap; da.bm_words = bm_words; da.claim = rclaim;
+            da.Tcap = kRankTcap; da.Qcap = Qcap; da.bm_words = bm_words_rank; da.claim = rclaim;
             da.R = std::min(1.0, std::max(0.05, 8.0 / std::sqrt((double)std::max(c->n, 2)))); da.g_rec = reinterpret_cast<StatRec *>(c->dd_gthr.p);
             da.score_tab = c->dd_tab.p; da.phase_clk = nullptr; da.rank_out = c->rank_strip.p;
             COEX_TRY(stage_begin(c, ST_COUNT));
@@ -273,31 +267,8 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
         const int n_items_s = (int)(strip_item_begin[s_idx + 1] - strip_item_begin[s_idx]);
         const int grid = std::min(grid_max, std::max(n_items_s, 1));
         const double R = std::min(1.0, std::max(0.05, 8.0 / std::sqrt((double)std::max(c->n, 2))));
-        if (split) {
-            COEX_TRY(stage_begin(c, ST_STATSORT));
-            COEX_CUDA(cudaMemsetAsync(c->st_cursor.p, 0, sizeof(unsigned long long), st));
-            SortArgs sa{};
-            sa.strip = c->strip.p; sa.ld = ld; sa.items = items_s; sa.n_items = n_items_s; sa.uniq_rows = c->dd_uniq.p + u0;
-            sa.qlist = c->dd_qlist.p; sa.q_perm = c->dd_qperm.p; sa.perm_off = c->d_perm_off.p; sa.sc_off = c->d_sc_off.p;
-            sa.hit_rows = d_hits; sa.sx = c->sx.p; sa.sxg = c->sxg.p; sa.rawsum_pos = c->rawsum_pos.p; sa.N = N; sa.scores = d_sc; sa.counts = d_cn;
-            sa.Tcap = Tcap; sa.bscale = (float)((double)kDdBuckets / (2.0 * R));
-            sa.st_rec = reinterpret_cast<StatRec *>(c->st_thr.p); sa.st_w = c->st_w.p; sa.st_cap = st_cap; sa.st_cursor = c->st_cursor.p;
-            sa.err = c->pl_err.p; sa.item_soff = c->st_itemoff.p; sa.item_T = c->st_itemT.p;
-            sa.phase_clk = dbg ? phase.p + 8 : nullptr;
-            stat_sort_kernel<<<std::min(sort_grid_max, std::max(n_items_s, 1)), kSsThreads, ssmem, st>>>(sa);
-            COEX_KCHECK(st);
-            COEX_TRY(stage_end(c, 1));
-        }
         COEX_TRY(stage_begin(c, ST_COUNT));
-        if (rows_kernel) {
-            RowCountArgs ra{};
-            ra.strip = c->strip.p; ra.ld = ld; ra.items = items_s; ra.n_items = n_items_s; ra.uniq_rows = c->dd_uniq.p + u0;
-            ra.qlist = c->dd_qlist.p; ra.q_perm = c->dd_qperm.p; ra.perm_off = c->d_perm_off.p; ra.sc_off = c->d_sc_off.p;
-            ra.hit_rows = d_hits; ra.sx = c->sx.p; ra.icol = c->icol.p; ra.rawsum_pos = c->rawsum_pos.p; ra.N = N;
-            ra.n_degenerate = c->d_ndeg.p; ra.anticor = prm->anticorrelation; ra.scores = d_sc; ra.counts = d_cn; ra.Tcap = Tcap; ra.Qcap = Qcap;
-            ra.g_t64 = c->dd_gthr.p; ra.score_tab = c->dd_tab.p; ra.phase_clk = dbg ? phase.p : nullptr;
-            count_rows_kernel<<<grid, kCrThreads, smem, st>>>(ra);
-        } else {
+        {
             DedupArgs da{};
             da.strip = c->strip.p; da.ld = ld; da.items = items_s; da.n_items = n_items_s;
             da.uniq_rows = c->dd_uniq.p + u0; da.qlist = c->dd_qlist.p; da.q_perm = c->dd_qperm.p;
@@ -312,17 +283,7 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
                 COEX_CUDA(cudaMemsetAsync(c->dd_work.p, 0, sizeof(int), st));
                 da.work_counter = c->dd_work.p;
             }
-            if (split) {
-                da.st_rec = reinterpret_cast<const StatRec *>(c->st_thr.p); da.st_cnt = c->st_cnt.p; da.item_soff = c->st_itemoff.p;
-                da.item_T = c->st_itemT.p;
-                count_dedup_kernel<3><<<grid, kDdThreads, smem, st>>>(da);
-                COEX_KCHECK(st);
-                ScatterArgs sc{};
-                sc.st_w = c->st_w.p; sc.st_cnt = c->st_cnt.p; sc.st_total = c->st_cursor.p; sc.n_degenerate = c->d_ndeg.p; sc.N = N;
-                sc.anticor = prm->anticorrelation; sc.score_tab = c->dd_tab.p; sc.scores = d_sc; sc.counts = d_cn;
-                score_scatter_kernel<<<c->sm_count * 8, 256, 0, st>>>(sc);
-                c->launches += 1; c->stage_launches[ST_COUNT] += 1;
-            } else if (pearson) {
+            if (pearson) {
                 da.eps_row = c->z_valid.p;
                 da.strip_f32 = c->strip_f32.p; da.raw = c->raw; da.raw_sum = c->raw_sum.p; da.raw_mean = c->raw_mean.p;
                 da.raw_xx = c->raw_xx.p; da.n = c->n; da.icol = c->z_valid.p; da.n_degenerate = c->z_ninv.p;
@@ -338,13 +299,6 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
         COEX_CUDA(cudaStreamSynchronize(st));
         unsigned long long h[16];
         COEX_CUDA(cudaMemcpy(h, phase.p, sizeof h, cudaMemcpyDeviceToHost));
-        if (split && h[15])
-            fprintf(stderr, "[coex stat_sort] items=%llu cycles/item: meta=%llu stats=%llu scan=%llu group=%llu rank=%llu write=%llu (grid<=%d, smem=%zu)\n",
-                    h[15], h[8] / h[15], h[9] / h[15], h[10] / h[15], h[11] / h[15], h[12] / h[15], h[13] / h[15], sort_grid_max, ssmem);
-        if (rows_kernel)
-            fprintf(stderr, "[coex count rows] items=%llu cycles/item: meta=%llu stats=%llu chunks=%llu score=%llu (Tcap=%d Qcap=%d grid<=%d smem=%zu)\n",
-                    h[6], h[0] / std::max(1ULL, h[6]), h[1] / std::max(1ULL, h[6]), h[2] / std::max(1ULL, h[6]), h[3] / std::max(1ULL, h[6]), Tcap, Qcap, grid_max, smem);
-        else
         fprintf(stderr, "[coex count] items=%llu queued=%llu cycles/item: meta=%llu stats=%llu rank=%llu stream=%llu refine=%llu score=%llu (Tcap=%d Qcap=%d grid<=%d)\n",
                 h[6], h[7], h[0] / std::max(1ULL, h[6]), h[1] / std::max(1ULL, h[6]), h[2] / std::max(1ULL, h[6]), h[3] / std::max(1ULL, h[6]),
                 h[4] / std::max(1ULL, h[6]), h[5] / std::max(1ULL, h[6]), Tcap, Qcap, grid_max);
@@ -717,7 +671,7 @@ using namespace coex;
 extern "C" {
 
 const char *coex_last_error(void) { return g_last_error.c_str(); }
-int coex_abi_version(void) { return 1; }
+int coex_abi_version(void) { return 2; }
 
 int coex_device_count(void) {
     int n = 0;
@@ -756,7 +710,7 @@ int coex_destroy(coex_ctx *c) {
     c->st_thr.release(); c->st_w.release(); c->st_cnt.release(); c->st_itemoff.release(); c->st_itemT.release();
     c->st_cursor.release(); c->sxg.release(); c->dd_work.release();
     c->z_planes.release(); c->z_ok.release(); c->z_l1.release(); c->z_inv_s.release();
-    c->ap_hist.release(); c->feat_key.release(); c->feat_row.release(); c->pm_blob.release(); c->pm_counts.release(); c->pm_hits_tmp.release(); c->pm_off.release();
+    c->ap_hist.release(); c->feat_key.release(); c->feat_row.release(); c->feat_wrank.release(); c->feat_wrow.release(); c->pm_blob.release(); c->pm_counts.release(); c->pm_hits_tmp.release(); c->pm_off.release();
     c->chrom_id.release(); c->name_rank.release(); c->feat_start.release(); c->feat_end.release(); c->glist.release();
     c->a_hi.release(); c->a_lo.release(); c->strip.release(); c->strip_f64.release(); c->strip_f32.release(); c->rank_strip.release();
     c->d_perm_off.release(); c->d_sc_off.release(); c->d_warp_off.release(); c->d_hits.release(); c->d_ngroups.release(); c->d_grp.release();
@@ -843,16 +797,28 @@ int coex_set_features(coex_ctx *c, const int *chrom_id, const long long *start, 
         c->feat_maxlen = maxlen;
         COEX_CUDA(cudaStreamSynchronize(c->stream));
     }
+    c->h_chrom_id.assign(chrom_id, chrom_id + N); c->h_feat_start.assign(start, start + N); c->h_feat_end.assign(end, end + N);
+    c->h_bed_index.resize((size_t)N);
+    for (long long i = 0; i < N; ++i) c->h_bed_index[(size_t)i] = (int)i;       // default: the feature BED lists the rows in table order
+    COEX_TRY(upload_window_order(c));
     COEX_CUDA(cudaStreamSynchronize(c->stream));
     c->have_features = true;
     return 0;
+}
+
+int coex_set_feature_order(coex_ctx *c, const int *bed_index, long long N) {
+    COEX_TRY(check_ctx(c));
+    if (!c->have_features) COEX_FAIL("coex_set_feature_order: call coex_set_features first");
+    if (N != c->N || !bed_index) COEX_FAIL("coex_set_feature_order: one line number per table row");
+    c->h_bed_index.assign(bed_index, bed_index + N);
+    return upload_window_order(c);
 }
 
 int coex_permute_map(coex_ctx *c, int mode, const int *snp_chrom, const long long *snp_addr, const long long *snp_back,
                      int M, const long long *shifts, int K, const long long *chrom_start, const long long *chrom_end,
                      const int *chrom_fid, int n_chrom, const int *back_chrom, const long long *back_addr,
                      long long n_back, long long window, long long *perm_off, int *hit_rows, long long capacity,
-                     int on_device) {
+                     int on_device, int *hit_loci) {
     COEX_TRY(check_ctx(c));
     if (!c->have_features) COEX_FAIL("coex_permute_map: call coex_set_features first");
     if (mode != 0 && mode != 1 && mode != 2) COEX_FAIL("coex_permute_map: mode 0 = circular, 1 = backcirc, 2 = background");
@@ -898,6 +864,7 @@ int coex_permute_map(coex_ctx *c, int mode, const int *snp_chrom, const long lon
     pa.back_addr = reinterpret_cast<const long long *>(c->pm_blob.p + o_ba);
     pa.n_back = n_back; pa.window = window;
     pa.fkey = c->feat_key.p; pa.frow = c->feat_row.p; pa.fstart = c->feat_start.p; pa.fend = c->feat_end.p;
+    pa.wrank = c->feat_wrank.p; pa.wrow = c->feat_wrow.p;
     pa.N = c->N; pa.maxlen = c->feat_maxlen;
     COEX_TRY(c->pm_counts.reserve((size_t)2 * K + 1));
     COEX_CUDA(cudaMemsetAsync(c->pm_counts.p, 0, ((size_t)2 * K + 1) * sizeof(int), st));
@@ -914,8 +881,9 @@ int coex_permute_map(coex_ctx *c, int mode, const int *snp_chrom, const long lon
     const int cap = std::max(256, next_pow2(cmax));
     if (cap > 8192) COEX_FAIL("coex_permute_map: more than 8192 (locus, feature) pairs in one set");
     pa.cap = cap;
-    COEX_TRY(c->pm_hits_tmp.reserve((size_t)K * cap));
+    COEX_TRY(c->pm_hits_tmp.reserve((size_t)K * cap * (hit_loci ? 3 : 1)));
     pa.hits_tmp = c->pm_hits_tmp.p;
+    pa.loci_tmp = hit_loci ? c->pm_hits_tmp.p + (size_t)K * cap : nullptr;
     // ---- pass 2: hits of every set, then offsets and the packed list ------------------------------------
     const size_t smem = (size_t)2 * cap * sizeof(unsigned long long);
     COEX_CUDA(cudaFuncSetAttribute(permute_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -931,15 +899,21 @@ int coex_permute_map(coex_ctx *c, int mode, const int *snp_chrom, const long lon
     COEX_CUDA(cudaStreamSynchronize(st));
     const long long H = h_off[(size_t)K];
     if (H > capacity) COEX_FAIL("coex_permute_map: hit_rows capacity too small (needs " + std::to_string(H) + ")");
-    if (!on_device) { COEX_TRY(c->d_hits.reserve((size_t)std::max<long long>(H, 1))); d_rows = c->d_hits.p; }
+    int *d_loci = hit_loci;
+    if (!on_device) {
+        COEX_TRY(c->d_hits.reserve((size_t)std::max<long long>(H, 1) * (hit_loci ? 3 : 1)));
+        d_rows = c->d_hits.p;
+        if (hit_loci) d_loci = c->d_hits.p + std::max<long long>(H, 1);
+    }
     if (H > 0) {
-        permute_compact_kernel<<<K, 256, 0, st>>>(pa.hits_tmp, cap, d_off, K, d_rows);
+        permute_compact_kernel<<<K, 256, 0, st>>>(pa.hits_tmp, pa.loci_tmp, cap, d_off, K, d_rows, d_loci);
         COEX_KCHECK(st);
     }
     c->launches += 4;
     if (!on_device) {
         memcpy(perm_off, h_off.data(), ((size_t)K + 1) * sizeof(long long));
         if (H > 0) COEX_CUDA(cudaMemcpyAsync(hit_rows, d_rows, (size_t)H * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (H > 0 && hit_loci) COEX_CUDA(cudaMemcpyAsync(hit_loci, d_loci, (size_t)H * 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     }
     COEX_CUDA(cudaStreamSynchronize(st));
     return 0;
@@ -1062,9 +1036,9 @@ int coex_set_gemm_mode(coex_ctx *c, int mode) {
 
 int coex_set_count_mode(coex_ctx *c, int mode) {
     if (!c) COEX_FAIL("null context");
-    if (mode < 0 || mode > 4)
+    if (mode != 0 && mode != 1 && mode != 3)
         COEX_FAIL("coex_set_count_mode: 0 = de-duplicated sorted-statistics kernel (row-rank mode chosen by cost), 1 = per-query kernel, "
-                  "2 = de-duplicated bucket-window kernel, 3 = row-rank mode forced, 4 = mode 0 split into sort / stream / score kernels");
+                  "3 = row-rank mode forced");
     c->count_mode = mode;
     return 0;
 }

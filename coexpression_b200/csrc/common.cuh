@@ -129,6 +129,10 @@ struct coex_ctx {
     coex::DevBuf<unsigned long long> feat_key;
     coex::DevBuf<int> feat_row;
     long long feat_maxlen = 0;
+    // order in which `bedtools window` reports the B records of one A record (permute.cuh): rank of every table row and its inverse
+    coex::DevBuf<int> feat_wrank, feat_wrow;
+    std::vector<int> h_chrom_id, h_bed_index;
+    std::vector<long long> h_feat_start, h_feat_end;
     coex::DevBuf<unsigned char> pm_blob;      // staged inputs of coex_permute_map
     coex::DevBuf<int> pm_counts, pm_hits_tmp;
     coex::DevBuf<long long> pm_off;

@@ -27,7 +27,10 @@
 namespace coex {
 
 constexpr int kDdThreads = 512;
-constexpr int kDdBuckets = 8192;
+constexpr int kDdBuckets = 8192;         // coarse buckets of [-R, R]: the counting sort of the statistics and the search window of a value
+constexpr int kDdSub = 16;               // each coarse bucket is cut into 16 sub-buckets: 131072 "virtual" buckets whose occupancy is two
+                                         // 16-bit masks in the coarse bucket's table entry (>= 1 statistic / >= 2 statistics)
+constexpr int kDdFine = kDdBuckets * kDdSub;
 constexpr int kDdQueue = 2048;
 constexpr int kRankTcap = 8192;          // columns ranked per work item in row-rank mode
 constexpr float kDdDelta = 5e-7f;        // |v32 - v64| <= 3e-7 |v|, |t32 - t64| <= 6e-8 |t|  
@@ -91,12 +94,6 @@ struct DedupArgs {
     const double *raw_sum, *raw_mean, *raw_xx;
     int n;
     unsigned int *rank_out;         // MODE 2: [rows_in_strip, ld] number of null values strictly below each column's value
-    // ---- MODE 3: the item's statistics arrive SORTED from stat_sort_kernel (count_split.cuh) ----------------------
-    const StatRec *st_rec;          // sorted statistics of every item of the launch, item `it` at item_soff[it] .. + item_T[it]
-    unsigned int *st_cnt;           // OUT: number of streamed + hit columns strictly below the statistic (score_scatter_kernel
-                                    //      turns it into the bisect index and the edge score)
-    const long long *item_soff;     // [n_items]
-    const int *item_T;              // [n_items]
     const float *eps_row;           // [N_pad] per-row share of the bound of |tensor r - exact r| (= icol in this mode; 0 = undefined row):
                                     // |error(u, c)| <= eps_row[u] + eps_row[c] (digit quantisation)
 };
@@ -118,11 +115,24 @@ __device__ __forceinline__ double pearson_exact_thread(const DedupArgs &a, long 
 // both for the float compare of the fast path and for the double compare of the refinement: the statistics <= v are
 // all the statistics of the lower buckets plus some of v's OWN bucket -- a one-bucket search window with no
 // "off by one bucket in float" case.
-__device__ __forceinline__ int dd_bucket32(float x, float scale) {
-    const int b = __float2int_rz(__fmaf_rn(x, scale, (float)(kDdBuckets / 2)));
-    return min(max(b, 0), kDdBuckets - 1);
+// `scale` is the scale of the VIRTUAL buckets (kDdFine / 2R); the coarse bucket is the virtual one >> 4, so one monotone
+// function places statistics and values at both levels.
+__device__ __forceinline__ int dd_fine32(float x, float scale) {
+    const int b = __float2int_rz(__fmaf_rn(x, scale, (float)(kDdFine / 2)));
+    return min(max(b, 0), kDdFine - 1);
 }
-__device__ __forceinline__ int dd_bucket(double t, float scale) { return dd_bucket32(__double2float_rn(t), scale); }
+__device__ __forceinline__ int dd_fine(double t, float scale) { return dd_fine32(__double2float_rn(t), scale); }
+__device__ __forceinline__ int dd_bucket32(float x, float scale) { return dd_fine32(x, scale) >> 4; }
+__device__ __forceinline__ int dd_bucket(double t, float scale) { return dd_fine(t, scale) >> 4; }
+// table entry of a coarse bucket while the statistics are sorted: .x = first statistic of the bucket (their number during the
+// counting pass), .y = sub-buckets holding >= 1 statistic (low half) | sub-buckets holding >= 2 statistics (high half).
+// FINAL form (dd_finish_table), what the streaming pass reads with ONE 8-byte load per value:
+//   .x = first statistic (14 bits) | sub-buckets holding >= 2 statistics << 16
+//   .y = OCC: sub-buckets holding >= 1 statistic | BUSY << 16: sub-buckets that hold a statistic, or whose neighbour sub-bucket
+//        (also across the coarse bucket's edges) does, or that lie at or above a sub-bucket with >= 2 statistics
+// the number of statistics of bucket b is lut[b + 1].x - lut[b].x (lut[kDdBuckets].x = T).
+constexpr unsigned int kDdStartMask = 0x3fffu;
+static_assert(kDdSub == 16, "two 16-bit occupancy masks per table entry");
 
 // the same for a whole warp: coalesced loads, the products added in order through shuffles (every lane gets the result)
 __device__ __forceinline__ double pearson_exact_warp(const DedupArgs &a, long long ra, long long rb, int lane) {
@@ -147,24 +157,20 @@ __device__ __forceinline__ double pearson_exact_warp(const DedupArgs &a, long lo
 //         when the hit sets are so large that a row's queries carry more statistics than the row has columns (config C5:
 //         wide windows, thousands of hits per set): every (query, hit) then only LOOKS UP the rank of its column
 //         (rank_score_kernel) instead of having the row streamed once per query.
-// MODE 3: Spearman null as MODE 0, but phases A - C (query metadata, statistics, sort) were done for ALL items of the launch by
-//         stat_sort_kernel (count_split.cuh), whose shared memory holds the statistics during the sort and which keeps many more
-//         items in flight per SM than this kernel's two CTAs: the set-up phases were latency bound and half of this kernel's
-//         cycles (profiles/r01_count_split.md).  What is left here: load the sorted statistics, build the bucket table, stream.
 template <int MODE>
 __global__ void __launch_bounds__(kDdThreads)
 count_dedup_kernel(DedupArgs a) {
-    constexpr bool PEARSON = (MODE == 1), RANKROW = (MODE == 2), PRE = (MODE == 3);
+    constexpr bool PEARSON = (MODE == 1), RANKROW = (MODE == 2);
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: q_vi[Qcap] | thr32[Tcap+4] | hist[Tcap+4] (thr32|hist = cursor[B] during step B) | lut[B+4] | queue[kDdQueue] | q_k q_i q_toff
+    // layout: q_vi[Qcap] | thr32[Tcap+4] | hist[Tcap+4] (thr32|hist = cursor[B] during step B) | lut[B+2] (8 bytes each) | queue[kDdQueue] | q_k q_i q_toff
     // (the double statistics and their origins live in an L2-resident per-CTA scratch: they are only
     //  touched by the rare exact refinements and by the final scoring)
     double *q_vi = reinterpret_cast<double *>(smem_raw);                      // [Qcap] exact null value at the skipped column
     float *thr32 = reinterpret_cast<float *>(q_vi + a.Qcap) + 1;             // [-1 .. Tcap+2]: thr32[-1] = -inf, thr32[T] = +inf (sentinels)
     unsigned int *hist = reinterpret_cast<unsigned int *>(thr32 + a.Tcap + 3);
-    unsigned int *lut = hist + a.Tcap + 4;
+    uint2 *lut = reinterpret_cast<uint2 *>(hist + a.Tcap + 4);              // [kDdBuckets + 2] table entries (8-byte aligned: Qcap * 8 + (Tcap + 4) * 8 bytes in front)
     unsigned int *cursor = reinterpret_cast<unsigned int *>(thr32 - 1);   // bucket cursors alias thr32|hist (both dead until step C; 2*Tcap >= buckets)
-    int *queue = reinterpret_cast<int *>(lut + kDdBuckets + 4);
+    int *queue = reinterpret_cast<int *>(lut + kDdBuckets + 2);
     long long *q_sc = reinterpret_cast<long long *>(queue + kDdQueue);   // [Qcap] offset of the query's score row
     int *q_i = reinterpret_cast<int *>(q_sc + a.Qcap);                     // [Qcap] hit position
     int *q_off = q_i + a.Qcap;                   // [Qcap] offset of the query's permutation in hit_rows
@@ -175,11 +181,11 @@ count_dedup_kernel(DedupArgs a) {
     __shared__ unsigned int s_warp[kDdThreads / 32];
 
     const int tid = threadIdx.x;
-    const float bscale_f = (float)((double)kDdBuckets / (2.0 * a.R));
-    StatRec *rec_tmp = PRE ? nullptr : a.g_rec + (long long)blockIdx.x * 3 * a.Tcap;   // statistic of flat index t
+    const float bscale_f = (float)((double)kDdFine / (2.0 * a.R));        // scale of the virtual buckets
+    StatRec *rec_tmp = a.g_rec + (long long)blockIdx.x * 3 * a.Tcap;   // statistic of flat index t
     StatRec *rec_grp = rec_tmp + a.Tcap;                             // grouped by bucket
     StatRec *srt_w = rec_grp + a.Tcap;                               // sorted
-    const StatRec *srt = srt_w;                                      // (MODE 3: the item's slice of the pre-sorted array)
+    const StatRec *srt = srt_w;
 
     const int n_deg = *a.n_degenerate;
     const int nchunk = RANKROW ? (int)((a.N + a.Tcap - 1) / a.Tcap) : 1;
@@ -205,77 +211,7 @@ count_dedup_kernel(DedupArgs a) {
         long long tclk = clock64();
 #define DD_PHASE(id) do { if (a.phase_clk && tid == 0) { const long long now = clock64(); atomicAdd(&a.phase_clk[id], (unsigned long long)(now - tclk)); tclk = now; } } while (0)
         int T = 0;
-        long long soff = 0;
-        if constexpr (PRE) {
-            // ---- A'. the item's sorted statistics and query metadata come from stat_sort_kernel -------------------
-            T = a.item_T[it];
-            soff = a.item_soff[it];
-            srt = a.st_rec + soff;
-            if (T == 0) continue;                           // every statistic undefined: scores already written
-            // the item's statistics: every load of the thread issued before the first is used (T <= 16 * kDdThreads)
-            double t_in[4];
-            int c_in[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int s = tid + e * kDdThreads;
-                StatRec x = {0.0, 0u, 0};
-                if (s < T) x = srt[s];
-                t_in[e] = x.r; c_in[e] = x.col;
-            }
-            if (tid == 0) s_qn = 0;
-            for (int b = tid; b < kDdBuckets; b += kDdThreads) lut[b] = 0;
-            for (int wd = tid; wd < (a.claim ? 2 : 1) * a.bm_words; wd += kDdThreads) bitmap[wd] = 0;
-            __syncthreads();
-            for (int s0 = 0; s0 < T; s0 += 4 * kDdThreads) {
-                if (s0) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int s = s0 + tid + e * kDdThreads;
-                        StatRec x = {0.0, 0u, 0};
-                        if (s < T) x = srt[s];
-                        t_in[e] = x.r; c_in[e] = x.col;
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int s = s0 + tid + e * kDdThreads;
-                    if (s >= T) continue;
-                    thr32[s] = (float)t_in[e];
-                    hist[s] = 0;
-                    atomicAdd(&lut[dd_bucket(t_in[e], bscale_f)], 1u);
-                    if (a.bm_words) {
-                        const unsigned int bit = 1u << (c_in[e] & 31);
-                        atomicOr(&bitmap[c_in[e] >> 5], bit);
-                        if (a.claim) atomicOr(&bitmap[a.bm_words + (c_in[e] >> 5)], bit);
-                    }
-                }
-            }
-            if (tid == 0) { hist[T] = 0; thr32[-1] = -CUDART_INF_F; thr32[T] = CUDART_INF_F; }
-            __syncthreads();
-            DD_PHASE(0);
-            {   // exclusive scan of the bucket counts, start | count << 16 (as the fused modes leave it)
-                constexpr int kWarps = kDdThreads / 32, kPerWarp = kDdBuckets / kWarps;
-                const int wid = tid >> 5, ln = tid & 31;
-                unsigned int carry = 0;
-                for (int c = 0; c < kPerWarp; c += 32) {
-                    const int b = wid * kPerWarp + c + ln;
-                    const unsigned int v = lut[b];
-                    unsigned int incl = v;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const unsigned int x = __shfl_up_sync(0xffffffffu, incl, o); if (ln >= o) incl += x; }
-                    lut[b] = (carry + incl - v) | (v << 16);
-                    carry += __shfl_sync(0xffffffffu, incl, 31);
-                }
-                if (ln == 0) s_warp[wid] = carry;
-                __syncthreads();
-                unsigned int base = 0;
-                for (int w = 0; w < wid; ++w) base += s_warp[w];
-                if (base)
-                    for (int c = 0; c < kPerWarp; c += 32) lut[wid * kPerWarp + c + ln] += base;
-                __syncthreads();
-            }
-            DD_PHASE(1);
-        } else {
+        {
         // ---- A. query metadata ----------------------------------------------------------------
         for (int ql = tid; ql < nq; ql += kDdThreads) {
             const long long q = a.qlist[item.qb + ql];
@@ -305,7 +241,7 @@ count_dedup_kernel(DedupArgs a) {
             }
         }
         if (tid == 0) { s_T = 0; s_qn = 0; }
-        for (int b = tid; b <= kDdBuckets; b += kDdThreads) lut[b] = 0;
+        for (int b = tid; b <= kDdBuckets; b += kDdThreads) lut[b] = make_uint2(0u, 0u);
         for (int wd = tid; wd < (a.claim ? 2 : 1) * a.bm_words; wd += kDdThreads) bitmap[wd] = 0;
         __syncthreads();
         if (tid == 0) {
@@ -363,7 +299,12 @@ count_dedup_kernel(DedupArgs a) {
                         if (a.counts) a.counts[w] = -1;
                     }
                 } else {
-                    atomicAdd(&lut[dd_bucket(r, bscale_f)], 1u);
+                    {   // coarse bucket count + occupancy of the statistic's sub-bucket (>= 1 / >= 2 statistics)
+                        const int fi = dd_fine(r, bscale_f);
+                        atomicAdd(&lut[fi >> 4].x, 1u);
+                        const unsigned int bit = 1u << (fi & 15);
+                        if (atomicOr(&lut[fi >> 4].y, bit) & bit) atomicOr(&lut[fi >> 4].y, bit << 16);
+                    }
                     // the null value of a hit column IS this statistic (same arithmetic): it is accounted
                     // exactly in step C' and skipped by the float streaming pass
                     if (a.bm_words) {
@@ -381,11 +322,11 @@ count_dedup_kernel(DedupArgs a) {
             unsigned int carry = 0;
             for (int c = 0; c < kPerWarp; c += 32) {
                 const int b = wid * kPerWarp + c + ln;
-                const unsigned int v = lut[b];
+                const unsigned int v = lut[b].x;
                 unsigned int incl = v;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const unsigned int x = __shfl_up_sync(0xffffffffu, incl, o); if (ln >= o) incl += x; }
-                lut[b] = carry + incl - v;
+                lut[b].x = carry + incl - v;
                 carry += __shfl_sync(0xffffffffu, incl, 31);
             }
             if (ln == 0) s_warp[wid] = carry;
@@ -394,10 +335,10 @@ count_dedup_kernel(DedupArgs a) {
             for (int w = 0; w < wid; ++w) base += s_warp[w];
             for (int c = 0; c < kPerWarp; c += 32) {
                 const int b = wid * kPerWarp + c + ln;
-                lut[b] += base;
+                lut[b].x += base;
                 cursor[b] = 0;
             }
-            if (tid == kDdThreads - 1) { lut[kDdBuckets] = base + carry; s_T = (int)(base + carry); }
+            if (tid == kDdThreads - 1) { lut[kDdBuckets].x = base + carry; s_T = (int)(base + carry); }
             __syncthreads();
         }
         // group by bucket
@@ -408,15 +349,12 @@ count_dedup_kernel(DedupArgs a) {
                 int lo = 0, hi = nq;
                 if (!RANKROW) while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (q_toff[mid] <= t) lo = mid; else hi = mid; }
                 const int b = dd_bucket(r, bscale_f);
-                const unsigned int pos = lut[b] + atomicAdd(&cursor[b], 1u);
+                const unsigned int pos = lut[b].x + atomicAdd(&cursor[b], 1u);
                 rec_grp[pos] = StatRec{r, RANKROW ? (unsigned int)t : ((unsigned int)lo << 13) | (unsigned int)(t - q_toff[lo]), x.col};
             }
         }
         __syncthreads();
         T = s_T;
-        // lut[b] = first statistic of bucket b | number of statistics in it << 16 (the cursors have counted them; T <= 8192):
-        // one shared-memory load per streamed value gives its whole search window
-        for (int b = tid; b < kDdBuckets; b += kDdThreads) lut[b] |= cursor[b] << 16;
         __syncthreads();                                    // the cursors (aliasing thr32 | hist) are dead from here on
         DD_PHASE(1);
         if (T == 0) continue;                               // every statistic undefined: scores already written
@@ -424,8 +362,8 @@ count_dedup_kernel(DedupArgs a) {
         for (int e = tid; e < T; e += kDdThreads) {
             const StatRec x = rec_grp[e];
             const double t = x.r;
-            const unsigned int pk = lut[dd_bucket(t, bscale_f)];
-            const int lo = (int)(pk & 0xffffu), hi = lo + (int)(pk >> 16);
+            const int bt = dd_bucket(t, bscale_f);
+            const int lo = (int)(lut[bt].x & kDdStartMask), hi = (int)(lut[bt + 1].x & kDdStartMask);
             int rank = 0;
             for (int m = lo; m < hi; ++m) {
                 const double y = rec_grp[m].r;
@@ -436,8 +374,19 @@ count_dedup_kernel(DedupArgs a) {
         }
         for (int p = tid; p <= T; p += kDdThreads) hist[p] = 0;
         if (tid == 0) { thr32[-1] = -CUDART_INF_F; thr32[T] = CUDART_INF_F; }
+        // final form of the table (see kDdStartMask).  In place: a neighbour's OCC half-word, the only thing read from it, is the
+        // same before and after its own entry is rewritten.
+        for (int b = tid; b < kDdBuckets; b += kDdThreads) {
+            const uint2 e = lut[b];
+            const unsigned int occ = e.y & 0xffffu, multi = e.y >> 16;
+            const unsigned int prev_top = (b > 0) ? (lut[b - 1].y >> 15) & 1u : 0u;
+            const unsigned int next_bot = (b + 1 < kDdBuckets) ? lut[b + 1].y & 1u : 0u;
+            unsigned int busy = occ | (occ << 1) | (occ >> 1) | prev_top | (next_bot << 15);
+            if (multi) busy |= ~((multi & (0u - multi)) - 1u);          // every sub-bucket at or above the lowest one with two statistics
+            lut[b] = make_uint2((e.x & kDdStartMask) | (multi << 16), occ | (busy << 16));
+        }
         __syncthreads();
-        }   // !PRE
+        }
         // ---- C'. hit columns: value == statistic exactly.  A column hit by several queries of the item appears as
         // several EQUAL statistics (same row, same column, same arithmetic) and is added once: by the statistic that
         // claims its bit in a second bitmap (short tables), or by the first of the equal statistics in sorted order
@@ -481,6 +430,8 @@ count_dedup_kernel(DedupArgs a) {
         // ---- D. stream the null values of table row u (fp32 fast path) -----------------------------
         const float iu = (float)(0.5 / sxu);
         const float eps_u = PEARSON ? a.eps_row[u] : 0.0f;
+        // Pearson: the fast branch needs |tensor r - exact r| (<= eps_u + eps_c) well inside a virtual bucket (2R / 131072 wide)
+        const float pearson_fast_eps = (float)(a.R / (double)kDdFine * 0.125);
         const long long N = a.N;
         // Four columns per thread are handled in lockstep (independent shared-memory chains overlap)
         // and the next 16-byte strip / norm loads are issued before the current ones are consumed.
@@ -510,19 +461,47 @@ count_dedup_kernel(DedupArgs a) {
                 if (have) fetch(c0);
                 float v[4];
                 int p[4], len[4];
-                bool act[4];
+                unsigned int mid4 = 0u, slow4 = 0u;                       // per slot: resolved by its three neighbours / needs the search loop
+                float tlo[4], thi[4];                                     // the value's two neighbours among the sorted statistics
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     // zero-variance column (and the padding behind column N): mask 0 -> -99, counted in bulk; hit column:
                     // accounted exactly in step C'
-                    act[e] = (wv[e] != 0.0f) && !((skip4 >> e) & 1u);
+                    const bool act = (wv[e] != 0.0f) && !((skip4 >> e) & 1u);
                     v[e] = PEARSON ? __int_as_float(sv[e]) : __int2float_rn(sv[e]) * (iu * wv[e]);
-                    // the statistics <= v are those of the lower buckets and some of v's own bucket (dd_bucket32 is monotone)
-                    const unsigned int pk = lut[dd_bucket32(v[e], bscale_f)];
-                    p[e] = (int)(pk & 0xffffu);
-                    len[e] = act[e] ? (int)(pk >> 16) : 0;
+                    const unsigned int fi = min(__float2uint_rz(__fmaf_rn(v[e], bscale_f, (float)(kDdFine / 2))), (unsigned int)(kDdFine - 1));
+                    const uint2 ent = lut[fi >> 4];                       // (negative / NaN -> 0: the conversion saturates)
+                    const unsigned int sub = fi & 15u, below = (1u << sub) - 1u;
+                    // statistics of the lower virtual buckets: exact unless a lower sub-bucket holds two (then BUSY is set)
+                    p[e] = (int)(ent.x & kDdStartMask) + __popc(ent.y & below);
+                    len[e] = 0;
+                    tlo[e] = thi[e] = 0.0f;
+                    if (act) {
+                        // FAST: no statistic in the value's virtual bucket nor in the two next to it.  A virtual bucket is >= 10 x
+                        // wider than the float error of a value (Spearman: 5e-7 |v| against 2R / 131072 >= 5.7e-6 |v|_max; Pearson
+                        // columns with a large digit error are sent to the other branches), so no statistic is within the error
+                        // of v, dd_fine32 is monotone, and the statistics <= v64 are exactly those of the lower virtual buckets.
+                        const bool busy = ((ent.y >> 16) >> sub) & 1u;
+                        if (!busy && (!PEARSON || wv[e] + eps_u <= pearson_fast_eps)) {
+                            atomicAdd(&hist[p[e]], 1u);
+                        } else if (((ent.x >> 16) & (below | (1u << sub))) == 0u) {
+                            // at most ONE statistic in the value's virtual bucket and none doubled below: p[e] is exact up to that
+                            // statistic; it and the two around it are three independent loads (no search)
+                            mid4 |= 1u << e;
+                            const float t0 = thr32[p[e] - 1], t1 = thr32[p[e]];
+                            const float t2 = ((ent.y >> sub) & 1u) ? thr32[p[e] + 1] : CUDART_INF_F;
+                            const bool up = ((ent.y >> sub) & 1u) && t1 <= v[e];              // the bucket's own statistic is <= v
+                            p[e] += up ? 1 : 0;
+                            tlo[e] = up ? t1 : t0;
+                            thi[e] = up ? t2 : t1;
+                        } else {
+                            slow4 |= 1u << e;
+                            p[e] = (int)(ent.x & kDdStartMask);
+                            len[e] = (int)(lut[(fi >> 4) + 1].x & kDdStartMask) - p[e];
+                        }
+                    }
                 }
-                while ((len[0] | len[1] | len[2] | len[3]) > 0) {         // statistics <= v inside the bucket
+                while ((len[0] | len[1] | len[2] | len[3]) > 0) {         // statistics <= v inside the coarse bucket (rare)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         if (len[e] > 0) {
@@ -533,12 +512,19 @@ count_dedup_kernel(DedupArgs a) {
                 }
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    if (!act[e]) continue;
-                    // a statistic closer than delta cannot be ordered in float: the two neighbours of v in the sorted
+                    if (!(((mid4 | slow4) >> e) & 1u)) continue;
+                    // a statistic closer than tol cannot be ordered in float: the two neighbours of v in the sorted
                     // statistics decide (sentinels -inf / +inf at both ends)
-                    const float below = v[e] - thr32[p[e] - 1];
-                    const float above = thr32[p[e]] - v[e];
-                    if (fminf(below, above) >= (PEARSON ? dd_delta(v[e]) + eps_u + wv[e] : dd_delta(v[e]))) {
+                    float below, above;
+                    if ((slow4 >> e) & 1u) {
+                        below = v[e] - thr32[p[e] - 1];
+                        above = thr32[p[e]] - v[e];
+                    } else {
+                        below = v[e] - tlo[e];
+                        above = thi[e] - v[e];
+                    }
+                    const float tol = PEARSON ? dd_delta(v[e]) + eps_u + wv[e] : dd_delta(v[e]);
+                    if (fminf(below, above) >= tol) {
                         atomicAdd(&hist[p[e]], 1u);
                     } else {
                         const int slot = atomicAdd(&s_qn, 1);
@@ -547,9 +533,9 @@ count_dedup_kernel(DedupArgs a) {
                         } else {                                          // queue full: refine in place
                             const double vv = PEARSON ? pearson_exact_thread(a, u, cc + e)
                                                       : __ddiv_rn(0.25 * (double)srow[cc + e], __dmul_rn(sxu, a.sx[cc + e]));
-                            const unsigned int pk = lut[dd_bucket(vv, bscale_f)];
-                            int pp = (int)(pk & 0xffffu);
-                            int ln = (int)(pk >> 16);
+                            const int bv = dd_bucket(vv, bscale_f);
+                            int pp = (int)(lut[bv].x & kDdStartMask);
+                            int ln = (int)(lut[bv + 1].x & kDdStartMask) - pp;
                             while (ln > 0) {
                                 const int half = ln >> 1;
                                 if (srt[pp + half].r <= vv) { pp += half + 1; ln -= half + 1; } else ln = half;
@@ -567,9 +553,9 @@ count_dedup_kernel(DedupArgs a) {
                 const int c = queue[x];
                 const double vv = PEARSON ? pearson_exact_thread(a, u, c)
                                           : __ddiv_rn(0.25 * (double)srow[c], __dmul_rn(sxu, a.sx[c]));
-                const unsigned int pk = lut[dd_bucket(vv, bscale_f)];
-                int pp = (int)(pk & 0xffffu);
-                int len = (int)(pk >> 16);
+                const int bv = dd_bucket(vv, bscale_f);
+                int pp = (int)(lut[bv].x & kDdStartMask);
+                int len = (int)(lut[bv + 1].x & kDdStartMask) - pp;
                 while (len > 0) {
                     const int half = len >> 1;
                     if (srt[pp + half].r <= vv) { pp += half + 1; len -= half + 1; } else len = half;
@@ -603,9 +589,6 @@ count_dedup_kernel(DedupArgs a) {
             // all columns strictly below the column's own value (zero-variance columns: -99 < everything)
             unsigned int *rrow = a.rank_out + (long long)item.urow * a.ld + rank_c0;
             for (int s = tid; s < T; s += kDdThreads) rrow[srt[s].org] = hist[s] + (unsigned int)n_deg;
-        } else if (PRE) {
-            // streamed + hit columns strictly below each sorted statistic; score_scatter_kernel does the rest
-            for (int s = tid; s < T; s += kDdThreads) a.st_cnt[soff + s] = hist[s];
         } else
         for (int s0 = 0; s0 < T; s0 += 4 * kDdThreads) {
             // four statistics per thread: record loads, then score-table gathers, then stores -- each kind in flight together
@@ -733,7 +716,7 @@ __global__ void icol_kernel(const double *__restrict__ sx, const unsigned char *
 }
 
 inline size_t dedup_smem_bytes(int Tcap, int Qcap, int bm_words, int claim) {
-    return (size_t)Qcap * 8 + (size_t)(Tcap + 4) * 4 + (size_t)(Tcap + 4) * 4 + (size_t)(kDdBuckets + 4) * 4 +
+    return (size_t)Qcap * 8 + (size_t)(Tcap + 4) * 4 + (size_t)(Tcap + 4) * 4 + (size_t)(kDdBuckets + 2) * 8 +
            (size_t)kDdQueue * 4 + (size_t)Qcap * 8 + (size_t)Qcap * 4 * 3 + (size_t)(Qcap + 2) * 4 + (size_t)bm_words * 4 * (claim ? 2 : 1) + 16;
 }
 

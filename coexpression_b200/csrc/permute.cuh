@@ -11,8 +11,9 @@
 //                         stream); chromosome = column 0, address = column 2 of that line
 //   windowBed -w W ...... bedtools window: A = [address, address + 1) widened by W (start clamped at 0), every
 //                         feature with a.start' < b.end and b.start < a.end' on the same chromosome
-//   promoters ........... first-appearance order over (locus in input order, feature in ascending table row), the
-//                         explicit order this repo gives to the reference's dict (1-make-network.py:131-177)
+//   promoters ........... first-appearance order over (locus in input order, feature in the order `bedtools window` reports the
+//                         B records of one A record: UCSC-bin level, bin, line of the B file -- coex.cu upload_window_order),
+//                         the order a Python-3 dict gives to the reference's snp_map (1-make-network.py:131-177)
 // The features are the rows of the resident table (coex_set_features): a BED feature that is not in the expression
 // table is dropped by the reference anyway (1-make-network.py:142-146).
 // Output = perm_off / hit_rows exactly as coex_network_batch takes them, optionally left on the device.
@@ -41,12 +42,14 @@ struct PermuteArgs {
     const unsigned long long *fkey;  // [N] chrom_id << 40 | start
     const int *frow;                 // [N] table row
     const long long *fstart, *fend;  // [N] by table row
+    const int *wrank, *wrow;         // [N] rank of a table row in bedtools' reporting order, and the row of a rank
     long long N;
     long long maxlen;
     // outputs / scratch
     int *cand_count;                 // [K] candidate (locus, feature) pairs of each set
     int *hit_count;                  // [K]
     int *hits_tmp;                   // [K, cap]
+    int *loci_tmp;                   // [K, cap, 2] or nullptr: first and last locus (input order) mapping to each hit
     int cap;                         // power of two
     int *overflow;
 };
@@ -136,7 +139,7 @@ __device__ void bitonic_keys(unsigned long long *keys, int n2) {
         }
 }
 
-// one CTA per locus set: candidates -> first appearances -> (locus, row) order
+// one CTA per locus set: candidates -> first appearances -> (locus, bedtools reporting order) order
 __global__ void __launch_bounds__(256)
 permute_map_kernel(PermuteArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -163,14 +166,28 @@ permute_map_kernel(PermuteArgs a) {
         const unsigned long long key = keys[i];
         unsigned long long out = ~0ULL;
         if (key != ~0ULL && (i == 0 || (keys[i - 1] >> 32) != (key >> 32)))
-            out = ((key & 0xffffffffULL) << 32) | (key >> 32);       // (locus, row)
+            out = ((key & 0xffffffffULL) << 32) | (unsigned)a.wrank[(int)(key >> 32)];       // (locus, reporting rank of the row)
         keys2[i] = out;
     }
     __syncthreads();
-    bitonic_keys(keys2, a.cap);                                      // by (locus, row); sentinels last
+    // (`keys` stays sorted by (row, locus): the last locus of a row -- the reference's real-data map file keeps the LAST
+    //  windowBed line of a promoter, 0-prepare-coex.py:396-399 -- is looked up there after the second sort)
+    bitonic_keys(keys2, a.cap);                                      // by (locus, reporting rank); sentinels last
     int n = 0;
+    const int ncand = min(s_n, a.cap);
     for (int i = threadIdx.x; i < a.cap; i += blockDim.x)
-        if (keys2[i] != ~0ULL) { a.hits_tmp[(long long)k * a.cap + i] = (int)(keys2[i] & 0xffffffffULL); ++n; }
+        if (keys2[i] != ~0ULL) {
+            const int row = a.wrow[(int)(keys2[i] & 0xffffffffULL)];
+            a.hits_tmp[(long long)k * a.cap + i] = row;
+            if (a.loci_tmp) {
+                // `keys` is still sorted by (row, locus): the last candidate of this row
+                int lo = 0, hi = ncand;                       // first index with key.row > row
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)(keys[mid] >> 32) <= row) lo = mid + 1; else hi = mid; }
+                a.loci_tmp[((long long)k * a.cap + i) * 2] = (int)(keys2[i] >> 32);
+                a.loci_tmp[((long long)k * a.cap + i) * 2 + 1] = (int)(keys[lo - 1] & 0xffffffffULL);
+            }
+            ++n;
+        }
     if (n) atomicAdd(&a.hit_count[k], n);
 }
 
@@ -182,11 +199,18 @@ __global__ void permute_scan_kernel(const int *hit_count, int K, long long *perm
     }
 }
 
-__global__ void permute_compact_kernel(const int *hits_tmp, int cap, const long long *perm_off, int K, int *hit_rows) {
+__global__ void permute_compact_kernel(const int *hits_tmp, const int *loci_tmp, int cap, const long long *perm_off, int K, int *hit_rows,
+                                       int *hit_loci) {
     const int k = blockIdx.x;
     const long long off = perm_off[k];
     const int P = (int)(perm_off[k + 1] - off);
-    for (int i = threadIdx.x; i < P; i += blockDim.x) hit_rows[off + i] = hits_tmp[(long long)k * cap + i];
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        hit_rows[off + i] = hits_tmp[(long long)k * cap + i];
+        if (hit_loci) {
+            hit_loci[2 * (off + i)] = loci_tmp[((long long)k * cap + i) * 2];
+            hit_loci[2 * (off + i) + 1] = loci_tmp[((long long)k * cap + i) * 2 + 1];
+        }
+    }
 }
 
 }  // namespace coex

@@ -63,6 +63,10 @@ int coex_get_ranks(coex_ctx *ctx, double *ranks_out);
  * chrom_id orders like the chromosome string, name_rank orders like the row label. */
 int coex_set_features(coex_ctx *ctx, const int *chrom_id, const long long *start,
                       const long long *end, const int *name_rank, long long N);
+/* Optional: bed_index[row] = line number of the row's feature in the feature BED (`-q`, the B file of `windowBed`).  `bedtools
+ * window` reports the B records of one A record by (UCSC-bin level, bin, line of the B file), and that order decides the order of a
+ * permutation's promoters (1-make-network.py:131-177, quirk Q1).  Default after coex_set_features: the BED lists the rows in table order. */
+int coex_set_feature_order(coex_ctx *ctx, const int *bed_index, long long N);
 /* ascending global correlation list (<expr>.spearmanlist, 1-make-network.py:76-79) */
 int coex_set_global_list(coex_ctx *ctx, const double *sorted_values, long long len);
 
@@ -77,13 +81,16 @@ int coex_set_global_list(coex_ctx *ctx, const double *sorted_values, long long l
  *   background: back_chrom / back_addr = column 0 / column 2 of every line of the background file in FILE order and
  *   snp_back[k * M + m] = the line `random.sample(range(n_back), M)` drew for locus m of set k (the draw stays with the
  *   caller: it is the reference's RNG stream); any non-zero shifts[k] marks a permuted set.
- * Output: perm_off[K+1] and hit_rows (table rows, first-appearance order) exactly as coex_network_batch takes them;
- * host arrays, or device arrays when on_device != 0.  Fails if capacity is too small. */
+ * Output: perm_off[K+1] and hit_rows (table rows, first-appearance order over the loci in input order and, within a locus, the
+ * order in which `bedtools window` reports the features: coex_set_feature_order) exactly as coex_network_batch takes them;
+ * host arrays, or device arrays when on_device != 0.  hit_loci (optional, int [2 * capacity]): for every hit the first and the
+ * last locus (input order) that map to it -- what a map-file writer needs for column 3 (0-prepare-coex.py:396-399 keeps the
+ * last windowBed line of a promoter for the real data).  Fails if capacity is too small. */
 int coex_permute_map(coex_ctx *ctx, int mode, const int *snp_chrom, const long long *snp_addr,
                      const long long *snp_back, int M, const long long *shifts, int K,
                      const long long *chrom_start, const long long *chrom_end, const int *chrom_fid, int n_chrom,
                      const int *back_chrom, const long long *back_addr, long long n_back, long long window,
-                     long long *perm_off, int *hit_rows, long long capacity, int on_device);
+                     long long *perm_off, int *hit_rows, long long capacity, int on_device, int *hit_loci);
 
 /* A1 on the resident table.  which: 0 = raw values (Pearson), 1 = ranks (Spearman).
  * idxa/idxb/out are host pointers (on_device == 0) or device pointers. */
@@ -151,8 +158,7 @@ int coex_network_batch(coex_ctx *ctx, const coex_params *params, int K,
 
 /* Introspection for bench.py: kernels launched by ctx so far, and per-stage device time (ms,
  * CUDA events on coex_stream) of the last coex_network_batch / coex_prepare call.
- * stage ids: 0 rank+pack, 1 row stats, 2 gather, 3 correlation GEMM, 4 count+score, 5 network, 6 statistics + sort
- * (the set-up half of the count stage, stat_sort_kernel) */
+ * stage ids: 0 rank+pack, 1 row stats, 2 gather, 3 correlation GEMM, 4 count+score, 5 network, 6 unused (kept for ABI stability) */
 long long coex_launch_count(coex_ctx *ctx);
 int coex_stage_ms(coex_ctx *ctx, int stage, double *ms, long long *launches);
 /* 0 = tcgen05/TMA tensor-core GEMM (default: persistent kernel; 128 x 64 tiles with double-buffered TMEM accumulators, or
@@ -160,9 +166,8 @@ int coex_stage_ms(coex_ctx *ctx, int stage, double *ms, long long *launches);
  * 2 / 3 = the persistent tcgen05 kernel with 128 x 64 / 128 x 128 tiles explicitly,
  * 64 / 128 = one-tile-per-CTA tcgen05 kernel with that table-column tile */
 int coex_set_gemm_mode(coex_ctx *ctx, int mode);
-/* 0 = de-duplicated sorted-statistics count kernel (default, count_dedup.cuh; 4 = the same split into a sort, a streaming and
- * a score kernel, count_split.cuh -- a cross-check, slower at the bench shape), 1 = per-query binary-search kernel,
- * 2 = de-duplicated bucket-window kernel (count_rows.cuh): three independent implementations of the same counts.
+/* 0 = de-duplicated sorted-statistics count kernel (default, count_dedup.cuh), 1 = per-query binary-search kernel (count.cuh): an
+ * independent implementation of the same counts, kept as the cross-check of the tests.
  * Mode 0 switches by itself to ROW-RANK mode (every strip row ranked once, the queries look their bisect indices up) when the hit
  * sets are so large that this is cheaper (config C5: thousands of hits per set); 3 forces that mode. */
 int coex_set_count_mode(coex_ctx *ctx, int mode);

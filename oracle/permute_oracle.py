@@ -17,12 +17,16 @@ Follows, with explicit orders where the reference iterates Python-2 dicts:
   backcirc mode ........ reference 0-prepare-coex.py:579-593  (sorted background by (gwad, key), :582)
   background mode ...... reference 0-prepare-coex.py:564-578  (random.sample of background lines; the draw is an input here)
   temporary BED ........ reference 0-prepare-coex.py:598-607  `chrom(without chr) address address+1 name`
-  windowBed -w W ....... bedtools (v2.x, README.md:24; NOT under /root/reference and not installed here): published
-                         semantics restated -- A is widened by W on both sides (start clamped at 0) and every B with
-                         a.start' < b.end and b.start < a.end' is reported.  PARITY UNPINNED against a real bedtools
-                         binary (none in this image); the output ORDER of bedtools (bin traversal) is irrelevant to the
-                         reference, whose consumer puts the promoters into a dict (1-make-network.py:131-177).
-Orders fixed here (and in the CUDA path): loci in input order, features of one locus in ascending table row,
+  windowBed -w W ....... bedtools (v2.x, README.md:24; NOT under /root/reference and not installed here): restated from the
+                         published bedtools2 source -- windowBed.cpp BedWindow::FindWindowOverlaps (A widened by W on both
+                         sides, start clamped at 0; a B record is reported iff min(a.end', b.end) - max(a.start', b.start) > 0)
+                         and bedFile.cpp BedFile::allHits / bedFile.h getBin (UCSC binning: 16 kb bins, 7 levels of x8; the
+                         B records of one A record come out by level from the finest up, bin ascending, B-file order inside
+                         a bin).  PARITY UNPINNED against a real bedtools binary (none in this image).  The ORDER is irrelevant
+                         to the Python-2 reference, whose consumer puts the promoters into a hash-ordered dict
+                         (1-make-network.py:131-177), but it is the order an insertion-ordered (Python 3) run of the reference
+                         gives to a permutation's promoters, so this repo adopts it.
+Orders fixed here (and in the CUDA path): loci in input order, features of one locus in bedtools' reporting order,
 promoters of a permutation in first-appearance order.
 """
 from __future__ import annotations
@@ -115,12 +119,36 @@ def background_positions(backlines, picks):
     return out
 
 
-def window_bed(positions, feat_chrom, feat_start, feat_end, window):
-    """positions: list of (chrom, address) or None; features as parallel arrays (chrom strings WITH the `chr`
-    prefix).  A = [address, address + 1).  -> list of (locus index, feature row)."""
+def bedtools_bin(start, end):
+    """UCSC binning scheme as bedtools keeps its B file in (bedtools2 src/utils/bedFile/bedFile.h: _binFirstShift = 14,
+    _binNextShift = 3, _binLevels = 7; getBin): (level, bin number inside the level) of the smallest bin containing
+    [start, end - 1]."""
+    s, e = start >> 14, (max(end, start + 1) - 1) >> 14
+    level = 0
+    while level < 6 and s != e:
+        s >>= 3
+        e >>= 3
+        level += 1
+    return level, s
+
+
+def window_bed(positions, feat_chrom, feat_start, feat_end, window, bed_index=None):
+    """`bedtools window -w W -a A -b B` restated (bedtools2 windowBed.cpp BedWindow::FindWindowOverlaps + bedFile.cpp
+    BedFile::allHits).  positions: list of (chrom, address) or None = the A records in file order, A = [address,
+    address + 1) widened by W on both sides (start clamped at 0); features as parallel arrays (chrom strings WITH the
+    `chr` prefix) = the B records, bed_index[row] = line number of the feature in the B file (default: row order).
+    A B record is reported iff min(a.end', b.end) - max(a.start', b.start) > 0.  ORDER of the B records of one A record:
+    allHits walks the bin levels from the finest (16 kb) upwards, the bins of a level in ascending order and the
+    records of a bin in B-file order, i.e. ascending (level, bin, line) -- a feature straddling a 16 kb boundary is
+    reported after every finer-bin feature of the window.  The order matters: it is the order of the map file's lines,
+    hence of the permutation's promoters (1-make-network.py:131-177) and of quirk Q1's skipped column.
+    UNPINNED: no bedtools binary in the build image; restated from the published source.  -> list of (locus index,
+    feature row)."""
     feat_chrom = np.asarray(feat_chrom)
     feat_start = np.asarray(feat_start, dtype=np.int64)
     feat_end = np.asarray(feat_end, dtype=np.int64)
+    if bed_index is None:
+        bed_index = np.arange(len(feat_start))
     out = []
     for k, p in enumerate(positions):
         if p is None:
@@ -129,8 +157,10 @@ def window_bed(positions, feat_chrom, feat_start, feat_end, window):
         a0 = max(0, a - window)
         a1 = a + 1 + window
         ok = (feat_chrom == chrom) & (feat_end > a0) & (feat_start < a1)
-        for r in np.nonzero(ok)[0]:
-            out.append((k, int(r)))
+        rows = [int(r) for r in np.nonzero(ok)[0]]
+        rows.sort(key=lambda r: bedtools_bin(int(feat_start[r]), int(feat_end[r])) + (int(bed_index[r]), r))
+        for r in rows:
+            out.append((k, r))
     return out
 
 

@@ -54,7 +54,7 @@ def test_library_is_sm100a_tensor_core_code():
 
 def test_abi_version_and_params_layout(lib):
     from coexpression_b200._lib import CoexParams
-    assert lib.coex_abi_version() == 1
+    assert lib.coex_abi_version() == 2
     assert ctypes.sizeof(CoexParams) == 48          # 6 ints + 2 doubles + 1 long long, no padding surprises
     assert CoexParams.pval_to_join.offset == 24 and CoexParams.soft_separation.offset == 40
 

@@ -161,7 +161,7 @@ def test_network_golden_dp4a(name):
 
 
 @pytest.mark.parametrize("name", ["spearman_default", "spearman_anticor", "spearman_useavg_m"])
-@pytest.mark.parametrize("count_mode", ["per_query", "dedup_window", "row_rank", "dedup_split"])
+@pytest.mark.parametrize("count_mode", ["per_query", "row_rank"])
 def test_network_golden_other_count_kernels(name, count_mode):
     _run_case(name, "tcgen05", count_mode)
 
@@ -489,11 +489,11 @@ def test_properties_at_scale_and_cross_implementation():
         ctx.set_global_list(np.sort(np.where(np.isnan(g), -99.0, g)))
         ctx.set_features(t.chrom, t.start, t.end, t.names)
         out = {}
-        for mode in ("dedup", "per_query", "dedup_window", "row_rank", "dedup_split"):
+        for mode in ("dedup", "per_query", "row_rank"):
             ctx.set_count_mode(mode)
             out[mode] = ctx.network_batch(hits, Options(anticorrelation=True), want_scores=True, want_counts=True)
         a = out["dedup"]
-        for other in ("per_query", "dedup_window", "row_rank", "dedup_split"):
+        for other in ("per_query", "row_rank"):
             b = out[other]
             assert np.array_equal(a.counts, b.counts), other
             assert np.array_equal(a.scores, b.scores), other
@@ -651,12 +651,12 @@ def test_large_hit_set_shared_memory_limits():
         g = ctx.pairs(ga, gb, ranked=True)
         ctx.set_global_list(np.sort(np.where(np.isnan(g), -99.0, g)))
         ctx.set_features(t.chrom, t.start, t.end, t.names)
-        for mode in ("dedup", "per_query", "dedup_window", "row_rank", "dedup_split"):
+        for mode in ("dedup", "per_query", "row_rank"):
             ctx.set_count_mode(mode)
             out[mode] = ctx.network_batch(hits, Options(pval_to_join=0.01), want_scores=True, want_counts=True)
     a = out["dedup"]
     assert int(a.n_groups[0]) > 100
-    for other in ("per_query", "dedup_window", "row_rank", "dedup_split"):
+    for other in ("per_query", "row_rank"):
         b = out[other]
         assert np.array_equal(a.counts, b.counts), other
         assert np.array_equal(a.scores, b.scores), other

@@ -164,3 +164,55 @@ def test_gpu_mapped_sets_feed_the_network_batch():
         b = ctx.network_batch(want, Options())
     assert np.array_equal(a.group_density, b.group_density) and np.array_equal(a.n_groups, b.n_groups)
     assert sum(len(h) for h in hits) > 50
+
+
+def test_window_bed_reports_in_bedtools_bin_order():
+    """`bedtools window` walks the UCSC bins from the finest level up: a feature straddling a 16 kb boundary sits in a
+    coarser bin and is reported AFTER the finer-bin features behind it, and features of one bin come in B-file order."""
+    assert po.bedtools_bin(0, 10) == (0, 0) and po.bedtools_bin(16383, 16384) == (0, 0)
+    assert po.bedtools_bin(16380, 16390) == (1, 0)            # straddles the first 16 kb boundary -> 128 kb level
+    assert po.bedtools_bin(131070, 131080) == (2, 0)          # straddles a 128 kb boundary -> 1 Mb level
+    assert po.bedtools_bin(16384, 16400) == (0, 1)
+    fc = ["chr1"] * 5
+    fs = [16000, 16380, 16390, 16500, 40000]
+    fe = [16010, 16390, 16400, 16510, 40010]
+    pairs = po.window_bed([("chr1", 16395)], fc, fs, fe, 1000)
+    # level 0: bin 0 -> row 0, bin 1 -> rows 2, 3; level 1: row 1 (straddler)
+    assert pairs == [(0, 0), (0, 2), (0, 3), (0, 1)]
+    # B-file order inside a bin: the BED lists row 3 before row 2
+    pairs = po.window_bed([("chr1", 16395)], fc, fs, fe, 1000, bed_index=[0, 1, 3, 2, 4])
+    assert pairs == [(0, 0), (0, 3), (0, 2), (0, 1)]
+    # a wide window reaches the next bin of level 0 before any coarser level
+    pairs = po.window_bed([("chr1", 16395)], fc, fs, fe, 30000)
+    assert pairs == [(0, 0), (0, 2), (0, 3), (0, 4), (0, 1)]
+
+
+@pytest.mark.gpu
+def test_gpu_window_order_follows_the_bed_file():
+    """coex_set_feature_order: the B file lists the features in another order than the table; promoters of a locus come
+    out by (UCSC-bin level, bin, B-file line) as `bedtools window` reports them.  Long features (some straddling 16 kb
+    bin boundaries) make the coarser levels matter."""
+    from coexpression_b200.api import CoexContext
+    t, chromlist, cr, snps, rng = _synthetic_inputs(21, N=6000)
+    start = t.start.copy()
+    end = t.end.copy()
+    wide = rng.random(t.N) < 0.3
+    end[wide] = start[wide] + rng.integers(2000, 40000, size=int(wide.sum()))
+    bed_index = rng.permutation(t.N).astype(np.int32)
+    levels = {po.bedtools_bin(int(s), int(e))[0] for s, e in zip(start, end)}
+    assert len(levels) >= 3
+    shifts = [0] + [int(rng.random() * 10000000000) for _ in range(5)]
+    with CoexContext() as ctx:
+        ctx.set_expression(t.X); ctx.prepare()
+        ctx.set_features(t.chrom, start, end, t.names)
+        got_default = ctx.permute_map("circular", [c for c, _ in snps], [a for _, a in snps], shifts, chromlist, cr, 20000)
+        ctx.set_feature_order(bed_index)
+        got = ctx.permute_map("circular", [c for c, _ in snps], [a for _, a in snps], shifts, chromlist, cr, 20000)
+    differs = False
+    for k, s in enumerate(shifts):
+        pos = po.circular_positions(snps, s, cr, chromlist)
+        assert got_default[k].tolist() == po.hit_rows(po.window_bed(pos, t.chrom, start, end, 20000)), k
+        assert got[k].tolist() == po.hit_rows(po.window_bed(pos, t.chrom, start, end, 20000, bed_index=bed_index)), k
+        differs |= got[k].tolist() != got_default[k].tolist()
+        assert sorted(got[k].tolist()) == sorted(got_default[k].tolist())
+    assert differs
