@@ -31,7 +31,8 @@ constexpr int kDdBuckets = 8192;         // coarse buckets of [-R, R]: the count
 constexpr int kDdSub = 16;               // each coarse bucket is cut into 16 sub-buckets: 131072 "virtual" buckets whose occupancy is two
                                          // 16-bit masks in the coarse bucket's table entry (>= 1 statistic / >= 2 statistics)
 constexpr int kDdFine = kDdBuckets * kDdSub;
-constexpr int kDdQueue = 2048;
+constexpr int kDdQueue = 512;            // columns waiting for the exact (double) refinement; overflow is refined in place
+constexpr int kDdWarpQueue = 48;         // per warp: streamed values off the fast route, resolved 32 at a time
 constexpr int kRankTcap = 8192;          // columns ranked per work item in row-rank mode
 constexpr float kDdDelta = 5e-7f;        // |v32 - v64| <= 3e-7 |v|, |t32 - t64| <= 6e-8 |t|  
 constexpr int kDdSuper = 32768;          // columns streamed between two drains of the refinement queue (multiple of 4 * kDdThreads)
@@ -170,7 +171,8 @@ count_dedup_kernel(DedupArgs a) {
     unsigned int *hist = reinterpret_cast<unsigned int *>(thr32 + a.Tcap + 3);
     uint2 *lut = reinterpret_cast<uint2 *>(hist + a.Tcap + 4);              // [kDdBuckets + 2] table entries (8-byte aligned: Qcap * 8 + (Tcap + 4) * 8 bytes in front)
     unsigned int *cursor = reinterpret_cast<unsigned int *>(thr32 - 1);   // bucket cursors alias thr32|hist (both dead until step C; 2*Tcap >= buckets)
-    int *queue = reinterpret_cast<int *>(lut + kDdBuckets + 2);
+    uint2 *slowq = lut + kDdBuckets + 2;                                   // [kDdThreads / 32][kDdWarpQueue]
+    int *queue = reinterpret_cast<int *>(slowq + (kDdThreads / 32) * kDdWarpQueue);
     long long *q_sc = reinterpret_cast<long long *>(queue + kDdQueue);   // [Qcap] offset of the query's score row
     int *q_i = reinterpret_cast<int *>(q_sc + a.Qcap);                     // [Qcap] hit position
     int *q_off = q_i + a.Qcap;                   // [Qcap] offset of the query's permutation in hit_rows
@@ -439,10 +441,50 @@ count_dedup_kernel(DedupArgs a) {
         // double arithmetic is drained by the whole CTA after each of them (a long row of a zero-inflated table holds
         // thousands of values TIED with a statistic, far more than one queue; refining them in place -- one lane's
         // double division at a time -- is what it used to cost).
+        const int lane = tid & 31;
+        const unsigned int lane_lt = (1u << lane) - 1u;
+        uint2 *myq = slowq + (tid >> 5) * kDdWarpQueue;          // this warp's queue of (float value, column)
+        int wq = 0;                                              // its fill (warp-uniform)
+        // General route of one streamed value: float search among the statistics of its coarse bucket, then its two
+        // neighbours in the sorted statistics decide -- closer than tol: the column is redone in double (phase E).
+        auto resolve_slow = [&](float v, int c) {
+            const int bv = dd_bucket32(v, bscale_f);
+            int pp = (int)(lut[bv].x & kDdStartMask);
+            int ln = (int)(lut[bv + 1].x & kDdStartMask) - pp;
+            while (ln > 0) {                                     // statistics <= v inside the coarse bucket
+                const int half = ln >> 1;
+                if (thr32[pp + half] <= v) { pp += half + 1; ln -= half + 1; } else ln = half;
+            }
+            // sentinels -inf / +inf at both ends
+            const float tol = PEARSON ? dd_delta(v) + eps_u + a.eps_row[c] : dd_delta(v);
+            if (fminf(v - thr32[pp - 1], thr32[pp] - v) >= tol) {
+                atomicAdd(&hist[pp], 1u);
+            } else {
+                const int slot = atomicAdd(&s_qn, 1);
+                if (slot < kDdQueue) {
+                    queue[slot] = c;
+                } else {                                          // queue full: refine in place
+                    const double vv = PEARSON ? pearson_exact_thread(a, u, c)
+                                              : __ddiv_rn(0.25 * (double)srow[c], __dmul_rn(sxu, a.sx[c]));
+                    const int b2 = dd_bucket(vv, bscale_f);
+                    int p2 = (int)(lut[b2].x & kDdStartMask);
+                    int l2 = (int)(lut[b2 + 1].x & kDdStartMask) - p2;
+                    while (l2 > 0) {
+                        const int half = l2 >> 1;
+                        if (srt[p2 + half].r <= vv) { p2 += half + 1; l2 -= half + 1; } else l2 = half;
+                    }
+                    atomicAdd(&hist[p2], 1u);
+                }
+            }
+        };
         for (long long cb = 0; cb < N; cb += kDdSuper) {
             const long long cend = (cb + kDdSuper < N) ? cb + kDdSuper : N;
-            long long c0 = cb + (long long)tid * 4;
-            bool have = c0 < cend;
+            // A warp walks its 128-column blocks together (the queue bookkeeping below votes with the full warp): the loop
+            // condition is the block's first column; lanes past the table's last column read the zero padding of the strip
+            // and of the norms (ld = N_pad, a multiple of 256), whose mask 0 keeps them out.
+            long long cw = cb + (long long)(tid >> 5) * 128;
+            long long c0 = cw + (long long)lane * 4;
+            bool have = cw < cend;
             int4 s4n = make_int4(0, 0, 0, 0);
             float4 w4n = make_float4(0.f, 0.f, 0.f, 0.f);
             auto fetch = [&](long long cpos) {
@@ -455,95 +497,53 @@ count_dedup_kernel(DedupArgs a) {
                 const int sv[4] = {s4n.x, s4n.y, s4n.z, s4n.w};
                 const float wv[4] = {w4n.x, w4n.y, w4n.z, w4n.w};
                 const long long cc = c0;
-                const unsigned int skip4 = a.bm_words ? (bitmap[cc >> 5] >> (cc & 31)) & 15u : 0u;   // cc % 4 == 0
+                const unsigned int skip4 = (a.bm_words && cc < N) ? (bitmap[cc >> 5] >> (cc & 31)) & 15u : 0u;   // cc % 4 == 0
                 c0 += kDdThreads * 4;
-                have = c0 < cend;
+                cw += kDdThreads * 4;
+                have = cw < cend;
                 if (have) fetch(c0);
-                float v[4];
-                int p[4], len[4];
-                unsigned int mid4 = 0u, slow4 = 0u;                       // per slot: resolved by its three neighbours / needs the search loop
-                float tlo[4], thi[4];                                     // the value's two neighbours among the sorted statistics
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     // zero-variance column (and the padding behind column N): mask 0 -> -99, counted in bulk; hit column:
                     // accounted exactly in step C'
                     const bool act = (wv[e] != 0.0f) && !((skip4 >> e) & 1u);
-                    v[e] = PEARSON ? __int_as_float(sv[e]) : __int2float_rn(sv[e]) * (iu * wv[e]);
-                    const unsigned int fi = min(__float2uint_rz(__fmaf_rn(v[e], bscale_f, (float)(kDdFine / 2))), (unsigned int)(kDdFine - 1));
+                    const float v = PEARSON ? __int_as_float(sv[e]) : __int2float_rn(sv[e]) * (iu * wv[e]);
+                    const unsigned int fi = min(__float2uint_rz(__fmaf_rn(v, bscale_f, (float)(kDdFine / 2))), (unsigned int)(kDdFine - 1));
                     const uint2 ent = lut[fi >> 4];                       // (negative / NaN -> 0: the conversion saturates)
-                    const unsigned int sub = fi & 15u, below = (1u << sub) - 1u;
-                    // statistics of the lower virtual buckets: exact unless a lower sub-bucket holds two (then BUSY is set)
-                    p[e] = (int)(ent.x & kDdStartMask) + __popc(ent.y & below);
-                    len[e] = 0;
-                    tlo[e] = thi[e] = 0.0f;
-                    if (act) {
-                        // FAST: no statistic in the value's virtual bucket nor in the two next to it.  A virtual bucket is >= 10 x
-                        // wider than the float error of a value (Spearman: 5e-7 |v| against 2R / 131072 >= 5.7e-6 |v|_max; Pearson
-                        // columns with a large digit error are sent to the other branches), so no statistic is within the error
-                        // of v, dd_fine32 is monotone, and the statistics <= v64 are exactly those of the lower virtual buckets.
-                        const bool busy = ((ent.y >> 16) >> sub) & 1u;
-                        if (!busy && (!PEARSON || wv[e] + eps_u <= pearson_fast_eps)) {
-                            atomicAdd(&hist[p[e]], 1u);
-                        } else if (((ent.x >> 16) & (below | (1u << sub))) == 0u) {
-                            // at most ONE statistic in the value's virtual bucket and none doubled below: p[e] is exact up to that
-                            // statistic; it and the two around it are three independent loads (no search)
-                            mid4 |= 1u << e;
-                            const float t0 = thr32[p[e] - 1], t1 = thr32[p[e]];
-                            const float t2 = ((ent.y >> sub) & 1u) ? thr32[p[e] + 1] : CUDART_INF_F;
-                            const bool up = ((ent.y >> sub) & 1u) && t1 <= v[e];              // the bucket's own statistic is <= v
-                            p[e] += up ? 1 : 0;
-                            tlo[e] = up ? t1 : t0;
-                            thi[e] = up ? t2 : t1;
-                        } else {
-                            slow4 |= 1u << e;
-                            p[e] = (int)(ent.x & kDdStartMask);
-                            len[e] = (int)(lut[(fi >> 4) + 1].x & kDdStartMask) - p[e];
+                    const unsigned int sub = fi & 15u;
+                    // FAST: no statistic in the value's virtual bucket nor in the two next to it, none doubled below it in the
+                    // coarse bucket (BUSY clear).  A virtual bucket is >= 10 x wider than the float error of a value (Spearman:
+                    // 5e-7 |v| against 2R / 131072; Pearson columns with a large digit error take the other route), so no
+                    // statistic is within the error of v, dd_fine32 is monotone, and the statistics <= v64 are exactly those of
+                    // the lower virtual buckets: first statistic of the coarse bucket + occupied lower sub-buckets.
+                    bool slow = ((ent.y >> 16) >> sub) & 1u;
+                    if (PEARSON) slow = slow || (wv[e] + eps_u > pearson_fast_eps);
+                    if (act && !slow) atomicAdd(&hist[(ent.x & kDdStartMask) + __popc(ent.y & ((1u << sub) - 1u))], 1u);
+                    slow = slow && act;
+                    // everything else goes to the warp's queue and is resolved by whole warps (drain_slow): one lane's search
+                    // loop must not stall the 31 lanes on the fast route
+                    const unsigned int m = __ballot_sync(0xffffffffu, slow);
+                    if (m) {
+                        const int at = wq + __popc(m & lane_lt);
+                        if (slow) {
+                            if (at < kDdWarpQueue) myq[at] = make_uint2(__float_as_uint(v), (unsigned int)(cc + e));
+                            else resolve_slow(v, (int)(cc + e));
                         }
+                        wq = min(wq + __popc(m), kDdWarpQueue);
                     }
                 }
-                while ((len[0] | len[1] | len[2] | len[3]) > 0) {         // statistics <= v inside the coarse bucket (rare)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        if (len[e] > 0) {
-                            const int half = len[e] >> 1;
-                            if (thr32[p[e] + half] <= v[e]) { p[e] += half + 1; len[e] -= half + 1; } else len[e] = half;
-                        }
-                    }
+                if (wq >= 32) {
+                    __syncwarp();
+                    for (int i = lane; i < wq; i += 32) { const uint2 q = myq[i]; resolve_slow(__uint_as_float(q.x), (int)q.y); }
+                    __syncwarp();
+                    wq = 0;
                 }
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    if (!(((mid4 | slow4) >> e) & 1u)) continue;
-                    // a statistic closer than tol cannot be ordered in float: the two neighbours of v in the sorted
-                    // statistics decide (sentinels -inf / +inf at both ends)
-                    float below, above;
-                    if ((slow4 >> e) & 1u) {
-                        below = v[e] - thr32[p[e] - 1];
-                        above = thr32[p[e]] - v[e];
-                    } else {
-                        below = v[e] - tlo[e];
-                        above = thi[e] - v[e];
-                    }
-                    const float tol = PEARSON ? dd_delta(v[e]) + eps_u + wv[e] : dd_delta(v[e]);
-                    if (fminf(below, above) >= tol) {
-                        atomicAdd(&hist[p[e]], 1u);
-                    } else {
-                        const int slot = atomicAdd(&s_qn, 1);
-                        if (slot < kDdQueue) {
-                            queue[slot] = (int)(cc + e);
-                        } else {                                          // queue full: refine in place
-                            const double vv = PEARSON ? pearson_exact_thread(a, u, cc + e)
-                                                      : __ddiv_rn(0.25 * (double)srow[cc + e], __dmul_rn(sxu, a.sx[cc + e]));
-                            const int bv = dd_bucket(vv, bscale_f);
-                            int pp = (int)(lut[bv].x & kDdStartMask);
-                            int ln = (int)(lut[bv + 1].x & kDdStartMask) - pp;
-                            while (ln > 0) {
-                                const int half = ln >> 1;
-                                if (srt[pp + half].r <= vv) { pp += half + 1; ln -= half + 1; } else ln = half;
-                            }
-                            atomicAdd(&hist[pp], 1u);
-                        }
-                    }
-                }
+            }
+            if (wq > 0) {
+                __syncwarp();
+                for (int i = lane; i < wq; i += 32) { const uint2 q = myq[i]; resolve_slow(__uint_as_float(q.x), (int)q.y); }
+                __syncwarp();
+                wq = 0;
             }
             __syncthreads();
             // ---- E. exact refinement of the queued columns ------------------------------------------
@@ -717,7 +717,7 @@ __global__ void icol_kernel(const double *__restrict__ sx, const unsigned char *
 
 inline size_t dedup_smem_bytes(int Tcap, int Qcap, int bm_words, int claim) {
     return (size_t)Qcap * 8 + (size_t)(Tcap + 4) * 4 + (size_t)(Tcap + 4) * 4 + (size_t)(kDdBuckets + 2) * 8 +
-           (size_t)kDdQueue * 4 + (size_t)Qcap * 8 + (size_t)Qcap * 4 * 3 + (size_t)(Qcap + 2) * 4 + (size_t)bm_words * 4 * (claim ? 2 : 1) + 16;
+           (size_t)kDdQueue * 4 + (size_t)(kDdThreads / 32) * kDdWarpQueue * 8 + (size_t)Qcap * 8 + (size_t)Qcap * 4 * 3 + (size_t)(Qcap + 2) * 4 + (size_t)bm_words * 4 * (claim ? 2 : 1) + 16;
 }
 
 }  // namespace coex
