@@ -182,12 +182,9 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     std::vector<long long> strip_item_begin((size_t)n_strips + 1);
     COEX_CUDA(cudaMemcpyAsync(strip_item_begin.data(), c->pl_bounds.p, ((size_t)n_strips + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
     c->launches += 7;
-    // hit-column bitmap (the hit columns' values ARE statistics: accounted exactly in phase C' and skipped by the streaming pass).  On a
-    // long table it would cost the second resident CTA (8 KB at 65536 rows) while the hit columns are a vanishing share of the row:
-    // there they take the ordinary route (flagged virtual bucket -> float tie with their own statistic -> exact refinement).
-    // Pearson null: a hit column's value is not its (Spearman) statistic.  Row-rank mode ranks EVERY column of a run, so it keeps the bitmap.
-    const int bm_words = (!pearson && N <= 65536) ? (int)((N + 31) / 32) : 0;
-    const int bm_words_rank = (!pearson && N <= 262144) ? (int)((N + 31) / 32) : 0;
+    // hit-column bitmap (<= 32 KB: two CTAs per SM stay resident); Pearson null: a hit column's value is not its (Spearman) statistic
+    const int bm_words = (!pearson && N <= 262144) ? (int)((N + 31) / 32) : 0;
+    const int bm_words_rank = bm_words;
     if (tdbg) fprintf(stderr, "[coex host] dedupe plan (device): %.0f us on the host incl. one sync (H=%lld U=%lld)\n", now_us() - t_start, H, U);
     const int claim = (bm_words > 0 && bm_words <= 2048) ? 1 : 0;      // <= 8 KB for the second bitmap
     const size_t smem = dedup_smem_bytes(Tcap, Qcap, bm_words, claim);
@@ -526,6 +523,14 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
     COEX_CUDA(cudaMemcpyAsync(c->d_warp_off.p, warp_off.data(), (K + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
     na.warp_off = c->d_warp_off.p;
     const unsigned rs_blocks = (unsigned)((warp_off[K] + kRsWarps - 1) / kRsWarps), rs_threads = kRsWarps * 32;
+    auto pass2_round = [&](bool last) -> int {
+        net_rowsum_kernel<1><<<rs_blocks, rs_threads, 0, st>>>(na);
+        COEX_KCHECK(st);
+        if (last) COEX_CUDA(cudaMemsetAsync(na.w_flags, 0, sizeof(int), st));
+        net_commit_kernel<<<K, 256, 0, st>>>(na, 0);
+        COEX_KCHECK(st);
+        return 0;
+    };
     auto density_tail = [&]() -> int {
         const size_t rsmem = (size_t)T2max * 8;
         net_rowsum_kernel<4><<<rs_blocks, rs_threads, 0, st>>>(na);      // allpromoterscores against the final winners
@@ -539,6 +544,7 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
         COEX_KCHECK(st);
         return 0;
     };
+    const int kRounds = 12;
     long long net_launches = 0;
     if (H > 0) {
         const size_t gsmem = (size_t)T2max * 24, lsmem = (size_t)T2max * 16;
@@ -556,10 +562,9 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
         COEX_KCHECK(st);
         net_commit_kernel<<<K, 256, 0, st>>>(na, 1);
         COEX_KCHECK(st);
-        net_pass2_kernel<<<K, kP2Warps * 32, 0, st>>>(na);          // every permutation iterates its own pass 2 to the fixed point
-        COEX_KCHECK(st);
+        for (int r = 0; r < kRounds; ++r) COEX_TRY(pass2_round(r == kRounds - 1));
         COEX_TRY(density_tail());
-        net_launches = 6 + (prm->noiter ? 4 : 5);
+        net_launches = 5 + 2 * kRounds + (prm->noiter ? 4 : 5);
         COEX_TRY(stage_end(c, net_launches));
     } else {
         COEX_CUDA(cudaMemsetAsync(d_ng, 0, K * sizeof(int), st));
@@ -576,6 +581,28 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
     }
     // perm_off / sc_off staging copies read host memory that dies with this frame
     COEX_CUDA(cudaStreamSynchronize(st));
+    if (H > 0) {
+        // pass 2 is a fixed-point iteration: kRounds rounds were queued without looking; in the rare
+        // case that some permutation was still moving, iterate to convergence and redo the tail.
+        int flag = 0;
+        COEX_CUDA(cudaMemcpy(&flag, na.w_flags, sizeof(int), cudaMemcpyDeviceToHost));
+        if (flag) {
+            for (int guard = 0; flag && guard < 8192 + 2; ++guard) {
+                COEX_TRY(pass2_round(true));
+                c->launches += 2;
+                COEX_CUDA(cudaStreamSynchronize(st));
+                COEX_CUDA(cudaMemcpy(&flag, na.w_flags, sizeof(int), cudaMemcpyDeviceToHost));
+            }
+            COEX_TRY(density_tail());
+            c->launches += 5;
+            if (!on_device) {
+                COEX_CUDA(cudaMemcpyAsync(group_winner, d_win, H * sizeof(int), cudaMemcpyDeviceToHost, st));
+                COEX_CUDA(cudaMemcpyAsync(group_density, d_dens, H * sizeof(double), cudaMemcpyDeviceToHost, st));
+                COEX_CUDA(cudaMemcpyAsync(hit_score, d_aps, H * sizeof(double), cudaMemcpyDeviceToHost, st));
+            }
+            COEX_CUDA(cudaStreamSynchronize(st));
+        }
+    }
     if (prm->use_specific_p && (c->gemm_mode == 0 || prm->measure == 1)) COEX_TRY(tc_check_error(c));   // (-cm Pearson runs the tcgen05 digit GEMM in every gemm mode)
     return 0;
 }

@@ -27,12 +27,8 @@
 namespace coex {
 
 constexpr int kDdThreads = 512;
-constexpr int kDdBuckets = 8192;         // coarse buckets of [-R, R]: the counting sort of the statistics and the search window of a value
-constexpr int kDdSub = 16;               // each coarse bucket is cut into 16 sub-buckets: 131072 "virtual" buckets whose occupancy is two
-                                         // 16-bit masks in the coarse bucket's table entry (>= 1 statistic / >= 2 statistics)
-constexpr int kDdFine = kDdBuckets * kDdSub;
-constexpr int kDdQueue = 512;            // columns waiting for the exact (double) refinement; overflow is refined in place
-constexpr int kDdWarpQueue = 48;         // per warp: streamed values off the fast route, resolved 32 at a time
+constexpr int kDdBuckets = 8192;
+constexpr int kDdQueue = 2048;
 constexpr int kRankTcap = 8192;          // columns ranked per work item in row-rank mode
 constexpr float kDdDelta = 5e-7f;        // |v32 - v64| <= 3e-7 |v|, |t32 - t64| <= 6e-8 |t|  
 constexpr int kDdSuper = 32768;          // columns streamed between two drains of the refinement queue (multiple of 4 * kDdThreads)
@@ -116,24 +112,11 @@ __device__ __forceinline__ double pearson_exact_thread(const DedupArgs &a, long 
 // both for the float compare of the fast path and for the double compare of the refinement: the statistics <= v are
 // all the statistics of the lower buckets plus some of v's OWN bucket -- a one-bucket search window with no
 // "off by one bucket in float" case.
-// `scale` is the scale of the VIRTUAL buckets (kDdFine / 2R); the coarse bucket is the virtual one >> 4, so one monotone
-// function places statistics and values at both levels.
-__device__ __forceinline__ int dd_fine32(float x, float scale) {
-    const int b = __float2int_rz(__fmaf_rn(x, scale, (float)(kDdFine / 2)));
-    return min(max(b, 0), kDdFine - 1);
+__device__ __forceinline__ int dd_bucket32(float x, float scale) {
+    const int b = __float2int_rz(__fmaf_rn(x, scale, (float)(kDdBuckets / 2)));
+    return min(max(b, 0), kDdBuckets - 1);
 }
-__device__ __forceinline__ int dd_fine(double t, float scale) { return dd_fine32(__double2float_rn(t), scale); }
-__device__ __forceinline__ int dd_bucket32(float x, float scale) { return dd_fine32(x, scale) >> 4; }
-__device__ __forceinline__ int dd_bucket(double t, float scale) { return dd_fine(t, scale) >> 4; }
-// table entry of a coarse bucket while the statistics are sorted: .x = first statistic of the bucket (their number during the
-// counting pass), .y = sub-buckets holding >= 1 statistic (low half) | sub-buckets holding >= 2 statistics (high half).
-// FINAL form (dd_finish_table), what the streaming pass reads with ONE 8-byte load per value:
-//   .x = first statistic (14 bits) | sub-buckets holding >= 2 statistics << 16
-//   .y = OCC: sub-buckets holding >= 1 statistic | BUSY << 16: sub-buckets that hold a statistic, or whose neighbour sub-bucket
-//        (also across the coarse bucket's edges) does, or that lie at or above a sub-bucket with >= 2 statistics
-// the number of statistics of bucket b is lut[b + 1].x - lut[b].x (lut[kDdBuckets].x = T).
-constexpr unsigned int kDdStartMask = 0x3fffu;
-static_assert(kDdSub == 16, "two 16-bit occupancy masks per table entry");
+__device__ __forceinline__ int dd_bucket(double t, float scale) { return dd_bucket32(__double2float_rn(t), scale); }
 
 // the same for a whole warp: coalesced loads, the products added in order through shuffles (every lane gets the result)
 __device__ __forceinline__ double pearson_exact_warp(const DedupArgs &a, long long ra, long long rb, int lane) {
@@ -163,16 +146,15 @@ __global__ void __launch_bounds__(kDdThreads)
 count_dedup_kernel(DedupArgs a) {
     constexpr bool PEARSON = (MODE == 1), RANKROW = (MODE == 2);
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: q_vi[Qcap] | thr32[Tcap+4] | hist[Tcap+4] (thr32|hist = cursor[B] during step B) | lut[B+2] (8 bytes each) | queue[kDdQueue] | q_k q_i q_toff
+    // layout: q_vi[Qcap] | thr32[Tcap+4] | hist[Tcap+4] (thr32|hist = cursor[B] during step B) | lut[B+4] | queue[kDdQueue] | q_k q_i q_toff
     // (the double statistics and their origins live in an L2-resident per-CTA scratch: they are only
     //  touched by the rare exact refinements and by the final scoring)
     double *q_vi = reinterpret_cast<double *>(smem_raw);                      // [Qcap] exact null value at the skipped column
     float *thr32 = reinterpret_cast<float *>(q_vi + a.Qcap) + 1;             // [-1 .. Tcap+2]: thr32[-1] = -inf, thr32[T] = +inf (sentinels)
     unsigned int *hist = reinterpret_cast<unsigned int *>(thr32 + a.Tcap + 3);
-    uint2 *lut = reinterpret_cast<uint2 *>(hist + a.Tcap + 4);              // [kDdBuckets + 2] table entries (8-byte aligned: Qcap * 8 + (Tcap + 4) * 8 bytes in front)
+    unsigned int *lut = hist + a.Tcap + 4;
     unsigned int *cursor = reinterpret_cast<unsigned int *>(thr32 - 1);   // bucket cursors alias thr32|hist (both dead until step C; 2*Tcap >= buckets)
-    uint2 *slowq = lut + kDdBuckets + 2;                                   // [kDdThreads / 32][kDdWarpQueue]
-    int *queue = reinterpret_cast<int *>(slowq + (kDdThreads / 32) * kDdWarpQueue);
+    int *queue = reinterpret_cast<int *>(lut + kDdBuckets + 4);
     long long *q_sc = reinterpret_cast<long long *>(queue + kDdQueue);   // [Qcap] offset of the query's score row
     int *q_i = reinterpret_cast<int *>(q_sc + a.Qcap);                     // [Qcap] hit position
     int *q_off = q_i + a.Qcap;                   // [Qcap] offset of the query's permutation in hit_rows
@@ -183,7 +165,7 @@ count_dedup_kernel(DedupArgs a) {
     __shared__ unsigned int s_warp[kDdThreads / 32];
 
     const int tid = threadIdx.x;
-    const float bscale_f = (float)((double)kDdFine / (2.0 * a.R));        // scale of the virtual buckets
+    const float bscale_f = (float)((double)kDdBuckets / (2.0 * a.R));
     StatRec *rec_tmp = a.g_rec + (long long)blockIdx.x * 3 * a.Tcap;   // statistic of flat index t
     StatRec *rec_grp = rec_tmp + a.Tcap;                             // grouped by bucket
     StatRec *srt_w = rec_grp + a.Tcap;                               // sorted
@@ -243,7 +225,7 @@ count_dedup_kernel(DedupArgs a) {
             }
         }
         if (tid == 0) { s_T = 0; s_qn = 0; }
-        for (int b = tid; b <= kDdBuckets; b += kDdThreads) lut[b] = make_uint2(0u, 0u);
+        for (int b = tid; b <= kDdBuckets; b += kDdThreads) lut[b] = 0;
         for (int wd = tid; wd < (a.claim ? 2 : 1) * a.bm_words; wd += kDdThreads) bitmap[wd] = 0;
         __syncthreads();
         if (tid == 0) {
@@ -301,12 +283,7 @@ count_dedup_kernel(DedupArgs a) {
                         if (a.counts) a.counts[w] = -1;
                     }
                 } else {
-                    {   // coarse bucket count + occupancy of the statistic's sub-bucket (>= 1 / >= 2 statistics)
-                        const int fi = dd_fine(r, bscale_f);
-                        atomicAdd(&lut[fi >> 4].x, 1u);
-                        const unsigned int bit = 1u << (fi & 15);
-                        if (atomicOr(&lut[fi >> 4].y, bit) & bit) atomicOr(&lut[fi >> 4].y, bit << 16);
-                    }
+                    atomicAdd(&lut[dd_bucket(r, bscale_f)], 1u);
                     // the null value of a hit column IS this statistic (same arithmetic): it is accounted
                     // exactly in step C' and skipped by the float streaming pass
                     if (a.bm_words) {
@@ -324,11 +301,11 @@ count_dedup_kernel(DedupArgs a) {
             unsigned int carry = 0;
             for (int c = 0; c < kPerWarp; c += 32) {
                 const int b = wid * kPerWarp + c + ln;
-                const unsigned int v = lut[b].x;
+                const unsigned int v = lut[b];
                 unsigned int incl = v;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const unsigned int x = __shfl_up_sync(0xffffffffu, incl, o); if (ln >= o) incl += x; }
-                lut[b].x = carry + incl - v;
+                lut[b] = carry + incl - v;
                 carry += __shfl_sync(0xffffffffu, incl, 31);
             }
             if (ln == 0) s_warp[wid] = carry;
@@ -337,10 +314,10 @@ count_dedup_kernel(DedupArgs a) {
             for (int w = 0; w < wid; ++w) base += s_warp[w];
             for (int c = 0; c < kPerWarp; c += 32) {
                 const int b = wid * kPerWarp + c + ln;
-                lut[b].x += base;
+                lut[b] += base;
                 cursor[b] = 0;
             }
-            if (tid == kDdThreads - 1) { lut[kDdBuckets].x = base + carry; s_T = (int)(base + carry); }
+            if (tid == kDdThreads - 1) { lut[kDdBuckets] = base + carry; s_T = (int)(base + carry); }
             __syncthreads();
         }
         // group by bucket
@@ -351,12 +328,15 @@ count_dedup_kernel(DedupArgs a) {
                 int lo = 0, hi = nq;
                 if (!RANKROW) while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (q_toff[mid] <= t) lo = mid; else hi = mid; }
                 const int b = dd_bucket(r, bscale_f);
-                const unsigned int pos = lut[b].x + atomicAdd(&cursor[b], 1u);
+                const unsigned int pos = lut[b] + atomicAdd(&cursor[b], 1u);
                 rec_grp[pos] = StatRec{r, RANKROW ? (unsigned int)t : ((unsigned int)lo << 13) | (unsigned int)(t - q_toff[lo]), x.col};
             }
         }
         __syncthreads();
         T = s_T;
+        // lut[b] = first statistic of bucket b | number of statistics in it << 16 (the cursors have counted them; T <= 8192):
+        // one shared-memory load per streamed value gives its whole search window
+        for (int b = tid; b < kDdBuckets; b += kDdThreads) lut[b] |= cursor[b] << 16;
         __syncthreads();                                    // the cursors (aliasing thr32 | hist) are dead from here on
         DD_PHASE(1);
         if (T == 0) continue;                               // every statistic undefined: scores already written
@@ -364,8 +344,8 @@ count_dedup_kernel(DedupArgs a) {
         for (int e = tid; e < T; e += kDdThreads) {
             const StatRec x = rec_grp[e];
             const double t = x.r;
-            const int bt = dd_bucket(t, bscale_f);
-            const int lo = (int)(lut[bt].x & kDdStartMask), hi = (int)(lut[bt + 1].x & kDdStartMask);
+            const unsigned int pk = lut[dd_bucket(t, bscale_f)];
+            const int lo = (int)(pk & 0xffffu), hi = lo + (int)(pk >> 16);
             int rank = 0;
             for (int m = lo; m < hi; ++m) {
                 const double y = rec_grp[m].r;
@@ -376,17 +356,6 @@ count_dedup_kernel(DedupArgs a) {
         }
         for (int p = tid; p <= T; p += kDdThreads) hist[p] = 0;
         if (tid == 0) { thr32[-1] = -CUDART_INF_F; thr32[T] = CUDART_INF_F; }
-        // final form of the table (see kDdStartMask).  In place: a neighbour's OCC half-word, the only thing read from it, is the
-        // same before and after its own entry is rewritten.
-        for (int b = tid; b < kDdBuckets; b += kDdThreads) {
-            const uint2 e = lut[b];
-            const unsigned int occ = e.y & 0xffffu, multi = e.y >> 16;
-            const unsigned int prev_top = (b > 0) ? (lut[b - 1].y >> 15) & 1u : 0u;
-            const unsigned int next_bot = (b + 1 < kDdBuckets) ? lut[b + 1].y & 1u : 0u;
-            unsigned int busy = occ | (occ << 1) | (occ >> 1) | prev_top | (next_bot << 15);
-            if (multi) busy |= ~((multi & (0u - multi)) - 1u);          // every sub-bucket at or above the lowest one with two statistics
-            lut[b] = make_uint2((e.x & kDdStartMask) | (multi << 16), occ | (busy << 16));
-        }
         __syncthreads();
         }
         // ---- C'. hit columns: value == statistic exactly.  A column hit by several queries of the item appears as
@@ -432,8 +401,6 @@ count_dedup_kernel(DedupArgs a) {
         // ---- D. stream the null values of table row u (fp32 fast path) -----------------------------
         const float iu = (float)(0.5 / sxu);
         const float eps_u = PEARSON ? a.eps_row[u] : 0.0f;
-        // Pearson: the fast branch needs |tensor r - exact r| (<= eps_u + eps_c) well inside a virtual bucket (2R / 131072 wide)
-        const float pearson_fast_eps = (float)(a.R / (double)kDdFine * 0.125);
         const long long N = a.N;
         // Four columns per thread are handled in lockstep (independent shared-memory chains overlap)
         // and the next 16-byte strip / norm loads are issued before the current ones are consumed.
@@ -441,50 +408,10 @@ count_dedup_kernel(DedupArgs a) {
         // double arithmetic is drained by the whole CTA after each of them (a long row of a zero-inflated table holds
         // thousands of values TIED with a statistic, far more than one queue; refining them in place -- one lane's
         // double division at a time -- is what it used to cost).
-        const int lane = tid & 31;
-        const unsigned int lane_lt = (1u << lane) - 1u;
-        uint2 *myq = slowq + (tid >> 5) * kDdWarpQueue;          // this warp's queue of (float value, column)
-        int wq = 0;                                              // its fill (warp-uniform)
-        // General route of one streamed value: float search among the statistics of its coarse bucket, then its two
-        // neighbours in the sorted statistics decide -- closer than tol: the column is redone in double (phase E).
-        auto resolve_slow = [&](float v, int c) {
-            const int bv = dd_bucket32(v, bscale_f);
-            int pp = (int)(lut[bv].x & kDdStartMask);
-            int ln = (int)(lut[bv + 1].x & kDdStartMask) - pp;
-            while (ln > 0) {                                     // statistics <= v inside the coarse bucket
-                const int half = ln >> 1;
-                if (thr32[pp + half] <= v) { pp += half + 1; ln -= half + 1; } else ln = half;
-            }
-            // sentinels -inf / +inf at both ends
-            const float tol = PEARSON ? dd_delta(v) + eps_u + a.eps_row[c] : dd_delta(v);
-            if (fminf(v - thr32[pp - 1], thr32[pp] - v) >= tol) {
-                atomicAdd(&hist[pp], 1u);
-            } else {
-                const int slot = atomicAdd(&s_qn, 1);
-                if (slot < kDdQueue) {
-                    queue[slot] = c;
-                } else {                                          // queue full: refine in place
-                    const double vv = PEARSON ? pearson_exact_thread(a, u, c)
-                                              : __ddiv_rn(0.25 * (double)srow[c], __dmul_rn(sxu, a.sx[c]));
-                    const int b2 = dd_bucket(vv, bscale_f);
-                    int p2 = (int)(lut[b2].x & kDdStartMask);
-                    int l2 = (int)(lut[b2 + 1].x & kDdStartMask) - p2;
-                    while (l2 > 0) {
-                        const int half = l2 >> 1;
-                        if (srt[p2 + half].r <= vv) { p2 += half + 1; l2 -= half + 1; } else l2 = half;
-                    }
-                    atomicAdd(&hist[p2], 1u);
-                }
-            }
-        };
         for (long long cb = 0; cb < N; cb += kDdSuper) {
             const long long cend = (cb + kDdSuper < N) ? cb + kDdSuper : N;
-            // A warp walks its 128-column blocks together (the queue bookkeeping below votes with the full warp): the loop
-            // condition is the block's first column; lanes past the table's last column read the zero padding of the strip
-            // and of the norms (ld = N_pad, a multiple of 256), whose mask 0 keeps them out.
-            long long cw = cb + (long long)(tid >> 5) * 128;
-            long long c0 = cw + (long long)lane * 4;
-            bool have = cw < cend;
+            long long c0 = cb + (long long)tid * 4;
+            bool have = c0 < cend;
             int4 s4n = make_int4(0, 0, 0, 0);
             float4 w4n = make_float4(0.f, 0.f, 0.f, 0.f);
             auto fetch = [&](long long cpos) {
@@ -497,53 +424,60 @@ count_dedup_kernel(DedupArgs a) {
                 const int sv[4] = {s4n.x, s4n.y, s4n.z, s4n.w};
                 const float wv[4] = {w4n.x, w4n.y, w4n.z, w4n.w};
                 const long long cc = c0;
-                const unsigned int skip4 = (a.bm_words && cc < N) ? (bitmap[cc >> 5] >> (cc & 31)) & 15u : 0u;   // cc % 4 == 0
+                const unsigned int skip4 = a.bm_words ? (bitmap[cc >> 5] >> (cc & 31)) & 15u : 0u;   // cc % 4 == 0
                 c0 += kDdThreads * 4;
-                cw += kDdThreads * 4;
-                have = cw < cend;
+                have = c0 < cend;
                 if (have) fetch(c0);
+                float v[4];
+                int p[4], len[4];
+                bool act[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     // zero-variance column (and the padding behind column N): mask 0 -> -99, counted in bulk; hit column:
                     // accounted exactly in step C'
-                    const bool act = (wv[e] != 0.0f) && !((skip4 >> e) & 1u);
-                    const float v = PEARSON ? __int_as_float(sv[e]) : __int2float_rn(sv[e]) * (iu * wv[e]);
-                    const unsigned int fi = min(__float2uint_rz(__fmaf_rn(v, bscale_f, (float)(kDdFine / 2))), (unsigned int)(kDdFine - 1));
-                    const uint2 ent = lut[fi >> 4];                       // (negative / NaN -> 0: the conversion saturates)
-                    const unsigned int sub = fi & 15u;
-                    // FAST: no statistic in the value's virtual bucket nor in the two next to it, none doubled below it in the
-                    // coarse bucket (BUSY clear).  A virtual bucket is >= 10 x wider than the float error of a value (Spearman:
-                    // 5e-7 |v| against 2R / 131072; Pearson columns with a large digit error take the other route), so no
-                    // statistic is within the error of v, dd_fine32 is monotone, and the statistics <= v64 are exactly those of
-                    // the lower virtual buckets: first statistic of the coarse bucket + occupied lower sub-buckets.
-                    bool slow = ((ent.y >> 16) >> sub) & 1u;
-                    if (PEARSON) slow = slow || (wv[e] + eps_u > pearson_fast_eps);
-                    if (act && !slow) atomicAdd(&hist[(ent.x & kDdStartMask) + __popc(ent.y & ((1u << sub) - 1u))], 1u);
-                    slow = slow && act;
-                    // everything else goes to the warp's queue and is resolved by whole warps (drain_slow): one lane's search
-                    // loop must not stall the 31 lanes on the fast route
-                    const unsigned int m = __ballot_sync(0xffffffffu, slow);
-                    if (m) {
-                        const int at = wq + __popc(m & lane_lt);
-                        if (slow) {
-                            if (at < kDdWarpQueue) myq[at] = make_uint2(__float_as_uint(v), (unsigned int)(cc + e));
-                            else resolve_slow(v, (int)(cc + e));
+                    act[e] = (wv[e] != 0.0f) && !((skip4 >> e) & 1u);
+                    v[e] = PEARSON ? __int_as_float(sv[e]) : __int2float_rn(sv[e]) * (iu * wv[e]);
+                    // the statistics <= v are those of the lower buckets and some of v's own bucket (dd_bucket32 is monotone)
+                    const unsigned int pk = lut[dd_bucket32(v[e], bscale_f)];
+                    p[e] = (int)(pk & 0xffffu);
+                    len[e] = act[e] ? (int)(pk >> 16) : 0;
+                }
+                while ((len[0] | len[1] | len[2] | len[3]) > 0) {         // statistics <= v inside the bucket
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (len[e] > 0) {
+                            const int half = len[e] >> 1;
+                            if (thr32[p[e] + half] <= v[e]) { p[e] += half + 1; len[e] -= half + 1; } else len[e] = half;
                         }
-                        wq = min(wq + __popc(m), kDdWarpQueue);
                     }
                 }
-                if (wq >= 32) {
-                    __syncwarp();
-                    for (int i = lane; i < wq; i += 32) { const uint2 q = myq[i]; resolve_slow(__uint_as_float(q.x), (int)q.y); }
-                    __syncwarp();
-                    wq = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (!act[e]) continue;
+                    // a statistic closer than delta cannot be ordered in float: the two neighbours of v in the sorted
+                    // statistics decide (sentinels -inf / +inf at both ends)
+                    const float below = v[e] - thr32[p[e] - 1];
+                    const float above = thr32[p[e]] - v[e];
+                    if (fminf(below, above) >= (PEARSON ? dd_delta(v[e]) + eps_u + wv[e] : dd_delta(v[e]))) {
+                        atomicAdd(&hist[p[e]], 1u);
+                    } else {
+                        const int slot = atomicAdd(&s_qn, 1);
+                        if (slot < kDdQueue) {
+                            queue[slot] = (int)(cc + e);
+                        } else {                                          // queue full: refine in place
+                            const double vv = PEARSON ? pearson_exact_thread(a, u, cc + e)
+                                                      : __ddiv_rn(0.25 * (double)srow[cc + e], __dmul_rn(sxu, a.sx[cc + e]));
+                            const unsigned int pk = lut[dd_bucket(vv, bscale_f)];
+                            int pp = (int)(pk & 0xffffu);
+                            int ln = (int)(pk >> 16);
+                            while (ln > 0) {
+                                const int half = ln >> 1;
+                                if (srt[pp + half].r <= vv) { pp += half + 1; ln -= half + 1; } else ln = half;
+                            }
+                            atomicAdd(&hist[pp], 1u);
+                        }
+                    }
                 }
-            }
-            if (wq > 0) {
-                __syncwarp();
-                for (int i = lane; i < wq; i += 32) { const uint2 q = myq[i]; resolve_slow(__uint_as_float(q.x), (int)q.y); }
-                __syncwarp();
-                wq = 0;
             }
             __syncthreads();
             // ---- E. exact refinement of the queued columns ------------------------------------------
@@ -553,9 +487,9 @@ count_dedup_kernel(DedupArgs a) {
                 const int c = queue[x];
                 const double vv = PEARSON ? pearson_exact_thread(a, u, c)
                                           : __ddiv_rn(0.25 * (double)srow[c], __dmul_rn(sxu, a.sx[c]));
-                const int bv = dd_bucket(vv, bscale_f);
-                int pp = (int)(lut[bv].x & kDdStartMask);
-                int len = (int)(lut[bv + 1].x & kDdStartMask) - pp;
+                const unsigned int pk = lut[dd_bucket(vv, bscale_f)];
+                int pp = (int)(pk & 0xffffu);
+                int len = (int)(pk >> 16);
                 while (len > 0) {
                     const int half = len >> 1;
                     if (srt[pp + half].r <= vv) { pp += half + 1; len -= half + 1; } else len = half;
@@ -716,8 +650,8 @@ __global__ void icol_kernel(const double *__restrict__ sx, const unsigned char *
 }
 
 inline size_t dedup_smem_bytes(int Tcap, int Qcap, int bm_words, int claim) {
-    return (size_t)Qcap * 8 + (size_t)(Tcap + 4) * 4 + (size_t)(Tcap + 4) * 4 + (size_t)(kDdBuckets + 2) * 8 +
-           (size_t)kDdQueue * 4 + (size_t)(kDdThreads / 32) * kDdWarpQueue * 8 + (size_t)Qcap * 8 + (size_t)Qcap * 4 * 3 + (size_t)(Qcap + 2) * 4 + (size_t)bm_words * 4 * (claim ? 2 : 1) + 16;
+    return (size_t)Qcap * 8 + (size_t)(Tcap + 4) * 4 + (size_t)(Tcap + 4) * 4 + (size_t)(kDdBuckets + 4) * 4 +
+           (size_t)kDdQueue * 4 + (size_t)Qcap * 8 + (size_t)Qcap * 4 * 3 + (size_t)(Qcap + 2) * 4 + (size_t)bm_words * 4 * (claim ? 2 : 1) + 16;
 }
 
 }  // namespace coex

@@ -326,12 +326,16 @@ constexpr int kRsWarps = 8;
 constexpr int kRsRows = 4;          // rows per warp: more warps in flight than 32-row blocks
 constexpr int kRsStages = 4;        // register pipeline depth: 32-column chunks of addends in flight per warp
 
-// one warp: kRsRows consecutive row slots (slot i0 = wslot * kRsRows) of permutation k; tile = the warp's kRsRows x 33 doubles
 template <int MODE>
-__device__ __forceinline__ void net_rowsum_warp(const NetArgs &a, int k, int wslot, double *tile) {
-    const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(kRsWarps * 32)
+net_rowsum_kernel(NetArgs a) {
+    __shared__ double tiles[kRsWarps][kRsRows * 33];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long w = (long long)blockIdx.x * kRsWarps + wib;
+    if (w >= a.warp_off[a.K]) return;
     constexpr bool kHitRows = (MODE == 0 || MODE == 1 || MODE == 4);        // rows are hits (else groups)
     constexpr bool kPass2 = (MODE == 1 || MODE == 4);
+    const int k = perm_of(a.warp_off, a.K, w);
     if (MODE == 1 && !a.w_state[k]) return;
     const long long off = a.perm_off[k];
     const int P = (int)(a.perm_off[k + 1] - off);
@@ -339,8 +343,9 @@ __device__ __forceinline__ void net_rowsum_warp(const NetArgs &a, int k, int wsl
     const int G = a.n_groups[k];
     const int nrows = (MODE == 1) ? a.w_actn[k] : (kHitRows ? P : G);
     const int ncols = (MODE == 0) ? P : G;
-    const int i0 = wslot * kRsRows;
+    const int i0 = (int)(w - a.warp_off[k]) * kRsRows;
     if (i0 >= nrows) return;
+    double *tile = tiles[wib];
     const int *grp = a.group_of_hit + off;
     const int *win = a.group_winner + off, *w1 = a.w_pos + off, *vis = a.w_root + off;
     const double *Sc = a.scores + a.sc_off[k];
@@ -439,17 +444,6 @@ __device__ __forceinline__ void net_rowsum_warp(const NetArgs &a, int k, int wsl
     }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kRsWarps * 32)
-net_rowsum_kernel(NetArgs a) {
-    __shared__ double tiles[kRsWarps][kRsRows * 33];
-    const int wib = threadIdx.x >> 5;
-    const long long w = (long long)blockIdx.x * kRsWarps + wib;
-    if (w >= a.warp_off[a.K]) return;
-    const int k = perm_of(a.warp_off, a.K, w);
-    net_rowsum_warp<MODE>(a, k, (int)(w - a.warp_off[k]), tiles[wib]);
-}
-
 // one CTA per permutation: pick and commit the winners.  Pick = argmax with the tie-break of the oracle: among the
 // members reaching the group's best sum (w_best, atomicMax of the row-sum kernel), the smallest name.
 // first != 0: pass-1 winners (w1 + working copy); it also counts the members of every group and lists the hits of
@@ -459,7 +453,9 @@ net_rowsum_kernel(NetArgs a) {
 // W^r[g] = f_g(W^(r-1)[< g], W1[> g]) from W^0 = W1 reaches W* as its unique fixed point; if c is the FIRST group whose
 // winner moved in round r, every group <= c has unchanged inputs in round r + 1 and is final: front[k] = c, the next
 // round only recomputes the groups behind it, and state[k] drops to 0 when nothing moved.
-__device__ __forceinline__ void net_commit_cta(const NetArgs &a, int k, int first) {
+__global__ void __launch_bounds__(256)
+net_commit_kernel(NetArgs a, int first) {
+    const int k = blockIdx.x;
     if (!a.w_state[k]) return;
     const long long off = a.perm_off[k];
     const int P = (int)(a.perm_off[k + 1] - off);
@@ -537,35 +533,6 @@ __device__ __forceinline__ void net_commit_cta(const NetArgs &a, int k, int firs
             a.w_front[k] = c;
             atomicOr(a.w_flags, 1);
         }
-    }
-}
-
-__global__ void __launch_bounds__(256)
-net_commit_kernel(NetArgs a, int first) { net_commit_cta(a, blockIdx.x, first); }
-
-// Pass 2 of ONE permutation per CTA, iterated to its fixed point inside the kernel: a round = ordered row sums of the members of
-// the multi-member groups behind the frontier (net_rowsum_warp<1>, the CTA's warps share the row slots) + pick / commit
-// (net_commit_cta).  The frontier moves by at least one group per round, so G + 1 rounds always suffice; a permutation needs a
-// handful.  Replaces twelve blind (row-sum, commit) launch pairs over ALL permutations (each waiting for the slowest one) and the
-// host loop behind them.
-constexpr int kP2Warps = 16;
-__global__ void __launch_bounds__(kP2Warps * 32)
-net_pass2_kernel(NetArgs a) {
-    __shared__ double tiles[kP2Warps][kRsRows * 33];
-    const int k = blockIdx.x;
-    const long long off = a.perm_off[k];
-    const int P = (int)(a.perm_off[k + 1] - off);
-    if (P < 2) { if (threadIdx.x == 0) a.w_state[k] = 0; return; }
-    const int G = a.n_groups[k];
-    const int wib = threadIdx.x >> 5;
-    for (int round = 0; round <= G + 1; ++round) {
-        __syncthreads();
-        if (!a.w_state[k]) break;                               // uniform: written by thread 0 before the barrier above
-        const int nslots = (a.w_actn[k] + kRsRows - 1) / kRsRows;
-        for (int ws = wib; ws < nslots; ws += kP2Warps) net_rowsum_warp<1>(a, k, ws, tiles[wib]);
-        __threadfence_block();
-        __syncthreads();
-        net_commit_cta(a, k, 0);
     }
 }
 
