@@ -629,20 +629,22 @@ def ctx_n_pad(n):
 
 
 def strong_scaling(env, ctx, args, t, X_dev, opts, one_gpu_ms, dens_one_gpu):
-    """ONE fixed job (rank 0's 101 hit sets) split over the ranks: what runlocal.py:19,78-79 does with processes."""
+    """ONE fixed job (rank 0's 101 hit sets) shared by the ranks -- what runlocal.py:19,78-79 does with processes.  Count stage
+    sharded by table row, edge scores stored into the owning rank's buffer over NVLink inside the count kernel, network stage by
+    permutation (dist.SharedJob); the gathered densities are checked against rank 0 doing the whole list alone."""
     from coexpression_b200 import synth
-    from coexpression_b200.dist import shard_permutations, gather_densities
+    from coexpression_b200.dist import SharedJob, gather_densities
     torch = env.torch
     hits, _, _ = synth.make_permutation_hits(t, args.loci, args.perms, window=args.window, seed=args.seed + 17)   # rank 0's list
-    shards = shard_permutations([len(h) for h in hits], env.world)
-    mine = shards[env.rank]
-    job = DeviceJob(env, ctx, [hits[k] for k in mine])
+    sjob = SharedJob(ctx, hits, env.dev)
+    mine = sjob.mine
     stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=env.dev)
+    last = {}
 
     def step():
         ctx.set_expression_device(X_dev.data_ptr(), t.N, t.n, keepalive=X_dev)
         ctx.prepare()
-        job.run(opts)
+        last["res"] = sjob.run(opts)
 
     for _ in range(max(1, args.warmup)):
         step()
@@ -660,17 +662,21 @@ def strong_scaling(env, ctx, args, t, X_dev, opts, one_gpu_ms, dens_one_gpu):
     dev_ms = env.max_over_ranks(float(np.mean(ms)))
     # the gather (outside the device timing: it is the same single collective as in the weak run) and the check
     w0 = time.perf_counter()
-    allden = gather_densities(mine, job.densities(), len(hits), device=env.dev)
+    dens = [last["res"].perm(j)["density"].copy() for j in range(len(mine))]
+    allden = gather_densities(mine, dens, len(hits), device=env.dev)
     gather_ms = env.max_over_ranks(1e3 * (time.perf_counter() - w0))
     ok = True
     if env.rank == 0:
         ok = all(allden[k] is not None and np.array_equal(allden[k], dens_one_gpu[k]) for k in range(len(hits)))
     ok = env.max_over_ranks(0.0 if ok else 1.0) == 0.0
-    uniq = env.sum_over_ranks(float(np.unique(job.hit_rows).size))
-    out = {"workload": f"the {len(hits)} hit sets of rank 0's C2 job, sharded by dist.shard_permutations (longest P^2 first)",
+    rows = np.unique(np.concatenate(hits))
+    uniq = env.sum_over_ranks(float((rows % env.world == env.rank).sum()))
+    one = env.max_over_ranks(one_gpu_ms)
+    sjob.barrier()
+    out = {"workload": f"the {len(hits)} hit sets of rank 0's C2 job shared by {env.world} GPUs: count stage by table row (row % world), "
+                       "score rows stored into the owner's buffer over NVLink (CUDA IPC peer memory), network stage by permutation",
            "ms_per_step": dev_ms, "permutations_per_sec": len(hits) / (dev_ms * 1e-3),
-           "one_gpu_ms_per_step": env.max_over_ranks(one_gpu_ms),
-           "speedup_vs_one_gpu": env.max_over_ranks(one_gpu_ms) / dev_ms,
+           "one_gpu_ms_per_step": one, "speedup_vs_one_gpu": one / dev_ms,
            "unique_hit_rows_summed_over_ranks": int(uniq),
            "gather_ms_host_clock": gather_ms,
            "gathered_equals_one_gpu_bit_for_bit": bool(ok), "_ok": bool(ok)}
@@ -722,15 +728,31 @@ def full_shape(env, args):
     glist = np.sort(np.where(np.isnan(g), -99.0, g))
     ctx.set_global_list(glist)
     Kall = len(hits)
-    shards = shard_permutations([len(h) for h in hits], world)
-    mine = shards[rank]
-    job = DeviceJob(env, ctx, [hits[k] for k in mine])
     stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=dev)
+    last = {}
+    if world > 1:
+        # ONE job shared by the ranks: count stage by table row, network stage by permutation, score rows stored into the
+        # owner's buffer over NVLink inside the count kernel (include/coexpression_b200.h section 3)
+        from coexpression_b200.dist import SharedJob
+        sjob = SharedJob(ctx, hits, dev)
+        mine = sjob.mine
+        my_rows = np.unique(np.concatenate(hits))
+        my_rows = my_rows[my_rows % world == rank]
+        job = None
 
-    def step():
-        ctx.set_expression_device(X_dev.data_ptr(), N, n, keepalive=X_dev)
-        ctx.prepare()
-        job.run(opts)
+        def step():
+            ctx.set_expression_device(X_dev.data_ptr(), N, n, keepalive=X_dev)
+            ctx.prepare()
+            last["res"] = sjob.run(opts)
+    else:
+        mine = list(range(Kall))
+        job = DeviceJob(env, ctx, hits)
+        my_rows = np.unique(job.hit_rows)
+
+        def step():
+            ctx.set_expression_device(X_dev.data_ptr(), N, n, keepalive=X_dev)
+            ctx.prepare()
+            job.run(opts)
 
     step()                                                   # warm-up (allocations, tensor maps)
     env.barrier()
@@ -760,11 +782,13 @@ def full_shape(env, args):
     dev_ms = env.max_over_ranks(float(np.mean(ms)))
     env.log(f"full shape: {dev_ms:.1f} ms per job")
     w0 = time.perf_counter()
-    dens_mine = job.densities()
+    dens_mine = job.densities() if job is not None else [last["res"].perm(j)["density"].copy() for j in range(len(mine))]
     allden = gather_densities(mine, dens_mine, Kall, device=dev)
     gather_ms = env.max_over_ranks(1e3 * (time.perf_counter() - w0))
-    U_mine = int(np.unique(job.hit_rows).size)
+    U_mine = int(my_rows.size)
     U_sum = env.sum_over_ranks(U_mine)
+    my_perm_off = np.zeros(len(mine) + 1, dtype=np.int64)
+    my_perm_off[1:] = np.cumsum([len(hits[k]) for k in mine])
     per = {s: (stage_tot[s] / args.full_steps, stage_launch[s] / args.full_steps) for s in STAGES}
 
     # ---- e2e through the host-buffer API (one GPU only: pinned table of 2.9 GB + host hit lists) ---------------
@@ -781,7 +805,8 @@ def full_shape(env, args):
             a1 = time.perf_counter()
             w.append(1e3 * (a1 - a0))
         e2e = {"ms": w[-1], "permutations_per_sec": Kall / (w[-1] * 1e-3), "h2d_bytes": int(Xh.nbytes + job.hit_rows.nbytes),
-               "d2h_bytes": int(4 * Kall + 28 * job.H)}
+               "d2h_bytes": int(4 * Kall + 28 * job.H),
+               "api": "CoexContext.set_expression (pinned host table) + prepare + network_batch (host hit lists)"}
         ctx.set_expression_device(X_dev.data_ptr(), N, n, keepalive=X_dev)
         ctx.prepare()
 
@@ -857,7 +882,7 @@ def full_shape(env, args):
         mean_hits = float(np.mean([len(x) for x in hits]))
         pairs_ref = float(sum(len(x) * (N - 1) for x in hits))
         gemm_flops = 2.0 * n * U_mine * N                   # rank 0's strips (the stage times are rank 0's too)
-        count_bytes = 4.0 * U_mine * N + 8.0 * float(np.sum(np.diff(job.perm_off) ** 2))
+        count_bytes = 4.0 * U_mine * N + 8.0 * float(sum(len(x) ** 2 for x in hits)) / world   # (score rows follow the hit rows)
         roof = {}
         if per["corr_gemm"][0] > 0:
             a = gemm_flops / (per["corr_gemm"][0] * 1e-3) / 1e12
@@ -879,7 +904,9 @@ def full_shape(env, args):
         full = {
             "workload": f"north-star target: {N} x {n} synthetic table, {Kall} hit sets (real + {Kall - 1} circular permutations of 500 loci, "
                         f"-w 10000, mean {mean_hits:.0f} hit regions), Spearman, defaults; "
-                        + ("one GPU" if world == 1 else f"ONE job sharded over {world} GPUs by dist.shard_permutations (strong scaling)"),
+                        + ("one GPU" if world == 1 else f"ONE job shared by {world} GPUs (strong scaling): count stage sharded by table row, "
+                           "edge scores stored into the owning rank's buffer over NVLink inside the count kernel, network stage by "
+                           "permutation (dist.SharedJob), one NCCL gather of the densities"),
             "n_gpus": world, "steps": args.full_steps, "warmup": 1,
             "ms": dev_ms, "permutations_per_sec": Kall / (dev_ms * 1e-3),
             "pairs_per_sec_reference_equivalent": pairs_ref / (dev_ms * 1e-3),

@@ -62,6 +62,11 @@ SIGNATURES = {
     "coex_set_pearson": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "coex_network_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(CoexParams), ctypes.c_int] +
                            [ctypes.c_void_p] * 10 + [ctypes.c_int]),
+    "coex_shard_scores_alloc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_ll, ctypes.c_void_p]),
+    "coex_shard_scores_open": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "coex_shard_count": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(CoexParams), ctypes.c_int] + [ctypes.c_void_p] * 4),
+    "coex_shard_finish": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(CoexParams), ctypes.c_int] + [ctypes.c_void_p] * 9 +
+                          [ctypes.c_int]),
     "coex_launch_count": (c_ll, [ctypes.c_void_p]),
     "coex_stage_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
                                      ctypes.POINTER(c_ll)]),

@@ -295,6 +295,56 @@ class CoexContext:
                                           g("group_winner"), g("group_density"), g("hit_score"), g("scores"),
                                           g("counts"), 1), "coex_network_batch")
 
+    # ---- ONE job shared by several GPUs (include/coexpression_b200.h section 3; dist.SharedJob drives these) ----------
+    def shard_scores_alloc(self, world, rank, n_doubles):
+        """-> the 64-byte CUDA IPC handle of this rank's score buffer."""
+        h = (ctypes.c_ubyte * 64)()
+        check(self.lib.coex_shard_scores_alloc(self.h, int(world), int(rank), int(n_doubles), h), "coex_shard_scores_alloc")
+        return bytes(h)
+
+    def shard_scores_open(self, peer_rank, handle):
+        buf = (ctypes.c_ubyte * 64).from_buffer_copy(bytes(handle))
+        check(self.lib.coex_shard_scores_open(self.h, int(peer_rank), buf), "coex_shard_scores_open")
+
+    @staticmethod
+    def _flatten(hit_sets):
+        K = len(hit_sets)
+        perm_off = np.zeros(K + 1, dtype=np.int64)
+        perm_off[1:] = np.cumsum([len(h) for h in hit_sets])
+        H = int(perm_off[-1])
+        hit_rows = (np.concatenate([np.asarray(h, dtype=np.int32) for h in hit_sets]) if H else np.zeros(0, dtype=np.int32))
+        return K, perm_off, np.ascontiguousarray(hit_rows, dtype=np.int32), H
+
+    def shard_count(self, hit_sets_all, options: Options, perm_owner, perm_score_off):
+        """Count stage of THIS rank's table rows over ALL permutations of the job; the score rows are stored into the buffers of
+        the permutations' owners (peer memory)."""
+        K, perm_off, hit_rows, _ = self._flatten(hit_sets_all)
+        owner = np.ascontiguousarray(perm_owner, dtype=np.int32)
+        soff = np.ascontiguousarray(perm_score_off, dtype=np.int64)
+        prm = options.to_params(self.N)
+        check(self.lib.coex_shard_count(self.h, ctypes.byref(prm), K, perm_off.ctypes.data, _ptr(hit_rows), owner.ctypes.data,
+                                        soff.ctypes.data), "coex_shard_count")
+
+    def shard_finish(self, hit_sets_mine, options: Options, want_scores=False):
+        """Network stage of THIS rank's permutations (their score blocks are complete after the caller's barrier)."""
+        K, perm_off, hit_rows, H = self._flatten(hit_sets_mine)
+        Hn = max(H, 1)
+        n_groups = np.zeros(max(K, 1), dtype=np.int32)
+        group_of_hit = np.full(Hn, -1, dtype=np.int32)
+        group_label = np.full(Hn, -1, dtype=np.int32)
+        group_winner = np.full(Hn, -1, dtype=np.int32)
+        group_density = np.zeros(Hn, dtype=np.float64)
+        hit_score = np.zeros(Hn, dtype=np.float64)
+        SC = int(np.sum(np.diff(perm_off) ** 2))
+        scores = np.zeros(max(SC, 1), dtype=np.float64) if want_scores else None
+        prm = options.to_params(self.N)
+        check(self.lib.coex_shard_finish(self.h, ctypes.byref(prm), K, perm_off.ctypes.data, _ptr(hit_rows),
+                                         n_groups.ctypes.data, group_of_hit.ctypes.data, group_label.ctypes.data,
+                                         group_winner.ctypes.data, group_density.ctypes.data, hit_score.ctypes.data,
+                                         _ptr(scores), 0), "coex_shard_finish")
+        return BatchResult(perm_off, hit_rows, n_groups[:K], group_of_hit[:H], group_label[:H], group_winner[:H],
+                           group_density[:H], hit_score[:H], scores, None)
+
     # ---- introspection ------------------------------------------------------------------------------
     def stage_ms(self):
         out = {}

@@ -140,7 +140,10 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     COEX_CUDA(cudaMemsetAsync(c->pl_cnt.p, 0, ((size_t)N + 2) * sizeof(int), st));
     COEX_CUDA(cudaMemsetAsync(c->pl_err.p, 0, sizeof(int), st));
     const unsigned hb = (unsigned)((H + 255) / 256);
-    plan_count_kernel<<<hb, 256, 0, st>>>(d_hits, c->d_perm_off.p, K, H, N, c->pl_cnt.p, c->dd_qperm.p, c->pl_err.p);
+    const bool sharded = (c->shard_phase == 1);
+    const int sh_world = sharded ? c->shard_world : 1, sh_rank = sharded ? c->shard_rank : 0;
+    double *const *perm_scores = sharded ? c->d_perm_scores.p : nullptr;
+    plan_count_kernel<<<hb, 256, 0, st>>>(d_hits, c->d_perm_off.p, K, H, N, c->pl_cnt.p, c->dd_qperm.p, c->pl_err.p, sh_world, sh_rank);
     COEX_KCHECK(st);
     plan_rows_kernel<<<1, kPlanThreads, 0, st>>>(c->pl_cnt.p, N, c->dd_uniq.p, c->pl_ustart.p, c->pl_cursor.p, c->pl_meta.p);
     COEX_KCHECK(st);
@@ -148,11 +151,12 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     int h_err = 0;
     COEX_CUDA(cudaMemcpyAsync(h_meta, c->pl_meta.p, sizeof h_meta, cudaMemcpyDeviceToHost, st));
     COEX_CUDA(cudaMemcpyAsync(&h_err, c->pl_err.p, sizeof h_err, cudaMemcpyDeviceToHost, st));
-    plan_scatter_kernel<<<hb, 256, 0, st>>>(d_hits, H, c->pl_cursor.p, c->dd_qlist.p);
+    plan_scatter_kernel<<<hb, 256, 0, st>>>(d_hits, H, c->pl_cursor.p, c->dd_qlist.p, sh_world, sh_rank);
     COEX_KCHECK(st);
     COEX_CUDA(cudaStreamSynchronize(st));                  // the one read-back of the plan: U sizes the strips
     if (h_err) COEX_FAIL("hit row out of range");
     const long long U = h_meta[0];
+    if (U == 0) return 0;                                  // (a rank of a shared job may own none of the hit rows)
     // ---- strips of unique rows ------------------------------------------------------------------------
     const long long ld = c->N_pad;
     long long Us = (c->strip_mb << 20) / (ld * (pearson ? 8 : 4));     // Pearson: the float r strip + the int32 Spearman strip of the statistics
@@ -243,7 +247,7 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
             da.strip = c->strip.p; da.ld = ld; da.items = nullptr; da.n_items = (int)(nu * nchunk);
             da.uniq_rows = c->dd_uniq.p + u0; da.qlist = c->dd_qlist.p; da.q_perm = c->dd_qperm.p; da.perm_off = c->d_perm_off.p; da.sc_off = c->d_sc_off.p;
             da.K = K; da.hit_rows = d_hits; da.sx = c->sx.p; da.sxg = c->sxg.p; da.icol = c->icol.p; da.rawsum_pos = c->rawsum_pos.p; da.N = N;
-            da.n_degenerate = c->d_ndeg.p; da.anticor = prm->anticorrelation; da.scores = d_sc; da.counts = d_cn;
+            da.n_degenerate = c->d_ndeg.p; da.anticor = prm->anticorrelation; da.scores = d_sc; da.counts = d_cn; da.perm_scores = perm_scores;
             da.Tcap = kRankTcap; da.Qcap = Qcap; da.bm_words = bm_words_rank; da.claim = rclaim;
             da.R = std::min(1.0, std::max(0.05, 8.0 / std::sqrt((double)std::max(c->n, 2)))); da.g_rec = reinterpret_cast<StatRec *>(c->dd_gthr.p);
             da.score_tab = c->dd_tab.p; da.phase_clk = nullptr; da.rank_out = c->rank_strip.p;
@@ -254,7 +258,7 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
             rs.strip = c->strip.p; rs.rank = c->rank_strip.p; rs.ld = ld; rs.uniq_rows = c->dd_uniq.p + u0; rs.ustart = c->pl_ustart.p + u0;
             rs.qlist = c->dd_qlist.p; rs.q_perm = c->dd_qperm.p; rs.u_count = nu; rs.perm_off = c->d_perm_off.p; rs.sc_off = c->d_sc_off.p;
             rs.hit_rows = d_hits; rs.sx = c->sx.p; rs.sxg = c->sxg.p; rs.rawsum_pos = c->rawsum_pos.p; rs.N = N; rs.anticor = prm->anticorrelation;
-            rs.scores = d_sc; rs.counts = d_cn; rs.score_tab = c->dd_tab.p;
+            rs.scores = d_sc; rs.counts = d_cn; rs.perm_scores = perm_scores; rs.score_tab = c->dd_tab.p;
             rank_score_kernel<<<(unsigned)std::min<long long>(H, (long long)c->sm_count * 16), 256, 0, st>>>(rs);
             COEX_KCHECK(st);
             COEX_TRY(stage_end(c, 2));
@@ -271,7 +275,7 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
             da.uniq_rows = c->dd_uniq.p + u0; da.qlist = c->dd_qlist.p; da.q_perm = c->dd_qperm.p;
             da.perm_off = c->d_perm_off.p; da.sc_off = c->d_sc_off.p; da.K = K; da.hit_rows = d_hits;
             da.sx = c->sx.p; da.sxg = c->sxg.p; da.icol = c->icol.p; da.rawsum_pos = c->rawsum_pos.p; da.N = N;
-            da.n_degenerate = c->d_ndeg.p; da.anticor = prm->anticorrelation; da.scores = d_sc; da.counts = d_cn;
+            da.n_degenerate = c->d_ndeg.p; da.anticor = prm->anticorrelation; da.scores = d_sc; da.counts = d_cn; da.perm_scores = perm_scores;
             da.Tcap = Tcap; da.Qcap = Qcap; da.bm_words = bm_words; da.claim = claim;
             da.R = R; da.g_rec = reinterpret_cast<StatRec *>(c->dd_gthr.p);
             da.score_tab = c->dd_tab.p; da.phase_clk = dbg ? phase.p : nullptr;
@@ -385,7 +389,14 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
     const long long SC = sc_off[K];
     if (prm->measure == 0 && prm->use_specific_p && c->n > 1860)
         COEX_FAIL("Spearman tensor path supports up to 1860 samples (int32 dot products)");
-    stage_reset_from(c, ST_GATHER);
+    const int phase = c->shard_phase;              // 0 = plain call; 1 / 2 = the two halves of a job shared by several GPUs
+    if (phase == 1) {
+        if (!prm->use_specific_p || c->count_mode == 1 || (prm->measure == 1 && (c->pearson_mode != 0 || c->n > 1860)))
+            COEX_FAIL("a job shared by several GPUs runs the de-duplicated node-specific count path only");
+        if (counts) COEX_FAIL("bisect indices are not returned by a job shared by several GPUs");
+    }
+    if (phase == 2 && SC > (long long)c->shard_scores.cap) COEX_FAIL("coex_shard_finish: score buffer smaller than this rank's permutations");
+    if (c->shard_phase != 2) stage_reset_from(c, ST_GATHER);      // (the second half of a shared job keeps the first half's stage times)
     cudaStream_t st = c->stream;
 
     // ---- buffers ----------------------------------------------------------------------------
@@ -409,7 +420,9 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
         if (counts) { COEX_TRY(c->d_counts.reserve(std::max<long long>(SC, 1))); d_cn = c->d_counts.p; }
         d_sc = nullptr;
     }
-    if (!d_sc) { COEX_TRY(c->d_scores.reserve(std::max<long long>(SC, 1))); d_sc = c->d_scores.p; }
+    if (phase == 2) d_sc = c->shard_scores.p;      // written by every rank's count stage (coex_shard_count), complete after the caller's barrier
+    else if (phase == 1) d_sc = nullptr;           // the score rows go to their owners through c->d_perm_scores
+    else if (!d_sc) { COEX_TRY(c->d_scores.reserve(std::max<long long>(SC, 1))); d_sc = c->d_scores.p; }
     COEX_TRY(c->w_root.reserve(Hs_alloc)); COEX_TRY(c->w_pos.reserve(Hs_alloc)); COEX_TRY(c->w_s1.reserve(Hs_alloc));
     COEX_TRY(c->w_d0.reserve(Hs_alloc)); COEX_TRY(c->w_w.reserve(Hs_alloc)); COEX_TRY(c->w_best.reserve(Hs_alloc));
     COEX_TRY(c->w_cand.reserve(Hs_alloc)); COEX_TRY(c->w_state.reserve(K + 1));
@@ -424,7 +437,11 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
     COEX_CUDA(cudaMemsetAsync(d_aps, 0, H * sizeof(double), st));
 
     const int T2max = next_pow2(std::max(Pmax, 2));
-    if (H > 0 && Pmax >= 2) {
+    if (phase == 1) {
+        COEX_TRY(c->d_perm_scores.reserve((size_t)K));
+        COEX_CUDA(cudaMemcpyAsync(c->d_perm_scores.p, c->h_perm_scores.data(), (size_t)K * sizeof(double *), cudaMemcpyHostToDevice, st));
+    }
+    if (H > 0 && Pmax >= 2 && phase != 2) {
         if (prm->use_specific_p) {
             // ---- node-specific null: strips of query rows x all table columns ---------------
             const long long ld = (prm->measure == 0) ? c->N_pad : c->N;
@@ -498,6 +515,13 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
             COEX_CUDA(cudaGetLastError());
             COEX_TRY(stage_end(c, 2));
         }
+    }
+    if (phase == 1) {
+        // every score row of my table rows is on its way to the rank that owns its permutation (stores into peer memory over
+        // NVLink): they have landed when this stream is idle; the caller's barrier then tells the owners
+        COEX_CUDA(cudaStreamSynchronize(st));
+        if (c->gemm_mode == 0 || prm->measure == 1) COEX_TRY(tc_check_error(c));
+        return 0;
     }
     // ---- K4: groups, winners, densities -----------------------------------------------------
     NetArgs na{};
@@ -717,6 +741,8 @@ int coex_destroy(coex_ctx *c) {
     c->p_out.release(); c->icol.release(); c->d_ndeg.release(); c->dd_uniq.release(); c->dd_qlist.release();
     c->dd_items.release(); c->dd_qperm.release(); c->pl_cnt.release(); c->pl_cursor.release(); c->pl_ustart.release(); c->pl_nitems.release();
     c->pl_itemoff.release(); c->pl_bounds.release(); c->pl_meta.release(); c->pl_err.release(); c->dd_gthr.release(); c->dd_tab.release();
+    for (void *p : c->peer_mapped) if (p) cudaIpcCloseMemHandle(p);
+    c->shard_scores.release(); c->d_perm_scores.release();
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -999,6 +1025,68 @@ int coex_network_batch(coex_ctx *c, const coex_params *prm, int K, const long lo
     if (!prm || !perm_off || (!hit_rows && perm_off[K] > 0)) COEX_FAIL("coex_network_batch: null argument");
     return network_batch_impl(c, prm, K, perm_off, hit_rows, n_groups, group_of_hit, group_label, group_winner,
                               group_density, hit_score, scores, counts, on_device);
+}
+
+// --------------------------------------------------------------------------------------------
+// ONE job shared by several GPUs of a box (one process per GPU)
+// --------------------------------------------------------------------------------------------
+int coex_shard_scores_alloc(coex_ctx *c, int world, int rank, long long n_doubles, void *ipc_handle_out) {
+    COEX_TRY(check_ctx(c));
+    if (world < 1 || rank < 0 || rank >= world || n_doubles < 0 || !ipc_handle_out) COEX_FAIL("coex_shard_scores_alloc: bad argument");
+    for (void *p : c->peer_mapped) if (p) cudaIpcCloseMemHandle(p);
+    c->peer_mapped.assign((size_t)world, nullptr);
+    c->peer_scores.assign((size_t)world, nullptr);
+    c->shard_world = world; c->shard_rank = rank;
+    COEX_TRY(c->shard_scores.reserve((size_t)std::max<long long>(n_doubles, 1)));
+    c->peer_scores[(size_t)rank] = c->shard_scores.p;
+    cudaIpcMemHandle_t h;
+    COEX_CUDA(cudaIpcGetMemHandle(&h, c->shard_scores.p));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the header promises 64 bytes");
+    memcpy(ipc_handle_out, &h, sizeof h);
+    return 0;
+}
+
+int coex_shard_scores_open(coex_ctx *c, int peer_rank, const void *ipc_handle) {
+    COEX_TRY(check_ctx(c));
+    if (peer_rank < 0 || peer_rank >= c->shard_world || !ipc_handle) COEX_FAIL("coex_shard_scores_open: bad argument");
+    if (peer_rank == c->shard_rank) return 0;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof h);
+    void *p = nullptr;
+    COEX_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    if (c->peer_mapped[(size_t)peer_rank]) cudaIpcCloseMemHandle(c->peer_mapped[(size_t)peer_rank]);
+    c->peer_mapped[(size_t)peer_rank] = p;
+    c->peer_scores[(size_t)peer_rank] = static_cast<double *>(p);
+    return 0;
+}
+
+int coex_shard_count(coex_ctx *c, const coex_params *prm, int K, const long long *perm_off, const int *hit_rows,
+                     const int *perm_owner, const long long *perm_score_off) {
+    COEX_TRY(check_ctx(c));
+    if (!prm || !perm_off || !perm_owner || !perm_score_off || (!hit_rows && perm_off[K] > 0)) COEX_FAIL("coex_shard_count: null argument");
+    if (c->peer_scores.size() != (size_t)c->shard_world) COEX_FAIL("coex_shard_count: call coex_shard_scores_alloc first");
+    c->h_perm_scores.assign((size_t)std::max(K, 1), nullptr);
+    for (int k = 0; k < K; ++k) {
+        const int o = perm_owner[k];
+        if (o < 0 || o >= c->shard_world || !c->peer_scores[(size_t)o]) COEX_FAIL("coex_shard_count: the score buffer of rank " + std::to_string(o) + " is not mapped");
+        c->h_perm_scores[(size_t)k] = c->peer_scores[(size_t)o] + perm_score_off[k];
+    }
+    c->shard_phase = 1;
+    const int status = network_batch_impl(c, prm, K, perm_off, hit_rows, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+    c->shard_phase = 0;
+    return status;
+}
+
+int coex_shard_finish(coex_ctx *c, const coex_params *prm, int K, const long long *perm_off, const int *hit_rows,
+                      int *n_groups, int *group_of_hit, int *group_label, int *group_winner, double *group_density,
+                      double *hit_score, double *scores, int on_device) {
+    COEX_TRY(check_ctx(c));
+    if (!prm || !perm_off || (!hit_rows && perm_off[K] > 0)) COEX_FAIL("coex_shard_finish: null argument");
+    c->shard_phase = 2;
+    const int status = network_batch_impl(c, prm, K, perm_off, hit_rows, n_groups, group_of_hit, group_label, group_winner,
+                                          group_density, hit_score, scores, nullptr, on_device);
+    c->shard_phase = 0;
+    return status;
 }
 
 long long coex_launch_count(coex_ctx *c) { return c ? c->launches : 0; }

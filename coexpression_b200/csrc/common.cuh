@@ -129,6 +129,14 @@ struct coex_ctx {
     coex::DevBuf<unsigned long long> feat_key;
     coex::DevBuf<int> feat_row;
     long long feat_maxlen = 0;
+    // ---- ONE job shared by several GPUs (coex_shard_*): this rank's score buffer (exported with CUDA IPC), the peers' buffers
+    // mapped into this process, and the per-permutation base pointers of the running call
+    int shard_world = 1, shard_rank = 0, shard_phase = 0;      // phase: 0 = plain call, 1 = count stage of my ROWS, 2 = network stage of my PERMUTATIONS
+    coex::DevBuf<double> shard_scores;
+    std::vector<double *> peer_scores;                         // [world] (own buffer at shard_rank)
+    std::vector<void *> peer_mapped;                           // what cudaIpcOpenMemHandle returned (closed in coex_destroy)
+    coex::DevBuf<double *> d_perm_scores;
+    std::vector<double *> h_perm_scores;
     // order in which `bedtools window` reports the B records of one A record (permute.cuh): rank of every table row and its inverse
     coex::DevBuf<int> feat_wrank, feat_wrow;
     std::vector<int> h_chrom_id, h_bed_index;

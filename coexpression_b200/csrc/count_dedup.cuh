@@ -74,6 +74,9 @@ struct DedupArgs {
     int anticor;
     double *scores;
     long long *counts;
+    double *const *perm_scores;     // nullptr, or [K]: where the P x P score block of every permutation lives -- on a multi-GPU run
+                                    // the buffer of the rank that OWNS the permutation (peer memory over NVLink, mapped with CUDA IPC):
+                                    // the score rows are stored straight into it, there is no exchange step afterwards
     int Tcap, Qcap;                 // shared-memory capacities (statistics, queries per item)
     double R;                       // bucket range [-R, R]
     int bm_words;                   // 32-bit words of the hit-column bitmap (0 = table too long, bitmap disabled)
@@ -155,8 +158,9 @@ count_dedup_kernel(DedupArgs a) {
     unsigned int *lut = hist + a.Tcap + 4;
     unsigned int *cursor = reinterpret_cast<unsigned int *>(thr32 - 1);   // bucket cursors alias thr32|hist (both dead until step C; 2*Tcap >= buckets)
     int *queue = reinterpret_cast<int *>(lut + kDdBuckets + 4);
-    long long *q_sc = reinterpret_cast<long long *>(queue + kDdQueue);   // [Qcap] offset of the query's score row
-    int *q_i = reinterpret_cast<int *>(q_sc + a.Qcap);                     // [Qcap] hit position
+    long long *q_sc = reinterpret_cast<long long *>(queue + kDdQueue);   // [Qcap] ADDRESS of the query's score row
+    long long *q_cn = q_sc + a.Qcap;                                       // [Qcap] offset of the query's row in a.counts
+    int *q_i = reinterpret_cast<int *>(q_cn + a.Qcap);                     // [Qcap] hit position
     int *q_off = q_i + a.Qcap;                   // [Qcap] offset of the query's permutation in hit_rows
     int *q_P = q_off + a.Qcap;                   // [Qcap] hits of that permutation
     int *q_toff = q_P + a.Qcap;                  // [Qcap+2] offset of the query's statistics in the item
@@ -206,7 +210,9 @@ count_dedup_kernel(DedupArgs a) {
             q_i[ql] = i;
             q_off[ql] = (int)off;
             q_P[ql] = P;
-            q_sc[ql] = a.sc_off[lo] + (long long)i * P;
+            double *sbase = a.perm_scores ? a.perm_scores[lo] : a.scores + a.sc_off[lo];
+            q_sc[ql] = (long long)(size_t)(sbase + (long long)i * P);
+            q_cn[ql] = a.sc_off[lo] + (long long)i * P;
             double vi = -99.0;                             // null value at table column i (quirk Q1)
             if (PEARSON) {
                 vi = 0.0;                                  // filled in by one warp per query below
@@ -278,9 +284,8 @@ count_dedup_kernel(DedupArgs a) {
                 rec_tmp[tt[e]] = StatRec{r, 0u, cc4[e]};
                 if (r == -99.0) {                                           // diagonal, or 1-make-network.py:284-285
                     if (!RANKROW) {
-                        const long long w = q_sc[qq[e]] + jj[e];
-                        a.scores[w] = (cc4[e] < 0) ? 0.0 : -log10(1.0);
-                        if (a.counts) a.counts[w] = -1;
+                        reinterpret_cast<double *>((size_t)q_sc[qq[e]])[jj[e]] = (cc4[e] < 0) ? 0.0 : -log10(1.0);
+                        if (a.counts) a.counts[q_cn[qq[e]] + jj[e]] = -1;
                     }
                 } else {
                     atomicAdd(&lut[dd_bucket(r, bscale_f)], 1u);
@@ -526,13 +531,13 @@ count_dedup_kernel(DedupArgs a) {
         } else
         for (int s0 = 0; s0 < T; s0 += 4 * kDdThreads) {
             // four statistics per thread: record loads, then score-table gathers, then stores -- each kind in flight together
-            long long idx4[4], w4[4];
+            long long idx4[4], w4[4], wc4[4];                 // w4: address of the score (0 = none), wc4: offset in a.counts
             double sc4[4];
             bool tab4[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int s = s0 + tid + e * kDdThreads;
-                w4[e] = -1; idx4[e] = 0; tab4[e] = true;
+                w4[e] = 0; wc4[e] = 0; idx4[e] = 0; tab4[e] = true;
                 if (s < T) {
                     const StatRec x = srt[s];
                     const unsigned int o = x.org;
@@ -543,17 +548,18 @@ count_dedup_kernel(DedupArgs a) {
                     long long idx = (long long)hist[s] + n_deg;
                     if (i < N) { if (q_vi[ql] < x.r) idx -= 1; } else tab4[e] = false;     // no skipped column: N values
                     idx4[e] = idx;
-                    w4[e] = q_sc[ql] + j;
+                    w4[e] = q_sc[ql] + 8LL * j;
+                    wc4[e] = q_cn[ql] + j;
                 }
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-                sc4[e] = (w4[e] < 0) ? 0.0 : (tab4[e] ? a.score_tab[idx4[e]] : edge_score_dev(idx4[e], N, a.anticor));
+                sc4[e] = (w4[e] == 0) ? 0.0 : (tab4[e] ? a.score_tab[idx4[e]] : edge_score_dev(idx4[e], N, a.anticor));
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                if (w4[e] < 0) continue;
-                a.scores[w4[e]] = sc4[e];
-                if (a.counts) a.counts[w4[e]] = idx4[e];
+                if (w4[e] == 0) continue;
+                *reinterpret_cast<double *>((size_t)w4[e]) = sc4[e];
+                if (a.counts) a.counts[wc4[e]] = idx4[e];
             }
         }
         DD_PHASE(5);
@@ -580,6 +586,7 @@ struct RankScoreArgs {
     int anticor;
     double *scores;
     long long *counts;
+    double *const *perm_scores;     // as in DedupArgs
     const double *score_tab;
 };
 
@@ -607,7 +614,7 @@ rank_score_kernel(RankScoreArgs a) {
         const double sxu_g = a.sxg[u];
         double vi = -99.0;                            // null value at table column i (quirk Q1)
         if (i < a.N) { const double sxc = a.sx[i]; if (sxu != 0.0 && sxc != 0.0) vi = __ddiv_rn(0.25 * (double)srow[i], __dmul_rn(sxu, sxc)); }
-        double *sc = a.scores + a.sc_off[k] + (long long)i * P;
+        double *sc = (a.perm_scores ? a.perm_scores[k] : a.scores + a.sc_off[k]) + (long long)i * P;
         long long *cn = a.counts ? a.counts + a.sc_off[k] + (long long)i * P : nullptr;
         for (int j = threadIdx.x; j < P; j += blockDim.x) {
             if (j == i) { sc[j] = 0.0; if (cn) cn[j] = -1; continue; }
@@ -651,7 +658,7 @@ __global__ void icol_kernel(const double *__restrict__ sx, const unsigned char *
 
 inline size_t dedup_smem_bytes(int Tcap, int Qcap, int bm_words, int claim) {
     return (size_t)Qcap * 8 + (size_t)(Tcap + 4) * 4 + (size_t)(Tcap + 4) * 4 + (size_t)(kDdBuckets + 4) * 4 +
-           (size_t)kDdQueue * 4 + (size_t)Qcap * 8 + (size_t)Qcap * 4 * 3 + (size_t)(Qcap + 2) * 4 + (size_t)bm_words * 4 * (claim ? 2 : 1) + 16;
+           (size_t)kDdQueue * 4 + (size_t)Qcap * 8 * 2 + (size_t)Qcap * 4 * 3 + (size_t)(Qcap + 2) * 4 + (size_t)bm_words * 4 * (claim ? 2 : 1) + 16;
 }
 
 }  // namespace coex

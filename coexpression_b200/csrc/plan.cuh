@@ -18,13 +18,17 @@ namespace coex {
 constexpr int kPlanThreads = 1024;
 constexpr int kPlanQcap = 8;             // queries per work item (shared-memory capacity of the count kernels)
 
+// world > 1: ONE job shared by several GPUs -- this rank plans only the queries whose table row it owns (row % world == rank),
+// so that a row is correlated and streamed once whatever the number of GPUs (sharding by permutation would repeat it on every
+// rank whose permutations hit it).
 __global__ void plan_count_kernel(const int *__restrict__ hit_rows, const long long *__restrict__ perm_off, int K,
                                   long long H, long long N, int *__restrict__ cnt, int *__restrict__ q_perm,
-                                  int *__restrict__ err) {
+                                  int *__restrict__ err, int world, int rank) {
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= H) return;
     const int r = hit_rows[q];
     if (r < 0 || r >= N) { atomicOr(err, 1); return; }
+    if (world > 1 && r % world != rank) return;
     atomicAdd(&cnt[r + 1], 1);
     int lo = 0, hi = K;
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (perm_off[mid] <= q) lo = mid; else hi = mid; }
@@ -79,9 +83,10 @@ plan_rows_kernel(const int *__restrict__ cnt, long long N, int *__restrict__ uni
 }
 
 __global__ void plan_scatter_kernel(const int *__restrict__ hit_rows, long long H, int *__restrict__ cursor,
-                                    int *__restrict__ qlist) {
+                                    int *__restrict__ qlist, int world, int rank) {
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= H) return;
+    if (world > 1 && hit_rows[q] % world != rank) return;
     qlist[atomicAdd(&cursor[hit_rows[q]], 1)] = (int)q;
 }
 

@@ -72,6 +72,61 @@ def gather_densities(local_perm_ids, densities, numperms_total, device=None):
 
 
 # ------------------------------------------------------------------------------------------------
+# ONE job shared by the GPUs of a box: count stage sharded by table row, network stage by permutation, the edge scores
+# stored straight into the owner's buffer over NVLink (include/coexpression_b200.h section 3).  The host side here only
+# deals the permutations, exchanges the 64-byte IPC handles once and places one barrier between the two stages.
+# ------------------------------------------------------------------------------------------------
+def score_layout(hit_counts, world):
+    """-> (shards, owner [K], score_off [K], n_doubles [world]): permutation k lives in the buffer of owner[k] at
+    score_off[k] (doubles); a rank's blocks follow each other in ascending k."""
+    shards = shard_permutations(hit_counts, world)
+    K = len(hit_counts)
+    owner = np.zeros(K, dtype=np.int32)
+    soff = np.zeros(K, dtype=np.int64)
+    sizes = np.zeros(world, dtype=np.int64)
+    for r, mine in enumerate(shards):
+        acc = 0
+        for k in mine:
+            owner[k] = r
+            soff[k] = acc
+            acc += int(hit_counts[k]) ** 2
+        sizes[r] = acc
+    return shards, owner, soff, sizes
+
+
+class SharedJob:
+    """All ranks construct it with the SAME list of hit sets (and an initialised NCCL process group) and call run()."""
+
+    def __init__(self, ctx, hit_sets, device):
+        self.ctx, self.hit_sets, self.device = ctx, hit_sets, device
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        counts = [len(h) for h in hit_sets]
+        self.shards, self.owner, self.score_off, sizes = score_layout(counts, self.world)
+        self.mine = self.shards[self.rank]
+        handle = ctx.shard_scores_alloc(self.world, self.rank, int(sizes[self.rank]))
+        if self.world > 1:
+            t = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+            got = [torch.zeros_like(t) for _ in range(self.world)]
+            dist.all_gather(got, t)
+            for r, h in enumerate(got):
+                if r != self.rank:
+                    ctx.shard_scores_open(r, bytes(h.cpu().tolist()))
+
+    def barrier(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+
+    def run(self, options, want_scores=False):
+        """-> api.BatchResult of this rank's permutations (self.mine)."""
+        self.barrier()                       # nobody is still reading last run's scores
+        self.ctx.shard_count(self.hit_sets, options, self.owner, self.score_off)
+        self.barrier()                       # every rank's score rows have landed
+        return self.ctx.shard_finish([self.hit_sets[k] for k in self.mine], options, want_scores=want_scores)
+
+
+# ------------------------------------------------------------------------------------------------
 # C3: all unordered row pairs.  Row block b = rows [b * block, (b + 1) * block) against every LATER row; the blocks
 # are independent (no exchange), their cost falls linearly with b, so they are dealt to the ranks in a zig-zag
 # (0, 1, .., w-1, w-1, .., 1, 0, 0, 1, ..) that balances the pair counts; the ONE collective is the reduction of the

@@ -156,6 +156,34 @@ int coex_network_batch(coex_ctx *ctx, const coex_params *params, int K,
                        double *group_density, double *hit_score,
                        double *scores, long long *counts, int on_device);
 
+/* ------------------------------------------------------------------------------------------
+ * 3. ONE job shared by the GPUs of a box (one process and one coex_ctx per GPU; the reference's counterpart is runlocal.py's
+ *    pool of per-permutation processes, runlocal.py:19,50-55,78-79).
+ *    Splitting the PERMUTATIONS over the ranks would repeat the work of the node-specific null: a table row hit by permutations
+ *    of several ranks would be correlated against the whole table and streamed on each of them.  So the count stage
+ *    (A4 - A7) is sharded by TABLE ROW -- rank r handles the queries of EVERY permutation whose hit row u has u % world == r,
+ *    each row still exactly once -- and the network stage (A8 - A12) by permutation.  The edge scores move from the rank that
+ *    computes a score row to the rank that owns its permutation inside the count kernel: plain stores into the owner's score
+ *    buffer, mapped into this process with CUDA IPC (peer memory over NVLink / NVSwitch).  There is no exchange step and no
+ *    collective on the data path; the caller provides one barrier between the two calls (all stores have landed when every
+ *    rank's coex_shard_count has returned) and gathers the density vectors afterwards (2-collate-results.py:68-76).
+ *
+ *    coex_shard_scores_alloc  this rank's score buffer of n_doubles (= sum of P_k^2 over ITS permutations) and its 64-byte
+ *                             CUDA IPC handle, to be exchanged by the caller (e.g. torch.distributed.all_gather)
+ *    coex_shard_scores_open   maps the buffer of a peer rank
+ *    coex_shard_count         K = ALL permutations of the job (host arrays); perm_owner[k] = rank that owns permutation k,
+ *                             perm_score_off[k] = offset (in doubles) of its P_k x P_k block inside the owner's buffer
+ *    coex_shard_finish        K = THIS rank's permutations, in the order their blocks have in its buffer; outputs as
+ *                             coex_network_batch (scores: optional host copy of the blocks; on_device as there)
+ * ---------------------------------------------------------------------------------------- */
+int coex_shard_scores_alloc(coex_ctx *ctx, int world, int rank, long long n_doubles, void *ipc_handle_out);
+int coex_shard_scores_open(coex_ctx *ctx, int peer_rank, const void *ipc_handle);
+int coex_shard_count(coex_ctx *ctx, const coex_params *params, int K, const long long *perm_off, const int *hit_rows,
+                     const int *perm_owner, const long long *perm_score_off);
+int coex_shard_finish(coex_ctx *ctx, const coex_params *params, int K, const long long *perm_off, const int *hit_rows,
+                      int *n_groups, int *group_of_hit, int *group_label, int *group_winner, double *group_density,
+                      double *hit_score, double *scores, int on_device);
+
 /* Introspection for bench.py: kernels launched by ctx so far, and per-stage device time (ms,
  * CUDA events on coex_stream) of the last coex_network_batch / coex_prepare call.
  * stage ids: 0 rank+pack, 1 row stats, 2 gather, 3 correlation GEMM, 4 count+score, 5 network, 6 unused (kept for ABI stability) */

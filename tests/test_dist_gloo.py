@@ -103,3 +103,18 @@ def test_histogram_reduce_world2_gloo():
         assert p.exitcode == 0
     want = [a + b for a, b in zip(got[0][1], got[1][1])]
     assert got[0][2] == want and got[1][2] == want and got[0][3] == got[1][3] == 21
+
+
+def test_score_layout_partitions_the_score_buffers():
+    from coexpression_b200.dist import score_layout
+    counts = [1690] + [600 + (37 * k) % 90 for k in range(40)] + [0, 1]
+    for world in (1, 2, 4, 8):
+        shards, owner, soff, sizes = score_layout(counts, world)
+        assert sorted(k for s in shards for k in s) == list(range(len(counts)))
+        for r, mine in enumerate(shards):
+            assert mine == sorted(mine) and all(owner[k] == r for k in mine)
+            acc = 0
+            for k in mine:                                       # a rank's blocks follow each other in ascending k
+                assert soff[k] == acc
+                acc += counts[k] ** 2
+            assert sizes[r] == acc

@@ -761,3 +761,29 @@ def test_pearson_null_more_than_1860_samples_takes_the_exact_strip():
         _oracle_vs_gpu(t, hits, Options(correlationmeasure="Pearson"), glist, R, ctx)
         with pytest.raises(CoexError):                          # Spearman null: refused loudly, never wrong silently
             ctx.network_batch(hits, Options())
+
+
+def test_shared_job_entry_points_on_one_rank_equal_the_plain_call():
+    """coex_shard_count + coex_shard_finish with world = 1 (score rows through the per-permutation pointer table, network stage
+    on the job's own buffer) against coex_network_batch: every output bit for bit, scores included."""
+    from coexpression_b200 import synth
+    from coexpression_b200.api import CoexContext, Options
+    from coexpression_b200.dist import SharedJob
+    t = synth.make_table(4000, 96, seed=61)
+    hits, _, _ = synth.make_permutation_hits(t, 150, 6, window=7000, seed=62)
+    hits = hits + [np.zeros(0, dtype=np.int32), hits[0][:1]]
+    ga, gb = synth.global_pair_indices(t.names, 40000, seed=63)
+    for opts in (Options(), Options(anticorrelation=True, noiter=True), Options(correlationmeasure="Pearson")):
+        with CoexContext() as ctx:
+            ctx.set_expression(t.X); ctx.prepare()
+            ctx.set_features(t.chrom, t.start, t.end, t.names)
+            g = ctx.pairs(ga, gb, ranked=opts.correlationmeasure == "Spearman")
+            ctx.set_global_list(np.sort(np.where(np.isnan(g), -99.0, g)))
+            want = ctx.network_batch(hits, opts, want_scores=True)
+            job = SharedJob(ctx, hits, None)
+            assert job.mine == list(range(len(hits)))
+            got = job.run(opts, want_scores=True)
+            again = job.run(opts, want_scores=True)              # the buffers are reused
+        for res in (got, again):
+            for name in ("n_groups", "group_of_hit", "group_label", "group_winner", "group_density", "hit_score", "scores"):
+                assert np.array_equal(getattr(res, name), getattr(want, name)), name
