@@ -436,15 +436,22 @@ def run_ours(args):
     dens_resident = job.densities()                          # of the last timed step
 
     # ---- e2e: host buffers through the public API, copies inside the timed region ----------------
-    # N > 1: the table is uploaded ONCE (rank 0, pinned host memory) and broadcast over NVLink (NCCL); every rank then
-    # ranks / packs its copy, reduces its own hit sets (host lists), and the density vectors are gathered on the device
-    # and read back once.
-    X_pin = torch.from_numpy(t.X).pin_memory() if rank == 0 else None
-    Xh = X_pin.numpy() if rank == 0 else None
-    X_bc = torch.empty((t.N, t.n), dtype=torch.float64, device=dev) if world > 1 else None
+    # N > 1: the table crosses PCIe ONCE in total -- every rank uploads its 1 / N-th of the rows from pinned host memory (the
+    # ranks' PCIe links work in parallel) and the slices are all-gathered over NVLink (NCCL); every rank then ranks / packs
+    # its copy, reduces its own hit sets (host lists), and the density vectors are gathered on the device and read back once.
+    chunk = (t.N + world - 1) // world
+    r0, r1 = min(t.N, rank * chunk), min(t.N, (rank + 1) * chunk)
+    X_pin = torch.zeros((chunk, t.n), dtype=torch.float64).pin_memory() if world > 1 else torch.from_numpy(t.X).pin_memory()
+    if world > 1:
+        X_pin[:r1 - r0].copy_(torch.from_numpy(t.X[r0:r1]))
+    Xh = X_pin.numpy()
+    X_bc = torch.empty((world * chunk, t.n), dtype=torch.float64, device=dev) if world > 1 else None
+    X_slice = X_bc[rank * chunk:(rank + 1) * chunk] if world > 1 else None
     e2e_ms = []
-    h2d = t.X.nbytes + hit_rows.nbytes + perm_off.nbytes
-    d2h = 4 * K + 3 * 4 * H + 2 * 8 * H
+    # bytes of the WHOLE job per step (all ranks): the table once, every rank's hit lists; every rank's result arrays
+    # (+ the gathered density block read back on rank 0)
+    h2d = (X_pin.nbytes * world if world > 1 else t.X.nbytes) + env.sum_over_ranks(hit_rows.nbytes + perm_off.nbytes)
+    d2h = env.sum_over_ranks(4 * K + 3 * 4 * H + 2 * 8 * H) + (8 * world * Hpad if world > 1 else 0)
     res = None
     for i in range(2 + max(2, args.steps // 2)):
         env.barrier()
@@ -452,9 +459,8 @@ def run_ours(args):
         if world == 1:
             ctx.set_expression(Xh)
         else:
-            if rank == 0:
-                X_bc.copy_(X_pin, non_blocking=True)
-            dist.broadcast(X_bc, src=0)
+            X_slice.copy_(X_pin, non_blocking=True)
+            dist.all_gather_into_tensor(X_bc, X_slice)
             torch.cuda.current_stream().synchronize()
             ctx.set_expression_device(X_bc.data_ptr(), t.N, t.n, keepalive=X_bc)
         ctx.prepare()
@@ -558,8 +564,8 @@ def run_ours(args):
             "e2e": {"value": total_perms / (e2e_step_ms * 1e-3), "unit": "permutations/s", "ms_per_step": e2e_step_ms,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "api": ("CoexContext.set_expression + prepare + network_batch (pinned host table, host hit lists)" if world == 1 else
-                            "rank 0 uploads the pinned host table once, NCCL broadcast over NVLink, then per rank prepare + "
-                            "network_batch (host hit lists) and one NCCL all-gather of the densities read back on rank 0")},
+                            "every rank uploads its 1/N-th of the pinned host table, NCCL all-gather of the slices over NVLink, then per "
+                            "rank prepare + network_batch (host hit lists) and one NCCL all-gather of the densities read back on rank 0")},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -596,6 +602,17 @@ def run_ours(args):
                   and agg["max_abs_hit_score_err"] <= 1e-6 and agg["batch_of_%d_equals_alone" % K])
             parity.update(agg)
             parity["ok"] &= bool(ok)
+    c5 = None
+    if not args.no_extras:
+        try:
+            job = None
+            c5 = config_c5(env, args, ctx, t, X_dev, opts)
+        except Exception as e:
+            c5 = {"ok": False, "error": f"{type(e).__name__}: {e}"}
+        if rank == 0:
+            line["c5"] = c5
+            if not c5.get("ok", False):
+                parity["ok"] = False
     ctx.close()
     del X_dev, job
 
@@ -683,6 +700,172 @@ def strong_scaling(env, ctx, args, t, X_dev, opts, one_gpu_ms, dens_one_gpu):
     return out
 
 
+def genome_of(t):
+    """chromlist / chromrange as 0-prepare-coex.py:319-330 builds them, from the synthetic table's chromosome lengths."""
+    chromlist = list(t.chrom_len)
+    cr, start = {}, 0
+    for c in chromlist:
+        cr[c] = [start, start + int(t.chrom_len[c])]
+        start += int(t.chrom_len[c])
+    return chromlist, cr
+
+
+def loci_of(t, n_loci, seed):
+    """(chrom, address) of n_loci GWAS-like loci (most near a feature), unique."""
+    from coexpression_b200 import synth
+    m = synth.Mapper(t)
+    g = synth.make_loci(t, n_loci, seed)
+    ci, pos = m.gwad_to_chrom(g)
+    return list(dict.fromkeys((m.chrom_list[int(c)], int(max(1, a))) for c, a in zip(ci, pos)))
+
+
+def run_job_timed(env, ctx, hits, opts, X_dev, N, n, steps, chunk=0):
+    """One fixed list of hit sets on all ranks (world == 1: resident DeviceJob; world > 1: dist.SharedJob), optionally in
+    chunks of `chunk` sets (score matrices of a chunk must fit HBM).  -> (ms per whole list, max over ranks; densities of
+    this rank's sets of the LAST chunk; the rank's set indices of that chunk)."""
+    torch = env.torch
+    from coexpression_b200.dist import SharedJob
+    chunk = chunk or len(hits)
+    parts = [list(range(a, min(len(hits), a + chunk))) for a in range(0, len(hits), chunk)]
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=env.dev)
+    state = {}
+
+    if env.world > 1:
+        sjob = SharedJob(ctx, None, env.dev)                 # one pair of score buffers per rank, sized by the largest chunk
+        for ids in sorted(parts, key=len, reverse=True)[:1]:
+            sjob.plan([hits[k] for k in ids])
+    else:
+        jobs = [DeviceJob(env, ctx, [hits[k] for k in ids]) for ids in parts]      # (small: hit lists + per-hit outputs)
+
+    def one_pass():
+        for pi, ids in enumerate(parts):
+            if env.world > 1:
+                res = sjob.run(opts, hit_sets=[hits[k] for k in ids] if len(parts) > 1 or sjob.hit_sets is None else None)
+                state["dens"] = [res.perm(j)["density"].copy() for j in range(len(sjob.mine))]
+                state["mine"] = [ids[j] for j in sjob.mine]
+            else:
+                jobs[pi].run(opts)
+        if env.world == 1:
+            state["dens"] = jobs[-1].densities()
+            state["mine"] = list(parts[-1])
+
+    ctx.set_expression_device(X_dev.data_ptr(), N, n, keepalive=X_dev)
+    ctx.prepare()
+    one_pass()                                               # warm-up
+    ms = []
+    for _ in range(steps):
+        env.flush.fill_(1)
+        env.barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ctx.set_expression_device(X_dev.data_ptr(), N, n, keepalive=X_dev)
+        ctx.prepare()
+        one_pass()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    env.barrier()
+    out = env.max_over_ranks(float(np.mean(ms))), state["dens"], state["mine"]
+    state.clear()
+    return out
+
+
+def config_c4(env, args, ctx, t, X_dev, N, n, seed):
+    """BASELINE config C4: backcirc permutation mode with a 1M-variant background file, -n 1000, Spearman with -a, on the resident
+    full-shape table; the K locus sets and their promoters come from ONE device call (coex_permute_map, row N1)."""
+    dist = env.dist
+    K = args.full_perms
+    box = [None]
+    info = {}
+    if env.rank == 0:
+        if not args.no_cpu_baseline:
+            from oracle import permute_oracle as po                # the checker of two of the mapped sets, below
+        t0 = time.perf_counter()
+        chromlist, cr = genome_of(t)
+        snps = loci_of(t, 500, seed + 31)
+        rng = np.random.default_rng(seed + 32)
+        nb = 1000000
+        lens = np.array([t.chrom_len[c] for c in chromlist], dtype=np.float64)
+        bc = rng.choice(len(chromlist), size=nb, p=lens / lens.sum())
+        ba = (rng.random(nb) * (lens[bc] - 2)).astype(np.int64) + 1
+        backdict = {"%s_%s" % (chromlist[c], a): cr[chromlist[c]][0] + int(a) for c, a in zip(bc, ba)}
+        for c, a in snps:                                      # 0-prepare-coex.py:520-528: the real loci too
+            backdict.setdefault("%s_%s" % (c, a), cr[c][0] + a)
+        sb = [k for k, _ in sorted(backdict.items(), key=lambda kv: (kv[1], kv[0]))]      # the sort of 0-prepare-coex.py:582
+        background = [(k.split("_")[0], int(k.split("_")[1])) for k in sb]
+        shifts = [0] + [int(rng.random() * 10000000000) for _ in range(K)]
+        t1 = time.perf_counter()
+        hits = ctx.permute_map("backcirc", [c for c, _ in snps], [a for _, a in snps], shifts, chromlist, cr, 10000,
+                               background=background)
+        t2 = time.perf_counter()
+        # two of the sets against the restated reference arithmetic (oracle/permute_oracle.py)
+        okm = True
+        for k in (() if args.no_cpu_baseline else (1, K)):
+            want = po.hit_rows(po.window_bed(po.backcirc_positions(snps, shifts[k], sb), t.chrom, t.start, t.end, 10000))
+            okm &= hits[k].tolist() == want
+        info = {"background_variants": len(sb), "host_prepare_s": t1 - t0, "permute_map_s": t2 - t1, "sets": len(hits),
+                "mapped_sets_equal_restated_reference": bool(okm), "mean_hits": float(np.mean([len(h) for h in hits]))}
+        box = [hits]
+    if env.world > 1:
+        dist.broadcast_object_list(box, src=0)
+    hits = box[0]
+    from coexpression_b200.api import Options
+    opts = Options(anticorrelation=True)
+    ms, dens, mine = run_job_timed(env, ctx, hits, opts, X_dev, N, n, args.full_steps)
+    res1 = ctx.network_batch([hits[mine[0]]], opts)
+    alone = bool(np.array_equal(res1.perm(0)["density"], dens[0]))
+    alone = env.max_over_ranks(0.0 if alone else 1.0) == 0.0
+    if env.rank != 0:
+        return None
+    info.update({"workload": f"C4: backcirc permutations from a {info['background_variants']}-variant background (device permute_map), "
+                             f"{len(hits)} hit sets, Spearman, -a, {N} x {n} table, {env.world} GPU(s)",
+                 "ms": ms, "permutations_per_sec": len(hits) / (ms * 1e-3),
+                 "pairs_per_sec_reference_equivalent": float(sum(len(h) for h in hits)) * (N - 1) / (ms * 1e-3),
+                 "set_alone_equals_set_in_job": bool(alone), "ok": bool(alone and info["mapped_sets_equal_restated_reference"])})
+    return info
+
+
+def config_c5(env, args, ctx, t, X_dev, opts_base):
+    """BASELINE config C5 (iterative-removal stress): wide window (-w 100000 -> thousands of hit regions per set), -j 0.01,
+    iterative removal on, minimal shape; a bounded sample of the -n 10000 job, reduced in chunks whose score matrices fit HBM."""
+    dist = env.dist
+    from coexpression_b200.api import Options
+    K = 1000
+    box = [None]
+    info = {}
+    if env.rank == 0:
+        chromlist, cr = genome_of(t)
+        snps = loci_of(t, args.loci, args.seed + 41)
+        rng = np.random.default_rng(args.seed + 42)
+        shifts = [0] + [int(rng.random() * 10000000000) for _ in range(K)]
+        t1 = time.perf_counter()
+        hits = ctx.permute_map("circular", [c for c, _ in snps], [a for _, a in snps], shifts, chromlist, cr, 100000)
+        info = {"permute_map_s": time.perf_counter() - t1, "sets": len(hits), "mean_hits": float(np.mean([len(h) for h in hits])),
+                "max_hits": int(max(len(h) for h in hits))}
+        box = [hits]
+    if env.world > 1:
+        dist.broadcast_object_list(box, src=0)
+    hits = box[0]
+    opts = Options(pval_to_join=0.01)
+    pmax = max(len(h) for h in hits)
+    chunk = max(8, int((40 << 30) // (8 * pmax * pmax)) * env.world)       # ~40 GB of score matrices per GPU and chunk
+    ms, dens, mine = run_job_timed(env, ctx, hits, opts, X_dev, t.N, t.n, 1, chunk=chunk)
+    st = ctx.stage_ms()
+    res1 = ctx.network_batch([hits[mine[0]]], opts)
+    alone = bool(np.array_equal(res1.perm(0)["density"], dens[0]))
+    alone = env.max_over_ranks(0.0 if alone else 1.0) == 0.0
+    if env.rank != 0:
+        return None
+    info.update({"workload": f"C5: -w 100000 (mean {info['mean_hits']:.0f} hit regions per set), -j 0.01, iterative removal, Spearman, "
+                             f"{t.N} x {t.n} table; {len(hits)} hit sets = a bounded sample of the -n 10000 job, in chunks of {chunk} "
+                             f"sets, {env.world} GPU(s)",
+                 "ms": ms, "permutations_per_sec": len(hits) / (ms * 1e-3), "chunk_sets": chunk,
+                 "seconds_for_10001_sets_extrapolated": 10001 * ms * 1e-3 / len(hits),
+                 "last_chunk_stage_ms_rank0": {k: v[0] for k, v in st.items()},
+                 "set_alone_equals_set_in_job": bool(alone), "ok": bool(alone)})
+    return info
+
+
 def full_shape(env, args):
     """North-star target (BASELINE.json): 200 000 x 1 829 synthetic table, 1 000 permutations + the real set, Spearman;
     then config C3 (all unordered pairs, Spearman + Pearson) on the same resident table.  N > 1: rank 0 makes the table,
@@ -724,6 +907,8 @@ def full_shape(env, args):
     ctx.set_expression_device(X_dev.data_ptr(), N, n, keepalive=X_dev)
     ctx.prepare()
     ctx.set_features_raw(*feats)
+    if rank == 0:
+        ctx._feature_chroms = [str(u) for u in uniq]          # (what set_features would have recorded: permute_map maps chromosome names)
     g = ctx.pairs(ga, gb, ranked=True)
     glist = np.sort(np.where(np.isnan(g), -99.0, g))
     ctx.set_global_list(glist)
@@ -870,6 +1055,12 @@ def full_shape(env, args):
     flag = env.max_over_ranks(0.0 if parity["ok"] else 1.0) == 0.0
     parity["ok"] = bool(flag)
 
+    # ---- C4 on the same resident table -----------------------------------------------------------------------------
+    c4 = None
+    try:
+        c4 = config_c4(env, args, ctx, t, X_dev, N, n, seed)
+    except Exception as e:
+        c4 = {"ok": False, "error": f"{type(e).__name__}: {e}"}
     # ---- C3: all unordered pairs on the resident table ------------------------------------------------------------
     allp = None
     try:
@@ -920,6 +1111,10 @@ def full_shape(env, args):
             "parity": parity,
             "cpu_baseline": cpu,
         }
+        if c4 is not None:
+            full["c4"] = c4
+            if not c4.get("ok", False):
+                full["parity"]["ok"] = False
     ctx.close()
     return full, allp
 

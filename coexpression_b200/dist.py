@@ -95,31 +95,45 @@ def score_layout(hit_counts, world):
 
 
 class SharedJob:
-    """All ranks construct it with the SAME list of hit sets (and an initialised NCCL process group) and call run()."""
+    """All ranks construct it with an initialised NCCL process group and call plan() / run() with the SAME list of hit sets.
+    The score buffers are allocated (and their IPC handles exchanged) once and again only when a larger list arrives."""
 
     def __init__(self, ctx, hit_sets, device):
-        self.ctx, self.hit_sets, self.device = ctx, hit_sets, device
+        self.ctx, self.device = ctx, device
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.cap = -1
+        self.hit_sets = None
+        if hit_sets is not None:
+            self.plan(hit_sets)
+
+    def plan(self, hit_sets):
+        self.hit_sets = hit_sets
         counts = [len(h) for h in hit_sets]
         self.shards, self.owner, self.score_off, sizes = score_layout(counts, self.world)
         self.mine = self.shards[self.rank]
-        handle = ctx.shard_scores_alloc(self.world, self.rank, int(sizes[self.rank]))
-        if self.world > 1:
-            t = torch.tensor(list(handle), dtype=torch.uint8, device=device)
-            got = [torch.zeros_like(t) for _ in range(self.world)]
-            dist.all_gather(got, t)
-            for r, h in enumerate(got):
-                if r != self.rank:
-                    ctx.shard_scores_open(r, bytes(h.cpu().tolist()))
+        need = int(sizes.max()) if len(sizes) else 0          # the same number on every rank: they (re)allocate together
+        if need > self.cap:
+            self.barrier()                                     # nobody still writes into the buffers about to be replaced
+            handle = self.ctx.shard_scores_alloc(self.world, self.rank, need)
+            self.cap = need
+            if self.world > 1:
+                t = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+                got = [torch.zeros_like(t) for _ in range(self.world)]
+                dist.all_gather(got, t)
+                for r, h in enumerate(got):
+                    if r != self.rank:
+                        self.ctx.shard_scores_open(r, bytes(h.cpu().tolist()))
 
     def barrier(self):
         torch.cuda.synchronize()
         if self.world > 1:
             dist.barrier()
 
-    def run(self, options, want_scores=False):
+    def run(self, options, want_scores=False, hit_sets=None):
         """-> api.BatchResult of this rank's permutations (self.mine)."""
+        if hit_sets is not None:
+            self.plan(hit_sets)
         self.barrier()                       # nobody is still reading last run's scores
         self.ctx.shard_count(self.hit_sets, options, self.owner, self.score_off)
         self.barrier()                       # every rank's score rows have landed
