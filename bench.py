@@ -660,7 +660,7 @@ def strong_scaling(env, ctx, args, t, X_dev, opts, one_gpu_ms, dens_one_gpu):
 
     def step():
         ctx.set_expression_device(X_dev.data_ptr(), t.N, t.n, keepalive=X_dev)
-        ctx.prepare()
+        sjob.prepare()                                       # every rank ranks 1/N-th of the rows, for everybody (NVLink stores)
         last["res"] = sjob.run(opts)
 
     for _ in range(max(1, args.warmup)):
@@ -749,8 +749,14 @@ def run_job_timed(env, ctx, hits, opts, X_dev, N, n, steps, chunk=0):
             state["dens"] = jobs[-1].densities()
             state["mine"] = list(parts[-1])
 
-    ctx.set_expression_device(X_dev.data_ptr(), N, n, keepalive=X_dev)
-    ctx.prepare()
+    def prepare():
+        ctx.set_expression_device(X_dev.data_ptr(), N, n, keepalive=X_dev)
+        if env.world > 1:
+            sjob.prepare()
+        else:
+            ctx.prepare()
+
+    prepare()
     one_pass()                                               # warm-up
     ms = []
     for _ in range(steps):
@@ -758,8 +764,7 @@ def run_job_timed(env, ctx, hits, opts, X_dev, N, n, steps, chunk=0):
         env.barrier()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        ctx.set_expression_device(X_dev.data_ptr(), N, n, keepalive=X_dev)
-        ctx.prepare()
+        prepare()
         one_pass()
         e1.record(stream)
         torch.cuda.synchronize()
@@ -927,7 +932,7 @@ def full_shape(env, args):
 
         def step():
             ctx.set_expression_device(X_dev.data_ptr(), N, n, keepalive=X_dev)
-            ctx.prepare()
+            sjob.prepare()                                   # every rank ranks 1/N-th of the rows, for everybody (NVLink stores)
             last["res"] = sjob.run(opts)
     else:
         mine = list(range(Kall))

@@ -62,6 +62,10 @@ SIGNATURES = {
     "coex_set_pearson": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "coex_network_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(CoexParams), ctypes.c_int] +
                            [ctypes.c_void_p] * 10 + [ctypes.c_int]),
+    "coex_shard_table_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "coex_shard_table_open": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "coex_shard_prepare_rows": (ctypes.c_int, [ctypes.c_void_p]),
+    "coex_shard_prepare_finish": (ctypes.c_int, [ctypes.c_void_p]),
     "coex_shard_scores_alloc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_ll, ctypes.c_void_p]),
     "coex_shard_scores_open": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "coex_shard_count": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(CoexParams), ctypes.c_int] + [ctypes.c_void_p] * 4),

@@ -296,6 +296,22 @@ class CoexContext:
                                           g("counts"), 1), "coex_network_batch")
 
     # ---- ONE job shared by several GPUs (include/coexpression_b200.h section 3; dist.SharedJob drives these) ----------
+    def shard_table_export(self, world, rank):
+        """After set_expression: -> the 9 x 64 bytes of CUDA IPC handles of this rank's packed-table buffers."""
+        h = (ctypes.c_ubyte * (9 * 64))()
+        check(self.lib.coex_shard_table_export(self.h, int(world), int(rank), h), "coex_shard_table_export")
+        return bytes(h)
+
+    def shard_table_open(self, peer_rank, handles):
+        buf = (ctypes.c_ubyte * (9 * 64)).from_buffer_copy(bytes(handles))
+        check(self.lib.coex_shard_table_open(self.h, int(peer_rank), buf), "coex_shard_table_open")
+
+    def shard_prepare_rows(self):
+        check(self.lib.coex_shard_prepare_rows(self.h), "coex_shard_prepare_rows")
+
+    def shard_prepare_finish(self):
+        check(self.lib.coex_shard_prepare_finish(self.h), "coex_shard_prepare_finish")
+
     def shard_scores_alloc(self, world, rank, n_doubles):
         """-> the 64-byte CUDA IPC handle of this rank's score buffer."""
         h = (ctypes.c_ubyte * 64)()

@@ -55,47 +55,64 @@ static int check_ctx(coex_ctx *c) {
     return 0;
 }
 
-static int prepare_impl(coex_ctx *c) {
+// The packed table: sizes, buffers (stable addresses as long as the shape does not grow: their CUDA IPC handles are exchanged once
+// by a job shared by several GPUs), zero padding.
+static int prepare_reserve(coex_ctx *c) {
     if (!c->raw) COEX_FAIL("coex_prepare: call coex_set_expression first");
     const long long N = c->N;
     const int n = c->n;
     if (n > 8192) COEX_FAIL("coex_prepare: more than 8192 samples per row is not supported");
     c->n_pad = (int)round_up(n, 128);
     c->N_pad = round_up(N, 256);
-    stage_reset(c);
-    c->z_digits = 0;
     COEX_TRY(c->raw_sum.reserve(N)); COEX_TRY(c->raw_mean.reserve(N)); COEX_TRY(c->raw_xx.reserve(N));
     COEX_TRY(c->rawsum_pos.reserve(N));
     COEX_TRY(c->rank2.reserve((size_t)N * n));
     COEX_TRY(c->u_hi.reserve((size_t)c->N_pad * c->n_pad));
     COEX_TRY(c->u_lo.reserve((size_t)c->N_pad * c->n_pad));
     COEX_TRY(c->suu.reserve(c->N_pad)); COEX_TRY(c->sx.reserve(c->N_pad));
-    // padding rows must be exact zeros (they enter the GEMM as B rows)
+    COEX_TRY(c->icol.reserve(c->N_pad)); COEX_TRY(c->d_ndeg.reserve(1)); COEX_TRY(c->sxg.reserve(c->N_pad));
+    return 0;
+}
+
+// rows [row0, row1) of the table: rank transform + packing, in-order row statistics; stored to every destination of `ro` / `so`
+static int prepare_rows(coex_ctx *c, long long row0, long long row1, const RankOut &ro, const StatOut &so) {
+    const long long N = c->N;
+    const int n = c->n;
+    stage_reset(c);
+    c->z_digits = 0;
+    c->prepared = false;
+    // padding rows must be exact zeros (they enter the GEMM as B rows); every rank zeroes its own copy
     const size_t tail = (size_t)(c->N_pad - N) * c->n_pad;
     if (tail) {
         COEX_CUDA(cudaMemsetAsync(c->u_hi.p + (size_t)N * c->n_pad, 0, tail, c->stream));
         COEX_CUDA(cudaMemsetAsync(c->u_lo.p + (size_t)N * c->n_pad, 0, tail, c->stream));
     }
-    COEX_CUDA(cudaMemsetAsync(c->suu.p, 0, c->N_pad * sizeof(long long), c->stream));
-    COEX_CUDA(cudaMemsetAsync(c->sx.p, 0, c->N_pad * sizeof(double), c->stream));
-
+    if (c->N_pad > N) {
+        COEX_CUDA(cudaMemsetAsync(c->suu.p + N, 0, (c->N_pad - N) * sizeof(long long), c->stream));
+        COEX_CUDA(cudaMemsetAsync(c->sx.p + N, 0, (c->N_pad - N) * sizeof(double), c->stream));
+    }
     COEX_TRY(stage_begin(c, ST_RANK));
-    const int P2 = std::max(32, next_pow2(n));         // at least one warp-wide block of the in-register sort stages
-    const size_t smem = (size_t)P2 * 10 + (size_t)c->n_pad * 2;
-    COEX_CUDA(cudaFuncSetAttribute(rank_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rank_pack_kernel<<<(unsigned)N, kRankThreads, smem, c->stream>>>(
-        c->raw, N, n, c->n_pad, P2, c->rank2.p, c->u_hi.p, c->u_lo.p, c->suu.p, c->sx.p);
-    COEX_CUDA(cudaGetLastError());
+    if (row1 > row0) {
+        const int P2 = std::max(32, next_pow2(n));         // at least one warp-wide block of the in-register sort stages
+        const size_t smem = (size_t)P2 * 10 + (size_t)c->n_pad * 2;
+        COEX_CUDA(cudaFuncSetAttribute(rank_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rank_pack_kernel<<<(unsigned)(row1 - row0), kRankThreads, smem, c->stream>>>(c->raw, N, n, c->n_pad, P2, row0, ro);
+        COEX_CUDA(cudaGetLastError());
+    }
     COEX_TRY(stage_end(c, 1));
-
     COEX_TRY(stage_begin(c, ST_ROWSTATS));
-    rowstats_kernel<<<(unsigned)((N + kStatRows - 1) / kStatRows), 256, 0, c->stream>>>(
-        c->raw, N, n, c->raw_sum.p, c->raw_mean.p, c->raw_xx.p, c->rawsum_pos.p);
-    COEX_CUDA(cudaGetLastError());
+    if (row1 > row0) {
+        rowstats_kernel<<<(unsigned)((row1 - row0 + kStatRows - 1) / kStatRows), 256, 0, c->stream>>>(c->raw, row1, n, row0, so);
+        COEX_CUDA(cudaGetLastError());
+    }
     COEX_TRY(stage_end(c, 1));
-    COEX_TRY(c->icol.reserve(c->N_pad)); COEX_TRY(c->d_ndeg.reserve(1)); COEX_TRY(c->sxg.reserve(c->N_pad));
+    return 0;
+}
+
+// what needs the WHOLE packed table: float reciprocal half-norms, guarded half-norms, number of zero-variance rows
+static int prepare_finish(coex_ctx *c) {
     COEX_CUDA(cudaMemsetAsync(c->d_ndeg.p, 0, sizeof(int), c->stream));
-    icol_kernel<<<(unsigned)((c->N_pad + 255) / 256), 256, 0, c->stream>>>(c->sx.p, c->rawsum_pos.p, N, c->N_pad, c->icol.p, c->sxg.p, c->d_ndeg.p);
+    icol_kernel<<<(unsigned)((c->N_pad + 255) / 256), 256, 0, c->stream>>>(c->sx.p, c->rawsum_pos.p, c->N, c->N_pad, c->icol.p, c->sxg.p, c->d_ndeg.p);
     COEX_CUDA(cudaGetLastError());
     c->launches += 1;
     // no synchronisation here: the count of zero-variance rows stays on the device (the count kernels read it there),
@@ -103,6 +120,20 @@ static int prepare_impl(coex_ctx *c) {
     COEX_TRY(tc_invalidate(c));
     c->prepared = true;
     return 0;
+}
+
+static void local_outputs(coex_ctx *c, RankOut &ro, StatOut &so) {
+    ro = RankOut{}; so = StatOut{};
+    ro.rank2[0] = c->rank2.p; ro.hi[0] = c->u_hi.p; ro.lo[0] = c->u_lo.p; ro.suu[0] = c->suu.p; ro.sx[0] = c->sx.p; ro.n_dst = 1;
+    so.sum[0] = c->raw_sum.p; so.mean[0] = c->raw_mean.p; so.xx[0] = c->raw_xx.p; so.pos[0] = c->rawsum_pos.p; so.n_dst = 1;
+}
+
+static int prepare_impl(coex_ctx *c) {
+    COEX_TRY(prepare_reserve(c));
+    RankOut ro; StatOut so;
+    local_outputs(c, ro, so);
+    COEX_TRY(prepare_rows(c, 0, c->N, ro, so));
+    return prepare_finish(c);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -742,6 +773,7 @@ int coex_destroy(coex_ctx *c) {
     c->dd_items.release(); c->dd_qperm.release(); c->pl_cnt.release(); c->pl_cursor.release(); c->pl_ustart.release(); c->pl_nitems.release();
     c->pl_itemoff.release(); c->pl_bounds.release(); c->pl_meta.release(); c->pl_err.release(); c->dd_gthr.release(); c->dd_tab.release();
     for (void *p : c->peer_mapped) if (p) cudaIpcCloseMemHandle(p);
+    for (void *p : c->tab_mapped) if (p) cudaIpcCloseMemHandle(p);
     c->shard_scores.release(); c->d_perm_scores.release();
     cudaStreamDestroy(c->stream);
     delete c;
@@ -1060,6 +1092,76 @@ int coex_shard_scores_open(coex_ctx *c, int peer_rank, const void *ipc_handle) {
     return 0;
 }
 
+// The packed table of a shared job: every rank ranks its block of rows and stores the results into every rank's copy.
+static const int kTabBufs = 9;
+static void *tab_local(coex_ctx *c, int i) {
+    switch (i) {
+        case 0: return c->rank2.p; case 1: return c->u_hi.p; case 2: return c->u_lo.p; case 3: return c->suu.p; case 4: return c->sx.p;
+        case 5: return c->raw_sum.p; case 6: return c->raw_mean.p; case 7: return c->raw_xx.p; default: return c->rawsum_pos.p;
+    }
+}
+
+int coex_shard_table_export(coex_ctx *c, int world, int rank, void *ipc_handles_out) {
+    COEX_TRY(check_ctx(c));
+    if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || !ipc_handles_out) COEX_FAIL("coex_shard_table_export: bad argument (at most 8 ranks)");
+    COEX_TRY(prepare_reserve(c));
+    for (void *p : c->tab_mapped) if (p) cudaIpcCloseMemHandle(p);
+    c->tab_mapped.assign((size_t)world * kTabBufs, nullptr);
+    c->tab_peer.assign((size_t)world * kTabBufs, nullptr);
+    c->shard_world = world; c->shard_rank = rank;
+    c->tab_N = c->N; c->tab_n = c->n;
+    for (int i = 0; i < kTabBufs; ++i) {
+        c->tab_peer[(size_t)rank * kTabBufs + i] = tab_local(c, i);
+        cudaIpcMemHandle_t h;
+        COEX_CUDA(cudaIpcGetMemHandle(&h, tab_local(c, i)));
+        memcpy(static_cast<unsigned char *>(ipc_handles_out) + 64 * i, &h, sizeof h);
+    }
+    return 0;
+}
+
+int coex_shard_table_open(coex_ctx *c, int peer_rank, const void *ipc_handles) {
+    COEX_TRY(check_ctx(c));
+    if (c->tab_peer.size() != (size_t)c->shard_world * kTabBufs) COEX_FAIL("coex_shard_table_open: call coex_shard_table_export first");
+    if (peer_rank < 0 || peer_rank >= c->shard_world || !ipc_handles) COEX_FAIL("coex_shard_table_open: bad argument");
+    if (peer_rank == c->shard_rank) return 0;
+    for (int i = 0; i < kTabBufs; ++i) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const unsigned char *>(ipc_handles) + 64 * i, sizeof h);
+        void *p = nullptr;
+        COEX_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c->tab_mapped[(size_t)peer_rank * kTabBufs + i] = p;
+        c->tab_peer[(size_t)peer_rank * kTabBufs + i] = p;
+    }
+    return 0;
+}
+
+int coex_shard_prepare_rows(coex_ctx *c) {
+    COEX_TRY(check_ctx(c));
+    const int W = c->shard_world, r = c->shard_rank;
+    if (c->tab_peer.size() != (size_t)W * kTabBufs || c->tab_N != c->N || c->tab_n != c->n)
+        COEX_FAIL("coex_shard_prepare_rows: export / open the table buffers for this table shape first");
+    for (int i = 0; i < kTabBufs; ++i)
+        if (tab_local(c, i) != c->tab_peer[(size_t)r * kTabBufs + i]) COEX_FAIL("coex_shard_prepare_rows: table buffers were reallocated since the export");
+    RankOut ro{}; StatOut so{};
+    for (int d = 0; d < W; ++d) {
+        void **t = &c->tab_peer[(size_t)d * kTabBufs];
+        for (int i = 0; i < kTabBufs; ++i) if (!t[i]) COEX_FAIL("coex_shard_prepare_rows: the table of rank " + std::to_string(d) + " is not mapped");
+        ro.rank2[d] = (uint16_t *)t[0]; ro.hi[d] = (int8_t *)t[1]; ro.lo[d] = (int8_t *)t[2]; ro.suu[d] = (long long *)t[3]; ro.sx[d] = (double *)t[4];
+        so.sum[d] = (double *)t[5]; so.mean[d] = (double *)t[6]; so.xx[d] = (double *)t[7]; so.pos[d] = (unsigned char *)t[8];
+    }
+    ro.n_dst = so.n_dst = W;
+    const long long chunk = round_up((c->N + W - 1) / W, 32);
+    const long long row0 = std::min(c->N, (long long)r * chunk), row1 = std::min(c->N, row0 + chunk);
+    COEX_TRY(prepare_rows(c, row0, row1, ro, so));
+    COEX_CUDA(cudaStreamSynchronize(c->stream));            // my rows have landed everywhere; the caller's barrier tells the peers
+    return 0;
+}
+
+int coex_shard_prepare_finish(coex_ctx *c) {
+    COEX_TRY(check_ctx(c));
+    return prepare_finish(c);
+}
+
 int coex_shard_count(coex_ctx *c, const coex_params *prm, int K, const long long *perm_off, const int *hit_rows,
                      const int *perm_owner, const long long *perm_score_off) {
     COEX_TRY(check_ctx(c));
@@ -1160,8 +1262,9 @@ void getPearson(double *dataAll, double *resultAll, int *idxa_all, int *idxb_all
         COEX_CUDA(cudaMemcpyAsync(c->raw_own.p, dataAll, (size_t)rows * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         c->raw = c->raw_own.p; c->N = rows; c->n = n;
         COEX_TRY(c->raw_sum.reserve(rows)); COEX_TRY(c->raw_mean.reserve(rows)); COEX_TRY(c->raw_xx.reserve(rows));
-        rowstats_kernel<<<(unsigned)((rows + kStatRows - 1) / kStatRows), 256, 0, c->stream>>>(
-            c->raw, rows, n, c->raw_sum.p, c->raw_mean.p, c->raw_xx.p, nullptr);
+        StatOut so{};
+        so.sum[0] = c->raw_sum.p; so.mean[0] = c->raw_mean.p; so.xx[0] = c->raw_xx.p; so.pos[0] = nullptr; so.n_dst = 1;
+        rowstats_kernel<<<(unsigned)((rows + kStatRows - 1) / kStatRows), 256, 0, c->stream>>>(c->raw, rows, n, 0, so);
         COEX_CUDA(cudaGetLastError());
         c->prepared = true;               // only the raw statistics are needed by which == 0
         COEX_TRY(coex_pairs(c, 0, idxa_all, idxb_all, nPromPairs, resultAll, 0));

@@ -19,19 +19,33 @@ namespace coex {
 // HBM traffic per element: 8 B read (f64) + 2 B (u16 2*rank) + 2 B (two int8 digits) written.
 // -------------------------------------------------------------------------------------------
 constexpr int kRankThreads = 256;
+constexpr int kMaxPeers = 8;
+
+// Where a row's outputs go: one destination on a single GPU; on a job shared by several GPUs every rank ranks ITS block of rows
+// and stores the results into its own copy AND into every peer's copy of the packed table (peer memory mapped with CUDA IPC,
+// NVLink / NVSwitch stores issued by this kernel) -- the table is never ranked twice and there is no all-gather afterwards.
+struct RankOut {
+    uint16_t *rank2[kMaxPeers];
+    int8_t *hi[kMaxPeers], *lo[kMaxPeers];
+    long long *suu[kMaxPeers];
+    double *sx[kMaxPeers];
+    int n_dst;
+};
+struct StatOut {
+    double *sum[kMaxPeers], *mean[kMaxPeers], *xx[kMaxPeers];
+    unsigned char *pos[kMaxPeers];
+    int n_dst;
+};
 
 __global__ void __launch_bounds__(kRankThreads)
-rank_pack_kernel(const double *__restrict__ raw, long long N, int n, int n_pad, int P2,
-                 uint16_t *__restrict__ rank2_out, int8_t *__restrict__ hi_out,
-                 int8_t *__restrict__ lo_out, long long *__restrict__ suu_out,
-                 double *__restrict__ sx_out) {
+rank_pack_kernel(const double *__restrict__ raw, long long N, int n, int n_pad, int P2, long long first_row, RankOut out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *keys = reinterpret_cast<double *>(smem_raw);                    // [P2]
     uint16_t *idx = reinterpret_cast<uint16_t *>(keys + P2);                // [P2]
     uint16_t *r2 = idx + P2;                                                // [n_pad]
     __shared__ long long red[kRankThreads / 32];
 
-    const long long row = blockIdx.x;
+    const long long row = first_row + blockIdx.x;
     const int tid = threadIdx.x;
     const double *x = raw + row * (long long)n;
 
@@ -156,10 +170,10 @@ rank_pack_kernel(const double *__restrict__ raw, long long N, int n, int n_pad, 
 
     // outputs: u16 2*rank, digits of u = 2*rank-(n+1) = 128*hi + lo, lo in [-64, 63]
     long long acc = 0;
-    uint16_t *r2row = rank2_out + row * (long long)n;
     for (int c = tid; c < n; c += kRankThreads) {
-        r2row[c] = r2[c];
-        const long long u = (long long)r2[c] - (n + 1);
+        const uint16_t v = r2[c];
+        for (int d = 0; d < out.n_dst; ++d) out.rank2[d][row * (long long)n + c] = v;
+        const long long u = (long long)v - (n + 1);
         acc += u * u;
     }
     const long long prow = row * (long long)n_pad;
@@ -173,8 +187,10 @@ rank_pack_kernel(const double *__restrict__ raw, long long N, int n, int n_pad, 
             h[e] = (int8_t)hh;
             l[e] = (int8_t)(u - (hh << 7));
         }
-        *reinterpret_cast<int4 *>(hi_out + prow + (v << 4)) = *reinterpret_cast<const int4 *>(h);
-        *reinterpret_cast<int4 *>(lo_out + prow + (v << 4)) = *reinterpret_cast<const int4 *>(l);
+        for (int d = 0; d < out.n_dst; ++d) {
+            *reinterpret_cast<int4 *>(out.hi[d] + prow + (v << 4)) = *reinterpret_cast<const int4 *>(h);
+            *reinterpret_cast<int4 *>(out.lo[d] + prow + (v << 4)) = *reinterpret_cast<const int4 *>(l);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -183,9 +199,9 @@ rank_pack_kernel(const double *__restrict__ raw, long long N, int n, int n_pad, 
     if (tid == 0) {
         long long s = 0;
         for (int w = 0; w < kRankThreads / 32; ++w) s += red[w];
-        suu_out[row] = s;
         // reference: xx = sum((rank-mean)^2) = s/4 exactly; sqrt as coexpression_v2.c:113
-        sx_out[row] = sqrt(0.25 * (double)s);
+        const double sxv = sqrt(0.25 * (double)s);
+        for (int d = 0; d < out.n_dst; ++d) { out.suu[d][row] = s; out.sx[d][row] = sxv; }
     }
 }
 
@@ -197,12 +213,10 @@ rank_pack_kernel(const double *__restrict__ raw, long long N, int n, int n_pad, 
 constexpr int kStatRows = 32;
 
 __global__ void __launch_bounds__(256)
-rowstats_kernel(const double *__restrict__ data, long long N, int n, double *__restrict__ sum_out,
-                double *__restrict__ mean_out, double *__restrict__ xx_out,
-                unsigned char *__restrict__ pos_out) {
+rowstats_kernel(const double *__restrict__ data, long long N, int n, long long first_row, StatOut out) {
     __shared__ double tile[kStatRows][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const long long row0 = (long long)blockIdx.x * kStatRows;
+    const long long row0 = first_row + (long long)blockIdx.x * kStatRows;
     double s = 0.0, mean = 0.0, xx = 0.0;
     for (int pass = 0; pass < 2; ++pass) {
         for (int c0 = 0; c0 < n; c0 += 32) {
@@ -230,10 +244,12 @@ rowstats_kernel(const double *__restrict__ data, long long N, int n, double *__r
     }
     const long long row = row0 + tx;
     if (ty == 0 && row < N) {
-        sum_out[row] = s;
-        mean_out[row] = mean;
-        xx_out[row] = xx;
-        if (pos_out) pos_out[row] = (s > 0.0) ? 1 : 0;
+        for (int d = 0; d < out.n_dst; ++d) {
+            out.sum[d][row] = s;
+            out.mean[d][row] = mean;
+            out.xx[d][row] = xx;
+            if (out.pos[d]) out.pos[d][row] = (s > 0.0) ? 1 : 0;
+        }
     }
 }
 

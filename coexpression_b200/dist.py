@@ -130,6 +130,31 @@ class SharedJob:
         if self.world > 1:
             dist.barrier()
 
+    def _exchange(self, payload):
+        """all-gather of one byte string per rank -> list over ranks."""
+        if self.world == 1:
+            return [payload]
+        t = torch.tensor(list(payload), dtype=torch.uint8, device=self.device)
+        got = [torch.zeros_like(t) for _ in range(self.world)]
+        dist.all_gather(got, t)
+        return [bytes(h.cpu().tolist()) for h in got]
+
+    def prepare(self):
+        """Rank transform + packing of the table the contexts hold (every rank: the same table, set_expression done): each
+        rank ranks its block of rows and stores the results into every rank's packed table over NVLink.  Replaces ctx.prepare()."""
+        shape = (self.ctx.N, self.ctx.n)
+        if getattr(self, "_table_shape", None) != shape:
+            self.barrier()
+            handles = self._exchange(self.ctx.shard_table_export(self.world, self.rank))
+            for r, h in enumerate(handles):
+                if r != self.rank:
+                    self.ctx.shard_table_open(r, h)
+            self._table_shape = shape
+        self.barrier()                       # nobody still reads the packed table of the previous run
+        self.ctx.shard_prepare_rows()
+        self.barrier()                       # every block of rows has landed everywhere
+        self.ctx.shard_prepare_finish()
+
     def run(self, options, want_scores=False, hit_sets=None):
         """-> api.BatchResult of this rank's permutations (self.mine)."""
         if hit_sets is not None:

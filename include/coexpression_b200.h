@@ -176,6 +176,17 @@ int coex_network_batch(coex_ctx *ctx, const coex_params *params, int K,
  *    coex_shard_finish        K = THIS rank's permutations, in the order their blocks have in its buffer; outputs as
  *                             coex_network_batch (scores: optional host copy of the blocks; on_device as there)
  * ---------------------------------------------------------------------------------------- */
+/* The rank transform of a shared job (optional; every rank may also call coex_prepare on the whole table): rank r ranks and
+ * packs ITS block of rows only, and rank_pack_kernel / rowstats_kernel store every result into its own AND into every peer's
+ * packed table (nine buffers per rank, mapped with CUDA IPC) -- no rank ranks a row twice, nothing is gathered afterwards.
+ *   coex_shard_table_export   after coex_set_expression: sizes the packed table, -> 9 x 64 bytes of IPC handles (at most 8 ranks)
+ *   coex_shard_table_open     maps the nine buffers of a peer
+ *   coex_shard_prepare_rows   my rows -> everybody (returns when the stores have landed); then ONE barrier by the caller
+ *   coex_shard_prepare_finish what needs the whole table (reciprocal norms); the context is then prepared as after coex_prepare */
+int coex_shard_table_export(coex_ctx *ctx, int world, int rank, void *ipc_handles_out);
+int coex_shard_table_open(coex_ctx *ctx, int peer_rank, const void *ipc_handles);
+int coex_shard_prepare_rows(coex_ctx *ctx);
+int coex_shard_prepare_finish(coex_ctx *ctx);
 int coex_shard_scores_alloc(coex_ctx *ctx, int world, int rank, long long n_doubles, void *ipc_handle_out);
 int coex_shard_scores_open(coex_ctx *ctx, int peer_rank, const void *ipc_handle);
 int coex_shard_count(coex_ctx *ctx, const coex_params *params, int K, const long long *perm_off, const int *hit_rows,

@@ -780,9 +780,12 @@ def test_shared_job_entry_points_on_one_rank_equal_the_plain_call():
             g = ctx.pairs(ga, gb, ranked=opts.correlationmeasure == "Spearman")
             ctx.set_global_list(np.sort(np.where(np.isnan(g), -99.0, g)))
             want = ctx.network_batch(hits, opts, want_scores=True)
+            ranks = ctx.ranks()
             job = SharedJob(ctx, hits, None)
             assert job.mine == list(range(len(hits)))
             got = job.run(opts, want_scores=True)
+            job.prepare()                                        # the rank transform through the shared-job entry points
+            assert np.array_equal(ctx.ranks(), ranks)
             again = job.run(opts, want_scores=True)              # the buffers are reused
         for res in (got, again):
             for name in ("n_groups", "group_of_hit", "group_label", "group_winner", "group_density", "hit_score", "scores"):

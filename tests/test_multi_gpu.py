@@ -99,12 +99,15 @@ def _shared_worker(rank, world, port, q):
     t, hits, ga, gb = _inputs()
     opts = Options(anticorrelation=True)
     with CoexContext(rank) as ctx:
-        ctx.set_expression(t.X); ctx.prepare()
+        ctx.set_expression(t.X)
+        job = SharedJob(ctx, None, dev)
+        job.prepare()                                            # every rank ranks half of the rows, for both packed tables
         ctx.set_features(t.chrom, t.start, t.end, t.names)
         g = ctx.pairs(ga, gb, ranked=True)
         ctx.set_global_list(np.sort(np.where(np.isnan(g), -99.0, g)))
-        job = SharedJob(ctx, hits, dev)
+        job.plan(hits)
         res = job.run(opts, want_scores=True)
+        job.prepare()
         res2 = job.run(opts)                                     # a second run over the same (reused) peer buffers
         local = [res.perm(j)["density"].copy() for j in range(len(job.mine))]
         same = all(np.array_equal(res2.perm(j)["density"], local[j]) for j in range(len(job.mine)))
