@@ -975,6 +975,23 @@ def full_shape(env, args):
     dens_mine = job.densities() if job is not None else [last["res"].perm(j)["density"].copy() for j in range(len(mine))]
     allden = gather_densities(mine, dens_mine, Kall, device=dev)
     gather_ms = env.max_over_ranks(1e3 * (time.perf_counter() - w0))
+    # A14 on the gathered vectors (2-collate-results.py:67-76,142,161-163): pooled null of the permuted densities, empirical p and
+    # BH / BY of the real data's groups, on the device (coex_collate) -- checked against the host mirror of the reference's functions
+    collation = None
+    if rank == 0 and allden[0] is not None and len(allden[0]):
+        pool = np.concatenate([d for d in allden[1:] if d is not None and len(d)]) if Kall > 1 else np.zeros(0)
+        c0 = time.perf_counter()
+        col = ctx.collate(pool, allden[0])
+        c_ms = 1e3 * (time.perf_counter() - c0)
+        collation = {"real_groups": int(len(allden[0])), "pooled_permuted_densities": int(pool.size), "ms_host_clock": c_ms,
+                     "min_p": float(min(col["p"])), "groups_fdr_bh_below_0.05": int(sum(1 for v in col["fdr_bh"] if v < 0.05))}
+        if not args.no_cpu_baseline:
+            from coexpression_b200.collate import collate_numbers
+            want = collate_numbers(pool.tolist(), {"indmeasure": {str(i): float(v) for i, v in enumerate(allden[0])},
+                                                   "indjoined": {str(i): {} for i in range(len(allden[0]))}})
+            collation["device_equals_host_mirror_of_reference"] = bool(
+                col["p"] == want["p"] and col["fdr_bh"] == [float(x) for x in want["fdr_bh"]] and
+                col["fdr_by"] == [float(x) for x in want["fdr_by"]])
     U_mine = int(my_rows.size)
     U_sum = env.sum_over_ranks(U_mine)
     my_perm_off = np.zeros(len(mine) + 1, dtype=np.int64)
@@ -1111,11 +1128,14 @@ def full_shape(env, args):
             "stage_ms_rank0": {s: per[s][0] for s in STAGES},
             "roofline_all": roof,
             "gather_ms_host_clock": gather_ms,
+            "collation": collation,
             "e2e": e2e,
             "clocks": clocks,
             "parity": parity,
             "cpu_baseline": cpu,
         }
+        if collation is not None and collation.get("device_equals_host_mirror_of_reference") is False:
+            full["parity"]["ok"] = False
         if c4 is not None:
             full["c4"] = c4
             if not c4.get("ok", False):

@@ -361,6 +361,22 @@ class CoexContext:
         return BatchResult(perm_off, hit_rows, n_groups[:K], group_of_hit[:H], group_label[:H], group_winner[:H],
                            group_density[:H], hit_score[:H], scores, None)
 
+    # ---- A14: pooled null, empirical p, FDR (2-collate-results.py:67-76,142,161-163) on the device ----------------------
+    def collate(self, pool, realmeasures, pool_device_ptr=None, n_pool=None):
+        """pool: host array of every permuted density (or pool_device_ptr + n_pool: a device buffer, e.g. the gathered block);
+        -> dict(p ascending, fdr_bh, fdr_by) as collate.collate_numbers computes them on the host."""
+        real = np.ascontiguousarray(realmeasures, dtype=np.float64)
+        G = real.size
+        p, bh, by = np.zeros(max(G, 1)), np.zeros(max(G, 1)), np.zeros(max(G, 1))
+        if pool_device_ptr is not None:
+            src, npool, on_dev = ctypes.c_void_p(pool_device_ptr), int(n_pool), 1
+        else:
+            pool = np.ascontiguousarray(pool, dtype=np.float64)
+            src, npool, on_dev = (pool.ctypes.data if pool.size else None), int(pool.size), 0
+        check(self.lib.coex_collate(self.h, src, npool, on_dev, real.ctypes.data if G else None, G, p.ctypes.data, bh.ctypes.data,
+                                    by.ctypes.data), "coex_collate")
+        return {"p": p[:G].tolist(), "fdr_bh": bh[:G].tolist(), "fdr_by": by[:G].tolist()}
+
     # ---- introspection ------------------------------------------------------------------------------
     def stage_ms(self):
         out = {}

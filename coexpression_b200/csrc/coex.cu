@@ -12,6 +12,7 @@
 #include "network.cuh"
 #include "allpairs.cuh"
 #include "permute.cuh"
+#include "collate.cuh"
 
 #include <algorithm>
 #include <ctime>
@@ -235,10 +236,22 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     const int grid_max = std::max(1, per_sm) * c->sm_count;
     COEX_TRY(c->dd_gthr.reserve((size_t)grid_max * Tcap * 6));      // 3 x Tcap records of 16 bytes per CTA
     if (tdbg) fprintf(stderr, "[coex host] count kernel: %zu bytes of shared memory, %d CTA(s) per SM, Tcap %d, bitmap words %d\n", smem, per_sm, Tcap, bm_words);
+    // Edge score of every possible bisect index, built ON THE HOST with the C library's log exactly as the reference evaluates
+    // -math.log(p1, 10) = -(log(p1) / log(10)) (1-make-network.py:310; CPython divides two libm logs): the scores, the `>= threshold`
+    // selections and the equal-density ties of the iterative removal (quirk Q7) are then decided on the reference's own doubles
+    // (a device log10 differs in the last bit).  N + 1 values, rebuilt only when N or -a change.
     COEX_TRY(c->dd_tab.reserve((size_t)N + 1));
-    score_table_kernel<<<(unsigned)((N + 256) / 256), 256, 0, st>>>(c->dd_tab.p, N, prm->anticorrelation);
-    COEX_CUDA(cudaGetLastError());
-    c->launches += 1;
+    if (c->tab_for_N != N || c->tab_for_anticor != prm->anticorrelation) {
+        c->h_score_tab.resize((size_t)N + 1);
+        const double len = (double)(N - 1), l10 = std::log(10.0);
+        for (long long idx = 0; idx <= N; ++idx) {
+            double p1 = 1.0 - (double)idx / len;
+            if (prm->anticorrelation) p1 = std::min(p1, (double)idx / len);
+            c->h_score_tab[(size_t)idx] = (p1 > 0.0) ? -(std::log(p1) / l10) : 0.0;     // math.log raises for p1 <= 0 -> score 0 (Q4)
+        }
+        COEX_CUDA(cudaMemcpyAsync(c->dd_tab.p, c->h_score_tab.data(), ((size_t)N + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
+        c->tab_for_N = N; c->tab_for_anticor = prm->anticorrelation;
+    }
     DevBuf<unsigned long long> phase;
     const bool dbg = getenv("COEX_COUNT_DEBUG") != nullptr;
     if (dbg) { COEX_TRY(phase.reserve(16)); COEX_CUDA(cudaMemsetAsync(phase.p, 0, 16 * sizeof(unsigned long long), st)); }
@@ -1189,6 +1202,43 @@ int coex_shard_finish(coex_ctx *c, const coex_params *prm, int K, const long lon
                                           group_density, hit_score, scores, nullptr, on_device);
     c->shard_phase = 0;
     return status;
+}
+
+int coex_collate(coex_ctx *c, const double *pool, long long n_pool, int pool_on_device, const double *real, int G,
+                 double *p_out, double *bh_out, double *by_out) {
+    COEX_TRY(check_ctx(c));
+    if (G < 0 || G > kCollateMax || n_pool < 0 || (G > 0 && (!real || !p_out || !bh_out || !by_out)) || (n_pool > 0 && !pool))
+        COEX_FAIL("coex_collate: bad argument (at most 8192 real groups)");
+    if (G == 0) return 0;
+    cudaStream_t st = c->stream;
+    const int G2 = std::max(2, next_pow2(G));
+    DevBuf<double> d_pool, d_real, d_out;
+    DevBuf<unsigned long long> d_hist;
+    const double *dp = pool;
+    if (!pool_on_device && n_pool > 0) {
+        COEX_TRY(d_pool.reserve((size_t)n_pool));
+        COEX_CUDA(cudaMemcpyAsync(d_pool.p, pool, (size_t)n_pool * sizeof(double), cudaMemcpyHostToDevice, st));
+        dp = d_pool.p;
+    }
+    COEX_TRY(d_real.reserve((size_t)G)); COEX_TRY(d_out.reserve((size_t)3 * G)); COEX_TRY(d_hist.reserve((size_t)G + 1));
+    COEX_CUDA(cudaMemcpyAsync(d_real.p, real, (size_t)G * sizeof(double), cudaMemcpyHostToDevice, st));
+    COEX_CUDA(cudaMemsetAsync(d_hist.p, 0, ((size_t)G + 1) * sizeof(unsigned long long), st));
+    const size_t sm1 = (size_t)G2 * 8 + ((size_t)G + 1) * 4, sm2 = (size_t)G2 * 16;
+    COEX_CUDA(cudaFuncSetAttribute(collate_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+    COEX_CUDA(cudaFuncSetAttribute(collate_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+    if (n_pool > 0) {
+        const int grid = (int)std::min<long long>((n_pool + 1023) / 1024, (long long)c->sm_count);
+        collate_count_kernel<<<grid, 1024, sm1, st>>>(dp, n_pool, d_real.p, G, G2, d_hist.p);
+        COEX_KCHECK(st);
+    }
+    collate_finish_kernel<<<1, 1024, sm2, st>>>(d_real.p, G, G2, d_hist.p, n_pool, d_out.p, d_out.p + G, d_out.p + 2 * G);
+    COEX_KCHECK(st);
+    COEX_CUDA(cudaMemcpyAsync(p_out, d_out.p, (size_t)G * sizeof(double), cudaMemcpyDeviceToHost, st));
+    COEX_CUDA(cudaMemcpyAsync(bh_out, d_out.p + G, (size_t)G * sizeof(double), cudaMemcpyDeviceToHost, st));
+    COEX_CUDA(cudaMemcpyAsync(by_out, d_out.p + 2 * G, (size_t)G * sizeof(double), cudaMemcpyDeviceToHost, st));
+    COEX_CUDA(cudaStreamSynchronize(st));
+    d_pool.release(); d_real.release(); d_out.release(); d_hist.release();
+    return 0;
 }
 
 long long coex_launch_count(coex_ctx *c) { return c ? c->launches : 0; }

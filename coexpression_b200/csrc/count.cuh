@@ -46,7 +46,10 @@ __device__ __forceinline__ double edge_score_dev(long long idx, long long len, i
         const double p2 = (double)idx / (double)len;
         p1 = fmin(p1, p2);
     }
-    return (p1 == 0.0) ? 0.0 : -log10(p1);
+    // -math.log(p1, 10) of 1-make-network.py:310 is -(log(p1) / log(10)); the device log is within 1 ulp of the C library's, so
+    // this device function serves the side paths only (per-query cross-check kernel, global-list null): the production path
+    // looks the score up in a table the HOST built with the C library (coex.cu)
+    return (p1 > 0.0) ? -(log(p1) / log(10.0)) : 0.0;
 }
 
 // F64 == false: Spearman null from the integer strip, statistics taken from the same strip.

@@ -195,6 +195,14 @@ int coex_shard_finish(coex_ctx *ctx, const coex_params *params, int K, const lon
                       int *n_groups, int *group_of_hit, int *group_label, int *group_winner, double *group_density,
                       double *hit_score, double *scores, int on_device);
 
+/* A14, the consumer of the gathered density vectors (2-collate-results.py:67-76,142,161-163; coexfunctions.py:379-383 empiricalp,
+ * :333-358 fdr_correction): pool = every permuted density (device pointer if pool_on_device, e.g. the gathered block), real = the
+ * G densities of the real data (host).  p_out = sorted(empiricalp(x, pool) for x in real) (ascending), bh_out / by_out = the
+ * Benjamini-Hochberg ('indep') / Benjamini-Yekutieli ('negcorr') adjusted values aligned with p_out; host arrays of G doubles,
+ * bit-identical to the reference's arithmetic. */
+int coex_collate(coex_ctx *ctx, const double *pool, long long n_pool, int pool_on_device, const double *real, int G,
+                 double *p_out, double *bh_out, double *by_out);
+
 /* Introspection for bench.py: kernels launched by ctx so far, and per-stage device time (ms,
  * CUDA events on coex_stream) of the last coex_network_batch / coex_prepare call.
  * stage ids: 0 rank+pack, 1 row stats, 2 gather, 3 correlation GEMM, 4 count+score, 5 network, 6 unused (kept for ABI stability) */

@@ -687,6 +687,12 @@ def _oracle_vs_gpu(t, hits, opts, glist, R, ctx, **okw):
             worst = max(worst, abs(got["indmeasure"][grp] - v))
         for p_, v in want["allpromoterscores"].items():
             worst = max(worst, abs(got["allpromoterscores"][p_] - v))
+        if opts.correlationmeasure == "Spearman" and opts.nsp == 1.0 and len(h) > 1:
+            # the edge scores come from a table the host builds with the C library's log, as -math.log(p, 10) does: BIT-identical
+            S = res.score_matrix(k)
+            nm = [t.names[r] for r in h]
+            W = np.array([[0.0 if i == j else want["individualscores"][nm[i]][nm[j]] for j in range(len(h))] for i in range(len(h))])
+            assert np.array_equal(S, W), k
     assert worst <= 1e-6, worst                                # north_star tolerance
     return res
 
@@ -790,3 +796,25 @@ def test_shared_job_entry_points_on_one_rank_equal_the_plain_call():
         for res in (got, again):
             for name in ("n_groups", "group_of_hit", "group_label", "group_winner", "group_density", "hit_score", "scores"):
                 assert np.array_equal(getattr(res, name), getattr(want, name)), name
+
+
+def test_collate_on_device_equals_the_reference_arithmetic():
+    """Row A14 (2-collate-results.py:67-76,142,161-163): pooled null, empirical p, BH / BY on the device, bit for bit against
+    the host mirror of the reference's functions (which tests/test_reference_pin.py pins to the executed reference)."""
+    from coexpression_b200.api import CoexContext
+    from coexpression_b200.collate import collate_numbers
+    rng = np.random.default_rng(14)
+    with CoexContext() as ctx:
+        for n_pool, G in ((0, 5), (1, 1), (1000, 37), (250000, 612), (5000, 1500)):
+            pool = np.round(rng.gamma(2.0, 30.0, size=n_pool), 2)              # ties inside the pool
+            real = np.round(rng.gamma(2.0, 35.0, size=G), 2)
+            if G > 3 and n_pool:
+                real[0] = real[1]                                               # equal real densities
+                real[2] = pool[0]                                               # a real density equal to pool values
+                real[3] = pool.max() + 1.0                                      # above everything: p = 0 -> FDR 0
+            want = collate_numbers(pool.tolist(), {"indmeasure": {str(i): float(v) for i, v in enumerate(real)},
+                                                   "indjoined": {str(i): {} for i in range(G)}})
+            got = ctx.collate(pool, real)
+            assert got["p"] == want["p"], (n_pool, G)
+            assert got["fdr_bh"] == [float(x) for x in want["fdr_bh"]], (n_pool, G)
+            assert got["fdr_by"] == [float(x) for x in want["fdr_by"]], (n_pool, G)
