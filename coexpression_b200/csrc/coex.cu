@@ -140,6 +140,28 @@ static int prepare_impl(coex_ctx *c) {
 // ------------------------------------------------------------------------------------------
 // de-duplicated Spearman null: unique hit rows -> GEMM strips -> count_dedup_kernel
 // ------------------------------------------------------------------------------------------
+static int ensure_score_table(coex_ctx *c, const coex_params *prm) {
+    const long long N = c->N;
+    cudaStream_t st = c->stream;
+    // Edge score of every possible bisect index, built ON THE HOST with the C library's log exactly as the reference evaluates
+    // -math.log(p1, 10) = -(log(p1) / log(10)) (1-make-network.py:310; CPython divides two libm logs): the scores, the `>= threshold`
+    // selections and the equal-density ties of the iterative removal (quirk Q7) are then decided on the reference's own doubles
+    // (a device log10 differs in the last bit).  N + 1 values, rebuilt only when N or -a change.
+    COEX_TRY(c->dd_tab.reserve((size_t)N + 1));
+    if (c->tab_for_N != N || c->tab_for_anticor != prm->anticorrelation) {
+        c->h_score_tab.resize((size_t)N + 1);
+        const double len = (double)(N - 1), l10 = std::log(10.0);
+        for (long long idx = 0; idx <= N; ++idx) {
+            double p1 = 1.0 - (double)idx / len;
+            if (prm->anticorrelation) p1 = std::min(p1, (double)idx / len);
+            c->h_score_tab[(size_t)idx] = (p1 > 0.0) ? -(std::log(p1) / l10) : 0.0;     // math.log raises for p1 <= 0 -> score 0 (Q4)
+        }
+        COEX_CUDA(cudaMemcpyAsync(c->dd_tab.p, c->h_score_tab.data(), ((size_t)N + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
+        c->tab_for_N = N; c->tab_for_anticor = prm->anticorrelation;
+    }
+    return 0;
+}
+
 static int run_strip_gemm(coex_ctx *c, const int *d_rows, long long nq, long long nq_pad);
 static int run_strip_gemm_pearson(coex_ctx *c, const int *d_rows, long long nq, long long nq_pad, long long a_rows);
 
@@ -236,22 +258,7 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     const int grid_max = std::max(1, per_sm) * c->sm_count;
     COEX_TRY(c->dd_gthr.reserve((size_t)grid_max * Tcap * 6));      // 3 x Tcap records of 16 bytes per CTA
     if (tdbg) fprintf(stderr, "[coex host] count kernel: %zu bytes of shared memory, %d CTA(s) per SM, Tcap %d, bitmap words %d\n", smem, per_sm, Tcap, bm_words);
-    // Edge score of every possible bisect index, built ON THE HOST with the C library's log exactly as the reference evaluates
-    // -math.log(p1, 10) = -(log(p1) / log(10)) (1-make-network.py:310; CPython divides two libm logs): the scores, the `>= threshold`
-    // selections and the equal-density ties of the iterative removal (quirk Q7) are then decided on the reference's own doubles
-    // (a device log10 differs in the last bit).  N + 1 values, rebuilt only when N or -a change.
-    COEX_TRY(c->dd_tab.reserve((size_t)N + 1));
-    if (c->tab_for_N != N || c->tab_for_anticor != prm->anticorrelation) {
-        c->h_score_tab.resize((size_t)N + 1);
-        const double len = (double)(N - 1), l10 = std::log(10.0);
-        for (long long idx = 0; idx <= N; ++idx) {
-            double p1 = 1.0 - (double)idx / len;
-            if (prm->anticorrelation) p1 = std::min(p1, (double)idx / len);
-            c->h_score_tab[(size_t)idx] = (p1 > 0.0) ? -(std::log(p1) / l10) : 0.0;     // math.log raises for p1 <= 0 -> score 0 (Q4)
-        }
-        COEX_CUDA(cudaMemcpyAsync(c->dd_tab.p, c->h_score_tab.data(), ((size_t)N + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
-        c->tab_for_N = N; c->tab_for_anticor = prm->anticorrelation;
-    }
+    COEX_TRY(ensure_score_table(c, prm));
     DevBuf<unsigned long long> phase;
     const bool dbg = getenv("COEX_COUNT_DEBUG") != nullptr;
     if (dbg) { COEX_TRY(phase.reserve(16)); COEX_CUDA(cudaMemsetAsync(phase.p, 0, 16 * sizeof(unsigned long long), st)); }
@@ -518,6 +525,7 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
                 COEX_TRY(spearman_dedup_path(c, prm, K, perm_off, d_hits, Pmax, d_sc, d_cn));
             } else {
             const size_t smem = (size_t)T2max * 16;
+            COEX_TRY(ensure_score_table(c, prm));
             COEX_CUDA(cudaFuncSetAttribute(count_score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             COEX_CUDA(cudaFuncSetAttribute(count_score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             for (long long q0 = 0; q0 < H; q0 += Hs) {
@@ -526,6 +534,7 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
                 ca.ld = ld; ca.q0 = q0; ca.nq = nq; ca.perm_off = c->d_perm_off.p; ca.sc_off = c->d_sc_off.p;
                 ca.K = K; ca.hit_rows = d_hits; ca.sx = c->sx.p; ca.rawsum_pos = c->rawsum_pos.p; ca.N = c->N;
                 ca.anticor = prm->anticorrelation; ca.scores = d_sc; ca.counts = d_cn; ca.T2max = T2max;
+                ca.score_tab = c->dd_tab.p;
                 if (prm->measure == 0) {
                     COEX_TRY(run_strip_gemm(c, d_hits + q0, nq, round_up(nq, 256)));
                     ca.strip = c->strip.p;

@@ -38,6 +38,7 @@ struct CountArgs {
     double *scores;                 // [sum P_k^2]
     long long *counts;              // optional
     int T2max;                      // shared-memory capacity (power of two)
+    const double *score_tab;        // [N + 1] edge score of every bisect index of a list of N - 1 values (built on the host, coex.cu)
 };
 
 __device__ __forceinline__ double edge_score_dev(long long idx, long long len, int anticor) {
@@ -178,7 +179,7 @@ count_score_kernel(CountArgs a) {
     for (int s = tid; s < T; s += kCountThreads) {
         const long long idx = hist[s];
         const int j = origin[s];
-        sc[j] = edge_score_dev(idx, len, a.anticor);
+        sc[j] = (len == N - 1 && a.score_tab) ? a.score_tab[idx] : edge_score_dev(idx, len, a.anticor);
         if (cn) cn[j] = idx;
     }
 }
