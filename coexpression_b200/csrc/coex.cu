@@ -1023,7 +1023,7 @@ int coex_pairs(coex_ctx *c, int which, const int *idxa, const int *idxb, long lo
     }
     if (which == 1) {
         const long long blocks = (npairs * 32 + 255) / 256;
-        pairs_rank_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(c->rank2.p, c->n, da, db, npairs, c->sx.p, dout);
+        pairs_rank_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(c->u_hi.p, c->u_lo.p, c->n_pad, da, db, npairs, c->sx.p, dout);
     } else {
         const long long blocks = (npairs + kPairsPerBlock - 1) / kPairsPerBlock;
         pairs_exact_kernel<<<(unsigned)blocks, kPairsPerBlock, 0, c->stream>>>(c->raw, c->n, da, db, npairs, c->raw_sum.p,

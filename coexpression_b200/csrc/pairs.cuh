@@ -62,23 +62,28 @@ pairs_exact_kernel(const double *__restrict__ data, int n, const int *__restrict
     }
 }
 
-// one warp per pair; u16 2*rank rows
+// One warp per pair, on the PACKED rank rows (two int8 digit planes, u = 2*rank-(n+1) = 128*hi + lo, rows padded to a multiple
+// of 128 bytes and zero-filled): 16-byte coalesced loads (a rank2 row of an odd number of samples is only 2-byte aligned) and
+// four dp4a per four samples instead of scalar u16 loads; S = 16384 HH + 128 (HL + LH) + LL is the same exact integer.
 __global__ void __launch_bounds__(256)
-pairs_rank_kernel(const uint16_t *__restrict__ rank2, int n, const int *__restrict__ idxa,
+pairs_rank_kernel(const int8_t *__restrict__ hi, const int8_t *__restrict__ lo, int n_pad, const int *__restrict__ idxa,
                   const int *__restrict__ idxb, long long npairs, const double *__restrict__ sx,
                   double *__restrict__ out) {
     const long long pair = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (pair >= npairs) return;
     const int ia = idxa[pair], ib = idxb[pair];
-    const uint16_t *a = rank2 + (long long)ia * n;
-    const uint16_t *b = rank2 + (long long)ib * n;
-    long long acc = 0;
-    const int off = n + 1;
-    for (int c = lane; c < n; c += 32) {
-        const int ua = (int)a[c] - off, ub = (int)b[c] - off;
-        acc += (long long)ua * ub;
+    const int4 *ah = reinterpret_cast<const int4 *>(hi + (long long)ia * n_pad), *al = reinterpret_cast<const int4 *>(lo + (long long)ia * n_pad);
+    const int4 *bh = reinterpret_cast<const int4 *>(hi + (long long)ib * n_pad), *bl = reinterpret_cast<const int4 *>(lo + (long long)ib * n_pad);
+    int hh = 0, hl = 0, ll = 0;                            // per lane: at most 60 samples x 64 x 64 (no overflow)
+    for (int v = lane; v < (n_pad >> 4); v += 32) {
+        const int4 x = ah[v], y = al[v], p = bh[v], q = bl[v];
+        hh = __dp4a(x.x, p.x, hh); hh = __dp4a(x.y, p.y, hh); hh = __dp4a(x.z, p.z, hh); hh = __dp4a(x.w, p.w, hh);
+        hl = __dp4a(x.x, q.x, hl); hl = __dp4a(x.y, q.y, hl); hl = __dp4a(x.z, q.z, hl); hl = __dp4a(x.w, q.w, hl);
+        hl = __dp4a(y.x, p.x, hl); hl = __dp4a(y.y, p.y, hl); hl = __dp4a(y.z, p.z, hl); hl = __dp4a(y.w, p.w, hl);
+        ll = __dp4a(y.x, q.x, ll); ll = __dp4a(y.y, q.y, ll); ll = __dp4a(y.z, q.z, ll); ll = __dp4a(y.w, q.w, ll);
     }
+    long long acc = 16384LL * hh + 128LL * hl + ll;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) {
