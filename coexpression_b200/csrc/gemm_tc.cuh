@@ -391,7 +391,8 @@ gemm_i8_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_ah, const _
 //   * allocation and barrier set-up happen once per CTA.
 //   barriers: full[3] / empty[3] (TMA <-> MMA), tmem_full (MMA -> epilogue), tmem_empty (8 epilogue warps -> MMA)
 // ---------------------------------------------------------------------------------------------
-constexpr int kP8Threads = 320, kP8BN = 128;
+constexpr int kP8EpiWarps = 16;                           // epilogue warps: four per TMEM lane quarter, 32 columns each
+constexpr int kP8Threads = 64 + 32 * kP8EpiWarps, kP8BN = 128;
 
 __global__ void __launch_bounds__(kP8Threads, 1)
 gemm_i8_tc_persistent128_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
@@ -410,7 +411,7 @@ gemm_i8_tc_persistent128_kernel(const __grid_constant__ CUtensorMap map_ah, cons
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_tfull, 1);
-        mbar_init(bar_tempty, 8);
+        mbar_init(bar_tempty, kP8EpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -473,7 +474,10 @@ gemm_i8_tc_persistent128_kernel(const __grid_constant__ CUtensorMap map_ah, cons
             }
         }
     } else {
-        // ===== epilogue: 8 warps; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+        // ===== epilogue: kP8EpiWarps warps; TMEM lane quarter = warp % 4, column part = (warp - 2) / 4 =====
+        // (the accumulators fill all 512 TMEM columns, so this phase is serial with the MMAs of the next tile: the more warps drain
+        //  them in parallel, the shorter it is -- 16 instead of 8 warps, measured)
+        constexpr int kCols = kP8BN / (kP8EpiWarps / 4);
         const int quarter = warp & 3, half = (warp - 2) >> 2;
         int it = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -484,7 +488,7 @@ gemm_i8_tc_persistent128_kernel(const __grid_constant__ CUtensorMap map_ah, cons
             const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16);
             int *orow = out + (long long)(m0 + quarter * 32 + lane) * ldo + c0;
 #pragma unroll 1
-            for (int cc = half * 64; cc < half * 64 + 64; cc += 16) {
+            for (int cc = half * kCols; cc < half * kCols + kCols; cc += 16) {
                 uint32_t hh[16], hl[16], lh[16], ll[16];
                 tmem_ld16(tl + cc, hh);
                 tmem_ld16(tl + kP8BN + cc, hl);
