@@ -235,6 +235,12 @@ def collate_vectors():
         out = {"store": files, "settings": {k: v for k, v in settings.items() if k in ("supplementary_label", "verbose")},
                "individual_scores": open(os.path.join(wd, "golden.individual_scores")).read(),
                "allscores": open(os.path.join(wd, "allscores.txt")).read(), "feature_bed": open(bed).read(),
+               # the reporting files of 2-collate-results.py:165-430 (html table, circos network, BioLayout file, stats, file list,
+               # and the qq_plot file, of which the reference only ever writes the header: `fullrange_perm_indm` is undefined)
+               "reports": {f: open(os.path.join(wd, f)).read() for f in ("golden.html", "golden.network.php", "golden.layout",
+                                                                          "golden_stats.html", "golden.filelist", "golden.qq_plot")},
+               "map0": open(os.path.join(wd, "permutation_store", "f5ep.0.bed")).read(),
+               "full_settings": dict(settings, config_file="<cfg>"), "f5resource": "http://x/",
                "how": "unmodified coexfunctions.py + mechanically 2to3-rewritten 1-make-network.py and 2-collate-results.py"}
     with gzip.open(os.path.join(HERE, "reference_collate.json.gz"), "wt") as o:
         json.dump(out, o)
