@@ -9,7 +9,14 @@
 
   allscores.txt ...... one line per hit: address, group, allpromoterscores, group density, group FDR (:264-283)
 
-The HTML / BioLayout / network writers of the reference (:165-430) are reporting only and are not rebuilt.
+  reports ............ the remaining files of :165-430 (`write_reports`): `<label>.html` (results table), `<label>.network.php`
+                       (circos network), `<label>.layout` (BioLayout / d3), `<label>_stats.html`, `<label>.filelist` and the
+                       `<label>.qq_plot` file -- of which the reference only ever writes the header line (`fullrange_perm_indm`
+                       is an undefined name inside a bare try/except, :148-158).  Text for text equal to what the executed
+                       reference writes (tests/golden/reference_collate.json.gz), with two documented freedoms: the
+                       `//NODECLASS` lines of the layout file follow the iteration order of a Python set in the reference
+                       (hash order; written sorted here), and `round()` is Python 3's as in the executed reference.  The
+                       reference's metadata file is read through an undefined name (`promoter_details`, :113-119), i.e. never.
 Same command line: `2-collate-results.py -wd <working_files_dir> [-t N]`.
 """
 from __future__ import annotations
@@ -88,6 +95,137 @@ def write_allscores(path, real, fdrstore, prom_addresses):
             o.write("%s\n" % ("\t".join(str(x) for x in row)))
 
 
+def _sum(values):
+    """Python 2's `sum` of floats: plain left-to-right double additions (Python >= 3.12 compensates)."""
+    s = 0
+    for v in values:
+        s = s + v
+    return s
+
+
+def remove_overlap(thisdict):
+    """coexfunctions.py:437-461: {chrom: {start: end}} -> merged, non-overlapping ranges."""
+    newdict = {}
+    for chrom in thisdict:
+        newdict[chrom] = {}
+        starts = sorted(thisdict[chrom].keys())
+        last_start = starts[0]
+        last_end = thisdict[chrom][last_start]
+        for this_start in starts[1:]:
+            this_end = thisdict[chrom][this_start]
+            if this_start <= last_end:
+                last_start = min(this_start, last_start)
+                last_end = max(this_end, last_end)
+            else:
+                newdict[chrom][last_start] = last_end
+                last_start = this_start
+                last_end = this_end
+        newdict[chrom][last_start] = last_end
+    return newdict
+
+
+def write_reports(working_files_dir, settings, real, numbers, num_completed_perms, f5resource, feature_dict):
+    """The reporting files of 2-collate-results.py:144-158, 165-262 (html), 285-322 (network), 324-380 (layout), 382-430 (stats,
+    file list).  -> list of the files written."""
+    label = str(settings.get("supplementary_label", "coex"))
+    indmeasure, winners, ptj = real["indmeasure"], real["winners"], real["prom_to_join"]
+    ji, snp_map, indjoined, individualscores = real["joining_instructions"], real["snp_map"], real["indjoined"], real["individualscores"]
+    wd = working_files_dir
+    written = []
+
+    def out(name, text):
+        with open(os.path.join(wd, name), "w") as o:
+            o.write(text)
+        written.append(name)
+
+    qqfile = label + ".qq_plot"
+    out(qqfile, "rand\t%s\n" % qqfile)                                     # :146-148, the rest of the block raises NameError
+    # ---- html table (:170-262) ----
+    html = ["<table id=\"results\">\n<tr>\n<th>Top promoter (click for details in new tab)</th>\n<th>SNPs in top_promoter</th>\n"
+            "<th>Corrected coexpression score</th>\n<th>FDR</th>\n</tr>"]
+    pseudonyms, highlight = {}, []
+    for i, (key, value) in enumerate(sorted(indmeasure.items(), key=lambda kv: (kv[1], kv[0]), reverse=True)):
+        group_label = ji[key]
+        winner = winners[group_label]
+        pseudonyms[winner] = winner                                          # (no metadata: `promoter_details` is undefined, :113)
+        winning_snps = snp_map[winner]["snps"] if winner in snp_map else ""
+        winning_snps = winning_snps.replace("||", "|")
+        if winning_snps[-1:] == "|":
+            winning_snps = winning_snps[:-1]
+        fdr = numbers["fdr_bh"][i]
+        if fdr < 0.05:
+            html.append("<tr class=\"sig\">\n")
+            highlight.append(winner)
+            highlight.extend(ptj[group_label])
+        else:
+            html.append("<tr>\n")
+        html.append("<td><a href=\"%s%s\" target=\"_blank\">%s</a></td><td>%s</td><td>%s</td><td>%s</td></tr>\n"
+                    % (f5resource, winner, winner, winning_snps.replace("|", ", "), round(value / len(indmeasure), 1), round(fdr, 2)))
+    html.append("</table>")
+    out(label + ".html", "".join(html))
+    # ---- circos network (:285-322): mean of the group-level edges of every pair of hits of different groups ----
+    already = {}
+    for prom1 in individualscores:
+        for prom2 in individualscores[prom1]:
+            if prom1 != prom2:
+                g1, g2 = ji[prom1], ji[prom2]
+                if g1 != g2 and g1 in indjoined and g2 in indjoined[g1]:
+                    already.setdefault("\t".join(sorted([prom1, prom2])), []).append(indjoined[g1][g2])
+    net = ['<? header("Access-Control-Allow-Origin: https://baillielab.net")?>\nsource\ttarget\tvalue\n']
+    for c in already:
+        net.append("%s\t%s\n" % (c, float(_sum(already[c])) / len(already[c])))
+    out(label + ".network.php", "".join(net))
+    # ---- BioLayout / d3 layout file (:324-380) ----
+    lf = ["//BioLayout Express 3D Version 2.1  Layout File\n"]
+    included = []
+    for g1 in indjoined:
+        for g2 in indjoined[g1]:
+            w1, w2 = winners[ji[g1]], winners[ji[g2]]
+            edgelist = [indjoined[g1][g2]]
+            if g2 in indjoined and g1 in indjoined[g2]:
+                edgelist.append(indjoined[g2][g1])
+            edge = float(_sum(edgelist)) / len(edgelist)                      # the two directions differ under nsp
+            if edge >= -1:
+                lf.append('"%s"\t"%s"\t%s\n' % (pseudonyms[w1], pseudonyms[w2], edge))
+                included.append(w1)
+                included.append(w2)
+    for entry in sorted(set(included)):                                      # (the reference: set iteration order)
+        lf.append('//NODECLASS\t"%s"\t%s\t"significantly_coexpressed"\n' % (pseudonyms[entry], "TRUE" if entry in highlight else "FALSE"))
+    lf.append('//EDGECOLOR\t"#FF0033"\n')
+    lf.append("//EDGESIZE\t2\n")
+    lf.append('//NODECLASSCOLOR\t"TRUE"\t"significantly_coexpressed"\t"#0000FF"\n')
+    lf.append('//NODECLASSCOLOR\t"FALSE"\t"significantly_coexpressed"\t"#BAAAD1"\n')
+    lf.append('//CURRENTCLASSSET\t"significantly_coexpressed"\n')
+    lf.append('//DEFAULTSEARCH\t"%s"\n' % f5resource)
+    out(label + ".layout", "".join(lf))
+    # ---- stats of the real data (:382-418) ----
+    feature_label = str(settings["feature_coordinates"]).split("/")[-1].split(".")[0]
+    snps_mapped = os.path.join(wd, "permutation_store", feature_label + ".0.bed")
+    proms, tss_snps = set(), set()
+    with open(snps_mapped) as f:
+        for raw in f:
+            line = raw.strip().split("\t")
+            proms.add(line[-1])
+            tss_snps.add(line[3])
+    snp_count, genome_length = int(settings["snp_count"]), int(settings["genome_length"])
+    hpm_genome = snp_count * 1000000.0 / genome_length * 1.0
+    range_length = 0
+    merged = remove_overlap(feature_dict)
+    for chrom in merged:
+        for start in merged[chrom]:
+            range_length += merged[chrom][start] - start
+    try:
+        hpm = (float(len(proms)) * 1000000) / float(range_length)
+    except ZeroDivisionError:
+        hpm = "div0"
+    statsfile = label + "_stats.html"
+    out(statsfile, "snps_searched\t%s\ntss_snps\t%s\nhpm_genome\t%s\nhpm_tss\t%s\nnumperms\t%s\nnsp\t%s\nallproms\t%s\ndistinct\t%s\n"
+        % (snp_count, len(tss_snps), hpm_genome, hpm, num_completed_perms, settings.get("nsp"), len(real["allpromoterscores"]), len(ptj)))
+    out(label + ".filelist", "qqfile\t%s.svg\nlayoutfile\t%s\nstatsfile\t%s\nfullresults\t%s\nhtmlresults\t%s\nemail\t%s\n"
+        % (qqfile, label + ".layout", statsfile, label + ".individual_scores", label + ".html", settings.get("useremail")))
+    return written
+
+
 def collate(working_files_dir):
     settings = readsettings(working_files_dir)
     pool, real, n_perm = load_store(os.path.join(working_files_dir, "perm_results_store"))
@@ -97,8 +235,20 @@ def collate(working_files_dir):
     numbers["fdrstore"] = write_individual_scores(out, real, numbers)
     feat = settings.get("feature_coordinates")
     if feat and os.path.exists(str(feat)):
-        write_allscores(os.path.join(working_files_dir, "allscores.txt"), real, numbers["fdrstore"],
-                        readfeaturecoordinates(str(feat))[0])
+        prom_addresses, feature_dict, _ = readfeaturecoordinates(str(feat))
+        write_allscores(os.path.join(working_files_dir, "allscores.txt"), real, numbers["fdrstore"], prom_addresses)
+        f5resource = ""
+        cfg = settings.get("config_file")
+        if cfg and os.path.exists(str(cfg)):                                 # 2-collate-results.py:52-57
+            import configparser
+            config = configparser.RawConfigParser(allow_no_value=True)
+            config.read(str(cfg))
+            if config.has_option("directorypaths", "f5resource"):
+                f5resource = config.get("directorypaths", "f5resource")
+        try:
+            numbers["reports"] = write_reports(working_files_dir, settings, real, numbers, n_perm, f5resource, feature_dict)
+        except (KeyError, OSError) as e:                                     # e.g. settings.txt of a hand-made store without snp_count
+            numbers["reports_error"] = "%s: %s" % (type(e).__name__, e)
     numbers["num_completed_perms"] = n_perm
     numbers["individual_scores_file"] = out
     return numbers

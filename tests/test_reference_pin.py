@@ -306,6 +306,40 @@ def test_collate_reproduces_executed_reference_tables(tmp_path):
     assert open(res["individual_scores_file"]).read() == fx["individual_scores"]
     assert (wd / "allscores.txt").read_text() == fx["allscores"]
     assert len(fx["individual_scores"].splitlines()) > 40
+    assert "reports_error" in res and "reports" not in res          # a store without the full settings: tables only
+
+
+def test_collate_reports_reproduce_executed_reference_files(tmp_path):
+    """The reporting files of 2-collate-results.py:144-430 (html table, circos network, BioLayout / d3 layout, stats, file list,
+    the header-only qq_plot file) against what the executed reference wrote into its working directory -- text for text, except
+    that the layout file's //NODECLASS lines follow a Python set's iteration order in the reference (compared as a set here)."""
+    from coexpression_b200.collate import collate
+    with gzip.open(os.path.join(HERE, "golden", "reference_collate.json.gz"), "rt") as f:
+        fx = json.load(f)
+    wd = tmp_path / "work"
+    (wd / "perm_results_store").mkdir(parents=True)
+    (wd / "permutation_store").mkdir()
+    for name, text in fx["store"].items():
+        (wd / "perm_results_store" / name).write_text(text)
+    (wd / "permutation_store" / "f5ep.0.bed").write_text(fx["map0"])
+    bed = tmp_path / "f5ep.bed"
+    bed.write_text(fx["feature_bed"])
+    cfg = tmp_path / "app.cfg"
+    cfg.write_text("[directorypaths]\nsourcefilesdir=x\nresdir=x\npathtobedtools=/nonexistent\nf5resource=%s\n" % fx["f5resource"])
+    settings = dict(fx["full_settings"], feature_coordinates=str(bed), config_file=str(cfg))
+    (wd / "settings.txt").write_text(json.dumps(settings))
+    res = collate(str(wd))
+    assert sorted(res["reports"]) == sorted(fx["reports"])
+    for name, want in fx["reports"].items():
+        got = (wd / name).read_text()
+        if name.endswith(".layout"):
+            split = lambda text: ([l for l in text.split("\n") if not l.startswith("//NODECLASS\t")],
+                                  sorted(l for l in text.split("\n") if l.startswith("//NODECLASS\t")))
+            assert split(got) == split(want), name
+            assert got.count("//NODECLASS\t") > 20
+        else:
+            assert got == want, name
+    assert (wd / "golden.individual_scores").read_text() == fx["individual_scores"]
 
 
 def test_py2_rewrite_is_line_local_and_mechanical():
