@@ -451,7 +451,7 @@ def run_ours(args):
     # bytes of the WHOLE job per step (all ranks): the table once, every rank's hit lists; every rank's result arrays
     # (+ the gathered density block read back on rank 0)
     h2d = (X_pin.nbytes * world if world > 1 else t.X.nbytes) + env.sum_over_ranks(hit_rows.nbytes + perm_off.nbytes)
-    d2h = env.sum_over_ranks(4 * K + 3 * 4 * H + 2 * 8 * H) + (8 * world * Hpad if world > 1 else 0)
+    d2h = env.sum_over_ranks(4 * K + 3 * 4 * H + 2 * 8 * H + 8 * len(hits[0]) ** 2) + (8 * world * Hpad if world > 1 else 0)
     res = None
     for i in range(2 + max(2, args.steps // 2)):
         env.barrier()
@@ -465,6 +465,7 @@ def run_ours(args):
             ctx.set_expression_device(X_bc.data_ptr(), t.N, t.n, keepalive=X_bc)
         ctx.prepare()
         res = ctx.network_batch(hits, opts)
+        real_scores = ctx.read_scores(0, len(hits[0]))       # the real data's P x P block (2-collate-results.py:79-109 reads it)
         if world > 1:
             job.o_den[:H].copy_(torch.from_numpy(res.group_density), non_blocking=False)
             dist.all_gather_into_tensor(gather_buf, job.o_den)

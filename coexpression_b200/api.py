@@ -361,6 +361,13 @@ class CoexContext:
         return BatchResult(perm_off, hit_rows, n_groups[:K], group_of_hit[:H], group_label[:H], group_winner[:H],
                            group_density[:H], hit_score[:H], scores, None)
 
+    def read_scores(self, k, P):
+        """individualscores of permutation k of the last reduced batch, as a [P, P] array (the batch itself only returns
+        densities unless want_scores: the permuted sets' score matrices are never needed on the host)."""
+        out = np.empty((int(P), int(P)), dtype=np.float64)
+        check(self.lib.coex_read_scores(self.h, int(k), out.ctypes.data), "coex_read_scores")
+        return out
+
     # ---- A14: pooled null, empirical p, FDR (2-collate-results.py:67-76,142,161-163) on the device ----------------------
     def collate(self, pool, realmeasures, pool_device_ptr=None, n_pool=None):
         """pool: host array of every permuted density (or pool_device_ptr + n_pool: a device buffer, e.g. the gathered block);

@@ -438,6 +438,7 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
         sc_off[k + 1] = sc_off[k] + P * P;
     }
     const long long SC = sc_off[K];
+    c->last_sc_off.clear();
     if (prm->measure == 0 && prm->use_specific_p && c->n > 1860)
         COEX_FAIL("Spearman tensor path supports up to 1860 samples (int32 dot products)");
     const int phase = c->shard_phase;              // 0 = plain call; 1 / 2 = the two halves of a job shared by several GPUs
@@ -681,6 +682,7 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
         }
     }
     if (prm->use_specific_p && (c->gemm_mode == 0 || prm->measure == 1)) COEX_TRY(tc_check_error(c));   // (-cm Pearson runs the tcgen05 digit GEMM in every gemm mode)
+    c->last_sc_off = sc_off; c->last_scores = d_sc;           // coex_read_scores
     return 0;
 }
 
@@ -1211,6 +1213,16 @@ int coex_shard_finish(coex_ctx *c, const coex_params *prm, int K, const long lon
                                           group_density, hit_score, scores, nullptr, on_device);
     c->shard_phase = 0;
     return status;
+}
+
+int coex_read_scores(coex_ctx *c, int k, double *out) {
+    COEX_TRY(check_ctx(c));
+    if (!out || c->last_sc_off.empty() || !c->last_scores) COEX_FAIL("coex_read_scores: no batch has been reduced by this context");
+    if (k < 0 || k + 1 >= (int)c->last_sc_off.size()) COEX_FAIL("coex_read_scores: no such permutation in the last batch");
+    const long long a = c->last_sc_off[(size_t)k], b = c->last_sc_off[(size_t)k + 1];
+    if (b > a) COEX_CUDA(cudaMemcpyAsync(out, c->last_scores + a, (size_t)(b - a) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    COEX_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
 }
 
 int coex_collate(coex_ctx *c, const double *pool, long long n_pool, int pool_on_device, const double *real, int G,

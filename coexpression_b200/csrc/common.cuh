@@ -136,6 +136,8 @@ struct coex_ctx {
     std::vector<double *> peer_scores;                         // [world] (own buffer at shard_rank)
     std::vector<void *> peer_mapped;                           // what cudaIpcOpenMemHandle returned (closed in coex_destroy)
     coex::DevBuf<double *> d_perm_scores;
+    std::vector<long long> last_sc_off;                        // score-block offsets of the last reduced batch and where its scores
+    const double *last_scores = nullptr;                       // live (the context's buffer, or the caller's device buffer)
     std::vector<double> h_score_tab;                           // host-built edge-score table (see spearman_dedup_path)
     long long tab_for_N = -1; int tab_for_anticor = -1;
     std::vector<void *> tab_peer, tab_mapped;                  // [world][9] packed-table buffers of every rank (own at shard_rank) / IPC mappings

@@ -195,6 +195,11 @@ int coex_shard_finish(coex_ctx *ctx, const coex_params *params, int K, const lon
                       int *n_groups, int *group_of_hit, int *group_label, int *group_winner, double *group_density,
                       double *hit_score, double *scores, int on_device);
 
+/* The P_k x P_k edge-score block (individualscores, 1-make-network.py:316-320) of permutation k of the LAST batch this context
+ * reduced, copied to the host: a batch of permuted sets only needs its densities back (2-collate-results.py:68-76 reads nothing
+ * else of them), the real data (k = 0) also its scores (:79-109).  Valid until the next coex_network_batch / coex_shard_* call. */
+int coex_read_scores(coex_ctx *ctx, int k, double *out);
+
 /* A14, the consumer of the gathered density vectors (2-collate-results.py:67-76,142,161-163; coexfunctions.py:379-383 empiricalp,
  * :333-358 fdr_correction): pool = every permuted density (device pointer if pool_on_device, e.g. the gathered block), real = the
  * G densities of the real data (host).  p_out = sorted(empiricalp(x, pool) for x in real) (ascending), bh_out / by_out = the

@@ -786,6 +786,8 @@ def test_shared_job_entry_points_on_one_rank_equal_the_plain_call():
             g = ctx.pairs(ga, gb, ranked=opts.correlationmeasure == "Spearman")
             ctx.set_global_list(np.sort(np.where(np.isnan(g), -99.0, g)))
             want = ctx.network_batch(hits, opts, want_scores=True)
+            for k in (0, 3):                                     # coex_read_scores: one block of the last batch
+                assert np.array_equal(ctx.read_scores(k, len(hits[k])), want.score_matrix(k))
             ranks = ctx.ranks()
             job = SharedJob(ctx, hits, None)
             assert job.mine == list(range(len(hits)))
