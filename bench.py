@@ -447,6 +447,8 @@ def run_ours(args):
     Xh = X_pin.numpy()
     X_bc = torch.empty((world * chunk, t.n), dtype=torch.float64, device=dev) if world > 1 else None
     X_slice = X_bc[rank * chunk:(rank + 1) * chunk] if world > 1 else None
+    sc_pin = torch.empty(len(hits[0]) ** 2, dtype=torch.float64).pin_memory().numpy()       # pinned landing area of the real data's scores
+    ctx.set_score_readback(0, sc_pin)                        # copied out by network_batch under the network stage
     e2e_ms = []
     # bytes of the WHOLE job per step (all ranks): the table once, every rank's hit lists; every rank's result arrays
     # (+ the gathered density block read back on rank 0)
@@ -464,8 +466,7 @@ def run_ours(args):
             torch.cuda.current_stream().synchronize()
             ctx.set_expression_device(X_bc.data_ptr(), t.N, t.n, keepalive=X_bc)
         ctx.prepare()
-        res = ctx.network_batch(hits, opts)
-        real_scores = ctx.read_scores(0, len(hits[0]))       # the real data's P x P block (2-collate-results.py:79-109 reads it)
+        res = ctx.network_batch(hits, opts)                  # (also fills sc_pin: the real data's P x P block, 2-collate-results.py:79-109)
         if world > 1:
             job.o_den[:H].copy_(torch.from_numpy(res.group_density), non_blocking=False)
             dist.all_gather_into_tensor(gather_buf, job.o_den)
@@ -477,6 +478,10 @@ def run_ours(args):
         if i >= 2:
             e2e_ms.append(1e3 * (w1 - w0))
     e2e_step_ms = env.max_over_ranks(float(np.mean(e2e_ms)))
+    ctx.set_score_readback(0, None)
+    if not np.array_equal(sc_pin.reshape(len(hits[0]), -1), ctx.read_scores(0, len(hits[0]))):
+        parity["ok"] = False
+        parity["score_readback_equals_scores"] = False
     for k in range(K):                                       # host-buffer API == resident API, bit for bit
         a, b = int(perm_off[k]), int(perm_off[k]) + int(res.n_groups[k])
         if not np.array_equal(res.group_density[a:b], dens_resident[k]):

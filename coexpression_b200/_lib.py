@@ -72,6 +72,7 @@ SIGNATURES = {
     "coex_shard_finish": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(CoexParams), ctypes.c_int] + [ctypes.c_void_p] * 9 +
                           [ctypes.c_int]),
     "coex_read_scores": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "coex_set_score_readback": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "coex_collate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_ll, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "coex_launch_count": (c_ll, [ctypes.c_void_p]),

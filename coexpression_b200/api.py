@@ -361,12 +361,22 @@ class CoexContext:
         return BatchResult(perm_off, hit_rows, n_groups[:K], group_of_hit[:H], group_label[:H], group_winner[:H],
                            group_density[:H], hit_score[:H], scores, None)
 
-    def read_scores(self, k, P):
+    def read_scores(self, k, P, out=None):
         """individualscores of permutation k of the last reduced batch, as a [P, P] array (the batch itself only returns
-        densities unless want_scores: the permuted sets' score matrices are never needed on the host)."""
-        out = np.empty((int(P), int(P)), dtype=np.float64)
+        densities unless want_scores: the permuted sets' score matrices are never needed on the host).  out: a C-contiguous
+        float64 array of P * P elements to fill (e.g. a view of pinned memory: a pageable destination copies ~10 x slower)."""
+        if out is None:
+            out = np.empty((int(P), int(P)), dtype=np.float64)
+        assert out.dtype == np.float64 and out.size == int(P) * int(P) and out.flags["C_CONTIGUOUS"]
         check(self.lib.coex_read_scores(self.h, int(k), out.ctypes.data), "coex_read_scores")
-        return out
+        return out.reshape(int(P), int(P))
+
+    def set_score_readback(self, k, out):
+        """network_batch itself copies the score block of permutation k into `out` (float64, P_k^2 elements, ideally pinned)
+        while the network stage runs; out=None switches it off."""
+        self._rb = out
+        check(self.lib.coex_set_score_readback(self.h, int(k), out.ctypes.data if out is not None else None),
+              "coex_set_score_readback")
 
     # ---- A14: pooled null, empirical p, FDR (2-collate-results.py:67-76,142,161-163) on the device ----------------------
     def collate(self, pool, realmeasures, pool_device_ptr=None, n_pool=None):

@@ -570,6 +570,19 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
             COEX_TRY(stage_end(c, 2));
         }
     }
+    // coex_set_score_readback: the score block of one permutation (the real data's) starts its way to the host NOW, on a second
+    // stream, under the network stage
+    bool readback = false;
+    if (phase == 0 && c->rb_host && c->rb_k >= 0 && c->rb_k < K && H > 0) {
+        const long long a = sc_off[(size_t)c->rb_k], b = sc_off[(size_t)c->rb_k + 1];
+        if (b > a) {
+            if (!c->rb_stream) { COEX_CUDA(cudaStreamCreateWithFlags(&c->rb_stream, cudaStreamNonBlocking)); COEX_CUDA(cudaEventCreateWithFlags(&c->rb_event, cudaEventDisableTiming)); }
+            COEX_CUDA(cudaEventRecord(c->rb_event, st));
+            COEX_CUDA(cudaStreamWaitEvent(c->rb_stream, c->rb_event, 0));
+            COEX_CUDA(cudaMemcpyAsync(c->rb_host, d_sc + a, (size_t)(b - a) * sizeof(double), cudaMemcpyDeviceToHost, c->rb_stream));
+            readback = true;
+        }
+    }
     if (phase == 1) {
         // every score row of my table rows is on its way to the rank that owns its permutation (stores into peer memory over
         // NVLink): they have landed when this stream is idle; the caller's barrier then tells the owners
@@ -683,6 +696,7 @@ static int network_batch_impl(coex_ctx *c, const coex_params *prm, int K, const 
     }
     if (prm->use_specific_p && (c->gemm_mode == 0 || prm->measure == 1)) COEX_TRY(tc_check_error(c));   // (-cm Pearson runs the tcgen05 digit GEMM in every gemm mode)
     c->last_sc_off = sc_off; c->last_scores = d_sc;           // coex_read_scores
+    if (readback) COEX_CUDA(cudaStreamSynchronize(c->rb_stream));
     return 0;
 }
 
@@ -796,6 +810,7 @@ int coex_destroy(coex_ctx *c) {
     c->p_out.release(); c->icol.release(); c->d_ndeg.release(); c->dd_uniq.release(); c->dd_qlist.release();
     c->dd_items.release(); c->dd_qperm.release(); c->pl_cnt.release(); c->pl_cursor.release(); c->pl_ustart.release(); c->pl_nitems.release();
     c->pl_itemoff.release(); c->pl_bounds.release(); c->pl_meta.release(); c->pl_err.release(); c->dd_gthr.release(); c->dd_tab.release();
+    if (c->rb_stream) { cudaStreamDestroy(c->rb_stream); cudaEventDestroy(c->rb_event); }
     for (void *p : c->peer_mapped) if (p) cudaIpcCloseMemHandle(p);
     for (void *p : c->tab_mapped) if (p) cudaIpcCloseMemHandle(p);
     c->shard_scores.release(); c->d_perm_scores.release();
@@ -1213,6 +1228,12 @@ int coex_shard_finish(coex_ctx *c, const coex_params *prm, int K, const long lon
                                           group_density, hit_score, scores, nullptr, on_device);
     c->shard_phase = 0;
     return status;
+}
+
+int coex_set_score_readback(coex_ctx *c, int k, double *host_out) {
+    if (!c) COEX_FAIL("null context");
+    c->rb_k = k; c->rb_host = host_out;
+    return 0;
 }
 
 int coex_read_scores(coex_ctx *c, int k, double *out) {

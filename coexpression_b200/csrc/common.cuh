@@ -136,6 +136,8 @@ struct coex_ctx {
     std::vector<double *> peer_scores;                         // [world] (own buffer at shard_rank)
     std::vector<void *> peer_mapped;                           // what cudaIpcOpenMemHandle returned (closed in coex_destroy)
     coex::DevBuf<double *> d_perm_scores;
+    int rb_k = -1; double *rb_host = nullptr;                  // coex_set_score_readback: block to copy out during the network stage
+    cudaStream_t rb_stream = nullptr; cudaEvent_t rb_event = nullptr;
     std::vector<long long> last_sc_off;                        // score-block offsets of the last reduced batch and where its scores
     const double *last_scores = nullptr;                       // live (the context's buffer, or the caller's device buffer)
     std::vector<double> h_score_tab;                           // host-built edge-score table (see spearman_dedup_path)

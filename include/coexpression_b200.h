@@ -199,6 +199,9 @@ int coex_shard_finish(coex_ctx *ctx, const coex_params *params, int K, const lon
  * reduced, copied to the host: a batch of permuted sets only needs its densities back (2-collate-results.py:68-76 reads nothing
  * else of them), the real data (k = 0) also its scores (:79-109).  Valid until the next coex_network_batch / coex_shard_* call. */
 int coex_read_scores(coex_ctx *ctx, int k, double *out);
+/* The same block copied out BY coex_network_batch itself, on a second stream under the network stage (host_out: pinned memory of
+ * P_k^2 doubles for the copy to overlap; filled when coex_network_batch returns).  host_out == NULL switches it off. */
+int coex_set_score_readback(coex_ctx *ctx, int k, double *host_out);
 
 /* A14, the consumer of the gathered density vectors (2-collate-results.py:67-76,142,161-163; coexfunctions.py:379-383 empiricalp,
  * :333-358 fdr_correction): pool = every permuted density (device pointer if pool_on_device, e.g. the gathered block), real = the
