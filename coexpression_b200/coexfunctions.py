@@ -188,12 +188,17 @@ def read_snp_map(mapfile, table, verbose=False):
     return snp_map
 
 
-def make_correlation_list(ctx, names, correlationfile, correlationmeasure="Spearman", gpl_len=1000000, seed=None):
+def make_correlation_list(ctx, names, correlationfile, correlationmeasure="Spearman", gpl_len=1000000, seed=None,
+                          py2_format=False):
     """Row N2: the global correlation list (reference 0-prepare-coex.py:621-716), the second caller of the
     pair-list ABI.  Existing entries are kept (sub-sampled to gpl_len), int(1.1 * missing) random row pairs are
     drawn, only pairs whose labels differ in their first five characters ("different chromosome", :682) are
     correlated -- on the GPU, through the resident table (ctx.pairs == getPearson) -- NaN -> -99, and the
-    ascending list is written one value per line.  Returns the list as a numpy array."""
+    ascending list is written one value per line.  Returns the list as a numpy array.
+    py2_format: write the values as the Python-2.7 reference does -- `"%s" % r` is str(float) there, 12 significant digits
+    (0-prepare-coex.py:707-709) -- instead of Python 3's shortest round-trip repr; a reader (`float(line)`) takes either, but a
+    list truncated to 12 digits bisects 1-2 entries differently, so this matters only for file-level equality with a deployed
+    Python-2 reference."""
     import random
     rnd = random.Random(seed)
     existing = []
@@ -220,7 +225,7 @@ def make_correlation_list(ctx, names, correlationfile, correlationmeasure="Spear
         existing.sort()
         with open(correlationfile, "w") as o:
             for v in existing:
-                o.write("%s\n" % v)
+                o.write(("%.12g\n" % v) if py2_format else ("%s\n" % v))
     return np.array(existing, dtype=np.float64)
 
 
