@@ -2,7 +2,8 @@
 """Development aid: joins the SASS-level source page of an ncu report (`ncu -i X.ncu-rep --page source --csv`) with the
 line table of the library (`nvdisasm -g -c` of the cubin inside coexpression_v2.so) and prints executed instructions and
 stall samples per CUDA source line of one kernel.
-    python scripts/ncu_lines.py gpurun_out/X.ncu-rep count_dedup_kernelILi0 [top]"""
+    python scripts/ncu_lines.py gpurun_out/X.ncu-rep count_dedup_kernelILi0 [top] [regex of the demangled kernel name, for
+    reports that hold several kernels]"""
 import csv
 import io
 import os
@@ -33,7 +34,8 @@ for ln in dis:
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/", ln)
     if m:
         line_of[int(m.group(1), 16)] = cur
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+flt = ["--kernel-name", "regex:" + sys.argv[4]] if len(sys.argv) > 4 else []
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + flt, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 h = rows[1]
 ia, ii, isamp = h.index("Address"), h.index("Instructions Executed"), h.index("# Samples")
