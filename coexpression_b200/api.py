@@ -418,7 +418,7 @@ class CoexContext:
               "coex_set_gemm_mode")
 
     def set_count_mode(self, mode):
-        check(self.lib.coex_set_count_mode(self.h, {"dedup": 0, "per_query": 1, "row_rank": 3}.get(mode, mode)), "coex_set_count_mode")
+        check(self.lib.coex_set_count_mode(self.h, {"dedup": 0, "per_query": 1, "dedup_sorted": 2, "row_rank": 3, "dedup_fine": 4}.get(mode, mode)), "coex_set_count_mode")
 
     def set_workspace_mb(self, mb):
         check(self.lib.coex_set_workspace_mb(self.h, int(mb)), "coex_set_workspace_mb")

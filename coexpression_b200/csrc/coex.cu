@@ -8,6 +8,7 @@
 #include "gemm_tc.cuh"
 #include "count.cuh"
 #include "count_dedup.cuh"
+#include "count_fine.cuh"
 #include "plan.cuh"
 #include "network.cuh"
 #include "allpairs.cuh"
@@ -259,6 +260,27 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
     COEX_TRY(c->dd_gthr.reserve((size_t)grid_max * Tcap * 6));      // 3 x Tcap records of 16 bytes per CTA
     if (tdbg) fprintf(stderr, "[coex host] count kernel: %zu bytes of shared memory, %d CTA(s) per SM, Tcap %d, bitmap words %d\n", smem, per_sm, Tcap, bm_words);
     COEX_TRY(ensure_score_table(c, prm));
+    // Spearman null, query items: count_fine_kernel (count_fine.cuh); what it declines goes to count_dedup_kernel<0> through a re-do list
+    // (it wins where a row is long against the statistics of its work items -- FANTOM5: 200 000 columns, ~2 000 statistics, 55 ms
+    //  against 72 ms for 201 hit sets; on a 20 000-row table its per-item set-up, alone on its SM, loses to the sorted-statistics
+    //  kernel, 4.6 ms against 3.6 ms: profiles/r02_count_experiments.md)
+    const bool fine_ok = !pearson && Tcap <= kCfTcap && Qcap <= kCfQcap;
+    const bool fine = fine_ok && (c->count_mode == 4 || (c->count_mode == 0 && N >= c->fine_min_rows));
+    if (c->count_mode == 4 && !fine_ok) COEX_FAIL("count mode 4: Spearman null and at most 4096 hits per set");
+    int fine_nb = (N <= 32768) ? 16384 : 32768;
+    if (const char *e = getenv("COEX_FINE_NB")) fine_nb = atoi(e);
+    const size_t fsmem = fine_smem_bytes(fine_nb);
+    long long fine_chunk = 0;
+    double fine_sigmas = 4.0;                // centre of the bucket map in standard deviations of a null correlation (count_fine.cuh: CfMap)
+    if (const char *e = getenv("COEX_FINE_SIGMAS")) fine_sigmas = atof(e);
+    if (fine) {
+        if (fine_nb < 1024 || fine_nb > 32768 || (fine_nb & (fine_nb - 1))) COEX_FAIL("COEX_FINE_NB: a power of two in 1024 .. 32768");
+        const long long nch = (N + kCfChunkMax - 1) / kCfChunkMax;
+        fine_chunk = round_up((N + nch - 1) / nch, 4 * kCfThreads);
+        if (const char *e = getenv("COEX_FINE_CHUNK")) fine_chunk = std::min<long long>(kCfChunkMax, round_up(std::max(1LL, atoll(e)), 4 * kCfThreads));   // (tests: several passes on a small table)
+        COEX_CUDA(cudaFuncSetAttribute(count_fine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        COEX_TRY(c->dd_redo.reserve((size_t)H + 2));
+    }
     DevBuf<unsigned long long> phase;
     const bool dbg = getenv("COEX_COUNT_DEBUG") != nullptr;
     if (dbg) { COEX_TRY(phase.reserve(16)); COEX_CUDA(cudaMemsetAsync(phase.p, 0, 16 * sizeof(unsigned long long), st)); }
@@ -340,19 +362,32 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
                 da.strip_f32 = c->strip_f32.p; da.raw = c->raw; da.raw_sum = c->raw_sum.p; da.raw_mean = c->raw_mean.p;
                 da.raw_xx = c->raw_xx.p; da.n = c->n; da.icol = c->z_valid.p; da.n_degenerate = c->z_ninv.p;
                 count_dedup_kernel<1><<<grid, kDdThreads, smem, st>>>(da);
+            } else if (fine) {
+                // dd_redo: [0] number of declined items, [1] work counter of the re-do launch, [2 ..] the declined items
+                COEX_CUDA(cudaMemsetAsync(c->dd_redo.p, 0, 2 * sizeof(int), st));
+                DedupArgs fa = da;
+                fa.fine_nb = fine_nb; fa.fine_chunk = fine_chunk; fa.redo_count = c->dd_redo.p; fa.redo_list = c->dd_redo.p + 2;
+                fa.R = std::min(0.5, std::max(0.02, fine_sigmas / std::sqrt((double)std::max(c->n, 2))));      // half-width of the map's centre
+                fa.fine_map.r1 = (float)fa.R; fa.fine_map.half = (float)(fine_nb / 2); fa.fine_map.nbm1 = fine_nb - 1;
+                fa.fine_map.st = (float)(0.125 * fine_nb / (1.0 - fa.R));
+                fa.fine_map.k = (float)(0.375 * fine_nb / fa.R) - fa.fine_map.st;
+                count_fine_kernel<<<std::min(c->sm_count, std::max(n_items_s, 1)), kCfThreads, fsmem, st>>>(fa);
+                COEX_KCHECK(st);
+                da.redo_count = c->dd_redo.p; da.redo_list = c->dd_redo.p + 2; da.work_counter = c->dd_redo.p + 1; da.phase_clk = nullptr;
+                count_dedup_kernel<0><<<std::min(grid, 2 * c->sm_count), kDdThreads, smem, st>>>(da);
             } else {
                 count_dedup_kernel<0><<<grid, kDdThreads, smem, st>>>(da);
             }
         }
         COEX_KCHECK(st);
-        COEX_TRY(stage_end(c, 1));
+        COEX_TRY(stage_end(c, fine ? 2 : 1));
     }
     if (dbg) {
         COEX_CUDA(cudaStreamSynchronize(st));
         unsigned long long h[16];
         COEX_CUDA(cudaMemcpy(h, phase.p, sizeof h, cudaMemcpyDeviceToHost));
-        fprintf(stderr, "[coex count] items=%llu queued=%llu cycles/item: meta=%llu stats=%llu rank=%llu stream=%llu refine=%llu score=%llu (Tcap=%d Qcap=%d grid<=%d)\n",
-                h[6], h[7], h[0] / std::max(1ULL, h[6]), h[1] / std::max(1ULL, h[6]), h[2] / std::max(1ULL, h[6]), h[3] / std::max(1ULL, h[6]),
+        fprintf(stderr, "[coex count] items=%llu queued=%llu (beyond the queue %llu) cycles/item: meta=%llu stats=%llu rank=%llu stream=%llu refine=%llu score=%llu (Tcap=%d Qcap=%d grid<=%d)\n",
+                h[6], h[7], h[8], h[0] / std::max(1ULL, h[6]), h[1] / std::max(1ULL, h[6]), h[2] / std::max(1ULL, h[6]), h[3] / std::max(1ULL, h[6]),
                 h[4] / std::max(1ULL, h[6]), h[5] / std::max(1ULL, h[6]), Tcap, Qcap, grid_max);
         phase.release();
     }
@@ -783,6 +818,7 @@ int coex_create(coex_ctx **out, int device) {
     c->sm_count = prop.multiProcessorCount;
     COEX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     if (const char *e = getenv("COEX_STRIP_MB")) { const long long mb = atoll(e); if (mb >= 16) c->strip_mb = mb; }   // profiling aid: same as coex_set_workspace_mb
+    if (const char *e = getenv("COEX_FINE_MIN_ROWS")) c->fine_min_rows = atoll(e);
     if (const char *e = getenv("COEX_COUNT_MODE")) c->count_mode = atoi(e);      // profiling aid (scripts/): same as coex_set_count_mode
     *out = c;
     return 0;
@@ -798,7 +834,7 @@ int coex_destroy(coex_ctx *c) {
     c->rank2.release(); c->u_hi.release(); c->u_lo.release(); c->suu.release(); c->sx.release();
     c->z_valid.release(); c->z_ninv.release(); c->za_planes.release(); c->za_inv_s.release();
     c->st_thr.release(); c->st_w.release(); c->st_cnt.release(); c->st_itemoff.release(); c->st_itemT.release();
-    c->st_cursor.release(); c->sxg.release(); c->dd_work.release();
+    c->st_cursor.release(); c->sxg.release(); c->dd_work.release(); c->dd_redo.release();
     c->z_planes.release(); c->z_ok.release(); c->z_l1.release(); c->z_inv_s.release();
     c->ap_hist.release(); c->feat_key.release(); c->feat_row.release(); c->feat_wrank.release(); c->feat_wrow.release(); c->pm_blob.release(); c->pm_counts.release(); c->pm_hits_tmp.release(); c->pm_off.release();
     c->chrom_id.release(); c->name_rank.release(); c->feat_start.release(); c->feat_end.release(); c->glist.release();
@@ -1315,9 +1351,9 @@ int coex_set_gemm_mode(coex_ctx *c, int mode) {
 
 int coex_set_count_mode(coex_ctx *c, int mode) {
     if (!c) COEX_FAIL("null context");
-    if (mode != 0 && mode != 1 && mode != 3)
-        COEX_FAIL("coex_set_count_mode: 0 = de-duplicated sorted-statistics kernel (row-rank mode chosen by cost), 1 = per-query kernel, "
-                  "3 = row-rank mode forced");
+    if (mode < 0 || mode > 4)
+        COEX_FAIL("coex_set_count_mode: 0 = de-duplicated count kernels (bucket-table or sorted-statistics kernel by table length, row-rank mode by "
+                  "cost), 1 = per-query kernel, 2 = sorted-statistics kernel, 3 = row-rank mode forced, 4 = bucket-table kernel forced");
     c->count_mode = mode;
     return 0;
 }

@@ -176,11 +176,12 @@ struct coex_ctx {
     // sorted statistics of a strip's work items (count_split.cuh: stat_sort_kernel -> count_dedup_kernel<3>)
     coex::DevBuf<double> st_thr, sxg;
     coex::DevBuf<unsigned int> st_cnt;
-    coex::DevBuf<int> st_itemT, dd_work;
+    coex::DevBuf<int> st_itemT, dd_work, dd_redo;
     coex::DevBuf<long long> st_itemoff;
     coex::DevBuf<unsigned long long> st_cursor, st_w;
     coex::DevBuf<double> dd_gthr, dd_tab;
-    int count_mode = 0;                       // 0 = de-duplicated sorted-statistics kernel (count_dedup<0>), 1 = per-query binary-search kernel, 2 = de-duplicated bucket-window kernel (count_rows), 3 = row-rank forced, 4 = split form of 0 (stat_sort + count_dedup<3> + score_scatter)
+    int count_mode = 0;                       // coex_set_count_mode: 0 = de-duplicated (count_fine for long tables / count_dedup, row-rank by cost), 1 = per-query, 2 = sorted statistics (count_dedup<0>), 3 = row-rank forced, 4 = bucket table (count_fine) forced
+    long long fine_min_rows = 65536;          // mode 0: tables at least this long use count_fine_kernel (COEX_FINE_MIN_ROWS)
     coex::DevBuf<int> p_idxa, p_idxb;         // coex_pairs staging
     coex::DevBuf<double> p_out;
     long long strip_mb = 4096;                // correlation-strip workspace in MB: fewer, larger GEMM + count launches (C2: 6.15 -> 6.06 ms,

@@ -54,6 +54,8 @@ struct DedupItem {
     int T;           // number of statistics of this item (upper bound: sum (P-1))
 };
 
+struct CfMap { float st, k, r1, half; int nbm1; };      // bucket map of count_fine_kernel (count_fine.cuh)
+
 struct DedupArgs {
     const int *strip;               // [rows_in_strip, ld]
     long long ld;
@@ -94,6 +96,12 @@ struct DedupArgs {
     const double *raw_sum, *raw_mean, *raw_xx;
     int n;
     unsigned int *rank_out;         // MODE 2: [rows_in_strip, ld] number of null values strictly below each column's value
+    // ---- count_fine_kernel (count_fine.cuh) and its re-do list ----------------------------------------------------
+    int fine_nb;                    // buckets of the shared-memory table (power of two, 1024 .. 32768)
+    CfMap fine_map;
+    long long fine_chunk;           // columns per pass of its 16-bit counters (multiple of 4096, <= 57344)
+    int *redo_list, *redo_count;    // count_fine_kernel: items it declines (appended); count_dedup_kernel<0>: if redo_count is set, the
+                                    // items to work on are items[redo_list[0 .. *redo_count)]
     const float *eps_row;           // [N_pad] per-row share of the bound of |tensor r - exact r| (= icol in this mode; 0 = undefined row):
                                     // |error(u, c)| <= eps_row[u] + eps_row[c] (digit quantisation)
 };
@@ -184,10 +192,11 @@ count_dedup_kernel(DedupArgs a) {
         __syncthreads();
         return s_next;
     };
-    for (int it = blockIdx.x; it < a.n_items; it = next_item(it)) {
+    const int n_items = (MODE == 0 && a.redo_count) ? *a.redo_count : a.n_items;
+    for (int it = blockIdx.x; it < n_items; it = next_item(it)) {
         DedupItem item;
         if (RANKROW) { item.urow = it / nchunk; item.qb = item.qe = 0; item.T = 0; }
-        else item = a.items[it];
+        else item = a.items[(MODE == 0 && a.redo_count) ? a.redo_list[it] : it];
         const int rank_c0 = RANKROW ? (it % nchunk) * a.Tcap : 0;        // first column of the run
         const int nq = item.qe - item.qb;
         const int u = a.uniq_rows[item.urow];

@@ -221,10 +221,13 @@ int coex_stage_ms(coex_ctx *ctx, int stage, double *ms, long long *launches);
  * 2 / 3 = the persistent tcgen05 kernel with 128 x 64 / 128 x 128 tiles explicitly,
  * 64 / 128 = one-tile-per-CTA tcgen05 kernel with that table-column tile */
 int coex_set_gemm_mode(coex_ctx *ctx, int mode);
-/* 0 = de-duplicated sorted-statistics count kernel (default, count_dedup.cuh), 1 = per-query binary-search kernel (count.cuh): an
- * independent implementation of the same counts, kept as the cross-check of the tests.
+/* 0 = de-duplicated count kernels (default).  Spearman null: the bucket-table kernel of count_fine.cuh for tables of >= 65536 rows
+ * (a streamed null value costs one shared-memory atomic and never looks at the statistics; what it declines is re-done by the
+ * sorted-statistics kernel), the sorted-statistics kernel of count_dedup.cuh below that; `-cm Pearson`: the sorted-statistics kernel.
  * Mode 0 switches by itself to ROW-RANK mode (every strip row ranked once, the queries look their bisect indices up) when the hit
- * sets are so large that this is cheaper (config C5: thousands of hits per set); 3 forces that mode. */
+ * sets are so large that this is cheaper (config C5: thousands of hits per set); 3 forces that mode.
+ * 1 = per-query binary-search kernel (count.cuh), 2 = sorted-statistics kernel forced, 4 = bucket-table kernel forced: independent
+ * implementations of the same counts, cross-checked against each other and against the oracle by the tests. */
 int coex_set_count_mode(coex_ctx *ctx, int mode);
 int coex_set_workspace_mb(coex_ctx *ctx, long long strip_mb);
 /* On-device cross-check: the first m_rows table rows against the whole table through the tcgen05

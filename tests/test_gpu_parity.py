@@ -161,7 +161,7 @@ def test_network_golden_dp4a(name):
 
 
 @pytest.mark.parametrize("name", ["spearman_default", "spearman_anticor", "spearman_useavg_m"])
-@pytest.mark.parametrize("count_mode", ["per_query", "row_rank"])
+@pytest.mark.parametrize("count_mode", ["per_query", "dedup_sorted", "dedup_fine", "row_rank"])
 def test_network_golden_other_count_kernels(name, count_mode):
     _run_case(name, "tcgen05", count_mode)
 
@@ -489,11 +489,22 @@ def test_properties_at_scale_and_cross_implementation():
         ctx.set_global_list(np.sort(np.where(np.isnan(g), -99.0, g)))
         ctx.set_features(t.chrom, t.start, t.end, t.names)
         out = {}
-        for mode in ("dedup", "per_query", "row_rank"):
+        for mode in ("dedup", "per_query", "dedup_sorted", "dedup_fine", "row_rank"):
             ctx.set_count_mode(mode)
             out[mode] = ctx.network_batch(hits, Options(anticorrelation=True), want_scores=True, want_counts=True)
+        # the bucket-table kernel with several passes of its counters over the row and with a small table (long chains of
+        # statistics per bucket, many statistics next to a bucket edge)
+        import os
+        for tag, env in (("fine_chunked", {"COEX_FINE_CHUNK": "8192"}), ("fine_small_table", {"COEX_FINE_NB": "1024"})):
+            os.environ.update(env)
+            try:
+                ctx.set_count_mode("dedup_fine")
+                out[tag] = ctx.network_batch(hits, Options(anticorrelation=True), want_scores=True, want_counts=True)
+            finally:
+                for k in env:
+                    del os.environ[k]
         a = out["dedup"]
-        for other in ("per_query", "row_rank"):
+        for other in ("per_query", "dedup_sorted", "dedup_fine", "row_rank", "fine_chunked", "fine_small_table"):
             b = out[other]
             assert np.array_equal(a.counts, b.counts), other
             assert np.array_equal(a.scores, b.scores), other
@@ -651,12 +662,12 @@ def test_large_hit_set_shared_memory_limits():
         g = ctx.pairs(ga, gb, ranked=True)
         ctx.set_global_list(np.sort(np.where(np.isnan(g), -99.0, g)))
         ctx.set_features(t.chrom, t.start, t.end, t.names)
-        for mode in ("dedup", "per_query", "row_rank"):
+        for mode in ("dedup", "per_query", "dedup_sorted", "row_rank"):      # (the bucket-table kernel takes at most 4096 hits per set)
             ctx.set_count_mode(mode)
             out[mode] = ctx.network_batch(hits, Options(pval_to_join=0.01), want_scores=True, want_counts=True)
     a = out["dedup"]
     assert int(a.n_groups[0]) > 100
-    for other in ("per_query", "row_rank"):
+    for other in ("per_query", "dedup_sorted", "row_rank"):
         b = out[other]
         assert np.array_equal(a.counts, b.counts), other
         assert np.array_equal(a.scores, b.scores), other
