@@ -42,9 +42,10 @@ constexpr float kCfDelta = 7e-7f;        // see cf_delta
 
 // The float value of a column and of a statistic are the SAME expression, fl(fl(int -> float) * fl(fl(0.5 / sx_u) * fl(0.5 / sx_c))):
 // five roundings, |x32 - x64| <= 5 * 2^-24 |x| = 2.98e-7 |x| each.  With d = v32 - t32: the doubles are ordered like the floats
-// whenever |d| > 3e-7 (|v| + |t|); |v| <= |t32| + |d| (up to 1 + 3e-7) makes |d| >= 6.1e-7 |t32| sufficient.  The floor keeps exact
-// zeros out of the "certain" branch.
-__device__ __forceinline__ float cf_delta(float t) { return fmaxf(kCfDelta * fabsf(t), 1e-30f); }
+// whenever |d| > 3e-7 (|v| + |t|); |v| <= |t32| + |d| (up to 1 + 3e-7) makes |d| >= 6.1e-7 |t32| sufficient.  t32 == 0 is an exact
+// zero (integer sum 0; the smallest non-zero |value| of a row of n <= 8192 samples is ~1e-12, far from the denormals) and any float
+// order against it is the true one: no floor is needed, and v32 == t32 == 0 is "certain" and not below, which is right.
+__device__ __forceinline__ float cf_delta(float t) { return kCfDelta * fabsf(t); }
 
 // Bucket of a correlation: piecewise linear over the whole of [-1, 1] -- three quarters of the buckets for the centre |x| <= r1
 // (4 standard deviations of a null correlation), one eighth for each tail (co-expressed rows are NOT null-distributed: a table
@@ -381,7 +382,7 @@ count_fine_kernel(DedupArgs a) {
                     if (col[tt] < 0 || (int)alias[tt] != tt) continue;
                     const int hb = cf_bucket(t32[tt], bm);
                     unsigned int below = rowpre[hb >> 5];
-                    for (int b = hb & ~31; b < hb; ++b) below += tab[b] & kCfCntMask;
+                    for (int b = hb & ~31; b < hb; ++b) below += tab[b] & kCfCntMask;   // (eight 16-byte loads of the whole row: slower)
                     cnt[tt] += (int)below;
                 }
                 __syncthreads();
