@@ -15,7 +15,7 @@ import tempfile
 rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-so = os.path.join(root, "coexpression_b200", "csrc", "coexpression_v2.so")
+so = os.environ.get("COEX_SO") or os.path.join(root, "coexpression_b200", "csrc", "coexpression_v2.so")   # (COEX_SO: the library of the commit the report was taken with)
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
@@ -58,7 +58,7 @@ for key, (ni, ns) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     f, l = key
     if f not in src and f != "?":
         try:
-            src[f] = open(os.path.join(root, "coexpression_b200", "csrc", f)).read().split("\n")
+            src[f] = open(os.path.join(os.path.dirname(so), f)).read().split("\n")     # the sources next to the library
         except OSError:
             src[f] = []
     text = src.get(f, [])[l - 1].strip()[:100] if f in src and 0 < l <= len(src[f]) else ""
