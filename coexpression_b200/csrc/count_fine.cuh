@@ -356,6 +356,11 @@ count_fine_kernel(DedupArgs a) {
                     }
                 }
             }
+            if (wq > 0) {                                  // what is left in the warp's queue (the other warps are still streaming)
+                __syncwarp();
+                for (int x = lane; x < wq; x += 32) cf_slow(cx, myq[x]);
+                wq = 0;
+            }
             __syncthreads();                               // every value of the chunk is in the table
             CF_PHASE(3);
             // ---- D. prefix over the table: values of this chunk in the buckets below every statistic ----------------
@@ -392,9 +397,6 @@ count_fine_kernel(DedupArgs a) {
             }
             CF_PHASE(4);
         }
-        for (int x = lane; x < wq; x += 32) cf_slow(cx, myq[x]);   // what is left in the warps' queues
-        __syncthreads();
-        CF_PHASE(2);
         // ---- F. scores ------------------------------------------------------------------------------------------
         for (int t0 = tid; t0 < TP; t0 += 4 * kCfThreads) {
             long long idx4[4], w4[4], wc4[4];
