@@ -366,6 +366,7 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
                 // dd_redo: [0] number of declined items, [1] work counter of the re-do launch, [2 ..] the declined items
                 COEX_CUDA(cudaMemsetAsync(c->dd_redo.p, 0, 2 * sizeof(int), st));
                 DedupArgs fa = da;
+                if (const char *e = getenv("COEX_FINE_DECLINE_EVERY")) fa.fine_decline_mod = atoi(e);      // (tests: the re-do list)
                 fa.fine_nb = fine_nb; fa.fine_chunk = fine_chunk; fa.redo_count = c->dd_redo.p; fa.redo_list = c->dd_redo.p + 2;
                 fa.R = std::min(0.5, std::max(0.02, fine_sigmas / std::sqrt((double)std::max(c->n, 2))));      // half-width of the map's centre
                 fa.fine_map.r1 = (float)fa.R; fa.fine_map.half = (float)(fine_nb / 2); fa.fine_map.nbm1 = fine_nb - 1;

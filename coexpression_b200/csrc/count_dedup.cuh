@@ -99,6 +99,7 @@ struct DedupArgs {
     // ---- count_fine_kernel (count_fine.cuh) and its re-do list ----------------------------------------------------
     int fine_nb;                    // buckets of the shared-memory table (power of two, 1024 .. 32768)
     CfMap fine_map;
+    int fine_decline_mod;           // test hook (COEX_FINE_DECLINE_EVERY): count_fine_kernel declines every item whose index is a multiple of it
     long long fine_chunk;           // columns per pass of its 16-bit counters (multiple of 4096, <= 57344)
     int *redo_list, *redo_count;    // count_fine_kernel: items it declines (appended); count_dedup_kernel<0>: if redo_count is set, the
                                     // items to work on are items[redo_list[0 .. *redo_count)]

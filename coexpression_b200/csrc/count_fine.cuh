@@ -194,7 +194,7 @@ count_fine_kernel(DedupArgs a) {
         }
         __syncthreads();
         const int TP = q_toff[nq];
-        if (TP > kCfTcap) {                                 // (the plan cuts items at the host's Tcap <= kCfTcap; belt and braces)
+        if (TP > kCfTcap || (a.fine_decline_mod > 0 && it % a.fine_decline_mod == 0)) {      // (the plan cuts items at the host's Tcap <= kCfTcap)
             if (tid == 0) a.redo_list[atomicAdd(a.redo_count, 1)] = it;
             continue;
         }

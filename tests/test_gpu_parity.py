@@ -492,10 +492,12 @@ def test_properties_at_scale_and_cross_implementation():
         for mode in ("dedup", "per_query", "dedup_sorted", "dedup_fine", "row_rank"):
             ctx.set_count_mode(mode)
             out[mode] = ctx.network_batch(hits, Options(anticorrelation=True), want_scores=True, want_counts=True)
-        # the bucket-table kernel with several passes of its counters over the row and with a small table (long chains of
-        # statistics per bucket, many statistics next to a bucket edge)
+        # the bucket-table kernel with several passes of its counters over the row, with a small table (long chains of
+        # statistics per bucket, many statistics next to a bucket edge) and with every third work item handed to the
+        # sorted-statistics kernel through the re-do list
         import os
-        for tag, env in (("fine_chunked", {"COEX_FINE_CHUNK": "8192"}), ("fine_small_table", {"COEX_FINE_NB": "1024"})):
+        for tag, env in (("fine_chunked", {"COEX_FINE_CHUNK": "8192"}), ("fine_small_table", {"COEX_FINE_NB": "1024"}),
+                         ("fine_redo_list", {"COEX_FINE_DECLINE_EVERY": "3"})):
             os.environ.update(env)
             try:
                 ctx.set_count_mode("dedup_fine")
@@ -504,7 +506,7 @@ def test_properties_at_scale_and_cross_implementation():
                 for k in env:
                     del os.environ[k]
         a = out["dedup"]
-        for other in ("per_query", "dedup_sorted", "dedup_fine", "row_rank", "fine_chunked", "fine_small_table"):
+        for other in ("per_query", "dedup_sorted", "dedup_fine", "row_rank", "fine_chunked", "fine_small_table", "fine_redo_list"):
             b = out[other]
             assert np.array_equal(a.counts, b.counts), other
             assert np.array_equal(a.scores, b.scores), other
