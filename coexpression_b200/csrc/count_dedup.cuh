@@ -130,21 +130,67 @@ __device__ __forceinline__ int dd_bucket32(float x, float scale) {
 }
 __device__ __forceinline__ int dd_bucket(double t, float scale) { return dd_bucket32(__double2float_rn(t), scale); }
 
-// the same for a whole warp: coalesced loads, the products added in order through shuffles (every lane gets the result)
-__device__ __forceinline__ double pearson_exact_warp(const DedupArgs &a, long long ra, long long rb, int lane) {
-    if (a.raw_sum[ra] == 0.0 || a.raw_sum[rb] == 0.0) return -99.0;
-    const double *pa = a.raw + ra * a.n, *pb = a.raw + rb * a.n;
-    const double ma = a.raw_mean[ra], mb = a.raw_mean[rb];
-    double xy = 0.0;
-    for (int c0 = 0; c0 < a.n; c0 += 32) {
-        const int c = c0 + lane;
-        double prod = 0.0;
-        if (c < a.n) prod = __dmul_rn(__dsub_rn(pa[c], ma), __dsub_rn(pb[c], mb));
-        const int lim = min(32, a.n - c0);
-        for (int l = 0; l < lim; ++l) xy = __dadd_rn(xy, __shfl_sync(0xffffffffu, prod, l));
+// Sixteen of them per warp.  The reference adds the 1829 products strictly left to right: ONE refinement is a chain of dependent
+// double additions, ~60 k cycles whatever the number of lanes working on it (a warp per column with staged products was measured:
+// 64 k cycles; a thread per column walking its two rows with uncoalesced 8-byte loads: 300 k).  So a warp runs 16 chains at once, one
+// per lane 0..15: per 8 samples, lane (g, s) = (lane >> 3, lane & 7) loads sample s of row u once and of the columns of chains
+// 4 q + g, q = 0..3 (eight lanes share a 64-byte segment of a row; the next 8 samples are in flight meanwhile), the 16 x 8 products
+// are staged in a warp-private tile of shared memory (rows padded to 9 doubles: conflict-free), and lane r adds row r in order.
+// Samples behind the end of a row contribute +0.0 (x + 0.0 == x).  cols[r] < 0: no chain.  Returns lane r's r(u, cols[r]).
+constexpr int kPxChains = 16, kPxTile = kPxChains * 9;
+__device__ __forceinline__ double pearson_exact_16(const DedupArgs &a, long long ru, int my_col /* lane r < 16: column of chain r */,
+                                                   int lane, double *tile) {
+    const int g = lane >> 3, sidx = lane & 7;
+    const double mu = a.raw_mean[ru];
+    const double *pu = a.raw + ru * a.n;
+    int cq[4];
+    double mq[4];
+    const double *pq[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        cq[q] = __shfl_sync(0xffffffffu, my_col, 4 * q + g);
+        mq[q] = (cq[q] >= 0) ? a.raw_mean[cq[q]] : 0.0;
+        pq[q] = a.raw + (long long)max(cq[q], 0) * a.n;
     }
-    const double r = __ddiv_rn(xy, __dmul_rn(sqrt(a.raw_xx[ra]), sqrt(a.raw_xx[rb])));
-    return (r != r) ? -99.0 : r;
+    double xy = 0.0;
+    // two groups of 8 samples in flight (the rows come from HBM: the table does not fit L2)
+    double vu0, vq0[4], vu1, vq1[4];
+    auto fetch = [&](int c, double &vu, double (&vq)[4]) {
+        vu = (c < a.n) ? pu[c] : mu;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) vq[q] = (cq[q] >= 0 && c < a.n) ? pq[q][c] : mq[q];
+    };
+    auto chain8 = [&](const double vu, const double (&vq)[4]) {
+        const double du = __dsub_rn(vu, mu);
+        double prod[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) prod[q] = __dmul_rn(du, __dsub_rn(vq[q], mq[q]));
+        __syncwarp();                                  // the previous tile has been read
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tile[(4 * q + g) * 9 + sidx] = prod[q];
+        __syncwarp();
+        if (lane < kPxChains) {
+            const double *row = tile + lane * 9;
+#pragma unroll
+            for (int l = 0; l < 8; ++l) xy = __dadd_rn(xy, row[l]);
+        }
+    };
+    fetch(sidx, vu0, vq0);
+    fetch(8 + sidx, vu1, vq1);
+    for (int c0 = 0; c0 < a.n; c0 += 16) {
+        const double tu0 = vu0; const double tq0[4] = {vq0[0], vq0[1], vq0[2], vq0[3]};
+        fetch(c0 + 16 + sidx, vu0, vq0);
+        chain8(tu0, tq0);
+        const double tu1 = vu1; const double tq1[4] = {vq1[0], vq1[1], vq1[2], vq1[3]};
+        fetch(c0 + 24 + sidx, vu1, vq1);
+        chain8(tu1, tq1);                              // (behind the end of the row: eight times + 0.0)
+    }
+    double r = -99.0;
+    if (lane < kPxChains && my_col >= 0 && a.raw_sum[ru] != 0.0 && a.raw_sum[my_col] != 0.0) {
+        r = __ddiv_rn(xy, __dmul_rn(sqrt(a.raw_xx[ru]), sqrt(a.raw_xx[my_col])));
+        if (r != r) r = -99.0;
+    }
+    return r;
 }
 
 // MODE 0: Spearman null, statistics of the item's queries.  MODE 1: Pearson null (tensor filter), same items.
@@ -154,7 +200,7 @@ __device__ __forceinline__ double pearson_exact_warp(const DedupArgs &a, long lo
 //         wide windows, thousands of hits per set): every (query, hit) then only LOOKS UP the rank of its column
 //         (rank_score_kernel) instead of having the row streamed once per query.
 template <int MODE>
-__global__ void __launch_bounds__(kDdThreads)
+__global__ void __launch_bounds__(kDdThreads, 2)
 count_dedup_kernel(DedupArgs a) {
     constexpr bool PEARSON = (MODE == 1), RANKROW = (MODE == 2);
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -176,6 +222,7 @@ count_dedup_kernel(DedupArgs a) {
     unsigned int *bitmap = reinterpret_cast<unsigned int *>(q_toff + a.Qcap + 2);   // [bm_words] hit columns of this item (skipped by the streaming pass) | [bm_words] claim mask if a.claim
     __shared__ int s_T, s_qn, s_next;
     __shared__ unsigned int s_warp[kDdThreads / 32];
+    __shared__ double s_tile[PEARSON ? (kDdThreads / 32) * kPxTile : 1];        // staged products of a warp's 16 chains (pearson_exact_16)
 
     const int tid = threadIdx.x;
     const float bscale_f = (float)((double)kDdBuckets / (2.0 * a.R));
@@ -225,20 +272,12 @@ count_dedup_kernel(DedupArgs a) {
             q_cn[ql] = a.sc_off[lo] + (long long)i * P;
             double vi = -99.0;                             // null value at table column i (quirk Q1)
             if (PEARSON) {
-                vi = 0.0;                                  // filled in by one warp per query below
+                vi = 0.0;                                  // filled in by the last refinement pass (phase E)
             } else {
                 const double sxc = a.sx[i];
                 if (sxu != 0.0 && sxc != 0.0) vi = __ddiv_rn(0.25 * (double)srow[i], __dmul_rn(sxu, sxc));
             }
             q_vi[ql] = vi;
-        }
-        if (PEARSON) {
-            __syncthreads();
-            for (int ql = tid >> 5; ql < nq; ql += kDdThreads / 32) {
-                const int i = q_i[ql];
-                const double vi = (i < a.N) ? pearson_exact_warp(a, u, i, tid & 31) : -99.0;
-                if ((tid & 31) == 0) q_vi[ql] = vi;
-            }
         }
         if (tid == 0) { s_T = 0; s_qn = 0; }
         for (int b = tid; b <= kDdBuckets; b += kDdThreads) lut[b] = 0;
@@ -497,11 +536,39 @@ count_dedup_kernel(DedupArgs a) {
             __syncthreads();
             // ---- E. exact refinement of the queued columns ------------------------------------------
             const int qn = min(s_qn, kDdQueue);
-            // (a warp per queued column with shuffle-ordered additions was measured slower than a thread per column)
+            if (PEARSON) {
+                // A refinement pass costs one chain of n dependent additions whatever it holds (pearson_exact_16): the queue is
+                // worked off when it is half full and behind the last column, together with the exact null values at the skipped
+                // columns of the item's queries (quirk Q1), which phase F needs.
+                const bool last = cend >= N;
+                if (!last && qn < kDdQueue / 2) continue;              // (qn is the same in every thread: read behind the barrier)
+                const int total = qn + (last ? nq : 0);
+                for (int x0 = (tid >> 5) * kPxChains; x0 < total; x0 += (kDdThreads / 32) * kPxChains) {
+                    const int lane = tid & 31, x = x0 + lane;
+                    int c = -1;
+                    if (lane < kPxChains && x < total) {
+                        if (x < qn) c = queue[x];
+                        else { const int i = q_i[x - qn]; c = (i < a.N) ? i : -1; }
+                    }
+                    const double vv = pearson_exact_16(a, u, c, lane, s_tile + (tid >> 5) * kPxTile);
+                    if (lane < kPxChains && x < total) {
+                        if (x >= qn) q_vi[x - qn] = vv;                // (c < 0: -99)
+                        else {
+                            const unsigned int pk = lut[dd_bucket(vv, bscale_f)];
+                            int pp = (int)(pk & 0xffffu);
+                            int len = (int)(pk >> 16);
+                            while (len > 0) {
+                                const int half = len >> 1;
+                                if (srt[pp + half].r <= vv) { pp += half + 1; len -= half + 1; } else len = half;
+                            }
+                            atomicAdd(&hist[pp], 1u);
+                        }
+                    }
+                }
+            } else
             for (int x = tid; x < qn; x += kDdThreads) {
                 const int c = queue[x];
-                const double vv = PEARSON ? pearson_exact_thread(a, u, c)
-                                          : __ddiv_rn(0.25 * (double)srow[c], __dmul_rn(sxu, a.sx[c]));
+                const double vv = __ddiv_rn(0.25 * (double)srow[c], __dmul_rn(sxu, a.sx[c]));
                 const unsigned int pk = lut[dd_bucket(vv, bscale_f)];
                 int pp = (int)(pk & 0xffffu);
                 int len = (int)(pk >> 16);
