@@ -459,7 +459,7 @@ def run_ours(args):
         env.barrier()
         w0 = time.perf_counter()
         if world == 1:
-            ctx.set_expression(Xh)
+            ctx.set_expression(Xh, pipelined=True)           # page-locked table: row chunks, ranked as they land
         else:
             X_slice.copy_(X_pin, non_blocking=True)
             dist.all_gather_into_tensor(X_bc, X_slice)
@@ -569,7 +569,7 @@ def run_ours(args):
             "stage_ms_per_step": {s: per[s][0] for s in STAGES},
             "e2e": {"value": total_perms / (e2e_step_ms * 1e-3), "unit": "permutations/s", "ms_per_step": e2e_step_ms,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": ("CoexContext.set_expression + prepare + network_batch (pinned host table, host hit lists)" if world == 1 else
+                    "api": ("CoexContext.set_expression(pipelined) + prepare + network_batch (pinned host table, host hit lists)" if world == 1 else
                             "every rank uploads its 1/N-th of the pinned host table, NCCL all-gather of the slices over NVLink, then per "
                             "rank prepare + network_batch (host hit lists) and one NCCL all-gather of the densities read back on rank 0")},
             "gpu_launches": int(launches),
@@ -1012,7 +1012,7 @@ def full_shape(env, args):
         for i in range(2):
             torch.cuda.synchronize()
             a0 = time.perf_counter()
-            ctx.set_expression(Xh)
+            ctx.set_expression(Xh, pipelined=True)
             ctx.prepare()
             res_e = ctx.network_batch(hits, opts)
             a1 = time.perf_counter()

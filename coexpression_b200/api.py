@@ -113,11 +113,15 @@ class CoexContext:
             pass
 
     # ---- table -------------------------------------------------------------------------------
-    def set_expression(self, X):
-        """X: float64 [N, n] numpy array (host) -- one bulk H2D copy (A3)."""
+    def set_expression(self, X, pipelined=False):
+        """X: float64 [N, n] numpy array (host) -- one bulk H2D copy (A3).
+        pipelined=True: X is page-locked memory (e.g. the numpy view of a pinned torch tensor); the copy goes out in row chunks
+        and prepare() ranks every chunk as it lands.  X is kept referenced here and must not be modified until a synchronising
+        call (network_batch, sync) has returned."""
         X = np.ascontiguousarray(X, dtype=np.float64)
         self.N, self.n = X.shape
-        check(self.lib.coex_set_expression(self.h, X.ctypes.data, self.N, self.n, 0), "coex_set_expression")
+        self._host_table = X if pipelined else None
+        check(self.lib.coex_set_expression(self.h, X.ctypes.data, self.N, self.n, 2 if pipelined else 0), "coex_set_expression")
 
     def set_expression_device(self, dev_ptr, N, n, keepalive=None):
         """dev_ptr: device pointer to float64 [N, n] (e.g. torch tensor .data_ptr())."""

@@ -98,8 +98,20 @@ static int prepare_rows(coex_ctx *c, long long row0, long long row1, const RankO
         const int P2 = std::max(32, next_pow2(n));         // at least one warp-wide block of the in-register sort stages
         const size_t smem = (size_t)P2 * 10 + (size_t)c->n_pad * 2;
         COEX_CUDA(cudaFuncSetAttribute(rank_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rank_pack_kernel<<<(unsigned)(row1 - row0), kRankThreads, smem, c->stream>>>(c->raw, N, n, c->n_pad, P2, row0, ro);
-        COEX_CUDA(cudaGetLastError());
+        if (c->up_pending) {
+            // the table is still arriving (coex_set_expression, on_device = 2): rank every chunk of rows as it lands
+            for (int k = 0; k < c->up_pending; ++k) {
+                const long long a0 = std::max(row0, (long long)k * c->up_rows), a1 = std::min(row1, (long long)(k + 1) * c->up_rows);
+                COEX_CUDA(cudaStreamWaitEvent(c->stream, c->up_event[k], 0));
+                if (a1 <= a0) continue;
+                rank_pack_kernel<<<(unsigned)(a1 - a0), kRankThreads, smem, c->stream>>>(c->raw, N, n, c->n_pad, P2, a0, ro);
+                COEX_CUDA(cudaGetLastError());
+            }
+            c->up_pending = 0;                             // the compute stream is behind every chunk from here on
+        } else {
+            rank_pack_kernel<<<(unsigned)(row1 - row0), kRankThreads, smem, c->stream>>>(c->raw, N, n, c->n_pad, P2, row0, ro);
+            COEX_CUDA(cudaGetLastError());
+        }
     }
     COEX_TRY(stage_end(c, 1));
     COEX_TRY(stage_begin(c, ST_ROWSTATS));
@@ -848,6 +860,11 @@ int coex_destroy(coex_ctx *c) {
     c->dd_items.release(); c->dd_qperm.release(); c->pl_cnt.release(); c->pl_cursor.release(); c->pl_ustart.release(); c->pl_nitems.release();
     c->pl_itemoff.release(); c->pl_bounds.release(); c->pl_meta.release(); c->pl_err.release(); c->dd_gthr.release(); c->dd_tab.release();
     if (c->rb_stream) { cudaStreamDestroy(c->rb_stream); cudaEventDestroy(c->rb_event); }
+    if (c->up_stream) {
+        cudaStreamSynchronize(c->up_stream);
+        cudaStreamDestroy(c->up_stream); cudaEventDestroy(c->up_start);
+        for (int k = 0; k < coex_ctx::kUpChunks; ++k) cudaEventDestroy(c->up_event[k]);
+    }
     for (void *p : c->peer_mapped) if (p) cudaIpcCloseMemHandle(p);
     for (void *p : c->tab_mapped) if (p) cudaIpcCloseMemHandle(p);
     c->shard_scores.release(); c->d_perm_scores.release();
@@ -871,7 +888,32 @@ int coex_set_expression(coex_ctx *c, const double *data, long long N, int n, int
     c->prepared = false;
     c->z_digits = 0;
     c->N = N; c->n = n;
-    if (on_device) {
+    if (c->up_pending) {                        // a pipelined upload nobody prepared: the compute stream gets behind it first
+        COEX_CUDA(cudaStreamWaitEvent(c->stream, c->up_event[c->up_pending - 1], 0));
+        c->up_pending = 0;
+    }
+    if (on_device == 2) {
+        // page-locked host memory, pipelined with the rank transform: kUpChunks row chunks on a stream of their own (behind
+        // everything queued on the compute stream, which may still read the previous table), an event per chunk
+        COEX_TRY(c->raw_own.reserve((size_t)N * n));
+        if (!c->up_stream) {
+            COEX_CUDA(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+            COEX_CUDA(cudaEventCreateWithFlags(&c->up_start, cudaEventDisableTiming));
+            for (int k = 0; k < coex_ctx::kUpChunks; ++k) COEX_CUDA(cudaEventCreateWithFlags(&c->up_event[k], cudaEventDisableTiming));
+        }
+        COEX_CUDA(cudaEventRecord(c->up_start, c->stream));
+        COEX_CUDA(cudaStreamWaitEvent(c->up_stream, c->up_start, 0));
+        c->up_rows = (N + coex_ctx::kUpChunks - 1) / coex_ctx::kUpChunks;
+        int k = 0;
+        for (long long r0 = 0; r0 < N; r0 += c->up_rows, ++k) {
+            const long long r1 = std::min(N, r0 + c->up_rows);
+            COEX_CUDA(cudaMemcpyAsync(c->raw_own.p + (size_t)r0 * n, data + (size_t)r0 * n, (size_t)(r1 - r0) * n * sizeof(double),
+                                      cudaMemcpyHostToDevice, c->up_stream));
+            COEX_CUDA(cudaEventRecord(c->up_event[k], c->up_stream));
+        }
+        c->up_pending = k;
+        c->raw = c->raw_own.p;
+    } else if (on_device) {
         c->raw = data;
     } else {
         COEX_TRY(c->raw_own.reserve((size_t)N * n));

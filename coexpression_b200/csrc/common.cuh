@@ -138,6 +138,11 @@ struct coex_ctx {
     coex::DevBuf<double *> d_perm_scores;
     int rb_k = -1; double *rb_host = nullptr;                  // coex_set_score_readback: block to copy out during the network stage
     cudaStream_t rb_stream = nullptr; cudaEvent_t rb_event = nullptr;
+    // coex_set_expression(on_device = 2): the table arrives in row chunks on up_stream; coex_prepare ranks a chunk when its event fires
+    static constexpr int kUpChunks = 8;
+    cudaStream_t up_stream = nullptr; cudaEvent_t up_event[kUpChunks] = {}, up_start = nullptr;
+    int up_pending = 0;                       // chunks in flight (0: the table is resident)
+    long long up_rows = 0;                    // rows per chunk
     std::vector<long long> last_sc_off;                        // score-block offsets of the last reduced batch and where its scores
     const double *last_scores = nullptr;                       // live (the context's buffer, or the caller's device buffer)
     std::vector<double> h_score_tab;                           // host-built edge-score table (see spearman_dedup_path)

@@ -50,7 +50,10 @@ int coex_sync(coex_ctx *ctx);
 void *coex_stream(coex_ctx *ctx);       /* the cudaStream_t every kernel of ctx is launched on */
 
 /* A3 "matrix marshal" (1-make-network.py:100-122): one bulk copy instead of N*n Python stores.
- * data: double [N * n] row-major in table order.  `on_device` != 0: data is a device pointer. */
+ * data: double [N * n] row-major in table order.  `on_device` = 1: data is a device pointer (used in place).
+ * `on_device` = 2: data is PAGE-LOCKED host memory and the call returns while the copy is in flight -- row chunks on a stream of
+ * their own, and coex_prepare ranks every chunk as it lands (the rank transform hides under the PCIe copy); the caller must leave
+ * `data` alone until a synchronising call (coex_sync, coex_network_batch, ...) has returned. */
 int coex_set_expression(coex_ctx *ctx, const double *data, long long N, int n, int on_device);
 
 /* A2 rank transform (scipy.stats.rankdata 'average', 1-make-network.py:108-111) + per-row
