@@ -515,6 +515,314 @@ gemm_i8_tc_persistent128_kernel(const __grid_constant__ CUtensorMap map_ah, cons
 }
 
 // =============================================================================================
+// 128 x 128 tiles, TWO CTAs of a cluster on neighbouring query-row tiles of the SAME table-column tile: the B operand of a K block
+// is fetched from L2 once per cluster -- rank 0 loads the B_hi plane, rank 1 the B_lo plane, each with a multicast TMA into both
+// CTAs -- so a CTA reads 48 KB instead of 64 KB per K block.  Why: at the FANTOM5 shape the 128 x 128 kernel pulls 2.25 TB through
+// L2 -> shared memory in 189 ms (11.9 TB/s): it is bound by that traffic, not by the tensor pipe (77 %) or its epilogue.
+// Same MMAs (cta_group::1), same epilogue.  A stage may be refilled when BOTH CTAs have consumed it (the partner's multicast
+// writes into it too): every MMA thread commits to the empty barrier of both CTAs (count 2).
+// =============================================================================================
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, unsigned short mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, unsigned short mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP8Threads, 1)
+gemm_i8_tc_cluster128_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                             const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+                             int *__restrict__ out, long long ldo, int nkb, int m_tiles, long long n_tiles, int col_tile0,
+                             int *err) {
+    using C = TcCfg<128>;
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    const uint32_t bars = base + C::kStages * C::kStage;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * C::kStages;
+    const uint32_t bar_tfull = bars + 16 * C::kStages, bar_tempty = bar_tfull + 8;
+    const uint32_t tmem_slot = bar_tempty + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 2); }
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tempty, kP8EpiWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // the partner's barriers exist
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    // tile pair p of the cluster: tiles 2 p and 2 p + 1 in query-row-fastest order (m_tiles is even: the same column tile)
+    const long long first = 2 * (long long)(blockIdx.x >> 1) + rank, step = 2 * (long long)(gridDim.x >> 1);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            long long g = 0;
+            bool ok = true;
+            for (long long tile = first; tile < n_tiles && ok; tile += step) {
+                const int m0 = (int)(tile % m_tiles) * kTcBM;
+                const int c0 = ((int)(tile / m_tiles) + col_tile0) * kP8BN;
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = (int)(g % C::kStages);
+                    if (g >= C::kStages && !mbar_wait(bar_empty + 8 * s, (uint32_t)((g / C::kStages) - 1) & 1u, err, 1)) { ok = false; break; }
+                    const uint32_t st = base + s * C::kStage;
+                    mbar_expect_tx(bar_full + 8 * s, C::kStage);
+                    tma_load_2d(st, &map_ah, bar_full + 8 * s, kb * kTcBK, m0);
+                    tma_load_2d(st + 16384, &map_al, bar_full + 8 * s, kb * kTcBK, m0);
+                    if (rank == 0) tma_load_2d_mc(st + 32768, &map_bh, bar_full + 8 * s, kb * kTcBK, c0, 3);
+                    else tma_load_2d_mc(st + 32768 + kP8BN * 128, &map_bl, bar_full + 8 * s, kb * kTcBK, c0, 3);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_i8(128, 2 * kP8BN);
+            long long g = 0;
+            int it = 0;
+            bool ok = true;
+            for (long long tile = first; tile < n_tiles && ok; tile += step, ++it) {
+                if (it >= 1 && !mbar_wait(bar_tempty, (uint32_t)(it - 1) & 1u, err, 4)) { ok = false; break; }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = (int)(g % C::kStages);
+                    if (!mbar_wait(bar_full + 8 * s, (uint32_t)(g / C::kStages) & 1u, err, 2)) { ok = false; break; }
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = base + s * C::kStage;
+#pragma unroll
+                    for (int ks = 0; ks < kTcBK / 32; ++ks) {
+                        const uint64_t a_hi = umma_desc_sw128(st + ks * 32);
+                        const uint64_t a_lo = umma_desc_sw128(st + 16384 + ks * 32);
+                        const uint64_t b_cat = umma_desc_sw128(st + 32768 + ks * 32);
+                        const uint32_t acc = (kb | ks) ? 1u : 0u;
+                        umma_i8(tmem_base, a_hi, b_cat, idesc, acc);                    // [hi.hi | hi.lo]
+                        umma_i8(tmem_base + 2 * kP8BN, a_lo, b_cat, idesc, acc);        // [lo.hi | lo.lo]
+                    }
+                    umma_commit_mc(bar_empty + 8 * s, 3);                              // both CTAs' producers
+                }
+                if (ok) umma_commit(bar_tfull);
+            }
+        }
+    } else {
+        constexpr int kCols = kP8BN / (kP8EpiWarps / 4);
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        int it = 0;
+        for (long long tile = first; tile < n_tiles; tile += step, ++it) {
+            const int m0 = (int)(tile % m_tiles) * kTcBM;
+            const int c0 = ((int)(tile / m_tiles) + col_tile0) * kP8BN;
+            if (!mbar_wait(bar_tfull, (uint32_t)it & 1u, err, 3)) break;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16);
+            int *orow = out + (long long)(m0 + quarter * 32 + lane) * ldo + c0;
+#pragma unroll 1
+            for (int cc = half * kCols; cc < half * kCols + kCols; cc += 16) {
+                uint32_t hh[16], hl[16], lh[16], ll[16];
+                tmem_ld16(tl + cc, hh);
+                tmem_ld16(tl + kP8BN + cc, hl);
+                tmem_ld16(tl + 2 * kP8BN + cc, lh);
+                tmem_ld16(tl + 3 * kP8BN + cc, ll);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                int v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    v[j] = (int)(16384LL * (int)hh[j] + 128LL * ((long long)(int)hl[j] + (int)lh[j]) + (int)ll[j]);
+                store_chunk16_paired(orow, ldo, cc, v, lane);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    // (the partner may still be multicasting into this CTA's shared memory / arriving on its barriers)
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// =============================================================================================
+// CTA-PAIR variant (cta_group::2): two CTAs of a cluster (one TPC) work on a 256 x 64 tile -- rank r owns query rows
+// [m0 + 128 r, + 128) and their accumulators -- with ONE tcgen05.mma.cta_group::2 of M = 256, N = 128 per product issued by the
+// leader: the stacked B operand [B_hi ; B_lo] is split between the CTAs (the leader stages the 64 B_hi rows, its peer the 64 B_lo
+// rows, at the same shared-memory offset), so a CTA moves 40 KB per 128-byte K block for a 128 x 64 tile -- the operand rate of
+// the 128 x 128 kernel above (~92 B/clk at the int8 rate) -- while its four partial sums take only 256 TMEM columns: the
+// accumulators are DOUBLE-BUFFERED and the epilogue of tile t runs under the MMAs of tile t + 1, which the 128 x 128 kernel
+// cannot do (its accumulators fill all 512 columns; the epilogue is 4 - 5 k of ~20 k cycles per tile there).
+//   full[s]    leader's barrier: armed by the leader with the bytes of BOTH CTAs, every TMA of the pair completes on it
+//   empty[s]   one per CTA, signalled by the leader's multicast tcgen05.commit
+//   tfull[a]   one per CTA, multicast commit after the last K block of a tile
+//   tempty[a]  leader's barrier, 2 x kPrEpiWarps arrivals (the peer's epilogue warps arrive remotely)
+// =============================================================================================
+constexpr int kPrStages = 5, kPrStage = 32768 + 64 * 128, kPrEpiWarps = 8, kPrThreads = 64 + 32 * kPrEpiWarps;
+constexpr int kPrSmem = kPrStages * kPrStage + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_i8_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((unsigned short)3) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPrThreads, 1)
+gemm_i8_tc_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                       const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+                       int *__restrict__ out, long long ldo, int nkb, int m_pairs, long long n_tiles, int col_tile0, int *err) {
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    const uint32_t bars = base + kPrStages * kPrStage;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * kPrStages;
+    const uint32_t bar_tfull = bars + 16 * kPrStages, bar_tempty = bar_tfull + 16;
+    const uint32_t tmem_slot = bar_tempty + 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kPrStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 2 * kPrEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                                 // the peer's barriers are initialised, its TMEM allocated
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    const long long cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own A rows, own half of the stacked B =====
+        if (lane == 0) {
+            long long g = 0;
+            bool ok = true;
+            for (long long tile = cid; tile < n_tiles && ok; tile += ncl) {
+                const int m0 = (int)(tile % m_pairs) * 256 + (int)rank * 128;        // query-row tile fastest
+                const int c0 = ((int)(tile / m_pairs) + col_tile0) * 64;
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = (int)(g % kPrStages);
+                    if (g >= kPrStages && !mbar_wait(bar_empty + 8 * s, (uint32_t)((g / kPrStages) - 1) & 1u, err, 1)) { ok = false; break; }
+                    const uint32_t st = base + s * kPrStage;
+                    const uint32_t lf = mapa_rank(bar_full + 8 * s, 0);
+                    if (leader) mbar_expect_tx(bar_full + 8 * s, 2 * kPrStage);
+                    tma_load_2d_pair(st, &map_ah, lf, kb * kTcBK, m0);
+                    tma_load_2d_pair(st + 16384, &map_al, lf, kb * kTcBK, m0);
+                    tma_load_2d_pair(st + 32768, leader ? &map_bh : &map_bl, lf, kb * kTcBK, c0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader only): two accumulator sets of 256 columns =====
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = umma_idesc_i8(256, 128);
+            long long g = 0;
+            int it = 0;
+            bool ok = true;
+            for (long long tile = cid; tile < n_tiles && ok; tile += ncl, ++it) {
+                const int as = it & 1;
+                if (it >= 2 && !mbar_wait(bar_tempty + 8 * as, (uint32_t)((it >> 1) - 1) & 1u, err, 4)) { ok = false; break; }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d0 = tmem_base + (uint32_t)as * 256u;
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = (int)(g % kPrStages);
+                    if (!mbar_wait(bar_full + 8 * s, (uint32_t)(g / kPrStages) & 1u, err, 2)) { ok = false; break; }
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = base + s * kPrStage;
+#pragma unroll
+                    for (int ks = 0; ks < kTcBK / 32; ++ks) {
+                        const uint64_t a_hi = umma_desc_sw128(st + ks * 32);
+                        const uint64_t a_lo = umma_desc_sw128(st + 16384 + ks * 32);
+                        const uint64_t b_cat = umma_desc_sw128(st + 32768 + ks * 32);
+                        const uint32_t acc = (kb | ks) ? 1u : 0u;
+                        umma_i8_pair(d0, a_hi, b_cat, idesc, acc);                      // [hi.hi | hi.lo], 64 columns each
+                        umma_i8_pair(d0 + 128, a_lo, b_cat, idesc, acc);                // [lo.hi | lo.lo]
+                    }
+                    umma_commit_pair(bar_empty + 8 * s);
+                }
+                if (ok) umma_commit_pair(bar_tfull + 8 * as);
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): TMEM lane quarter = warp % 4, 32 of the 64 columns per warp =====
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        int it = 0;
+        for (long long tile = cid; tile < n_tiles; tile += ncl, ++it) {
+            const int as = it & 1;
+            const int m0 = (int)(tile % m_pairs) * 256 + (int)rank * 128;
+            const int c0 = ((int)(tile / m_pairs) + col_tile0) * 64;
+            if (!mbar_wait(bar_tfull + 8 * as, (uint32_t)(it >> 1) & 1u, err, 3)) break;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tl = tmem_base + (uint32_t)as * 256u + ((uint32_t)(quarter * 32) << 16);
+            int *orow = out + (long long)(m0 + quarter * 32 + lane) * ldo + c0;
+#pragma unroll 1
+            for (int cc = half * 32; cc < half * 32 + 32; cc += 16) {
+                uint32_t hh[16], hl[16], lh[16], ll[16];
+                tmem_ld16(tl + cc, hh);
+                tmem_ld16(tl + 64 + cc, hl);
+                tmem_ld16(tl + 128 + cc, lh);
+                tmem_ld16(tl + 192 + cc, ll);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                int v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    v[j] = (int)(16384LL * (int)hh[j] + 128LL * ((long long)(int)hl[j] + (int)lh[j]) + (int)ll[j]);
+                store_chunk16_paired(orow, ldo, cc, v, lane);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_rank(bar_tempty + 8 * as, 0));
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                                 // the leader's MMAs read this CTA's shared memory and write its TMEM
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// =============================================================================================
 // Generic D-digit variant (Pearson): z-scores quantised to D base-128 int8 digits
 // (prepare.cuh: pearson_pack_kernel).  One CTA per 128 x 32 output tile; per 32-byte K step
 //      D_i[128 x (D*32)] += A_i * [B_{D-1} ; ... ; B_0]^T            i = 0 .. D-1
@@ -722,7 +1030,9 @@ inline int tc_gemm_i8_ptrs(coex_ctx *c, const int8_t *a_hi, const int8_t *a_lo, 
     // gemm_bn: 0 = persistent (128 x 64 tiles; 128 x 128 tiles for long rows), -64 / -128 = that persistent kernel forced,
     //          64 / 128 = one-tile-per-CTA kernel with that table-column tile
     const bool persistent = (c->gemm_bn <= 0);
-    const bool wide = persistent && (c->gemm_bn == -128 || (c->gemm_bn == 0 && c->n_pad >= 1024));
+    const bool pair = (c->gemm_bn == -256) && (m_rows % 256 == 0) && (c->sm_count >= 2);      // CTA pairs, 256 x 64 tiles
+    const bool wide = persistent && !pair && (c->gemm_bn == -128 || c->gemm_bn == -129 || (c->gemm_bn == 0 && c->n_pad >= 1024));
+    const bool clustered = wide && c->gemm_bn == -129 && (m_rows % 256 == 0) && c->sm_count >= 2;      // B multicast inside CTA pairs
     const int BN = persistent ? (wide ? kP8BN : kPsBN) : c->gemm_bn;
     if (t->bh != c->u_hi.p || t->bl != c->u_lo.p || t->b_rows != c->N_pad || t->n_pad != c->n_pad || t->bn != BN) {
         COEX_TRY(tc_encode(t, &t->map_bh, c->u_hi.p, c->N_pad, c->n_pad, BN));
@@ -740,12 +1050,32 @@ inline int tc_gemm_i8_ptrs(coex_ctx *c, const int8_t *a_hi, const int8_t *a_lo, 
         COEX_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::kSmem));
         COEX_CUDA(cudaFuncSetAttribute(gemm_i8_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPsSmem));
         COEX_CUDA(cudaFuncSetAttribute(gemm_i8_tc_persistent128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmem));
+        COEX_CUDA(cudaFuncSetAttribute(gemm_i8_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrSmem));
+        COEX_CUDA(cudaFuncSetAttribute(gemm_i8_tc_cluster128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmem));
         t->attr_set = true;
+    }
+    if (pair) {
+        const int m_pairs = (int)(m_rows / 256);
+        const int col_tile0 = (int)std::min<long long>(c->gemm_col0 / 64, c->N_pad / 64 - 1);
+        const long long n_tiles = (long long)m_pairs * (c->N_pad / 64 - col_tile0);
+        const unsigned ctas = 2u * (unsigned)std::min<long long>(n_tiles, c->sm_count / 2);
+        gemm_i8_tc_pair_kernel<<<ctas, kPrThreads, kPrSmem, c->stream>>>(t->map_ah, t->map_al, t->map_bh, t->map_bl, out, ldo,
+                                                                        c->n_pad / kTcBK, m_pairs, n_tiles, col_tile0, t->d_err);
+        COEX_CUDA(cudaGetLastError());
+        return 0;
     }
     if (wide) {
         const int m_tiles = (int)(m_rows / kTcBM);
         const int col_tile0 = (int)std::min<long long>(c->gemm_col0 / kP8BN, c->N_pad / kP8BN - 1);
         const long long n_tiles = (long long)m_tiles * (c->N_pad / kP8BN - col_tile0);
+        if (clustered) {
+            const unsigned cl = 2u * (unsigned)std::min<long long>(n_tiles / 2, c->sm_count / 2);
+            gemm_i8_tc_cluster128_kernel<<<cl, kP8Threads, TcCfg<128>::kSmem, c->stream>>>(t->map_ah, t->map_al, t->map_bh, t->map_bl,
+                                                                                           out, ldo, c->n_pad / kTcBK, m_tiles, n_tiles,
+                                                                                           col_tile0, t->d_err);
+            COEX_CUDA(cudaGetLastError());
+            return 0;
+        }
         const unsigned ctas = (unsigned)std::min<long long>(n_tiles, c->sm_count);
         gemm_i8_tc_persistent128_kernel<<<ctas, kP8Threads, TcCfg<128>::kSmem, c->stream>>>(t->map_ah, t->map_al, t->map_bh, t->map_bl,
                                                                                           out, ldo, c->n_pad / kTcBK, m_tiles, n_tiles,
