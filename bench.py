@@ -63,7 +63,7 @@ def parse():
     ap.add_argument("--window", type=int, default=10000, help="-w")
     ap.add_argument("--anticorrelation", action="store_true")
     ap.add_argument("--pval-to-join", type=float, default=0.1)
-    ap.add_argument("--gemm", default="tcgen05", choices=["tcgen05", "simt", "tcgen05_bn64", "tcgen05_bn128", "tcgen05_persistent", "tcgen05_persistent128", "tcgen05_pair", "tcgen05_cluster128"])
+    ap.add_argument("--gemm", default="tcgen05", choices=["tcgen05", "simt", "tcgen05_bn64", "tcgen05_bn128", "tcgen05_persistent", "tcgen05_persistent128", "tcgen05_cluster128", "tcgen05_split"])
     ap.add_argument("--cpu-sample-perms", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the full_shape / allpairs / strong objects")

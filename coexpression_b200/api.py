@@ -418,7 +418,7 @@ class CoexContext:
         check(self.lib.coex_sync(self.h), "coex_sync")
 
     def set_gemm_mode(self, mode):
-        check(self.lib.coex_set_gemm_mode(self.h, {"tcgen05": 0, "simt": 1, "tcgen05_bn64": 64, "tcgen05_bn128": 128, "tcgen05_persistent": 2, "tcgen05_persistent128": 3, "tcgen05_pair": 4, "tcgen05_cluster128": 5}.get(mode, mode)),
+        check(self.lib.coex_set_gemm_mode(self.h, {"tcgen05": 0, "simt": 1, "tcgen05_bn64": 64, "tcgen05_bn128": 128, "tcgen05_persistent": 2, "tcgen05_persistent128": 3, "tcgen05_cluster128": 5, "tcgen05_split": 6}.get(mode, mode)),
               "coex_set_gemm_mode")
 
     def set_count_mode(self, mode):

@@ -1385,10 +1385,11 @@ int coex_set_gemm_mode(coex_ctx *c, int mode) {
     if (mode == 2) { c->gemm_mode = 0; c->gemm_bn = -64; return 0; }                    // persistent tcgen05 kernel, 128 x 64 tiles
     if (mode == 3) { c->gemm_mode = 0; c->gemm_bn = -128; return 0; }                   // persistent tcgen05 kernel, 128 x 128 tiles
     if (mode == 4) { c->gemm_mode = 0; c->gemm_bn = -256; return 0; }
-    if (mode == 5) { c->gemm_mode = 0; c->gemm_bn = -129; return 0; }                   // 128 x 128 tiles, B multicast inside CTA pairs                   // CTA-pair tcgen05 kernel (cta_group::2), 256 x 64 tiles
+    if (mode == 5) { c->gemm_mode = 0; c->gemm_bn = -129; return 0; }
+    if (mode == 6) { c->gemm_mode = 0; c->gemm_bn = -257; return 0; }                   // digit-split CTA pairs (cta_group::2), double-buffered accumulators                   // 128 x 128 tiles, B multicast inside CTA pairs                   // CTA-pair tcgen05 kernel (cta_group::2), 256 x 64 tiles
     if (mode != 0 && mode != 1)
         COEX_FAIL("coex_set_gemm_mode: 0 = tcgen05 (persistent, tile chosen by row length), 1 = SIMT dp4a, 2 / 3 = persistent tcgen05 with "
-                  "128 x 64 / 128 x 128 tiles, 4 = cta_group::2 pair kernel, 5 = 128 x 128 with B multicast in CTA pairs, "
+                  "128 x 64 / 128 x 128 tiles, 5 = 128 x 128 with B multicast in CTA pairs, 6 = digit-split cta_group::2 pairs, "
                   "64 / 128 = one-tile-per-CTA tcgen05 with that column tile");
     c->gemm_mode = mode;
     if (mode == 0) c->gemm_bn = 0;

@@ -655,20 +655,8 @@ gemm_i8_tc_cluster128_kernel(const __grid_constant__ CUtensorMap map_ah, const _
 }
 
 // =============================================================================================
-// CTA-PAIR variant (cta_group::2): two CTAs of a cluster (one TPC) work on a 256 x 64 tile -- rank r owns query rows
-// [m0 + 128 r, + 128) and their accumulators -- with ONE tcgen05.mma.cta_group::2 of M = 256, N = 128 per product issued by the
-// leader: the stacked B operand [B_hi ; B_lo] is split between the CTAs (the leader stages the 64 B_hi rows, its peer the 64 B_lo
-// rows, at the same shared-memory offset), so a CTA moves 40 KB per 128-byte K block for a 128 x 64 tile -- the operand rate of
-// the 128 x 128 kernel above (~92 B/clk at the int8 rate) -- while its four partial sums take only 256 TMEM columns: the
-// accumulators are DOUBLE-BUFFERED and the epilogue of tile t runs under the MMAs of tile t + 1, which the 128 x 128 kernel
-// cannot do (its accumulators fill all 512 columns; the epilogue is 4 - 5 k of ~20 k cycles per tile there).
-//   full[s]    leader's barrier: armed by the leader with the bytes of BOTH CTAs, every TMA of the pair completes on it
-//   empty[s]   one per CTA, signalled by the leader's multicast tcgen05.commit
-//   tfull[a]   one per CTA, multicast commit after the last K block of a tile
-//   tempty[a]  leader's barrier, 2 x kPrEpiWarps arrivals (the peer's epilogue warps arrive remotely)
+// cta_group::2 helpers (two CTAs of a cluster = one TPC driving ONE tcgen05.mma of M = 256)
 // =============================================================================================
-constexpr int kPrStages = 5, kPrStage = 32768 + 64 * 128, kPrEpiWarps = 8, kPrThreads = 64 + 32 * kPrEpiWarps;
-constexpr int kPrSmem = kPrStages * kPrStage + 1024 + 256;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -701,23 +689,64 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
                  ::"r"(bar), "h"((unsigned short)3) : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPrThreads, 1)
-gemm_i8_tc_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
-                       const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
-                       int *__restrict__ out, long long ldo, int nkb, int m_pairs, long long n_tiles, int col_tile0, int *err) {
+// =============================================================================================
+// DIGIT-SPLIT CTA pair (cta_group::2): both CTAs of a cluster work on the SAME 128 x 128 output tile; the leader stages the A_hi
+// plane of the 128 query rows and the B_hi plane of the 128 table rows, its peer A_lo and B_lo, and ONE tcgen05.mma.cta_group::2
+// of M = 256, N = 256 per K step computes [A_hi ; A_lo] x [B_hi ; B_lo]^T: the leader's TMEM receives [hi.hi | hi.lo], the peer's
+// [lo.hi | lo.lo] -- 256 columns per tile and CTA, so the accumulators are DOUBLE-BUFFERED and the epilogue of tile t runs under the
+// MMAs of tile t + 1, with the N = 256 MMAs the other double-buffered shapes cannot have.  The price is a
+// combine step: S = (16384 hi.hi + 128 hi.lo) + (128 lo.hi + lo.lo), the two brackets live in different CTAs.  Each is formed
+// modulo 2^32 (S itself fits 32 bits); the leader finishes columns 0..63 of the tile, its peer columns 64..127, and each sends the
+// other half of its bracket to the partner's shared memory (st.shared::cluster, [column][row] layout: conflict-free).
+//   full[s]     leader's barrier, armed with the bytes of both CTAs       empty[s]   per CTA, multicast commit
+//   tfull[a]    per CTA, multicast commit after a tile's last K block     tempty[a]  leader's, 2 x 16 arrivals (the peer's remotely)
+//   recv[a]     per CTA: the partner's 8 sender warps have written their half bracket into this CTA's staging buffer a
+//   sendok[a]   per CTA: the partner's 8 keeper warps have read staging buffer a of THEIR CTA (it may be written again)
+// =============================================================================================
+constexpr int kSpStages = 4, kSpStage = 16384 + 16384, kSpStaging = 64 * 128 * 4;
+constexpr int kSpSmem = kSpStages * kSpStage + 2 * kSpStaging + 1024 + 256;
+
+// wait with acquire semantics at CLUSTER scope: what the partner CTA wrote into this CTA's shared memory before its (release.cluster)
+// arrival is visible afterwards
+__device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity, int *err, int code) {
+    for (unsigned spin = 0; spin < kTcSpinLimit; ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    atomicExch(err, code);
+    return false;
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t cluster_addr, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP8Threads, 1)
+gemm_i8_tc_split_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                        const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+                        int *__restrict__ out, long long ldo, int nkb, int m_tiles, long long n_tiles, int col_tile0, int *err) {
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-    const uint32_t bars = base + kPrStages * kPrStage;
-    const uint32_t bar_full = bars, bar_empty = bars + 8 * kPrStages;
-    const uint32_t bar_tfull = bars + 16 * kPrStages, bar_tempty = bar_tfull + 16;
-    const uint32_t tmem_slot = bar_tempty + 16;
+    const uint32_t staging = base + kSpStages * kSpStage;                     // [2][64 columns][128 rows] u32
+    const uint32_t bars = staging + 2 * kSpStaging;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * kSpStages;
+    const uint32_t bar_tfull = bars + 16 * kSpStages, bar_tempty = bar_tfull + 16;
+    const uint32_t bar_recv = bar_tempty + 16, bar_sendok = bar_recv + 16;
+    const uint32_t tmem_slot = bar_sendok + 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kPrStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 2 * kPrEpiWarps); }
+        for (int s = 0; s < kSpStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 2 * kP8EpiWarps);
+            mbar_init(bar_recv + 8 * a, kP8EpiWarps / 2); mbar_init(bar_sendok + 8 * a, kP8EpiWarps / 2);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -726,36 +755,36 @@ gemm_i8_tc_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    cluster_sync_all();                                 // the peer's barriers are initialised, its TMEM allocated
+    cluster_sync_all();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     const long long cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
 
     if (warp == 0) {
-        // ===== TMA producer (both CTAs): own A rows, own half of the stacked B =====
+        // ===== TMA producer: this CTA's digit plane of the query rows and of the table rows =====
         if (lane == 0) {
+            const CUtensorMap *ma = leader ? &map_ah : &map_al, *mb = leader ? &map_bh : &map_bl;
             long long g = 0;
             bool ok = true;
             for (long long tile = cid; tile < n_tiles && ok; tile += ncl) {
-                const int m0 = (int)(tile % m_pairs) * 256 + (int)rank * 128;        // query-row tile fastest
-                const int c0 = ((int)(tile / m_pairs) + col_tile0) * 64;
+                const int m0 = (int)(tile % m_tiles) * kTcBM;                         // query-row tile fastest
+                const int c0 = ((int)(tile / m_tiles) + col_tile0) * kP8BN;
                 for (int kb = 0; kb < nkb; ++kb, ++g) {
-                    const int s = (int)(g % kPrStages);
-                    if (g >= kPrStages && !mbar_wait(bar_empty + 8 * s, (uint32_t)((g / kPrStages) - 1) & 1u, err, 1)) { ok = false; break; }
-                    const uint32_t st = base + s * kPrStage;
+                    const int s = (int)(g % kSpStages);
+                    if (g >= kSpStages && !mbar_wait(bar_empty + 8 * s, (uint32_t)((g / kSpStages) - 1) & 1u, err, 1)) { ok = false; break; }
+                    const uint32_t st = base + s * kSpStage;
                     const uint32_t lf = mapa_rank(bar_full + 8 * s, 0);
-                    if (leader) mbar_expect_tx(bar_full + 8 * s, 2 * kPrStage);
-                    tma_load_2d_pair(st, &map_ah, lf, kb * kTcBK, m0);
-                    tma_load_2d_pair(st + 16384, &map_al, lf, kb * kTcBK, m0);
-                    tma_load_2d_pair(st + 32768, leader ? &map_bh : &map_bl, lf, kb * kTcBK, c0);
+                    if (leader) mbar_expect_tx(bar_full + 8 * s, 2 * kSpStage);
+                    tma_load_2d_pair(st, ma, lf, kb * kTcBK, m0);
+                    tma_load_2d_pair(st + 16384, mb, lf, kb * kTcBK, c0);
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (leader only): two accumulator sets of 256 columns =====
+        // ===== MMA issuer (leader only): one M = 256, N = 256 MMA per K step, two accumulator sets =====
         if (lane == 0 && leader) {
-            constexpr uint32_t idesc = umma_idesc_i8(256, 128);
+            constexpr uint32_t idesc = umma_idesc_i8(256, 2 * kP8BN);
             long long g = 0;
             int it = 0;
             bool ok = true;
@@ -765,58 +794,79 @@ gemm_i8_tc_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d0 = tmem_base + (uint32_t)as * 256u;
                 for (int kb = 0; kb < nkb; ++kb, ++g) {
-                    const int s = (int)(g % kPrStages);
-                    if (!mbar_wait(bar_full + 8 * s, (uint32_t)(g / kPrStages) & 1u, err, 2)) { ok = false; break; }
+                    const int s = (int)(g % kSpStages);
+                    if (!mbar_wait(bar_full + 8 * s, (uint32_t)(g / kSpStages) & 1u, err, 2)) { ok = false; break; }
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t st = base + s * kPrStage;
+                    const uint32_t st = base + s * kSpStage;
 #pragma unroll
-                    for (int ks = 0; ks < kTcBK / 32; ++ks) {
-                        const uint64_t a_hi = umma_desc_sw128(st + ks * 32);
-                        const uint64_t a_lo = umma_desc_sw128(st + 16384 + ks * 32);
-                        const uint64_t b_cat = umma_desc_sw128(st + 32768 + ks * 32);
-                        const uint32_t acc = (kb | ks) ? 1u : 0u;
-                        umma_i8_pair(d0, a_hi, b_cat, idesc, acc);                      // [hi.hi | hi.lo], 64 columns each
-                        umma_i8_pair(d0 + 128, a_lo, b_cat, idesc, acc);                // [lo.hi | lo.lo]
-                    }
+                    for (int ks = 0; ks < kTcBK / 32; ++ks)
+                        umma_i8_pair(d0, umma_desc_sw128(st + ks * 32), umma_desc_sw128(st + 16384 + ks * 32), idesc, (kb | ks) ? 1u : 0u);
                     umma_commit_pair(bar_empty + 8 * s);
                 }
                 if (ok) umma_commit_pair(bar_tfull + 8 * as);
             }
         }
     } else {
-        // ===== epilogue (both CTAs): TMEM lane quarter = warp % 4, 32 of the 64 columns per warp =====
-        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        // ===== epilogue: TMEM lane quarter = warp % 4 (32 tile rows), 32 of the 128 tile columns per warp =====
+        const int quarter = warp & 3, cp = (warp - 2) >> 2;                    // cp 0, 1: columns 0..63, cp 2, 3: columns 64..127
+        const bool keeper = leader ? (cp < 2) : (cp >= 2);                     // this CTA finishes and stores these columns
+        const uint32_t peer = rank ^ 1u;
+        const uint32_t leader_tempty0 = mapa_rank(bar_tempty, 0);
+        const uint32_t peer_staging = mapa_rank(staging, peer), peer_recv = mapa_rank(bar_recv, peer), peer_sendok = mapa_rank(bar_sendok, peer);
+        const int row = quarter * 32 + lane;
+        const int scol0 = (cp & 1) * 32;                                       // first column of the warp inside a 64-column half
+        const unsigned int w_hi = leader ? 16384u : 128u, w_lo = leader ? 128u : 1u;   // this CTA's bracket: w_hi * [x.hi] + w_lo * [x.lo]
         int it = 0;
         for (long long tile = cid; tile < n_tiles; tile += ncl, ++it) {
             const int as = it & 1;
-            const int m0 = (int)(tile % m_pairs) * 256 + (int)rank * 128;
-            const int c0 = ((int)(tile / m_pairs) + col_tile0) * 64;
+            const int m0 = (int)(tile % m_tiles) * kTcBM;
+            const int c0 = ((int)(tile / m_tiles) + col_tile0) * kP8BN;
             if (!mbar_wait(bar_tfull + 8 * as, (uint32_t)(it >> 1) & 1u, err, 3)) break;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tl = tmem_base + (uint32_t)as * 256u + ((uint32_t)(quarter * 32) << 16);
-            int *orow = out + (long long)(m0 + quarter * 32 + lane) * ldo + c0;
+            bool ok = true;
+            if (!keeper) {
+                // the partner's staging buffer `as` has been read (tile it - 2)
+                if (it >= 2 && !mbar_wait_cluster(bar_sendok + 8 * as, (uint32_t)((it >> 1) - 1) & 1u, err, 5)) ok = false;
+            } else {
+                if (!mbar_wait_cluster(bar_recv + 8 * as, (uint32_t)(it >> 1) & 1u, err, 6)) ok = false;
+            }
+            if (!ok) break;
+            int *orow = out + (long long)(m0 + row) * ldo + c0 + (leader ? 0 : 64);
 #pragma unroll 1
-            for (int cc = half * 32; cc < half * 32 + 32; cc += 16) {
-                uint32_t hh[16], hl[16], lh[16], ll[16];
-                tmem_ld16(tl + cc, hh);
-                tmem_ld16(tl + 64 + cc, hl);
-                tmem_ld16(tl + 128 + cc, lh);
-                tmem_ld16(tl + 192 + cc, ll);
+            for (int cc = 0; cc < 32; cc += 16) {
+                uint32_t xh[16], xl[16];
+                tmem_ld16(tl + cp * 32 + cc, xh);
+                tmem_ld16(tl + kP8BN + cp * 32 + cc, xl);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                int v[16];
+                if (!keeper) {
+                    const uint32_t dst = peer_staging + (uint32_t)as * kSpStaging + ((uint32_t)(scol0 + cc) * 128u + (uint32_t)row) * 4u;
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    v[j] = (int)(16384LL * (int)hh[j] + 128LL * ((long long)(int)hl[j] + (int)lh[j]) + (int)ll[j]);
-                store_chunk16_paired(orow, ldo, cc, v, lane);
+                    for (int j = 0; j < 16; ++j) st_cluster_u32(dst + (uint32_t)j * 512u, w_hi * xh[j] + w_lo * xl[j]);
+                } else {
+                    const uint32_t src = staging + (uint32_t)as * kSpStaging + ((uint32_t)(scol0 + cc) * 128u + (uint32_t)row) * 4u;
+                    int v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        uint32_t other;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(other) : "r"(src + (uint32_t)j * 512u));
+                        v[j] = (int)(w_hi * xh[j] + w_lo * xl[j] + other);
+                    }
+                    store_chunk16_paired(orow, ldo, scol0 + cc, v, lane);
+                }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_rank(bar_tempty + 8 * as, 0));
+            if (lane == 0) {
+                if (!keeper) mbar_arrive_cluster(peer_recv + 8 * as);           // release.cluster: the stores above are visible to the partner
+                else mbar_arrive_cluster(peer_sendok + 8 * as);
+                mbar_arrive_cluster(leader_tempty0 + 8 * as);
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    cluster_sync_all();                                 // the leader's MMAs read this CTA's shared memory and write its TMEM
+    cluster_sync_all();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
@@ -1030,8 +1080,8 @@ inline int tc_gemm_i8_ptrs(coex_ctx *c, const int8_t *a_hi, const int8_t *a_lo, 
     // gemm_bn: 0 = persistent (128 x 64 tiles; 128 x 128 tiles for long rows), -64 / -128 = that persistent kernel forced,
     //          64 / 128 = one-tile-per-CTA kernel with that table-column tile
     const bool persistent = (c->gemm_bn <= 0);
-    const bool pair = (c->gemm_bn == -256) && (m_rows % 256 == 0) && (c->sm_count >= 2);      // CTA pairs, 256 x 64 tiles
-    const bool wide = persistent && !pair && (c->gemm_bn == -128 || c->gemm_bn == -129 || (c->gemm_bn == 0 && c->n_pad >= 1024));
+    const bool split = (c->gemm_bn == -257) && (c->sm_count >= 2);                            // digit-split CTA pairs, 128 x 128 tiles
+    const bool wide = persistent && (split || c->gemm_bn == -128 || c->gemm_bn == -129 || (c->gemm_bn == 0 && c->n_pad >= 1024));
     const bool clustered = wide && c->gemm_bn == -129 && (m_rows % 256 == 0) && c->sm_count >= 2;      // B multicast inside CTA pairs
     const int BN = persistent ? (wide ? kP8BN : kPsBN) : c->gemm_bn;
     if (t->bh != c->u_hi.p || t->bl != c->u_lo.p || t->b_rows != c->N_pad || t->n_pad != c->n_pad || t->bn != BN) {
@@ -1050,17 +1100,17 @@ inline int tc_gemm_i8_ptrs(coex_ctx *c, const int8_t *a_hi, const int8_t *a_lo, 
         COEX_CUDA(cudaFuncSetAttribute(gemm_i8_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::kSmem));
         COEX_CUDA(cudaFuncSetAttribute(gemm_i8_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPsSmem));
         COEX_CUDA(cudaFuncSetAttribute(gemm_i8_tc_persistent128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmem));
-        COEX_CUDA(cudaFuncSetAttribute(gemm_i8_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrSmem));
         COEX_CUDA(cudaFuncSetAttribute(gemm_i8_tc_cluster128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmem));
+        COEX_CUDA(cudaFuncSetAttribute(gemm_i8_tc_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpSmem));
         t->attr_set = true;
     }
-    if (pair) {
-        const int m_pairs = (int)(m_rows / 256);
-        const int col_tile0 = (int)std::min<long long>(c->gemm_col0 / 64, c->N_pad / 64 - 1);
-        const long long n_tiles = (long long)m_pairs * (c->N_pad / 64 - col_tile0);
+    if (split) {
+        const int m_tiles = (int)(m_rows / kTcBM);
+        const int col_tile0 = (int)std::min<long long>(c->gemm_col0 / kP8BN, c->N_pad / kP8BN - 1);
+        const long long n_tiles = (long long)m_tiles * (c->N_pad / kP8BN - col_tile0);
         const unsigned ctas = 2u * (unsigned)std::min<long long>(n_tiles, c->sm_count / 2);
-        gemm_i8_tc_pair_kernel<<<ctas, kPrThreads, kPrSmem, c->stream>>>(t->map_ah, t->map_al, t->map_bh, t->map_bl, out, ldo,
-                                                                        c->n_pad / kTcBK, m_pairs, n_tiles, col_tile0, t->d_err);
+        gemm_i8_tc_split_kernel<<<ctas, kP8Threads, kSpSmem, c->stream>>>(t->map_ah, t->map_al, t->map_bh, t->map_bl, out, ldo,
+                                                                         c->n_pad / kTcBK, m_tiles, n_tiles, col_tile0, t->d_err);
         COEX_CUDA(cudaGetLastError());
         return 0;
     }

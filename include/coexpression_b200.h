@@ -222,8 +222,9 @@ int coex_stage_ms(coex_ctx *ctx, int stage, double *ms, long long *launches);
 /* 0 = tcgen05/TMA tensor-core GEMM (default: persistent kernel; 128 x 64 tiles with double-buffered TMEM accumulators, or
  * 128 x 128 tiles with eight epilogue warps when a row has >= 1024 samples), 1 = SIMT dp4a GEMM (validation path),
  * 2 / 3 = the persistent tcgen05 kernel with 128 x 64 / 128 x 128 tiles explicitly,
- * 4 = CTA-pair kernel (tcgen05.mma.cta_group::2, 256 x 64 tiles, double-buffered accumulators), 5 = 128 x 128 tiles with the B operand
- * multicast inside clusters of two CTAs -- both exact, measured slower / equal, kept selectable,
+ * 5 = 128 x 128 tiles with the B planes multicast inside clusters of two CTAs, 6 = digit-split CTA pairs (tcgen05.mma.cta_group::2:
+ * the leader holds the hi digits, its peer the lo digits of the same tile; double-buffered accumulators) -- both exact, both as fast as
+ * the default and no faster: the contraction runs at the board's power cap,
  * 64 / 128 = one-tile-per-CTA tcgen05 kernel with that table-column tile */
 int coex_set_gemm_mode(coex_ctx *ctx, int mode);
 /* 0 = de-duplicated count kernels (default).  Spearman null: the bucket-table kernel of count_fine.cuh for tables of >= 65536 rows

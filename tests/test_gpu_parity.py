@@ -106,7 +106,7 @@ def test_tcgen05_gemm_matches_dp4a(N, n):
     t = synth.make_table(N, n, seed=N + n)
     with CoexContext() as ctx:
         ctx.set_expression(t.X); ctx.prepare()
-        for mode in ("tcgen05_bn128", "tcgen05_bn64", "tcgen05_persistent", "tcgen05_persistent128", "tcgen05_pair", "tcgen05_cluster128"):
+        for mode in ("tcgen05_bn128", "tcgen05_bn64", "tcgen05_persistent", "tcgen05_persistent128", "tcgen05_cluster128", "tcgen05_split"):
             ctx.set_gemm_mode(mode)
             bad, first = ctx.selftest_gemm(min(N, 512))
             assert bad == 0, (mode, first)
