@@ -1107,6 +1107,11 @@ def full_shape(env, args):
             a = gemm_flops / (per["corr_gemm"][0] * 1e-3) / 1e12
             roof["corr_gemm"] = {"bound": "tensor", "achieved": a, "peak": env.tc_sustained, "unit": "TFLOP/s", "frac": a / env.tc_sustained,
                                  "peak_kind": "sustained bf16 (kernel timed inside a long step)", "frac_of_burst": a / env.tc_peak,
+                                 "executed_int8_tops": 4.0 * a,
+                                 "executed_frac_of_twice_bf16_sustained": 4.0 * a / (2.0 * env.tc_sustained),
+                                 "executed_note": "the exact digit scheme executes 4 int8 products per algorithmic multiply-add; int8 runs at "
+                                                  "twice the bf16 rate, so `achieved` can reach 0.5 of the bf16 figure at most; the stage runs "
+                                                  "under sw_power_cap (see clocks)",
                                  "ms": per["corr_gemm"][0], "launches": per["corr_gemm"][1]}
         if per["count_score"][0] > 0:
             a = count_bytes / (per["count_score"][0] * 1e-3) / 1e9
