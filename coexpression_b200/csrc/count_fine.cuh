@@ -48,7 +48,7 @@ constexpr float kCfDelta = 7e-7f;        // see cf_delta
 __device__ __forceinline__ float cf_delta(float t) { return kCfDelta * fabsf(t); }
 
 // Bucket of a correlation: piecewise linear over the whole of [-1, 1] -- three quarters of the buckets for the centre |x| <= r1
-// (4 standard deviations of a null correlation), one eighth for each tail (co-expressed rows are NOT null-distributed: a table
+// (6 standard deviations of a null correlation), one eighth for each tail (co-expressed rows are NOT null-distributed: a table
 // with shared expression programmes has a fifth of its hit-vs-hit statistics out there, and a clamped uniform table would put
 // them, and their values, into two edge buckets).  Monotone non-decreasing in x: the clamp, both fused multiply-adds (k >= 0,
 // st > 0), the truncation and the final clamps all are, so  v32 <= t32  =>  bucket(v32) <= bucket(t32).
