@@ -311,8 +311,11 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
             // columns, rank every strip row once (count_dedup_kernel<2>) and let the queries look their indices up.
             const long long SCtot = c_sc_total;
             const double cost_items = (double)strip_item_begin[(size_t)n_strips] * (double)N;
-            const double cost_rank = (double)U * (double)((N + kRankTcap - 1) / kRankTcap) * (double)N + 2.0 * (double)SCtot;
-            if (c->count_mode == 0 && !pearson && bm_words_rank > 0 && cost_rank < 0.6 * cost_items) rank_mode = true;
+            // in streamed values: a rank item carries 8192 statistics (heavier set-up than a query item: x 1.5), a look-up of
+            // rank_score_kernel costs about half a streamed value.  Measured on 132 hit sets of ~5 400 regions on a 20 000-row table
+            // (config C5): query items 194 ms (1.4e10 values), rank mode 46 ms (1.2e9 values + 3.9e9 look-ups).
+            const double cost_rank = 1.5 * (double)U * (double)((N + kRankTcap - 1) / kRankTcap) * (double)N + 0.6 * (double)SCtot;
+            if (c->count_mode == 0 && !pearson && bm_words_rank > 0 && cost_rank < cost_items) rank_mode = true;
             if (rank_mode && bm_words_rank == 0) COEX_FAIL("rank mode needs the hit-column bitmap (table of at most 262144 rows)");
             if (tdbg) fprintf(stderr, "[coex host] count: %lld items, cost items %.3g vs rank %.3g -> %s\n", strip_item_begin[(size_t)n_strips],
                               cost_items, cost_rank, rank_mode ? "rank mode" : "query items");
