@@ -67,6 +67,7 @@ def parse():
     ap.add_argument("--cpu-sample-perms", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the full_shape / allpairs / strong objects")
+    ap.add_argument("--no-full-shape", action="store_true", help="skip the full_shape / allpairs objects only (development aid)")
     ap.add_argument("--full-rows", type=int, default=200000)
     ap.add_argument("--full-samples", type=int, default=1829)
     ap.add_argument("--full-perms", type=int, default=1000)
@@ -623,7 +624,7 @@ def run_ours(args):
     del X_dev, job
 
     # ---- the north-star target and C3 on the full FANTOM5 shape -----------------------------------------------
-    if not args.no_extras:
+    if not args.no_extras and not args.no_full_shape:
         try:
             full, allp = full_shape(env, args)
             if rank == 0:

@@ -309,7 +309,7 @@ static int spearman_dedup_path(coex_ctx *c, const coex_params *prm, int K, const
             COEX_CUDA(cudaStreamSynchronize(st));     // second (and last) read-back of the plan; the first GEMM is queued already
             // Regime switch: when the hit sets are so large that the queries of a row carry more statistics than the row has
             // columns, rank every strip row once (count_dedup_kernel<2>) and let the queries look their indices up.
-            const long long SCtot = c_sc_total;
+            const long long SCtot = c_sc_total / sh_world;      // (a rank of a shared job looks up the rows it owns)
             const double cost_items = (double)strip_item_begin[(size_t)n_strips] * (double)N;
             // in streamed values: a rank item carries 8192 statistics (heavier set-up than a query item: x 1.5), a look-up of
             // rank_score_kernel costs about half a streamed value.  Measured on 132 hit sets of ~5 400 regions on a 20 000-row table
