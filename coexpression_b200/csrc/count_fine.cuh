@@ -5,7 +5,8 @@
 // sorted null list), turned into the edge score.  What changed is the shape of the work (profiles/r02_count_experiments.md:
 // the sorted-statistics kernel is bound by its ~70 instructions per streamed value and by a set-up that sorts the statistics):
 //
-//   * ONE table in shared memory, nb (16384 / 32768) uniform buckets of [-R, R], one 32-bit word per bucket:
+//   * ONE table in shared memory, nb (16384 / 32768) buckets over the whole of [-1, 1] (piecewise linear, three quarters of them
+//     for the centre: cf_bucket), one 32-bit word per bucket:
 //         bits  0..17  number of streamed values of the current chunk of columns that fell into the bucket
 //         bits 18..30  head of the chain of statistics that live in the bucket (node + 1, 0 = none)
 //         bit  31      MULTI: more than one statistic, or a statistic of a NEIGHBOUR bucket that is closer than the float
@@ -15,8 +16,9 @@
 //   * #values below t_j = (values in the buckets below the bucket of t_j: a prefix over the table, per chunk of <= 258048
 //     columns so that 18 bits suffice) + (values of t_j's own bucket below t_j: counted by the values themselves -- 85 % of
 //     the values see an empty bucket, most of the others one statistic and a float compare that is certain).
-//   * Everything else -- MULTI buckets, a float compare that is not certain (|v - t| < 7e-7 |t|), exact ties -- goes through a
-//     queue that the whole CTA drains in lock step with the reference's double arithmetic; a statistic closer than the float
+//   * Everything else -- MULTI buckets, a float compare that is not certain (|v - t| < 7e-7 |t|), exact ties -- goes through
+//     per-warp queues (no barrier inside a chunk: a warp drains its own queue while the others stream) to a slow path with the
+//     reference's double arithmetic; statistics that are the same double are counted once (alias); a statistic closer than the float
 //     uncertainty to a bucket edge is ALSO chained into the neighbouring bucket, whose values then correct the prefix
 //     (+-1) when the doubles disagree with the bucket order.  Counts are EXACT, as before.
 //   * An item this kernel does not want (no room for the chains) is appended to a re-do list that count_dedup_kernel<0>
