@@ -1,0 +1,66 @@
+"""The float filter of the count kernels (coexpression_b200/csrc/count_fine.cuh: cf_delta, count_dedup.cuh: dd_delta), restated in
+numpy float32 arithmetic: a streamed null value and a statistic are the SAME five-rounding float expression of an exact integer sum
+and two norms, so each is within 5 * 2^-24 of the reference's double, and a float difference of at least 7e-7 |t| decides the order
+of the doubles.  (The GPU tests compare every resulting bisect index with the oracle; this pins the error budget itself.)"""
+import numpy as np
+
+
+def _float_value(S, sxu, sxc):
+    """fl(fl(int -> float) * fl(fl(0.5 / sx_u) * fl(0.5 / sx_c))), the kernels' expression (no fused operation in it)."""
+    iu = np.float32(0.5 / sxu)
+    w = (0.5 / sxc).astype(np.float32)
+    return S.astype(np.float32) * (iu * w)
+
+
+def _double_value(S, sxu, sxc):
+    """the reference on rank rows: xy / (sqrt(xx) * sqrt(yy)) with xy = S / 4 (coexpression_v2.c:113)"""
+    return (0.25 * S.astype(np.float64)) / (sxu * sxc)
+
+
+def _rows(rng, n, count):
+    # half-norms of rank rows: sqrt(sum u^2) / 2 with u = 2 rank - (n + 1); ties lower the sum
+    suu_max = n * (n * n - 1) / 3.0
+    suu = np.floor(rng.uniform(0.05, 1.0, size=count) * suu_max)
+    sx = np.sqrt(suu) / 2.0
+    return sx
+
+
+def test_float_value_is_within_five_roundings_of_the_double():
+    rng = np.random.default_rng(1)
+    for n in (24, 256, 1829):
+        sxc = _rows(rng, n, 200000)
+        sxu = float(_rows(rng, n, 1)[0])
+        bound = 4.0 * sxu * sxc                                   # |S| <= 4 sx_u sx_c (Cauchy-Schwarz)
+        S = np.rint(rng.uniform(-1, 1, size=sxc.size) * bound).astype(np.int64)
+        S = np.clip(S, -(2 ** 31) + 1, 2 ** 31 - 1)
+        v32 = _float_value(S, sxu, sxc).astype(np.float64)
+        v64 = _double_value(S, sxu, sxc)
+        nz = v64 != 0
+        rel = np.abs(v32[nz] - v64[nz]) / np.abs(v64[nz])
+        assert rel.max() <= 5 * 2.0 ** -24 * (1 + 1e-6), (n, rel.max())
+        assert np.all(v32[~nz] == 0)                               # an exact zero stays an exact zero
+
+
+def test_a_certain_float_compare_never_contradicts_the_doubles():
+    rng = np.random.default_rng(2)
+    delta = np.float32(7e-7)
+    for n in (256, 1829):
+        sxc = _rows(rng, n, 400000)
+        sxu = float(_rows(rng, n, 1)[0])
+        # values crowded around a few statistics: integer sums a handful of units apart
+        centre = np.rint(rng.uniform(-0.3, 0.3, size=sxc.size) * 4.0 * sxu * sxc)
+        S = (centre + rng.integers(-3, 4, size=sxc.size)).astype(np.int64)
+        v32 = _float_value(S, sxu, sxc)
+        v64 = _double_value(S, sxu, sxc)
+        order = np.argsort(v64, kind="stable")
+        a, b = order[:-1], order[1:]                               # neighbours in the exact order: the hardest pairs
+        for lo, hi in ((a, b), (rng.permutation(a), rng.permutation(b))):
+            t32, t64 = v32[hi], v64[hi]
+            d = v32[lo] - t32
+            certain = np.abs(d) >= delta * np.abs(t32)
+            below32 = d < 0
+            below64 = v64[lo] < t64
+            assert np.array_equal(below32[certain], below64[certain])
+        # and the filter is not vacuous: nearly every pair IS certain
+        d = v32[a] - v32[b]
+        assert np.mean(np.abs(d) >= delta * np.abs(v32[b])) > 0.5
