@@ -64,3 +64,36 @@ def test_a_certain_float_compare_never_contradicts_the_doubles():
         # and the filter is not vacuous: nearly every pair IS certain
         d = v32[a] - v32[b]
         assert np.mean(np.abs(d) >= delta * np.abs(v32[b])) > 0.5
+
+
+def test_digit_scheme_of_the_tensor_core_contraction_is_exact():
+    """The Spearman contraction in integers (coexpression_b200/csrc/prepare.cuh: rank_pack_kernel, gemm_tc.cuh): u = 2 rank - (n + 1)
+    = 128 hi + lo with lo in [-64, 63] and hi an int8 for every row length the library accepts (n <= 8192), the four int8 digit
+    products recombine to the exact dot product, S fits int32 up to n = 1860 (the guard in coex_network_batch), and the digit-split
+    CTA pair may form its two brackets modulo 2^32 (gemm_i8_tc_split_kernel)."""
+    from scipy.stats import rankdata
+    rng = np.random.default_rng(3)
+    for n in (2, 37, 256, 1829, 1860, 8192):
+        X = rng.gamma(0.5, 1.0, size=(6, n))
+        X[X < 0.4] = 0.0                                          # ties
+        X[0] = np.arange(n)                                       # an untied row: the largest possible |u| and sum of squares
+        X[1] = X[0]                                               # ... against itself: the largest possible S
+        X[2] = -X[0]
+        u = np.rint(2.0 * rankdata(X, axis=1) - (n + 1)).astype(np.int64)
+        hi = (u + 64) >> 7                                        # floor((u + 64) / 128): arithmetic shift, as in the kernel
+        lo = u - (hi << 7)
+        assert lo.min() >= -64 and lo.max() <= 63
+        assert hi.min() >= -128 and hi.max() <= 127
+        assert np.array_equal(128 * hi + lo, u)
+        HH, HL, LH, LL = hi @ hi.T, hi @ lo.T, lo @ hi.T, lo @ lo.T
+        S = u @ u.T
+        assert np.array_equal(16384 * HH + 128 * (HL + LH) + LL, S)
+        if n <= 1860:
+            assert np.abs(S).max() < 2 ** 31                      # (n = 1860: 2 144 865 540 < 2 147 483 648)
+            assert np.abs(np.stack([HH, HL, LH, LL])).max() < 2 ** 31          # the int32 accumulators of the MMAs
+            leader = (16384 * HH + 128 * HL) & 0xFFFFFFFF         # each bracket may wrap ...
+            peer = (128 * LH + LL) & 0xFFFFFFFF
+            both = (leader + peer) & 0xFFFFFFFF
+            assert np.array_equal(np.where(both >= 2 ** 31, both - 2 ** 32, both), S)   # ... their sum is S
+        else:
+            assert np.abs(S).max() >= 2 ** 31                     # why longer rows are refused for the int32 strip
