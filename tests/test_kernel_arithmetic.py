@@ -97,3 +97,56 @@ def test_digit_scheme_of_the_tensor_core_contraction_is_exact():
             assert np.array_equal(np.where(both >= 2 ** 31, both - 2 ** 32, both), S)   # ... their sum is S
         else:
             assert np.abs(S).max() >= 2 ** 31                     # why longer rows are refused for the int32 strip
+
+
+def _bucket_model(x32, nb, r1):
+    """A monotone piecewise-linear bucket map like cf_bucket (three quarters of the buckets for |x| <= r1); the scheme below is
+    exact for ANY non-decreasing map, which is all the kernel's float version has to be."""
+    x = x32.astype(np.float64)
+    st = 0.125 * nb / (1.0 - r1)
+    k = 0.375 * nb / r1 - st
+    b = np.floor(nb / 2 + st * x + k * np.clip(x, -r1, r1))
+    return np.clip(b, 0, nb - 1).astype(np.int64)
+
+
+def test_bucket_table_counting_scheme_is_exact():
+    """count_fine_kernel restated on the host: #values below a statistic = prefix of the bucket table + the certain float compares
+    and the exact double compares of its own bucket, corrected by the values of the neighbouring buckets that are closer than the
+    float uncertainty -- equal to counting with the reference's doubles, for tiny tables (everything shares buckets), heavy ties
+    (equal integer sums and norms) and statistics next to bucket edges."""
+    rng = np.random.default_rng(4)
+    delta = np.float32(7e-7)
+    for trial, (N, n, nb) in enumerate([(3000, 256, 64), (3000, 256, 1024), (5000, 1829, 4096), (4000, 37, 16)]):
+        sx = _rows(rng, n, N)
+        sx[rng.random(N) < 0.3] = sx[0]                            # many columns share a norm ...
+        sxu = float(sx[1])
+        S = np.rint(rng.normal(0, 0.08, size=N) * 4.0 * sxu * sx).astype(np.int64)
+        S[rng.random(N) < 0.3] = S[2]                              # ... and an integer sum: exact ties
+        S[rng.random(N) < 0.02] = 0
+        active = rng.random(N) > 0.01                              # zero-variance columns are counted in bulk elsewhere
+        v32 = _float_value(S, sxu, sx)
+        r64 = _double_value(S, sxu, sx)
+        r1 = min(0.5, 6.0 / np.sqrt(n))
+        bv = _bucket_model(v32, nb, r1)
+        table = np.bincount(bv[active], minlength=nb)
+        prefix = np.concatenate([[0], np.cumsum(table)[:-1]])
+        cols = rng.choice(np.flatnonzero(active), size=300, replace=False)
+        for j in cols:
+            t32, tj = v32[j], r64[j]
+            dl = delta * np.abs(t32)
+            hb = _bucket_model(np.float32([t32]), nb, r1)[0]
+            b0 = _bucket_model(np.float32([t32 - dl]), nb, r1)[0]
+            b1 = _bucket_model(np.float32([t32 + dl]), nb, r1)[0]
+            cnt = int(prefix[hb])
+            for b in range(b0, b1 + 1):
+                members = np.flatnonzero(active & (bv == b))
+                d = v32[members] - t32
+                certain = np.abs(d) >= dl
+                less_exact = r64[members] < tj
+                if b == hb:
+                    cnt += int(np.sum(certain & (d < 0))) + int(np.sum(~certain & less_exact))
+                elif b < hb:                                       # the prefix has counted them as below
+                    cnt -= int(np.sum(~certain & ~less_exact))
+                else:                                              # the prefix has not
+                    cnt += int(np.sum(~certain & less_exact))
+            assert cnt == int(np.sum(active & (r64 < tj))), (trial, int(j))
