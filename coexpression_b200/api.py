@@ -12,7 +12,7 @@ import numpy as np
 from . import _lib
 from ._lib import CoexParams, check
 
-STAGES = ["rank_pack", "rowstats", "gather", "corr_gemm", "count_score", "network", "stat_sort"]
+STAGES = ["rank_pack", "rowstats", "gather", "corr_gemm", "count_score", "network"]    # (stage 6 of the library, the split count pipeline, is gone)
 
 
 @dataclass
