@@ -18,6 +18,7 @@ import sys
 
 import numpy as np
 
+from . import hostio
 from .api import CoexContext, Options
 from .coexfunctions import (read_correlation_list, read_expression_file, read_snp_map, readfeaturecoordinates,
                             readsettings)
@@ -84,34 +85,70 @@ class Session:
             raise KeyError(missing[0])          # the reference fails in join_nearby (coexfunctions.py:285)
         return snp_map, rows
 
-    def run(self, mapfiles, store, full_dump=True, max_scores_bytes=8 << 30):
-        """Reduce the map files in chunks whose score matrices fit `max_scores_bytes`."""
+    def run(self, mapfiles, store, full_dump=True, max_scores_bytes=8 << 30, lean=False):
+        """Reduce the map files in chunks whose score matrices fit `max_scores_bytes` and write each file's result objects
+        (1-make-network.py:523-540).  full_dump: all eight objects; lean: the two P x P objects (`individualscores`,
+        `indjoined`) only for the real data, permutation number 0 -- 2-collate-results.py reads nothing but `indmeasure`
+        of a permuted set (:67-76) --, which also keeps the permuted sets' score blocks on the device."""
         os.makedirs(store, exist_ok=True)
         parsed = [self.hits_of(mf) for mf in mapfiles]
+        scored = [full_dump and (not lean or permutation_number(mf) == 0) for mf in mapfiles]
         written = []
         i = 0
         while i < len(mapfiles):
             j, used = i, 0
-            while j < len(mapfiles):
+            while j < len(mapfiles) and scored[j] == scored[i]:
                 need = 8 * len(parsed[j][1]) ** 2
                 if j > i and used + need > max_scores_bytes:
                     break
                 used += need
                 j += 1
-            res = self.ctx.network_batch([parsed[k][1] for k in range(i, j)], self.options, want_scores=full_dump)
+            res = self.ctx.network_batch([parsed[k][1] for k in range(i, j)], self.options, want_scores=scored[i])
             for k in range(i, j):
-                objs = perm_objects(res, k - i, self.table.names, with_scores=full_dump)
-                objs["snp_map"] = parsed[k][0]
-                for label, var in objs.items():
-                    path = result_path(store, mapfiles[k], label)
-                    with open(path, "w") as o:
-                        json.dump(var, o)
-                    written.append(path)
+                written += write_result_objects(store, mapfiles[k], res, k - i, self.table.names, parsed[k][0], scored[i])
             i = j
         return written
 
 
-def run_batch(working_files_dir, mapfiles=None, device=0, verbose=False, full_dump=True, cache=False):
+def permutation_number(mapfile):
+    """<feature label>.<k>.bed -> k (0 = the real data, 0-prepare-coex.py:357,598-613); -1 if the name has no number."""
+    try:
+        return int(os.path.split(mapfile)[-1].replace(".bed", "").split(".")[-1])
+    except ValueError:
+        return -1
+
+
+def write_result_objects(store, mapfile, res, k, names, snp_map, with_scores):
+    """The files `<stem>.<object>.<k>` of one permutation, same names, same text as the reference's json.dump calls.  The
+    six small objects go through json.dump; the two P x P ones are written straight from the score matrix by the host
+    library (hostio.write_json_matrix: the same bytes json.dump would write, without building 420 000 Python floats)."""
+    objs = perm_objects(res, k, names, with_scores=False)
+    if with_scores:
+        p = res.perm(k)
+        hit_names = [names[r] for r in p["hit_rows"]]
+        G = len(p["label"])
+        if G == 0 or len(hit_names) < 2:
+            objs["individualscores"] = {}
+            objs["indjoined"] = {}
+        else:
+            S = res.score_matrix(k)
+            w = np.asarray(p["winner"], dtype=np.int64)
+            objs["individualscores"] = (S, hit_names)
+            objs["indjoined"] = (S[np.ix_(w, w)], [hit_names[i] for i in p["label"]])
+    objs["snp_map"] = snp_map
+    written = []
+    for label, var in objs.items():
+        path = result_path(store, mapfile, label)
+        if isinstance(var, tuple):
+            hostio.write_json_matrix(path, var[0], var[1], skip_diag=True)
+        else:
+            with open(path, "w") as o:
+                json.dump(var, o)
+        written.append(path)
+    return written
+
+
+def run_batch(working_files_dir, mapfiles=None, device=0, verbose=False, full_dump=True, cache=False, lean=False):
     settings = readsettings(working_files_dir)
     perm_dir = os.path.join(working_files_dir, "permutation_store")
     if mapfiles is None:
@@ -119,7 +156,7 @@ def run_batch(working_files_dir, mapfiles=None, device=0, verbose=False, full_du
                           key=lambda p: int(p.split(".")[-2]))
     sess = Session(settings, device, verbose, cache)
     try:
-        return sess.run(mapfiles, os.path.join(working_files_dir, "perm_results_store"), full_dump)
+        return sess.run(mapfiles, os.path.join(working_files_dir, "perm_results_store"), full_dump, lean=lean)
     finally:
         sess.close()
 
@@ -132,6 +169,9 @@ def main(argv=None):
     ap.add_argument("-r", "--recordedges", action="store_true", default=False,
                     help="accepted; the reference crashes on it (Q11) so nothing is recorded")
     ap.add_argument("--all", action="store_true", help="B200 extension: reduce every map file of permutation_store/")
+    ap.add_argument("--lean", action="store_true",
+                    help="B200 extension: write `individualscores` / `indjoined` for the real data (permutation 0) only; "
+                         "2-collate-results.py reads nothing else of a permuted set than `indmeasure`")
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--cache", action="store_true", default=bool(os.environ.get("COEX_TABLE_CACHE")),
                     help="B200 extension: keep a binary cache of the parsed expression table next to the text file")
@@ -139,9 +179,9 @@ def main(argv=None):
     settings = readsettings(args.working_files_dir)
     verbose = bool(settings.get("verbose", False))
     if args.all:
-        run_batch(args.working_files_dir, None, args.device, verbose, cache=args.cache)
+        run_batch(args.working_files_dir, None, args.device, verbose, cache=args.cache, lean=args.lean)
     else:
-        run_batch(args.working_files_dir, [args.mapfile], args.device, verbose, cache=args.cache)
+        run_batch(args.working_files_dir, [args.mapfile], args.device, verbose, cache=args.cache, lean=args.lean)
     return 0
 
 

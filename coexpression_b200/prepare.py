@@ -78,6 +78,9 @@ def build_parser(coexappdir):
     parser.add_argument('--device', type=int, default=0, help='B200 extension: CUDA device')
     parser.add_argument('--rng_seed', type=int, default=None,
                         help='B200 extension: seed of the permutation RNG (the reference is unseeded, 0-prepare-coex.py:233-234)')
+    parser.add_argument('--lean_results', action="store_true", default=False,
+                        help='B200 extension: write the two P x P result objects (individualscores, indjoined) for the real data '
+                             'only; 2-collate-results.py reads nothing else of a permuted set than indmeasure')
     parser.add_argument('--cache', action="store_true", default=False,
                         help='B200 extension: binary cache of the parsed expression table')
     return parser
@@ -261,7 +264,7 @@ def main(argv=None, coexappdir=None):
                 print("Stopping after preparation")
             return 0
         from . import collate, make_network
-        make_network.run_batch(working_files_dir, None, a.device, verbose, cache=a.cache)
+        make_network.run_batch(working_files_dir, None, a.device, verbose, cache=a.cache, lean=a.lean_results)
         collate.collate(working_files_dir)
         return 0
 
@@ -310,7 +313,7 @@ def main(argv=None, coexappdir=None):
                                        a.window, with_loci=True)
         write_map_file(snps_mapped, rows0[0], loci0[0], 1, loci, snp_names, names, prom_addresses, "")
         numhits = len(rows0[0])
-        settingsdict = {k: v for k, v in vars(a).items() if k not in ("device", "rng_seed", "cache")}
+        settingsdict = {k: v for k, v in vars(a).items() if k not in ("device", "rng_seed", "cache", "lean_results")}
         settingsdict.update(version=version, genome_length=genome_length, snp_count=snp_count, numhits=numhits,
                             runcommand=runcommand, correlationfile=correlationfile, supplementary_label=supplementary_label)
         # (selectionthreshold goes in as given: the reference dumps vars(args), and 1-make-network.py:95-96 applies -m itself)
