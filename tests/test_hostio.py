@@ -129,3 +129,59 @@ def test_permutation_number_of_a_map_file():
     assert permutation_number("/a/b/f5ep300_100.0.bed") == 0
     assert permutation_number("permutation_store/f5ep.17.bed") == 17
     assert permutation_number("whatever.bed") == -1
+
+
+def test_session_run_chunks_and_lean_mode_on_a_stand_in_context(tmp_path):
+    """Session.run (make_network.py) without a GPU: the context is a stand-in that hands back made-up results.  Checked:
+    which calls ask for the score blocks, that a byte budget splits the map files, and which files a lean run writes."""
+    from coexpression_b200.make_network import Session
+
+    names = ["chr%d:%d..%d,+" % (i % 22 + 1, 700 * i, 700 * i + 250) for i in range(500)]
+
+    class Table:
+        pass
+
+    class Ctx:
+        def __init__(self):
+            self.calls = []
+
+        def network_batch(self, hit_lists, options, want_scores=True):
+            self.calls.append(([len(h) for h in hit_lists], want_scores))
+            res = _fake_batch(len(self.calls), [len(h) for h in hit_lists])
+            res.hit_rows = np.concatenate([np.asarray(h, dtype=np.int32) for h in hit_lists])
+            if not want_scores:
+                res.scores = None
+            return res
+
+    sess = Session.__new__(Session)
+    sess.table = Table()
+    sess.table.names = names
+    sess.options = None
+    sess.ctx = Ctx()
+    rng = np.random.default_rng(3)
+    hits = {("f5ep.%d.bed" % k): rng.permutation(500)[:P] for k, P in enumerate([30, 12, 20, 25])}
+    sess.hits_of = lambda mf: ({names[r]: {"p": -9999, "snps": "rs%d" % r} for r in hits[os.path.split(mf)[-1]]},
+                               hits[os.path.split(mf)[-1]].astype(np.int32))
+    mapfiles = [str(tmp_path / nm) for nm in hits]
+
+    full = sess.run(mapfiles, str(tmp_path / "full"))
+    assert sess.ctx.calls == [([30, 12, 20, 25], True)] and len(full) == 4 * 8
+
+    sess.ctx.calls.clear()
+    sess.run(mapfiles, str(tmp_path / "chunks"), max_scores_bytes=8 * (30 * 30 + 12 * 12))
+    assert sess.ctx.calls == [([30, 12], True), ([20, 25], True)]
+    sess.ctx.calls.clear()
+    sess.run(mapfiles, str(tmp_path / "one"), max_scores_bytes=1)                # a file larger than the budget still runs, alone
+    assert sess.ctx.calls == [([30], True), ([12], True), ([20], True), ([25], True)]
+
+    sess.ctx.calls.clear()
+    lean = sess.run(mapfiles, str(tmp_path / "lean"), lean=True)
+    assert sess.ctx.calls == [([30], True), ([12, 20, 25], False)]
+    got = sorted(os.listdir(tmp_path / "lean"))
+    assert len(lean) == len(got) == 8 + 3 * 6
+    assert [f for f in got if "individualscores" in f or "indjoined" in f] == ["f5ep.individualscores.0", "f5ep.indjoined.0"]
+    assert sum(".indmeasure." in f for f in got) == 4                      # what 2-collate pools (2-collate-results.py:67-76)
+
+    sess.ctx.calls.clear()
+    none = sess.run(mapfiles, str(tmp_path / "none"), full_dump=False)
+    assert sess.ctx.calls == [([30, 12, 20, 25], False)] and len(none) == 4 * 6
