@@ -140,3 +140,15 @@ def test_prepare_run_collate_end_to_end(tmp_path):
     assert any(f.endswith(".individual_scores") for f in os.listdir(wd)) or os.path.exists(os.path.join(wd, "allscores.txt"))
     # ---- resume: a second call finds the permutations and reruns only the batch -------------------------------------------
     assert prepare.main(argv + ["-po"]) == 0
+    # ---- --lean_results (B200 extension): the P x P objects of the real data only, same collation ----------------------------
+    assert prepare.main(argv + ["-o", "gwas_lean", "--lean_results"]) == 0
+    wl = str(tmp_path / "results") + "/gwas_lean"
+    store = sorted(os.listdir(os.path.join(wl, "perm_results_store")))
+    assert [f for f in store if "individualscores" in f or "indjoined" in f] == ["feat.individualscores.0", "feat.indjoined.0"]
+    assert len(store) == 8 + 4 * 6
+    for k in order:
+        a_, b_ = (open(os.path.join(d_, "perm_results_store", "feat.indmeasure.%d" % k)).read() for d_ in (wd, wl))
+        assert a_ == b_
+    for name in ("allscores.txt",) + tuple(f for f in os.listdir(wd) if f.endswith(".individual_scores")):
+        other = name.replace("gwas_complete_CIRCULAR_w3000_pj0.1_tab", "gwas_lean")
+        assert open(os.path.join(wd, name)).read() == open(os.path.join(wl, other)).read(), name
