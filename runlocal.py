@@ -13,6 +13,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("-wd", "--working_files_dir", type=str, default="null", help="filepath")
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--lean", action="store_true", help="B200 extension: the two P x P result objects for the real data only")
     a = ap.parse_args()
-    make_network.run_batch(a.working_files_dir, None, a.device)
+    make_network.run_batch(a.working_files_dir, None, a.device, lean=a.lean)
     collate.collate(a.working_files_dir)
