@@ -100,3 +100,39 @@ def test_options_map_to_reference_semantics():
     assert p.selectionthreshold == -math.log(0.01, 10)
     with pytest.raises(NameError):                                                   # quirk Q8
         Options(nsp=0.5).to_params(100)
+
+
+def test_headers_are_plain_c_and_the_libraries_link_from_c(tmp_path, lib):
+    """The boundary is a C ABI: both headers compile as C99 (no C++ in the signatures), and a C program linked against the
+    two libraries gets the ABI version, a loud failure of coex_create without a device, and the host writer's text."""
+    from coexpression_b200 import _lib, hostio
+    hostio.build()
+    inc = os.path.join(ROOT, "include")
+    for h in ("coexpression_b200.h", "coexpression_b200_io.h"):
+        subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(inc, h)])
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n'
+        '#include "coexpression_b200.h"\n#include "coexpression_b200_io.h"\n'
+        'int main(void) {\n'
+        '    double v[3] = {0.1, -0.0, 1e16};\n'
+        '    char out[128];\n'
+        '    long long n = coex_io_format_doubles(v, 3, out, sizeof out);\n'
+        '    if (n < 0) return 2;\n'
+        '    out[n] = 0;\n'
+        '    printf("abi=%d devices=%d\\n%s", coex_abi_version(), coex_device_count(), out);\n'
+        '    if (coex_device_count() == 0) {\n'
+        '        coex_ctx *c = NULL;\n'
+        '        if (coex_create(&c, 0) == 0) return 3;\n'
+        '        printf("create failed: %s\\n", strlen(coex_last_error()) ? "with a message" : "silently");\n'
+        '    }\n'
+        '    return 0;\n}\n')
+    csrc = os.path.dirname(_lib.SO_PATH)
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(exe), "-L", csrc,
+                           "-l:coexpression_v2.so", "-l:coex_hostio.so", "-Wl,-rpath," + csrc])
+    out = subprocess.check_output([str(exe)], text=True)
+    lines = out.split("\n")
+    assert lines[0].startswith("abi=2 devices=") and lines[1:4] == ["0.1", "-0.0", "1e+16"]
+    if not has_cuda():
+        assert lines[4] == "create failed: with a message"
