@@ -150,3 +150,32 @@ def test_bucket_table_counting_scheme_is_exact():
                 else:                                              # the prefix has not
                     cnt += int(np.sum(~certain & less_exact))
             assert cnt == int(np.sum(active & (r64 < tj))), (trial, int(j))
+
+
+def test_sorted_statistics_kernel_filter_rule():
+    """count_dedup.cuh (dd_delta): there the statistic is ONE rounding of its double (thr32 = (float) t) and the window is
+    relative to the streamed value: |v32 - v64| <= 5 * 2^-24 |v|, |t32 - t64| <= 2^-24 |t|; a float difference of at least
+    5e-7 |v32| (floor 1e-30) decides the order of the doubles, for both neighbours of v among the statistics."""
+    rng = np.random.default_rng(7)
+    for n in (256, 1829):
+        sxc = _rows(rng, n, 400000)
+        sxu = float(_rows(rng, n, 1)[0])
+        centre = np.rint(rng.uniform(-0.4, 0.4, size=sxc.size) * 4.0 * sxu * sxc)
+        S = (centre + rng.integers(-3, 4, size=sxc.size)).astype(np.int64)
+        v32 = _float_value(S, sxu, sxc)
+        v64 = _double_value(S, sxu, sxc)
+        t32_all = v64.astype(np.float32)                           # a statistic IS some column's double, rounded once
+        order = np.argsort(v64, kind="stable")
+        a, b = order[:-1], order[1:]
+        n_certain = 0
+        for val, stat in ((a, b), (b, a), (rng.permutation(a), rng.permutation(b))):
+            d = v32[val] - t32_all[stat]
+            window = np.maximum(np.float32(5e-7) * np.abs(v32[val]), np.float32(1e-30))
+            certain = np.abs(d) >= window
+            assert np.array_equal((d < 0)[certain], (v64[val] < v64[stat])[certain])
+            assert np.array_equal((d > 0)[certain], (v64[val] > v64[stat])[certain])
+            n_certain += int(certain.sum())
+        assert n_certain > 0.5 * 3 * a.size
+        # exact ties (same integer sum, same norm) are never "certain": they go to the double refinement
+        same = v32 - v64.astype(np.float32)
+        assert np.all(np.abs(same) < np.maximum(np.float32(5e-7) * np.abs(v32), np.float32(1e-30)) + (v32 == 0))
